@@ -1,0 +1,142 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the CLIP ViT-B image encoder forward.
+
+Functional torch-fp32 restatement of the reference's
+  VisualTransformer.forward      src/eoe/models/clip_official/clip/model.py:219-236
+  ResidualAttentionBlock.forward model.py:167-188 (nn.MultiheadAttention, no mask for vision)
+  LayerNorm (fp32, eps 1e-5)     model.py:153-159
+  QuickGELU                      model.py:162-164
+  CLIP.encode_image              model.py:336-337
+operating directly on the reference's state_dict keys (`visual.conv1.weight`,
+`visual.transformer.resblocks.{i}.attn.in_proj_weight`, ... model.py:395-402), so the same
+weights feed the oracle, the live reference and the CUDA encoder.
+
+Pinned against the live reference `CLIP(...).encode_image` in
+tests/test_oracle_vs_reference.py (where /root/reference is mounted) and against
+tests/golden/vit_*.npz (features produced by the live reference from seeded weights; generated
+by oracle/make_golden.py).
+
+`operand_dtype` (None = exact fp32 oracle) rounds every tensor that the CUDA path stores in
+16 bit (GEMM operands: patches, LN outputs, qkv, softmax probabilities, attention output, GELU
+output, weights) to that dtype while keeping fp32 accumulation / residual stream / LN / softmax
+statistics -- the "precision-matched" oracle used to separate kernel bugs from rounding.
+"""
+import math
+import torch
+import torch.nn.functional as F
+
+N_LAYERS = 12
+WIDTH = 768
+HEADS = 12
+EMBED = 512
+
+
+def synth_state_dict(patch: int, seed: int = 0, layers: int = N_LAYERS, width: int = WIDTH,
+                     embed: int = EMBED, res: int = 224, dtype=torch.float32):
+    """Seeded random visual-tower weights with the reference's key names and shapes.
+    Scales follow model.py:207-217,295-322 in spirit (std ~ width**-0.5) but are our own
+    generator so that the weights are identical on every box (no dependence on nn init order).
+    LayerNorm weights/biases are perturbed away from (1,0) so that they are exercised."""
+    g = torch.Generator().manual_seed(seed)
+    L = (res // patch) ** 2 + 1
+    sc = width ** -0.5
+
+    def rn(*shape, std=1.0):
+        return (torch.randn(*shape, generator=g) * std).to(dtype)
+
+    sd = {
+        "visual.conv1.weight": rn(width, 3, patch, patch, std=(3 * patch * patch) ** -0.5),
+        "visual.class_embedding": rn(width, std=sc),
+        "visual.positional_embedding": rn(L, width, std=sc),
+        "visual.ln_pre.weight": 1 + rn(width, std=0.1),
+        "visual.ln_pre.bias": rn(width, std=0.1),
+        "visual.ln_post.weight": 1 + rn(width, std=0.1),
+        "visual.ln_post.bias": rn(width, std=0.1),
+        "visual.proj": rn(width, embed, std=sc),
+    }
+    attn_std = sc
+    proj_std = sc * ((2 * layers) ** -0.5)
+    fc_std = (2 * width) ** -0.5
+    for i in range(layers):
+        p = f"visual.transformer.resblocks.{i}."
+        sd[p + "ln_1.weight"] = 1 + rn(width, std=0.1)
+        sd[p + "ln_1.bias"] = rn(width, std=0.1)
+        sd[p + "ln_2.weight"] = 1 + rn(width, std=0.1)
+        sd[p + "ln_2.bias"] = rn(width, std=0.1)
+        sd[p + "attn.in_proj_weight"] = rn(3 * width, width, std=attn_std)
+        sd[p + "attn.in_proj_bias"] = rn(3 * width, std=0.02)
+        sd[p + "attn.out_proj.weight"] = rn(width, width, std=proj_std)
+        sd[p + "attn.out_proj.bias"] = rn(width, std=0.02)
+        sd[p + "mlp.c_fc.weight"] = rn(4 * width, width, std=fc_std)
+        sd[p + "mlp.c_fc.bias"] = rn(4 * width, std=0.02)
+        sd[p + "mlp.c_proj.weight"] = rn(width, 4 * width, std=proj_std)
+        sd[p + "mlp.c_proj.bias"] = rn(width, std=0.02)
+    return sd
+
+
+def n_layers_of(sd):
+    return len({k.split(".")[3] for k in sd if k.startswith("visual.transformer.resblocks.")})
+
+
+def _r(t, dt):
+    return t if dt is None else t.to(dt).to(torch.float32)
+
+
+@torch.no_grad()
+def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens: bool = False):
+    """model.py:219-236. imgs [B,3,R,R] float32 (already CLIP-normalised) -> features [B, embed]."""
+    dt = operand_dtype
+    f32 = torch.float32
+    w = {k: v.to(f32) for k, v in sd.items()}
+    conv_w = w["visual.conv1.weight"]
+    width, _, P, _ = conv_w.shape
+    B = imgs.shape[0]
+    layers = n_layers_of(sd)
+    # model.py:220-222  conv1 (stride = kernel = P, no bias) -> [B, g*g, width]
+    x = F.conv2d(_r(imgs.to(f32), dt), _r(conv_w, dt), stride=P)
+    x = x.reshape(B, width, -1).permute(0, 2, 1)
+    # model.py:223-225  class token, positional embedding, ln_pre
+    cls = w["visual.class_embedding"].expand(B, 1, width)
+    x = torch.cat([cls, x], dim=1) + w["visual.positional_embedding"]
+    x = F.layer_norm(x, (width,), w["visual.ln_pre.weight"], w["visual.ln_pre.bias"], 1e-5)
+    L = x.shape[1]
+    dh = width // heads
+    for i in range(layers):
+        p = f"visual.transformer.resblocks.{i}."
+        # model.py:186  x = x + attn(ln_1(x))
+        h = F.layer_norm(x, (width,), w[p + "ln_1.weight"], w[p + "ln_1.bias"], 1e-5)
+        qkv = F.linear(_r(h, dt), _r(w[p + "attn.in_proj_weight"], dt), w[p + "attn.in_proj_bias"])
+        qkv = _r(qkv, dt)
+        q, k, v = qkv.split(width, dim=-1)
+        q = q.reshape(B, L, heads, dh).transpose(1, 2)
+        k = k.reshape(B, L, heads, dh).transpose(1, 2)
+        v = v.reshape(B, L, heads, dh).transpose(1, 2)
+        s = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(dh))
+        if dt is None:
+            pr = s.softmax(dim=-1)
+            o = pr @ v
+        else:
+            # CUDA path: un-normalised exp in 16 bit for the PV product, fp32 row sum, divide after
+            e = torch.exp(s - s.amax(dim=-1, keepdim=True))
+            o = (_r(e, dt) @ v) / e.sum(dim=-1, keepdim=True)
+        o = _r(o.transpose(1, 2).reshape(B, L, width), dt)
+        x = x + F.linear(o, _r(w[p + "attn.out_proj.weight"], dt), w[p + "attn.out_proj.bias"])
+        # model.py:187  x = x + mlp(ln_2(x)),  mlp = c_proj(QuickGELU(c_fc(.)))  (model.py:173-177)
+        h = F.layer_norm(x, (width,), w[p + "ln_2.weight"], w[p + "ln_2.bias"], 1e-5)
+        u = F.linear(_r(h, dt), _r(w[p + "mlp.c_fc.weight"], dt), w[p + "mlp.c_fc.bias"])
+        u = _r(u * torch.sigmoid(1.702 * u), dt)
+        x = x + F.linear(u, _r(w[p + "mlp.c_proj.weight"], dt), w[p + "mlp.c_proj.bias"])
+    if return_tokens:
+        return x
+    # model.py:231-234  ln_post on the class token, then @ proj
+    c = F.layer_norm(x[:, 0, :], (width,), w["visual.ln_post.weight"], w["visual.ln_post.bias"], 1e-5)
+    return c @ w["visual.proj"]
+
+
+def flops_per_image(patch: int, res: int = 224, layers: int = N_LAYERS, width: int = WIDTH,
+                    embed: int = EMBED) -> float:
+    """2*MAC over GEMMs + QK^T + PV: 8.818e9 (B/32), 35.127e9 (B/16)."""
+    g2 = (res // patch) ** 2
+    L = g2 + 1
+    pe = 2 * g2 * 3 * patch * patch * width
+    per_layer = 2 * L * width * (3 * width + width + 4 * width + 4 * width) + 2 * 2 * L * L * width
+    return float(pe + layers * per_layer + 2 * width * embed)

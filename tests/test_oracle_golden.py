@@ -1,0 +1,117 @@
+"""CPU: the oracle restatements reproduce the fixtures generated from the LIVE reference
+(oracle/make_golden.py).  Tolerances: heads 1e-5 relative (fp32 summation order only),
+AUC / curves bit-exact, ViT features 2e-5 absolute on O(1) values."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import auc as oauc
+from oracle import golden_inputs as gi
+from oracle import heads as oh
+from oracle import vit as ovit
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _close(a, b, rtol=1e-5, atol=1e-7):
+    np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
+
+
+def test_hsc_oracle_matches_reference_fixture(golden_dir):
+    g = _load(golden_dir, "heads.npz")
+    z, y = gi.hsc_inputs()
+    assert float(g["hsc_in_sum"]) == float(z.astype(np.float64).sum())
+    _close(oh.hsc_score(z), g["hsc_score"])
+    for nom in (0, 1):
+        _close(oh.hsc_loss(z, y, nom), g[f"hsc_loss_nom{nom}"])
+        _close(oh.hsc_grad(z, y, nom), g[f"hsc_grad_nom{nom}"], rtol=2e-5, atol=1e-9)
+
+
+def test_bce_oracle_matches_reference_fixture(golden_dir):
+    g = _load(golden_dir, "heads.npz")
+    x, y = gi.bce_inputs()
+    assert float(g["bce_in_sum"]) == float(x.astype(np.float64).sum())
+    _close(oh.bce_loss(x, y), g["bce_loss"])
+    _close(oh.bce_grad(x, y).reshape(-1, 1), g["bce_grad"], atol=1e-10)
+    for nom in (0, 1):
+        _close(oh.bce_score(x, nom), g[f"bce_score_nom{nom}"], atol=1e-12)
+
+
+@pytest.mark.parametrize("K", [2, 10, 30])
+def test_clip_oracle_matches_reference_fixture(golden_dir, K):
+    g = _load(golden_dir, "heads.npz")
+    z, y, c = gi.clip_inputs(K)
+    assert float(g[f"clip_in_sum_K{K}"]) == float(z.astype(np.float64).sum() + c.astype(np.float64).sum())
+    _close(oh.clip_score(z, c), g[f"clip_score_K{K}"], rtol=2e-4, atol=1e-30)
+    for mode in ("one_vs_rest", "leave_one_out"):
+        for nom in (0, 1):
+            loo = mode == "leave_one_out"
+            _close(oh.clip_oe_loss(z, y, c, nom, loo), g[f"clip_loss_K{K}_{mode}_nom{nom}"], rtol=2e-5)
+            _close(oh.clip_oe_grad(z, y, c, nom, loo), g[f"clip_grad_K{K}_{mode}_nom{nom}"], rtol=2e-3, atol=2e-7)
+
+
+@pytest.mark.parametrize("name", gi.AUC_CASES)
+def test_auc_oracle_bit_exact_vs_fixture(golden_dir, name):
+    g = _load(golden_dir, f"auc_{name}.npz")
+    y, s = gi.auc_inputs(name)
+    assert float(g["in_sum"]) == float(s.astype(np.float64).sum() + y.sum())
+    fpr, tpr, thr = oauc.roc_curve(y, s)
+    assert np.array_equal(fpr, g["fpr"]) and np.array_equal(tpr, g["tpr"])
+    assert np.array_equal(thr.astype(np.float64), g["thresholds"])
+    assert oauc.auc(fpr, tpr) == float(g["auc"])
+    assert oauc.average_precision(y, s) == float(g["ap"])
+    p, r, _ = oauc.precision_recall_curve(y, s)
+    assert np.array_equal(p, g["precision"]) and np.array_equal(r, g["recall"])
+
+
+@pytest.mark.parametrize("n", [2, 7, 8, 9, 127, 128, 129, 1000, 4099, 100003])
+@pytest.mark.parametrize("kind", ["f32", "f16", "coarse"])
+def test_auc_oracle_bit_exact_vs_sklearn(n, kind):
+    """sklearn (the reference's third-party AUC, ad_trainer.py:8) ships in the image on both boxes."""
+    from sklearn.metrics import auc, roc_curve
+    rng = np.random.default_rng(n * 7 + len(kind))
+    s = (1 - np.exp(-np.abs(rng.standard_normal(n)))).astype(np.float32)
+    if kind == "f16":
+        s = s.astype(np.float16)
+    elif kind == "coarse":
+        s = np.round(s * 20) / np.float32(20)
+    y = (rng.random(n) < 0.35).astype(np.int64)
+    y[0], y[-1] = 1, 0
+    fpr, tpr, thr = roc_curve(y, s)
+    f2, t2, th2 = oauc.roc_curve(y, s)
+    assert np.array_equal(fpr, f2) and np.array_equal(tpr, t2)
+    assert np.array_equal(thr.astype(np.float64), th2.astype(np.float64))
+    assert auc(fpr, tpr) == oauc.auc(f2, t2)
+
+
+def test_pairwise_sum_is_numpy_sum():
+    rng = np.random.default_rng(5)
+    for n in [0, 1, 5, 7, 8, 9, 15, 16, 127, 128, 129, 255, 256, 1000, 4097, 99999]:
+        a = rng.standard_normal(n) * 10.0 ** rng.integers(-8, 8, n)
+        assert oauc.pairwise_sum(a) == a.sum(), n
+
+
+def test_auc_nonfinite_raises():
+    with pytest.raises(ValueError):
+        oauc.roc_curve(np.array([0, 1, 1]), np.array([0.1, np.nan, 0.3], np.float32))
+
+
+@pytest.mark.parametrize("patch", [32, 16])
+def test_vit_oracle_matches_reference_fixture(golden_dir, patch):
+    g = _load(golden_dir, f"vit_b{patch}.npz")
+    sd = ovit.synth_state_dict(patch, seed=gi.VIT_WEIGHT_SEED)
+    imgs = gi.vit_images()
+    assert abs(float(g["img_sum"]) - float(imgs.double().sum())) < 1e-9
+    assert abs(float(g["w_sum"]) - float(sum(v.double().sum() for v in sd.values()))) < 1e-6
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    feats = ovit.encode_image(sd, imgs).numpy()
+    np.testing.assert_allclose(feats, g["features"], rtol=0, atol=2e-5)
+
+
+def test_vit_flop_counts():
+    assert abs(ovit.flops_per_image(32) / 1e9 - 8.818) < 1e-3
+    assert abs(ovit.flops_per_image(16) / 1e9 - 35.127) < 1e-3
