@@ -1,0 +1,639 @@
+// ROC-AUC (+ PRC / average precision) on the device, bit-exact with scikit-learn as the reference calls it
+// (src/eoe/training/ad_trainer.py:453-454, 517-521): roc_curve(labels, scores) -> auc(fpr, tpr).
+//
+// Pipeline (all on the caller's stream, no host sync; every size after the sort is a DEVICE value):
+//   1 keys      score -> descending-sortable u32 key (-0.0 == +0.0), label bit, 4x256 digit histogram, counts
+//   2 sort      4 LSD radix passes (8 bit), one kernel each: per-warp match_any ranking + decoupled look-back
+//   3 distinct  tie merge: flag last element of every run of equal keys, inclusive label count -> (tps, fps)
+//               at distinct thresholds, compacted with a single-pass (look-back) scan         [_binary_clf_curve]
+//   4 corners   drop_intermediate: keep points whose 2nd difference of fps or tps is non-zero [roc_curve]
+//   5 terms     fpr = fps/fps[-1], tpr = tps/tps[-1]; term_i = (fpr[i+1]-fpr[i]) * (tpr[i+1]+tpr[i]) / 2.0
+//   6 leaves    numpy pairwise-sum leaves (<=128 terms: 8 strided accumulators)              [np.trapezoid -> sum]
+//   7 tree      numpy pairwise-sum internal nodes (split at n/2 rounded down to a multiple of 8)
+// The float64 summation ORDER is what makes the result bit-identical to sklearn; see oracle/auc.py.
+#include "common.cuh"
+
+namespace eoe {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 keys per tile
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;   // 2048
+constexpr uint32_t kFlagAgg = 1u, kFlagIncl = 2u;
+constexpr int kSpinLimit = 1 << 20;                     // bounded spins: a protocol bug must not hang the GPU
+
+struct AucControl {            // zeroed by one memset per call
+    uint32_t hist[4 * 256];
+    uint32_t tickets[8];       // 0-3 sort passes, 4 distinct scan, 5 corner scan, 6 prc
+    uint32_t status;           // EOE_AUC_STATUS_* | 0x100 internal protocol error
+    uint32_t pad0[7];
+    unsigned long long n_valid, n_pos, n_distinct, n_kept;   // n_kept excludes the prepended origin
+    unsigned long long pad1[4];
+};
+
+struct AucLayout {
+    size_t control, sort_status, scan1_status, scan2_status, control_bytes;
+    size_t keys_a, keys_b, labs_a, labs_b, d_tps, d_fps, k_tps, k_fps, terms, nodes, total;
+    int sort_tiles, scan_tiles, max_depth;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int pairwise_depth(int64_t n) {   // depth of numpy's pairwise tree (right spine is the deepest)
+    int d = 0;
+    while (n > 128) { n -= (n / 2) & ~(int64_t)7; ++d; }
+    return d;
+}
+
+static AucLayout auc_layout(int64_t n) {
+    AucLayout L;
+    L.sort_tiles = (int)((n + kSortTile - 1) / kSortTile);
+    L.scan_tiles = (int)((n + kScanTile - 1) / kScanTile);
+    L.max_depth = pairwise_depth(n);
+    size_t o = 0;
+    L.control = o; o = align_up(o + sizeof(AucControl), 256);
+    L.sort_status = o; o = align_up(o + (size_t)4 * L.sort_tiles * 256 * 4, 256);
+    L.scan1_status = o; o = align_up(o + (size_t)L.scan_tiles * 8, 256);
+    L.scan2_status = o; o = align_up(o + (size_t)L.scan_tiles * 8, 256);
+    L.control_bytes = o;
+    L.keys_a = o; o = align_up(o + (size_t)n * 4, 256);
+    L.keys_b = o; o = align_up(o + (size_t)n * 4 + 64, 256);
+    L.labs_a = o; o = align_up(o + (size_t)n, 256);
+    L.labs_b = o; o = align_up(o + (size_t)n, 256);
+    L.d_tps = o; o = align_up(o + (size_t)(n + 2) * 4, 256);
+    L.d_fps = o; o = align_up(o + (size_t)(n + 2) * 4, 256);
+    L.k_tps = o; o = align_up(o + (size_t)(n + 2) * 4, 256);
+    L.k_fps = o; o = align_up(o + (size_t)(n + 2) * 4, 256);
+    L.terms = o; o = align_up(o + (size_t)(n + 2) * 8, 256);
+    L.nodes = o; o = align_up(o + ((size_t)2 << L.max_depth) * 8 + 64, 256);
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ uint32_t desc_key(float f) {
+    uint32_t b = __float_as_uint(f);
+    if (f == 0.0f) b = 0u;                                       // -0.0 and +0.0 are one threshold
+    const uint32_t asc = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+    return ~asc;                                                 // ascending key order == descending score
+}
+__device__ __forceinline__ float key_to_score(uint32_t key) {
+    const uint32_t asc = ~key;
+    const uint32_t b = (asc & 0x80000000u) ? (asc ^ 0x80000000u) : ~asc;
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------ 1 keys
+template <typename T>
+__global__ void __launch_bounds__(256)
+auc_keys_kernel(const T* __restrict__ scores, const int64_t* __restrict__ labels, int64_t n, int flags,
+                uint32_t* __restrict__ keys, uint8_t* __restrict__ labs, AucControl* c) {
+    __shared__ uint32_t s_hist[4 * 256];
+    __shared__ unsigned int s_cnt[3];
+    for (int i = threadIdx.x; i < 1024; i += 256) s_hist[i] = 0;
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned int nv = 0, np = 0, bad = 0;
+    const bool ignore_neg = flags & EOE_AUC_IGNORE_NEGATIVE_LABELS;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const float f = to_f32<T>(scores[i]);
+        const int64_t l = labels[i];
+        const bool valid = !(ignore_neg && l < 0);
+        uint32_t key = 0xffffffffu;      // dropped rows sort behind every finite score
+        uint8_t lb = 0;
+        if (valid) {
+            if (!isfinite(f)) bad = 1;
+            key = desc_key(f);
+            lb = (l == 1);
+            nv++;
+            np += lb;
+        }
+        keys[i] = key;
+        labs[i] = lb;
+        atomicAdd(&s_hist[key & 255], 1u);
+        atomicAdd(&s_hist[256 + ((key >> 8) & 255)], 1u);
+        atomicAdd(&s_hist[512 + ((key >> 16) & 255)], 1u);
+        atomicAdd(&s_hist[768 + (key >> 24)], 1u);
+    }
+    nv = __reduce_add_sync(kFullMask, nv);
+    np = __reduce_add_sync(kFullMask, np);
+    bad = __reduce_or_sync(kFullMask, bad);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_cnt[0], nv);
+        atomicAdd(&s_cnt[1], np);
+        atomicOr(&s_cnt[2], bad);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1024; i += 256)
+        if (s_hist[i]) atomicAdd(&c->hist[i], s_hist[i]);
+    if (threadIdx.x == 0) {
+        atomicAdd(&c->n_valid, (unsigned long long)s_cnt[0]);
+        atomicAdd(&c->n_pos, (unsigned long long)s_cnt[1]);
+        if (s_cnt[2]) atomicOr(&c->status, (uint32_t)EOE_AUC_STATUS_NONFINITE);
+    }
+}
+
+// block-wide exclusive scan of one u32 per thread (256 threads); returns exclusive prefix, total in *total
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_tmp /*[8]*/, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(kFullMask, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_tmp[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t t = s_tmp[w];
+        if (w < warp) woff += t;
+        tot += t;
+    }
+    __syncthreads();
+    if (total) *total = tot;
+    return woff + inc - v;
+}
+
+// ------------------------------------------------------------------------------------------ 2 sort pass
+__global__ void __launch_bounds__(kSortThreads)
+auc_sort_pass_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
+                     uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int64_t n, int pass,
+                     AucControl* c, uint32_t* status /* [tiles][256] for this pass */) {
+    __shared__ uint32_t s_warp_hist[8][256];
+    __shared__ uint32_t s_base[256];
+    __shared__ uint32_t s_tmp[8];
+    __shared__ unsigned int s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(&c->tickets[pass], 1u);
+    for (int i = tid; i < 8 * 256; i += kSortThreads) (&s_warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int shift = pass * 8;
+    const int64_t base = (int64_t)tile * kSortTile + warp * (32 * kSortItems);
+    uint32_t key[kSortItems];
+    uint8_t lab[kSortItems];
+    uint16_t rank[kSortItems];
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        const int64_t idx = base + j * 32 + lane;
+        const bool valid = idx < n;
+        key[j] = valid ? __ldg(keys_in + idx) : 0xffffffffu;
+        lab[j] = valid ? __ldg(labs_in + idx) : (uint8_t)0;
+    }
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        const bool valid = (base + j * 32 + lane) < n;
+        const uint32_t d = (key[j] >> shift) & 255u;
+        const uint32_t mask = __match_any_sync(kFullMask, valid ? d : (256u + lane));
+        const int leader = __ffs(mask) - 1;
+        uint32_t old = 0;
+        if (lane == leader && valid) {
+            old = s_warp_hist[warp][d];
+            s_warp_hist[warp][d] = old + __popc(mask);
+        }
+        old = __shfl_sync(kFullMask, old, leader);
+        rank[j] = (uint16_t)(old + __popc(mask & lt_mask));
+        __syncwarp();
+    }
+    __syncthreads();
+    // thread = digit: exclusive prefix over the 8 warps, tile count, global digit start, look-back
+    const uint32_t d = tid;
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t t = s_warp_hist[w][d];
+        s_warp_hist[w][d] = run;
+        run += t;
+    }
+    const uint32_t gstart = block_excl_scan_256(c->hist[pass * 256 + d], s_tmp, nullptr);
+    uint32_t* my = status + (size_t)tile * 256 + d;
+    uint32_t excl = 0;
+    if (tile == 0) {
+        st_volatile_u32(my, run | (kFlagIncl << 30));
+    } else {
+        st_volatile_u32(my, run | (kFlagAgg << 30));
+        int64_t t = (int64_t)tile - 1;
+        bool done = false;
+        int spins = 0;
+        while (!done) {
+            // batches of up to 8 independent (volatile) loads so that the walk is latency- not chain-bound
+            uint32_t v[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+                v[b] = (t - b >= 0) ? ld_volatile_u32(status + (size_t)(t - b) * 256 + d) : (kFlagIncl << 30);
+            int consumed = 0;
+            bool stall = false;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const uint32_t f = v[b] >> 30;
+                if (!done && !stall) {
+                    if (f == 0) {
+                        stall = true;                  // predecessor not published yet: re-poll from here
+                    } else {
+                        excl += v[b] & 0x3fffffffu;
+                        ++consumed;
+                        if (f == kFlagIncl) done = true;
+                    }
+                }
+            }
+            t -= consumed;
+            if (stall && ++spins > kSpinLimit) { atomicOr(&c->status, 0x100u); done = true; }
+        }
+        st_volatile_u32(my, (excl + run) | (kFlagIncl << 30));
+    }
+    s_base[d] = gstart + excl;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        if ((base + j * 32 + lane) < n) {
+            const uint32_t dj = (key[j] >> shift) & 255u;
+            const uint32_t pos = s_base[dj] + s_warp_hist[warp][dj] + rank[j];
+            keys_out[pos] = key[j];
+            labs_out[pos] = lab[j];
+        }
+    }
+}
+
+// Warp-parallel decoupled look-back over packed 64-bit tile states: [63:62] flag, [61:31] a, [30:0] b.
+// Called by warp 0 of the block; returns the exclusive prefix (a, b) and publishes the inclusive state.
+__device__ __forceinline__ void lookback_pair(unsigned long long* status, unsigned int tile, uint32_t agg_a,
+                                              uint32_t agg_b, uint32_t& excl_a, uint32_t& excl_b, AucControl* c) {
+    const int lane = threadIdx.x & 31;
+    auto pack = [](uint32_t f, uint32_t a, uint32_t b) {
+        return ((unsigned long long)f << 62) | ((unsigned long long)a << 31) | (unsigned long long)b;
+    };
+    excl_a = 0; excl_b = 0;
+    if (tile == 0) {
+        if (lane == 0) st_volatile_u64(status, pack(kFlagIncl, agg_a, agg_b));
+        return;
+    }
+    if (lane == 0) st_volatile_u64(status + tile, pack(kFlagAgg, agg_a, agg_b));
+    int64_t t = (int64_t)tile - 1;      // lane 0 looks at t, lane 1 at t-1, ...
+    int spins = 0;
+    while (true) {
+        const int64_t mine = t - lane;
+        unsigned long long v = (mine >= 0) ? ld_volatile_u64(status + mine) : pack(kFlagIncl, 0, 0);
+        const uint32_t f = (uint32_t)(v >> 62);
+        const unsigned pending = __ballot_sync(kFullMask, f == 0);
+        const unsigned incl = __ballot_sync(kFullMask, f == kFlagIncl);
+        // usable window: lanes before the first pending one, cut after the first inclusive one
+        int limit = pending ? (__ffs(pending) - 1) : 32;
+        const int first_incl = incl ? (__ffs(incl) - 1) : 32;
+        const bool finish = first_incl < limit;
+        if (finish) limit = first_incl + 1;
+        uint32_t a = (lane < limit) ? (uint32_t)((v >> 31) & 0x7fffffffu) : 0u;
+        uint32_t b = (lane < limit) ? (uint32_t)(v & 0x7fffffffu) : 0u;
+        excl_a += __reduce_add_sync(kFullMask, a);
+        excl_b += __reduce_add_sync(kFullMask, b);
+        if (finish) break;
+        t -= limit;
+        if (limit == 0 && ++spins > kSpinLimit) { if (lane == 0) atomicOr(&c->status, 0x100u); break; }
+    }
+    if (lane == 0) st_volatile_u64(status + tile, pack(kFlagIncl, excl_a + agg_a, excl_b + agg_b));
+}
+
+// ------------------------------------------------------------------------------------------ 3 distinct
+// sklearn _binary_clf_curve: distinct_value_indices = where(diff(sorted_scores)); threshold_idxs = r_[., n-1];
+// tps = cumsum(y)[idxs]; fps = 1 + idxs - tps.
+__global__ void __launch_bounds__(kScanThreads)
+auc_distinct_kernel(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ labs, AucControl* c,
+                    unsigned long long* status, uint32_t* __restrict__ d_tps, uint32_t* __restrict__ d_fps,
+                    uint32_t* __restrict__ d_key) {
+    __shared__ uint32_t s_tmp[8];
+    __shared__ uint32_t s_excl[2];
+    __shared__ unsigned int s_tile;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(&c->tickets[4], 1u);
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int64_t nv = (int64_t)c->n_valid;
+    const int64_t base = (int64_t)tile * kScanTile + tid * kScanItems;
+    if ((int64_t)tile * kScanTile >= nv) return;          // whole tile beyond the kept rows (uniform per block)
+    uint32_t k[kScanItems + 1];
+    uint32_t f[kScanItems], l[kScanItems];
+#pragma unroll
+    for (int j = 0; j <= kScanItems; ++j) k[j] = (base + j < nv) ? keys[base + j] : 0u;
+    uint32_t fc = 0, lc = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        const int64_t i = base + j;
+        const bool in = i < nv;
+        l[j] = in ? (uint32_t)labs[i] : 0u;
+        f[j] = in && (i == nv - 1 || k[j] != k[j + 1]);
+        fc += f[j];
+        lc += l[j];
+    }
+    uint32_t tot_f, tot_l;
+    uint32_t ex_f = block_excl_scan_256(fc, s_tmp, &tot_f);
+    uint32_t ex_l = block_excl_scan_256(lc, s_tmp, &tot_l);
+    if (tid < 32) {
+        uint32_t ea, eb;
+        lookback_pair(status, tile, tot_f, tot_l, ea, eb, c);
+        if (tid == 0) { s_excl[0] = ea; s_excl[1] = eb; }
+    }
+    __syncthreads();
+    uint32_t slot = s_excl[0] + ex_f;
+    uint32_t tps = s_excl[1] + ex_l;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        tps += l[j];
+        if (f[j]) {
+            const uint32_t i = (uint32_t)(base + j);
+            d_tps[slot] = tps;
+            d_fps[slot] = 1u + i - tps;
+            d_key[slot] = k[j];
+            ++slot;
+        }
+    }
+    if (base <= nv - 1 && nv - 1 < base + kScanItems) c->n_distinct = slot;   // the thread owning the last row
+}
+
+// ------------------------------------------------------------------------------------------ 4 corners
+// roc_curve(drop_intermediate=True): optimal_idxs = where(r_[True, logical_or(diff(fps,2), diff(tps,2)), True])
+// (only if len(fps) > 2); then tps = r_[0, tps], fps = r_[0, fps], thresholds = r_[inf, thresholds].
+__global__ void __launch_bounds__(kScanThreads)
+auc_corner_kernel(const uint32_t* __restrict__ d_tps, const uint32_t* __restrict__ d_fps,
+                  const uint32_t* __restrict__ d_key, AucControl* c, unsigned long long* status,
+                  uint32_t* __restrict__ k_tps, uint32_t* __restrict__ k_fps, float* __restrict__ thr_out) {
+    __shared__ uint32_t s_tmp[8];
+    __shared__ uint32_t s_excl;
+    __shared__ unsigned int s_tile;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(&c->tickets[5], 1u);
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int64_t m = (int64_t)c->n_distinct;
+    if ((int64_t)tile * kScanTile >= m) return;
+    const int64_t base = (int64_t)tile * kScanTile + tid * kScanItems;
+    if (tile == 0 && tid == 0) {
+        k_tps[0] = 0; k_fps[0] = 0;
+        if (thr_out) thr_out[0] = INFINITY;
+    }
+    int64_t tp[kScanItems + 2], fp[kScanItems + 2];
+#pragma unroll
+    for (int j = 0; j < kScanItems + 2; ++j) {
+        const int64_t i = base + j - 1;
+        const bool in = (i >= 0 && i < m);
+        tp[j] = in ? (int64_t)d_tps[i] : 0;
+        fp[j] = in ? (int64_t)d_fps[i] : 0;
+    }
+    uint32_t keep[kScanItems], kc = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        const int64_t i = base + j;
+        bool kp = false;
+        if (i < m) {
+            kp = (m <= 2) || i == 0 || i == m - 1 || (fp[j] - 2 * fp[j + 1] + fp[j + 2] != 0) ||
+                 (tp[j] - 2 * tp[j + 1] + tp[j + 2] != 0);
+        }
+        keep[j] = kp;
+        kc += kp;
+    }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan_256(kc, s_tmp, &tot);
+    if (tid < 32) {
+        uint32_t ea, eb;
+        lookback_pair(status, tile, tot, 0u, ea, eb, c);
+        if (tid == 0) s_excl = ea;
+    }
+    __syncthreads();
+    uint32_t slot = s_excl + ex + 1;           // +1: the prepended origin
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        if (keep[j]) {
+            k_tps[slot] = (uint32_t)tp[j + 1];
+            k_fps[slot] = (uint32_t)fp[j + 1];
+            if (thr_out) thr_out[slot] = key_to_score(d_key[base + j]);
+            ++slot;
+        }
+    }
+    if (base <= m - 1 && m - 1 < base + kScanItems) c->n_kept = slot - 1;
+}
+
+// ------------------------------------------------------------------------------------------ 5 terms
+// fpr = fps / fps[-1]; tpr = tps / tps[-1]; np.trapezoid integrand d * (y[1:] + y[:-1]) / 2.0 (fp64, this order)
+__global__ void __launch_bounds__(256)
+auc_terms_kernel(const uint32_t* __restrict__ k_tps, const uint32_t* __restrict__ k_fps, AucControl* c,
+                 double* __restrict__ terms, double* __restrict__ fpr_out, double* __restrict__ tpr_out) {
+    const int64_t P = (int64_t)c->n_kept + 1;        // points incl. origin
+    const double ftot = (double)(c->n_valid - c->n_pos);
+    const double ttot = (double)c->n_pos;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < P; i += (int64_t)gridDim.x * 256) {
+        const double f0 = __ddiv_rn((double)k_fps[i], ftot), t0 = __ddiv_rn((double)k_tps[i], ttot);
+        if (fpr_out) { fpr_out[i] = f0; tpr_out[i] = t0; }
+        if (i + 1 < P) {
+            const double f1 = __ddiv_rn((double)k_fps[i + 1], ftot), t1 = __ddiv_rn((double)k_tps[i + 1], ttot);
+            terms[i] = __ddiv_rn(__dmul_rn(__dsub_rn(f1, f0), __dadd_rn(t1, t0)), 2.0);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 6/7 pairwise sum
+__device__ __forceinline__ int dev_pairwise_depth(int64_t n) {
+    int d = 0;
+    while (n > 128) { n -= (n >> 1) & ~(int64_t)7; ++d; }
+    return d;
+}
+
+// One group of 8 lanes per leaf slot of the virtual complete tree of depth D; lane j owns accumulator r[j].
+__global__ void __launch_bounds__(256)
+pairwise_leaves_kernel(const double* __restrict__ a, const unsigned long long* n_ptr, int64_t n_minus,
+                       double* __restrict__ nodes) {
+    const int64_t T = (int64_t)(*n_ptr) - n_minus;   // number of terms
+    if (T <= 0) { if (blockIdx.x == 0 && threadIdx.x == 0) nodes[1] = 0.0; return; }
+    const int D = dev_pairwise_depth(T);
+    const int64_t g = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
+    const int j = threadIdx.x & 7;
+    if (g >= ((int64_t)1 << D)) return;
+    int64_t off = 0, len = T;
+    int lvl = 0;
+    while (len > 128) {
+        const int64_t h = (len >> 1) & ~(int64_t)7;
+        if ((g >> (D - 1 - lvl)) & 1) { off += h; len -= h; } else len = h;
+        ++lvl;
+    }
+    const int rem = D - lvl;
+    if (g & (((int64_t)1 << rem) - 1)) return;        // this leaf is represented by its left-most slot only
+    const int64_t heap = ((int64_t)1 << lvl) + (g >> rem);
+    const double* p = a + off;
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);   // the 8 lanes of this group (all take the same path)
+    double res;
+    if (len < 8) {
+        if (j != 0) return;
+        res = 0.0;
+        for (int64_t i = 0; i < len; ++i) res = __dadd_rn(res, p[i]);
+        nodes[heap] = res;
+        return;
+    }
+    double r = p[j];
+    const int64_t body = len - (len & 7);
+    for (int64_t i = 8; i < body; i += 8) r = __dadd_rn(r, p[i + j]);
+    // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+    double o = __shfl_xor_sync(gmask, r, 1);
+    r = (j & 1) ? __dadd_rn(o, r) : __dadd_rn(r, o);
+    o = __shfl_xor_sync(gmask, r, 2);
+    r = (j & 2) ? __dadd_rn(o, r) : __dadd_rn(r, o);
+    o = __shfl_xor_sync(gmask, r, 4);
+    r = (j & 4) ? __dadd_rn(o, r) : __dadd_rn(r, o);
+    if (j == 0) {
+        res = r;
+        for (int64_t i = body; i < len; ++i) res = __dadd_rn(res, p[i]);
+        nodes[heap] = res;
+    }
+}
+
+// Internal nodes bottom-up (single block); finally writes the result (NaN if the curve is undefined).
+__global__ void __launch_bounds__(1024)
+pairwise_tree_kernel(const unsigned long long* n_ptr, int64_t n_minus, double* __restrict__ nodes, AucControl* c,
+                     double* __restrict__ out, int negate_clip) {
+    const int64_t T = (int64_t)(*n_ptr) - n_minus;
+    const int D = (T > 0) ? dev_pairwise_depth(T) : 0;
+    for (int lvl = D - 1; lvl >= 0; --lvl) {
+        for (int64_t p = threadIdx.x; p < ((int64_t)1 << lvl); p += 1024) {
+            int64_t len = T;
+            bool exists = true;
+            for (int s = 0; s < lvl; ++s) {
+                if (len <= 128) { exists = false; break; }
+                const int64_t h = (len >> 1) & ~(int64_t)7;
+                len = ((p >> (lvl - 1 - s)) & 1) ? (len - h) : h;
+            }
+            if (exists && len > 128) {
+                const int64_t heap = ((int64_t)1 << lvl) + p;
+                nodes[heap] = __dadd_rn(nodes[2 * heap], nodes[2 * heap + 1]);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double v = nodes[1];
+        if (negate_clip) v = fmax(0.0, -v);
+        const bool single = (c->n_pos == 0) || (c->n_pos == c->n_valid);
+        if (single) atomicOr(&c->status, (uint32_t)EOE_AUC_STATUS_SINGLE_CLASS);
+        if (single || (c->status & ~(uint32_t)EOE_AUC_STATUS_SINGLE_CLASS)) v = __longlong_as_double(0x7ff8000000000000LL);
+        *out = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ PRC / AP
+// precision_recall_curve (reversed, (1,0) appended) and average_precision_score = max(0, -sum(diff(recall)*precision[:-1])).
+// With m distinct thresholds j = 0..m-1 (descending score): reversed index i = m-1-j.
+__global__ void __launch_bounds__(256)
+auc_prc_terms_kernel(const uint32_t* __restrict__ d_tps, const uint32_t* __restrict__ d_fps, AucControl* c,
+                     double* __restrict__ terms, double* __restrict__ prec_out, double* __restrict__ rec_out) {
+    const int64_t m = (int64_t)c->n_distinct;
+    const double ttot = (double)c->n_pos;
+    auto prec = [&](int64_t j) {
+        const double tp = (double)d_tps[j], ps = __dadd_rn(tp, (double)d_fps[j]);
+        return ps != 0.0 ? __ddiv_rn(tp, ps) : 0.0;
+    };
+    auto rec = [&](int64_t j) { return ttot == 0.0 ? 1.0 : __ddiv_rn((double)d_tps[j], ttot); };
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < m; i += (int64_t)gridDim.x * 256) {
+        const int64_t j = m - 1 - i;
+        const double p = prec(j), r = rec(j);
+        const double r_next = (i + 1 < m) ? rec(j - 1) : 0.0;
+        terms[i] = __dmul_rn(__dsub_rn(r_next, r), p);
+        if (prec_out) { prec_out[i] = p; rec_out[i] = r; }
+    }
+    if (prec_out && blockIdx.x == 0 && threadIdx.x == 0) { prec_out[m] = 1.0; rec_out[m] = 0.0; }
+}
+
+__global__ void auc_info_kernel(const AucControl* c, int64_t* info) {
+    info[0] = (int64_t)c->n_valid; info[1] = (int64_t)c->n_pos; info[2] = (int64_t)c->n_distinct;
+    info[3] = (int64_t)c->n_kept + 1; info[4] = (int64_t)c->status; info[5] = info[6] = info[7] = 0;
+}
+
+template <typename T>
+static int auc_run(const void* scores, const int64_t* labels, int64_t n, int flags, char* ws, const AucLayout& L,
+                   double* auc_out, int64_t* info_out, double* fpr_out, double* tpr_out, float* thr_out,
+                   double* prec_out, double* rec_out, cudaStream_t st) {
+    AucControl* c = (AucControl*)(ws + L.control);
+    uint32_t* keys_a = (uint32_t*)(ws + L.keys_a);
+    uint32_t* keys_b = (uint32_t*)(ws + L.keys_b);
+    uint8_t* labs_a = (uint8_t*)(ws + L.labs_a);
+    uint8_t* labs_b = (uint8_t*)(ws + L.labs_b);
+    uint32_t* sort_status = (uint32_t*)(ws + L.sort_status);
+    cudaError_t e = cudaMemsetAsync(ws, 0, L.control_bytes, st);
+    if (e != cudaSuccess) { set_cuda_error(e, "auc memset"); return EOE_ERR_CUDA; }
+    int kgrid = (int)((n + 256 * 8 - 1) / (256 * 8));
+    if (kgrid > kNumSMs * 8) kgrid = kNumSMs * 8;
+    auc_keys_kernel<T><<<kgrid, 256, 0, st>>>((const T*)scores, labels, n, flags, keys_a, labs_a, c);
+    for (int pass = 0; pass < 4; ++pass) {
+        const bool fwd = (pass & 1) == 0;
+        auc_sort_pass_kernel<<<L.sort_tiles, kSortThreads, 0, st>>>(
+            fwd ? keys_a : keys_b, fwd ? labs_a : labs_b, fwd ? keys_b : keys_a, fwd ? labs_b : labs_a, n, pass, c,
+            sort_status + (size_t)pass * L.sort_tiles * 256);
+    }
+    // sorted data is back in (keys_a, labs_a); keys_b is free and receives the distinct thresholds
+    uint32_t* d_tps = (uint32_t*)(ws + L.d_tps);
+    uint32_t* d_fps = (uint32_t*)(ws + L.d_fps);
+    uint32_t* k_tps = (uint32_t*)(ws + L.k_tps);
+    uint32_t* k_fps = (uint32_t*)(ws + L.k_fps);
+    double* terms = (double*)(ws + L.terms);
+    double* nodes = (double*)(ws + L.nodes);
+    auc_distinct_kernel<<<L.scan_tiles, kScanThreads, 0, st>>>(keys_a, labs_a, c, (unsigned long long*)(ws + L.scan1_status),
+                                                               d_tps, d_fps, keys_b);
+    auc_corner_kernel<<<L.scan_tiles, kScanThreads, 0, st>>>(d_tps, d_fps, keys_b, c,
+                                                             (unsigned long long*)(ws + L.scan2_status), k_tps, k_fps, thr_out);
+    int tgrid = (int)((n + 1 + 255) / 256);
+    if (tgrid > kNumSMs * 4) tgrid = kNumSMs * 4;
+    auc_terms_kernel<<<tgrid, 256, 0, st>>>(k_tps, k_fps, c, terms, fpr_out, tpr_out);
+    const int lgrid = (int)((((int64_t)8 << L.max_depth) + 255) / 256);
+    pairwise_leaves_kernel<<<lgrid, 256, 0, st>>>(terms, &c->n_kept, 0, nodes);
+    pairwise_tree_kernel<<<1, 1024, 0, st>>>(&c->n_kept, 0, nodes, c, auc_out, 0);
+    if (flags & EOE_AUC_WITH_PRC) {
+        auc_prc_terms_kernel<<<tgrid, 256, 0, st>>>(d_tps, d_fps, c, terms, prec_out, rec_out);
+        pairwise_leaves_kernel<<<lgrid, 256, 0, st>>>(terms, &c->n_distinct, 0, nodes);
+        pairwise_tree_kernel<<<1, 1024, 0, st>>>(&c->n_distinct, 0, nodes, c, auc_out + 1, 1);
+    }
+    if (info_out) auc_info_kernel<<<1, 1, 0, st>>>(c, info_out);
+    return check_launch("auc pipeline");
+}
+
+}  // namespace eoe
+
+using namespace eoe;
+
+extern "C" size_t eoe_auc_workspace_bytes(int64_t n) {
+    if (n <= 0) return 0;
+    return auc_layout(n).total;
+}
+
+extern "C" int eoe_auc(const void* scores, int score_dtype, const int64_t* labels, int64_t n, int flags,
+                       void* workspace, size_t workspace_bytes, double* auc_out, int64_t* info_out,
+                       double* fpr_out, double* tpr_out, float* thr_out, double* prec_out, double* rec_out,
+                       void* stream) {
+    if (!scores || !labels || !auc_out || n <= 0) return EOE_ERR_ARG;
+    if (n >= ((int64_t)1 << 30)) return EOE_ERR_SHAPE;
+    if ((fpr_out == nullptr) != (tpr_out == nullptr)) return EOE_ERR_ARG;
+    if ((prec_out == nullptr) != (rec_out == nullptr)) return EOE_ERR_ARG;
+    const AucLayout L = auc_layout(n);
+    if (!workspace || workspace_bytes < L.total) return EOE_ERR_WORKSPACE;
+    if ((uintptr_t)workspace % 256 != 0) return EOE_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (score_dtype) {
+        case EOE_F32: return auc_run<float>(scores, labels, n, flags, (char*)workspace, L, auc_out, info_out, fpr_out, tpr_out, thr_out, prec_out, rec_out, st);
+        case EOE_F16: return auc_run<__half>(scores, labels, n, flags, (char*)workspace, L, auc_out, info_out, fpr_out, tpr_out, thr_out, prec_out, rec_out, st);
+        case EOE_BF16: return auc_run<__nv_bfloat16>(scores, labels, n, flags, (char*)workspace, L, auc_out, info_out, fpr_out, tpr_out, thr_out, prec_out, rec_out, st);
+        default: return EOE_ERR_DTYPE;
+    }
+}

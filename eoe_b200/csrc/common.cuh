@@ -1,0 +1,133 @@
+// Shared device/host helpers for the eoe_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/eoe_b200.h"
+
+namespace eoe {
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+constexpr unsigned kFullMask = 0xffffffffu;
+
+void set_cuda_error(cudaError_t e, const char* where);
+int check_launch(const char* where);
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements of T <-> 4 floats; one 16-byte (fp32) or 8-byte (16-bit) transaction.
+// Streaming variants bypass L1 allocation: every head tensor is touched exactly once.
+template <typename T>
+__device__ __forceinline__ void load4_stream(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load4_stream<float>(const float* p, float (&v)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+}
+template <>
+__device__ __forceinline__ void load4_stream<__half>(const __half* p, float (&v)[4]) {
+    uint32_t a, b;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+    __half2 h0 = *reinterpret_cast<__half2*>(&a), h1 = *reinterpret_cast<__half2*>(&b);
+    float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+}
+template <>
+__device__ __forceinline__ void load4_stream<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+    uint32_t a, b;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+    v[0] = __uint_as_float(a << 16); v[1] = __uint_as_float(a & 0xffff0000u);
+    v[2] = __uint_as_float(b << 16); v[3] = __uint_as_float(b & 0xffff0000u);
+}
+
+template <typename T>
+__device__ __forceinline__ void store4_stream(T* p, const float (&v)[4]);
+template <>
+__device__ __forceinline__ void store4_stream<float>(float* p, const float (&v)[4]) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+template <>
+__device__ __forceinline__ void store4_stream<__half>(__half* p, const float (&v)[4]) {
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};"
+                 :: "l"(p), "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)) : "memory");
+}
+template <>
+__device__ __forceinline__ void store4_stream<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};"
+                 :: "l"(p), "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+    return v;
+}
+
+// Deterministic mean over the grid: every block deposits one partial, the last block to arrive
+// (threadfence + ticket) adds the partials in index order in fp64 and writes sum/n.  The ticket is
+// reset so the (zero-initialised) workspace can be reused by the next call.
+struct HeadWorkspace {
+    unsigned int ticket;
+    unsigned int pad[31];
+    float partial[(EOE_HEAD_WS_BYTES - 128) / 4];
+};
+constexpr int kMaxHeadBlocks = (EOE_HEAD_WS_BYTES - 128) / 4;
+
+template <int BLOCK>
+__device__ __forceinline__ void grid_mean_finish(float thread_val, HeadWorkspace* ws, float* out, double inv_n) {
+    __shared__ float s_warp[BLOCK / 32];
+    __shared__ bool s_last;
+    float w = warp_sum(thread_val);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float b = 0.f;
+#pragma unroll
+        for (int i = 0; i < BLOCK / 32; ++i) b += s_warp[i];
+        ws->partial[blockIdx.x] = b;
+        __threadfence();
+        unsigned int t = atomicAdd(&ws->ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+        __threadfence();
+        double acc = 0.0;
+        // fixed order: lane l adds partial[l], partial[l+32], ...; then a fixed shuffle tree
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) acc += (double)__ldcg(&ws->partial[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
+        if (threadIdx.x == 0) {
+            *out = (float)(acc * inv_n);
+            ws->ticket = 0;
+        }
+    }
+}
+
+}  // namespace eoe

@@ -1,0 +1,194 @@
+/*
+ * eoe_b200 -- C ABI of the B200-native anomaly-detection scoring / loss / AUC hot path.
+ *
+ * The reference (liznerski/eoe) is pure Python: its "FFI" for this path is the three ADTrainer hooks
+ *   prepare_metric / compute_anomaly_score / loss      src/eoe/training/ad_trainer.py:624-662
+ * implemented per objective in src/eoe/training/{hsc,bce,clip}.py, the image-encoder call
+ *   image_features = model(imgs)                        ad_trainer.py:429,507
+ * and the scikit-learn AUC call at ad_trainer.py:453-454,517-521.  Each entry point below names the
+ * reference lines it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, never synchronise,
+ *     never allocate, and are re-entrant as long as two in-flight calls do not share a workspace
+ *   - return value 0 = success, negative = error (eoe_strerror); nothing throws across the ABI
+ *   - NaN / Inf inputs propagate into scores and losses (the reference's NanGradientsError guard,
+ *     ad_trainer.py:448-449, relies on that); eoe_auc reports non-finite scores in its status word
+ *   - dtypes: EOE_F32 / EOE_F16 / EOE_BF16 for feature and score tensors; labels are int64
+ *     (torch.long, as produced by the reference's loaders); accumulation is always fp32 (fp64 for AUC)
+ */
+#ifndef EOE_B200_H
+#define EOE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EOE_ABI_VERSION 1
+
+enum { EOE_F32 = 0, EOE_F16 = 1, EOE_BF16 = 2 };
+
+enum {
+    EOE_OK = 0,
+    EOE_ERR_ARG = -1,         /* null pointer / negative size / bad enum                        */
+    EOE_ERR_DTYPE = -2,       /* unsupported dtype                                              */
+    EOE_ERR_SHAPE = -3,       /* unsupported shape (e.g. d not a multiple of 4, K too large)     */
+    EOE_ERR_ALIGN = -4,       /* pointer not aligned as required (16 B for feature rows)         */
+    EOE_ERR_WORKSPACE = -5,   /* workspace missing or too small                                  */
+    EOE_ERR_CUDA = -6,        /* a CUDA runtime / driver call or kernel launch failed            */
+    EOE_ERR_ARCH = -7         /* device is not sm_100 (Blackwell B200)                            */
+};
+
+int eoe_abi_version(void);
+const char* eoe_strerror(int code);
+/* last CUDA error string recorded by this library on the calling thread ("" if none) */
+const char* eoe_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loss / score heads.  `head_ws` is a zero-initialised device buffer of EOE_HEAD_WS_BYTES bytes
+ * allocated once by the caller; kernels leave it zeroed again so it can be reused call after call.
+ * ---------------------------------------------------------------------------------------------- */
+#define EOE_HEAD_WS_BYTES 32768
+
+/* HSCTrainer.loss + its autograd backward + HSCTrainer.compute_anomaly_score in ONE kernel.
+ * Replaces src/eoe/training/hsc.py:17-21 (loss), :12-15 (score) and the 28-op autograd backward.
+ *   z [n,d] row-major (z_dtype), labels [n] int64, nominal_label as in kwargs (ad_trainer.py:430)
+ *   loss_out  [1] fp32   = mean_i( label_i==nominal ? dist_i : -log(score_i + 1e-9) )
+ *   scores_out[n] fp32   = 1 - exp(-dist_i), dist_i = sqrt(||z_i||^2 + 1) - 1        (nullable)
+ *   grad_z_out[n,d] z_dtype = d loss / d z   (for upstream gradient 1)                  (nullable)
+ * d % 4 == 0 and 16-byte aligned rows take the vector path; any other d takes a scalar path. */
+int eoe_hsc_fwd_bwd(const void* z, int z_dtype, const int64_t* labels, int64_t n, int64_t d,
+                    int64_t nominal_label, float* loss_out, float* scores_out, void* grad_z_out,
+                    void* head_ws, void* stream);
+
+/* HSCTrainer.compute_anomaly_score alone (test time, ad_trainer.py:508). hsc.py:12-15 */
+int eoe_hsc_score(const void* z, int z_dtype, int64_t n, int64_t d, float* scores_out, void* stream);
+
+/* BCETrainer.loss + backward + compute_anomaly_score. Replaces src/eoe/training/bce.py:15-20.
+ *   x [n] (= features [n,1] squeezed), labels [n] int64 used raw as float targets (bce.py:20)
+ *   loss_out [1] fp32 = mean( max(x,0) - x*y + log1p(exp(-|x|)) )
+ *   scores_out [n] fp32 = sigmoid(x), or 1 - sigmoid(x) if nominal_label != 0 (bce.py:17)  (nullable)
+ *   grad_x_out [n] x_dtype = (sigmoid(x) - y)/n                                           (nullable) */
+int eoe_bce_fwd_bwd(const void* x, int x_dtype, const int64_t* labels, int64_t n, int64_t nominal_label,
+                    float* loss_out, float* scores_out, void* grad_x_out, void* head_ws, void* stream);
+
+int eoe_bce_score(const void* x, int x_dtype, int64_t n, int64_t nominal_label, float* scores_out,
+                  void* stream);
+
+/* ADClipTrainer.compute_anomaly_score. Replaces src/eoe/training/clip.py:66-79.
+ *   z [n,d] image features, text [K,d] fp32 (`center`); text rows are re-normalised (clip.py:69)
+ *   scores_out [n] fp32 = softmax_k(scale * z^_i . T^_k)[K-1]     (scale = 100, clip.py:71)
+ * Limits: d % 4 == 0, d <= 1024, K*d*4 <= 192 KiB (text lives in shared memory). */
+int eoe_clip_score(const void* z, int z_dtype, const float* text, int64_t n, int64_t d, int64_t K,
+                   float scale, float* scores_out, void* stream);
+
+/* ADClipTrainer.loss + backward w.r.t. image features. Replaces src/eoe/training/clip.py:81-103.
+ *   text used as given (not re-normalised, clip.py:82,86); leave_one_out != 0 selects clip.py:93-98
+ *   loss_out [1] fp32; grad_z_out [n,d] z_dtype (nullable). Rows whose label is neither nominal nor
+ *   1-nominal contribute 0 but count in the mean (clip.py:90,96,102). */
+int eoe_clip_oe_loss_fwd_bwd(const void* z, int z_dtype, const float* text, const int64_t* labels,
+                             int64_t n, int64_t d, int64_t K, float scale, int64_t nominal_label,
+                             int leave_one_out, float* loss_out, void* grad_z_out, void* head_ws,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ROC-AUC (and PRC / AP) on the device, bit-exact with scikit-learn's
+ *   fpr, tpr, thr = roc_curve(labels, scores); auc(fpr, tpr)         ad_trainer.py:453-454,517-518
+ *   precision_recall_curve / average_precision_score                  ad_trainer.py:520-521
+ * Device radix sort of (descending score key, label bit) + tie / corner scans + fp64 trapezoid terms
+ * summed in numpy's pairwise order.
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+    EOE_AUC_IGNORE_NEGATIVE_LABELS = 1,   /* drop rows with label < 0 (ad_trainer.py:517 filter)   */
+    EOE_AUC_WITH_PRC = 2                  /* also compute average precision (+ PRC arrays if given) */
+};
+enum {                                    /* bits of info_out[4]                                    */
+    EOE_AUC_STATUS_NONFINITE = 1,         /* a kept score is NaN/Inf (sklearn raises ValueError)     */
+    EOE_AUC_STATUS_SINGLE_CLASS = 2       /* only one class present: AUC undefined (NaN)             */
+};
+size_t eoe_auc_workspace_bytes(int64_t n);
+/*   scores [n] (score_dtype), labels [n] int64 (positive class == 1)
+ *   auc_out  [2] fp64 device: [0] = ROC-AUC, [1] = average precision (if EOE_AUC_WITH_PRC)
+ *   info_out [8] int64 device: [0] n kept, [1] n positives, [2] n distinct scores,
+ *                               [3] n ROC points (incl. the prepended origin), [4] status bits
+ *   fpr_out, tpr_out [n+1] fp64, thr_out [n+1] fp32 (thr[0] = +inf): ROC curve, nullable (all three or none)
+ *   prec_out, rec_out [n+1] fp64: PRC in sklearn's (reversed, (1,0)-terminated) order, nullable */
+int eoe_auc(const void* scores, int score_dtype, const int64_t* labels, int64_t n, int flags,
+            void* workspace, size_t workspace_bytes, double* auc_out, int64_t* info_out,
+            double* fpr_out, double* tpr_out, float* thr_out, double* prec_out, double* rec_out,
+            void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CLIP ViT-B image encoder forward (+ optional fused zero-shot score head).
+ * Replaces VisualTransformer.forward  src/eoe/models/clip_official/clip/model.py:219-236
+ * (ResidualAttentionBlock :167-188, LayerNorm :153-159, QuickGELU :162-164, encode_image :336-337)
+ * followed, when `text` is given, by ADClipTrainer.compute_anomaly_score (training/clip.py:66-79).
+ * GEMMs run on tcgen05 tensor cores (16-bit operands, fp32 TMEM accumulators, TMA-fed); the
+ * residual stream, LayerNorm and softmax statistics are fp32.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct eoe_vit_layer {
+    const float* ln_1_w; const float* ln_1_b;          /* [width]                                  */
+    const void*  in_proj_w;  const float* in_proj_b;   /* [3*width, width] operand dtype, [3*width] */
+    const void*  out_proj_w; const float* out_proj_b;  /* [width, width], [width]                  */
+    const float* ln_2_w; const float* ln_2_b;
+    const void*  c_fc_w;   const float* c_fc_b;        /* [4*width, width], [4*width]              */
+    const void*  c_proj_w; const float* c_proj_b;      /* [width, 4*width], [width]                */
+} eoe_vit_layer;
+
+typedef struct eoe_vit_weights {
+    int32_t patch;            /* 32 or 16                                                           */
+    int32_t resolution;       /* 224                                                                */
+    int32_t width;            /* 768                                                                */
+    int32_t heads;            /* 12 (head dim must be 64)                                           */
+    int32_t n_layers;         /* 12                                                                 */
+    int32_t embed_dim;        /* 512                                                                */
+    int32_t operand_dtype;    /* EOE_BF16 or EOE_F16: dtype of all *_w matrices below               */
+    int32_t reserved;
+    const void*  conv1_w;     /* [width, 3*patch*patch]  (visual.conv1.weight flattened)            */
+    const float* class_embedding;       /* [width]                                                  */
+    const float* positional_embedding;  /* [L, width], L = (resolution/patch)^2 + 1                 */
+    const float* ln_pre_w;  const float* ln_pre_b;
+    const float* ln_post_w; const float* ln_post_b;
+    const float* proj;        /* [width, embed_dim] fp32 (visual.proj)                              */
+    const eoe_vit_layer* layers_host;   /* HOST array of n_layers entries holding DEVICE pointers   */
+} eoe_vit_weights;
+
+typedef struct eoe_vit_plan eoe_vit_plan;
+
+/* Builds TMA descriptors / launch geometry for batches of up to max_batch images whose activations
+ * live in `workspace` (device, eoe_vit_workspace_bytes(...) bytes, 1024-byte aligned). The plan keeps
+ * pointers to the weights and the workspace; both must outlive it. Host-side only, no GPU work. */
+size_t eoe_vit_workspace_bytes(const eoe_vit_weights* w_host, int64_t max_batch);
+int eoe_vit_plan_create(const eoe_vit_weights* w_host, int64_t max_batch, void* workspace,
+                        size_t workspace_bytes, eoe_vit_plan** plan_out);
+void eoe_vit_plan_destroy(eoe_vit_plan* plan);
+
+/*   imgs [B,3,R,R] NCHW fp32 (already normalised, as handed to model(imgs) at ad_trainer.py:507), B <= max_batch
+ *   feats_out [B, embed_dim] fp32                                        (nullable)
+ *   text [K, embed_dim] fp32 + scores_out [B] fp32: fused clip.py:66-79   (nullable together) */
+int eoe_vit_encode(eoe_vit_plan* plan, const float* imgs, int64_t B, float* feats_out,
+                   const float* text, int64_t K, float scale, float* scores_out, void* stream);
+
+/* Building blocks of the encoder, exported so that each kernel is parity-tested through the ABI. */
+enum { EOE_EPI_BIAS = 0, EOE_EPI_BIAS_QUICKGELU = 1, EOE_EPI_BIAS_RESIDUAL_F32 = 2, EOE_EPI_PATCH_EMBED = 3 };
+/* out = epilogue(A[M,K] @ W[N,K]^T): tcgen05 GEMM, A/W operand dtype (BF16/F16), K % 64 == 0, N % 64 == 0.
+ *   EOE_EPI_BIAS / _QUICKGELU: out [M,N] operand dtype;  _RESIDUAL_F32: out [M,N] fp32 += (in place);
+ *   _PATCH_EMBED: out fp32 row (m/g2)*(g2+1)+1+(m%g2) = acc + pos_emb[1+m%g2] (aux = pos_emb, aux_i = g2). */
+int eoe_gemm(const void* A, const void* W, const float* bias, void* out, int64_t M, int64_t N, int64_t K,
+             int operand_dtype, int epilogue, const float* aux, int64_t aux_i, void* stream);
+/* y[M,width] (out_dtype) = LayerNorm_fp32(x[M,width]) * w + b, eps 1e-5 (model.py:153-159) */
+int eoe_layernorm(const float* x, const float* w, const float* b, void* y, int out_dtype, int64_t M,
+                  int64_t width, void* stream);
+/* softmax(Q K^T / sqrt(64)) V per (image, head); qkv [B*L, 3*width] operand dtype (q;k;v column blocks,
+ * model.py:171 in_proj layout), out [B*L, width] operand dtype */
+int eoe_attention(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int operand_dtype,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EOE_B200_H */

@@ -1,0 +1,175 @@
+"""GPU parity of the fused loss/score heads (through the C ABI) vs the CPU oracle (oracle/heads.py) and the
+golden fixtures generated from the live reference.  Tolerance: 1e-3 relative (north_star), tighter where
+the arithmetic allows; written next to each assert."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import golden_inputs as gi
+from oracle import heads as oh
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _t(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def _np(t):
+    return t.detach().float().cpu().numpy()
+
+
+def _close(got, want, rtol=1e-3, atol=1e-7):
+    np.testing.assert_allclose(np.asarray(got, np.float64), np.asarray(want, np.float64), rtol=rtol, atol=atol)
+
+
+def test_hsc_golden(golden_dir):
+    from eoe_b200 import ops
+    g = np.load(os.path.join(golden_dir, "heads.npz"))
+    z, y = gi.hsc_inputs()
+    for nom in (0, 1):
+        zt = _t(z).requires_grad_(True)
+        loss, scores = ops.hsc_loss(zt, _t(y), nominal_label=nom)
+        loss.backward()
+        _close(loss.item(), g[f"hsc_loss_nom{nom}"], rtol=1e-5)
+        _close(_np(zt.grad), g[f"hsc_grad_nom{nom}"], rtol=1e-4, atol=1e-9)
+        _close(_np(scores), g["hsc_score"], rtol=1e-4, atol=1e-7)
+    _close(_np(ops.hsc_score(_t(z))), g["hsc_score"], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("n,d", [(1, 4), (3, 8), (7, 100), (33, 128), (256, 256), (257, 512), (64, 1024),
+                                 (5, 33), (19, 2048), (1000, 260)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_hsc_vs_oracle(n, d, dtype):
+    from eoe_b200 import ops
+    rng = np.random.default_rng(n * 1000 + d)
+    z = (0.8 / np.sqrt(d) * rng.standard_normal((n, d))).astype(np.float32)
+    zt = _t(z, dtype)
+    zq = _np(zt)                                   # oracle sees the same (rounded) inputs
+    y = rng.integers(0, 2, n)
+    for nom in (0, 1):
+        zz = zt.clone().requires_grad_(True)
+        loss, scores = ops.hsc_loss(zz, _t(y), nominal_label=nom)
+        (loss * 3.0).backward()                    # upstream gradient is honoured
+        _close(loss.item(), oh.hsc_loss(zq, y, nom), rtol=1e-4)
+        _close(_np(scores), oh.hsc_score(zq), rtol=2e-4, atol=1e-7)
+        gtol = 1e-4 if dtype == torch.float32 else 1e-2   # grads are rounded to the feature dtype
+        _close(_np(zz.grad), 3.0 * oh.hsc_grad(zq, y, nom), rtol=gtol, atol=1e-6 if dtype != torch.float32 else 1e-9)
+
+
+def test_hsc_nan_propagates_and_zero_row():
+    from eoe_b200 import ops
+    z = torch.zeros(4, 256, device=DEV)
+    z[1, 5] = float("nan")
+    z[2] = 0.01
+    loss, scores, grad = ops.hsc_fused(z, torch.tensor([0, 1, 1, 1], device=DEV))
+    s = _np(scores)
+    assert s[0] == 0.0 and np.isnan(s[1]) and np.isfinite(s[2])
+    assert np.isnan(loss.item())
+    assert float(grad[0].abs().sum()) == 0.0 and float(grad[3].abs().sum()) == 0.0
+
+
+def test_bce_golden(golden_dir):
+    from eoe_b200 import ops
+    g = np.load(os.path.join(golden_dir, "heads.npz"))
+    x, y = gi.bce_inputs()
+    xt = _t(x).requires_grad_(True)
+    loss, scores = ops.bce_loss(xt, _t(y))
+    loss.backward()
+    _close(loss.item(), g["bce_loss"], rtol=1e-5)
+    _close(_np(xt.grad), g["bce_grad"], rtol=1e-4, atol=1e-10)
+    for nom in (0, 1):
+        _close(_np(ops.bce_score(_t(x), nominal_label=nom)), g[f"bce_score_nom{nom}"], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 255, 256, 1001, 65537])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_bce_vs_oracle(n, dtype):
+    from eoe_b200 import ops
+    rng = np.random.default_rng(n)
+    x = (4 * rng.standard_normal((n, 1))).astype(np.float32)
+    xt = _t(x, dtype)
+    xq = _np(xt)
+    y = rng.integers(0, 2, n)
+    xx = xt.clone().requires_grad_(True)
+    loss, scores = ops.bce_loss(xx, _t(y), nominal_label=1)
+    loss.backward()
+    assert xx.grad.shape == xx.shape
+    _close(loss.item(), oh.bce_loss(xq, y), rtol=1e-4)
+    _close(_np(scores), oh.bce_score(xq, 1), rtol=1e-4, atol=1e-7)
+    gtol = 1e-4 if dtype == torch.float32 else 1e-2
+    _close(_np(xx.grad).reshape(-1), oh.bce_grad(xq, y), rtol=gtol, atol=1e-9 if dtype == torch.float32 else 1e-6)
+    # unaligned views take the scalar path
+    if n > 3:
+        l2, s2, g2 = ops.bce_fused(xt.reshape(-1)[1:], _t(y)[1:], 0)
+        _close(l2.item(), oh.bce_loss(xq[1:], y[1:]), rtol=1e-4)
+        _close(_np(s2), oh.bce_score(xq[1:], 0), rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("K", [2, 10, 30])
+def test_clip_golden(golden_dir, K):
+    from eoe_b200 import ops
+    g = np.load(os.path.join(golden_dir, "heads.npz"))
+    z, y, c = gi.clip_inputs(K)
+    _close(_np(ops.clip_score(_t(z), _t(c))), g[f"clip_score_K{K}"], rtol=1e-3, atol=1e-30)
+    for mode in ("one_vs_rest", "leave_one_out"):
+        for nom in (0, 1):
+            zt = _t(z).requires_grad_(True)
+            loss = ops.clip_oe_loss(zt, _t(y), _t(c), nominal_label=nom, leave_one_out=(mode == "leave_one_out"))
+            loss.backward()
+            _close(loss.item(), g[f"clip_loss_K{K}_{mode}_nom{nom}"], rtol=1e-4)
+            _close(_np(zt.grad), g[f"clip_grad_K{K}_{mode}_nom{nom}"], rtol=2e-3, atol=2e-6)
+
+
+@pytest.mark.parametrize("n,d,K", [(1, 512, 2), (37, 512, 5), (300, 512, 30), (64, 768, 33), (50, 1024, 40), (9, 64, 3)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_clip_vs_oracle(n, d, K, dtype):
+    from eoe_b200 import ops
+    rng = np.random.default_rng(n + d + K)
+    z = rng.standard_normal((n, d)).astype(np.float32)
+    c = (rng.standard_normal((K, d)) * 1.7).astype(np.float32)      # non-unit: the score path must renormalise
+    zt = _t(z, dtype)
+    zq = _np(zt)
+    _close(_np(ops.clip_score(zt, _t(c))), oh.clip_score(zq, c), rtol=1e-3, atol=1e-30)
+    cu = (c / np.linalg.norm(c, axis=1, keepdims=True)).astype(np.float32)
+    y = rng.integers(0, 2, n)
+    for loo in (False, True):
+        zz = zt.clone().requires_grad_(True)
+        loss = ops.clip_oe_loss(zz, _t(y), _t(cu), nominal_label=0, leave_one_out=loo)
+        loss.backward()
+        _close(loss.item(), oh.clip_oe_loss(zq, y, cu, 0, loo), rtol=1e-4)
+        gtol = 2e-3 if dtype == torch.float32 else 2e-2
+        _close(_np(zz.grad), oh.clip_oe_grad(zq, y, cu, 0, loo), rtol=gtol, atol=1e-5)
+
+
+def test_bad_arguments_raise():
+    from eoe_b200 import _lib, ops
+    with pytest.raises(_lib.EoeError):
+        ops.hsc_score(torch.zeros(4, 8))                      # CPU tensor: no fallback
+    with pytest.raises(_lib.EoeError):
+        ops.clip_score(torch.zeros(4, 510, device=DEV), torch.zeros(3, 510, device=DEV))   # d % 4 != 0
+    with pytest.raises(_lib.EoeError):
+        ops.clip_score(torch.zeros(4, 512, device=DEV), torch.zeros(100, 512, device=DEV))  # K too large
+
+
+def test_heads_large_property():
+    """BASELINE-size rows (2^20 x 256): size-independent properties instead of a CPU oracle pass:
+    score/loss of a tiled input equal the small-case values; grad is coef*z (linearity in z per row)."""
+    from eoe_b200 import ops
+    rng = np.random.default_rng(0)
+    base = (0.05 * rng.standard_normal((1024, 256))).astype(np.float32)
+    yb = rng.integers(0, 2, 1024)
+    z = _t(base).repeat(1024, 1)
+    y = _t(yb).repeat(1024)
+    loss, scores, grad = ops.hsc_fused(z, y, 0)
+    _close(loss.item(), oh.hsc_loss(base, yb, 0), rtol=1e-4)
+    sc = _np(scores).reshape(1024, 1024)
+    assert np.array_equal(sc[0], sc[-1]) and np.array_equal(sc[0], sc[511])
+    _close(sc[0], oh.hsc_score(base), rtol=2e-4, atol=1e-7)
+    g = _np(grad[:1024]) * 1024.0
+    _close(g, oh.hsc_grad(base, yb, 0), rtol=1e-4, atol=1e-9)
+    assert torch.equal(grad[:1024], grad[-1024:])
