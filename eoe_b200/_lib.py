@@ -67,6 +67,7 @@ SIGNATURES = {
 }
 
 _lib = None
+MISSING = []
 
 
 def lib():
@@ -80,7 +81,13 @@ def lib():
             "(there is no CPU / PyTorch fallback for the eoe_b200 hot path)")
     l = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(l, name)          # AttributeError (loud) if the library does not export the symbol
+        try:
+            fn = getattr(l, name)
+        except AttributeError:
+            # a stale build: calling the symbol later raises AttributeError (loud, no fallback);
+            # tests/test_capi_symbols.py requires every declared symbol to be exported
+            MISSING.append(name)
+            continue
         fn.restype = res
         fn.argtypes = args
     _lib = l

@@ -41,9 +41,12 @@ struct AucLayout {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static int pairwise_depth(int64_t n) {   // depth of numpy's pairwise tree (right spine is the deepest)
+// Upper bound, monotone in n, of the depth of numpy's pairwise tree over any T <= n terms.  The exact depth
+// (right spine: len -> len - ((len/2) & ~7) <= (len+15)/2) is NOT monotone in T (65443 terms are one level
+// deeper than 65536), so buffers and grids are sized with the bound; kernels use the exact depth of T.
+static int pairwise_depth(int64_t n) {
     int d = 0;
-    while (n > 128) { n -= (n / 2) & ~(int64_t)7; ++d; }
+    while (n > 128) { n = (n + 15) / 2; ++d; }
     return d;
 }
 

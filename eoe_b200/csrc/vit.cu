@@ -1,0 +1,622 @@
+// CLIP ViT-B image encoder forward on sm_100a: host orchestration + the non-GEMM kernels.
+// Reference: VisualTransformer.forward, src/eoe/models/clip_official/clip/model.py:219-236
+//   conv1 patchify (:220) -> im2col_kernel + tcgen05 GEMM with fused positional-embedding epilogue
+//   class token + pos-emb + ln_pre (:223-225) -> layernorm_kernel (cls rows synthesised in place)
+//   12 x ResidualAttentionBlock (:185-188): LN -> QKV GEMM -> attention_kernel -> out-proj GEMM (+residual)
+//                                           LN -> c_fc GEMM (+QuickGELU) -> c_proj GEMM (+residual)
+//   ln_post(x[:,0]) @ proj (:231-234) -> tail_kernel, then optionally the zero-shot score head (training/clip.py:66-79)
+// Token layout is [B, L, width] (batch major), residual stream fp32, GEMM operands bf16/fp16.
+#include <mutex>
+#include <new>
+
+#include "gemm_sm100.cuh"
+
+namespace eoe {
+
+int clip_score_f32(const float* z, const float* text, int64_t n, int64_t d, int64_t K, float scale, float* scores,
+                   cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        else set_cuda_error(e, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)");
+    });
+    return fn;
+}
+
+// [rows, K] row-major 16-bit matrix, box = box_rows x 64 columns (128 bytes), SWIZZLE_128B, OOB rows read as zero
+static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t K, int box_rows, int dtype) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return EOE_ERR_CUDA;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, dtype == EOE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+        return EOE_ERR_CUDA;
+    }
+    return EOE_OK;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = kNumSMs;
+    }
+    return n;
+}
+
+template <int EPI, bool BF16>
+static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, cudaStream_t st) {
+    auto kern = gemm::gemm_kernel<EPI, BF16>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::SMEM_BYTES);
+        if (e != cudaSuccess) { set_cuda_error(e, "gemm smem attr"); return EOE_ERR_CUDA; }
+        attr_done = true;
+    }
+    const int64_t tiles = ((p.M + gemm::BM - 1) / gemm::BM) * (p.N / gemm::BN);
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    kern<<<grid, gemm::THREADS, gemm::SMEM_BYTES, st>>>(ta, tb, p);
+    return check_launch("gemm_kernel");
+}
+
+static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int dtype, int epi,
+                       cudaStream_t st) {
+    const bool bf = dtype == EOE_BF16;
+    switch (epi) {
+        case EOE_EPI_BIAS: return bf ? gemm_launch_t<EOE_EPI_BIAS, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_BIAS, false>(ta, tb, p, st);
+        case EOE_EPI_BIAS_QUICKGELU: return bf ? gemm_launch_t<EOE_EPI_BIAS_QUICKGELU, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_BIAS_QUICKGELU, false>(ta, tb, p, st);
+        case EOE_EPI_BIAS_RESIDUAL_F32: return bf ? gemm_launch_t<EOE_EPI_BIAS_RESIDUAL_F32, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_BIAS_RESIDUAL_F32, false>(ta, tb, p, st);
+        case EOE_EPI_PATCH_EMBED: return bf ? gemm_launch_t<EOE_EPI_PATCH_EMBED, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_PATCH_EMBED, false>(ta, tb, p, st);
+        default: return EOE_ERR_ARG;
+    }
+}
+
+static int gemm_check(int64_t M, int64_t N, int64_t K, int dtype) {
+    if (M <= 0 || N <= 0 || K <= 0) return EOE_ERR_ARG;
+    if (dtype != EOE_BF16 && dtype != EOE_F16) return EOE_ERR_DTYPE;
+    if (N % gemm::BN != 0 || K % gemm::BK != 0) return EOE_ERR_SHAPE;
+    return EOE_OK;
+}
+
+// ------------------------------------------------------------------------------------------ im2col
+// imgs [B,3,R,R] fp32 NCHW -> patches [B*g*g, 3*P*P] 16-bit with k = c*P*P + py*P + px (= conv1.weight.view(width,-1))
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ imgs, uint16_t* __restrict__ patches, int64_t B, int R, int P) {
+    const int g = R / P;
+    const int pq = P / 4;
+    const int64_t total = B * 3 * (int64_t)R * R / 4;
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+        int64_t t = idx;
+        const int px4 = (int)(t % pq); t /= pq;
+        const int py = (int)(t % P); t /= P;
+        const int c = (int)(t % 3); t /= 3;
+        const int gx = (int)(t % g); t /= g;
+        const int gy = (int)(t % g); t /= g;
+        const int64_t b = t;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(
+            imgs + ((b * 3 + c) * R + (gy * P + py)) * (int64_t)R + gx * P + px4 * 4));
+        uint2 o;
+        o.x = gemm::pack2<BF16>(v.x, v.y);
+        o.y = gemm::pack2<BF16>(v.z, v.w);
+        *reinterpret_cast<uint2*>(patches + idx * 4) = o;      // idx*4 == ((b*g+gy)*g+gx)*3*P*P + c*P*P + py*P + px4*4
+    }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+// fp32 statistics over `width` (model.py:153-159, eps 1e-5); one warp per row, row kept in registers.
+// cls_emb != null: rows with row % L == 0 are synthesised as class_embedding + positional_embedding[0]
+// (model.py:223-224) -- used by ln_pre, whose other rows already hold patch_embed + pos_emb from the GEMM epilogue.
+template <typename OutT, int ITERS>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                 OutT* __restrict__ y, int64_t M, int width, const float* __restrict__ cls_emb,
+                 const float* __restrict__ pos0, int L) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nvec = width >> 2;
+    float v[ITERS][4];
+    const bool is_cls = cls_emb != nullptr && (row % L) == 0;
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int vi = it * 32 + lane;
+        if (vi < nvec) {
+            if (is_cls) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(cls_emb) + vi);
+                const float4 c = __ldg(reinterpret_cast<const float4*>(pos0) + vi);
+                v[it][0] = a.x + c.x; v[it][1] = a.y + c.y; v[it][2] = a.z + c.z; v[it][3] = a.w + c.w;
+            } else {
+                const float4 a = *(reinterpret_cast<const float4*>(x + row * width) + vi);
+                v[it][0] = a.x; v[it][1] = a.y; v[it][2] = a.z; v[it][3] = a.w;
+            }
+        } else {
+            v[it][0] = v[it][1] = v[it][2] = v[it][3] = 0.f;
+        }
+        s += v[it][0] + v[it][1] + v[it][2] + v[it][3];
+    }
+    const float mean = warp_sum(s) / (float)width;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int vi = it * 32 + lane;
+        if (vi < nvec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float dlt = v[it][j] - mean; q += dlt * dlt; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)width + 1e-5f);
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int vi = it * 32 + lane;
+        if (vi < nvec) {
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + vi);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + vi);
+            float o[4] = {(v[it][0] - mean) * rstd * ww.x + bb.x, (v[it][1] - mean) * rstd * ww.y + bb.y,
+                          (v[it][2] - mean) * rstd * ww.z + bb.z, (v[it][3] - mean) * rstd * ww.w + bb.w};
+            OutT* dst = y + row * width + vi * 4;
+            if (sizeof(OutT) == 4) {
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+                uint2 pk;
+                constexpr bool bf = std::is_same<OutT, __nv_bfloat16>::value;
+                pk.x = gemm::pack2<bf>(o[0], o[1]);
+                pk.y = gemm::pack2<bf>(o[2], o[3]);
+                *reinterpret_cast<uint2*>(dst) = pk;
+            }
+        }
+    }
+}
+
+template <typename OutT>
+static int layernorm_launch(const float* x, const float* w, const float* b, void* y, int64_t M, int64_t width,
+                            const float* cls_emb, const float* pos0, int L, cudaStream_t st) {
+    const int grid = (int)((M + 7) / 8);
+    if (width <= 768)
+        layernorm_kernel<OutT, 6><<<grid, 256, 0, st>>>(x, w, b, (OutT*)y, M, (int)width, cls_emb, pos0, L);
+    else
+        layernorm_kernel<OutT, 8><<<grid, 256, 0, st>>>(x, w, b, (OutT*)y, M, (int)width, cls_emb, pos0, L);
+    return check_launch("layernorm_kernel");
+}
+
+static int layernorm_dispatch(const float* x, const float* w, const float* b, void* y, int out_dtype, int64_t M,
+                              int64_t width, const float* cls_emb, const float* pos0, int L, cudaStream_t st) {
+    if (width % 4 != 0 || width > 1024) return EOE_ERR_SHAPE;
+    switch (out_dtype) {
+        case EOE_F32: return layernorm_launch<float>(x, w, b, y, M, width, cls_emb, pos0, L, st);
+        case EOE_F16: return layernorm_launch<__half>(x, w, b, y, M, width, cls_emb, pos0, L, st);
+        case EOE_BF16: return layernorm_launch<__nv_bfloat16>(x, w, b, y, M, width, cls_emb, pos0, L, st);
+        default: return EOE_ERR_DTYPE;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ attention
+// softmax(Q K^T / 8) V for one (image, head) per CTA: L <= LP keys live in shared memory, every warp owns 16 query
+// rows at a time, the whole score row block stays in registers (no online rescaling needed at L <= 208).
+// Tensor work uses warp-level mma.sync m16n8k16 (attention is 4 % of the encoder FLOPs; the GEMMs carry tcgen05).
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+template <bool BF16>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if (BF16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kAttnThreads = 128;
+
+template <bool BF16, int LP>
+__global__ void __launch_bounds__(kAttnThreads)
+attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int L, int heads) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    const int width = heads * 64;
+    const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* sQ = sm;
+    uint8_t* sK = sm + LP * 128;
+    uint8_t* sV = sm + 2 * LP * 128;
+    // stage Q, K, V head slices: row r = 128 bytes = 8 chunks of 16 B, chunk c stored at c ^ (r & 7)
+    for (int i = tid; i < 3 * LP * 8; i += kAttnThreads) {
+        const int mat = i / (LP * 8), rem = i % (LP * 8), r = rem >> 3, c = rem & 7;
+        const uint32_t dst = ptx::smem_u32(sm + mat * LP * 128 + r * 128 + ((c ^ (r & 7)) << 4));
+        if (r < L) {
+            const uint16_t* src = qkv + ((int64_t)b * L + r) * (3 * width) + mat * width + h * 64 + c * 8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        } else {
+            asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0u) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    constexpr int NT = LP / 8;                      // key tiles of 8
+    const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const uint32_t q_base = ptx::smem_u32(sQ), k_base = ptx::smem_u32(sK), v_base = ptx::smem_u32(sV);
+    for (int qt = warp; qt * 16 < L; qt += kAttnThreads / 32) {
+        const int q0 = qt * 16;
+        uint32_t qf[4][4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int r = q0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int c = kk * 2 + (lane >> 4);
+            ldmatrix_x4(q_base + r * 128 + ((c ^ (r & 7)) << 4), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+        }
+        float s[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int np = 0; np < NT / 2; ++np) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int mi = lane >> 3;
+                const int r = np * 16 + (lane & 7) + (mi >> 1) * 8;
+                const int c = kk * 2 + (mi & 1);
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(k_base + r * 128 + ((c ^ (r & 7)) << 4), b0, b1, b2, b3);
+                mma_16816<BF16>(s[2 * np], qf[kk], b0, b1);
+                mma_16816<BF16>(s[2 * np + 1], qf[kk], b2, b3);
+            }
+        }
+        // row-wise softmax statistics: this thread holds rows (lane/4) [e=0,1] and (lane/4 + 8) [e=2,3]
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int col = nt * 8 + (lane & 3) * 2;
+            if (col >= L) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+            if (col + 1 >= L) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+            m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+            m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(kFullMask, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(kFullMask, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(kFullMask, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(kFullMask, m1, 2));
+        float l0 = 0.f, l1 = 0.f;
+        const float ms0 = m0 * sl2, ms1 = m1 * sl2;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            s[nt][0] = exp2f(s[nt][0] * sl2 - ms0); s[nt][1] = exp2f(s[nt][1] * sl2 - ms0);
+            s[nt][2] = exp2f(s[nt][2] * sl2 - ms1); s[nt][3] = exp2f(s[nt][3] * sl2 - ms1);
+            l0 += s[nt][0] + s[nt][1];
+            l1 += s[nt][2] + s[nt][3];
+        }
+        l0 += __shfl_xor_sync(kFullMask, l0, 1); l0 += __shfl_xor_sync(kFullMask, l0, 2);
+        l1 += __shfl_xor_sync(kFullMask, l1, 1); l1 += __shfl_xor_sync(kFullMask, l1, 2);
+        float o[8][4];
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NT / 2; ++kk) {
+            uint32_t pa[4];
+            pa[0] = gemm::pack2<BF16>(s[2 * kk][0], s[2 * kk][1]);
+            pa[1] = gemm::pack2<BF16>(s[2 * kk][2], s[2 * kk][3]);
+            pa[2] = gemm::pack2<BF16>(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            pa[3] = gemm::pack2<BF16>(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+                const int mi = lane >> 3;
+                const int r = kk * 16 + (lane & 7) + (mi & 1) * 8;
+                const int c = dp * 2 + (mi >> 1);
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4_trans(v_base + r * 128 + ((c ^ (r & 7)) << 4), b0, b1, b2, b3);
+                mma_16816<BF16>(o[2 * dp], pa, b0, b1);
+                mma_16816<BF16>(o[2 * dp + 1], pa, b2, b3);
+            }
+        }
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+            const int d = dt * 8 + (lane & 3) * 2;
+            if (r0 < L)
+                *reinterpret_cast<uint32_t*>(out + ((int64_t)b * L + r0) * width + h * 64 + d) =
+                    gemm::pack2<BF16>(o[dt][0] * i0, o[dt][1] * i0);
+            if (r1 < L)
+                *reinterpret_cast<uint32_t*>(out + ((int64_t)b * L + r1) * width + h * 64 + d) =
+                    gemm::pack2<BF16>(o[dt][2] * i1, o[dt][3] * i1);
+        }
+    }
+}
+
+template <bool BF16, int LP>
+static int attention_launch_t(const void* qkv, void* out, int64_t B, int L, int heads, cudaStream_t st) {
+    auto kern = attention_kernel<BF16, LP>;
+    const int smem = 3 * LP * 128;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_cuda_error(e, "attention smem attr"); return EOE_ERR_CUDA; }
+        attr_done = true;
+    }
+    kern<<<(unsigned)(B * heads), kAttnThreads, smem, st>>>((const uint16_t*)qkv, (uint16_t*)out, L, heads);
+    return check_launch("attention_kernel");
+}
+
+static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int dtype, cudaStream_t st) {
+    if (dtype != EOE_BF16 && dtype != EOE_F16) return EOE_ERR_DTYPE;
+    if (B <= 0 || L <= 0 || heads <= 0 || B * heads > 0x7fffffff) return EOE_ERR_ARG;
+    const bool bf = dtype == EOE_BF16;
+    if (L <= 64) return bf ? attention_launch_t<true, 64>(qkv, out, B, (int)L, (int)heads, st) : attention_launch_t<false, 64>(qkv, out, B, (int)L, (int)heads, st);
+    if (L <= 208) return bf ? attention_launch_t<true, 208>(qkv, out, B, (int)L, (int)heads, st) : attention_launch_t<false, 208>(qkv, out, B, (int)L, (int)heads, st);
+    return EOE_ERR_SHAPE;
+}
+
+// ------------------------------------------------------------------------------------------ tail
+// feats[b] = ln_post(x[b, 0, :]) @ proj   (model.py:231-234).  4 images per block so that proj (1.5 MB, L2
+// resident) is streamed once per 4 images; thread j owns output columns j and j + 256 (embed_dim <= 512).
+constexpr int kTailImgs = 4;
+__global__ void __launch_bounds__(256)
+tail_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+            const float* __restrict__ proj, float* __restrict__ feats, int64_t B, int L, int width, int embed) {
+    extern __shared__ float s_h[];        // [kTailImgs][width]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t img0 = (int64_t)blockIdx.x * kTailImgs;
+    if (warp < kTailImgs) {
+        const int64_t img = img0 + warp;
+        float* h = s_h + warp * width;
+        if (img < B) {
+            const float* xr = x + img * L * (int64_t)width;
+            float s = 0.f;
+            for (int i = lane; i < width; i += 32) s += xr[i];
+            const float mean = warp_sum(s) / (float)width;
+            float q = 0.f;
+            for (int i = lane; i < width; i += 32) { const float d = xr[i] - mean; q += d * d; }
+            const float rstd = rsqrtf(warp_sum(q) / (float)width + 1e-5f);
+            for (int i = lane; i < width; i += 32) h[i] = (xr[i] - mean) * rstd * w[i] + b[i];
+        } else {
+            for (int i = lane; i < width; i += 32) h[i] = 0.f;
+        }
+    }
+    __syncthreads();
+    const int j0 = threadIdx.x, j1 = threadIdx.x + 256;
+    float a0[kTailImgs], a1[kTailImgs];
+#pragma unroll
+    for (int g = 0; g < kTailImgs; ++g) a0[g] = a1[g] = 0.f;
+    for (int i = 0; i < width; ++i) {
+        const float p0 = j0 < embed ? __ldg(proj + (int64_t)i * embed + j0) : 0.f;
+        const float p1 = j1 < embed ? __ldg(proj + (int64_t)i * embed + j1) : 0.f;
+#pragma unroll
+        for (int g = 0; g < kTailImgs; ++g) {
+            const float hv = s_h[g * width + i];
+            a0[g] += hv * p0;
+            a1[g] += hv * p1;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < kTailImgs; ++g) {
+        if (img0 + g < B) {
+            if (j0 < embed) feats[(img0 + g) * embed + j0] = a0[g];
+            if (j1 < embed) feats[(img0 + g) * embed + j1] = a1[g];
+        }
+    }
+}
+
+}  // namespace eoe
+
+// ================================================================================================ plan / encode
+using namespace eoe;
+
+struct eoe_vit_plan {
+    eoe_vit_weights w;
+    eoe_vit_layer* layers;      // host copy
+    int64_t max_batch;
+    int L, g2, kpatch;
+    char* ws;
+    size_t ws_bytes;
+    // workspace carve-up
+    uint16_t* patches;   // [B*g2, 3*P*P]
+    float* x;            // [B*L, width] fp32 residual stream
+    uint16_t* h;         // [B*L, width] LN output / attention output
+    uint16_t* qkv;       // [B*L, 3*width]
+    uint16_t* u;         // [B*L, 4*width]
+    float* feats;        // [B, embed]
+    CUtensorMap tm_patches, tm_h, tm_u, tm_conv;
+    CUtensorMap *tm_in, *tm_out, *tm_fc, *tm_proj;     // per layer
+};
+
+static size_t rup(size_t x) { return (x + 1023) / 1024 * 1024; }
+
+static int vit_check(const eoe_vit_weights* w) {
+    if (!w || !w->layers_host) return EOE_ERR_ARG;
+    if (w->operand_dtype != EOE_BF16 && w->operand_dtype != EOE_F16) return EOE_ERR_DTYPE;
+    if (w->patch <= 0 || w->resolution % w->patch != 0 || w->patch % 4 != 0) return EOE_ERR_SHAPE;
+    if (w->width != w->heads * 64 || w->width % 256 != 0 || w->width > 1024) return EOE_ERR_SHAPE;
+    if ((3 * w->patch * w->patch) % 64 != 0 || w->embed_dim > 512 || w->embed_dim % 4 != 0) return EOE_ERR_SHAPE;
+    const int g = w->resolution / w->patch;
+    if (g * g + 1 > 208) return EOE_ERR_SHAPE;
+    if (w->n_layers <= 0) return EOE_ERR_ARG;
+    return EOE_OK;
+}
+
+struct VitLayout { size_t patches, x, h, qkv, u, feats, total; };
+static VitLayout vit_layout(const eoe_vit_weights* w, int64_t B) {
+    const int g = w->resolution / w->patch;
+    const int64_t g2 = g * g, L = g2 + 1, W = w->width;
+    // +128 rows of slack: TMA boxes of the last M tile may start below M but never beyond the allocation
+    VitLayout l;
+    size_t o = 0;
+    l.patches = o; o += rup((size_t)(B * g2 + 128) * 3 * w->patch * w->patch * 2);
+    l.x = o; o += rup((size_t)(B * L + 128) * W * 4);
+    l.h = o; o += rup((size_t)(B * L + 128) * W * 2);
+    l.qkv = o; o += rup((size_t)(B * L + 128) * 3 * W * 2);
+    l.u = o; o += rup((size_t)(B * L + 128) * 4 * W * 2);
+    l.feats = o; o += rup((size_t)B * w->embed_dim * 4);
+    l.total = o;
+    return l;
+}
+
+extern "C" size_t eoe_vit_workspace_bytes(const eoe_vit_weights* w, int64_t max_batch) {
+    if (vit_check(w) != EOE_OK || max_batch <= 0) return 0;
+    return vit_layout(w, max_batch).total;
+}
+
+extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, void* workspace, size_t workspace_bytes,
+                                   eoe_vit_plan** plan_out) {
+    int rc = vit_check(w);
+    if (rc) return rc;
+    if (!plan_out || max_batch <= 0) return EOE_ERR_ARG;
+    const VitLayout lay = vit_layout(w, max_batch);
+    if (!workspace || workspace_bytes < lay.total) return EOE_ERR_WORKSPACE;
+    if ((uintptr_t)workspace % 1024 != 0) return EOE_ERR_ALIGN;
+    eoe_vit_plan* p = new (std::nothrow) eoe_vit_plan();
+    if (!p) return EOE_ERR_ARG;
+    p->w = *w;
+    p->layers = new eoe_vit_layer[w->n_layers];
+    for (int i = 0; i < w->n_layers; ++i) p->layers[i] = w->layers_host[i];
+    p->w.layers_host = p->layers;
+    p->max_batch = max_batch;
+    const int g = w->resolution / w->patch;
+    p->g2 = g * g;
+    p->L = p->g2 + 1;
+    p->kpatch = 3 * w->patch * w->patch;
+    p->ws = (char*)workspace;
+    p->ws_bytes = workspace_bytes;
+    p->patches = (uint16_t*)(p->ws + lay.patches);
+    p->x = (float*)(p->ws + lay.x);
+    p->h = (uint16_t*)(p->ws + lay.h);
+    p->qkv = (uint16_t*)(p->ws + lay.qkv);
+    p->u = (uint16_t*)(p->ws + lay.u);
+    p->feats = (float*)(p->ws + lay.feats);
+    const int W = w->width, dt = w->operand_dtype;
+    const int64_t rows = max_batch * p->L;
+    p->tm_in = new CUtensorMap[w->n_layers];
+    p->tm_out = new CUtensorMap[w->n_layers];
+    p->tm_fc = new CUtensorMap[w->n_layers];
+    p->tm_proj = new CUtensorMap[w->n_layers];
+    rc = make_tmap(&p->tm_patches, p->patches, max_batch * p->g2, p->kpatch, gemm::BM, dt);
+    if (!rc) rc = make_tmap(&p->tm_h, p->h, rows, W, gemm::BM, dt);
+    if (!rc) rc = make_tmap(&p->tm_u, p->u, rows, 4 * W, gemm::BM, dt);
+    if (!rc) rc = make_tmap(&p->tm_conv, w->conv1_w, W, p->kpatch, gemm::BN, dt);
+    for (int i = 0; i < w->n_layers && !rc; ++i) {
+        const eoe_vit_layer& l = p->layers[i];
+        rc = make_tmap(&p->tm_in[i], l.in_proj_w, 3 * W, W, gemm::BN, dt);
+        if (!rc) rc = make_tmap(&p->tm_out[i], l.out_proj_w, W, W, gemm::BN, dt);
+        if (!rc) rc = make_tmap(&p->tm_fc[i], l.c_fc_w, 4 * W, W, gemm::BN, dt);
+        if (!rc) rc = make_tmap(&p->tm_proj[i], l.c_proj_w, W, 4 * W, gemm::BN, dt);
+    }
+    if (rc) { eoe_vit_plan_destroy(p); return rc; }
+    *plan_out = p;
+    return EOE_OK;
+}
+
+extern "C" void eoe_vit_plan_destroy(eoe_vit_plan* p) {
+    if (!p) return;
+    delete[] p->layers;
+    delete[] p->tm_in;
+    delete[] p->tm_out;
+    delete[] p->tm_fc;
+    delete[] p->tm_proj;
+    delete p;
+}
+
+extern "C" int eoe_vit_encode(eoe_vit_plan* p, const float* imgs, int64_t B, float* feats_out, const float* text,
+                              int64_t K, float scale, float* scores_out, void* stream) {
+    if (!p || !imgs || B <= 0 || B > p->max_batch) return EOE_ERR_ARG;
+    if ((text == nullptr) != (scores_out == nullptr)) return EOE_ERR_ARG;
+    if ((uintptr_t)imgs % 16 != 0) return EOE_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    const eoe_vit_weights& w = p->w;
+    const int W = w.width, dt = w.operand_dtype, L = p->L;
+    const int64_t M = B * L, Mp = B * p->g2;
+    int rc;
+    // 1. patchify
+    {
+        const int64_t total = B * 3 * (int64_t)w.resolution * w.resolution / 4;
+        int grid = (int)((total + 255) / 256 < (int64_t)num_sms() * 16 ? (total + 255) / 256 : (int64_t)num_sms() * 16);
+        if (dt == EOE_BF16) im2col_kernel<true><<<grid, 256, 0, st>>>(imgs, p->patches, B, w.resolution, w.patch);
+        else im2col_kernel<false><<<grid, 256, 0, st>>>(imgs, p->patches, B, w.resolution, w.patch);
+        if ((rc = check_launch("im2col_kernel"))) return rc;
+    }
+    // 2. patch-embed GEMM, epilogue adds positional embedding and scatters to token rows 1..g2 of each image
+    {
+        gemm::Params gp{Mp, W, p->kpatch, nullptr, p->x, w.positional_embedding, p->g2};
+        if ((rc = gemm_launch(p->tm_patches, p->tm_conv, gp, dt, EOE_EPI_PATCH_EMBED, st))) return rc;
+    }
+    // 3. class token + ln_pre (in place, fp32)
+    if ((rc = layernorm_dispatch(p->x, w.ln_pre_w, w.ln_pre_b, p->x, EOE_F32, M, W, w.class_embedding,
+                                 w.positional_embedding, L, st))) return rc;
+    // 4. transformer blocks
+    for (int i = 0; i < w.n_layers; ++i) {
+        const eoe_vit_layer& l = p->layers[i];
+        if ((rc = layernorm_dispatch(p->x, l.ln_1_w, l.ln_1_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
+        gemm::Params g1{M, 3 * W, W, l.in_proj_b, p->qkv, nullptr, 0};
+        if ((rc = gemm_launch(p->tm_h, p->tm_in[i], g1, dt, EOE_EPI_BIAS, st))) return rc;
+        if ((rc = attention_dispatch(p->qkv, p->h, B, L, w.heads, dt, st))) return rc;
+        gemm::Params g2{M, W, W, l.out_proj_b, p->x, nullptr, 0};
+        if ((rc = gemm_launch(p->tm_h, p->tm_out[i], g2, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
+        if ((rc = layernorm_dispatch(p->x, l.ln_2_w, l.ln_2_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
+        gemm::Params g3{M, 4 * W, W, l.c_fc_b, p->u, nullptr, 0};
+        if ((rc = gemm_launch(p->tm_h, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
+        gemm::Params g4{M, W, 4 * W, l.c_proj_b, p->x, nullptr, 0};
+        if ((rc = gemm_launch(p->tm_u, p->tm_proj[i], g4, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
+    }
+    // 5. ln_post + proj (+ zero-shot score head)
+    float* feats = feats_out ? feats_out : p->feats;
+    {
+        const int grid = (int)((B + kTailImgs - 1) / kTailImgs);
+        tail_kernel<<<grid, 256, kTailImgs * W * sizeof(float), st>>>(p->x, w.ln_post_w, w.ln_post_b, w.proj, feats, B, L,
+                                                                      W, w.embed_dim);
+        if ((rc = check_launch("tail_kernel"))) return rc;
+    }
+    if (text) {
+        if (K <= 0 || K > 64) return EOE_ERR_SHAPE;
+        if ((rc = clip_score_f32(feats, text, B, w.embed_dim, K, scale, scores_out, st))) return rc;
+    }
+    return EOE_OK;
+}
+
+// ------------------------------------------------------------------------------------------ building blocks (tests)
+extern "C" int eoe_gemm(const void* A, const void* Wt, const float* bias, void* out, int64_t M, int64_t N, int64_t K,
+                        int operand_dtype, int epilogue, const float* aux, int64_t aux_i, void* stream) {
+    if (!A || !Wt || !out) return EOE_ERR_ARG;
+    int rc = gemm_check(M, N, K, operand_dtype);
+    if (rc) return rc;
+    if (epilogue == EOE_EPI_PATCH_EMBED && (!aux || aux_i <= 0)) return EOE_ERR_ARG;
+    if ((uintptr_t)A % 16 != 0 || (uintptr_t)Wt % 16 != 0 || (uintptr_t)out % 16 != 0) return EOE_ERR_ALIGN;
+    CUtensorMap ta, tb;
+    if ((rc = make_tmap(&ta, A, M, K, gemm::BM, operand_dtype))) return rc;
+    if ((rc = make_tmap(&tb, Wt, N, K, gemm::BN, operand_dtype))) return rc;
+    gemm::Params p{M, N, K, bias, out, aux, aux_i};
+    return gemm_launch(ta, tb, p, operand_dtype, epilogue, (cudaStream_t)stream);
+}
+
+extern "C" int eoe_layernorm(const float* x, const float* w, const float* b, void* y, int out_dtype, int64_t M,
+                             int64_t width, void* stream) {
+    if (!x || !w || !b || !y || M <= 0 || width <= 0) return EOE_ERR_ARG;
+    return layernorm_dispatch(x, w, b, y, out_dtype, M, width, nullptr, nullptr, 1, (cudaStream_t)stream);
+}
+
+extern "C" int eoe_attention(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int operand_dtype,
+                             void* stream) {
+    if (!qkv || !out) return EOE_ERR_ARG;
+    return attention_dispatch(qkv, out, B, L, heads, operand_dtype, (cudaStream_t)stream);
+}

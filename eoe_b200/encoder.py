@@ -1,0 +1,175 @@
+"""CLIP ViT-B image encoder as a drop-in `nn.Module`: `model(imgs) -> features [B, 512]`, the contract the
+reference trainer relies on (`image_features = model(imgs)`, src/eoe/training/ad_trainer.py:429,507, with
+`model.forward = model.encode_image`, src/eoe/training/clip.py:33).
+
+Weights are loaded from the reference's own state_dict keys (`visual.conv1.weight`,
+`visual.transformer.resblocks.{i}.attn.in_proj_weight`, ...; clip_official/clip/model.py:395-402), either with
+or without the `visual.` prefix.  The forward pass is one C call (`eoe_vit_encode`) that launches the hand-written
+sm_100a kernels; torch only owns the buffers.  Inference only (the zero-shot path of configs 2/3).
+"""
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+
+def _strip(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    if any(k.startswith("visual.") for k in sd):
+        return {k[len("visual."):]: v for k, v in sd.items() if k.startswith("visual.")}
+    return dict(sd)
+
+
+class ClipImageEncoder(nn.Module):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", operand_dtype=torch.bfloat16,
+                 max_batch: int = 256, heads: Optional[int] = None, resolution: Optional[int] = None):
+        super().__init__()
+        if operand_dtype not in (torch.bfloat16, torch.float16):
+            raise L.EoeError("operand_dtype must be torch.bfloat16 or torch.float16")
+        sd = _strip(state_dict)
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise L.EoeError("ClipImageEncoder needs a CUDA device (no CPU fallback)")
+        conv = sd["conv1.weight"]
+        self.width, _, self.patch, _ = conv.shape
+        n_pos = sd["positional_embedding"].shape[0]
+        grid = int(round((n_pos - 1) ** 0.5))
+        self.resolution = resolution or grid * self.patch
+        self.heads = heads or self.width // 64
+        self.embed_dim = sd["proj"].shape[1]
+        self.n_layers = len({k.split(".")[2] for k in sd if k.startswith("transformer.resblocks.")})
+        self.operand_dtype = operand_dtype
+        self.max_batch = int(max_batch)
+        self.device_ = dev
+
+        def f32(t):
+            return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+        def op(t):
+            return t.detach().to(device=dev, dtype=torch.float32).to(operand_dtype).contiguous()
+
+        # device-resident parameters in kernel layout (buffers so .to()/state_dict do not disturb pointers)
+        self._keep = []
+        w = L.VitWeights()
+        w.patch, w.resolution, w.width, w.heads = self.patch, self.resolution, self.width, self.heads
+        w.n_layers, w.embed_dim, w.operand_dtype = self.n_layers, self.embed_dim, L.DTYPE_CODE[operand_dtype]
+
+        def put(t):
+            self._keep.append(t)
+            return t.data_ptr()
+
+        w.conv1_w = put(op(conv.reshape(self.width, -1)))
+        w.class_embedding = put(f32(sd["class_embedding"]))
+        w.positional_embedding = put(f32(sd["positional_embedding"]))
+        w.ln_pre_w, w.ln_pre_b = put(f32(sd["ln_pre.weight"])), put(f32(sd["ln_pre.bias"]))
+        w.ln_post_w, w.ln_post_b = put(f32(sd["ln_post.weight"])), put(f32(sd["ln_post.bias"]))
+        w.proj = put(f32(sd["proj"]))
+        layers = (L.VitLayer * self.n_layers)()
+        for i in range(self.n_layers):
+            p = f"transformer.resblocks.{i}."
+            l = layers[i]
+            l.ln_1_w, l.ln_1_b = put(f32(sd[p + "ln_1.weight"])), put(f32(sd[p + "ln_1.bias"]))
+            l.in_proj_w, l.in_proj_b = put(op(sd[p + "attn.in_proj_weight"])), put(f32(sd[p + "attn.in_proj_bias"]))
+            l.out_proj_w, l.out_proj_b = put(op(sd[p + "attn.out_proj.weight"])), put(f32(sd[p + "attn.out_proj.bias"]))
+            l.ln_2_w, l.ln_2_b = put(f32(sd[p + "ln_2.weight"])), put(f32(sd[p + "ln_2.bias"]))
+            l.c_fc_w, l.c_fc_b = put(op(sd[p + "mlp.c_fc.weight"])), put(f32(sd[p + "mlp.c_fc.bias"]))
+            l.c_proj_w, l.c_proj_b = put(op(sd[p + "mlp.c_proj.weight"])), put(f32(sd[p + "mlp.c_proj.bias"]))
+        w.layers_host = C.cast(layers, C.POINTER(L.VitLayer))
+        self._layers, self._w = layers, w
+
+        lib = L.lib()
+        nbytes = lib.eoe_vit_workspace_bytes(C.byref(w), self.max_batch)
+        if nbytes == 0:
+            raise L.EoeError("unsupported ViT configuration for eoe_vit_* (see include/eoe_b200.h)")
+        self._ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        off = (-self._ws.data_ptr()) % 1024
+        self._ws_ptr = self._ws.data_ptr() + off
+        plan = C.c_void_p()
+        L.check(lib.eoe_vit_plan_create(C.byref(w), self.max_batch, C.c_void_p(self._ws_ptr), nbytes, C.byref(plan)),
+                "eoe_vit_plan_create")
+        self._plan = plan
+
+    def __del__(self):
+        plan = getattr(self, "_plan", None)
+        if plan:
+            try:
+                L.lib().eoe_vit_plan_destroy(plan)
+            except Exception:
+                pass
+            self._plan = None
+
+    @property
+    def flops_per_image(self) -> float:
+        g2 = (self.resolution // self.patch) ** 2
+        Ls = g2 + 1
+        W = self.width
+        per_layer = 2 * Ls * W * 12 * W + 4 * Ls * Ls * W
+        return float(2 * g2 * 3 * self.patch ** 2 * W + self.n_layers * per_layer + 2 * W * self.embed_dim)
+
+    def _prep(self, imgs):
+        L.require_cuda(imgs)
+        if imgs.dim() != 4 or imgs.shape[1] != 3 or imgs.shape[2] != self.resolution or imgs.shape[3] != self.resolution:
+            raise L.EoeError(f"images must be [B,3,{self.resolution},{self.resolution}], got {tuple(imgs.shape)}")
+        return imgs.detach().to(torch.float32).contiguous()       # encode_image casts to the weight dtype (model.py:337)
+
+    @torch.no_grad()
+    def forward(self, imgs: torch.Tensor) -> torch.Tensor:
+        imgs = self._prep(imgs)
+        B = imgs.shape[0]
+        feats = torch.empty(B, self.embed_dim, dtype=torch.float32, device=imgs.device)
+        lib = L.lib()
+        for s in range(0, B, self.max_batch):
+            n = min(self.max_batch, B - s)
+            L.check(lib.eoe_vit_encode(self._plan, L.ptr(imgs[s:s + n]), n, L.ptr(feats[s:s + n]), None, 0, 100.0, None,
+                                       L.stream_ptr(imgs.device)), "eoe_vit_encode")
+        return feats
+
+    encode_image = forward
+
+    @torch.no_grad()
+    def score(self, imgs: torch.Tensor, center: torch.Tensor, scale: float = 100.0, out: Optional[torch.Tensor] = None
+              ) -> torch.Tensor:
+        """Fused zero-shot path: encoder + ADClipTrainer.compute_anomaly_score (clip.py:66-79) -> scores [B]."""
+        imgs = self._prep(imgs)
+        B = imgs.shape[0]
+        text = center.detach().to(device=imgs.device, dtype=torch.float32).contiguous()
+        scores = out if out is not None else torch.empty(B, dtype=torch.float32, device=imgs.device)
+        lib = L.lib()
+        for s in range(0, B, self.max_batch):
+            n = min(self.max_batch, B - s)
+            L.check(lib.eoe_vit_encode(self._plan, L.ptr(imgs[s:s + n]), n, None, L.ptr(text), text.shape[0],
+                                       float(scale), L.ptr(scores[s:s + n]), L.stream_ptr(imgs.device)),
+                    "eoe_vit_encode")
+        return scores
+
+
+# thin functional wrappers over the exported building blocks (parity-tested one by one)
+def gemm(A, W, bias=None, epilogue=L.EOE_EPI_BIAS, out=None, aux=None, aux_i=0):
+    L.require_cuda(A, W)
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    L.check(L.lib().eoe_gemm(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(out), M, N, K, L.DTYPE_CODE[A.dtype], epilogue,
+                             L.ptr(aux), int(aux_i), L.stream_ptr(A.device)), "eoe_gemm")
+    return out
+
+
+def layernorm(x, w, b, out_dtype=torch.bfloat16):
+    L.require_cuda(x)
+    M, width = x.shape
+    y = torch.empty(M, width, dtype=out_dtype, device=x.device)
+    L.check(L.lib().eoe_layernorm(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.DTYPE_CODE[out_dtype], M, width,
+                                  L.stream_ptr(x.device)), "eoe_layernorm")
+    return y
+
+
+def attention(qkv, B, Lseq, heads):
+    L.require_cuda(qkv)
+    width = qkv.shape[1] // 3
+    out = torch.empty(B * Lseq, width, dtype=qkv.dtype, device=qkv.device)
+    L.check(L.lib().eoe_attention(L.ptr(qkv), L.ptr(out), B, Lseq, heads, L.DTYPE_CODE[qkv.dtype],
+                                  L.stream_ptr(qkv.device)), "eoe_attention")
+    return out
