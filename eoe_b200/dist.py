@@ -1,0 +1,128 @@
+"""Multi-GPU plumbing (new functionality: the reference is single-GPU, src/eoe/main/__init__.py:110-114).
+
+One process per GPU, `torch.distributed` over NCCL/NVLink (gloo on CPU for the host-logic tests).  The hot path
+shards by rows (images / score rows are independent), so there are exactly two collectives:
+  * all_gather of per-rank score / label shards before the global AUC      -> `all_gather_rows`
+  * bucketed all-reduce of gradients, overlapped with backward               -> `GradBuckets`
+"""
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """torchrun contract: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT. Returns (rank, local_rank, world)."""
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if ws > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        be = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        kw = {}
+        if be == "nccl":
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=be, rank=rank, world_size=ws, **kw)
+    return rank, local, ws
+
+
+def shard_range(n: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block partition [lo, hi) of n rows: rank r owns rows r*ceil(n/W) ... (last shards may be short/empty)."""
+    per = (n + world_size - 1) // world_size
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def all_gather_rows(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenate 1-D (or [n, ...]) per-rank shards of possibly different length, in rank order, on every rank."""
+    rank, ws = world()
+    if ws == 1:
+        return t
+    t = t.contiguous()
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(ws)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    if mx == 0:
+        return t
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    out = torch.empty((ws * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    if all(s == mx for s in sizes):
+        return out
+    return torch.cat([out[r * mx: r * mx + sizes[r]] for r in range(ws)])
+
+
+class GradBuckets:
+    """Data-parallel gradient averaging: parameters' .grad are views into a few flat buckets (filled in reverse
+    parameter order, the order backward produces them); a bucket's all-reduce is launched asynchronously from a
+    post-accumulate-grad hook as soon as its last gradient has been written, so communication overlaps the rest of
+    backward.  `finish()` waits and scales by 1/world.  Use `zero_grad()` of this object (keeps the views)."""
+
+    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None):
+        self.group = group
+        self.rank, self.ws = world()
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets: List[torch.Tensor] = []
+        self._bucket_of = {}
+        self._pending: List[int] = []
+        self._counts: List[int] = []
+        self._works = []
+        cur, cur_bytes = [], 0
+        groups = []
+        for p in reversed(self.params):
+            nb = p.numel() * p.element_size()
+            if cur and (cur_bytes + nb > bucket_bytes or cur[0].dtype != p.dtype):
+                groups.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nb
+        if cur:
+            groups.append(cur)
+        for bi, ps in enumerate(groups):
+            flat = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
+            off = 0
+            for p in ps:
+                p.grad = flat[off: off + p.numel()].view_as(p)
+                off += p.numel()
+                self._bucket_of[p] = bi
+                if self.ws > 1:
+                    p.register_post_accumulate_grad_hook(self._hook)
+            self.buckets.append(flat)
+            self._counts.append(len(ps))
+        self._pending = list(self._counts)
+
+    def _hook(self, p):
+        bi = self._bucket_of[p]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._works.append(dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Call after loss.backward(): wait for the in-flight all-reduces, average, re-arm."""
+        if self.ws > 1:
+            for bi, left in enumerate(self._pending):          # parameters that received no gradient this step
+                if left != 0:
+                    self._works.append(dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            for w in self._works:
+                w.wait()
+            for b in self.buckets:
+                b.div_(self.ws)
+        self._works = []
+        self._pending = list(self._counts)
+
+    def zero_grad(self):
+        for b in self.buckets:
+            b.zero_()

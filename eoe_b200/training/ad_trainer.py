@@ -1,0 +1,141 @@
+"""Re-hosted trainer runtime for the hot path (reference: src/eoe/training/ad_trainer.py).
+
+Kept from the reference: the three abstract hooks (ad_trainer.py:624-662) with identical names / arguments /
+kwargs (`inputs=imgs, nominal_label=...`, :430,434-436,508), the batch loop of `train_cls` (:406-444), the
+NaN guard (:447-449, `NanGradientsError`), the per-epoch training AUC (:452-455), `eval_cls` (:498-527) and
+its `(ROC, PRC)` result, optimiser / scheduler choice (:379-384).
+
+Changed for B200: scores and labels stay on the device (the reference does `.cpu()` per batch, :436-440,
+509-511); one device AUC per epoch (eoe_b200.metrics, bit-exact with sklearn) instead of sklearn on the host;
+one host sync per epoch instead of three per batch; optional data-parallel training / sharded evaluation over
+torch.distributed (new; see eoe_b200.dist).  Out of scope: datasets, transforms, logging,
+snapshots -- `train_cls` / `eval_cls` take a loader yielding the reference's batch triple `(imgs, lbls, idcs)`
+(datasets/bases.py:591-597) instead of a dataset object.
+"""
+from abc import ABC, abstractmethod
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import dist as edist
+from .. import metrics
+
+
+class NanGradientsError(RuntimeError):
+    """ad_trainer.py:23-24: raised when an epoch produced NaN anomaly scores."""
+
+
+class ADTrainer(ABC):
+    AD_MODES = ("one_vs_rest", "leave_one_out")
+
+    def __init__(self, model: Optional[torch.nn.Module], epochs: int = 0, lr: float = 1e-3, wdk: float = 0.0,
+                 milestones: Sequence[int] = (), batch_size: int = 128, ad_mode: str = "one_vs_rest",
+                 device="cuda", data_parallel: bool = False, sgd: bool = False):
+        if ad_mode not in self.AD_MODES:
+            raise NotImplementedError(f"AD mode {ad_mode} unknown. Known modes are {self.AD_MODES}.")
+        self.model = model
+        self.epochs, self.lr, self.wdk, self.milestones = epochs, lr, wdk, list(milestones)
+        self.batch_size, self.ad_mode = batch_size, ad_mode
+        self.device = torch.device(device)
+        self.center = None
+        self.data_parallel = data_parallel
+        self.sgd = sgd                       # the reference uses SGD(nesterov) iff the model is CLIP (:379-383)
+        self._score_cache = None
+
+    # ---------------------------------------------------------------- hooks (ad_trainer.py:624-662)
+    @abstractmethod
+    def prepare_metric(self, cstr: str, loader, model: torch.nn.Module, seed: int, **kwargs) -> torch.Tensor:
+        pass
+
+    @abstractmethod
+    def compute_anomaly_score(self, features: torch.Tensor, center: torch.Tensor, **kwargs) -> torch.Tensor:
+        pass
+
+    @abstractmethod
+    def loss(self, features: torch.Tensor, labels: torch.Tensor, center: torch.Tensor, **kwargs) -> torch.Tensor:
+        pass
+
+    # scores computed by the fused loss kernel are handed to the compute_anomaly_score call that follows on
+    # the same feature tensor (ad_trainer.py:430-436 calls loss, then compute_anomaly_score, on `image_features`)
+    def _remember_scores(self, features, scores, tag=None):
+        self._score_cache = (features.data_ptr(), features._version, tuple(features.shape), tag, scores)
+
+    def _cached_scores(self, features, tag=None):
+        c = self._score_cache
+        if c is not None and c[0] == features.data_ptr() and c[1] == features._version and \
+                c[2] == tuple(features.shape) and c[3] == tag:
+            self._score_cache = None
+            return c[4]
+        return None
+
+    # ---------------------------------------------------------------- training (ad_trainer.py:356-471)
+    def train_cls(self, model: torch.nn.Module, loader: Iterable, nominal_label: int = 0, clsstr: str = "",
+                  seed: int = 0, epochs: Optional[int] = None) -> Tuple[torch.nn.Module, Optional[metrics.ROC], List[float]]:
+        model = model.to(self.device).train()
+        epochs = self.epochs if epochs is None else epochs
+        params = [p for p in model.parameters() if p.requires_grad]
+        if self.sgd:
+            opt = torch.optim.SGD(params, lr=self.lr, weight_decay=self.wdk, momentum=0.9, nesterov=True)
+        else:
+            opt = torch.optim.Adam(params, lr=self.lr, weight_decay=self.wdk, amsgrad=False)
+        sched = torch.optim.lr_scheduler.MultiStepLR(opt, self.milestones, 0.1)
+        _, ws = edist.world()
+        buckets = edist.GradBuckets(params) if (self.data_parallel and ws > 1) else None
+        center = self.center = self.prepare_metric(clsstr, loader, model, seed)
+        cls_roc, losses = None, []
+        for ep in range(epochs):
+            ep_labels, ep_ascores, ep_losses = [], [], []
+            for imgs, lbls, _idcs in loader:
+                imgs = imgs.to(self.device, non_blocking=True)
+                lbls = lbls.to(self.device, non_blocking=True)
+                if buckets is not None:
+                    buckets.zero_grad()
+                else:
+                    opt.zero_grad()
+                image_features = model(imgs)
+                loss = self.loss(image_features, lbls, center, inputs=imgs, nominal_label=nominal_label)
+                loss.backward()
+                if buckets is not None:
+                    buckets.finish()
+                opt.step()
+                anomaly_scores = self.compute_anomaly_score(image_features, center, inputs=imgs, nominal_label=nominal_label)
+                ep_labels.append(lbls.detach())
+                ep_ascores.append(anomaly_scores.detach().reshape(-1))
+                ep_losses.append(loss.detach())
+            ep_labels, ep_ascores = torch.cat(ep_labels), torch.cat(ep_ascores)
+            if ws > 1 and self.data_parallel:
+                ep_labels, ep_ascores = edist.all_gather_rows(ep_labels), edist.all_gather_rows(ep_ascores)
+            # one host sync per epoch: NaN flag, class presence and the mean loss travel together
+            flags = torch.stack([ep_ascores.isnan().any().float(), (ep_labels == 1).any().float(),
+                                 torch.stack(ep_losses).float().mean()]).cpu()
+            if flags[0] > 0:
+                raise NanGradientsError()                                 # ad_trainer.py:448-449
+            losses.append(float(flags[2]))
+            if flags[1] > 0:                                              # ad_trainer.py:452-455
+                roc, _ = metrics.roc_curve_auc(ep_ascores, ep_labels)
+                cls_roc = roc if roc is not None else cls_roc
+            sched.step()
+        return model.eval(), cls_roc, losses
+
+    # ---------------------------------------------------------------- evaluation (ad_trainer.py:473-550)
+    @torch.no_grad()
+    def eval_cls(self, model: torch.nn.Module, loader: Iterable, nominal_label: int = 0, clsstr: str = "",
+                 gather: bool = True) -> Tuple[Optional[metrics.ROC], Optional[metrics.PRC]]:
+        """`loader` yields this rank's shard of the test set; with torch.distributed initialised and gather=True the
+        per-rank score / label shards are all-gathered (rank order == index order for eoe_b200.dist.shard_range)
+        and every rank computes the global ROC / PRC."""
+        model = model.to(self.device).eval() if isinstance(model, torch.nn.Module) else model
+        center = self.center
+        ep_labels, ep_ascores = [], []
+        for imgs, lbls, _idcs in loader:
+            imgs = imgs.to(self.device, non_blocking=True)
+            image_features = model(imgs)
+            anomaly_scores = self.compute_anomaly_score(image_features, center, inputs=imgs, nominal_label=nominal_label)
+            ep_labels.append(lbls.to(self.device, non_blocking=True))
+            ep_ascores.append(anomaly_scores.reshape(-1))
+        ep_labels, ep_ascores = torch.cat(ep_labels), torch.cat(ep_ascores)
+        if gather:
+            ep_labels, ep_ascores = edist.all_gather_rows(ep_labels), edist.all_gather_rows(ep_ascores)
+        self.last_eval = (ep_labels, ep_ascores)
+        # ad_trainer.py:516-527: both classes must be present, labels < 0 are dropped, else (None, None)
+        return metrics.roc_curve_auc(ep_ascores, ep_labels, with_prc=True, ignore_negative_labels=True)
