@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark: CLIP ViT-B/16 zero-shot anomaly-detection scoring (BASELINE.json configs[2]) in images/s.
+
+One "step" = one batch of 224x224 images per GPU through the hot path: patchify -> ViT-B/16 encoder (tcgen05 GEMMs,
+attention, LayerNorm) -> fused cosine-softmax anomaly score.  The timed region covers K steps, the score all-gather
+(N > 1) and the global device ROC-AUC over every score produced.  See DESIGN.md "Measurement".
+
+    python bench.py --gpus 1 --steps 8 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference          # the reference algorithm's CPU port on the host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "clip_zero_shot_ad_images_per_s"
+UNIT = "images/s"
+GFLOP_PER_IMG = {16: 35.12690688, 32: 8.81762304}      # 2*MAC over GEMMs + QK^T + PV
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/eoe_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw))
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def cpu_port_images_per_s(patch, K, n_img, threads):
+    """The reference algorithm on the host cores: oracle port of VisualTransformer.forward + CLIP score head (fp32)."""
+    from oracle import heads as oh
+    from oracle import vit as ovit
+    torch.set_num_threads(threads)
+    sd = ovit.synth_state_dict(patch, seed=0)
+    g = torch.Generator().manual_seed(1)
+    imgs = torch.randn(n_img, 3, 224, 224, generator=g)
+    text = torch.nn.functional.normalize(torch.randn(K, 512, generator=g), dim=-1).numpy()
+    chunk = 32
+    ovit.encode_image(sd, imgs[:min(4, n_img)])          # warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    for s in range(0, n_img, chunk):
+        f = ovit.encode_image(sd, imgs[s:s + chunk])
+        oh.clip_score(f.numpy(), text)
+    dt = time.perf_counter() - t0
+    return n_img / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_img = args.ref_images
+    t_all, n_all = 0.0, 0
+    for _ in range(args.warmup):
+        cpu_port_images_per_s(args.patch, args.prompts, min(n_img, 8), threads)
+    for _ in range(args.steps):
+        ips, dt = cpu_port_images_per_s(args.patch, args.prompts, n_img, threads)
+        t_all += dt
+        n_all += n_img
+    val = n_all / t_all
+    sample = f"{n_img} images of the same workload per step (oracle port of model.py:219-236 + clip.py:66-79, fp32)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"clip_vitb{args.patch}_zero_shot_ad_224px_{args.prompts}prompts", "batch_per_gpu": n_img},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def side_metrics(dev, pk):
+    """HSC head GB/s and AUC ms per 1M scores (the other two figures of BASELINE.json's metric), outside the timed region."""
+    from eoe_b200 import metrics, ops
+    out = {}
+    n, d = 1 << 21, 256
+    z = 0.05 * torch.randn(n, d, device=dev)
+    y = torch.randint(0, 2, (n,), device=dev)
+    for _ in range(3):
+        ops.hsc_fused(z, y, 0)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        ops.hsc_fused(z, y, 0)
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    bytes_ = 2 * n * d * 4 + 12 * n + 4
+    out["hsc_head"] = {"gbs": bytes_ / ms / 1e6, "frac_hbm": bytes_ / ms / 1e6 / pk["hbm"], "n": n, "d": d, "dtype": "f32",
+                       "note": "fused loss+grad+score, 2.1 GB working set > L2"}
+    x = torch.randn(1 << 26, device=dev)
+    yb = torch.randint(0, 2, (1 << 26,), device=dev)
+    for _ in range(3):
+        ops.bce_fused(x, yb, 0)
+    a.record()
+    for _ in range(10):
+        ops.bce_fused(x, yb, 0)
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    out["bce_head"] = {"gbs": 20 * (1 << 26) / ms / 1e6, "frac_hbm": 20 * (1 << 26) / ms / 1e6 / pk["hbm"], "n": 1 << 26}
+    del x, yb, z, y
+    n = 1_000_000
+    s = 1 - torch.exp(-torch.randn(n, device=dev).abs())
+    yl = (torch.rand(n, device=dev) < 0.5).long()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ws = metrics.AucWorkspace()
+    ts = []
+    for i in range(8):
+        flush.zero_()
+        a.record()
+        metrics.roc_auc_device(s, yl, workspace=ws)
+        b.record(); torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(a.elapsed_time(b))
+    out["auc"] = {"ms_per_1m_scores": statistics.median(ts), "n": n, "note": "device radix sort + scans, L2 flushed"}
+    return out
+
+
+def run_ours(args):
+    from eoe_b200 import _lib, dist as edist, metrics
+    from eoe_b200.encoder import ClipImageEncoder
+    from eoe_b200.synth import random_vit_state_dict
+    import torch.distributed as tdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the eoe_b200 hot path has no CPU fallback")
+    rank, local, ws = edist.init_from_env()
+    if ws != args.gpus:
+        if ws == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    dev = torch.device("cuda", local)
+    pk = peaks()
+    B, K, S, W, P = args.batch, args.prompts, args.steps, args.warmup, args.patch
+    op_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+
+    sd = random_vit_state_dict(P, seed=0)
+    enc = ClipImageEncoder(sd, device=dev, operand_dtype=op_dtype, max_batch=B)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    imgs = [torch.randn(B, 3, 224, 224, device=dev, generator=g) for _ in range(2)]     # 2 x 308 MB at B=512: > L2
+    text = torch.nn.functional.normalize(torch.randn(K, 512, device=dev, generator=g), dim=-1)
+    SW = max(S, W)
+    labels = (torch.rand(SW * B, device=dev, generator=g) < 0.9).long()                  # 90 % anomalous
+    scores = torch.empty(SW * B, dtype=torch.float32, device=dev)
+    auc_ws = metrics.AucWorkspace().ensure(SW * B * ws, dev)
+
+    def job(n_steps, sc, lb):
+        for k in range(n_steps):
+            enc.score(imgs[k & 1], text, out=sc[k * B:(k + 1) * B])
+        sc, lb = sc[:n_steps * B], lb[:n_steps * B]
+        s_all, l_all = (edist.all_gather_rows(sc), edist.all_gather_rows(lb)) if ws > 1 else (sc, lb)
+        return metrics.roc_auc_device(s_all, l_all, workspace=auc_ws)
+
+    def sync():
+        if ws > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    job(W, scores, labels)
+    sync()
+
+    # ---- timed region: device-resident inputs, GEMM launches bracketed by events for the roofline
+    enc.profile(True)
+    launches0 = _lib.lib().eoe_launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    auc_out, auc_info, _ = job(S, scores, labels)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = _lib.lib().eoe_launch_count() - launches0
+    prof = enc.profile_read()
+    enc.profile(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if ws > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = ws * S * B / (ms_max / 1e3)
+    auc_val = float(auc_out[0].item())
+
+    # ---- e2e: the same job through the public API with HOST (pinned) image batches and host score reads
+    host = [torch.randn(B, 3, 224, 224).pin_memory() for _ in range(2)]
+    dbuf = [torch.empty(B, 3, 224, 224, device=dev) for _ in range(2)]
+    h_scores = torch.empty(S, B, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+
+    def e2e_job(n_steps):
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        with torch.cuda.stream(copy_stream):
+            dbuf[0].copy_(host[0], non_blocking=True)
+            ready[0].record(copy_stream)
+        for k in range(n_steps):
+            cur, nxt = k & 1, (k + 1) & 1
+            if k + 1 < n_steps:
+                with torch.cuda.stream(copy_stream):
+                    if k >= 1:
+                        copy_stream.wait_event(freed[nxt])
+                    dbuf[nxt].copy_(host[nxt], non_blocking=True)       # H2D of step k+1 overlaps compute of step k
+                    ready[nxt].record(copy_stream)
+            main.wait_event(ready[cur])
+            sc = scores[k * B:(k + 1) * B]
+            enc.score(dbuf[cur], text, out=sc)
+            freed[cur].record(main)
+            h_scores[k % S].copy_(sc, non_blocking=True)                # D2H of the step's result
+        s_all, l_all = (edist.all_gather_rows(scores[:n_steps * B]), edist.all_gather_rows(labels[:n_steps * B])) \
+            if ws > 1 else (scores[:n_steps * B], labels[:n_steps * B])
+        out, _, _ = metrics.roc_auc_device(s_all, l_all, workspace=auc_ws)
+        return out.cpu()                                                 # the AUC is read on the host (sync)
+
+    e2e_job(min(W, S))
+    sync()
+    t0 = time.perf_counter()
+    e2e_job(S)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if ws > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    e2e_val = ws * S * B / float(t.item())
+
+    if rank != 0:
+        if ws > 1:
+            tdist.barrier()
+            tdist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM: all launches of the timed region)
+    g_ms = sum(v[0] for v in prof.values())
+    g_fl = sum(v[2] for v in prof.values())
+    g_n = sum(v[1] for v in prof.values())
+    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {
+        "bound": "tensor", "kernel": "eoe::gemm::gemm_kernel (tcgen05, all 49 GEMM launches per step)",
+        "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
+        "traffic": traffic, "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
+        "launches": g_n, "gemm_ms_per_step": g_ms / S, "gemm_share_of_step": g_ms / ms,
+        "per_kind_tflops": {k: (v[2] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else None) for k, v in prof.items()},
+        "encoder_tensor_frac": value / ws * GFLOP_PER_IMG[P] * 1e9 / 1e12 / pk["tf_sust"],
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": S, "warmup": W,
+        "ms_per_step": ms_max / S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"clip_vitb{P}_zero_shot_ad_224px_{K}prompts", "batch_per_gpu": B, "global_batch": B * ws,
+                   "images_scored": ws * S * B, "weights": "random-init ViT-B/%d visual tower (reference state_dict layout)" % P,
+                   "l2": "inputs exceed L2 (2 alternating %.0f MB image batches per GPU)" % (B * 3 * 224 * 224 * 4 / 1e6),
+                   "parallelism": f"dp{ws}: images sharded by rank, all_gather(scores, labels) -> global device AUC",
+                   "timed_region": "K x (patchify + ViT encoder + fused score head) + all-gather + ROC-AUC"},
+        "roofline": roofline,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4,
+                "note": "pinned fp32 host batches, double-buffered H2D on a copy stream, scores + AUC read on host"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "auc": auc_val,
+    }
+    if ws == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_img = args.ref_images
+        ips, dt = cpu_port_images_per_s(P, K, n_img, threads)
+        line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{n_img} images of the same workload, {dt:.1f} s (oracle port, fp32, torch CPU)"}
+    if not args.no_side:
+        line["side_metrics"] = side_metrics(dev, pk)
+    print(json.dumps(line), flush=True)
+    if ws > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
+    ap.add_argument("--patch", type=int, default=16, choices=[16, 32])
+    ap.add_argument("--prompts", type=int, default=30)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16"])
+    ap.add_argument("--ref-images", type=int, default=64, help="images per step of the CPU port (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3            # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

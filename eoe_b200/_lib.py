@@ -49,6 +49,7 @@ SIGNATURES = {
     "eoe_abi_version": (_I, []),
     "eoe_strerror": (C.c_char_p, [_I]),
     "eoe_last_cuda_error": (C.c_char_p, []),
+    "eoe_launch_count": (C.c_longlong, []),
     "eoe_hsc_fwd_bwd": (_I, [_P, _I, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P]),
     "eoe_hsc_score": (_I, [_P, _I, _I64, _I64, _P, _P]),
     "eoe_bce_fwd_bwd": (_I, [_P, _I, _P, _I64, _I64, _P, _P, _P, _P, _P]),
@@ -61,6 +62,8 @@ SIGNATURES = {
     "eoe_vit_plan_create": (_I, [C.POINTER(VitWeights), _I64, _P, _SZ, C.POINTER(_P)]),
     "eoe_vit_plan_destroy": (None, [_P]),
     "eoe_vit_encode": (_I, [_P, _P, _I64, _P, _P, _I64, _F, _P, _P]),
+    "eoe_vit_profile_enable": (_I, [_P, _I]),
+    "eoe_vit_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(C.c_double)]),
     "eoe_gemm": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _I, _I, _P, _I64, _P]),
     "eoe_layernorm": (_I, [_P, _P, _P, _P, _I, _I64, _I64, _P]),
     "eoe_attention": (_I, [_P, _P, _I64, _I64, _I64, _I, _P]),

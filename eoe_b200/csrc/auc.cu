@@ -609,7 +609,7 @@ static int auc_run(const void* scores, const int64_t* labels, int64_t n, int fla
         pairwise_tree_kernel<<<1, 1024, 0, st>>>(&c->n_distinct, 0, nodes, c, auc_out + 1, 1);
     }
     if (info_out) auc_info_kernel<<<1, 1, 0, st>>>(c, info_out);
-    return check_launch("auc pipeline");
+    return check_launch("auc pipeline", 10 + ((flags & EOE_AUC_WITH_PRC) ? 3 : 0) + (info_out ? 1 : 0));
 }
 
 }  // namespace eoe

@@ -2,6 +2,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace eoe {
@@ -12,18 +14,23 @@ void set_cuda_error(cudaError_t e, const char* where) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
-int check_launch(const char* where) {
+static std::atomic<long long> g_launches{0};
+
+int check_launch(const char* where, int n_launched) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_cuda_error(e, where);
         return EOE_ERR_CUDA;
     }
+    g_launches.fetch_add(n_launched, std::memory_order_relaxed);
     return EOE_OK;
 }
 
 }  // namespace eoe
 
 extern "C" int eoe_abi_version(void) { return EOE_ABI_VERSION; }
+
+extern "C" long long eoe_launch_count(void) { return eoe::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* eoe_last_cuda_error(void) { return eoe::g_cuda_err; }
 

@@ -13,7 +13,7 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in mult
 constexpr unsigned kFullMask = 0xffffffffu;
 
 void set_cuda_error(cudaError_t e, const char* where);
-int check_launch(const char* where);
+int check_launch(const char* where, int n_launched = 1);   // also feeds eoe_launch_count()
 
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);

@@ -8,6 +8,7 @@
 // Token layout is [B, L, width] (batch major), residual stream fp32, GEMM operands bf16/fp16.
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "gemm_sm100.cuh"
 
@@ -441,7 +442,31 @@ struct eoe_vit_plan {
     float* feats;        // [B, embed]
     CUtensorMap tm_patches, tm_h, tm_u, tm_conv;
     CUtensorMap *tm_in, *tm_out, *tm_fc, *tm_proj;     // per layer
+    // optional instrumentation (eoe_vit_profile_*): CUDA event pairs around every GEMM launch
+    bool profile;
+    struct Span { cudaEvent_t a, b; int kind; double flops; };
+    std::vector<Span> spans;
+    size_t spans_used;
 };
+
+enum { KIND_PATCH = 0, KIND_QKV = 1, KIND_OUT = 2, KIND_FC = 3, KIND_PROJ = 4 };
+
+static int timed_gemm(eoe_vit_plan* p, int kind, const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& gp,
+                      int dt, int epi, cudaStream_t st) {
+    if (!p->profile) return gemm_launch(ta, tb, gp, dt, epi, st);
+    if (p->spans_used == p->spans.size()) {
+        eoe_vit_plan::Span s;
+        if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return EOE_ERR_CUDA;
+        p->spans.push_back(s);
+    }
+    eoe_vit_plan::Span& s = p->spans[p->spans_used++];
+    s.kind = kind;
+    s.flops = 2.0 * (double)gp.M * (double)gp.N * (double)gp.K;
+    cudaEventRecord(s.a, st);
+    int rc = gemm_launch(ta, tb, gp, dt, epi, st);
+    cudaEventRecord(s.b, st);
+    return rc;
+}
 
 static size_t rup(size_t x) { return (x + 1023) / 1024 * 1024; }
 
@@ -494,6 +519,8 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     for (int i = 0; i < w->n_layers; ++i) p->layers[i] = w->layers_host[i];
     p->w.layers_host = p->layers;
     p->max_batch = max_batch;
+    p->profile = false;
+    p->spans_used = 0;
     const int g = w->resolution / w->patch;
     p->g2 = g * g;
     p->L = p->g2 + 1;
@@ -530,6 +557,7 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
 
 extern "C" void eoe_vit_plan_destroy(eoe_vit_plan* p) {
     if (!p) return;
+    for (auto& s : p->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     delete[] p->layers;
     delete[] p->tm_in;
     delete[] p->tm_out;
@@ -559,7 +587,7 @@ extern "C" int eoe_vit_encode(eoe_vit_plan* p, const float* imgs, int64_t B, flo
     // 2. patch-embed GEMM, epilogue adds positional embedding and scatters to token rows 1..g2 of each image
     {
         gemm::Params gp{Mp, W, p->kpatch, nullptr, p->x, w.positional_embedding, p->g2};
-        if ((rc = gemm_launch(p->tm_patches, p->tm_conv, gp, dt, EOE_EPI_PATCH_EMBED, st))) return rc;
+        if ((rc = timed_gemm(p, KIND_PATCH, p->tm_patches, p->tm_conv, gp, dt, EOE_EPI_PATCH_EMBED, st))) return rc;
     }
     // 3. class token + ln_pre (in place, fp32)
     if ((rc = layernorm_dispatch(p->x, w.ln_pre_w, w.ln_pre_b, p->x, EOE_F32, M, W, w.class_embedding,
@@ -569,15 +597,15 @@ extern "C" int eoe_vit_encode(eoe_vit_plan* p, const float* imgs, int64_t B, flo
         const eoe_vit_layer& l = p->layers[i];
         if ((rc = layernorm_dispatch(p->x, l.ln_1_w, l.ln_1_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
         gemm::Params g1{M, 3 * W, W, l.in_proj_b, p->qkv, nullptr, 0};
-        if ((rc = gemm_launch(p->tm_h, p->tm_in[i], g1, dt, EOE_EPI_BIAS, st))) return rc;
+        if ((rc = timed_gemm(p, KIND_QKV, p->tm_h, p->tm_in[i], g1, dt, EOE_EPI_BIAS, st))) return rc;
         if ((rc = attention_dispatch(p->qkv, p->h, B, L, w.heads, dt, st))) return rc;
         gemm::Params g2{M, W, W, l.out_proj_b, p->x, nullptr, 0};
-        if ((rc = gemm_launch(p->tm_h, p->tm_out[i], g2, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
+        if ((rc = timed_gemm(p, KIND_OUT, p->tm_h, p->tm_out[i], g2, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
         if ((rc = layernorm_dispatch(p->x, l.ln_2_w, l.ln_2_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
         gemm::Params g3{M, 4 * W, W, l.c_fc_b, p->u, nullptr, 0};
-        if ((rc = gemm_launch(p->tm_h, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
+        if ((rc = timed_gemm(p, KIND_FC, p->tm_h, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
         gemm::Params g4{M, W, 4 * W, l.c_proj_b, p->x, nullptr, 0};
-        if ((rc = gemm_launch(p->tm_u, p->tm_proj[i], g4, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
+        if ((rc = timed_gemm(p, KIND_PROJ, p->tm_u, p->tm_proj[i], g4, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
     }
     // 5. ln_post + proj (+ zero-shot score head)
     float* feats = feats_out ? feats_out : p->feats;
@@ -591,6 +619,30 @@ extern "C" int eoe_vit_encode(eoe_vit_plan* p, const float* imgs, int64_t B, flo
         if (K <= 0 || K > 64) return EOE_ERR_SHAPE;
         if ((rc = clip_score_f32(feats, text, B, w.embed_dim, K, scale, scores_out, st))) return rc;
     }
+    return EOE_OK;
+}
+
+extern "C" int eoe_vit_profile_enable(eoe_vit_plan* p, int enable) {
+    if (!p) return EOE_ERR_ARG;
+    p->profile = enable != 0;
+    p->spans_used = 0;
+    return EOE_OK;
+}
+
+extern "C" int eoe_vit_profile_read(eoe_vit_plan* p, double* ms_out, int64_t* launches_out, double* flops_out) {
+    if (!p || !ms_out || !launches_out || !flops_out) return EOE_ERR_ARG;
+    for (int k = 0; k < 5; ++k) { ms_out[k] = 0.0; launches_out[k] = 0; flops_out[k] = 0.0; }
+    for (size_t i = 0; i < p->spans_used; ++i) {
+        eoe_vit_plan::Span& s = p->spans[i];
+        cudaError_t e = cudaEventSynchronize(s.b);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.a, s.b);
+        if (e != cudaSuccess) { set_cuda_error(e, "eoe_vit_profile_read"); return EOE_ERR_CUDA; }
+        ms_out[s.kind] += ms;
+        launches_out[s.kind] += 1;
+        flops_out[s.kind] += s.flops;
+    }
+    p->spans_used = 0;
     return EOE_OK;
 }
 

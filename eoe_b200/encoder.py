@@ -128,6 +128,18 @@ class ClipImageEncoder(nn.Module):
 
     encode_image = forward
 
+    GEMM_KINDS = ("patch_embed", "qkv", "out_proj", "c_fc", "c_proj")
+
+    def profile(self, enable: bool):
+        """Bracket every GEMM launch of subsequent forward calls with CUDA events (see eoe_vit_profile_enable)."""
+        L.check(L.lib().eoe_vit_profile_enable(self._plan, int(enable)), "eoe_vit_profile_enable")
+
+    def profile_read(self):
+        """{kind: (ms, launches, flops)} accumulated since the last read; synchronises on the recorded events."""
+        ms, n, fl = (C.c_double * 5)(), (C.c_int64 * 5)(), (C.c_double * 5)()
+        L.check(L.lib().eoe_vit_profile_read(self._plan, ms, n, fl), "eoe_vit_profile_read")
+        return {k: (ms[i], n[i], fl[i]) for i, k in enumerate(self.GEMM_KINDS)}
+
     @torch.no_grad()
     def score(self, imgs: torch.Tensor, center: torch.Tensor, scale: float = 100.0, out: Optional[torch.Tensor] = None
               ) -> torch.Tensor:

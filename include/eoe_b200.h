@@ -47,6 +47,8 @@ int eoe_abi_version(void);
 const char* eoe_strerror(int code);
 /* last CUDA error string recorded by this library on the calling thread ("" if none) */
 const char* eoe_last_cuda_error(void);
+/* number of CUDA kernels this library has launched in this process so far (bench.py's `gpu_launches`) */
+long long eoe_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Loss / score heads.  `head_ws` is a zero-initialised device buffer of EOE_HEAD_WS_BYTES bytes
@@ -173,9 +175,16 @@ void eoe_vit_plan_destroy(eoe_vit_plan* plan);
 int eoe_vit_encode(eoe_vit_plan* plan, const float* imgs, int64_t B, float* feats_out,
                    const float* text, int64_t K, float scale, float* scores_out, void* stream);
 
+/* Optional instrumentation for roofline reporting: while enabled, eoe_vit_encode brackets every GEMM launch with a
+ * CUDA event pair on `stream` (no synchronisation). eoe_vit_profile_read waits for the recorded events and returns,
+ * per GEMM kind (0 patch-embed, 1 qkv, 2 out-proj, 3 c_fc, 4 c_proj), accumulated milliseconds, launches and
+ * algorithmic FLOPs (2*M*N*K) since the last read. HOST pointers to 5 entries each. */
+int eoe_vit_profile_enable(eoe_vit_plan* plan, int enable);
+int eoe_vit_profile_read(eoe_vit_plan* plan, double* ms_out_host, int64_t* launches_out_host, double* flops_out_host);
+
 /* Building blocks of the encoder, exported so that each kernel is parity-tested through the ABI. */
 enum { EOE_EPI_BIAS = 0, EOE_EPI_BIAS_QUICKGELU = 1, EOE_EPI_BIAS_RESIDUAL_F32 = 2, EOE_EPI_PATCH_EMBED = 3 };
-/* out = epilogue(A[M,K] @ W[N,K]^T): tcgen05 GEMM, A/W operand dtype (BF16/F16), K % 64 == 0, N % 64 == 0.
+/* out = epilogue(A[M,K] @ W[N,K]^T): tcgen05 GEMM, A/W operand dtype (BF16/F16), K % 64 == 0, N % 256 == 0.
  *   EOE_EPI_BIAS / _QUICKGELU: out [M,N] operand dtype;  _RESIDUAL_F32: out [M,N] fp32 += (in place);
  *   _PATCH_EMBED: out fp32 row (m/g2)*(g2+1)+1+(m%g2) = acc + pos_emb[1+m%g2] (aux = pos_emb, aux_i = g2). */
 int eoe_gemm(const void* A, const void* W, const float* bias, void* out, int64_t M, int64_t N, int64_t K,

@@ -1,0 +1,73 @@
+"""CPU: libeoe_b200.so builds, loads and exports every symbol include/eoe_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "eoe_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(eoe_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from eoe_b200 import build
+    path = build.build()
+    return ctypes.CDLL(path)
+
+
+def test_header_declares_the_expected_surface():
+    names = _declared()
+    for must in ("eoe_hsc_fwd_bwd", "eoe_hsc_score", "eoe_bce_fwd_bwd", "eoe_clip_score", "eoe_clip_oe_loss_fwd_bwd",
+                 "eoe_auc", "eoe_auc_workspace_bytes", "eoe_vit_encode", "eoe_vit_plan_create", "eoe_gemm",
+                 "eoe_attention", "eoe_layernorm", "eoe_strerror"):
+        assert must in names
+
+
+def test_every_declared_symbol_is_exported(lib):
+    missing = [n for n in _declared() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_header_and_loads():
+    from eoe_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+    l = _lib.lib()
+    assert not _lib.MISSING
+    assert l.eoe_abi_version() == 1
+    assert l.eoe_strerror(0) == b"ok" and b"dtype" in l.eoe_strerror(-2)
+    assert l.eoe_auc_workspace_bytes(1000) > 12 * 1000
+    assert l.eoe_auc_workspace_bytes(0) == 0
+
+
+def test_argument_validation_without_gpu(lib):
+    """Entry points reject bad arguments before touching the device."""
+    lib.eoe_hsc_score.restype = ctypes.c_int
+    assert lib.eoe_hsc_score(None, 0, ctypes.c_int64(4), ctypes.c_int64(8), None, None) == -1
+    lib.eoe_auc.restype = ctypes.c_int
+    assert lib.eoe_auc(None, 0, None, ctypes.c_int64(0), 0, None, ctypes.c_size_t(0), None, None, None, None, None, None,
+                       None, None) == -1
+
+
+def test_no_cpu_fallback_in_product_path():
+    import torch
+    from eoe_b200 import _lib, ops
+    with pytest.raises(_lib.EoeError):
+        ops.hsc_score(torch.zeros(4, 8))
+    with pytest.raises(_lib.EoeError):
+        ops.bce_score(torch.zeros(4, 1))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "eoe_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
