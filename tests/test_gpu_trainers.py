@@ -1,0 +1,125 @@
+"""GPU: the trainer plug-ins behave like the reference's hooks inside the re-hosted train/eval loops.
+The comparison arm is a plain torch statement of the reference objective (hsc.py:17-21 / bce.py:19-20) driving the
+same model from the same initial weights with the same optimiser; losses must agree step for step."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import auc as oauc
+from oracle import heads as oh
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _loader(n_batches, d_in, seed, clf=False):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(n_batches):
+        imgs = torch.randn(256, d_in, generator=g)
+        imgs[128:] += 0.7                                      # "OE" half is shifted
+        lbls = torch.cat([torch.zeros(128, dtype=torch.long), torch.ones(128, dtype=torch.long)])   # bases.py:591-597
+        out.append((imgs, lbls, torch.arange(i * 256, (i + 1) * 256)))
+    return out
+
+
+def _mlp(d_in, d_out):
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(d_in, 128), torch.nn.LeakyReLU(), torch.nn.Linear(128, d_out))
+
+
+def _ref_hsc(z, y, nominal=0):
+    d = torch.sqrt(torch.norm(z, p=2, dim=1) ** 2 + 1) - 1
+    s = 1 - torch.exp(-d)
+    return torch.where(y == nominal, d, -torch.log(s + 1e-9)).mean()
+
+
+@pytest.mark.parametrize("objective", ["hsc", "bce"])
+def test_training_loop_matches_reference_objective(objective):
+    from eoe_b200.training import TRAINER
+    d_out = 64 if objective == "hsc" else 1
+    loader = _loader(4, 32, seed=3)
+    model = _mlp(32, d_out)
+    ref_model = copy.deepcopy(model).to(DEV)
+    tr = TRAINER[objective](model, epochs=2, lr=1e-3, wdk=0.0, milestones=[1], batch_size=128, device=DEV)
+    model, roc, losses = tr.train_cls(model, loader, nominal_label=0, clsstr="airplane")
+    # reference arm
+    opt = torch.optim.Adam(ref_model.parameters(), lr=1e-3, weight_decay=0.0)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, [1], 0.1)
+    ref_losses, last_scores, last_labels = [], [], []
+    for ep in range(2):
+        acc, last_scores, last_labels = [], [], []
+        for imgs, lbls, _ in loader:
+            imgs, lbls = imgs.to(DEV), lbls.to(DEV)
+            opt.zero_grad()
+            f = ref_model(imgs)
+            if objective == "hsc":
+                loss = _ref_hsc(f, lbls)
+                sc = 1 - torch.exp(-(torch.sqrt(torch.norm(f, p=2, dim=1) ** 2 + 1) - 1))
+            else:
+                loss = torch.nn.functional.binary_cross_entropy_with_logits(f.squeeze(), lbls.float())
+                sc = torch.sigmoid(f).squeeze()
+            loss.backward()
+            opt.step()
+            acc.append(loss.item())
+            last_scores.append(sc.detach().cpu())
+            last_labels.append(lbls.cpu())
+        ref_losses.append(float(np.mean(acc)))
+        sched.step()
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-3)          # north_star tolerance for losses
+    for p, q in zip(model.parameters(), ref_model.parameters()):
+        torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-3, atol=2e-5)
+    want_auc = oauc.roc_auc(torch.cat(last_labels).numpy(), torch.cat(last_scores).numpy())
+    assert abs(roc.auc - want_auc) < 1e-3                               # scores differ in the last ulp -> ties may move
+
+
+def test_eval_loop_returns_reference_containers():
+    from eoe_b200.training import HSCTrainer
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    model = _mlp(32, 64).to(DEV)
+    tr = HSCTrainer(model, device=DEV)
+    tr.center = None
+    loader = _loader(3, 32, seed=5)
+    loader[1][1][5] = -1                                                # unlabeled sample is ignored (ad_trainer.py:517)
+    roc, prc = tr.eval_cls(model, loader, nominal_label=0)
+    labels, scores = tr.last_eval
+    keep = labels.cpu().numpy() >= 0
+    y, s = labels.cpu().numpy()[keep], scores.cpu().numpy()[keep]
+    assert roc.auc == roc_auc_score(y, s) and roc.auc == oauc.roc_auc(y, s)     # AUC bit-exact given identical scores
+    assert prc.avg_prec == average_precision_score(y, s)
+    assert roc.fpr[0] == 0 and roc.tpr[-1] == 1 and roc.ths[0] == np.inf
+    np.testing.assert_allclose(s, oh.hsc_score(model(torch.cat([b[0] for b in loader]).to(DEV)).detach().cpu().numpy()[keep]),
+                               rtol=1e-3, atol=1e-7)
+
+
+def test_nan_scores_raise_like_the_reference():
+    from eoe_b200.training import HSCTrainer, NanGradientsError
+    model = _mlp(32, 64)
+    with torch.no_grad():
+        model[2].weight[0, 0] = float("nan")
+    tr = HSCTrainer(model, epochs=1, device=DEV)
+    with pytest.raises(NanGradientsError):
+        tr.train_cls(model, _loader(1, 32, seed=1))
+
+
+def test_clip_trainer_zero_shot_eval():
+    """epochs == 0 => zero-shot (ad_trainer.py:406 never runs): prepare_metric, then eval through the B200 encoder."""
+    from eoe_b200.encoder import ClipImageEncoder
+    from eoe_b200.synth import random_vit_state_dict
+    from eoe_b200.training import ADClipTrainer
+    enc = ClipImageEncoder(random_vit_state_dict(32, seed=2, layers=2), device=DEV, max_batch=16)
+    g = torch.Generator().manual_seed(7)
+    text = torch.randn(2, 512, generator=g)
+    tr = ADClipTrainer(enc, device=DEV, text_features={"airplane": text}, epochs=0)
+    _, roc0, losses = tr.train_cls(enc, [], clsstr="airplane")
+    assert roc0 is None and losses == []
+    assert torch.allclose(tr.center.norm(dim=-1).cpu(), torch.ones(2))
+    batches = [(torch.randn(16, 3, 224, 224, generator=g), (torch.rand(16, generator=g) < 0.5).long(), torch.arange(16))
+               for _ in range(2)]
+    roc, prc = tr.eval_cls(enc, batches, nominal_label=0)
+    labels, scores = tr.last_eval
+    feats = enc(torch.cat([b[0] for b in batches]).to(DEV)).cpu().numpy()
+    np.testing.assert_allclose(scores.cpu().numpy(), oh.clip_score(feats, tr.center.cpu().numpy()), rtol=1e-3, atol=1e-30)
+    assert roc.auc == oauc.roc_auc(labels.cpu().numpy(), scores.cpu().numpy())
