@@ -37,47 +37,66 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 50 ms in the background; only samples whose timestamp falls inside the timed region
+    (marked with `begin()` / `end()`) are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.path = index, None, f"/tmp/eoe_clocks_{os.getpid()}.csv"
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "50", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def begin(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons, pw = [], [], set(), []
+        rows = []
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        if not inside and rows and self.t0 is not None:       # region shorter than the sampling period: nearest sample
+            mid = self.t0 + (self.t1 - self.t0) / 2
+            inside = [min(rows, key=lambda r: abs((r[0] - mid).total_seconds()))]
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
-                       power_w_max=max(pw))
+        if inside:
+            out.update(sm_mhz=statistics.median(r[1] for r in inside), sm_max_mhz=max(r[2] for r in inside),
+                       reasons=sorted(reasons), samples=len(inside), power_w_max=max(r[3] for r in inside))
         try:
             os.remove(self.path)
         except OSError:
@@ -216,21 +235,23 @@ def run_ours(args):
             tdist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     job(W, scores, labels)
     sync()
 
     # ---- timed region: device-resident inputs, GEMM launches bracketed by events for the roofline
     enc.profile(True)
     launches0 = _lib.lib().eoe_launch_count()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     sync()
+    clocks.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     auc_out, auc_info, _ = job(S, scores, labels)
     e1.record()
     sync()
+    clocks.end()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
     launches = _lib.lib().eoe_launch_count() - launches0
@@ -341,7 +362,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")

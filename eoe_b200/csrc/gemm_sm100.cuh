@@ -4,13 +4,19 @@
 // src/eoe/models/clip_official/clip/model.py:171,174-176,220).  Both operands are K-major 16-bit (activations
 // [tokens, K] and nn.Linear weights [N, K] are already in that layout), accumulation is fp32 in TMEM.
 //
-// CTA = 128 x 256 output tile, persistent over tiles (n fastest so that the CTAs running concurrently share the
-// same A rows in L2 while W, <= 4.7 MB, stays L2 resident).  Warp roles:
-//   warp 0   TMA producer: 4-stage ring of {A 128x64, B 256x64} bf16 tiles (SWIZZLE_128B), mbarrier full/empty
-//   warp 1   MMA issuer: one thread issues tcgen05.mma 128x256x16, tcgen05.commit frees the smem stage
-//   warp 2   TMEM allocator (512 columns = 2 accumulator stages of 256 columns)
-//   warps 4-7 epilogue: tcgen05.ld 32 rows x 32 columns per warp, fused bias / QuickGELU / residual / pos-emb,
-//            overlapped with the next tile's main loop through the second accumulator stage
+// A CTA PAIR (cluster of 2, `cta_group::2`) owns a 256 x 256 output tile: CTA r holds rows [r*128, +128) of A and rows
+// [r*128, +128) of the W tile, so every operand byte is fetched from L2 once per pair and the tensor cores of the two
+// SMs read each other's B half.  Persistent over tiles (n fastest: the pairs running concurrently share A rows in L2,
+// W <= 4.7 MB stays L2 resident).  Warp roles per CTA:
+//   warp 0     TMA producer: 5-stage ring of {A 128x64, B 128x64} tiles (SWIZZLE_128B); completion bytes of both CTAs
+//              are signalled on the LEADER CTA's `full` barrier
+//   warp 1     MMA issuer (leader CTA only): one thread issues tcgen05.mma.cta_group::2 256x256x16; tcgen05.commit
+//              multicasts to both CTAs' `empty` / `tmem_full` barriers
+//   warp 2     TMEM allocator (512 columns = 2 accumulator stages of 256 fp32 columns)
+//   warps 4-11 epilogue: warp (q, half) reads TMEM lanes [32q, 32q+32) x columns [128*half, +128) with tcgen05.ld,
+//              applies bias / QuickGELU in the row-owner layout, transposes 32x32 blocks through padded shared memory and
+//              issues fully coalesced 128-byte global accesses (stores, or the fp32 residual read-modify-write);
+//              overlapped with the next tile's main loop through the second accumulator stage
 #pragma once
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -18,11 +24,18 @@
 namespace eoe {
 namespace gemm {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
-constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int THREADS = 256;
+constexpr int BM = 256, BN = 256, BK = 64, UMMA_K = 16;   // tile of a CTA pair
+constexpr int CTA_M = 128, CTA_NB = 128;                   // rows of A / rows of W each CTA loads
+constexpr int STAGES = 5;
+constexpr uint32_t A_BYTES = CTA_M * BK * 2, B_BYTES = CTA_NB * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // per CTA
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 128 + EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int STAGE_LD = 33;                                // padded row stride (words) of the transpose buffers
+constexpr size_t EPI_STAGE_BYTES = (size_t)EPI_WARPS * 32 * STAGE_LD * 4;
+constexpr size_t EPI_BIAS_BYTES = (size_t)EPI_WARPS * 128 * 4;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + EPI_BIAS_BYTES + 256 /*barriers*/ +
+                              1024 /*alignment slack*/;
 
 struct Params {
     int64_t M, N, K;
@@ -43,22 +56,40 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     }
 }
 
+// x * sigmoid(1.702 x).  bf16 output (2^-9 rounding): sigmoid(y) = 0.5 + 0.5 tanh(y/2) with the single-MUFU
+// tanh.approx (abs error ~5e-4 on the sigmoid, below the output rounding); fp16 output keeps exp + divide.
+template <bool BF16>
+__device__ __forceinline__ float quick_gelu(float x) {
+    if (BF16) {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+        const float hx = 0.5f * x;
+        return fmaf(hx, t, hx);
+    }
+    return __fdividef(x, 1.0f + __expf(-1.702f * x));
+}
+
 template <int EPI, bool BF16>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;                                   // [STAGES][128 rows][128 B]
-    uint8_t* smem_b = smem + STAGES * A_BYTES;                // [STAGES][256 rows][128 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
-    uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
-    uint64_t* tmem_full = bars + 2 * STAGES;       // [2] MMA -> epilogue
-    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA
+    uint8_t* smem_b = smem + STAGES * A_BYTES;                // [STAGES][128 rows][128 B]
+    float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    float* epi_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES + EPI_BIAS_BYTES);
+    uint64_t* full = bars;                         // [STAGES]  TMA (both CTAs) -> MMA (leader)
+    uint64_t* empty = bars + STAGES;               // [STAGES]  MMA -> TMA, one copy per CTA
+    uint64_t* tmem_full = bars + 2 * STAGES;       // [2] MMA -> epilogue, one copy per CTA
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2] epilogue (both CTAs) -> MMA (leader)
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = __shfl_sync(kFullMask, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = ptx::cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const int num_n = (int)(p.N / BN);
     const int num_m = (int)((p.M + BM - 1) / BM);
     const int num_tiles = num_m * num_n;
@@ -70,50 +101,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            ptx::mbar_init(ptx::smem_u32(&full[s]), 1);
-            ptx::mbar_init(ptx::smem_u32(&empty[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&full[s]), 1);          // the leader's producer arrive.expect_tx
+            ptx::mbar_init(ptx::smem_u32(&empty[s]), 1);         // one tcgen05.commit arrival
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(ptx::smem_u32(&tmem_full[s]), 1);
-            ptx::mbar_init(ptx::smem_u32(&tmem_empty[s]), 4);   // one arrival per epilogue warp
+            ptx::mbar_init(ptx::smem_u32(&tmem_empty[s]), 2 * EPI_WARPS);   // every epilogue warp of both CTAs
         }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_base_slot), TMEM_COLS);
-        ptx::tmem_relinquish<1>();
+        ptx::tmem_alloc<2>(ptx::smem_u32(tmem_base_slot), TMEM_COLS);
+        ptx::tmem_relinquish<2>();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    ptx::cluster_sync();            // barriers of both CTAs are initialised before anyone signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
     if (warp == 0) {
         if (lane == 0) {
-            // ------------------------------------------------------------------ TMA producer
+            // ------------------------------------------------------------------ TMA producer (both CTAs)
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 const int m_blk = tile / num_n, n_blk = tile % num_n;
+                const int a_row = m_blk * BM + (int)cta_rank * CTA_M;
+                const int b_row = n_blk * BN + (int)cta_rank * CTA_NB;
                 for (int kb = 0; kb < num_k; ++kb) {
                     ptx::mbar_wait(ptx::smem_u32(&empty[stage]), phase ^ 1);
-                    const uint32_t fb = ptx::smem_u32(&full[stage]);
-                    ptx::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-                    ptx::tma_load_2d(ptx::smem_u32(smem_a + stage * A_BYTES), &tma_a, fb, kb * BK, m_blk * BM);
-                    ptx::tma_load_2d(ptx::smem_u32(smem_b + stage * B_BYTES), &tma_b, fb, kb * BK, n_blk * BN);
+                    const uint32_t fb_leader = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
+                    if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full[stage]), 2 * STAGE_BYTES);
+                    ptx::tma_load_2d_cg2(ptx::smem_u32(smem_a + stage * A_BYTES), &tma_a, fb_leader, kb * BK, a_row);
+                    ptx::tma_load_2d_cg2(ptx::smem_u32(smem_b + stage * B_BYTES), &tma_b, fb_leader, kb * BK, b_row);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------------------------ MMA issuer
+        if (leader && lane == 0) {
+            // ------------------------------------------------------------------ MMA issuer (leader CTA)
             constexpr uint32_t idesc = ptx::make_idesc_f16(BF16 ? 1u : 0u, BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 ptx::mbar_wait(ptx::smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
@@ -125,93 +158,129 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
-                        ptx::umma_f16<1>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        ptx::umma_f16<2>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit(ptx::smem_u32(&empty[stage]));      // frees the smem stage when the MMAs retire
+                    ptx::umma_commit_cg2(ptx::smem_u32(&empty[stage]), 3);      // frees the stage in both CTAs
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(ptx::smem_u32(&tmem_full[acc]));        // accumulator complete -> epilogue
+                ptx::umma_commit_cg2(ptx::smem_u32(&tmem_full[acc]), 3);        // accumulator complete -> both epilogues
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
-        // ---------------------------------------------------------------------- epilogue (warps 4..7)
-        const int wq = warp & 3;                       // TMEM lane quarter this warp may access
+        // ---------------------------------------------------------------------- epilogue (warps 4..11)
+        const int ew = warp - 4;
+        const int wq = warp & 3;                       // TMEM lane quarter this warp may access (warp id % 4)
+        const int half = ew >> 2;                      // which 128 of the 256 accumulator columns
+        float* st = epi_stage + ew * (32 * STAGE_LD);
+        float* sbias = epi_bias + ew * 128;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
+            const int64_t row0 = (int64_t)m_blk * BM + (int64_t)cta_rank * CTA_M + wq * 32;   // first of this warp's 32 rows
+            const int64_t nb = (int64_t)n_blk * BN + half * 128;
+            int pe_orow = 0, pe_prow = 0;
+            if (EPI != EOE_EPI_PATCH_EMBED) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sbias[i * 32 + lane] = p.bias ? __ldg(p.bias + nb + i * 32 + lane) : 0.f;
+            } else {
+                const int64_t row = row0 + lane, img = row / p.aux_i, pi = row % p.aux_i;
+                pe_orow = (int)(img * (p.aux_i + 1) + 1 + pi);      // token 0 of every image is the class token
+                pe_prow = (int)(1 + pi);
+            }
+            __syncwarp();
             ptx::mbar_wait(ptx::smem_u32(&tmem_full[acc]), acc_phase);
             ptx::tc_fence_after();
-            const int64_t row = (int64_t)m_blk * BM + wq * 32 + lane;
-            const bool row_ok = row < p.M;
-            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)acc * BN;
-            int64_t orow = row;
-            const float* pos = nullptr;
-            if (EPI == EOE_EPI_PATCH_EMBED) {
-                const int64_t img = row / p.aux_i, pi = row % p.aux_i;
-                orow = img * (p.aux_i + 1) + 1 + pi;
-                pos = p.aux + (1 + pi) * p.N;
-            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)acc * BN + (uint32_t)half * 128;
+
+            if (EPI == EOE_EPI_BIAS || EPI == EOE_EPI_BIAS_QUICKGELU) {
+                // 16-bit output: 64 columns per round = 32 packed words per row
+                uint16_t* out16 = reinterpret_cast<uint16_t*>(p.out);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-                ptx::tmem_ld_wait();
-                const int64_t n0 = (int64_t)n_blk * BN + c * 32;
-                float v[32];
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r0[32], r1[32];
+                    ptx::tmem_ld_32x32b_x32(taddr + c * 64, r0);
+                    ptx::tmem_ld_32x32b_x32(taddr + c * 64 + 32, r1);
+                    ptx::tmem_ld_wait();
+                    if (c == 1) {                      // all TMEM reads of this tile are done: release the accumulator
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), 0);
+                    }
+                    __syncwarp();                      // previous round's readers are done with `st`
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (EPI != EOE_EPI_PATCH_EMBED && p.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                    for (int j = 0; j < 32; j += 2) {
+                        float a0 = __uint_as_float(r0[j]) + sbias[c * 64 + j];
+                        float a1 = __uint_as_float(r0[j + 1]) + sbias[c * 64 + j + 1];
+                        float b0 = __uint_as_float(r1[j]) + sbias[c * 64 + 32 + j];
+                        float b1 = __uint_as_float(r1[j + 1]) + sbias[c * 64 + 32 + j + 1];
+                        if (EPI == EOE_EPI_BIAS_QUICKGELU) {      // QuickGELU (model.py:162-164): x * sigmoid(1.702 x)
+                            a0 = quick_gelu<BF16>(a0); a1 = quick_gelu<BF16>(a1);
+                            b0 = quick_gelu<BF16>(b0); b1 = quick_gelu<BF16>(b1);
+                        }
+                        reinterpret_cast<uint32_t*>(st)[lane * STAGE_LD + (j >> 1)] = pack2<BF16>(a0, a1);
+                        reinterpret_cast<uint32_t*>(st)[lane * STAGE_LD + 16 + (j >> 1)] = pack2<BF16>(b0, b1);
+                    }
+                    __syncwarp();
+                    // transposed read: lane = packed word (columns 2*lane, 2*lane+1) -> one 128-byte store per row
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) {
+                        const int64_t row = row0 + r;
+                        if (row < p.M)
+                            *reinterpret_cast<uint32_t*>(out16 + row * p.N + nb + c * 64 + 2 * lane) =
+                                reinterpret_cast<const uint32_t*>(st)[r * STAGE_LD + lane];
                     }
                 }
-                if (EPI == EOE_EPI_BIAS_QUICKGELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)            // QuickGELU (model.py:162-164): x * sigmoid(1.702 x)
-                        v[j] = __fdividef(v[j], 1.0f + __expf(-1.702f * v[j]));
-                }
-                if (!row_ok) continue;
-                if (EPI == EOE_EPI_BIAS || EPI == EOE_EPI_BIAS_QUICKGELU) {
-                    uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + orow * p.N + n0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 q;
-                        q.x = pack2<BF16>(v[j], v[j + 1]); q.y = pack2<BF16>(v[j + 2], v[j + 3]);
-                        q.z = pack2<BF16>(v[j + 4], v[j + 5]); q.w = pack2<BF16>(v[j + 6], v[j + 7]);
-                        *reinterpret_cast<uint4*>(o + j) = q;
+            } else {
+                // fp32 output (residual += or patch-embed scatter): 32 columns per round
+                float* out32 = reinterpret_cast<float*>(p.out);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r0[32];
+                    ptx::tmem_ld_32x32b_x32(taddr + c * 32, r0);
+                    ptx::tmem_ld_wait();
+                    if (c == 3) {
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), 0);
                     }
-                } else if (EPI == EOE_EPI_BIAS_RESIDUAL_F32) {
-                    float* o = reinterpret_cast<float*>(p.out) + orow * p.N + n0;
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 x = *reinterpret_cast<const float4*>(o + j);
-                        x.x += v[j]; x.y += v[j + 1]; x.z += v[j + 2]; x.w += v[j + 3];
-                        *reinterpret_cast<float4*>(o + j) = x;
+                    for (int j = 0; j < 32; ++j) {
+                        float v = __uint_as_float(r0[j]);
+                        if (EPI == EOE_EPI_BIAS_RESIDUAL_F32) v += sbias[c * 32 + j];
+                        st[lane * STAGE_LD + j] = v;
                     }
-                } else {   // PATCH_EMBED
-                    float* o = reinterpret_cast<float*>(p.out) + orow * p.N + n0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 e = __ldg(reinterpret_cast<const float4*>(pos + n0 + j));
-                        *reinterpret_cast<float4*>(o + j) = make_float4(v[j] + e.x, v[j + 1] + e.y, v[j + 2] + e.z, v[j + 3] + e.w);
+                    __syncwarp();
+                    const int64_t col = nb + c * 32 + lane;
+                    if (EPI == EOE_EPI_BIAS_RESIDUAL_F32) {
+                        // x += attn/mlp branch (model.py:186-187).  Each element receives exactly one addend per launch,
+                        // so the fire-and-forget L2 reduction is deterministic and keeps the read of x off the SM.
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r)
+                            if (row0 + r < p.M)
+                                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(out32 + (row0 + r) * p.N + col),
+                                             "f"(st[r * STAGE_LD + lane]) : "memory");
+                    } else {
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            const int orow = __shfl_sync(kFullMask, pe_orow, r);      // token row of patch row row0 + r
+                            const int prow = __shfl_sync(kFullMask, pe_prow, r);      // positional-embedding row
+                            if (row0 + r < p.M)
+                                out32[(int64_t)orow * p.N + col] = st[r * STAGE_LD + lane] + __ldg(p.aux + (int64_t)prow * p.N + col);
+                        }
                     }
                 }
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tmem_empty[acc]));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    ptx::cluster_sync();            // the peer may still be reading this CTA's smem / signalling its barriers
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<1>(tmem_base, TMEM_COLS);
+        ptx::tmem_dealloc<2>(tmem_base, TMEM_COLS);
     }
 }
 

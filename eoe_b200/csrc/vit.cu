@@ -74,7 +74,8 @@ static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const gem
         attr_done = true;
     }
     const int64_t tiles = ((p.M + gemm::BM - 1) / gemm::BM) * (p.N / gemm::BN);
-    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    const int64_t pairs = num_sms() / 2;                              // one CTA pair (cluster of 2) per tile at a time
+    const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
     kern<<<grid, gemm::THREADS, gemm::SMEM_BYTES, st>>>(ta, tb, p);
     return check_launch("gemm_kernel");
 }
@@ -372,15 +373,20 @@ static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, 
 }
 
 // ------------------------------------------------------------------------------------------ tail
-// feats[b] = ln_post(x[b, 0, :]) @ proj   (model.py:231-234).  4 images per block so that proj (1.5 MB, L2
-// resident) is streamed once per 4 images; thread j owns output columns j and j + 256 (embed_dim <= 512).
+// feats[b] = ln_post(x[b, 0, :]) @ proj   (model.py:231-234), fp32 throughout (it feeds a 100x cosine logit).
+// Block = 4 images x 128 output columns; proj (1.5 MB, L2 resident) is streamed once per 4 images.  Thread
+// (col = tid & 127, kh = tid >> 7) accumulates half of the K range for its column; halves are combined in smem.
 constexpr int kTailImgs = 4;
+constexpr int kTailCols = 128;
 __global__ void __launch_bounds__(256)
 tail_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
             const float* __restrict__ proj, float* __restrict__ feats, int64_t B, int L, int width, int embed) {
-    extern __shared__ float s_h[];        // [kTailImgs][width]
+    extern __shared__ float s_h[];        // [kTailImgs][width] then [kTailImgs][kTailCols] partials
+    float* s_part = s_h + kTailImgs * width;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t img0 = (int64_t)blockIdx.x * kTailImgs;
+    const int col = blockIdx.y * kTailCols + (threadIdx.x & (kTailCols - 1));
+    const int kh = threadIdx.x >> 7;
     if (warp < kTailImgs) {
         const int64_t img = img0 + warp;
         float* h = s_h + warp * width;
@@ -398,26 +404,27 @@ tail_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
         }
     }
     __syncthreads();
-    const int j0 = threadIdx.x, j1 = threadIdx.x + 256;
-    float a0[kTailImgs], a1[kTailImgs];
+    float acc[kTailImgs];
 #pragma unroll
-    for (int g = 0; g < kTailImgs; ++g) a0[g] = a1[g] = 0.f;
-    for (int i = 0; i < width; ++i) {
-        const float p0 = j0 < embed ? __ldg(proj + (int64_t)i * embed + j0) : 0.f;
-        const float p1 = j1 < embed ? __ldg(proj + (int64_t)i * embed + j1) : 0.f;
+    for (int g = 0; g < kTailImgs; ++g) acc[g] = 0.f;
+    const int k0 = kh * (width / 2), k1 = k0 + width / 2;
+    if (col < embed) {
+#pragma unroll 4
+        for (int i = k0; i < k1; ++i) {
+            const float pv = __ldg(proj + (int64_t)i * embed + col);
 #pragma unroll
-        for (int g = 0; g < kTailImgs; ++g) {
-            const float hv = s_h[g * width + i];
-            a0[g] += hv * p0;
-            a1[g] += hv * p1;
+            for (int g = 0; g < kTailImgs; ++g) acc[g] += s_h[g * width + i] * pv;
         }
     }
+    if (kh == 1) {
 #pragma unroll
-    for (int g = 0; g < kTailImgs; ++g) {
-        if (img0 + g < B) {
-            if (j0 < embed) feats[(img0 + g) * embed + j0] = a0[g];
-            if (j1 < embed) feats[(img0 + g) * embed + j1] = a1[g];
-        }
+        for (int g = 0; g < kTailImgs; ++g) s_part[g * kTailCols + (threadIdx.x & (kTailCols - 1))] = acc[g];
+    }
+    __syncthreads();
+    if (kh == 0 && col < embed) {
+#pragma unroll
+        for (int g = 0; g < kTailImgs; ++g)
+            if (img0 + g < B) feats[(img0 + g) * embed + col] = acc[g] + s_part[g * kTailCols + (threadIdx.x & (kTailCols - 1))];
     }
 }
 
@@ -475,7 +482,7 @@ static int vit_check(const eoe_vit_weights* w) {
     if (w->operand_dtype != EOE_BF16 && w->operand_dtype != EOE_F16) return EOE_ERR_DTYPE;
     if (w->patch <= 0 || w->resolution % w->patch != 0 || w->patch % 4 != 0) return EOE_ERR_SHAPE;
     if (w->width != w->heads * 64 || w->width % 256 != 0 || w->width > 1024) return EOE_ERR_SHAPE;
-    if ((3 * w->patch * w->patch) % 64 != 0 || w->embed_dim > 512 || w->embed_dim % 4 != 0) return EOE_ERR_SHAPE;
+    if ((3 * w->patch * w->patch) % 64 != 0 || w->embed_dim > 1024 || w->embed_dim % 4 != 0 || w->width % 2 != 0) return EOE_ERR_SHAPE;
     const int g = w->resolution / w->patch;
     if (g * g + 1 > 208) return EOE_ERR_SHAPE;
     if (w->n_layers <= 0) return EOE_ERR_ARG;
@@ -486,14 +493,14 @@ struct VitLayout { size_t patches, x, h, qkv, u, feats, total; };
 static VitLayout vit_layout(const eoe_vit_weights* w, int64_t B) {
     const int g = w->resolution / w->patch;
     const int64_t g2 = g * g, L = g2 + 1, W = w->width;
-    // +128 rows of slack: TMA boxes of the last M tile may start below M but never beyond the allocation
+    // +256 rows of slack: TMA boxes of the last M tile may start below M but never beyond the allocation
     VitLayout l;
     size_t o = 0;
-    l.patches = o; o += rup((size_t)(B * g2 + 128) * 3 * w->patch * w->patch * 2);
-    l.x = o; o += rup((size_t)(B * L + 128) * W * 4);
-    l.h = o; o += rup((size_t)(B * L + 128) * W * 2);
-    l.qkv = o; o += rup((size_t)(B * L + 128) * 3 * W * 2);
-    l.u = o; o += rup((size_t)(B * L + 128) * 4 * W * 2);
+    l.patches = o; o += rup((size_t)(B * g2 + 256) * 3 * w->patch * w->patch * 2);
+    l.x = o; o += rup((size_t)(B * L + 256) * W * 4);
+    l.h = o; o += rup((size_t)(B * L + 256) * W * 2);
+    l.qkv = o; o += rup((size_t)(B * L + 256) * 3 * W * 2);
+    l.u = o; o += rup((size_t)(B * L + 256) * 4 * W * 2);
     l.feats = o; o += rup((size_t)B * w->embed_dim * 4);
     l.total = o;
     return l;
@@ -539,16 +546,16 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     p->tm_out = new CUtensorMap[w->n_layers];
     p->tm_fc = new CUtensorMap[w->n_layers];
     p->tm_proj = new CUtensorMap[w->n_layers];
-    rc = make_tmap(&p->tm_patches, p->patches, max_batch * p->g2, p->kpatch, gemm::BM, dt);
-    if (!rc) rc = make_tmap(&p->tm_h, p->h, rows, W, gemm::BM, dt);
-    if (!rc) rc = make_tmap(&p->tm_u, p->u, rows, 4 * W, gemm::BM, dt);
-    if (!rc) rc = make_tmap(&p->tm_conv, w->conv1_w, W, p->kpatch, gemm::BN, dt);
+    rc = make_tmap(&p->tm_patches, p->patches, max_batch * p->g2, p->kpatch, gemm::CTA_M, dt);
+    if (!rc) rc = make_tmap(&p->tm_h, p->h, rows, W, gemm::CTA_M, dt);
+    if (!rc) rc = make_tmap(&p->tm_u, p->u, rows, 4 * W, gemm::CTA_M, dt);
+    if (!rc) rc = make_tmap(&p->tm_conv, w->conv1_w, W, p->kpatch, gemm::CTA_NB, dt);
     for (int i = 0; i < w->n_layers && !rc; ++i) {
         const eoe_vit_layer& l = p->layers[i];
-        rc = make_tmap(&p->tm_in[i], l.in_proj_w, 3 * W, W, gemm::BN, dt);
-        if (!rc) rc = make_tmap(&p->tm_out[i], l.out_proj_w, W, W, gemm::BN, dt);
-        if (!rc) rc = make_tmap(&p->tm_fc[i], l.c_fc_w, 4 * W, W, gemm::BN, dt);
-        if (!rc) rc = make_tmap(&p->tm_proj[i], l.c_proj_w, W, 4 * W, gemm::BN, dt);
+        rc = make_tmap(&p->tm_in[i], l.in_proj_w, 3 * W, W, gemm::CTA_NB, dt);
+        if (!rc) rc = make_tmap(&p->tm_out[i], l.out_proj_w, W, W, gemm::CTA_NB, dt);
+        if (!rc) rc = make_tmap(&p->tm_fc[i], l.c_fc_w, 4 * W, W, gemm::CTA_NB, dt);
+        if (!rc) rc = make_tmap(&p->tm_proj[i], l.c_proj_w, W, 4 * W, gemm::CTA_NB, dt);
     }
     if (rc) { eoe_vit_plan_destroy(p); return rc; }
     *plan_out = p;
@@ -610,9 +617,9 @@ extern "C" int eoe_vit_encode(eoe_vit_plan* p, const float* imgs, int64_t B, flo
     // 5. ln_post + proj (+ zero-shot score head)
     float* feats = feats_out ? feats_out : p->feats;
     {
-        const int grid = (int)((B + kTailImgs - 1) / kTailImgs);
-        tail_kernel<<<grid, 256, kTailImgs * W * sizeof(float), st>>>(p->x, w.ln_post_w, w.ln_post_b, w.proj, feats, B, L,
-                                                                      W, w.embed_dim);
+        const dim3 grid((unsigned)((B + kTailImgs - 1) / kTailImgs), (unsigned)((w.embed_dim + kTailCols - 1) / kTailCols));
+        tail_kernel<<<grid, 256, (kTailImgs * W + kTailImgs * kTailCols) * sizeof(float), st>>>(
+            p->x, w.ln_post_w, w.ln_post_b, w.proj, feats, B, L, W, w.embed_dim);
         if ((rc = check_launch("tail_kernel"))) return rc;
     }
     if (text) {
@@ -655,8 +662,8 @@ extern "C" int eoe_gemm(const void* A, const void* Wt, const float* bias, void* 
     if (epilogue == EOE_EPI_PATCH_EMBED && (!aux || aux_i <= 0)) return EOE_ERR_ARG;
     if ((uintptr_t)A % 16 != 0 || (uintptr_t)Wt % 16 != 0 || (uintptr_t)out % 16 != 0) return EOE_ERR_ALIGN;
     CUtensorMap ta, tb;
-    if ((rc = make_tmap(&ta, A, M, K, gemm::BM, operand_dtype))) return rc;
-    if ((rc = make_tmap(&tb, Wt, N, K, gemm::BN, operand_dtype))) return rc;
+    if ((rc = make_tmap(&ta, A, M, K, gemm::CTA_M, operand_dtype))) return rc;
+    if ((rc = make_tmap(&tb, Wt, N, K, gemm::CTA_NB, operand_dtype))) return rc;
     gemm::Params p{M, N, K, bias, out, aux, aux_i};
     return gemm_launch(ta, tb, p, operand_dtype, epilogue, (cudaStream_t)stream);
 }

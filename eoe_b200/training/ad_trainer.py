@@ -74,12 +74,19 @@ class ADTrainer(ABC):
         model = model.to(self.device).train()
         epochs = self.epochs if epochs is None else epochs
         params = [p for p in model.parameters() if p.requires_grad]
+        _, ws = edist.world()
+        if epochs == 0 or not params:
+            # zero-shot (ad_trainer.py:406 never runs for epochs == 0): only prepare_metric is executed.  The B200
+            # image encoder is inference-only, so it has no trainable parameters to hand to an optimiser.
+            if epochs > 0:
+                raise ValueError("train_cls with epochs > 0 needs a model with trainable parameters")
+            self.center = self.prepare_metric(clsstr, loader, model, seed)
+            return model.eval(), None, []
         if self.sgd:
             opt = torch.optim.SGD(params, lr=self.lr, weight_decay=self.wdk, momentum=0.9, nesterov=True)
         else:
             opt = torch.optim.Adam(params, lr=self.lr, weight_decay=self.wdk, amsgrad=False)
         sched = torch.optim.lr_scheduler.MultiStepLR(opt, self.milestones, 0.1)
-        _, ws = edist.world()
         buckets = edist.GradBuckets(params) if (self.data_parallel and ws > 1) else None
         center = self.center = self.prepare_metric(clsstr, loader, model, seed)
         cls_roc, losses = None, []
