@@ -31,7 +31,8 @@ constexpr uint32_t A_BYTES = CTA_M * BK * 2, B_BYTES = CTA_NB * BK * 2, STAGE_BY
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 128 + EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int STAGE_LD = 33;                                // padded row stride (words) of the transpose buffers
+constexpr int STAGE_LD = 36;                                // row stride (words) of the transpose buffers: 16-byte aligned rows,
+                                                            // conflict-free for 128-bit accesses by row owners and by 8-lane row readers
 constexpr size_t EPI_STAGE_BYTES = (size_t)EPI_WARPS * 32 * STAGE_LD * 4;
 constexpr size_t EPI_BIAS_BYTES = (size_t)EPI_WARPS * 128 * 4;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + EPI_BIAS_BYTES + 256 /*barriers*/ +
@@ -194,6 +195,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)acc * BN + (uint32_t)half * 128;
 
+            // Transposed access pattern shared by all variants: after the row owners (lane = row) have written their
+            // 32 words, lane l reads the 16-byte group (l & 7) of row (it*4 + (l >> 3)): 8 lanes cover one 128-byte row
+            // segment, one instruction covers 4 rows.
+            const int sub = lane >> 3, grp = lane & 7;
             if (EPI == EOE_EPI_BIAS || EPI == EOE_EPI_BIAS_QUICKGELU) {
                 // 16-bit output: 64 columns per round = 32 packed words per row
                 uint16_t* out16 = reinterpret_cast<uint16_t*>(p.out);
@@ -209,27 +214,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), 0);
                     }
                     __syncwarp();                      // previous round's readers are done with `st`
+                    uint32_t* strow = reinterpret_cast<uint32_t*>(st) + lane * STAGE_LD;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float a0 = __uint_as_float(r0[j]) + sbias[c * 64 + j];
-                        float a1 = __uint_as_float(r0[j + 1]) + sbias[c * 64 + j + 1];
-                        float b0 = __uint_as_float(r1[j]) + sbias[c * 64 + 32 + j];
-                        float b1 = __uint_as_float(r1[j + 1]) + sbias[c * 64 + 32 + j + 1];
-                        if (EPI == EOE_EPI_BIAS_QUICKGELU) {      // QuickGELU (model.py:162-164): x * sigmoid(1.702 x)
-                            a0 = quick_gelu<BF16>(a0); a1 = quick_gelu<BF16>(a1);
-                            b0 = quick_gelu<BF16>(b0); b1 = quick_gelu<BF16>(b1);
+                    for (int j = 0; j < 32; j += 8) {
+                        float a[8], b[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            a[e] = __uint_as_float(r0[j + e]) + sbias[c * 64 + j + e];
+                            b[e] = __uint_as_float(r1[j + e]) + sbias[c * 64 + 32 + j + e];
+                            if (EPI == EOE_EPI_BIAS_QUICKGELU) {      // QuickGELU (model.py:162-164): x * sigmoid(1.702 x)
+                                a[e] = quick_gelu<BF16>(a[e]);
+                                b[e] = quick_gelu<BF16>(b[e]);
+                            }
                         }
-                        reinterpret_cast<uint32_t*>(st)[lane * STAGE_LD + (j >> 1)] = pack2<BF16>(a0, a1);
-                        reinterpret_cast<uint32_t*>(st)[lane * STAGE_LD + 16 + (j >> 1)] = pack2<BF16>(b0, b1);
+                        *reinterpret_cast<uint4*>(strow + (j >> 1)) =
+                            make_uint4(pack2<BF16>(a[0], a[1]), pack2<BF16>(a[2], a[3]), pack2<BF16>(a[4], a[5]), pack2<BF16>(a[6], a[7]));
+                        *reinterpret_cast<uint4*>(strow + 16 + (j >> 1)) =
+                            make_uint4(pack2<BF16>(b[0], b[1]), pack2<BF16>(b[2], b[3]), pack2<BF16>(b[4], b[5]), pack2<BF16>(b[6], b[7]));
                     }
                     __syncwarp();
-                    // transposed read: lane = packed word (columns 2*lane, 2*lane+1) -> one 128-byte store per row
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + sub;
                         const int64_t row = row0 + r;
-                        if (row < p.M)
-                            *reinterpret_cast<uint32_t*>(out16 + row * p.N + nb + c * 64 + 2 * lane) =
-                                reinterpret_cast<const uint32_t*>(st)[r * STAGE_LD + lane];
+                        const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(st) + r * STAGE_LD + grp * 4);
+                        if (row < p.M) *reinterpret_cast<uint4*>(out16 + row * p.N + nb + c * 64 + grp * 8) = q;
                     }
                 }
             } else {
@@ -237,6 +246,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 float* out32 = reinterpret_cast<float*>(p.out);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
+                    const int64_t col = nb + c * 32 + grp * 4;
+                    float4 pos[8];
+                    if (EPI == EOE_EPI_PATCH_EMBED) {          // positional embedding rows: independent of the accumulator
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int prow = __shfl_sync(kFullMask, pe_prow, it * 4 + sub);
+                            pos[it] = __ldg(reinterpret_cast<const float4*>(p.aux + (int64_t)prow * p.N + col));
+                        }
+                    }
                     uint32_t r0[32];
                     ptx::tmem_ld_32x32b_x32(taddr + c * 32, r0);
                     ptx::tmem_ld_wait();
@@ -246,29 +264,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), 0);
                     }
                     __syncwarp();
+                    float* strow = st + lane * STAGE_LD;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float v = __uint_as_float(r0[j]);
-                        if (EPI == EOE_EPI_BIAS_RESIDUAL_F32) v += sbias[c * 32 + j];
-                        st[lane * STAGE_LD + j] = v;
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r0[j]), __uint_as_float(r0[j + 1]), __uint_as_float(r0[j + 2]),
+                                               __uint_as_float(r0[j + 3]));
+                        if (EPI == EOE_EPI_BIAS_RESIDUAL_F32) {
+                            v.x += sbias[c * 32 + j]; v.y += sbias[c * 32 + j + 1];
+                            v.z += sbias[c * 32 + j + 2]; v.w += sbias[c * 32 + j + 3];
+                        }
+                        *reinterpret_cast<float4*>(strow + j) = v;
                     }
                     __syncwarp();
-                    const int64_t col = nb + c * 32 + lane;
-                    if (EPI == EOE_EPI_BIAS_RESIDUAL_F32) {
-                        // x += attn/mlp branch (model.py:186-187).  Each element receives exactly one addend per launch,
-                        // so the fire-and-forget L2 reduction is deterministic and keeps the read of x off the SM.
-#pragma unroll 8
-                        for (int r = 0; r < 32; ++r)
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + sub;
+                        const float4 v = *reinterpret_cast<const float4*>(st + r * STAGE_LD + grp * 4);
+                        if (EPI == EOE_EPI_BIAS_RESIDUAL_F32) {
+                            // x += attn/mlp branch (model.py:186-187).  Each element receives exactly one addend per
+                            // launch, so the fire-and-forget L2 reduction is deterministic and keeps the read of x off the SM.
                             if (row0 + r < p.M)
-                                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(out32 + (row0 + r) * p.N + col),
-                                             "f"(st[r * STAGE_LD + lane]) : "memory");
-                    } else {
-#pragma unroll 8
-                        for (int r = 0; r < 32; ++r) {
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out32 + (row0 + r) * p.N + col),
+                                             "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                        } else {
                             const int orow = __shfl_sync(kFullMask, pe_orow, r);      // token row of patch row row0 + r
-                            const int prow = __shfl_sync(kFullMask, pe_prow, r);      // positional-embedding row
                             if (row0 + r < p.M)
-                                out32[(int64_t)orow * p.N + col] = st[r * STAGE_LD + lane] + __ldg(p.aux + (int64_t)prow * p.N + col);
+                                *reinterpret_cast<float4*>(out32 + (int64_t)orow * p.N + col) =
+                                    make_float4(v.x + pos[it].x, v.y + pos[it].y, v.z + pos[it].z, v.w + pos[it].w);
                         }
                     }
                 }
