@@ -10,6 +10,7 @@
 #include <new>
 #include <vector>
 
+#include "attention_sm100.cuh"
 #include "gemm_sm100.cuh"
 
 namespace eoe {
@@ -363,10 +364,36 @@ static int attention_launch_t(const void* qkv, void* out, int64_t B, int L, int 
     return check_launch("attention_kernel");
 }
 
-static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int dtype, cudaStream_t st) {
+// tcgen05 path (L == 197): qkv is read through a TMA descriptor with 128-row x 64-column boxes
+template <bool BF16>
+static int attention_tc_launch(const CUtensorMap& tm_qkv, void* out, int64_t B, int heads, cudaStream_t st) {
+    auto kern = attn::attention_tc_kernel<BF16, 197>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::SMEM_BYTES);
+        if (e != cudaSuccess) { set_cuda_error(e, "attention_tc smem attr"); return EOE_ERR_CUDA; }
+        attr_done = true;
+    }
+    const int64_t items = B * heads;
+    const int grid = (int)(items < 2 * (int64_t)num_sms() ? items : 2 * (int64_t)num_sms());
+    kern<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tm_qkv, (uint16_t*)out, (int)items, heads);
+    return check_launch("attention_tc_kernel");
+}
+
+static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int dtype, cudaStream_t st,
+                              const CUtensorMap* tm_qkv = nullptr) {
     if (dtype != EOE_BF16 && dtype != EOE_F16) return EOE_ERR_DTYPE;
     if (B <= 0 || L <= 0 || heads <= 0 || B * heads > 0x7fffffff) return EOE_ERR_ARG;
     const bool bf = dtype == EOE_BF16;
+    if (L == 197) {
+        CUtensorMap local;
+        if (!tm_qkv) {
+            int rc = make_tmap(&local, qkv, B * L, 3 * heads * 64, 128, dtype);
+            if (rc) return rc;
+            tm_qkv = &local;
+        }
+        return bf ? attention_tc_launch<true>(*tm_qkv, out, B, (int)heads, st) : attention_tc_launch<false>(*tm_qkv, out, B, (int)heads, st);
+    }
     if (L <= 64) return bf ? attention_launch_t<true, 64>(qkv, out, B, (int)L, (int)heads, st) : attention_launch_t<false, 64>(qkv, out, B, (int)L, (int)heads, st);
     if (L <= 208) return bf ? attention_launch_t<true, 208>(qkv, out, B, (int)L, (int)heads, st) : attention_launch_t<false, 208>(qkv, out, B, (int)L, (int)heads, st);
     return EOE_ERR_SHAPE;
@@ -447,7 +474,7 @@ struct eoe_vit_plan {
     uint16_t* qkv;       // [B*L, 3*width]
     uint16_t* u;         // [B*L, 4*width]
     float* feats;        // [B, embed]
-    CUtensorMap tm_patches, tm_h, tm_u, tm_conv;
+    CUtensorMap tm_patches, tm_h, tm_u, tm_conv, tm_qkv;
     CUtensorMap *tm_in, *tm_out, *tm_fc, *tm_proj;     // per layer
     // optional instrumentation (eoe_vit_profile_*): CUDA event pairs around every GEMM launch
     bool profile;
@@ -550,6 +577,7 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     if (!rc) rc = make_tmap(&p->tm_h, p->h, rows, W, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_u, p->u, rows, 4 * W, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_conv, w->conv1_w, W, p->kpatch, gemm::CTA_NB, dt);
+    if (!rc) rc = make_tmap(&p->tm_qkv, p->qkv, rows + 256, 3 * W, 128, dt);
     for (int i = 0; i < w->n_layers && !rc; ++i) {
         const eoe_vit_layer& l = p->layers[i];
         rc = make_tmap(&p->tm_in[i], l.in_proj_w, 3 * W, W, gemm::CTA_NB, dt);
@@ -605,7 +633,7 @@ extern "C" int eoe_vit_encode(eoe_vit_plan* p, const float* imgs, int64_t B, flo
         if ((rc = layernorm_dispatch(p->x, l.ln_1_w, l.ln_1_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
         gemm::Params g1{M, 3 * W, W, l.in_proj_b, p->qkv, nullptr, 0};
         if ((rc = timed_gemm(p, KIND_QKV, p->tm_h, p->tm_in[i], g1, dt, EOE_EPI_BIAS, st))) return rc;
-        if ((rc = attention_dispatch(p->qkv, p->h, B, L, w.heads, dt, st))) return rc;
+        if ((rc = attention_dispatch(p->qkv, p->h, B, L, w.heads, dt, st, &p->tm_qkv))) return rc;
         gemm::Params g2{M, W, W, l.out_proj_b, p->x, nullptr, 0};
         if ((rc = timed_gemm(p, KIND_OUT, p->tm_h, p->tm_out[i], g2, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
         if ((rc = layernorm_dispatch(p->x, l.ln_2_w, l.ln_2_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;

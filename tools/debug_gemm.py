@@ -86,5 +86,17 @@ if __name__ == "__main__":
             bench_gemm(M, N, K, bf, epi)
     elif case == "ln":
         ln_case()
+    elif case == "attn_bench":
+        for (B, Lseq) in [(512, 197), (512, 50)]:
+            qkv = torch.randn(B * Lseq, 2304, device="cuda").to(bf)
+            for _ in range(3): E.attention(qkv, B, Lseq, 12)
+            torch.cuda.synchronize()
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20): E.attention(qkv, B, Lseq, 12)
+            b2.record(); torch.cuda.synchronize()
+            ms = a.elapsed_time(b2) / 20
+            fl = 4.0 * B * 12 * Lseq * Lseq * 64
+            print(f"attention bench B={B} L={Lseq}: {ms*1e3:.1f} us, {fl/ms/1e9:.1f} TFLOP/s", flush=True)
     elif case == "attn":
         attn_case(2, 50, bf); attn_case(3, 197, bf); attn_case(2, 197, hf); attn_case(1, 64, bf); attn_case(1, 208, bf); attn_case(2, 17, hf)
