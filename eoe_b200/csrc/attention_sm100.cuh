@@ -27,6 +27,12 @@ constexpr uint32_t SMEM_BYTES = 6 * TILE_BYTES + 64 + 1024;   // Q0, Q1, K (2 bo
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t O_COL = 128;
 
+__device__ __forceinline__ float fast_exp2(float x) {      // x <= 0 here; MUFU.EX2, flushes denormal results to 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <bool BF16, int L>
 __global__ void __launch_bounds__(THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict__ out, int num_items, int heads) {
@@ -109,58 +115,64 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __rest
             ptx::tc_fence_after();
             float inv_sum = 0.f;
             if (warp_active) {
-                // pass 1: row maximum over the L valid keys
-                float m = -INFINITY;
+                constexpr int NC = LP / 32;                 // full 32-column chunks; LP % 32 == 16 leaves one half chunk
+                static_assert(LP % 32 == 0 || LP % 32 == 16, "chunking");
+                // pass 1: row maximum over the L valid keys.  TMEM loads are software pipelined (chunk c+1 is in
+                // flight while chunk c is reduced) and four independent accumulators break the FMNMX dependency chain.
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                uint32_t r[2][32];
+                ptx::tmem_ld_32x32b_x32(t_lane, r[0]);
 #pragma unroll
-                for (int c = 0; c < LP / 32; ++c) {
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32b_x32(t_lane + c * 32, r);
+                for (int c = 0; c < NC; ++c) {
                     ptx::tmem_ld_wait();
+                    if (c + 1 < NC) ptx::tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, r[(c + 1) & 1]);
+                    else if (LP % 32) ptx::tmem_ld_32x32b_x16(t_lane + NC * 32, reinterpret_cast<uint32_t(&)[16]>(r[(c + 1) & 1]));
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (c * 32 + j < L) m = fmaxf(m, __uint_as_float(r[j]));
+                        if (c * 32 + j < L) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[c & 1][j]));
                 }
                 if (LP % 32) {
-                    uint32_t r[16];
-                    ptx::tmem_ld_32x32b_x16(t_lane + (LP / 32) * 32, r);
                     ptx::tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if ((LP / 32) * 32 + j < L) m = fmaxf(m, __uint_as_float(r[j]));
+                        if (NC * 32 + j < L) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[NC & 1][j]));
                 }
+                const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
                 // pass 2: p = exp2((s - m) / 8 * log2 e), fp32 row sum, P -> TMEM as packed 16-bit pairs
                 const float ms = m * sl2;
-                float sum = 0.f;
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                ptx::tmem_ld_32x32b_x32(t_lane, r[0]);
 #pragma unroll
-                for (int c = 0; c < LP / 32; ++c) {
-                    uint32_t r[32], pk[16];
-                    ptx::tmem_ld_32x32b_x32(t_lane + c * 32, r);
+                for (int c = 0; c < NC; ++c) {
+                    uint32_t pk[16];
                     ptx::tmem_ld_wait();
+                    if (c + 1 < NC) ptx::tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, r[(c + 1) & 1]);
+                    else if (LP % 32) ptx::tmem_ld_32x32b_x16(t_lane + NC * 32, reinterpret_cast<uint32_t(&)[16]>(r[(c + 1) & 1]));
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
-                        const float p0 = (c * 32 + j < L) ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -ms)) : 0.f;
-                        const float p1 = (c * 32 + j + 1 < L) ? exp2f(fmaf(__uint_as_float(r[j + 1]), sl2, -ms)) : 0.f;
-                        sum += p0 + p1;
+                        const float p0 = (c * 32 + j < L) ? fast_exp2(fmaf(__uint_as_float(r[c & 1][j]), sl2, -ms)) : 0.f;
+                        const float p1 = (c * 32 + j + 1 < L) ? fast_exp2(fmaf(__uint_as_float(r[c & 1][j + 1]), sl2, -ms)) : 0.f;
+                        s4[(j >> 1) & 3] += p0 + p1;
                         pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
                     }
-                    ptx::tmem_st_32x32b_x16(t_lane + c * 16, pk);       // columns [16c, 16c+16) were read in round <= c
+                    // columns [16c, 16c+16) hold scores consumed in rounds <= c; the in-flight load of round c+1 reads
+                    // columns >= 32(c+1) > 16c+16, so the store cannot clobber unread scores
+                    ptx::tmem_st_32x32b_x16(t_lane + c * 16, pk);
                 }
                 if (LP % 32) {
-                    constexpr int c = LP / 32;
-                    uint32_t r[16], pk[8];
-                    ptx::tmem_ld_32x32b_x16(t_lane + c * 32, r);
+                    uint32_t pk[8];
                     ptx::tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {
-                        const float p0 = (c * 32 + j < L) ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -ms)) : 0.f;
-                        const float p1 = (c * 32 + j + 1 < L) ? exp2f(fmaf(__uint_as_float(r[j + 1]), sl2, -ms)) : 0.f;
-                        sum += p0 + p1;
+                        const float p0 = (NC * 32 + j < L) ? fast_exp2(fmaf(__uint_as_float(r[NC & 1][j]), sl2, -ms)) : 0.f;
+                        const float p1 = (NC * 32 + j + 1 < L) ? fast_exp2(fmaf(__uint_as_float(r[NC & 1][j + 1]), sl2, -ms)) : 0.f;
+                        s4[(j >> 1) & 3] += p0 + p1;
                         pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
                     }
-                    ptx::tmem_st_32x32b_x8(t_lane + c * 16, pk);
+                    ptx::tmem_st_32x32b_x8(t_lane + NC * 16, pk);
                 }
                 ptx::tmem_st_wait();
-                inv_sum = 1.0f / sum;
+                inv_sum = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
             }
             ptx::tc_fence_before();
             __syncthreads();                       // P of all rows is in TMEM (and the V tail is zeroed)
