@@ -399,6 +399,108 @@ static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, 
     return EOE_ERR_SHAPE;
 }
 
+// ------------------------------------------------------------------------------------------ last block, class token only
+// Only token 0 of the last ResidualAttentionBlock reaches ln_post (model.py:231), so for the last block the attention
+// output, out-proj, ln_2 and the MLP are evaluated for the class-token rows alone (the reference computes and discards
+// the other 196 rows).  K and V still come from all tokens.  One warp per (image, head): lanes own keys l, l+32, ...;
+// also gathers the class-token rows of the fp32 residual stream into the compact buffer x_cls [B, width].
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+attention_cls_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ x, uint16_t* __restrict__ h_cls,
+                     float* __restrict__ x_cls, int64_t B, int L, int heads) {
+    __shared__ float s_red[4][32][33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t item = (int64_t)blockIdx.x * 4 + wib;
+    if (item >= B * heads) return;
+    const int width = heads * 64;
+    const int64_t b = item / heads;
+    const int h = (int)(item % heads);
+    auto cvt2 = [](uint32_t u, float& lo, float& hi) {
+        if (BF16) { lo = __uint_as_float(u << 16); hi = __uint_as_float(u & 0xffff0000u); }
+        else { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u)); lo = f.x; hi = f.y; }
+    };
+    if (h == 0)                                     // gather the residual-stream row of the class token
+        for (int i = lane; i < width / 4; i += 32)
+            reinterpret_cast<float4*>(x_cls + b * width)[i] = reinterpret_cast<const float4*>(x + b * L * (int64_t)width)[i];
+    const uint16_t* base = qkv + b * L * (int64_t)(3 * width);
+    float q[64];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + h * 64) + i);
+        cvt2(v.x, q[i * 8], q[i * 8 + 1]); cvt2(v.y, q[i * 8 + 2], q[i * 8 + 3]);
+        cvt2(v.z, q[i * 8 + 4], q[i * 8 + 5]); cvt2(v.w, q[i * 8 + 6], q[i * 8 + 7]);
+    }
+    constexpr int MAXK = 7;                         // keys per lane: L <= 224
+    float sc[MAXK];
+    float m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < MAXK; ++t) {
+        const int j = t * 32 + lane;
+        float d = -INFINITY;
+        if (j < L) {
+            const uint4* kr = reinterpret_cast<const uint4*>(base + (int64_t)j * 3 * width + width + h * 64);
+            d = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 v = __ldg(kr + i);
+                float a0, a1;
+                cvt2(v.x, a0, a1); d += q[i * 8] * a0 + q[i * 8 + 1] * a1;
+                cvt2(v.y, a0, a1); d += q[i * 8 + 2] * a0 + q[i * 8 + 3] * a1;
+                cvt2(v.z, a0, a1); d += q[i * 8 + 4] * a0 + q[i * 8 + 5] * a1;
+                cvt2(v.w, a0, a1); d += q[i * 8 + 6] * a0 + q[i * 8 + 7] * a1;
+            }
+            d *= 0.125f;
+        }
+        sc[t] = d;
+        m = fmaxf(m, d);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < MAXK; ++t) {
+        const int j = t * 32 + lane;
+        if (j < L) {
+            const float pj = __expf(sc[t] - m);
+            sum += pj;
+            const uint4* vr = reinterpret_cast<const uint4*>(base + (int64_t)j * 3 * width + 2 * width + h * 64);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 v = __ldg(vr + i);
+                float a0, a1;
+                cvt2(v.x, a0, a1); o[i * 8] += pj * a0; o[i * 8 + 1] += pj * a1;
+                cvt2(v.y, a0, a1); o[i * 8 + 2] += pj * a0; o[i * 8 + 3] += pj * a1;
+                cvt2(v.z, a0, a1); o[i * 8 + 4] += pj * a0; o[i * 8 + 5] += pj * a1;
+                cvt2(v.w, a0, a1); o[i * 8 + 6] += pj * a0; o[i * 8 + 7] += pj * a1;
+            }
+        }
+    }
+    sum = warp_sum(sum);
+    // reduce the 64 per-lane partial outputs across the warp through shared memory (two 32-column halves)
+    float res[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s_red[wib][lane][i] = o[half * 32 + i];
+        __syncwarp();
+        float acc = 0.f;
+#pragma unroll
+        for (int l2 = 0; l2 < 32; ++l2) acc += s_red[wib][l2][lane];
+        res[half] = acc / sum;
+        __syncwarp();
+    }
+    uint16_t* dst = h_cls + b * width + h * 64;
+    if (BF16) {
+        dst[lane] = __bfloat16_as_ushort(__float2bfloat16_rn(res[0]));
+        dst[32 + lane] = __bfloat16_as_ushort(__float2bfloat16_rn(res[1]));
+    } else {
+        dst[lane] = __half_as_ushort(__float2half_rn(res[0]));
+        dst[32 + lane] = __half_as_ushort(__float2half_rn(res[1]));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ tail
 // feats[b] = ln_post(x[b, 0, :]) @ proj   (model.py:231-234), fp32 throughout (it feeds a 100x cosine logit).
 // Block = 4 images x 128 output columns; proj (1.5 MB, L2 resident) is streamed once per 4 images.  Thread
@@ -474,7 +576,10 @@ struct eoe_vit_plan {
     uint16_t* qkv;       // [B*L, 3*width]
     uint16_t* u;         // [B*L, 4*width]
     float* feats;        // [B, embed]
-    CUtensorMap tm_patches, tm_h, tm_u, tm_conv, tm_qkv;
+    float* x_cls;        // [B, width]   class-token rows of the residual stream (last block)
+    uint16_t* h_cls;     // [B, width]
+    uint16_t* u_cls;     // [B, 4*width]
+    CUtensorMap tm_patches, tm_h, tm_u, tm_conv, tm_qkv, tm_hc, tm_uc;
     CUtensorMap *tm_in, *tm_out, *tm_fc, *tm_proj;     // per layer
     // optional instrumentation (eoe_vit_profile_*): CUDA event pairs around every GEMM launch
     bool profile;
@@ -511,12 +616,12 @@ static int vit_check(const eoe_vit_weights* w) {
     if (w->width != w->heads * 64 || w->width % 256 != 0 || w->width > 1024) return EOE_ERR_SHAPE;
     if ((3 * w->patch * w->patch) % 64 != 0 || w->embed_dim > 1024 || w->embed_dim % 4 != 0 || w->width % 2 != 0) return EOE_ERR_SHAPE;
     const int g = w->resolution / w->patch;
-    if (g * g + 1 > 208) return EOE_ERR_SHAPE;
+    if (g * g + 1 > 208) return EOE_ERR_SHAPE;            // attention kernels: L <= 208 (and 7 keys per lane in the cls path)
     if (w->n_layers <= 0) return EOE_ERR_ARG;
     return EOE_OK;
 }
 
-struct VitLayout { size_t patches, x, h, qkv, u, feats, total; };
+struct VitLayout { size_t patches, x, h, qkv, u, feats, x_cls, h_cls, u_cls, total; };
 static VitLayout vit_layout(const eoe_vit_weights* w, int64_t B) {
     const int g = w->resolution / w->patch;
     const int64_t g2 = g * g, L = g2 + 1, W = w->width;
@@ -529,6 +634,9 @@ static VitLayout vit_layout(const eoe_vit_weights* w, int64_t B) {
     l.qkv = o; o += rup((size_t)(B * L + 256) * 3 * W * 2);
     l.u = o; o += rup((size_t)(B * L + 256) * 4 * W * 2);
     l.feats = o; o += rup((size_t)B * w->embed_dim * 4);
+    l.x_cls = o; o += rup((size_t)B * W * 4);                  // last block, class-token rows only
+    l.h_cls = o; o += rup((size_t)(B + 256) * W * 2);
+    l.u_cls = o; o += rup((size_t)(B + 256) * 4 * W * 2);
     l.total = o;
     return l;
 }
@@ -567,6 +675,9 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     p->qkv = (uint16_t*)(p->ws + lay.qkv);
     p->u = (uint16_t*)(p->ws + lay.u);
     p->feats = (float*)(p->ws + lay.feats);
+    p->x_cls = (float*)(p->ws + lay.x_cls);
+    p->h_cls = (uint16_t*)(p->ws + lay.h_cls);
+    p->u_cls = (uint16_t*)(p->ws + lay.u_cls);
     const int W = w->width, dt = w->operand_dtype;
     const int64_t rows = max_batch * p->L;
     p->tm_in = new CUtensorMap[w->n_layers];
@@ -578,6 +689,8 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     if (!rc) rc = make_tmap(&p->tm_u, p->u, rows, 4 * W, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_conv, w->conv1_w, W, p->kpatch, gemm::CTA_NB, dt);
     if (!rc) rc = make_tmap(&p->tm_qkv, p->qkv, rows + 256, 3 * W, 128, dt);
+    if (!rc) rc = make_tmap(&p->tm_hc, p->h_cls, max_batch, W, gemm::CTA_M, dt);
+    if (!rc) rc = make_tmap(&p->tm_uc, p->u_cls, max_batch, 4 * W, gemm::CTA_M, dt);
     for (int i = 0; i < w->n_layers && !rc; ++i) {
         const eoe_vit_layer& l = p->layers[i];
         rc = make_tmap(&p->tm_in[i], l.in_proj_w, 3 * W, W, gemm::CTA_NB, dt);
@@ -628,26 +741,46 @@ extern "C" int eoe_vit_encode(eoe_vit_plan* p, const float* imgs, int64_t B, flo
     if ((rc = layernorm_dispatch(p->x, w.ln_pre_w, w.ln_pre_b, p->x, EOE_F32, M, W, w.class_embedding,
                                  w.positional_embedding, L, st))) return rc;
     // 4. transformer blocks
+    const float* x_tail = p->x;          // rows that feed ln_post: token 0 of every image
+    int64_t tail_stride_rows = L;
     for (int i = 0; i < w.n_layers; ++i) {
         const eoe_vit_layer& l = p->layers[i];
+        const bool last = (i == w.n_layers - 1);
         if ((rc = layernorm_dispatch(p->x, l.ln_1_w, l.ln_1_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
         gemm::Params g1{M, 3 * W, W, l.in_proj_b, p->qkv, nullptr, 0};
         if ((rc = timed_gemm(p, KIND_QKV, p->tm_h, p->tm_in[i], g1, dt, EOE_EPI_BIAS, st))) return rc;
-        if ((rc = attention_dispatch(p->qkv, p->h, B, L, w.heads, dt, st, &p->tm_qkv))) return rc;
-        gemm::Params g2{M, W, W, l.out_proj_b, p->x, nullptr, 0};
-        if ((rc = timed_gemm(p, KIND_OUT, p->tm_h, p->tm_out[i], g2, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
-        if ((rc = layernorm_dispatch(p->x, l.ln_2_w, l.ln_2_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
-        gemm::Params g3{M, 4 * W, W, l.c_fc_b, p->u, nullptr, 0};
-        if ((rc = timed_gemm(p, KIND_FC, p->tm_h, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
-        gemm::Params g4{M, W, 4 * W, l.c_proj_b, p->x, nullptr, 0};
-        if ((rc = timed_gemm(p, KIND_PROJ, p->tm_u, p->tm_proj[i], g4, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
+        if (!last) {
+            if ((rc = attention_dispatch(p->qkv, p->h, B, L, w.heads, dt, st, &p->tm_qkv))) return rc;
+            gemm::Params g2{M, W, W, l.out_proj_b, p->x, nullptr, 0};
+            if ((rc = timed_gemm(p, KIND_OUT, p->tm_h, p->tm_out[i], g2, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
+            if ((rc = layernorm_dispatch(p->x, l.ln_2_w, l.ln_2_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
+            gemm::Params g3{M, 4 * W, W, l.c_fc_b, p->u, nullptr, 0};
+            if ((rc = timed_gemm(p, KIND_FC, p->tm_h, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
+            gemm::Params g4{M, W, 4 * W, l.c_proj_b, p->x, nullptr, 0};
+            if ((rc = timed_gemm(p, KIND_PROJ, p->tm_u, p->tm_proj[i], g4, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
+        } else {
+            // last block: only the class-token rows are needed downstream (model.py:231)
+            const unsigned grid = (unsigned)((B * w.heads + 3) / 4);
+            if (dt == EOE_BF16) attention_cls_kernel<true><<<grid, 128, 0, st>>>(p->qkv, p->x, p->h_cls, p->x_cls, B, L, w.heads);
+            else attention_cls_kernel<false><<<grid, 128, 0, st>>>(p->qkv, p->x, p->h_cls, p->x_cls, B, L, w.heads);
+            if ((rc = check_launch("attention_cls_kernel"))) return rc;
+            gemm::Params g2{B, W, W, l.out_proj_b, p->x_cls, nullptr, 0};
+            if ((rc = timed_gemm(p, KIND_OUT, p->tm_hc, p->tm_out[i], g2, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
+            if ((rc = layernorm_dispatch(p->x_cls, l.ln_2_w, l.ln_2_b, p->h_cls, dt, B, W, nullptr, nullptr, 1, st))) return rc;
+            gemm::Params g3{B, 4 * W, W, l.c_fc_b, p->u_cls, nullptr, 0};
+            if ((rc = timed_gemm(p, KIND_FC, p->tm_hc, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
+            gemm::Params g4{B, W, 4 * W, l.c_proj_b, p->x_cls, nullptr, 0};
+            if ((rc = timed_gemm(p, KIND_PROJ, p->tm_uc, p->tm_proj[i], g4, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
+            x_tail = p->x_cls;
+            tail_stride_rows = 1;
+        }
     }
     // 5. ln_post + proj (+ zero-shot score head)
     float* feats = feats_out ? feats_out : p->feats;
     {
         const dim3 grid((unsigned)((B + kTailImgs - 1) / kTailImgs), (unsigned)((w.embed_dim + kTailCols - 1) / kTailCols));
         tail_kernel<<<grid, 256, (kTailImgs * W + kTailImgs * kTailCols) * sizeof(float), st>>>(
-            p->x, w.ln_post_w, w.ln_post_b, w.proj, feats, B, L, W, w.embed_dim);
+            x_tail, w.ln_post_w, w.ln_post_b, w.proj, feats, B, (int)tail_stride_rows, W, w.embed_dim);
         if ((rc = check_launch("tail_kernel"))) return rc;
     }
     if (text) {
