@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/eoe_b200.h"
 
 namespace eoe {
@@ -76,6 +78,52 @@ __device__ __forceinline__ void store4_stream<__nv_bfloat16>(__nv_bfloat16* p, c
     __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};"
                  :: "l"(p), "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)) : "memory");
+}
+
+// 8 consecutive 16-bit elements <-> 8 floats in one 16-byte transaction (HSC rows in fp16 / bf16)
+template <typename T>
+__device__ __forceinline__ void load8_stream(const T* p, float (&v)[8]) {
+    uint32_t w[4];
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        } else {
+            const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w[i]));
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store8_stream(T* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (std::is_same<T, __nv_bfloat16>::value) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        } else {
+            __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+// VEC elements per lane per iteration: 4 (fp32, 16 B) or 8 (16-bit, 16 B)
+template <typename T, int VEC>
+__device__ __forceinline__ void loadv_stream(const T* p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) load4_stream<T>(p, v);
+    else load8_stream<T>(p, v);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void storev_stream(T* p, const float (&v)[VEC]) {
+    if constexpr (VEC == 4) store4_stream<T>(p, v);
+    else store8_stream<T>(p, v);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

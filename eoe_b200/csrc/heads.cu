@@ -42,19 +42,19 @@ __device__ __forceinline__ HscRow hsc_row_math(float sumsq, bool nominal, float 
     return r;
 }
 
-template <typename T, int ITERS, int ROWS>
+template <typename T, int VEC, int ITERS, int ROWS>
 __global__ void __launch_bounds__(kHeadBlock)
 hsc_rows_kernel(const T* __restrict__ z, const int64_t* __restrict__ labels, int64_t n, int d,
                 int64_t nominal_label, float* __restrict__ scores, T* __restrict__ grad,
                 HeadWorkspace* ws, float* loss_out, float inv_n_f, double inv_n) {
     const int lane = threadIdx.x & 31;
-    const int nvec = d >> 2;
+    const int nvec = d / VEC;
     const int64_t warp0 = (int64_t)blockIdx.x * kHeadWarps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kHeadWarps;
     float loss_acc = 0.f;
 
     for (int64_t base = warp0 * ROWS; base < n; base += nwarps * ROWS) {
-        float v[ROWS][ITERS][4];
+        float v[ROWS][ITERS][VEC];
         float ss[ROWS];
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
@@ -63,9 +63,10 @@ hsc_rows_kernel(const T* __restrict__ z, const int64_t* __restrict__ labels, int
             for (int it = 0; it < ITERS; ++it) {
                 const int vi = it * 32 + lane;
                 if (row < n && vi < nvec) {
-                    load4_stream<T>(z + row * d + vi * 4, v[r][it]);
+                    loadv_stream<T, VEC>(z + row * d + vi * VEC, v[r][it]);
                 } else {
-                    v[r][it][0] = v[r][it][1] = v[r][it][2] = v[r][it][3] = 0.f;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) v[r][it][e] = 0.f;
                 }
             }
         }
@@ -74,8 +75,8 @@ hsc_rows_kernel(const T* __restrict__ z, const int64_t* __restrict__ labels, int
             float s = 0.f;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it)
-                s += v[r][it][0] * v[r][it][0] + v[r][it][1] * v[r][it][1] + v[r][it][2] * v[r][it][2] +
-                     v[r][it][3] * v[r][it][3];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) s += v[r][it][e] * v[r][it][e];
             ss[r] = warp_sum(s);
         }
 #pragma unroll
@@ -93,9 +94,10 @@ hsc_rows_kernel(const T* __restrict__ z, const int64_t* __restrict__ labels, int
                 for (int it = 0; it < ITERS; ++it) {
                     const int vi = it * 32 + lane;
                     if (vi < nvec) {
-                        float g[4] = {h.coef * v[r][it][0], h.coef * v[r][it][1], h.coef * v[r][it][2],
-                                      h.coef * v[r][it][3]};
-                        store4_stream<T>(grad + row * d + vi * 4, g);
+                        float g[VEC];
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) g[e] = h.coef * v[r][it][e];
+                        storev_stream<T, VEC>(grad + row * d + vi * VEC, g);
                     }
                 }
             }
@@ -150,21 +152,20 @@ static int hsc_launch(const void* z_, const int64_t* labels, int64_t n, int64_t 
     HeadWorkspace* ws = (HeadWorkspace*)ws_;
     const float inv_n_f = 1.0f / (float)n;
     const double inv_n = 1.0 / (double)n;
-    const size_t vec_bytes = 4 * sizeof(T);
-    const bool vec_ok = (d % 4 == 0) && d <= 1024 && ((uintptr_t)z % vec_bytes == 0) &&
-                        (!grad || (uintptr_t)grad % vec_bytes == 0);
+    constexpr int VEC = sizeof(T) == 4 ? 4 : 8;            // 16 bytes per lane per access
+    const bool vec_ok = (d % VEC == 0) && d <= 32 * VEC * 8 && ((uintptr_t)z % 16 == 0) && (!grad || (uintptr_t)grad % 16 == 0);
     if (!vec_ok) {
         hsc_rows_generic_kernel<T><<<head_grid(n, kHeadWarps), kHeadBlock, 0, st>>>(
             z, labels, n, d, nominal, scores, grad, ws, loss_out, inv_n_f, inv_n);
         return check_launch("hsc_rows_generic_kernel");
     }
-    const int iters = (int)((d / 4 + 31) / 32);
+    const int iters = (int)((d / VEC + 31) / 32);
 #define EOE_HSC_CASE(IT, RW)                                                                           \
-    hsc_rows_kernel<T, IT, RW><<<head_grid(n, kHeadWarps * RW), kHeadBlock, 0, st>>>(                   \
+    hsc_rows_kernel<T, VEC, IT, RW><<<head_grid(n, kHeadWarps * RW), kHeadBlock, 0, st>>>(              \
         z, labels, n, (int)d, nominal, scores, grad, ws, loss_out, inv_n_f, inv_n)
     if (iters <= 1) EOE_HSC_CASE(1, 4);
-    else if (iters <= 2) EOE_HSC_CASE(2, 4);
-    else if (iters <= 4) EOE_HSC_CASE(4, 2);
+    else if (iters <= 2) EOE_HSC_CASE(2, VEC == 4 ? 4 : 2);
+    else if (iters <= 4) EOE_HSC_CASE(4, VEC == 4 ? 2 : 1);
     else EOE_HSC_CASE(8, 1);
 #undef EOE_HSC_CASE
     return check_launch("hsc_rows_kernel");
@@ -196,24 +197,37 @@ bce_kernel(const T* __restrict__ x, const int64_t* __restrict__ labels, int64_t 
     int64_t done = 0;
     if (VEC) {
         const int64_t n4 = n >> 2;
-        for (int64_t i = tid; i < n4; i += nthreads) {
-            float xv[4], sc[4], g[4];
-            load4_stream<T>(x + i * 4, xv);
-            float y[4] = {0.f, 0.f, 0.f, 0.f};
-            if (labels) {
-                longlong2 l0 = __ldg(reinterpret_cast<const longlong2*>(labels + i * 4));
-                longlong2 l1 = __ldg(reinterpret_cast<const longlong2*>(labels + i * 4) + 1);
-                y[0] = (float)l0.x; y[1] = (float)l0.y; y[2] = (float)l1.x; y[3] = (float)l1.y;
+        // two independent 4-sample groups per iteration: 6 x 16-byte loads in flight per thread before any store
+        for (int64_t i0 = tid; i0 < n4; i0 += 2 * nthreads) {
+            const int64_t idx[2] = {i0, i0 + nthreads};
+            float xv[2][4];
+            longlong2 lb[2][2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (idx[u] < n4) {
+                    load4_stream<T>(x + idx[u] * 4, xv[u]);
+                    if (labels) {
+                        lb[u][0] = __ldg(reinterpret_cast<const longlong2*>(labels + idx[u] * 4));
+                        lb[u][1] = __ldg(reinterpret_cast<const longlong2*>(labels + idx[u] * 4) + 1);
+                    }
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                BceOut o = bce_math(xv[j], y[j]);
-                loss_acc += o.loss;
-                sc[j] = flip_score ? 1.0f - o.sig : o.sig;
-                g[j] = (o.sig - y[j]) * inv_n_f;
+            for (int u = 0; u < 2; ++u) {
+                if (idx[u] >= n4) continue;
+                float y[4] = {0.f, 0.f, 0.f, 0.f};
+                if (labels) { y[0] = (float)lb[u][0].x; y[1] = (float)lb[u][0].y; y[2] = (float)lb[u][1].x; y[3] = (float)lb[u][1].y; }
+                float sc[4], g[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    BceOut o = bce_math(xv[u][j], y[j]);
+                    loss_acc += o.loss;
+                    sc[j] = flip_score ? 1.0f - o.sig : o.sig;
+                    g[j] = (o.sig - y[j]) * inv_n_f;
+                }
+                if (scores) store4_stream<float>(scores + idx[u] * 4, sc);
+                if (grad) store4_stream<T>(grad + idx[u] * 4, g);
             }
-            if (scores) store4_stream<float>(scores + i * 4, sc);
-            if (grad) store4_stream<T>(grad + i * 4, g);
         }
         done = n4 << 2;
     }
@@ -238,7 +252,7 @@ static int bce_launch(const void* x_, const int64_t* labels, int64_t n, int64_t 
     const size_t vb = 4 * sizeof(T);
     const bool vec = ((uintptr_t)x % vb == 0) && (!grad || (uintptr_t)grad % vb == 0) &&
                      (!labels || (uintptr_t)labels % 16 == 0) && (!scores || (uintptr_t)scores % 16 == 0);
-    const int grid = head_grid(n, kHeadBlock * 4);
+    const int grid = head_grid(n, kHeadBlock * 8);
     if (vec)
         bce_kernel<T, true><<<grid, kHeadBlock, 0, st>>>(x, labels, n, nominal != 0, scores, grad,
                                                          (HeadWorkspace*)ws_, loss_out, inv_n_f, inv_n);
