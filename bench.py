@@ -241,8 +241,8 @@ def run_ours(args):
     job(W, scores, labels)
     sync()
 
-    # ---- timed region: device-resident inputs, GEMM launches bracketed by events for the roofline
-    enc.profile(True)
+    # ---- timed region (device-resident inputs).  Pass 1 is clean and gives `value`; pass 2 repeats the identical K
+    # steps with every GEMM launch bracketed by a CUDA event pair (98 events per step) and gives the roofline.
     launches0 = _lib.lib().eoe_launch_count()
     sync()
     clocks.begin()
@@ -255,6 +255,14 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
     launches = _lib.lib().eoe_launch_count() - launches0
+    auc_val = float(auc_out[0].item())
+    enc.profile(True)
+    sync()
+    e0.record()
+    job(S, scores, labels)
+    e1.record()
+    sync()
+    ms_prof = e0.elapsed_time(e1)
     prof = enc.profile_read()
     enc.profile(False)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -262,7 +270,6 @@ def run_ours(args):
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = ws * S * B / (ms_max / 1e3)
-    auc_val = float(auc_out[0].item())
 
     # ---- e2e: the same job through the public API with HOST (pinned) image batches and host score reads
     host = [torch.randn(B, 3, 224, 224).pin_memory() for _ in range(2)]
@@ -325,7 +332,8 @@ def run_ours(args):
         "bound": "tensor", "kernel": "eoe::gemm::gemm_kernel (tcgen05, all 49 GEMM launches per step)",
         "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
         "traffic": traffic, "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
-        "launches": g_n, "gemm_ms_per_step": g_ms / S, "gemm_share_of_step": g_ms / ms,
+        "launches": g_n, "gemm_ms_per_step": g_ms / S, "gemm_share_of_step": g_ms / ms_prof,
+        "ms_per_step_instrumented": ms_prof / S,
         "per_kind_tflops": {k: (v[2] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else None) for k, v in prof.items()},
         "encoder_tensor_frac": value / ws * GFLOP_PER_IMG[P] * 1e9 / 1e12 / pk["tf_sust"],
     }
