@@ -324,14 +324,23 @@ def run_ours(args):
     g_fl = sum(v[2] for v in prof.values())
     g_n = sum(v[1] for v in prof.values())
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        if tj.get("batch") == B and P == 16:          # ncu capture of the c_fc GEMM at this batch size
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = {"kernel": tj.get("kernel"), "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"),
+                            "source": tj.get("source")}
+    fc = prof.get("c_fc", (0.0, 0, 0.0))
     roofline = {
         "bound": "tensor", "kernel": "eoe::gemm::gemm_kernel (tcgen05, all 49 GEMM launches per step)",
         "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
-        "traffic": traffic, "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
+        "traffic": traffic, "traffic_of": traffic_note,
+        "dominant_instance": {"kernel": "gemm_kernel<bias+QuickGELU> (c_fc)", "launches": fc[1],
+                              "achieved": (fc[2] / (fc[0] * 1e-3) / 1e12 if fc[0] > 0 else None), "unit": "TFLOP/s",
+                              "flops_per_launch": (fc[2] / fc[1] if fc[1] else None), "us_per_launch": (1e3 * fc[0] / fc[1] if fc[1] else None)},
+        "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
         "launches": g_n, "gemm_ms_per_step": g_ms / S, "gemm_share_of_step": g_ms / ms_prof,
         "ms_per_step_instrumented": ms_prof / S,
         "per_kind_tflops": {k: (v[2] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else None) for k, v in prof.items()},
