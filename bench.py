@@ -214,7 +214,7 @@ def run_ours(args):
     op_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
 
     sd = random_vit_state_dict(P, seed=0)
-    enc = ClipImageEncoder(sd, device=dev, operand_dtype=op_dtype, max_batch=B)
+    enc = ClipImageEncoder(sd, device=dev, operand_dtype=op_dtype, max_batch=B, fold_layernorm=not args.no_fold)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     imgs = [torch.randn(B, 3, 224, 224, device=dev, generator=g) for _ in range(2)]     # 2 x 308 MB at B=512: > L2
     text = torch.nn.functional.normalize(torch.randn(K, 512, device=dev, generator=g), dim=-1)
@@ -389,6 +389,7 @@ def main():
     ap.add_argument("--ref-images", type=int, default=64, help="images per step of the CPU port (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side", action="store_true")
+    ap.add_argument("--no-fold", action="store_true", help="stand-alone ln_1 / ln_2 kernels instead of the LayerNorm fold (A/B)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3            # timing rule: at least 3 warm-up steps

@@ -9,7 +9,9 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeoe_b200.so")
+# EOE_B200_LIB selects another build of the same library (A/B timing of kernel versions, tools/ab_encoder.py); there is
+# still no fallback: the named file must exist and export the full ABI.
+LIB_PATH = os.environ.get("EOE_B200_LIB") or os.path.join(_HERE, "libeoe_b200.so")
 
 EOE_F32, EOE_F16, EOE_BF16 = 0, 1, 2
 EOE_HEAD_WS_BYTES = 32768
@@ -18,6 +20,8 @@ EOE_AUC_WITH_PRC = 2
 EOE_AUC_STATUS_NONFINITE = 1
 EOE_AUC_STATUS_SINGLE_CLASS = 2
 EOE_EPI_BIAS, EOE_EPI_BIAS_QUICKGELU, EOE_EPI_BIAS_RESIDUAL_F32, EOE_EPI_PATCH_EMBED = 0, 1, 2, 3
+EOE_EPI_LNFOLD_BIAS, EOE_EPI_LNFOLD_QUICKGELU, EOE_EPI_RESIDUAL_STATS = 4, 5, 6
+EOE_ABI_VERSION = 2
 
 DTYPE_CODE = {torch.float32: EOE_F32, torch.float16: EOE_F16, torch.bfloat16: EOE_BF16}
 
@@ -29,7 +33,8 @@ class EoeError(RuntimeError):
 class VitLayer(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "ln_1_w", "ln_1_b", "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b",
-        "ln_2_w", "ln_2_b", "c_fc_w", "c_fc_b", "c_proj_w", "c_proj_b")]
+        "ln_2_w", "ln_2_b", "c_fc_w", "c_fc_b", "c_proj_w", "c_proj_b",
+        "in_proj_wf", "in_proj_c1", "in_proj_c2", "c_fc_wf", "c_fc_c1", "c_fc_c2")]
 
 
 class VitWeights(C.Structure):
@@ -65,6 +70,9 @@ SIGNATURES = {
     "eoe_vit_profile_enable": (_I, [_P, _I]),
     "eoe_vit_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(C.c_double)]),
     "eoe_gemm": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _I, _I, _P, _I64, _P]),
+    "eoe_vit_fold_layernorm": (_I, [_P, _P, _P, _P, _I64, _I64, _I, _P, _P, _P, _P]),
+    "eoe_gemm_lnfold": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _I, _P]),
+    "eoe_gemm_residual_stats": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P]),
     "eoe_layernorm": (_I, [_P, _P, _P, _P, _I, _I64, _I64, _P]),
     "eoe_attention": (_I, [_P, _P, _I64, _I64, _I64, _I, _P]),
 }

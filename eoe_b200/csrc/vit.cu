@@ -65,19 +65,24 @@ static int num_sms() {
     return n;
 }
 
+static int g_gemm_debug = 0;            // eoe_debug_set(): diagnostics only, 0 in production
+
 template <int EPI, bool BF16>
-static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, cudaStream_t st) {
+static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p_in, cudaStream_t st) {
+    gemm::Params p = p_in;
+    p.dbg = g_gemm_debug;
     auto kern = gemm::gemm_kernel<EPI, BF16>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::Cfg<EPI>::kSmemBytes);
         if (e != cudaSuccess) { set_cuda_error(e, "gemm smem attr"); return EOE_ERR_CUDA; }
         attr_done = true;
     }
     const int64_t tiles = ((p.M + gemm::BM - 1) / gemm::BM) * (p.N / gemm::BN);
-    const int64_t pairs = num_sms() / 2;                              // one CTA pair (cluster of 2) per tile at a time
+    int64_t pairs = num_sms() / 2;                                    // one CTA pair (cluster of 2) per tile at a time
+    if (g_gemm_debug >> 8) pairs = g_gemm_debug >> 8;                 // diagnostics: restrict the grid
     const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
-    kern<<<grid, gemm::THREADS, gemm::SMEM_BYTES, st>>>(ta, tb, p);
+    kern<<<grid, gemm::THREADS, gemm::Cfg<EPI>::kSmemBytes, st>>>(ta, tb, p);
     return check_launch("gemm_kernel");
 }
 
@@ -89,6 +94,12 @@ static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const gemm:
         case EOE_EPI_BIAS_QUICKGELU: return bf ? gemm_launch_t<EOE_EPI_BIAS_QUICKGELU, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_BIAS_QUICKGELU, false>(ta, tb, p, st);
         case EOE_EPI_BIAS_RESIDUAL_F32: return bf ? gemm_launch_t<EOE_EPI_BIAS_RESIDUAL_F32, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_BIAS_RESIDUAL_F32, false>(ta, tb, p, st);
         case EOE_EPI_PATCH_EMBED: return bf ? gemm_launch_t<EOE_EPI_PATCH_EMBED, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_PATCH_EMBED, false>(ta, tb, p, st);
+        case EOE_EPI_LNFOLD_BIAS: return bf ? gemm_launch_t<EOE_EPI_LNFOLD_BIAS, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_LNFOLD_BIAS, false>(ta, tb, p, st);
+        case EOE_EPI_LNFOLD_QUICKGELU: return bf ? gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU, false>(ta, tb, p, st);
+        case EOE_EPI_RESIDUAL_STATS:
+            if (p.K <= 1024)      // HBM-bound shapes (out_proj): cp.async residual pipeline; see gemm::Cfg
+                return bf ? gemm_launch_t<gemm::EPI_RESIDUAL_STATS_ASYNC, true>(ta, tb, p, st) : gemm_launch_t<gemm::EPI_RESIDUAL_STATS_ASYNC, false>(ta, tb, p, st);
+            return bf ? gemm_launch_t<EOE_EPI_RESIDUAL_STATS, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_RESIDUAL_STATS, false>(ta, tb, p, st);
         default: return EOE_ERR_ARG;
     }
 }
@@ -210,6 +221,106 @@ static int layernorm_dispatch(const float* x, const float* w, const float* b, vo
         case EOE_F16: return layernorm_launch<__half>(x, w, b, y, M, width, cls_emb, pos0, L, st);
         case EOE_BF16: return layernorm_launch<__nv_bfloat16>(x, w, b, y, M, width, cls_emb, pos0, L, st);
         default: return EOE_ERR_DTYPE;
+    }
+}
+
+// ln_pre for the LayerNorm-folded encoder: y = LN(x) in place (fp32, class-token rows synthesised as above) plus what the
+// first folded GEMM needs: xb = round16(y) and stats[row][0] = (sum y, sum y^2), stats[row][1..nch) = 0.
+template <bool BF16, int ITERS>
+__global__ void __launch_bounds__(256)
+ln_pre_stats_kernel(float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                    uint16_t* __restrict__ xb, float2* __restrict__ stats, int64_t M, int width,
+                    const float* __restrict__ cls_emb, const float* __restrict__ pos0, int L) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nvec = width >> 2;
+    float v[ITERS][4];
+    const bool is_cls = (row % L) == 0;
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int vi = it * 32 + lane;
+        if (vi < nvec) {
+            if (is_cls) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(cls_emb) + vi);
+                const float4 c = __ldg(reinterpret_cast<const float4*>(pos0) + vi);
+                v[it][0] = a.x + c.x; v[it][1] = a.y + c.y; v[it][2] = a.z + c.z; v[it][3] = a.w + c.w;
+            } else {
+                const float4 a = *(reinterpret_cast<const float4*>(x + row * width) + vi);
+                v[it][0] = a.x; v[it][1] = a.y; v[it][2] = a.z; v[it][3] = a.w;
+            }
+        } else {
+            v[it][0] = v[it][1] = v[it][2] = v[it][3] = 0.f;
+        }
+        s += v[it][0] + v[it][1] + v[it][2] + v[it][3];
+    }
+    const float mean = warp_sum(s) / (float)width;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int vi = it * 32 + lane;
+        if (vi < nvec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float dlt = v[it][j] - mean; q += dlt * dlt; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)width + 1e-5f);
+    float ys = 0.f, yq = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int vi = it * 32 + lane;
+        if (vi < nvec) {
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + vi);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + vi);
+            const float o[4] = {(v[it][0] - mean) * rstd * ww.x + bb.x, (v[it][1] - mean) * rstd * ww.y + bb.y,
+                                (v[it][2] - mean) * rstd * ww.z + bb.z, (v[it][3] - mean) * rstd * ww.w + bb.w};
+            *reinterpret_cast<float4*>(x + row * width + vi * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint2*>(xb + row * width + vi * 4) =
+                make_uint2(gemm::pack2<BF16>(o[0], o[1]), gemm::pack2<BF16>(o[2], o[3]));
+            ys += (o[0] + o[1]) + (o[2] + o[3]);
+            yq += (o[0] * o[0] + o[1] * o[1]) + (o[2] * o[2] + o[3] * o[3]);
+        }
+    }
+    ys = warp_sum(ys);
+    yq = warp_sum(yq);
+    const int nch = width >> 7;
+    if (lane < nch) stats[row * nch + lane] = lane == 0 ? make_float2(ys, yq) : make_float2(0.f, 0.f);
+}
+
+// LayerNorm fold of one Linear (eoe_vit_fold_layernorm): one warp per output row n.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+               const float* __restrict__ bias, int64_t N, int64_t K, uint16_t* __restrict__ wf,
+               float* __restrict__ c1, float* __restrict__ c2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= N) return;
+    float s1 = 0.f, s2 = 0.f;
+    for (int64_t k = lane * 4; k < K; k += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(w + n * K + k);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(ln_w + k));
+        const float4 be = __ldg(reinterpret_cast<const float4*>(ln_b + k));
+        const uint32_t p0 = gemm::pack2<BF16>(a.x * g.x, a.y * g.y), p1 = gemm::pack2<BF16>(a.z * g.z, a.w * g.w);
+        *reinterpret_cast<uint2*>(wf + n * K + k) = make_uint2(p0, p1);
+        float r[4];
+        if (BF16) {
+            r[0] = __uint_as_float(p0 << 16); r[1] = __uint_as_float(p0 & 0xffff0000u);
+            r[2] = __uint_as_float(p1 << 16); r[3] = __uint_as_float(p1 & 0xffff0000u);
+        } else {
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&p0));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&p1));
+            r[0] = f0.x; r[1] = f0.y; r[2] = f1.x; r[3] = f1.y;
+        }
+        s1 += (r[0] + r[1]) + (r[2] + r[3]);
+        s2 += (a.x * be.x + a.y * be.y) + (a.z * be.z + a.w * be.w);
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+        c1[n] = s1;
+        c2[n] = s2 + (bias ? bias[n] : 0.f);
     }
 }
 
@@ -579,8 +690,12 @@ struct eoe_vit_plan {
     float* x_cls;        // [B, width]   class-token rows of the residual stream (last block)
     uint16_t* h_cls;     // [B, width]
     uint16_t* u_cls;     // [B, 4*width]
-    CUtensorMap tm_patches, tm_h, tm_u, tm_conv, tm_qkv, tm_hc, tm_uc;
+    uint16_t* xb;        // [B*L, width] 16-bit copy of the residual stream (LayerNorm-folded path)
+    float2* stats;       // [B*L, width/128] per-row chunk (sum, sum of squares) of the residual stream
+    bool fused_ln;       // every layer carries folded in_proj / c_fc weights: no stand-alone ln_1 / ln_2 launches
+    CUtensorMap tm_patches, tm_h, tm_u, tm_conv, tm_qkv, tm_hc, tm_uc, tm_xb;
     CUtensorMap *tm_in, *tm_out, *tm_fc, *tm_proj;     // per layer
+    CUtensorMap *tm_inf, *tm_fcf;                      // per layer, LayerNorm-folded weights
     // optional instrumentation (eoe_vit_profile_*): CUDA event pairs around every GEMM launch
     bool profile;
     struct Span { cudaEvent_t a, b; int kind; double flops; };
@@ -618,10 +733,26 @@ static int vit_check(const eoe_vit_weights* w) {
     const int g = w->resolution / w->patch;
     if (g * g + 1 > 208) return EOE_ERR_SHAPE;            // attention kernels: L <= 208 (and 7 keys per lane in the cls path)
     if (w->n_layers <= 0) return EOE_ERR_ARG;
+    int folded = 0;
+    for (int i = 0; i < w->n_layers; ++i) {
+        const eoe_vit_layer& l = w->layers_host[i];
+        const int have = (l.in_proj_wf != nullptr) + (l.in_proj_c1 != nullptr) + (l.in_proj_c2 != nullptr) +
+                         (l.c_fc_wf != nullptr) + (l.c_fc_c1 != nullptr) + (l.c_fc_c2 != nullptr);
+        if (have != 0 && have != 6) return EOE_ERR_ARG;         // all six folded tensors of a layer or none
+        folded += have == 6;
+    }
+    if (folded != 0 && folded != w->n_layers) return EOE_ERR_ARG;   // every layer or none
+    for (int i = 0; i < w->n_layers; ++i) {                         // epilogue parameter vectors travel by 16-byte cp.async
+        const eoe_vit_layer& l = w->layers_host[i];
+        const void* v[] = {l.in_proj_b, l.out_proj_b, l.c_fc_b, l.c_proj_b, l.in_proj_c1, l.in_proj_c2, l.c_fc_c1, l.c_fc_c2};
+        for (const void* q : v)
+            if ((uintptr_t)q % 16 != 0) return EOE_ERR_ALIGN;
+    }
     return EOE_OK;
 }
+static bool vit_fused_ln(const eoe_vit_weights* w) { return w->layers_host[0].in_proj_wf != nullptr; }
 
-struct VitLayout { size_t patches, x, h, qkv, u, feats, x_cls, h_cls, u_cls, total; };
+struct VitLayout { size_t patches, x, h, qkv, u, feats, x_cls, h_cls, u_cls, xb, stats, total; };
 static VitLayout vit_layout(const eoe_vit_weights* w, int64_t B) {
     const int g = w->resolution / w->patch;
     const int64_t g2 = g * g, L = g2 + 1, W = w->width;
@@ -637,6 +768,11 @@ static VitLayout vit_layout(const eoe_vit_weights* w, int64_t B) {
     l.x_cls = o; o += rup((size_t)B * W * 4);                  // last block, class-token rows only
     l.h_cls = o; o += rup((size_t)(B + 256) * W * 2);
     l.u_cls = o; o += rup((size_t)(B + 256) * 4 * W * 2);
+    l.xb = o; l.stats = o;
+    if (vit_fused_ln(w)) {
+        o += rup((size_t)(B * L + 256) * W * 2);
+        l.stats = o; o += rup((size_t)(B * L) * (W / 128) * sizeof(float2));
+    }
     l.total = o;
     return l;
 }
@@ -678,12 +814,17 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     p->x_cls = (float*)(p->ws + lay.x_cls);
     p->h_cls = (uint16_t*)(p->ws + lay.h_cls);
     p->u_cls = (uint16_t*)(p->ws + lay.u_cls);
+    p->fused_ln = vit_fused_ln(w);
+    p->xb = (uint16_t*)(p->ws + lay.xb);
+    p->stats = (float2*)(p->ws + lay.stats);
     const int W = w->width, dt = w->operand_dtype;
     const int64_t rows = max_batch * p->L;
     p->tm_in = new CUtensorMap[w->n_layers];
     p->tm_out = new CUtensorMap[w->n_layers];
     p->tm_fc = new CUtensorMap[w->n_layers];
     p->tm_proj = new CUtensorMap[w->n_layers];
+    p->tm_inf = new CUtensorMap[w->n_layers];
+    p->tm_fcf = new CUtensorMap[w->n_layers];
     rc = make_tmap(&p->tm_patches, p->patches, max_batch * p->g2, p->kpatch, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_h, p->h, rows, W, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_u, p->u, rows, 4 * W, gemm::CTA_M, dt);
@@ -697,7 +838,10 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
         if (!rc) rc = make_tmap(&p->tm_out[i], l.out_proj_w, W, W, gemm::CTA_NB, dt);
         if (!rc) rc = make_tmap(&p->tm_fc[i], l.c_fc_w, 4 * W, W, gemm::CTA_NB, dt);
         if (!rc) rc = make_tmap(&p->tm_proj[i], l.c_proj_w, W, 4 * W, gemm::CTA_NB, dt);
+        if (!rc && p->fused_ln) rc = make_tmap(&p->tm_inf[i], l.in_proj_wf, 3 * W, W, gemm::CTA_NB, dt);
+        if (!rc && p->fused_ln) rc = make_tmap(&p->tm_fcf[i], l.c_fc_wf, 4 * W, W, gemm::CTA_NB, dt);
     }
+    if (!rc && p->fused_ln) rc = make_tmap(&p->tm_xb, p->xb, rows, W, gemm::CTA_M, dt);
     if (rc) { eoe_vit_plan_destroy(p); return rc; }
     *plan_out = p;
     return EOE_OK;
@@ -711,6 +855,8 @@ extern "C" void eoe_vit_plan_destroy(eoe_vit_plan* p) {
     delete[] p->tm_out;
     delete[] p->tm_fc;
     delete[] p->tm_proj;
+    delete[] p->tm_inf;
+    delete[] p->tm_fcf;
     delete p;
 }
 
@@ -734,42 +880,64 @@ extern "C" int eoe_vit_encode(eoe_vit_plan* p, const float* imgs, int64_t B, flo
     }
     // 2. patch-embed GEMM, epilogue adds positional embedding and scatters to token rows 1..g2 of each image
     {
-        gemm::Params gp{Mp, W, p->kpatch, nullptr, p->x, w.positional_embedding, p->g2};
+        gemm::Params gp{Mp, W, p->kpatch, nullptr, p->x, w.positional_embedding, p->g2, nullptr, nullptr, nullptr};
         if ((rc = timed_gemm(p, KIND_PATCH, p->tm_patches, p->tm_conv, gp, dt, EOE_EPI_PATCH_EMBED, st))) return rc;
     }
     // 3. class token + ln_pre (in place, fp32)
-    if ((rc = layernorm_dispatch(p->x, w.ln_pre_w, w.ln_pre_b, p->x, EOE_F32, M, W, w.class_embedding,
-                                 w.positional_embedding, L, st))) return rc;
+    if (!p->fused_ln) {
+        if ((rc = layernorm_dispatch(p->x, w.ln_pre_w, w.ln_pre_b, p->x, EOE_F32, M, W, w.class_embedding,
+                                     w.positional_embedding, L, st))) return rc;
+    } else {
+        const int grid = (int)((M + 7) / 8);
+#define EOE_LN_PRE(BF, IT) ln_pre_stats_kernel<BF, IT><<<grid, 256, 0, st>>>( \
+        p->x, w.ln_pre_w, w.ln_pre_b, p->xb, p->stats, M, W, w.class_embedding, w.positional_embedding, L)
+        if (dt == EOE_BF16) { if (W <= 768) EOE_LN_PRE(true, 6); else EOE_LN_PRE(true, 8); }
+        else { if (W <= 768) EOE_LN_PRE(false, 6); else EOE_LN_PRE(false, 8); }
+#undef EOE_LN_PRE
+        if ((rc = check_launch("ln_pre_stats_kernel"))) return rc;
+    }
     // 4. transformer blocks
     const float* x_tail = p->x;          // rows that feed ln_post: token 0 of every image
     int64_t tail_stride_rows = L;
+    const int epi_res = p->fused_ln ? EOE_EPI_RESIDUAL_STATS : EOE_EPI_BIAS_RESIDUAL_F32;
     for (int i = 0; i < w.n_layers; ++i) {
         const eoe_vit_layer& l = p->layers[i];
         const bool last = (i == w.n_layers - 1);
-        if ((rc = layernorm_dispatch(p->x, l.ln_1_w, l.ln_1_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
-        gemm::Params g1{M, 3 * W, W, l.in_proj_b, p->qkv, nullptr, 0};
-        if ((rc = timed_gemm(p, KIND_QKV, p->tm_h, p->tm_in[i], g1, dt, EOE_EPI_BIAS, st))) return rc;
+        if (!p->fused_ln) {
+            if ((rc = layernorm_dispatch(p->x, l.ln_1_w, l.ln_1_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
+            gemm::Params g1{M, 3 * W, W, l.in_proj_b, p->qkv, nullptr, 0, nullptr, nullptr, nullptr};
+            if ((rc = timed_gemm(p, KIND_QKV, p->tm_h, p->tm_in[i], g1, dt, EOE_EPI_BIAS, st))) return rc;
+        } else {
+            // ln_1 folded into the QKV GEMM: A = 16-bit residual stream, epilogue rstd*(acc - mean*c1) + c2
+            gemm::Params g1{M, 3 * W, W, l.in_proj_c2, p->qkv, l.in_proj_c1, 0, p->stats, nullptr, nullptr};
+            if ((rc = timed_gemm(p, KIND_QKV, p->tm_xb, p->tm_inf[i], g1, dt, EOE_EPI_LNFOLD_BIAS, st))) return rc;
+        }
         if (!last) {
             if ((rc = attention_dispatch(p->qkv, p->h, B, L, w.heads, dt, st, &p->tm_qkv))) return rc;
-            gemm::Params g2{M, W, W, l.out_proj_b, p->x, nullptr, 0};
-            if ((rc = timed_gemm(p, KIND_OUT, p->tm_h, p->tm_out[i], g2, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
-            if ((rc = layernorm_dispatch(p->x, l.ln_2_w, l.ln_2_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
-            gemm::Params g3{M, 4 * W, W, l.c_fc_b, p->u, nullptr, 0};
-            if ((rc = timed_gemm(p, KIND_FC, p->tm_h, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
-            gemm::Params g4{M, W, 4 * W, l.c_proj_b, p->x, nullptr, 0};
-            if ((rc = timed_gemm(p, KIND_PROJ, p->tm_u, p->tm_proj[i], g4, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
+            gemm::Params g2{M, W, W, l.out_proj_b, p->x, nullptr, 0, nullptr, p->stats, p->xb};
+            if ((rc = timed_gemm(p, KIND_OUT, p->tm_h, p->tm_out[i], g2, dt, epi_res, st))) return rc;
+            if (!p->fused_ln) {
+                if ((rc = layernorm_dispatch(p->x, l.ln_2_w, l.ln_2_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
+                gemm::Params g3{M, 4 * W, W, l.c_fc_b, p->u, nullptr, 0, nullptr, nullptr, nullptr};
+                if ((rc = timed_gemm(p, KIND_FC, p->tm_h, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
+            } else {
+                gemm::Params g3{M, 4 * W, W, l.c_fc_c2, p->u, l.c_fc_c1, 0, p->stats, nullptr, nullptr};
+                if ((rc = timed_gemm(p, KIND_FC, p->tm_xb, p->tm_fcf[i], g3, dt, EOE_EPI_LNFOLD_QUICKGELU, st))) return rc;
+            }
+            gemm::Params g4{M, W, 4 * W, l.c_proj_b, p->x, nullptr, 0, nullptr, p->stats, p->xb};
+            if ((rc = timed_gemm(p, KIND_PROJ, p->tm_u, p->tm_proj[i], g4, dt, epi_res, st))) return rc;
         } else {
             // last block: only the class-token rows are needed downstream (model.py:231)
             const unsigned grid = (unsigned)((B * w.heads + 3) / 4);
             if (dt == EOE_BF16) attention_cls_kernel<true><<<grid, 128, 0, st>>>(p->qkv, p->x, p->h_cls, p->x_cls, B, L, w.heads);
             else attention_cls_kernel<false><<<grid, 128, 0, st>>>(p->qkv, p->x, p->h_cls, p->x_cls, B, L, w.heads);
             if ((rc = check_launch("attention_cls_kernel"))) return rc;
-            gemm::Params g2{B, W, W, l.out_proj_b, p->x_cls, nullptr, 0};
+            gemm::Params g2{B, W, W, l.out_proj_b, p->x_cls, nullptr, 0, nullptr, nullptr, nullptr};
             if ((rc = timed_gemm(p, KIND_OUT, p->tm_hc, p->tm_out[i], g2, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
             if ((rc = layernorm_dispatch(p->x_cls, l.ln_2_w, l.ln_2_b, p->h_cls, dt, B, W, nullptr, nullptr, 1, st))) return rc;
-            gemm::Params g3{B, 4 * W, W, l.c_fc_b, p->u_cls, nullptr, 0};
+            gemm::Params g3{B, 4 * W, W, l.c_fc_b, p->u_cls, nullptr, 0, nullptr, nullptr, nullptr};
             if ((rc = timed_gemm(p, KIND_FC, p->tm_hc, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
-            gemm::Params g4{B, W, 4 * W, l.c_proj_b, p->x_cls, nullptr, 0};
+            gemm::Params g4{B, W, 4 * W, l.c_proj_b, p->x_cls, nullptr, 0, nullptr, nullptr, nullptr};
             if ((rc = timed_gemm(p, KIND_PROJ, p->tm_uc, p->tm_proj[i], g4, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
             x_tail = p->x_cls;
             tail_stride_rows = 1;
@@ -821,12 +989,66 @@ extern "C" int eoe_gemm(const void* A, const void* Wt, const float* bias, void* 
     int rc = gemm_check(M, N, K, operand_dtype);
     if (rc) return rc;
     if (epilogue == EOE_EPI_PATCH_EMBED && (!aux || aux_i <= 0)) return EOE_ERR_ARG;
-    if ((uintptr_t)A % 16 != 0 || (uintptr_t)Wt % 16 != 0 || (uintptr_t)out % 16 != 0) return EOE_ERR_ALIGN;
+    if ((uintptr_t)A % 16 != 0 || (uintptr_t)Wt % 16 != 0 || (uintptr_t)out % 16 != 0 || (uintptr_t)bias % 16 != 0)
+        return EOE_ERR_ALIGN;
     CUtensorMap ta, tb;
     if ((rc = make_tmap(&ta, A, M, K, gemm::CTA_M, operand_dtype))) return rc;
     if ((rc = make_tmap(&tb, Wt, N, K, gemm::CTA_NB, operand_dtype))) return rc;
-    gemm::Params p{M, N, K, bias, out, aux, aux_i};
+    gemm::Params p{M, N, K, bias, out, aux, aux_i, nullptr, nullptr, nullptr};
+    p.dbg_a = A;
     return gemm_launch(ta, tb, p, operand_dtype, epilogue, (cudaStream_t)stream);
+}
+
+extern "C" void eoe_debug_set(int flags) { g_gemm_debug = flags; }
+
+extern "C" int eoe_gemm_lnfold(const void* A, const void* Wf, const float* c1, const float* c2, const float* stats,
+                               void* out, int64_t M, int64_t N, int64_t K, int operand_dtype, int quick_gelu,
+                               void* stream) {
+    if (!A || !Wf || !c1 || !c2 || !stats || !out) return EOE_ERR_ARG;
+    int rc = gemm_check(M, N, K, operand_dtype);
+    if (rc) return rc;
+    if (K % 256 != 0 || K > 128 * gemm::MAX_NCH) return EOE_ERR_SHAPE;      // K in {256, 512, 768}
+    if ((uintptr_t)A % 16 != 0 || (uintptr_t)Wf % 16 != 0 || (uintptr_t)out % 16 != 0 || (uintptr_t)stats % 16 != 0 ||
+        (uintptr_t)c1 % 16 != 0 || (uintptr_t)c2 % 16 != 0) return EOE_ERR_ALIGN;
+    CUtensorMap ta, tb;
+    if ((rc = make_tmap(&ta, A, M, K, gemm::CTA_M, operand_dtype))) return rc;
+    if ((rc = make_tmap(&tb, Wf, N, K, gemm::CTA_NB, operand_dtype))) return rc;
+    gemm::Params p{M, N, K, c2, out, c1, 0, reinterpret_cast<const float2*>(stats), nullptr, nullptr};
+    return gemm_launch(ta, tb, p, operand_dtype, quick_gelu ? EOE_EPI_LNFOLD_QUICKGELU : EOE_EPI_LNFOLD_BIAS,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int eoe_gemm_residual_stats(const void* A, const void* Wt, const float* bias, float* x, void* xb_out,
+                                       float* stats_out, int64_t M, int64_t N, int64_t K, int operand_dtype,
+                                       void* stream) {
+    if (!A || !Wt || !x || !xb_out || !stats_out) return EOE_ERR_ARG;
+    int rc = gemm_check(M, N, K, operand_dtype);
+    if (rc) return rc;
+    if ((uintptr_t)A % 16 != 0 || (uintptr_t)Wt % 16 != 0 || (uintptr_t)x % 16 != 0 || (uintptr_t)xb_out % 8 != 0 || (uintptr_t)bias % 16 != 0 ||
+        (uintptr_t)stats_out % 8 != 0) return EOE_ERR_ALIGN;
+    CUtensorMap ta, tb;
+    if ((rc = make_tmap(&ta, A, M, K, gemm::CTA_M, operand_dtype))) return rc;
+    if ((rc = make_tmap(&tb, Wt, N, K, gemm::CTA_NB, operand_dtype))) return rc;
+    gemm::Params p{M, N, K, bias, x, nullptr, 0, nullptr, reinterpret_cast<float2*>(stats_out),
+                   reinterpret_cast<uint16_t*>(xb_out)};
+    return gemm_launch(ta, tb, p, operand_dtype, EOE_EPI_RESIDUAL_STATS, (cudaStream_t)stream);
+}
+
+extern "C" int eoe_vit_fold_layernorm(const float* w_f32, const float* ln_w, const float* ln_b, const float* bias,
+                                      int64_t N, int64_t K, int operand_dtype, void* w_folded_out, float* c1_out,
+                                      float* c2_out, void* stream) {
+    if (!w_f32 || !ln_w || !ln_b || !w_folded_out || !c1_out || !c2_out || N <= 0 || K <= 0) return EOE_ERR_ARG;
+    if (operand_dtype != EOE_BF16 && operand_dtype != EOE_F16) return EOE_ERR_DTYPE;
+    if (K % 4 != 0) return EOE_ERR_SHAPE;
+    if ((uintptr_t)w_f32 % 16 != 0 || (uintptr_t)ln_w % 16 != 0 || (uintptr_t)ln_b % 16 != 0 || (uintptr_t)w_folded_out % 8 != 0)
+        return EOE_ERR_ALIGN;
+    const int grid = (int)((N + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (operand_dtype == EOE_BF16)
+        fold_ln_kernel<true><<<grid, 256, 0, st>>>(w_f32, ln_w, ln_b, bias, N, K, (uint16_t*)w_folded_out, c1_out, c2_out);
+    else
+        fold_ln_kernel<false><<<grid, 256, 0, st>>>(w_f32, ln_w, ln_b, bias, N, K, (uint16_t*)w_folded_out, c1_out, c2_out);
+    return check_launch("fold_ln_kernel");
 }
 
 extern "C" int eoe_layernorm(const float* x, const float* w, const float* b, void* y, int out_dtype, int64_t M,

@@ -24,7 +24,11 @@ def _strip(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
 
 class ClipImageEncoder(nn.Module):
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", operand_dtype=torch.bfloat16,
-                 max_batch: int = 256, heads: Optional[int] = None, resolution: Optional[int] = None):
+                 max_batch: int = 256, heads: Optional[int] = None, resolution: Optional[int] = None,
+                 fold_layernorm: bool = True):
+        """fold_layernorm: fold ln_1 / ln_2 into the QKV / c_fc GEMMs (eoe_vit_fold_layernorm; DESIGN.md "LayerNorm
+        fold") instead of launching stand-alone LayerNorm kernels.  Same math (fp32 statistics of the fp32 residual
+        stream); the 16-bit rounding point moves from LN(x) to x and to W*ln_w."""
         super().__init__()
         if operand_dtype not in (torch.bfloat16, torch.float16):
             raise L.EoeError("operand_dtype must be torch.bfloat16 or torch.float16")
@@ -43,6 +47,7 @@ class ClipImageEncoder(nn.Module):
         self.operand_dtype = operand_dtype
         self.max_batch = int(max_batch)
         self.device_ = dev
+        self.fold_layernorm = bool(fold_layernorm) and self.width <= 768      # eoe_gemm_lnfold: K <= 768
 
         def f32(t):
             return t.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -76,6 +81,11 @@ class ClipImageEncoder(nn.Module):
             l.ln_2_w, l.ln_2_b = put(f32(sd[p + "ln_2.weight"])), put(f32(sd[p + "ln_2.bias"]))
             l.c_fc_w, l.c_fc_b = put(op(sd[p + "mlp.c_fc.weight"])), put(f32(sd[p + "mlp.c_fc.bias"]))
             l.c_proj_w, l.c_proj_b = put(op(sd[p + "mlp.c_proj.weight"])), put(f32(sd[p + "mlp.c_proj.bias"]))
+            if self.fold_layernorm:
+                l.in_proj_wf, l.in_proj_c1, l.in_proj_c2 = self._fold(
+                    f32(sd[p + "attn.in_proj_weight"]), l.ln_1_w, l.ln_1_b, l.in_proj_b, put)
+                l.c_fc_wf, l.c_fc_c1, l.c_fc_c2 = self._fold(
+                    f32(sd[p + "mlp.c_fc.weight"]), l.ln_2_w, l.ln_2_b, l.c_fc_b, put)
         w.layers_host = C.cast(layers, C.POINTER(L.VitLayer))
         self._layers, self._w = layers, w
 
@@ -90,6 +100,18 @@ class ClipImageEncoder(nn.Module):
         L.check(lib.eoe_vit_plan_create(C.byref(w), self.max_batch, C.c_void_p(self._ws_ptr), nbytes, C.byref(plan)),
                 "eoe_vit_plan_create")
         self._plan = plan
+
+    def _fold(self, w32, ln_w_ptr, ln_b_ptr, bias_ptr, put):
+        """eoe_vit_fold_layernorm on the fp32 master weights -> device pointers (folded W, c1, c2)."""
+        N, K = w32.shape
+        wf = torch.empty(N, K, dtype=self.operand_dtype, device=w32.device)
+        c1 = torch.empty(N, dtype=torch.float32, device=w32.device)
+        c2 = torch.empty(N, dtype=torch.float32, device=w32.device)
+        L.check(L.lib().eoe_vit_fold_layernorm(L.ptr(w32), C.c_void_p(ln_w_ptr), C.c_void_p(ln_b_ptr), C.c_void_p(bias_ptr),
+                                               N, K, L.DTYPE_CODE[self.operand_dtype], L.ptr(wf), L.ptr(c1), L.ptr(c2),
+                                               L.stream_ptr(w32.device)), "eoe_vit_fold_layernorm")
+        torch.cuda.current_stream(w32.device).synchronize()      # w32 is a temporary
+        return put(wf), put(c1), put(c2)
 
     def __del__(self):
         plan = getattr(self, "_plan", None)
@@ -167,6 +189,42 @@ def gemm(A, W, bias=None, epilogue=L.EOE_EPI_BIAS, out=None, aux=None, aux_i=0):
     L.check(L.lib().eoe_gemm(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(out), M, N, K, L.DTYPE_CODE[A.dtype], epilogue,
                              L.ptr(aux), int(aux_i), L.stream_ptr(A.device)), "eoe_gemm")
     return out
+
+
+def fold_layernorm(w32, ln_w, ln_b, bias, operand_dtype=torch.bfloat16):
+    """(W*ln_w rounded to operand dtype, c1, c2) of eoe_vit_fold_layernorm."""
+    L.require_cuda(w32, ln_w, ln_b)
+    N, K = w32.shape
+    wf = torch.empty(N, K, dtype=operand_dtype, device=w32.device)
+    c1 = torch.empty(N, dtype=torch.float32, device=w32.device)
+    c2 = torch.empty(N, dtype=torch.float32, device=w32.device)
+    L.check(L.lib().eoe_vit_fold_layernorm(L.ptr(w32), L.ptr(ln_w), L.ptr(ln_b), L.ptr(bias), N, K,
+                                           L.DTYPE_CODE[operand_dtype], L.ptr(wf), L.ptr(c1), L.ptr(c2),
+                                           L.stream_ptr(w32.device)), "eoe_vit_fold_layernorm")
+    return wf, c1, c2
+
+
+def gemm_lnfold(A, Wf, c1, c2, stats, quick_gelu=False):
+    """rstd*(A @ Wf^T - mean*c1) + c2 with (mean, rstd) from the per-row chunk sums `stats` [M, K/128, 2]."""
+    L.require_cuda(A, Wf, stats)
+    M, K = A.shape
+    N = Wf.shape[0]
+    out = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    L.check(L.lib().eoe_gemm_lnfold(L.ptr(A), L.ptr(Wf), L.ptr(c1), L.ptr(c2), L.ptr(stats), L.ptr(out), M, N, K,
+                                    L.DTYPE_CODE[A.dtype], int(quick_gelu), L.stream_ptr(A.device)), "eoe_gemm_lnfold")
+    return out
+
+
+def gemm_residual_stats(A, W, bias, x):
+    """x += A @ W^T + bias in place; returns (xb = x rounded to A.dtype, stats [M, N/128, 2] chunk sums of x)."""
+    L.require_cuda(A, W, x)
+    M, K = A.shape
+    N = W.shape[0]
+    xb = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    stats = torch.empty(M, N // 128, 2, dtype=torch.float32, device=A.device)
+    L.check(L.lib().eoe_gemm_residual_stats(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(x), L.ptr(xb), L.ptr(stats), M, N, K,
+                                            L.DTYPE_CODE[A.dtype], L.stream_ptr(A.device)), "eoe_gemm_residual_stats")
+    return xb, stats
 
 
 def layernorm(x, w, b, out_dtype=torch.bfloat16):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EOE_ABI_VERSION 1
+#define EOE_ABI_VERSION 2
 
 enum { EOE_F32 = 0, EOE_F16 = 1, EOE_BF16 = 2 };
 
@@ -139,6 +139,12 @@ typedef struct eoe_vit_layer {
     const float* ln_2_w; const float* ln_2_b;
     const void*  c_fc_w;   const float* c_fc_b;        /* [4*width, width], [4*width]              */
     const void*  c_proj_w; const float* c_proj_b;      /* [width, 4*width], [width]                */
+    /* Optional LayerNorm-folded copies produced by eoe_vit_fold_layernorm (all six or none, and for every
+     * layer or for none).  When present the encoder drops the stand-alone ln_1 / ln_2 kernels: the residual
+     * GEMM epilogues emit a 16-bit copy of the residual stream plus per-row (sum, sum of squares) and the
+     * QKV / c_fc GEMMs apply  rstd*(acc - mean*c1) + c2  in their epilogue (see DESIGN.md "LayerNorm fold"). */
+    const void*  in_proj_wf; const float* in_proj_c1; const float* in_proj_c2;   /* [3*width,width], [3*width] x2 */
+    const void*  c_fc_wf;    const float* c_fc_c1;    const float* c_fc_c2;      /* [4*width,width], [4*width] x2 */
 } eoe_vit_layer;
 
 typedef struct eoe_vit_weights {
@@ -182,13 +188,32 @@ int eoe_vit_encode(eoe_vit_plan* plan, const float* imgs, int64_t B, float* feat
 int eoe_vit_profile_enable(eoe_vit_plan* plan, int enable);
 int eoe_vit_profile_read(eoe_vit_plan* plan, double* ms_out_host, int64_t* launches_out_host, double* flops_out_host);
 
+/* LayerNorm fold (model.py:153-159 applied in front of a Linear, model.py:171,174):
+ *   LN(x) @ W^T + b  ==  rstd * ( x @ (W*ln_w)^T  -  mean * c1 )  +  c2
+ *   w_folded_out [N,K] operand dtype = round(W[n,k] * ln_w[k]);  c1[n] = sum_k float(w_folded[n,k]);
+ *   c2[n] = sum_k W[n,k] * ln_b[k] + bias[n].          w_f32 [N,K] fp32 master weights, K % 4 == 0. */
+int eoe_vit_fold_layernorm(const float* w_f32, const float* ln_w, const float* ln_b, const float* bias,
+                           int64_t N, int64_t K, int operand_dtype, void* w_folded_out, float* c1_out,
+                           float* c2_out, void* stream);
+
 /* Building blocks of the encoder, exported so that each kernel is parity-tested through the ABI. */
-enum { EOE_EPI_BIAS = 0, EOE_EPI_BIAS_QUICKGELU = 1, EOE_EPI_BIAS_RESIDUAL_F32 = 2, EOE_EPI_PATCH_EMBED = 3 };
+enum { EOE_EPI_BIAS = 0, EOE_EPI_BIAS_QUICKGELU = 1, EOE_EPI_BIAS_RESIDUAL_F32 = 2, EOE_EPI_PATCH_EMBED = 3,
+       EOE_EPI_LNFOLD_BIAS = 4, EOE_EPI_LNFOLD_QUICKGELU = 5, EOE_EPI_RESIDUAL_STATS = 6 };
 /* out = epilogue(A[M,K] @ W[N,K]^T): tcgen05 GEMM, A/W operand dtype (BF16/F16), K % 64 == 0, N % 256 == 0.
  *   EOE_EPI_BIAS / _QUICKGELU: out [M,N] operand dtype;  _RESIDUAL_F32: out [M,N] fp32 += (in place);
  *   _PATCH_EMBED: out fp32 row (m/g2)*(g2+1)+1+(m%g2) = acc + pos_emb[1+m%g2] (aux = pos_emb, aux_i = g2). */
 int eoe_gemm(const void* A, const void* W, const float* bias, void* out, int64_t M, int64_t N, int64_t K,
              int operand_dtype, int epilogue, const float* aux, int64_t aux_i, void* stream);
+/* LayerNorm-folded GEMM (QKV / c_fc with ln_1 / ln_2 folded in): A [M,K] = 16-bit copy of the residual stream,
+ * Wf / c1 / c2 from eoe_vit_fold_layernorm, stats [M, K/128] float2 = per-row (sum, sum of squares) of the fp32
+ * residual stream over each 128-column chunk.  out [M,N] operand dtype = rstd*(A@Wf^T - mean*c1) + c2, then
+ * QuickGELU if quick_gelu != 0.  K % 256 == 0, K <= 768; c1, c2, stats 16-byte aligned. */
+int eoe_gemm_lnfold(const void* A, const void* Wf, const float* c1, const float* c2, const float* stats,
+                    void* out, int64_t M, int64_t N, int64_t K, int operand_dtype, int quick_gelu, void* stream);
+/* Residual GEMM that also prepares the next folded LayerNorm: x [M,N] fp32 += A@W^T + bias (in place),
+ * xb_out [M,N] operand dtype = round(x), stats_out [M, N/128] float2 = per-row (sum, sum of squares) per chunk. */
+int eoe_gemm_residual_stats(const void* A, const void* W, const float* bias, float* x, void* xb_out,
+                            float* stats_out, int64_t M, int64_t N, int64_t K, int operand_dtype, void* stream);
 /* y[M,width] (out_dtype) = LayerNorm_fp32(x[M,width]) * w + b, eps 1e-5 (model.py:153-159) */
 int eoe_layernorm(const float* x, const float* w, const float* b, void* y, int out_dtype, int64_t M,
                   int64_t width, void* stream);

@@ -19,6 +19,12 @@ by oracle/make_golden.py).
 16 bit (GEMM operands: patches, LN outputs, qkv, softmax probabilities, attention output, GELU
 output, weights) to that dtype while keeping fp32 accumulation / residual stream / LN / softmax
 statistics -- the "precision-matched" oracle used to separate kernel bugs from rounding.
+
+`fold_layernorm=True` (only meaningful with an operand_dtype) moves the rounding points the way the CUDA encoder's
+LayerNorm-folded path does (DESIGN.md "LayerNorm fold"): ln_1 / ln_2 are applied as
+    rstd * ( round(x) @ round(W*ln_w)^T - mean * c1 ) + c2,   c1 = rowsum(round(W*ln_w)),  c2 = W @ ln_b + bias
+with mean / rstd taken from the fp32 residual stream; in exact arithmetic this IS LayerNorm followed by the Linear.
+The last block's ln_2 stays unfolded (the CUDA path evaluates it for the class-token rows only).
 """
 import math
 import torch
@@ -81,8 +87,24 @@ def _r(t, dt):
     return t if dt is None else t.to(dt).to(torch.float32)
 
 
+def _ln_linear(x, ln_w, ln_b, W, bias, dt, fold):
+    """Linear(LayerNorm(x)) with the rounding points of the selected CUDA path."""
+    width = x.shape[-1]
+    if not fold or dt is None:
+        h = F.layer_norm(x, (width,), ln_w, ln_b, 1e-5)
+        return F.linear(_r(h, dt), _r(W, dt), bias)
+    wf = _r(W * ln_w, dt)
+    c1 = wf.sum(dim=1)
+    c2 = W @ ln_b + bias
+    mean = x.mean(dim=-1, keepdim=True)
+    var = (x * x).mean(dim=-1, keepdim=True) - mean * mean
+    rstd = torch.rsqrt(var.clamp_min(0) + 1e-5)
+    return rstd * (_r(x, dt) @ wf.t() - mean * c1) + c2
+
+
 @torch.no_grad()
-def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens: bool = False):
+def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens: bool = False,
+                 fold_layernorm: bool = False):
     """model.py:219-236. imgs [B,3,R,R] float32 (already CLIP-normalised) -> features [B, embed]."""
     dt = operand_dtype
     f32 = torch.float32
@@ -103,8 +125,8 @@ def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens
     for i in range(layers):
         p = f"visual.transformer.resblocks.{i}."
         # model.py:186  x = x + attn(ln_1(x))
-        h = F.layer_norm(x, (width,), w[p + "ln_1.weight"], w[p + "ln_1.bias"], 1e-5)
-        qkv = F.linear(_r(h, dt), _r(w[p + "attn.in_proj_weight"], dt), w[p + "attn.in_proj_bias"])
+        qkv = _ln_linear(x, w[p + "ln_1.weight"], w[p + "ln_1.bias"], w[p + "attn.in_proj_weight"],
+                         w[p + "attn.in_proj_bias"], dt, fold_layernorm)
         qkv = _r(qkv, dt)
         q, k, v = qkv.split(width, dim=-1)
         q = q.reshape(B, L, heads, dh).transpose(1, 2)
@@ -121,8 +143,8 @@ def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens
         o = _r(o.transpose(1, 2).reshape(B, L, width), dt)
         x = x + F.linear(o, _r(w[p + "attn.out_proj.weight"], dt), w[p + "attn.out_proj.bias"])
         # model.py:187  x = x + mlp(ln_2(x)),  mlp = c_proj(QuickGELU(c_fc(.)))  (model.py:173-177)
-        h = F.layer_norm(x, (width,), w[p + "ln_2.weight"], w[p + "ln_2.bias"], 1e-5)
-        u = F.linear(_r(h, dt), _r(w[p + "mlp.c_fc.weight"], dt), w[p + "mlp.c_fc.bias"])
+        u = _ln_linear(x, w[p + "ln_2.weight"], w[p + "ln_2.bias"], w[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"], dt,
+                       fold_layernorm and i < layers - 1)
         u = _r(u * torch.sigmoid(1.702 * u), dt)
         x = x + F.linear(u, _r(w[p + "mlp.c_proj.weight"], dt), w[p + "mlp.c_proj.bias"])
     if return_tokens:

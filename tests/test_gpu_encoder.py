@@ -62,6 +62,72 @@ def test_gemm_patch_embed_epilogue():
     assert torch.all(out[:, 0] == 7.0)                    # class-token rows are left for ln_pre
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_fold_layernorm_kernel(dtype):
+    """eoe_vit_fold_layernorm: W*ln_w rounded once from the fp32 master (bit-exact), c1 = its row sums, c2 = W@ln_b + bias."""
+    from eoe_b200 import encoder as E
+    g = torch.Generator(device=DEV).manual_seed(11)
+    W = torch.randn(2304, 768, device=DEV, generator=g) * 0.04
+    ln_w = 1 + 0.1 * torch.randn(768, device=DEV, generator=g)
+    ln_b = 0.1 * torch.randn(768, device=DEV, generator=g)
+    bias = torch.randn(2304, device=DEV, generator=g)
+    wf, c1, c2 = E.fold_layernorm(W, ln_w, ln_b, bias, dtype)
+    want = (W * ln_w).to(dtype)
+    assert torch.equal(wf, want)
+    torch.testing.assert_close(c1, want.float().sum(1), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(c2, (W.double() @ ln_b.double() + bias.double()).float(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("M,N,K", [(100, 256, 768), (6400, 2304, 768), (25216, 3072, 768), (777, 768, 512)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("gelu", [False, True])
+def test_gemm_lnfold_vs_torch(M, N, K, dtype, gelu):
+    """LayerNorm folded into the GEMM epilogue == torch LayerNorm(fp32) -> Linear on the same rounded operands."""
+    from eoe_b200 import encoder as E
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV, generator=g) * 1.5 + 0.2
+    W = torch.randn(N, K, device=DEV, generator=g) * 0.04
+    ln_w = 1 + 0.1 * torch.randn(K, device=DEV, generator=g)
+    ln_b = 0.1 * torch.randn(K, device=DEV, generator=g)
+    bias = torch.randn(N, device=DEV, generator=g)
+    wf, c1, c2 = E.fold_layernorm(W, ln_w, ln_b, bias, dtype)
+    xc = x.reshape(M, K // 128, 128)
+    stats = torch.stack([xc.sum(-1), (xc * xc).sum(-1)], dim=-1).contiguous()       # [M, K/128, 2]
+    xb = x.to(dtype)
+    got = E.gemm_lnfold(xb, wf, c1, c2, stats, quick_gelu=gelu)
+    # the same algebra in fp64 on the same rounded operands (separates kernel bugs from the moved rounding point)
+    mean = x.double().mean(-1, keepdim=True)
+    rstd = torch.rsqrt(x.double().var(-1, unbiased=False, keepdim=True) + 1e-5)
+    ref = rstd * (xb.double() @ wf.double().t() - mean * c1.double()) + c2.double()
+    # and plain LayerNorm -> Linear in fp32 (what the reference computes, model.py:153-159,171)
+    plain = torch.nn.functional.layer_norm(x, (K,), ln_w, ln_b, 1e-5) @ W.t() + bias
+    if gelu:
+        ref = ref * torch.sigmoid(1.702 * ref)
+        plain = plain * torch.sigmoid(1.702 * plain)
+    tol = 3e-3 if dtype == torch.bfloat16 else 4e-4       # output rounding to the 16-bit operand dtype
+    assert _rel(got, ref.float()) < tol
+    assert _rel(got, plain) < (8e-3 if dtype == torch.bfloat16 else 1e-3)   # + operand rounding of x and W*ln_w
+
+
+@pytest.mark.parametrize("M,N,K", [(100, 768, 768), (6400, 768, 3072), (25216, 768, 768), (333, 1024, 256)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_gemm_residual_stats_vs_torch(M, N, K, dtype):
+    """x += A@W^T + bias (fp32), xb = round(x), per-row chunk sums of the updated x."""
+    from eoe_b200 import encoder as E
+    g = torch.Generator(device=DEV).manual_seed(M + N + K + 1)
+    A = (torch.randn(M, K, device=DEV, generator=g) * 0.5).to(dtype)
+    W = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(dtype)
+    bias = torch.randn(N, device=DEV, generator=g)
+    x = torch.randn(M, N, device=DEV, generator=g)
+    ref = x + A.float() @ W.float().t() + bias
+    xb, stats = E.gemm_residual_stats(A, W, bias, x)
+    assert _rel(x, ref) < 2e-5
+    assert torch.equal(xb, x.to(dtype))                   # the 16-bit copy is the rounding of exactly what was stored
+    xc = x.reshape(M, N // 128, 128).double()
+    torch.testing.assert_close(stats[..., 0].double(), xc.sum(-1), rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(stats[..., 1].double(), (xc * xc).sum(-1), rtol=1e-4, atol=1e-3)
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 4e-3), (torch.float16, 5e-4)])
 def test_layernorm_vs_torch(dtype, tol):
     from eoe_b200 import encoder as E
@@ -93,21 +159,22 @@ def tower(request):
     return patch, sd
 
 
+@pytest.mark.parametrize("fold", [True, False])
 @pytest.mark.parametrize("dtype,rel_tol,emu_tol", [(torch.bfloat16, 6e-3, 2.5e-3), (torch.float16, 8e-4, 4e-4)])
-def test_encoder_vs_oracle_and_golden(tower, golden_dir, dtype, rel_tol, emu_tol):
+def test_encoder_vs_oracle_and_golden(tower, golden_dir, dtype, rel_tol, emu_tol, fold):
     """features: relative L2 error vs (a) golden features from the live reference (fp32) <= rel_tol (16-bit operand
     rounding through 12 blocks: ~2e-3 bf16, ~2.6e-4 fp16 measured for the precision-matched oracle itself) and
     (b) the precision-matched oracle (same rounding points, fp32 accumulation) <= emu_tol."""
     from eoe_b200.encoder import ClipImageEncoder
     patch, sd = tower
     imgs = gi.vit_images()
-    enc = ClipImageEncoder(sd, device=DEV, operand_dtype=dtype, max_batch=4)
+    enc = ClipImageEncoder(sd, device=DEV, operand_dtype=dtype, max_batch=4, fold_layernorm=fold)
     feats = enc(imgs.to(DEV)).cpu()
     g = np.load(os.path.join(golden_dir, f"vit_b{patch}.npz"))
     gold = torch.from_numpy(g["features"])
     assert feats.shape == gold.shape and torch.isfinite(feats).all()
     assert _rel(feats, gold) < rel_tol
-    emu = ovit.encode_image(sd, imgs, operand_dtype=dtype)
+    emu = ovit.encode_image(sd, imgs, operand_dtype=dtype, fold_layernorm=fold)
     assert _rel(feats, emu) < emu_tol
     cos = torch.nn.functional.cosine_similarity(feats, gold, dim=-1)
     assert (1 - cos).max().item() < (3e-5 if dtype == torch.bfloat16 else 1e-6)

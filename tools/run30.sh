@@ -1,0 +1,5 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_gpu_encoder.py -m gpu -x -q 2>&1 | tail -3
+python tools/ab_encoder.py > gpurun_out/ab_cur.json 2> gpurun_out/ab_cur.err
+EOE_B200_LIB=$PWD/tools/_variants/libeoe_b200_v3.so python tools/ab_encoder.py > gpurun_out/ab_v3.json 2> gpurun_out/ab_v3.err
+python tools/ab_encoder.py > gpurun_out/ab_cur_2.json 2> gpurun_out/ab_cur_2.err
