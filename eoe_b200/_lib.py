@@ -59,6 +59,9 @@ SIGNATURES = {
     "eoe_hsc_score": (_I, [_P, _I, _I64, _I64, _P, _P]),
     "eoe_bce_fwd_bwd": (_I, [_P, _I, _P, _I64, _I64, _P, _P, _P, _P, _P]),
     "eoe_bce_score": (_I, [_P, _I, _I64, _I64, _P, _P]),
+    "eoe_dsad_fwd_bwd": (_I, [_P, _I, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P]),
+    "eoe_dsvdd_fwd_bwd": (_I, [_P, _I, _P, _I64, _I64, _P, _P, _P, _P, _P]),
+    "eoe_focal_fwd_bwd": (_I, [_P, _I, _P, _I64, _I64, _F, _F, _P, _P, _P, _P, _P]),
     "eoe_clip_score": (_I, [_P, _I, _P, _I64, _I64, _I64, _F, _P, _P]),
     "eoe_clip_oe_loss_fwd_bwd": (_I, [_P, _I, _P, _P, _I64, _I64, _I64, _F, _I64, _I, _P, _P, _P, _P]),
     "eoe_auc_workspace_bytes": (_SZ, [_I64]),

@@ -3,6 +3,9 @@
 //   hsc_*   : HSCTrainer.loss + autograd backward + compute_anomaly_score  (reference src/eoe/training/hsc.py:12-21)
 //   bce_*   : BCETrainer.loss + backward + compute_anomaly_score           (reference src/eoe/training/bce.py:15-20)
 //   clip_*  : ADClipTrainer.compute_anomaly_score / loss + backward         (reference src/eoe/training/clip.py:66-103)
+//   dsad_*  : DSADTrainer.loss + backward + compute_anomaly_score           (reference src/eoe/training/dsad.py:13-22)
+//   dsvdd_* : DSVDDTrainer.loss + backward + compute_anomaly_score          (reference src/eoe/training/dsvdd.py:23-27)
+//   focal_* : FocalTrainer.loss (FocalLoss) + backward + score              (reference src/eoe/training/focal.py:11-39)
 //
 // Layout: features [n,d] row-major.  One warp owns ROWS rows at a time and keeps them in registers
 // between the reduction pass (||z||^2, logits) and the gradient pass, so every feature byte is read from
@@ -42,11 +45,43 @@ __device__ __forceinline__ HscRow hsc_row_math(float sumsq, bool nominal, float 
     return r;
 }
 
-template <typename T, int VEC, int ITERS, int ROWS>
+// The three "row norm" objectives share one kernel: s = sum_j (z_j - c_j)^2 (c = 0 unless DSVDD), then per row
+//   HSC   (hsc.py:17-21)    loss = dist | -log(score + 1e-9),            score = 1 - exp(-(sqrt(s+1)-1))
+//   DSAD  (dsad.py:13-22)   loss = s | (s + 1e-9)^-1 (s via sqrt then square as in the reference), score as HSC
+//   DSVDD (dsvdd.py:23-27)  loss = score = s (labels unused)
+// and d loss / d z_j = coef * (z_j - c_j).
+enum { ROW_HSC = 0, ROW_DSAD = 1, ROW_DSVDD = 2 };
+template <int MODE>
+__device__ __forceinline__ HscRow row_math(float sumsq, bool nominal, float inv_n) {
+    if (MODE == ROW_HSC) return hsc_row_math(sumsq, nominal, inv_n);
+    HscRow r;
+    if (MODE == ROW_DSVDD) {
+        r.dist = sumsq;
+        r.score = sumsq;
+        r.loss = sumsq;
+        r.coef = 2.0f * inv_n;
+        return r;
+    }
+    const float nrm = sqrtf(sumsq);
+    const float d2 = nrm * nrm;                        // torch.norm(z, 2, dim=1) ** 2   (dsad.py:19)
+    r.dist = sqrtf(d2 + 1.0f) - 1.0f;                  // dsad.py:14
+    r.score = 1.0f - expf(-r.dist);
+    if (nominal) {
+        r.loss = d2;
+        r.coef = 2.0f * inv_n;
+    } else {
+        const float t = d2 + 1e-9f;
+        r.loss = 1.0f / t;                             // (dists + 1e-9) ** (-1)          (dsad.py:21)
+        r.coef = -2.0f * inv_n / (t * t);
+    }
+    return r;
+}
+
+template <typename T, int VEC, int ITERS, int ROWS, int MODE>
 __global__ void __launch_bounds__(kHeadBlock)
 hsc_rows_kernel(const T* __restrict__ z, const int64_t* __restrict__ labels, int64_t n, int d,
                 int64_t nominal_label, float* __restrict__ scores, T* __restrict__ grad,
-                HeadWorkspace* ws, float* loss_out, float inv_n_f, double inv_n) {
+                HeadWorkspace* ws, float* loss_out, float inv_n_f, double inv_n, const float* __restrict__ center) {
     const int lane = threadIdx.x & 31;
     const int nvec = d / VEC;
     const int64_t warp0 = (int64_t)blockIdx.x * kHeadWarps + (threadIdx.x >> 5);
@@ -64,6 +99,13 @@ hsc_rows_kernel(const T* __restrict__ z, const int64_t* __restrict__ labels, int
                 const int vi = it * 32 + lane;
                 if (row < n && vi < nvec) {
                     loadv_stream<T, VEC>(z + row * d + vi * VEC, v[r][it]);
+                    if (MODE == ROW_DSVDD) {           // (features - center), dsvdd.py:24,27
+#pragma unroll
+                        for (int e = 0; e < VEC; e += 4) {
+                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(center + vi * VEC + e));
+                            v[r][it][e] -= c4.x; v[r][it][e + 1] -= c4.y; v[r][it][e + 2] -= c4.z; v[r][it][e + 3] -= c4.w;
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) v[r][it][e] = 0.f;
@@ -84,7 +126,7 @@ hsc_rows_kernel(const T* __restrict__ z, const int64_t* __restrict__ labels, int
             const int64_t row = base + r;
             if (row >= n) break;
             const bool nominal = labels ? (labels[row] == nominal_label) : true;
-            HscRow h = hsc_row_math(ss[r], nominal, inv_n_f);
+            HscRow h = row_math<MODE>(ss[r], nominal, inv_n_f);
             if (lane == 0) {
                 if (scores) scores[row] = h.score;
                 loss_acc += h.loss;
@@ -107,11 +149,11 @@ hsc_rows_kernel(const T* __restrict__ z, const int64_t* __restrict__ labels, int
 }
 
 // Any d / any alignment: scalar lane-strided loops, second pass re-reads the row (L1/L2 hit).
-template <typename T>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kHeadBlock)
 hsc_rows_generic_kernel(const T* __restrict__ z, const int64_t* __restrict__ labels, int64_t n, int64_t d,
                         int64_t nominal_label, float* __restrict__ scores, T* __restrict__ grad,
-                        HeadWorkspace* ws, float* loss_out, float inv_n_f, double inv_n) {
+                        HeadWorkspace* ws, float* loss_out, float inv_n_f, double inv_n, const float* __restrict__ center) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * kHeadWarps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kHeadWarps;
@@ -120,18 +162,19 @@ hsc_rows_generic_kernel(const T* __restrict__ z, const int64_t* __restrict__ lab
         const T* zr = z + row * d;
         float s = 0.f;
         for (int64_t j = lane; j < d; j += 32) {
-            float x = to_f32<T>(zr[j]);
+            float x = to_f32<T>(zr[j]) - (MODE == ROW_DSVDD ? center[j] : 0.f);
             s += x * x;
         }
         s = warp_sum(s);
         const bool nominal = labels ? (labels[row] == nominal_label) : true;
-        HscRow h = hsc_row_math(s, nominal, inv_n_f);
+        HscRow h = row_math<MODE>(s, nominal, inv_n_f);
         if (lane == 0) {
             if (scores) scores[row] = h.score;
             loss_acc += h.loss;
         }
         if (grad)
-            for (int64_t j = lane; j < d; j += 32) grad[row * d + j] = from_f32<T>(h.coef * to_f32<T>(zr[j]));
+            for (int64_t j = lane; j < d; j += 32)
+                grad[row * d + j] = from_f32<T>(h.coef * (to_f32<T>(zr[j]) - (MODE == ROW_DSVDD ? center[j] : 0.f)));
     }
     if (loss_out) grid_mean_finish<kHeadBlock>(loss_acc, ws, loss_out, inv_n);
 }
@@ -144,25 +187,27 @@ static inline int head_grid(int64_t units, int units_per_block) {
     return (int)blocks;
 }
 
-template <typename T>
+template <typename T, int MODE = ROW_HSC>
 static int hsc_launch(const void* z_, const int64_t* labels, int64_t n, int64_t d, int64_t nominal,
-                      float* loss_out, float* scores, void* grad_, void* ws_, cudaStream_t st) {
+                      float* loss_out, float* scores, void* grad_, void* ws_, cudaStream_t st,
+                      const float* center = nullptr) {
     const T* z = (const T*)z_;
     T* grad = (T*)grad_;
     HeadWorkspace* ws = (HeadWorkspace*)ws_;
     const float inv_n_f = 1.0f / (float)n;
     const double inv_n = 1.0 / (double)n;
     constexpr int VEC = sizeof(T) == 4 ? 4 : 8;            // 16 bytes per lane per access
-    const bool vec_ok = (d % VEC == 0) && d <= 32 * VEC * 8 && ((uintptr_t)z % 16 == 0) && (!grad || (uintptr_t)grad % 16 == 0);
+    const bool vec_ok = (d % VEC == 0) && d <= 32 * VEC * 8 && ((uintptr_t)z % 16 == 0) && (!grad || (uintptr_t)grad % 16 == 0) &&
+                        (uintptr_t)center % 16 == 0;
     if (!vec_ok) {
-        hsc_rows_generic_kernel<T><<<head_grid(n, kHeadWarps), kHeadBlock, 0, st>>>(
-            z, labels, n, d, nominal, scores, grad, ws, loss_out, inv_n_f, inv_n);
+        hsc_rows_generic_kernel<T, MODE><<<head_grid(n, kHeadWarps), kHeadBlock, 0, st>>>(
+            z, labels, n, d, nominal, scores, grad, ws, loss_out, inv_n_f, inv_n, center);
         return check_launch("hsc_rows_generic_kernel");
     }
     const int iters = (int)((d / VEC + 31) / 32);
 #define EOE_HSC_CASE(IT, RW)                                                                           \
-    hsc_rows_kernel<T, VEC, IT, RW><<<head_grid(n, kHeadWarps * RW), kHeadBlock, 0, st>>>(              \
-        z, labels, n, (int)d, nominal, scores, grad, ws, loss_out, inv_n_f, inv_n)
+    hsc_rows_kernel<T, VEC, IT, RW, MODE><<<head_grid(n, kHeadWarps * RW), kHeadBlock, 0, st>>>(        \
+        z, labels, n, (int)d, nominal, scores, grad, ws, loss_out, inv_n_f, inv_n, center)
     if (iters <= 1) EOE_HSC_CASE(1, 4);
     else if (iters <= 2) EOE_HSC_CASE(2, VEC == 4 ? 4 : 2);
     else if (iters <= 4) EOE_HSC_CASE(4, VEC == 4 ? 2 : 1);
@@ -186,11 +231,27 @@ __device__ __forceinline__ BceOut bce_math(float x, float y) {
     return o;
 }
 
-template <typename T, bool VEC>
+// FocalLoss (focal.py:19-24, gamma = 2, eps = 1e-7): bce as above, pt = clamp(exp(-bce), eps, 1 - eps),
+// F = (1 - pt)^gamma * bce.  d F / d x = (sigmoid(x) - y) * [ (1-pt)^g + 1{eps <= exp(-bce) <= 1-eps} * g (1-pt)^(g-1) pt bce ]
+// (torch's clamp passes the gradient on the closed interval).  FOCAL turns bce_kernel into that objective.
+struct FocalParams { float gamma, eps; };
+__device__ __forceinline__ void focal_math(const BceOut& o, float y, const FocalParams fp, float& loss, float& dldx) {
+    const float pt_raw = expf(-o.loss);
+    const float pt = fminf(fmaxf(pt_raw, fp.eps), 1.0f - fp.eps);
+    const float q = 1.0f - pt;
+    const float qg = fp.gamma == 2.0f ? q * q : powf(q, fp.gamma);
+    const float qg1 = fp.gamma == 2.0f ? q : powf(q, fp.gamma - 1.0f);
+    loss = qg * o.loss;
+    const bool inside = pt_raw >= fp.eps && pt_raw <= 1.0f - fp.eps;
+    dldx = (o.sig - y) * (qg + (inside ? fp.gamma * qg1 * pt * o.loss : 0.f));
+    if (pt_raw != pt_raw) { loss = pt_raw; dldx = pt_raw; }      // NaN in -> NaN out (fminf/fmaxf would drop it)
+}
+
+template <typename T, bool VEC, bool FOCAL = false>
 __global__ void __launch_bounds__(kHeadBlock)
 bce_kernel(const T* __restrict__ x, const int64_t* __restrict__ labels, int64_t n, int flip_score,
            float* __restrict__ scores, T* __restrict__ grad, HeadWorkspace* ws, float* loss_out, float inv_n_f,
-           double inv_n) {
+           double inv_n, FocalParams fp = FocalParams{2.0f, 1e-7f}) {
     const int64_t tid = (int64_t)blockIdx.x * kHeadBlock + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * kHeadBlock;
     float loss_acc = 0.f;
@@ -221,9 +282,16 @@ bce_kernel(const T* __restrict__ x, const int64_t* __restrict__ labels, int64_t 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     BceOut o = bce_math(xv[u][j], y[j]);
-                    loss_acc += o.loss;
                     sc[j] = flip_score ? 1.0f - o.sig : o.sig;
-                    g[j] = (o.sig - y[j]) * inv_n_f;
+                    if (FOCAL) {
+                        float fl, dl;
+                        focal_math(o, y[j], fp, fl, dl);
+                        loss_acc += fl;
+                        g[j] = dl * inv_n_f;
+                    } else {
+                        loss_acc += o.loss;
+                        g[j] = (o.sig - y[j]) * inv_n_f;
+                    }
                 }
                 if (scores) store4_stream<float>(scores + idx[u] * 4, sc);
                 if (grad) store4_stream<T>(grad + idx[u] * 4, g);
@@ -235,16 +303,25 @@ bce_kernel(const T* __restrict__ x, const int64_t* __restrict__ labels, int64_t 
         const float xv = to_f32<T>(x[i]);
         const float y = labels ? (float)labels[i] : 0.f;
         BceOut o = bce_math(xv, y);
-        loss_acc += o.loss;
+        float gi;
+        if (FOCAL) {
+            float fl, dl;
+            focal_math(o, y, fp, fl, dl);
+            loss_acc += fl;
+            gi = dl * inv_n_f;
+        } else {
+            loss_acc += o.loss;
+            gi = (o.sig - y) * inv_n_f;
+        }
         if (scores) scores[i] = flip_score ? 1.0f - o.sig : o.sig;
-        if (grad) grad[i] = from_f32<T>((o.sig - y) * inv_n_f);
+        if (grad) grad[i] = from_f32<T>(gi);
     }
     if (loss_out) grid_mean_finish<kHeadBlock>(loss_acc, ws, loss_out, inv_n);
 }
 
-template <typename T>
+template <typename T, bool FOCAL = false>
 static int bce_launch(const void* x_, const int64_t* labels, int64_t n, int64_t nominal, float* loss_out,
-                      float* scores, void* grad_, void* ws_, cudaStream_t st) {
+                      float* scores, void* grad_, void* ws_, cudaStream_t st, FocalParams fp = FocalParams{2.0f, 1e-7f}) {
     const T* x = (const T*)x_;
     T* grad = (T*)grad_;
     const float inv_n_f = 1.0f / (float)n;
@@ -254,11 +331,11 @@ static int bce_launch(const void* x_, const int64_t* labels, int64_t n, int64_t 
                      (!labels || (uintptr_t)labels % 16 == 0) && (!scores || (uintptr_t)scores % 16 == 0);
     const int grid = head_grid(n, kHeadBlock * 8);
     if (vec)
-        bce_kernel<T, true><<<grid, kHeadBlock, 0, st>>>(x, labels, n, nominal != 0, scores, grad,
-                                                         (HeadWorkspace*)ws_, loss_out, inv_n_f, inv_n);
+        bce_kernel<T, true, FOCAL><<<grid, kHeadBlock, 0, st>>>(x, labels, n, nominal != 0, scores, grad,
+                                                                (HeadWorkspace*)ws_, loss_out, inv_n_f, inv_n, fp);
     else
-        bce_kernel<T, false><<<grid, kHeadBlock, 0, st>>>(x, labels, n, nominal != 0, scores, grad,
-                                                          (HeadWorkspace*)ws_, loss_out, inv_n_f, inv_n);
+        bce_kernel<T, false, FOCAL><<<grid, kHeadBlock, 0, st>>>(x, labels, n, nominal != 0, scores, grad,
+                                                                 (HeadWorkspace*)ws_, loss_out, inv_n_f, inv_n, fp);
     return check_launch("bce_kernel");
 }
 
@@ -538,6 +615,33 @@ extern "C" int eoe_bce_score(const void* x, int x_dtype, int64_t n, int64_t nomi
     if (!x || !scores_out || n <= 0) return EOE_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     EOE_DISPATCH_DTYPE(x_dtype, (bce_launch<T>(x, nullptr, n, nominal_label, nullptr, scores_out, nullptr, nullptr, st)))
+}
+
+extern "C" int eoe_dsad_fwd_bwd(const void* z, int z_dtype, const int64_t* labels, int64_t n, int64_t d,
+                                int64_t nominal_label, float* loss_out, float* scores_out, void* grad_z_out,
+                                void* head_ws, void* stream) {
+    if (!z || !labels || !loss_out || !head_ws || n <= 0 || d <= 0) return EOE_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    EOE_DISPATCH_DTYPE(z_dtype, (hsc_launch<T, ROW_DSAD>(z, labels, n, d, nominal_label, loss_out, scores_out, grad_z_out, head_ws, st)))
+}
+
+extern "C" int eoe_dsvdd_fwd_bwd(const void* z, int z_dtype, const float* center, int64_t n, int64_t d,
+                                 float* loss_out, float* scores_out, void* grad_z_out, void* head_ws, void* stream) {
+    if (!z || !center || n <= 0 || d <= 0) return EOE_ERR_ARG;
+    if (loss_out && !head_ws) return EOE_ERR_ARG;
+    if (!loss_out && !scores_out && !grad_z_out) return EOE_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    EOE_DISPATCH_DTYPE(z_dtype, (hsc_launch<T, ROW_DSVDD>(z, nullptr, n, d, 0, loss_out, scores_out, grad_z_out, head_ws, st, center)))
+}
+
+extern "C" int eoe_focal_fwd_bwd(const void* x, int x_dtype, const int64_t* labels, int64_t n, int64_t nominal_label,
+                                 float gamma, float eps, float* loss_out, float* scores_out, void* grad_x_out,
+                                 void* head_ws, void* stream) {
+    if (!x || !labels || !loss_out || !head_ws || n <= 0) return EOE_ERR_ARG;
+    if (!(gamma >= 0.f) || !(eps >= 0.f && eps < 0.5f)) return EOE_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const FocalParams fp{gamma, eps};
+    EOE_DISPATCH_DTYPE(x_dtype, (bce_launch<T, true>(x, labels, n, nominal_label, loss_out, scores_out, grad_x_out, head_ws, st, fp)))
 }
 
 static int clip_check(const void* z, const float* text, int64_t n, int64_t d, int64_t K) {

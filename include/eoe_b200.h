@@ -81,6 +81,30 @@ int eoe_bce_fwd_bwd(const void* x, int x_dtype, const int64_t* labels, int64_t n
 int eoe_bce_score(const void* x, int x_dtype, int64_t n, int64_t nominal_label, float* scores_out,
                   void* stream);
 
+/* DSADTrainer.loss + backward + compute_anomaly_score. Replaces src/eoe/training/dsad.py:13-22.
+ *   s_i = norm(z_i)^2 (square root then square, as the reference evaluates it)
+ *   loss_out [1] = mean_i( label_i==nominal ? s_i : 1/(s_i + 1e-9) );  grad = 2 z/n  |  -2 z/((s+1e-9)^2 n)
+ *   scores_out [n] = 1 - exp(-(sqrt(s_i + 1) - 1))   (dsad.py:13-16; identical to eoe_hsc_score)      (nullable) */
+int eoe_dsad_fwd_bwd(const void* z, int z_dtype, const int64_t* labels, int64_t n, int64_t d,
+                     int64_t nominal_label, float* loss_out, float* scores_out, void* grad_z_out,
+                     void* head_ws, void* stream);
+
+/* DSVDDTrainer.loss + backward + compute_anomaly_score. Replaces src/eoe/training/dsvdd.py:23-27.
+ *   center [d] fp32 (the [1,d] tensor returned by prepare_metric, dsvdd.py:11-21), 16-byte aligned for the vector path
+ *   scores_out [n] = sum_j (z_ij - c_j)^2;  loss_out [1] = mean(scores);  grad = 2 (z - c)/n
+ *   any of loss_out / scores_out / grad_z_out may be null (score only: test time, ad_trainer.py:508) */
+int eoe_dsvdd_fwd_bwd(const void* z, int z_dtype, const float* center, int64_t n, int64_t d,
+                      float* loss_out, float* scores_out, void* grad_z_out, void* head_ws, void* stream);
+
+/* FocalTrainer.loss (FocalLoss, gamma = 2, eps = 1e-7) + backward + compute_anomaly_score.
+ * Replaces src/eoe/training/focal.py:11-39.
+ *   bce_i = binary_cross_entropy_with_logits(x_i, y_i); pt = clamp(exp(-bce), eps, 1-eps)
+ *   loss_out [1] = mean( (1 - pt)^gamma * bce );  scores_out [n] = sigmoid(x) or 1 - sigmoid(x) (focal.py:33-35)
+ *   grad_x_out [n] = d loss / d x (clamp passes the gradient on the closed interval, as torch.clamp does) */
+int eoe_focal_fwd_bwd(const void* x, int x_dtype, const int64_t* labels, int64_t n, int64_t nominal_label,
+                      float gamma, float eps, float* loss_out, float* scores_out, void* grad_x_out,
+                      void* head_ws, void* stream);
+
 /* ADClipTrainer.compute_anomaly_score. Replaces src/eoe/training/clip.py:66-79.
  *   z [n,d] image features, text [K,d] fp32 (`center`); text rows are re-normalised (clip.py:69)
  *   scores_out [n] fp32 = softmax_k(scale * z^_i . T^_k)[K-1]     (scale = 100, clip.py:71)

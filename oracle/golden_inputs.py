@@ -35,6 +35,17 @@ def bce_inputs(n=256, seed=12):
     return x, y
 
 
+def dsvdd_inputs(n=256, d=256, seed=14):
+    """features and a DSVDD centre as prepare_metric leaves it (|c| >= eps = 0.1, dsvdd.py:19-20)."""
+    rng = np.random.default_rng(seed)
+    z = (0.3 * rng.standard_normal((n, d))).astype(np.float32)
+    c = (0.2 * rng.standard_normal((1, d))).astype(np.float32)
+    c[(np.abs(c) < 0.1) & (c < 0)] = -0.1
+    c[(np.abs(c) < 0.1) & (c > 0)] = 0.1
+    z[4] = c[0]                      # a row sitting on the centre: score 0, grad 0
+    return z, c
+
+
 def clip_inputs(K, n=128, d=512, seed=13):
     rng = np.random.default_rng(seed + K)
     z = rng.standard_normal((n, d)).astype(np.float32)

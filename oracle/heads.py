@@ -13,6 +13,9 @@ Reference lines restated (paths relative to /root/reference/src/eoe):
   bce_*        training/bce.py:15-20   (torch binary_cross_entropy_with_logits, mean reduction)
   clip_score   training/clip.py:66-79
   clip_oe_loss training/clip.py:81-103
+  dsad_*       training/dsad.py:13-22
+  dsvdd_*      training/dsvdd.py:23-27
+  focal_*      training/focal.py:11-39   (FocalLoss, gamma = 2, eps = 1e-7)
 """
 import numpy as np
 
@@ -94,6 +97,85 @@ def bce_grad(x, labels):
     x = _f32(np.asarray(x).reshape(-1))
     y = _f32(labels)
     return ((_sigmoid(x) - y) / F32(x.shape[0])).astype(F32)
+
+
+# --------------------------------------------------------------------------- DSAD
+def dsad_score(z):
+    """training/dsad.py:13-16: the HSC score formula."""
+    return hsc_score(z)
+
+
+def _dsad_dists(z):
+    z = _f32(z)
+    nrm = np.sqrt(np.sum(z * z, axis=1, dtype=np.float32)).astype(F32)
+    return (nrm * nrm).astype(F32)                       # torch.norm(z, p=2, dim=1) ** 2   (dsad.py:19)
+
+
+def dsad_loss(z, labels, nominal_label=0):
+    """training/dsad.py:18-22  mean(where(labels==nominal, dists, (dists + 1e-9) ** -1))."""
+    d = _dsad_dists(z)
+    with np.errstate(divide="ignore"):
+        anom = (F32(1) / (d + F32(1e-9))).astype(F32)
+    return F32(np.where(np.asarray(labels) == nominal_label, d, anom).astype(F32).mean(dtype=np.float32))
+
+
+def dsad_grad(z, labels, nominal_label=0):
+    """2 z / n (nominal) or -2 z / ((dists + 1e-9)^2 n) (anomalous)."""
+    z = _f32(z)
+    n = z.shape[0]
+    d = _dsad_dists(z)
+    with np.errstate(divide="ignore", over="ignore"):
+        coef = np.where(np.asarray(labels) == nominal_label, F32(2), F32(-2) / ((d + F32(1e-9)) ** 2)).astype(F32) / F32(n)
+    return (coef[:, None] * z).astype(F32)
+
+
+# --------------------------------------------------------------------------- DSVDD
+def dsvdd_score(z, center):
+    """training/dsvdd.py:23-24  (features - center).pow(2).sum(-1)."""
+    diff = _f32(z) - _f32(center).reshape(1, -1)
+    return np.sum(diff * diff, axis=1, dtype=np.float32).astype(F32)
+
+
+def dsvdd_loss(z, center):
+    """training/dsvdd.py:26-27  mean of the scores."""
+    return F32(dsvdd_score(z, center).mean(dtype=np.float32))
+
+
+def dsvdd_grad(z, center):
+    z = _f32(z)
+    return (F32(2) * (z - _f32(center).reshape(1, -1)) / F32(z.shape[0])).astype(F32)
+
+
+# --------------------------------------------------------------------------- focal
+def _bce_elem(x, y):
+    return (np.maximum(x, F32(0)) - x * y + np.log1p(np.exp(-np.abs(x)))).astype(F32)
+
+
+def focal_loss(x, labels, gamma=2.0, eps=1e-7):
+    """training/focal.py:19-24  mean((1 - clamp(exp(-bce), eps, 1-eps)) ** gamma * bce)."""
+    x = _f32(np.asarray(x).reshape(-1))
+    y = _f32(labels)
+    b = _bce_elem(x, y)
+    pt = np.clip(np.exp(-b).astype(F32), F32(eps), F32(1) - F32(eps))
+    return F32((((F32(1) - pt) ** F32(gamma)) * b).astype(F32).mean(dtype=np.float32))
+
+
+def focal_grad(x, labels, gamma=2.0, eps=1e-7):
+    """(sigmoid(x) - y) [ (1-pt)^g + 1{eps <= exp(-bce) <= 1-eps} g (1-pt)^(g-1) pt bce ] / n."""
+    x = _f32(np.asarray(x).reshape(-1))
+    y = _f32(labels)
+    b = _bce_elem(x, y)
+    raw = np.exp(-b).astype(F32)
+    pt = np.clip(raw, F32(eps), F32(1) - F32(eps))
+    inside = (raw >= F32(eps)) & (raw <= F32(1) - F32(eps))
+    q = F32(1) - pt
+    t = q ** F32(gamma) + np.where(inside, F32(gamma) * q ** F32(gamma - 1) * pt * b, F32(0))
+    return ((_sigmoid(x) - y) * t / F32(x.shape[0])).astype(F32)
+
+
+def focal_score(x, nominal_label=0):
+    """training/focal.py:33-35: sigmoid, or 1 - sigmoid when nominal_label != 0."""
+    return bce_score(x, nominal_label)
 
 
 # --------------------------------------------------------------------------- CLIP head

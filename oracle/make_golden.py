@@ -52,6 +52,24 @@ def make_heads(h):
         out[f"bce_score_nom{nom}"] = h["BCETrainer"].compute_anomaly_score(None, xt, None, nominal_label=nom).numpy()
     out["bce_in_sum"] = np.float64(x.astype(np.float64).sum())
 
+    # DSAD / DSVDD / focal (dsad.py:13-22, dsvdd.py:23-27, focal.py:11-39) on the HSC / BCE inputs
+    z, y = gi.hsc_inputs()
+    zt, yt = torch.from_numpy(z), torch.from_numpy(y)
+    for nom in (0, 1):
+        l, g = _grad(lambda t: h["DSADTrainer"].loss(None, t, yt, None, nominal_label=nom), zt)
+        out[f"dsad_loss_nom{nom}"], out[f"dsad_grad_nom{nom}"] = l, g
+    out["dsad_score"] = h["DSADTrainer"].compute_anomaly_score(None, zt, None).numpy()
+    zd, cd = gi.dsvdd_inputs()
+    zdt, cdt = torch.from_numpy(zd), torch.from_numpy(cd)
+    l, g = _grad(lambda t: h["DSVDDTrainer"].loss(None, t, None, cdt), zdt)
+    out["dsvdd_loss"], out["dsvdd_grad"] = l, g
+    out["dsvdd_score"] = h["DSVDDTrainer"].compute_anomaly_score(None, zdt, cdt).numpy()
+    out["dsvdd_in_sum"] = np.float64(zd.astype(np.float64).sum() + cd.astype(np.float64).sum())
+    l, g = _grad(lambda t: h["FocalTrainer"].loss(None, t, ybt, None), xt)
+    out["focal_loss"], out["focal_grad"] = l, g
+    for nom in (0, 1):
+        out[f"focal_score_nom{nom}"] = h["FocalTrainer"].compute_anomaly_score(None, xt, None, nominal_label=nom).numpy()
+
     for K in (2, 10, 30):
         zc, yc, c = gi.clip_inputs(K)
         zt, yt, ct = torch.from_numpy(zc), torch.from_numpy(yc), torch.from_numpy(c)

@@ -173,3 +173,96 @@ def test_heads_large_property():
     g = _np(grad[:1024]) * 1024.0
     _close(g, oh.hsc_grad(base, yb, 0), rtol=1e-4, atol=1e-9)
     assert torch.equal(grad[:1024], grad[-1024:])
+
+
+# ------------------------------------------------------------------------------------------------ DSAD / DSVDD / focal
+def test_dsad_dsvdd_focal_golden(golden_dir):
+    """The reference's own dsad.py / dsvdd.py / focal.py hooks (fixtures from oracle/make_golden.py)."""
+    from eoe_b200 import ops
+    g = np.load(os.path.join(golden_dir, "heads.npz"))
+    z, y = gi.hsc_inputs()
+    for nom in (0, 1):
+        zt = _t(z).requires_grad_(True)
+        loss, scores = ops.dsad_loss(zt, _t(y), nominal_label=nom)
+        loss.backward()
+        _close(loss.item(), g[f"dsad_loss_nom{nom}"], rtol=1e-5)
+        # the zero row of an anomalous sample has loss 1e9 and gradient 0 * 1e18: both sides give 0
+        _close(_np(zt.grad), g[f"dsad_grad_nom{nom}"], rtol=1e-4, atol=1e-9)
+        _close(_np(scores), g["dsad_score"], rtol=1e-4, atol=1e-7)
+    zd, cd = gi.dsvdd_inputs()
+    zt = _t(zd).requires_grad_(True)
+    loss, scores = ops.dsvdd_loss(zt, _t(cd))
+    loss.backward()
+    _close(loss.item(), g["dsvdd_loss"], rtol=1e-5)
+    _close(_np(scores), g["dsvdd_score"], rtol=1e-5, atol=1e-7)
+    _close(_np(zt.grad), g["dsvdd_grad"], rtol=1e-5, atol=1e-10)
+    _close(_np(ops.dsvdd_score(_t(zd), _t(cd))), g["dsvdd_score"], rtol=1e-5, atol=1e-7)
+    x, yb = gi.bce_inputs()
+    xt = _t(x).requires_grad_(True)
+    loss, scores = ops.focal_loss(xt, _t(yb))
+    loss.backward()
+    _close(loss.item(), g["focal_loss"], rtol=1e-5)
+    _close(_np(xt.grad), g["focal_grad"], rtol=1e-4, atol=1e-10)
+    _close(_np(scores), g["focal_score_nom0"], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("n,d", [(1, 4), (7, 100), (256, 256), (257, 512), (5, 33), (19, 2048), (1000, 260)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_dsad_dsvdd_vs_oracle(n, d, dtype):
+    from eoe_b200 import ops
+    rng = np.random.default_rng(n * 1000 + d + 1)
+    z = (0.8 / np.sqrt(d) * rng.standard_normal((n, d))).astype(np.float32)
+    c = (0.5 / np.sqrt(d) * rng.standard_normal((1, d))).astype(np.float32)
+    zt = _t(z, dtype)
+    zq = _np(zt)
+    y = rng.integers(0, 2, n)
+    gtol = 1e-4 if dtype == torch.float32 else 1e-2       # grads are rounded to the feature dtype
+    gatol = 1e-9 if dtype == torch.float32 else 1e-5
+    for nom in (0, 1):
+        zz = zt.clone().requires_grad_(True)
+        loss, scores = ops.dsad_loss(zz, _t(y), nominal_label=nom)
+        (loss * 2.0).backward()
+        _close(loss.item(), oh.dsad_loss(zq, y, nom), rtol=1e-4)
+        _close(_np(scores), oh.dsad_score(zq), rtol=2e-4, atol=1e-7)
+        _close(_np(zz.grad), 2.0 * oh.dsad_grad(zq, y, nom), rtol=gtol, atol=gatol * max(1.0, float(np.abs(oh.dsad_grad(zq, y, nom)).max())))
+    zz = zt.clone().requires_grad_(True)
+    loss, scores = ops.dsvdd_loss(zz, _t(c))
+    loss.backward()
+    _close(loss.item(), oh.dsvdd_loss(zq, c), rtol=1e-4)
+    _close(_np(scores), oh.dsvdd_score(zq, c), rtol=1e-4, atol=1e-7)
+    _close(_np(zz.grad), oh.dsvdd_grad(zq, c), rtol=gtol, atol=gatol)
+    _close(_np(ops.dsvdd_score(zt, _t(c))), oh.dsvdd_score(zq, c), rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 255, 1001, 65537])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_focal_vs_oracle(n, dtype):
+    from eoe_b200 import ops
+    rng = np.random.default_rng(n + 17)
+    x = (4 * rng.standard_normal((n, 1))).astype(np.float32)
+    x[0, 0] = 30.0                                         # pt below eps for label 0: the clamp branch (gradient cut)
+    xt = _t(x, dtype)
+    xq = _np(xt)
+    y = rng.integers(0, 2, n)
+    y[0] = 0
+    xx = xt.clone().requires_grad_(True)
+    loss, scores = ops.focal_loss(xx, _t(y), nominal_label=1)
+    loss.backward()
+    _close(loss.item(), oh.focal_loss(xq, y), rtol=1e-4)
+    _close(_np(scores), oh.focal_score(xq, 1), rtol=1e-4, atol=1e-7)
+    gtol = 2e-4 if dtype == torch.float32 else 1e-2
+    _close(_np(xx.grad).reshape(-1), oh.focal_grad(xq, y), rtol=gtol, atol=1e-9 if dtype == torch.float32 else 1e-6)
+
+
+def test_new_heads_nan_propagates():
+    from eoe_b200 import ops
+    z = torch.full((4, 64), 0.1, device=DEV)
+    z[1, 3] = float("nan")
+    y = torch.tensor([0, 1, 0, 1], device=DEV)
+    l, s, _ = ops.dsad_fused(z, y)
+    assert np.isnan(l.item()) and np.isnan(_np(s)[1]) and np.isfinite(_np(s)[0])
+    l, s, _ = ops.dsvdd_fused(z, torch.zeros(64, device=DEV))
+    assert np.isnan(l.item()) and np.isnan(_np(s)[1]) and np.isfinite(_np(s)[2])
+    x = torch.tensor([0.5, float("nan"), -1.0], device=DEV)
+    l, s, g = ops.focal_fused(x, torch.tensor([1, 0, 1], device=DEV))
+    assert np.isnan(l.item()) and np.isnan(_np(s)[1]) and np.isnan(_np(g)[1]) and np.isfinite(_np(g)[0])

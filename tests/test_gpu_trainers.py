@@ -36,10 +36,27 @@ def _ref_hsc(z, y, nominal=0):
     return torch.where(y == nominal, d, -torch.log(s + 1e-9)).mean()
 
 
-@pytest.mark.parametrize("objective", ["hsc", "bce"])
+def _ref_focal(x, y, gamma=2.0, eps=1e-7):                 # focal.py:19-24
+    b = torch.nn.functional.binary_cross_entropy_with_logits(x, y, reduction="none")
+    pt = torch.exp(-b).clamp(eps, 1.0 - eps)
+    return ((1 - pt).pow(gamma) * b).mean()
+
+
+def _ref_dsvdd_center(model, loader, eps=1e-1):            # dsvdd.py:11-21
+    center = []
+    for imgs, lbls, _ in loader:
+        with torch.no_grad():
+            center.append(model(imgs.to(DEV)[lbls.to(DEV) == 0]).cpu().mean(0).unsqueeze(0))
+    center = torch.cat(center).mean(0).unsqueeze(0).to(DEV)
+    center[(abs(center) < eps) & (center < 0)] = -eps
+    center[(abs(center) < eps) & (center > 0)] = eps
+    return center
+
+
+@pytest.mark.parametrize("objective", ["hsc", "bce", "dsad", "dsvdd", "focal"])
 def test_training_loop_matches_reference_objective(objective):
     from eoe_b200.training import TRAINER
-    d_out = 64 if objective == "hsc" else 1
+    d_out = 1 if objective in ("bce", "focal") else 64
     loader = _loader(4, 32, seed=3)
     model = _mlp(32, d_out)
     ref_model = copy.deepcopy(model).to(DEV)
@@ -49,6 +66,9 @@ def test_training_loop_matches_reference_objective(objective):
     opt = torch.optim.Adam(ref_model.parameters(), lr=1e-3, weight_decay=0.0)
     sched = torch.optim.lr_scheduler.MultiStepLR(opt, [1], 0.1)
     ref_losses, last_scores, last_labels = [], [], []
+    ref_center = _ref_dsvdd_center(ref_model, loader) if objective == "dsvdd" else None
+    if ref_center is not None:
+        torch.testing.assert_close(tr.center, ref_center, rtol=1e-5, atol=1e-6)
     for ep in range(2):
         acc, last_scores, last_labels = [], [], []
         for imgs, lbls, _ in loader:
@@ -58,6 +78,16 @@ def test_training_loop_matches_reference_objective(objective):
             if objective == "hsc":
                 loss = _ref_hsc(f, lbls)
                 sc = 1 - torch.exp(-(torch.sqrt(torch.norm(f, p=2, dim=1) ** 2 + 1) - 1))
+            elif objective == "dsad":                                  # dsad.py:13-22
+                d2 = torch.norm(f, p=2, dim=1) ** 2
+                loss = torch.where(lbls == 0, d2, (d2 + 1e-9) ** (-1)).mean()
+                sc = 1 - torch.exp(-(torch.sqrt(d2 + 1) - 1))
+            elif objective == "dsvdd":                                 # dsvdd.py:23-27
+                sc = (f - ref_center).pow(2).sum(-1)
+                loss = sc.mean()
+            elif objective == "focal":
+                loss = _ref_focal(f.squeeze(), lbls.float())
+                sc = torch.sigmoid(f).squeeze()
             else:
                 loss = torch.nn.functional.binary_cross_entropy_with_logits(f.squeeze(), lbls.float())
                 sc = torch.sigmoid(f).squeeze()

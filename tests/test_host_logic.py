@@ -106,7 +106,7 @@ def test_grad_buckets_average_equals_full_batch_gloo_world2():
 def test_trainer_registry_and_hook_signatures():
     import inspect
     from eoe_b200.training import TRAINER, ADTrainer
-    assert set(TRAINER) == {"hsc", "bce", "clip"}
+    assert set(TRAINER) == {"hsc", "bce", "clip", "dsvdd", "dsad", "focal"}      # training/__init__.py:8-11
     for cls in TRAINER.values():
         assert issubclass(cls, ADTrainer)
         for hook, first in (("prepare_metric", ["self", "cstr", "loader", "model", "seed"]),

@@ -41,6 +41,26 @@ def test_bce_oracle_matches_reference_fixture(golden_dir):
         _close(oh.bce_score(x, nom), g[f"bce_score_nom{nom}"], atol=1e-12)
 
 
+def test_dsad_dsvdd_focal_oracle_matches_reference_fixture(golden_dir):
+    """dsad.py:13-22, dsvdd.py:23-27, focal.py:11-39 run from the live reference (oracle/make_golden.py)."""
+    g = _load(golden_dir, "heads.npz")
+    z, y = gi.hsc_inputs()
+    _close(oh.dsad_score(z), g["dsad_score"])
+    for nom in (0, 1):
+        _close(oh.dsad_loss(z, y, nom), g[f"dsad_loss_nom{nom}"])
+        _close(oh.dsad_grad(z, y, nom), g[f"dsad_grad_nom{nom}"], rtol=2e-5, atol=1e-9)
+    zd, cd = gi.dsvdd_inputs()
+    assert float(g["dsvdd_in_sum"]) == float(zd.astype(np.float64).sum() + cd.astype(np.float64).sum())
+    _close(oh.dsvdd_score(zd, cd), g["dsvdd_score"])
+    _close(oh.dsvdd_loss(zd, cd), g["dsvdd_loss"])
+    _close(oh.dsvdd_grad(zd, cd), g["dsvdd_grad"], atol=1e-10)
+    x, yb = gi.bce_inputs()
+    _close(oh.focal_loss(x, yb), g["focal_loss"])
+    _close(oh.focal_grad(x, yb).reshape(-1, 1), g["focal_grad"], rtol=2e-5, atol=1e-10)
+    for nom in (0, 1):
+        _close(oh.focal_score(x, nom), g[f"focal_score_nom{nom}"], atol=1e-12)
+
+
 @pytest.mark.parametrize("K", [2, 10, 30])
 def test_clip_oracle_matches_reference_fixture(golden_dir, K):
     g = _load(golden_dir, "heads.npz")

@@ -54,6 +54,47 @@ def test_bce_live(ref, n):
         np.testing.assert_allclose(oh.bce_score(x, nom), sc, rtol=1e-6, atol=1e-12)
 
 
+@pytest.mark.parametrize("n,d", [(2, 8), (5, 33), (256, 256)])
+def test_dsad_dsvdd_live(ref, n, d):
+    rng = np.random.default_rng(n * d)
+    z = (0.3 * rng.standard_normal((n, d))).astype(np.float32)
+    y = rng.integers(0, 2, n)
+    c = (0.2 * rng.standard_normal((1, d))).astype(np.float32)
+    zt = torch.from_numpy(z).requires_grad_(True)
+    for nom in (0, 1):
+        loss = ref["DSADTrainer"].loss(None, zt, torch.from_numpy(y), None, nominal_label=nom)
+        zt.grad = None
+        loss.backward()
+        np.testing.assert_allclose(oh.dsad_loss(z, y, nom), loss.item(), rtol=1e-5)
+        np.testing.assert_allclose(oh.dsad_grad(z, y, nom), zt.grad.numpy(), rtol=3e-5, atol=1e-9)
+    np.testing.assert_allclose(oh.dsad_score(z), ref["DSADTrainer"].compute_anomaly_score(None, zt.detach(), None).numpy(),
+                               rtol=1e-5, atol=1e-8)
+    zt.grad = None
+    loss = ref["DSVDDTrainer"].loss(None, zt, None, torch.from_numpy(c))
+    loss.backward()
+    np.testing.assert_allclose(oh.dsvdd_loss(z, c), loss.item(), rtol=1e-5)
+    np.testing.assert_allclose(oh.dsvdd_grad(z, c), zt.grad.numpy(), rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(oh.dsvdd_score(z, c),
+                               ref["DSVDDTrainer"].compute_anomaly_score(None, zt.detach(), torch.from_numpy(c)).numpy(), rtol=1e-5)
+
+
+@pytest.mark.parametrize("n", [2, 257])
+def test_focal_live(ref, n):
+    rng = np.random.default_rng(n + 3)
+    x = (4 * rng.standard_normal((n, 1))).astype(np.float32)
+    x[0, 0] = 30.0                                        # exp(-bce) below eps when the label disagrees: clamp branch
+    y = rng.integers(0, 2, n)
+    y[0] = 0
+    xt = torch.from_numpy(x).requires_grad_(True)
+    loss = ref["FocalTrainer"].loss(None, xt, torch.from_numpy(y), None)
+    loss.backward()
+    np.testing.assert_allclose(oh.focal_loss(x, y), loss.item(), rtol=1e-5)
+    np.testing.assert_allclose(oh.focal_grad(x, y), xt.grad.numpy().reshape(-1), rtol=3e-5, atol=1e-10)
+    for nom in (0, 1):
+        sc = ref["FocalTrainer"].compute_anomaly_score(None, xt.detach(), None, nominal_label=nom).numpy()
+        np.testing.assert_allclose(oh.focal_score(x, nom), sc, rtol=3e-6, atol=1e-12)   # 1 - sigmoid: one fp32 ulp
+
+
 @pytest.mark.parametrize("K", [2, 5, 30])
 @pytest.mark.parametrize("mode", ["one_vs_rest", "leave_one_out"])
 def test_clip_live(ref, K, mode):
