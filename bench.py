@@ -278,7 +278,7 @@ def run_ours(args):
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
 
-    def e2e_job(n_steps):
+    def e2e_job(n_steps, host=host, dbuf=dbuf):
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
         with torch.cuda.stream(copy_stream):
@@ -312,6 +312,20 @@ def run_ours(args):
     if ws > 1:
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
     e2e_val = ws * S * B / float(t.item())
+
+    # ---- e2e from RAW pixels: uint8 NHWC host batches, ToTensor + Normalize fused into the patchify kernel
+    host8 = [torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    dbuf8 = [torch.empty(B, 224, 224, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+    e2e_job(min(W, S), host8, dbuf8)
+    sync()
+    t0 = time.perf_counter()
+    e2e_job(S, host8, dbuf8)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if ws > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    e2e_u8_val = ws * S * B / float(t.item())
 
     if rank != 0:
         if ws > 1:
@@ -358,6 +372,8 @@ def run_ours(args):
         "roofline": roofline,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4,
                 "note": "pinned fp32 host batches, double-buffered H2D on a copy stream, scores + AUC read on host"},
+        "e2e_u8": {"value": e2e_u8_val, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224, "d2h_bytes_per_step": B * 4,
+                   "note": "same job from raw uint8 NHWC pixels: ToTensor + Normalize fused into the patchify kernel (eoe_vit_encode_u8)"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "auc": auc_val,

@@ -22,6 +22,7 @@ EOE_AUC_STATUS_SINGLE_CLASS = 2
 EOE_EPI_BIAS, EOE_EPI_BIAS_QUICKGELU, EOE_EPI_BIAS_RESIDUAL_F32, EOE_EPI_PATCH_EMBED = 0, 1, 2, 3
 EOE_EPI_LNFOLD_BIAS, EOE_EPI_LNFOLD_QUICKGELU, EOE_EPI_RESIDUAL_STATS = 4, 5, 6
 EOE_ABI_VERSION = 2
+EOE_LAYOUT_NCHW, EOE_LAYOUT_NHWC = 0, 1
 
 DTYPE_CODE = {torch.float32: EOE_F32, torch.float16: EOE_F16, torch.bfloat16: EOE_BF16}
 
@@ -70,8 +71,10 @@ SIGNATURES = {
     "eoe_vit_plan_create": (_I, [C.POINTER(VitWeights), _I64, _P, _SZ, C.POINTER(_P)]),
     "eoe_vit_plan_destroy": (None, [_P]),
     "eoe_vit_encode": (_I, [_P, _P, _I64, _P, _P, _I64, _F, _P, _P]),
+    "eoe_vit_encode_u8": (_I, [_P, _P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _I64, _P, _P, _I64, _F, _P, _P]),
     "eoe_vit_profile_enable": (_I, [_P, _I]),
     "eoe_vit_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(C.c_double)]),
+    "eoe_debug_set": (None, [_I]),
     "eoe_gemm": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _I, _I, _P, _I64, _P]),
     "eoe_vit_fold_layernorm": (_I, [_P, _P, _P, _P, _I64, _I64, _I, _P, _P, _P, _P]),
     "eoe_gemm_lnfold": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _I, _P]),

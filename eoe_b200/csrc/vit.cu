@@ -136,6 +136,71 @@ im2col_kernel(const float* __restrict__ imgs, uint16_t* __restrict__ patches, in
     }
 }
 
+// uint8 images -> patches with torchvision's ToTensor + Normalize fused in (reference input pipeline:
+// clip_official/clip/clip.py:58-65 `_transform` = ... ToTensor(), Normalize(mean, std); eoe's GPU Normalize,
+// utils/transformations.py:126-138).  ToTensor is u8 / 255 and Normalize is (x - mean) / std, both fp32 with correctly
+// rounded divisions, so there are only 3 x 256 possible results: they are tabulated once per CTA in shared memory,
+// already rounded to the operand dtype -- bit-identical to normalising on the host and feeding the fp32 path.
+// NHWC == false: imgs [B,3,R,R] (ToTensor's layout);  NHWC == true: imgs [B,R,R,3] (decoded image files).
+// One thread converts 16 consecutive pixels of one patch row (16 | P).
+struct NormParams { float mean[3], stdv[3]; };
+template <bool BF16, bool NHWC>
+__global__ void __launch_bounds__(256)
+im2col_u8_kernel(const uint8_t* __restrict__ imgs, uint16_t* __restrict__ patches, int64_t B, int R, int P, NormParams np) {
+    __shared__ uint16_t lut[3][256];
+    for (int i = threadIdx.x; i < 768; i += 256) {
+        const int c = i >> 8, v = i & 255;
+        const float x = __fdiv_rn(__fdiv_rn((float)v, 255.0f) - np.mean[c], np.stdv[c]);
+        lut[c][v] = (uint16_t)(gemm::pack2<BF16>(x, 0.f) & 0xffffu);
+    }
+    __syncthreads();
+    const int g = R / P, segs = P / 16;
+    const int64_t total = NHWC ? B * (int64_t)R * (R / 16) : B * 3 * (int64_t)R * (R / 16);
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+        int64_t t = idx;
+        const int xs = (int)(t % (R / 16)); t /= (R / 16);          // 16-pixel segment along x
+        const int y = (int)(t % R); t /= R;
+        const int gx = xs / segs, sx = xs % segs, gy = y / P, py = y % P;
+        if (NHWC) {
+            const int64_t b = t;
+            const uint4* src = reinterpret_cast<const uint4*>(imgs + ((b * R + y) * (int64_t)R + xs * 16) * 3);
+            const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+            const uint32_t wds[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            uint16_t o[3][16];
+#pragma unroll
+            for (int i = 0; i < 48; ++i) {
+                const uint32_t byte = (wds[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+                o[i % 3][i / 3] = lut[i % 3][byte];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint16_t* dst = patches + (((b * g + gy) * g + gx) * 3 + c) * (int64_t)(P * P) + py * P + sx * 16;
+                uint4 w0, w1;
+                w0.x = o[c][0] | ((uint32_t)o[c][1] << 16); w0.y = o[c][2] | ((uint32_t)o[c][3] << 16);
+                w0.z = o[c][4] | ((uint32_t)o[c][5] << 16); w0.w = o[c][6] | ((uint32_t)o[c][7] << 16);
+                w1.x = o[c][8] | ((uint32_t)o[c][9] << 16); w1.y = o[c][10] | ((uint32_t)o[c][11] << 16);
+                w1.z = o[c][12] | ((uint32_t)o[c][13] << 16); w1.w = o[c][14] | ((uint32_t)o[c][15] << 16);
+                reinterpret_cast<uint4*>(dst)[0] = w0;
+                reinterpret_cast<uint4*>(dst)[1] = w1;
+            }
+        } else {
+            const int c = (int)(t % 3); t /= 3;
+            const int64_t b = t;
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(imgs + ((b * 3 + c) * R + y) * (int64_t)R + xs * 16));
+            const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t b0 = (wds[i >> 1] >> ((i & 1) * 16)) & 0xffu, b1 = (wds[i >> 1] >> ((i & 1) * 16 + 8)) & 0xffu;
+                o[i] = lut[c][b0] | ((uint32_t)lut[c][b1] << 16);
+            }
+            uint16_t* dst = patches + (((b * g + gy) * g + gx) * 3 + c) * (int64_t)(P * P) + py * P + sx * 16;
+            reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ LayerNorm
 // fp32 statistics over `width` (model.py:153-159, eps 1e-5); one warp per row, row kept in registers.
 // cls_emb != null: rows with row % L == 0 are synthesised as class_embedding + positional_embedding[0]
@@ -860,23 +925,31 @@ extern "C" void eoe_vit_plan_destroy(eoe_vit_plan* p) {
     delete p;
 }
 
-extern "C" int eoe_vit_encode(eoe_vit_plan* p, const float* imgs, int64_t B, float* feats_out, const float* text,
-                              int64_t K, float scale, float* scores_out, void* stream) {
-    if (!p || !imgs || B <= 0 || B > p->max_batch) return EOE_ERR_ARG;
-    if ((text == nullptr) != (scores_out == nullptr)) return EOE_ERR_ARG;
-    if ((uintptr_t)imgs % 16 != 0) return EOE_ERR_ALIGN;
+// imgs_f32 != null: normalised fp32 NCHW input; else imgs_u8 (+ layout, norm): raw pixels, ToTensor + Normalize fused
+static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t* imgs_u8, int layout, const NormParams& norm,
+                           int64_t B, float* feats_out, const float* text, int64_t K, float scale, float* scores_out,
+                           void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const eoe_vit_weights& w = p->w;
     const int W = w.width, dt = w.operand_dtype, L = p->L;
     const int64_t M = B * L, Mp = B * p->g2;
     int rc;
     // 1. patchify
-    {
+    if (imgs_f32) {
         const int64_t total = B * 3 * (int64_t)w.resolution * w.resolution / 4;
         int grid = (int)((total + 255) / 256 < (int64_t)num_sms() * 16 ? (total + 255) / 256 : (int64_t)num_sms() * 16);
-        if (dt == EOE_BF16) im2col_kernel<true><<<grid, 256, 0, st>>>(imgs, p->patches, B, w.resolution, w.patch);
-        else im2col_kernel<false><<<grid, 256, 0, st>>>(imgs, p->patches, B, w.resolution, w.patch);
+        if (dt == EOE_BF16) im2col_kernel<true><<<grid, 256, 0, st>>>(imgs_f32, p->patches, B, w.resolution, w.patch);
+        else im2col_kernel<false><<<grid, 256, 0, st>>>(imgs_f32, p->patches, B, w.resolution, w.patch);
         if ((rc = check_launch("im2col_kernel"))) return rc;
+    } else {
+        const int R = w.resolution;
+        const int64_t total = (layout ? 1 : 3) * B * (int64_t)R * (R / 16);
+        int grid = (int)((total + 255) / 256 < (int64_t)num_sms() * 8 ? (total + 255) / 256 : (int64_t)num_sms() * 8);
+#define EOE_U8(BF, HWC) im2col_u8_kernel<BF, HWC><<<grid, 256, 0, st>>>(imgs_u8, p->patches, B, R, w.patch, norm)
+        if (dt == EOE_BF16) { if (layout) EOE_U8(true, true); else EOE_U8(true, false); }
+        else { if (layout) EOE_U8(false, true); else EOE_U8(false, false); }
+#undef EOE_U8
+        if ((rc = check_launch("im2col_u8_kernel"))) return rc;
     }
     // 2. patch-embed GEMM, epilogue adds positional embedding and scatters to token rows 1..g2 of each image
     {
@@ -956,6 +1029,31 @@ extern "C" int eoe_vit_encode(eoe_vit_plan* p, const float* imgs, int64_t B, flo
         if ((rc = clip_score_f32(feats, text, B, w.embed_dim, K, scale, scores_out, st))) return rc;
     }
     return EOE_OK;
+}
+
+extern "C" int eoe_vit_encode(eoe_vit_plan* p, const float* imgs, int64_t B, float* feats_out, const float* text,
+                              int64_t K, float scale, float* scores_out, void* stream) {
+    if (!p || !imgs || B <= 0 || B > p->max_batch) return EOE_ERR_ARG;
+    if ((text == nullptr) != (scores_out == nullptr)) return EOE_ERR_ARG;
+    if ((uintptr_t)imgs % 16 != 0) return EOE_ERR_ALIGN;
+    return vit_encode_impl(p, imgs, nullptr, 0, NormParams{}, B, feats_out, text, K, scale, scores_out, stream);
+}
+
+extern "C" int eoe_vit_encode_u8(eoe_vit_plan* p, const uint8_t* imgs, int layout, const float* mean_host,
+                                 const float* std_host, int64_t B, float* feats_out, const float* text, int64_t K,
+                                 float scale, float* scores_out, void* stream) {
+    if (!p || !imgs || !mean_host || !std_host || B <= 0 || B > p->max_batch) return EOE_ERR_ARG;
+    if (layout != EOE_LAYOUT_NCHW && layout != EOE_LAYOUT_NHWC) return EOE_ERR_ARG;
+    if ((text == nullptr) != (scores_out == nullptr)) return EOE_ERR_ARG;
+    if ((uintptr_t)imgs % 16 != 0) return EOE_ERR_ALIGN;
+    if (p->w.patch % 16 != 0 || p->w.resolution % 16 != 0) return EOE_ERR_SHAPE;
+    NormParams np;
+    for (int c = 0; c < 3; ++c) {
+        np.mean[c] = mean_host[c];
+        np.stdv[c] = std_host[c];
+        if (!(std_host[c] > 0.f)) return EOE_ERR_ARG;
+    }
+    return vit_encode_impl(p, nullptr, imgs, layout == EOE_LAYOUT_NHWC, np, B, feats_out, text, K, scale, scores_out, stream);
 }
 
 extern "C" int eoe_vit_profile_enable(eoe_vit_plan* p, int enable) {

@@ -25,7 +25,8 @@ def _strip(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
 class ClipImageEncoder(nn.Module):
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", operand_dtype=torch.bfloat16,
                  max_batch: int = 256, heads: Optional[int] = None, resolution: Optional[int] = None,
-                 fold_layernorm: bool = True):
+                 fold_layernorm: bool = True, input_mean=(0.48145466, 0.4578275, 0.40821073),
+                 input_std=(0.26862954, 0.26130258, 0.27577711)):
         """fold_layernorm: fold ln_1 / ln_2 into the QKV / c_fc GEMMs (eoe_vit_fold_layernorm; DESIGN.md "LayerNorm
         fold") instead of launching stand-alone LayerNorm kernels.  Same math (fp32 statistics of the fp32 residual
         stream); the 16-bit rounding point moves from LN(x) to x and to W*ln_w."""
@@ -48,6 +49,10 @@ class ClipImageEncoder(nn.Module):
         self.max_batch = int(max_batch)
         self.device_ = dev
         self.fold_layernorm = bool(fold_layernorm) and self.width <= 768      # eoe_gemm_lnfold: K <= 768
+        # uint8 inputs get ToTensor + Normalize fused into the patchify kernel; defaults are CLIP's constants
+        # (clip_official/clip/clip.py:64)
+        self._mean = (C.c_float * 3)(*[float(v) for v in input_mean])
+        self._std = (C.c_float * 3)(*[float(v) for v in input_std])
 
         def f32(t):
             return t.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -131,21 +136,39 @@ class ClipImageEncoder(nn.Module):
         return float(2 * g2 * 3 * self.patch ** 2 * W + self.n_layers * per_layer + 2 * W * self.embed_dim)
 
     def _prep(self, imgs):
+        """-> (contiguous tensor, layout or None).  float tensors [B,3,R,R] are already normalised (what the reference
+        hands to model(imgs), ad_trainer.py:507); uint8 tensors [B,3,R,R] or [B,R,R,3] are raw pixels."""
         L.require_cuda(imgs)
-        if imgs.dim() != 4 or imgs.shape[1] != 3 or imgs.shape[2] != self.resolution or imgs.shape[3] != self.resolution:
-            raise L.EoeError(f"images must be [B,3,{self.resolution},{self.resolution}], got {tuple(imgs.shape)}")
-        return imgs.detach().to(torch.float32).contiguous()       # encode_image casts to the weight dtype (model.py:337)
+        R = self.resolution
+        if imgs.dim() != 4:
+            raise L.EoeError(f"images must be 4-d, got {tuple(imgs.shape)}")
+        if imgs.dtype == torch.uint8:
+            if tuple(imgs.shape[1:]) == (3, R, R):
+                return imgs.detach().contiguous(), L.EOE_LAYOUT_NCHW
+            if tuple(imgs.shape[1:]) == (R, R, 3):
+                return imgs.detach().contiguous(), L.EOE_LAYOUT_NHWC
+            raise L.EoeError(f"uint8 images must be [B,3,{R},{R}] or [B,{R},{R},3], got {tuple(imgs.shape)}")
+        if tuple(imgs.shape[1:]) != (3, R, R):
+            raise L.EoeError(f"images must be [B,3,{R},{R}], got {tuple(imgs.shape)}")
+        return imgs.detach().to(torch.float32).contiguous(), None     # encode_image casts to the weight dtype (model.py:337)
+
+    def _encode(self, imgs, layout, n, feats, text, K, scale, scores):
+        lib = L.lib()
+        if layout is None:
+            L.check(lib.eoe_vit_encode(self._plan, L.ptr(imgs), n, L.ptr(feats), L.ptr(text), K, float(scale), L.ptr(scores),
+                                       L.stream_ptr(imgs.device)), "eoe_vit_encode")
+        else:
+            L.check(lib.eoe_vit_encode_u8(self._plan, L.ptr(imgs), layout, self._mean, self._std, n, L.ptr(feats), L.ptr(text),
+                                          K, float(scale), L.ptr(scores), L.stream_ptr(imgs.device)), "eoe_vit_encode_u8")
 
     @torch.no_grad()
     def forward(self, imgs: torch.Tensor) -> torch.Tensor:
-        imgs = self._prep(imgs)
+        imgs, layout = self._prep(imgs)
         B = imgs.shape[0]
         feats = torch.empty(B, self.embed_dim, dtype=torch.float32, device=imgs.device)
-        lib = L.lib()
         for s in range(0, B, self.max_batch):
             n = min(self.max_batch, B - s)
-            L.check(lib.eoe_vit_encode(self._plan, L.ptr(imgs[s:s + n]), n, L.ptr(feats[s:s + n]), None, 0, 100.0, None,
-                                       L.stream_ptr(imgs.device)), "eoe_vit_encode")
+            self._encode(imgs[s:s + n], layout, n, feats[s:s + n], None, 0, 100.0, None)
         return feats
 
     encode_image = forward
@@ -166,16 +189,13 @@ class ClipImageEncoder(nn.Module):
     def score(self, imgs: torch.Tensor, center: torch.Tensor, scale: float = 100.0, out: Optional[torch.Tensor] = None
               ) -> torch.Tensor:
         """Fused zero-shot path: encoder + ADClipTrainer.compute_anomaly_score (clip.py:66-79) -> scores [B]."""
-        imgs = self._prep(imgs)
+        imgs, layout = self._prep(imgs)
         B = imgs.shape[0]
         text = center.detach().to(device=imgs.device, dtype=torch.float32).contiguous()
         scores = out if out is not None else torch.empty(B, dtype=torch.float32, device=imgs.device)
-        lib = L.lib()
         for s in range(0, B, self.max_batch):
             n = min(self.max_batch, B - s)
-            L.check(lib.eoe_vit_encode(self._plan, L.ptr(imgs[s:s + n]), n, None, L.ptr(text), text.shape[0],
-                                       float(scale), L.ptr(scores[s:s + n]), L.stream_ptr(imgs.device)),
-                    "eoe_vit_encode")
+            self._encode(imgs[s:s + n], layout, n, None, text, text.shape[0], scale, scores[s:s + n])
         return scores
 
 

@@ -205,6 +205,15 @@ void eoe_vit_plan_destroy(eoe_vit_plan* plan);
 int eoe_vit_encode(eoe_vit_plan* plan, const float* imgs, int64_t B, float* feats_out,
                    const float* text, int64_t K, float scale, float* scores_out, void* stream);
 
+/* Same forward pass from RAW uint8 pixels: torchvision's ToTensor (u8/255) and Normalize ((x-mean)/std), i.e. the tail of
+ * CLIP's `_transform` (clip_official/clip/clip.py:58-65) and eoe's GPU Normalize (utils/transformations.py:126-138), are
+ * fused into the patchify kernel -- bit-identical to normalising first and calling eoe_vit_encode, at a quarter of the
+ * input bytes.  layout: EOE_LAYOUT_NCHW imgs [B,3,R,R] | EOE_LAYOUT_NHWC imgs [B,R,R,3]; mean/std: HOST float[3]. */
+enum { EOE_LAYOUT_NCHW = 0, EOE_LAYOUT_NHWC = 1 };
+int eoe_vit_encode_u8(eoe_vit_plan* plan, const uint8_t* imgs, int layout, const float* mean_host,
+                      const float* std_host, int64_t B, float* feats_out, const float* text, int64_t K,
+                      float scale, float* scores_out, void* stream);
+
 /* Optional instrumentation for roofline reporting: while enabled, eoe_vit_encode brackets every GEMM launch with a
  * CUDA event pair on `stream` (no synchronisation). eoe_vit_profile_read waits for the recorded events and returns,
  * per GEMM kind (0 patch-embed, 1 qkv, 2 out-proj, 3 c_fc, 4 c_proj), accumulated milliseconds, launches and
@@ -219,6 +228,10 @@ int eoe_vit_profile_read(eoe_vit_plan* plan, double* ms_out_host, int64_t* launc
 int eoe_vit_fold_layernorm(const float* w_f32, const float* ln_w, const float* ln_b, const float* bias,
                            int64_t N, int64_t K, int operand_dtype, void* w_folded_out, float* c1_out,
                            float* c2_out, void* stream);
+
+/* Diagnostics for tools/gemm_probe.py (NOT part of the stable ABI; 0 in production): bit 0 GEMM epilogues only release
+ * their accumulators, bit 1 no global stores, bit 2 L2 prefetch of the next A tile, bits 8.. grid size in CTA pairs. */
+void eoe_debug_set(int flags);
 
 /* Building blocks of the encoder, exported so that each kernel is parity-tested through the ABI. */
 enum { EOE_EPI_BIAS = 0, EOE_EPI_BIAS_QUICKGELU = 1, EOE_EPI_BIAS_RESIDUAL_F32 = 2, EOE_EPI_PATCH_EMBED = 3,

@@ -197,3 +197,26 @@ def test_encoder_batching_and_fused_score(tower):
     assert torch.equal(s_fused, s_two)
     want = oh.clip_score(f1.cpu().numpy(), text.cpu().numpy())
     np.testing.assert_allclose(s_fused.cpu().numpy(), want, rtol=1e-3, atol=1e-30)   # head: 1e-3 given identical features
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_encoder_uint8_input_is_bit_identical_to_host_normalisation(tower, layout, dtype):
+    """ToTensor + Normalize (clip_official/clip/clip.py:58-65) fused into the patchify kernel: identical features,
+    bit for bit, to torchvision-style normalisation on the host followed by the fp32-input path."""
+    from eoe_b200.encoder import ClipImageEncoder
+    patch, sd = tower
+    g = torch.Generator().manual_seed(99)
+    u8 = torch.randint(0, 256, (3, 3, 224, 224), generator=g, dtype=torch.uint8)
+    u8[0, :, :4, :4] = 0
+    u8[0, :, 4:8, :4] = 255
+    mean = torch.tensor((0.48145466, 0.4578275, 0.40821073)).view(1, 3, 1, 1)
+    std = torch.tensor((0.26862954, 0.26130258, 0.27577711)).view(1, 3, 1, 1)
+    normed = (u8.float().div(255).sub(mean)).div(std)               # ToTensor, then Normalize's sub_().div_()
+    enc = ClipImageEncoder(sd, device=DEV, operand_dtype=dtype, max_batch=2)
+    want = enc(normed.to(DEV))
+    inp = u8 if layout == "nchw" else u8.permute(0, 2, 3, 1).contiguous()
+    got = enc(inp.to(DEV))
+    assert torch.equal(got, want)
+    text = torch.nn.functional.normalize(torch.randn(5, 512, generator=g), dim=-1).to(DEV)
+    assert torch.equal(enc.score(inp.to(DEV), text), enc.score(normed.to(DEV), text))
