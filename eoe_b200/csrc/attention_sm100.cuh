@@ -3,13 +3,14 @@
 //
 // One CTA of 128 threads per (image, head) item, persistent over items, 2 CTAs per SM (their TMA / MMA / softmax phases
 // interleave).  Per item: TMA brings the head's Q (2 tiles of 128 query rows), K and V slices ([rows][64] bf16, 128-byte
-// rows, SWIZZLE_128B) straight out of the qkv GEMM output.  Per query tile:
+// rows, SWIZZLE_128B) straight out of the qkv GEMM output through a 3-D [image][token][column] map (tokens past the image
+// are zero-filled for free).  Per query tile:
 //   S[128 x 208] = Q K^T        tcgen05.mma, both operands K-major from smem, fp32 in TMEM columns [0, 208)
 //   softmax                      thread t owns TMEM lane t = query row t: row max and exp2 need no cross-thread traffic;
 //                                un-normalised P is written back to TMEM as packed 16-bit pairs over columns [0, 104)
 //   O[128 x 64] = P V           tcgen05.mma with A = P from TMEM and B = V as an MN-major smem operand (no transpose),
 //                                fp32 in TMEM columns [128, 192)
-//   epilogue                     O * (1 / row sum) -> 16-bit -> global
+//   epilogue                     O * (1 / row sum) -> 16-bit -> staged in the dead Q tile -> one TMA tile store (clipped at L)
 // L = 197 rows do not fill two 128-lane tiles; the second tile alternates between rows [128, 256) and rows [69, 197)
 // from item to item so that the valid rows load all four TMEM lane quarters (= the four SM sub-partitions whose MUFU
 // units do the exp2 work) evenly.
@@ -33,12 +34,103 @@ __device__ __forceinline__ float fast_exp2(float x) {      // x <= 0 here; MUFU.
     return y;
 }
 
+
+// Softmax of one query row held in TMEM lane `t_lane` (S in fp32 over columns [0, LP)): un-normalised P is written back
+// over columns [0, LP/2) as packed 16-bit pairs, the fp32 row sum's reciprocal is returned.
+//
+// TMEM reads are the attention kernel's bottleneck (64 B/clk/SM: two passes over S cost 3 us per (image, head)), so
+// with bf16 probabilities S is read ONCE: the exponent reference is the maximum of the first 32 keys (held in
+// registers) plus 32 instead of the row maximum.  softmax is invariant to the reference; bf16 / fp32 keep full relative
+// precision at any magnitude; a key may exceed the reference by 2^142 before the (NaN-preserving) clamp at 2^110
+// engages, i.e. scores more than ~100 above the first 32 keys' maximum -- far beyond what the reference's own fp16
+// GPU path can represent.  fp16 probabilities (max 65504) keep the exact two-pass form.
+template <bool BF16, int L>
+__device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
+    constexpr int LP = (L + 15) / 16 * 16;
+    constexpr int NC = LP / 32;                 // full 32-column chunks; LP % 32 == 16 leaves one half chunk
+    static_assert(LP % 32 == 0 || LP % 32 == 16, "chunking");
+    static_assert(L >= 32, "first chunk fully valid");
+    uint32_t r[2][32];
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    float ms;
+    if (BF16) {
+        ptx::tmem_ld_32x32b_x32(t_lane, r[0]);
+        ptx::tmem_ld_wait();
+        if (NC > 1) ptx::tmem_ld_32x32b_x32(t_lane + 32, r[1]);
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[0][j]));
+        ms = fmaf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), sl2, 32.0f);
+    } else {
+        // pass 1: exact row maximum (TMEM loads software pipelined, four independent accumulators)
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        ptx::tmem_ld_32x32b_x32(t_lane, r[0]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            ptx::tmem_ld_wait();
+            if (c + 1 < NC) ptx::tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, r[(c + 1) & 1]);
+            else if (LP % 32) ptx::tmem_ld_32x32b_x16(t_lane + NC * 32, reinterpret_cast<uint32_t(&)[16]>(r[(c + 1) & 1]));
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c * 32 + j < L) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[c & 1][j]));
+        }
+        if (LP % 32) {
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (NC * 32 + j < L) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[NC & 1][j]));
+        }
+        ms = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sl2;
+        ptx::tmem_ld_32x32b_x32(t_lane, r[0]);
+    }
+    // p = exp2(s / 8 * log2 e - ms), fp32 row sum, P -> TMEM as packed 16-bit pairs
+    auto prob = [&](uint32_t bits) {
+        float e = fmaf(__uint_as_float(bits), sl2, -ms);
+        if (BF16) e = e > 110.0f ? 110.0f : e;          // NaN stays NaN (fminf would drop it)
+        return fast_exp2(e);
+    };
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        uint32_t pk[16];
+        if (!(BF16 && c == 0)) {                        // bf16: chunk 0 is already in registers, chunk 1 in flight
+            ptx::tmem_ld_wait();
+            if (c + 1 < NC) ptx::tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, r[(c + 1) & 1]);
+            else if (LP % 32) ptx::tmem_ld_32x32b_x16(t_lane + NC * 32, reinterpret_cast<uint32_t(&)[16]>(r[(c + 1) & 1]));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const float p0 = (c * 32 + j < L) ? prob(r[c & 1][j]) : 0.f;
+            const float p1 = (c * 32 + j + 1 < L) ? prob(r[c & 1][j + 1]) : 0.f;
+            s4[(j >> 1) & 3] += p0 + p1;
+            pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
+        }
+        // columns [16c, 16c+16) hold scores consumed in rounds <= c; the in-flight load of round c+1 reads
+        // columns >= 32(c+1) > 16c+16, so the store cannot clobber unread scores
+        ptx::tmem_st_32x32b_x16(t_lane + c * 16, pk);
+    }
+    if (LP % 32) {
+        uint32_t pk[8];
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const float p0 = (NC * 32 + j < L) ? prob(r[NC & 1][j]) : 0.f;
+            const float p1 = (NC * 32 + j + 1 < L) ? prob(r[NC & 1][j + 1]) : 0.f;
+            s4[(j >> 1) & 3] += p0 + p1;
+            pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
+        }
+        ptx::tmem_st_32x32b_x8(t_lane + NC * 16, pk);
+    }
+    ptx::tmem_st_wait();
+    return 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+}
+
 template <bool BF16, int L>
 __global__ void __launch_bounds__(THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __restrict__ out, int num_items, int heads) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out128,
+                    const __grid_constant__ CUtensorMap tm_out72, int num_items, int heads) {
     constexpr int LP = (L + 15) / 16 * 16;          // keys padded to the UMMA N granularity (208)
     constexpr int KSTEPS = LP / 16;                  // k-steps of the P*V product
-    static_assert(L > 128 && L <= 208, "two 128-row query tiles");
+    static_assert(L >= 193 && L <= 200, "two 128-row query tiles; the second tile's 72-row store window [L-72, L) must be covered by active warps");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;                         // [2][128][128 B]
@@ -76,25 +168,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __rest
         const int b = item / heads, h = item % heads;
         const int t1_start = (it & 1) ? (L - 128) : 128;              // first query row of the second tile
         if (tid == 0) {
+            ptx::bulk_wait_group_read0();        // the previous item's output tiles (staged in the Q buffers) have left
             const uint32_t lb = ptx::smem_u32(bar_load);
             ptx::mbar_arrive_expect_tx(lb, 6 * TILE_BYTES);
-            const int r0 = b * L;
-            ptx::tma_load_2d(ptx::smem_u32(sQ), &tm_qkv, lb, h * 64, r0);
-            ptx::tma_load_2d(ptx::smem_u32(sQ + TILE_BYTES), &tm_qkv, lb, h * 64, r0 + t1_start);
-            ptx::tma_load_2d(ptx::smem_u32(sK), &tm_qkv, lb, width + h * 64, r0);
-            ptx::tma_load_2d(ptx::smem_u32(sK + TILE_BYTES), &tm_qkv, lb, width + h * 64, r0 + 128);
-            ptx::tma_load_2d(ptx::smem_u32(sV), &tm_qkv, lb, 2 * width + h * 64, r0);
-            ptx::tma_load_2d(ptx::smem_u32(sV + TILE_BYTES), &tm_qkv, lb, 2 * width + h * 64, r0 + 128);
+            // 3-D map [image][token][3*width]: tokens >= L of a box are zero-filled without touching memory, so K / V rows
+            // L..255 cost no traffic and meet P == 0 with finite values
+            ptx::tma_load_3d(ptx::smem_u32(sQ), &tm_qkv, lb, h * 64, 0, b);
+            ptx::tma_load_3d(ptx::smem_u32(sQ + TILE_BYTES), &tm_qkv, lb, h * 64, t1_start, b);
+            ptx::tma_load_3d(ptx::smem_u32(sK), &tm_qkv, lb, width + h * 64, 0, b);
+            ptx::tma_load_3d(ptx::smem_u32(sK + TILE_BYTES), &tm_qkv, lb, width + h * 64, 128, b);
+            ptx::tma_load_3d(ptx::smem_u32(sV), &tm_qkv, lb, 2 * width + h * 64, 0, b);
+            ptx::tma_load_3d(ptx::smem_u32(sV + TILE_BYTES), &tm_qkv, lb, 2 * width + h * 64, 128, b);
         }
         ptx::mbar_wait(ptx::smem_u32(bar_load), load_phase);
         load_phase ^= 1;
-        // rows L..LP-1 of V belong to the next image (or to slack): they meet P == 0, but 0 * NaN would poison O
-        if (tid < (LP - L) * 8) {
-            const int r = L + (tid >> 3), c = tid & 7;
-            asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(ptx::smem_u32(sV + r * 128 + ((c ^ (r & 7)) << 4))), "r"(0u) : "memory");
-        }
-        ptx::fence_proxy_async_smem();
-
 #pragma unroll 1
         for (int tile = 0; tile < 2; ++tile) {
             if (tid == 0) {
@@ -106,8 +193,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __rest
                 ptx::umma_commit(ptx::smem_u32(bar_mma));
             }
             // query row owned by this thread, and whether its warp has any row to compute
-            const int qrow = (tile == 0 ? 0 : t1_start) + tid;
-            const bool own = (tile == 0) ? true : (qrow >= 128 && qrow < L);
             const int wfirst = (tile == 0 ? 0 : t1_start) + warp * 32;
             const bool warp_active = (tile == 0) ? true : (wfirst + 31 >= 128 && wfirst < L);
             ptx::mbar_wait(ptx::smem_u32(bar_mma), mma_phase);
@@ -115,64 +200,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __rest
             ptx::tc_fence_after();
             float inv_sum = 0.f;
             if (warp_active) {
-                constexpr int NC = LP / 32;                 // full 32-column chunks; LP % 32 == 16 leaves one half chunk
-                static_assert(LP % 32 == 0 || LP % 32 == 16, "chunking");
-                // pass 1: row maximum over the L valid keys.  TMEM loads are software pipelined (chunk c+1 is in
-                // flight while chunk c is reduced) and four independent accumulators break the FMNMX dependency chain.
-                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                uint32_t r[2][32];
-                ptx::tmem_ld_32x32b_x32(t_lane, r[0]);
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    ptx::tmem_ld_wait();
-                    if (c + 1 < NC) ptx::tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, r[(c + 1) & 1]);
-                    else if (LP % 32) ptx::tmem_ld_32x32b_x16(t_lane + NC * 32, reinterpret_cast<uint32_t(&)[16]>(r[(c + 1) & 1]));
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c * 32 + j < L) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[c & 1][j]));
-                }
-                if (LP % 32) {
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (NC * 32 + j < L) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[NC & 1][j]));
-                }
-                const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                // pass 2: p = exp2((s - m) / 8 * log2 e), fp32 row sum, P -> TMEM as packed 16-bit pairs
-                const float ms = m * sl2;
-                float s4[4] = {0.f, 0.f, 0.f, 0.f};
-                ptx::tmem_ld_32x32b_x32(t_lane, r[0]);
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    uint32_t pk[16];
-                    ptx::tmem_ld_wait();
-                    if (c + 1 < NC) ptx::tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, r[(c + 1) & 1]);
-                    else if (LP % 32) ptx::tmem_ld_32x32b_x16(t_lane + NC * 32, reinterpret_cast<uint32_t(&)[16]>(r[(c + 1) & 1]));
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float p0 = (c * 32 + j < L) ? fast_exp2(fmaf(__uint_as_float(r[c & 1][j]), sl2, -ms)) : 0.f;
-                        const float p1 = (c * 32 + j + 1 < L) ? fast_exp2(fmaf(__uint_as_float(r[c & 1][j + 1]), sl2, -ms)) : 0.f;
-                        s4[(j >> 1) & 3] += p0 + p1;
-                        pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
-                    }
-                    // columns [16c, 16c+16) hold scores consumed in rounds <= c; the in-flight load of round c+1 reads
-                    // columns >= 32(c+1) > 16c+16, so the store cannot clobber unread scores
-                    ptx::tmem_st_32x32b_x16(t_lane + c * 16, pk);
-                }
-                if (LP % 32) {
-                    uint32_t pk[8];
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        const float p0 = (NC * 32 + j < L) ? fast_exp2(fmaf(__uint_as_float(r[NC & 1][j]), sl2, -ms)) : 0.f;
-                        const float p1 = (NC * 32 + j + 1 < L) ? fast_exp2(fmaf(__uint_as_float(r[NC & 1][j + 1]), sl2, -ms)) : 0.f;
-                        s4[(j >> 1) & 3] += p0 + p1;
-                        pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
-                    }
-                    ptx::tmem_st_32x32b_x8(t_lane + NC * 16, pk);
-                }
-                ptx::tmem_st_wait();
-                inv_sum = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+                inv_sum = softmax_row_tmem<BF16, L>(t_lane, sl2);
             }
             ptx::tc_fence_before();
             __syncthreads();                       // P of all rows is in TMEM (and the V tail is zeroed)
@@ -187,37 +215,49 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, uint16_t* __rest
             ptx::mbar_wait(ptx::smem_u32(bar_mma), mma_phase);
             mma_phase ^= 1;
             ptx::tc_fence_after();
+            // Epilogue: O * (1 / row sum) -> 16 bit, staged row-major in the (now dead) Q tile with the 128-byte swizzle
+            // and written by ONE TMA tile store: full 128-byte lines instead of 32 half-sector writes per instruction.
+            // The output map is 3-D [image][token][width], so rows past the image's last token are clipped by the TMA unit.
+            uint8_t* stg = sQ + tile * TILE_BYTES;
             if (warp_active) {
                 uint32_t o0[32], o1[32];
                 ptx::tmem_ld_32x32b_x32(t_lane + O_COL, o0);
                 ptx::tmem_ld_32x32b_x32(t_lane + O_COL + 32, o1);
                 ptx::tmem_ld_wait();
-                if (own) {
-                    uint16_t* dst = out + ((int64_t)b * L + qrow) * width + h * 64;
+                const uint32_t srow = ptx::smem_u32(stg + tid * 128);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 q;
-                        q.x = gemm::pack2<BF16>(__uint_as_float(o0[j]) * inv_sum, __uint_as_float(o0[j + 1]) * inv_sum);
-                        q.y = gemm::pack2<BF16>(__uint_as_float(o0[j + 2]) * inv_sum, __uint_as_float(o0[j + 3]) * inv_sum);
-                        q.z = gemm::pack2<BF16>(__uint_as_float(o0[j + 4]) * inv_sum, __uint_as_float(o0[j + 5]) * inv_sum);
-                        q.w = gemm::pack2<BF16>(__uint_as_float(o0[j + 6]) * inv_sum, __uint_as_float(o0[j + 7]) * inv_sum);
-                        *reinterpret_cast<uint4*>(dst + j) = q;
-                    }
+                for (int j = 0; j < 32; j += 8) {
+                    const uint32_t q0 = gemm::pack2<BF16>(__uint_as_float(o0[j]) * inv_sum, __uint_as_float(o0[j + 1]) * inv_sum);
+                    const uint32_t q1 = gemm::pack2<BF16>(__uint_as_float(o0[j + 2]) * inv_sum, __uint_as_float(o0[j + 3]) * inv_sum);
+                    const uint32_t q2 = gemm::pack2<BF16>(__uint_as_float(o0[j + 4]) * inv_sum, __uint_as_float(o0[j + 5]) * inv_sum);
+                    const uint32_t q3 = gemm::pack2<BF16>(__uint_as_float(o0[j + 6]) * inv_sum, __uint_as_float(o0[j + 7]) * inv_sum);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((((j >> 3)) ^ (tid & 7)) << 4)), "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
+                }
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 q;
-                        q.x = gemm::pack2<BF16>(__uint_as_float(o1[j]) * inv_sum, __uint_as_float(o1[j + 1]) * inv_sum);
-                        q.y = gemm::pack2<BF16>(__uint_as_float(o1[j + 2]) * inv_sum, __uint_as_float(o1[j + 3]) * inv_sum);
-                        q.z = gemm::pack2<BF16>(__uint_as_float(o1[j + 4]) * inv_sum, __uint_as_float(o1[j + 5]) * inv_sum);
-                        q.w = gemm::pack2<BF16>(__uint_as_float(o1[j + 6]) * inv_sum, __uint_as_float(o1[j + 7]) * inv_sum);
-                        *reinterpret_cast<uint4*>(dst + 32 + j) = q;
-                    }
+                for (int j = 0; j < 32; j += 8) {
+                    const uint32_t q0 = gemm::pack2<BF16>(__uint_as_float(o1[j]) * inv_sum, __uint_as_float(o1[j + 1]) * inv_sum);
+                    const uint32_t q1 = gemm::pack2<BF16>(__uint_as_float(o1[j + 2]) * inv_sum, __uint_as_float(o1[j + 3]) * inv_sum);
+                    const uint32_t q2 = gemm::pack2<BF16>(__uint_as_float(o1[j + 4]) * inv_sum, __uint_as_float(o1[j + 5]) * inv_sum);
+                    const uint32_t q3 = gemm::pack2<BF16>(__uint_as_float(o1[j + 6]) * inv_sum, __uint_as_float(o1[j + 7]) * inv_sum);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + (((4 + (j >> 3)) ^ (tid & 7)) << 4)), "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
                 }
             }
+            ptx::fence_proxy_async_smem();
             ptx::tc_fence_before();
-            __syncthreads();                       // O has been read: TMEM and (after tile 1) the smem tiles are free
+            __syncthreads();                       // O has been read and staged: TMEM is free
+            if (tid == 0) {
+                if (tile == 0) {
+                    ptx::tma_store_3d(&tm_out128, ptx::smem_u32(stg), h * 64, 0, b);
+                } else if (t1_start == 128) {      // rows [128, 200): rows >= L are clipped
+                    ptx::tma_store_3d(&tm_out72, ptx::smem_u32(stg), h * 64, 128, b);
+                } else {                           // tile rows [L-128, L): store from staging row 56 = token L-72 (8-row aligned),
+                    ptx::tma_store_3d(&tm_out72, ptx::smem_u32(stg + 56 * 128), h * 64, L - 72, b);   // tokens < 128 repeat tile 0's values
+                }
+                ptx::bulk_commit_group();
+            }
         }
     }
+    if (tid == 0) ptx::bulk_wait_group_read0();
     if (warp == 0) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<1>(tmem, TMEM_COLS);

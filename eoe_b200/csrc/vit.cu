@@ -54,6 +54,25 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t K, 
     return EOE_OK;
 }
 
+// out [B, L, width] 16-bit as a 3-D map (width, token, image): a box of `box_rows` tokens x 64 columns that runs past the
+// image's last token is clipped by the TMA unit (stores) / zero-filled (loads)
+static int make_tmap_tokens(CUtensorMap* m, const void* base, int64_t B, int64_t L, int64_t width, int box_rows, int dtype) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return EOE_ERR_CUDA;
+    cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)L, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)L * width * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, dtype == EOE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(3d)");
+        return EOE_ERR_CUDA;
+    }
+    return EOE_OK;
+}
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -542,7 +561,16 @@ static int attention_launch_t(const void* qkv, void* out, int64_t B, int L, int 
 
 // tcgen05 path (L == 197): qkv is read through a TMA descriptor with 128-row x 64-column boxes
 template <bool BF16>
-static int attention_tc_launch(const CUtensorMap& tm_qkv, void* out, int64_t B, int heads, cudaStream_t st) {
+static int attention_tc_launch(const CUtensorMap& tm_qkv, void* out, int64_t B, int heads, int dtype, cudaStream_t st,
+                               const CUtensorMap* tm_o128 = nullptr, const CUtensorMap* tm_o72 = nullptr) {
+    CUtensorMap l128, l72;
+    if (!tm_o128) {
+        int rc = make_tmap_tokens(&l128, out, B, 197, heads * 64, 128, dtype);
+        if (!rc) rc = make_tmap_tokens(&l72, out, B, 197, heads * 64, 72, dtype);
+        if (rc) return rc;
+        tm_o128 = &l128;
+        tm_o72 = &l72;
+    }
     auto kern = attn::attention_tc_kernel<BF16, 197>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -552,23 +580,25 @@ static int attention_tc_launch(const CUtensorMap& tm_qkv, void* out, int64_t B, 
     }
     const int64_t items = B * heads;
     const int grid = (int)(items < 2 * (int64_t)num_sms() ? items : 2 * (int64_t)num_sms());
-    kern<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tm_qkv, (uint16_t*)out, (int)items, heads);
+    kern<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tm_qkv, *tm_o128, *tm_o72, (int)items, heads);
     return check_launch("attention_tc_kernel");
 }
 
 static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int dtype, cudaStream_t st,
-                              const CUtensorMap* tm_qkv = nullptr) {
+                              const CUtensorMap* tm_qkv = nullptr, const CUtensorMap* tm_o128 = nullptr,
+                              const CUtensorMap* tm_o72 = nullptr) {
     if (dtype != EOE_BF16 && dtype != EOE_F16) return EOE_ERR_DTYPE;
     if (B <= 0 || L <= 0 || heads <= 0 || B * heads > 0x7fffffff) return EOE_ERR_ARG;
     const bool bf = dtype == EOE_BF16;
     if (L == 197) {
         CUtensorMap local;
         if (!tm_qkv) {
-            int rc = make_tmap(&local, qkv, B * L, 3 * heads * 64, 128, dtype);
+            int rc = make_tmap_tokens(&local, qkv, B, L, 3 * heads * 64, 128, dtype);
             if (rc) return rc;
             tm_qkv = &local;
         }
-        return bf ? attention_tc_launch<true>(*tm_qkv, out, B, (int)heads, st) : attention_tc_launch<false>(*tm_qkv, out, B, (int)heads, st);
+        return bf ? attention_tc_launch<true>(*tm_qkv, out, B, (int)heads, dtype, st, tm_o128, tm_o72)
+                  : attention_tc_launch<false>(*tm_qkv, out, B, (int)heads, dtype, st, tm_o128, tm_o72);
     }
     if (L <= 64) return bf ? attention_launch_t<true, 64>(qkv, out, B, (int)L, (int)heads, st) : attention_launch_t<false, 64>(qkv, out, B, (int)L, (int)heads, st);
     if (L <= 208) return bf ? attention_launch_t<true, 208>(qkv, out, B, (int)L, (int)heads, st) : attention_launch_t<false, 208>(qkv, out, B, (int)L, (int)heads, st);
@@ -758,7 +788,7 @@ struct eoe_vit_plan {
     uint16_t* xb;        // [B*L, width] 16-bit copy of the residual stream (LayerNorm-folded path)
     float2* stats;       // [B*L, width/128] per-row chunk (sum, sum of squares) of the residual stream
     bool fused_ln;       // every layer carries folded in_proj / c_fc weights: no stand-alone ln_1 / ln_2 launches
-    CUtensorMap tm_patches, tm_h, tm_u, tm_conv, tm_qkv, tm_hc, tm_uc, tm_xb;
+    CUtensorMap tm_patches, tm_h, tm_u, tm_conv, tm_qkv, tm_hc, tm_uc, tm_xb, tm_ho128, tm_ho72;
     CUtensorMap *tm_in, *tm_out, *tm_fc, *tm_proj;     // per layer
     CUtensorMap *tm_inf, *tm_fcf;                      // per layer, LayerNorm-folded weights
     // optional instrumentation (eoe_vit_profile_*): CUDA event pairs around every GEMM launch
@@ -894,7 +924,9 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     if (!rc) rc = make_tmap(&p->tm_h, p->h, rows, W, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_u, p->u, rows, 4 * W, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_conv, w->conv1_w, W, p->kpatch, gemm::CTA_NB, dt);
-    if (!rc) rc = make_tmap(&p->tm_qkv, p->qkv, rows + 256, 3 * W, 128, dt);
+    if (!rc) rc = make_tmap_tokens(&p->tm_qkv, p->qkv, max_batch, p->L, 3 * W, 128, dt);
+    if (!rc && p->L == 197) rc = make_tmap_tokens(&p->tm_ho128, p->h, max_batch, p->L, W, 128, dt);
+    if (!rc && p->L == 197) rc = make_tmap_tokens(&p->tm_ho72, p->h, max_batch, p->L, W, 72, dt);
     if (!rc) rc = make_tmap(&p->tm_hc, p->h_cls, max_batch, W, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_uc, p->u_cls, max_batch, 4 * W, gemm::CTA_M, dt);
     for (int i = 0; i < w->n_layers && !rc; ++i) {
@@ -986,7 +1018,7 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
             if ((rc = timed_gemm(p, KIND_QKV, p->tm_xb, p->tm_inf[i], g1, dt, EOE_EPI_LNFOLD_BIAS, st))) return rc;
         }
         if (!last) {
-            if ((rc = attention_dispatch(p->qkv, p->h, B, L, w.heads, dt, st, &p->tm_qkv))) return rc;
+            if ((rc = attention_dispatch(p->qkv, p->h, B, L, w.heads, dt, st, &p->tm_qkv, &p->tm_ho128, &p->tm_ho72))) return rc;
             gemm::Params g2{M, W, W, l.out_proj_b, p->x, nullptr, 0, nullptr, p->stats, p->xb};
             if ((rc = timed_gemm(p, KIND_OUT, p->tm_h, p->tm_out[i], g2, dt, epi_res, st))) return rc;
             if (!p->fused_ln) {
@@ -1098,6 +1130,7 @@ extern "C" int eoe_gemm(const void* A, const void* Wt, const float* bias, void* 
 }
 
 extern "C" void eoe_debug_set(int flags) { g_gemm_debug = flags; }
+
 
 extern "C" int eoe_gemm_lnfold(const void* A, const void* Wf, const float* c1, const float* c2, const float* stats,
                                void* out, int64_t M, int64_t N, int64_t K, int operand_dtype, int quick_gelu,
