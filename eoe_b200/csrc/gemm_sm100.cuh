@@ -74,9 +74,7 @@ struct Params {
     const float2* stats_in; // LNFOLD_*: [M, K/128] per-row (sum, sum of squares) of the fp32 residual stream per chunk
     float2* stats_out;      // RESIDUAL_STATS: [M, N/128]
     uint16_t* xb_out;       // RESIDUAL_STATS: [M, N] operand-dtype copy of the updated residual stream
-    const void* dbg_a;      // diagnostics: base of A (for dbg & 4)
-    int dbg;                // diagnostics (eoe_debug_set): 1 epilogue only releases accumulators, 2 no global stores,
-                            // 4 warp 3 prefetches the next tile's A rows into L2
+    int dbg;                // diagnostics (eoe_debug_set): 1 epilogue only releases accumulators, 2 no global stores
 };
 
 template <bool BF16>
@@ -111,8 +109,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int EPI, bool BF16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+// CLP = CTA pairs per cluster (cluster of 2*CLP CTAs, set at launch).  With CLP = 2 the two pairs of a cluster work on
+// vertically adjacent tiles (same n block, m blocks 2i and 2i+1) and share the W tile: each half of it is fetched from L2
+// ONCE and multicast into both pairs' shared memory, which cuts the operand traffic per flop by a quarter -- the main
+// loop is bound by L2 -> SM bandwidth (12.6 TB/s at 1.6 PFLOP/s with 256 x 256 tiles).
+template <int EPI, bool BF16, int CLP>
+__global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
     using C = Cfg<EPI>;
     constexpr int STAGES = C::kStages;
@@ -134,13 +136,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
     const int warp = __shfl_sync(kFullMask, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
-    const uint32_t cta_rank = ptx::cluster_ctarank();
+    const uint32_t cluster_rank = ptx::cluster_ctarank();          // 0 .. 2*CLP-1
+    const uint32_t cta_rank = cluster_rank & 1;                     // rank inside the CTA pair
+    const int cpair = (int)(cluster_rank >> 1);                     // which pair of the cluster
+    const uint32_t leader_rank = cluster_rank & ~1u;                // cluster rank of this pair's leader CTA
     const bool leader = cta_rank == 0;
-    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    // work unit = CLP vertically adjacent tiles; `pair` / `num_pairs` count clusters, a unit's tile of this pair is
+    // (m block = unit / num_n * CLP + cpair, n block = unit % num_n).  A phantom m block past the matrix (odd block count)
+    // loads zeros and stores nothing.
+    const int pair = blockIdx.x / (2 * CLP), num_pairs = gridDim.x / (2 * CLP);
     const int num_n = (int)(p.N / BN);
     const int num_m = (int)((p.M + BM - 1) / BM);
-    const int num_tiles = num_m * num_n;
+    const int num_tiles = ((num_m + CLP - 1) / CLP) * num_n;
     const int num_k = (int)(p.K / BK);
+    auto m_block = [&](int unit) { return (unit / num_n) * CLP + cpair; };
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tma_a);
@@ -149,7 +158,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(ptx::smem_u32(&full[s]), 1);          // the leader's producer arrive.expect_tx
-            ptx::mbar_init(ptx::smem_u32(&empty[s]), 1);         // one tcgen05.commit arrival
+            ptx::mbar_init(ptx::smem_u32(&empty[s]), CLP);       // one tcgen05.commit arrival per pair of the cluster
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(ptx::smem_u32(&tmem_full[s]), 1);
@@ -173,15 +182,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-                const int m_blk = tile / num_n, n_blk = tile % num_n;
+                const int m_blk = m_block(tile), n_blk = tile % num_n;
                 const int a_row = m_blk * BM + (int)cta_rank * CTA_M;
                 const int b_row = n_blk * BN + (int)cta_rank * CTA_NB;
                 for (int kb = 0; kb < num_k; ++kb) {
-                    ptx::mbar_wait(ptx::smem_u32(&empty[stage]), phase ^ 1);
-                    const uint32_t fb_leader = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
+                    ptx::mbar_wait(ptx::smem_u32(&empty[stage]), phase ^ 1);   // released by EVERY pair of the cluster
+                    const uint32_t fb_leader = ptx::mapa(ptx::smem_u32(&full[stage]), leader_rank);
                     if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full[stage]), 2 * STAGE_BYTES);
                     ptx::tma_load_2d_cg2(ptx::smem_u32(smem_a + stage * A_BYTES), &tma_a, fb_leader, kb * BK, a_row);
-                    ptx::tma_load_2d_cg2(ptx::smem_u32(smem_b + stage * B_BYTES), &tma_b, fb_leader, kb * BK, b_row);
+                    if (CLP == 1) {
+                        ptx::tma_load_2d_cg2(ptx::smem_u32(smem_b + stage * B_BYTES), &tma_b, fb_leader, kb * BK, b_row);
+                    } else if (cpair == 0) {
+                        // W half `cta_rank` goes to the CTAs of that rank in both pairs; each copy signals the `full`
+                        // barrier of ITS pair's leader (cta_group::2: the barrier operand names the even CTA of the pair)
+                        const uint32_t fb_even = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
+                        ptx::tma_load_2d_cg2_mc(ptx::smem_u32(smem_b + stage * B_BYTES), &tma_b, fb_even, kb * BK, b_row,
+                                                (uint16_t)(0x5u << cta_rank));
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -208,27 +225,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 field
                         ptx::umma_f16<2>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit_cg2(ptx::smem_u32(&empty[stage]), 3);      // frees the stage in both CTAs
+                    ptx::umma_commit_cg2(ptx::smem_u32(&empty[stage]), (uint16_t)((1u << (2 * CLP)) - 1));   // every CTA of the cluster
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit_cg2(ptx::smem_u32(&tmem_full[acc]), 3);        // accumulator complete -> both epilogues
+                ptx::umma_commit_cg2(ptx::smem_u32(&tmem_full[acc]), (uint16_t)(3u << (2 * cpair)));   // accumulator complete -> both epilogues of the pair
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp == 3) {
-        if ((p.dbg & 4) && p.dbg_a) {
-            // experiment: pull the A rows of the pair's NEXT tile into L2 while the current tile is being computed
-            const uint8_t* a_base = reinterpret_cast<const uint8_t*>(p.dbg_a);
-            for (int tile = pair + num_pairs; tile < num_tiles; tile += num_pairs) {
-                const int m_blk = tile / num_n;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t row = (int64_t)m_blk * BM + (int64_t)cta_rank * CTA_M + i * 32 + lane;
-                    if (row < p.M) ptx::prefetch_l2_bulk(a_base + row * p.K * 2, (uint32_t)(p.K * 2));
-                }
-                __nanosleep(3000);
-            }
-        }
         if (kStatsAsync) {
             // ------------------------------------------------------------------ residual prefetcher
             // The epilogue streams the fp32 residual rows of its tile into shared memory with cp.async two rounds ahead;
@@ -242,7 +246,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     __nanosleep(200);
                     if (clock64() - t0 > 4000000000LL) __trap();
                 }
-                const int m_blk = tile / num_n, n_blk = tile % num_n;
+                const int m_blk = m_block(tile), n_blk = tile % num_n;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int64_t row = (int64_t)m_blk * BM + (int64_t)cta_rank * CTA_M + i * 32 + lane;
@@ -274,7 +278,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         // LNFOLD: chunk sums of the 32 rows of tile `t` (contiguous; nch is even, so a 16-byte chunk never straddles rows)
         auto prefetch_stats = [&](int t) {
             if (!kLnFold || t >= num_tiles) return;
-            const int64_t r0 = (int64_t)(t / num_n) * BM + (int64_t)cta_rank * CTA_M + wq * 32;
+            const int64_t r0 = (int64_t)m_block(t) * BM + (int64_t)cta_rank * CTA_M + wq * 32;
             const int chunks = 16 * nch;               // 32 rows * nch * 8 B / 16 B
             for (int ch = lane; ch < chunks; ch += 32) {
                 const bool ok = r0 + (ch * 2) / nch < p.M;
@@ -285,7 +289,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         // RESIDUAL_STATS: residual block (32 rows x 32 fp32 columns) of round `c` of tile `t` -> transpose buffer `buf`
         auto prefetch_x = [&](int t, int c, int buf) {
             if (t >= num_tiles) return;
-            const int mb = t / num_n, nbk = t % num_n;
+            const int mb = m_block(t), nbk = t % num_n;
             const int64_t r0 = (int64_t)mb * BM + (int64_t)cta_rank * CTA_M + wq * 32;
             const int64_t col = (int64_t)nbk * BN + half * 128 + c * 32 + grp * 4;
             float* xb = st + buf * (32 * STAGE_LD);
@@ -317,7 +321,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         int tiles_started = 0, pbuf = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs, pbuf ^= 1) {
             if (kStatsAsync && ew == 0 && lane == 0) *epi_progress = ++tiles_started;
-            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            const int m_blk = m_block(tile), n_blk = tile % num_n;
             const int64_t row0 = (int64_t)m_blk * BM + (int64_t)cta_rank * CTA_M + wq * 32;   // first of this warp's 32 rows
             const int64_t nb = (int64_t)n_blk * BN + half * 128;
             const float* sbias = reinterpret_cast<const float*>(pblock + pbuf * C::kColBytes);
@@ -369,7 +373,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (p.dbg & 1) {                           // diagnostics: main loop only
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), 0);
+                if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), leader_rank);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 continue;
             }
@@ -386,7 +390,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     if (c == 1) {                      // all TMEM reads of this tile are done: release the accumulator
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), 0);
+                        if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), leader_rank);
                     }
                     __syncwarp();                      // previous round's readers are done with `st`
                     uint32_t* strow = reinterpret_cast<uint32_t*>(st) + lane * STAGE_LD;
@@ -450,7 +454,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     if (c == 3) {                      // all TMEM reads of this tile are done: release the accumulator
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), 0);
+                        if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), leader_rank);
                     }
                     __syncwarp();
                     const int64_t col = nb + c * 32 + grp * 4;
@@ -518,7 +522,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     if (c == 3) {                      // all TMEM reads of this tile are done: release the accumulator
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), 0);
+                        if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), leader_rank);
                     }
                     __syncwarp();
                     const int64_t col = nb + c * 32 + grp * 4;
@@ -563,7 +567,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     if (c == 3) {
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), 0);
+                        if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), leader_rank);
                     }
                     __syncwarp();
                     float* strow = st + lane * STAGE_LD;

@@ -71,6 +71,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// 2-CTA pairs + multicast: the box lands at the same smem offset in every CTA of `cta_mask`; each copy's completion
+// bytes are signalled on the barrier at `bar_cluster`'s offset in the CTA of ITS pair that has bar_cluster's rank parity
+__device__ __forceinline__ void tma_load_2d_cg2_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
+                                                   uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(m), "r"(bar_cluster), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"

@@ -85,24 +85,64 @@ static int num_sms() {
 }
 
 static int g_gemm_debug = 0;            // eoe_debug_set(): diagnostics only, 0 in production
+static int g_last_max_clusters[2] = {0, 0};
 
-template <int EPI, bool BF16>
-static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p_in, cudaStream_t st) {
-    gemm::Params p = p_in;
-    p.dbg = g_gemm_debug;
-    auto kern = gemm::gemm_kernel<EPI, BF16>;
+template <int EPI, bool BF16, int CLP>
+static int gemm_launch_c(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, cudaStream_t st) {
+    auto kern = gemm::gemm_kernel<EPI, BF16, CLP>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::Cfg<EPI>::kSmemBytes);
         if (e != cudaSuccess) { set_cuda_error(e, "gemm smem attr"); return EOE_ERR_CUDA; }
         attr_done = true;
     }
-    const int64_t tiles = ((p.M + gemm::BM - 1) / gemm::BM) * (p.N / gemm::BN);
-    int64_t pairs = num_sms() / 2;                                    // one CTA pair (cluster of 2) per tile at a time
-    if (g_gemm_debug >> 8) pairs = g_gemm_debug >> 8;                 // diagnostics: restrict the grid
-    const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
-    kern<<<grid, gemm::THREADS, gemm::Cfg<EPI>::kSmemBytes, st>>>(ta, tb, p);
+    const int64_t units = (((p.M + gemm::BM - 1) / gemm::BM + CLP - 1) / CLP) * (p.N / gemm::BN);
+    // persistent grid = the number of clusters that can be co-resident (GPC boundaries can leave SMs unusable for
+    // clusters of 4: the occupancy query knows)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3((unsigned)(num_sms() / (2 * CLP) * 2 * CLP), 1, 1);
+        q.blockDim = dim3(gemm::THREADS, 1, 1);
+        q.dynamicSmemBytes = gemm::Cfg<EPI>::kSmemBytes;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = 2 * CLP; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        q.attrs = qa; q.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / (2 * CLP); }
+        max_clusters = n < num_sms() / (2 * CLP) ? n : num_sms() / (2 * CLP);
+        g_last_max_clusters[CLP - 1] = max_clusters;
+    }
+    int64_t clusters = max_clusters;
+    if (g_gemm_debug >> 8) clusters = (g_gemm_debug >> 8) / CLP > 0 ? (g_gemm_debug >> 8) / CLP : 1;   // diagnostics: restrict the grid
+    if (units < clusters) clusters = units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * 2 * CLP), 1, 1);
+    cfg.blockDim = dim3(gemm::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = gemm::Cfg<EPI>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2 * CLP;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) { set_cuda_error(e, "gemm_kernel launch"); return EOE_ERR_CUDA; }
     return check_launch("gemm_kernel");
+}
+
+// Default: one CTA pair per cluster (all 148 SMs).  Diagnostics bit 4 (16) selects two pairs per cluster sharing the W
+// tile by TMA multicast: -25 % operand traffic and +8 % per SM, but only 33 clusters of 4 fit the GPCs (132 SMs), so it
+// does not pay on B200 (profiles/r1_gemm_probe_multicast.json).
+template <int EPI, bool BF16>
+static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p_in, cudaStream_t st) {
+    gemm::Params p = p_in;
+    p.dbg = g_gemm_debug & 3;
+    if (g_gemm_debug & 16) return gemm_launch_c<EPI, BF16, 2>(ta, tb, p, st);
+    return gemm_launch_c<EPI, BF16, 1>(ta, tb, p, st);
 }
 
 static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int dtype, int epi,
@@ -1125,11 +1165,11 @@ extern "C" int eoe_gemm(const void* A, const void* Wt, const float* bias, void* 
     if ((rc = make_tmap(&ta, A, M, K, gemm::CTA_M, operand_dtype))) return rc;
     if ((rc = make_tmap(&tb, Wt, N, K, gemm::CTA_NB, operand_dtype))) return rc;
     gemm::Params p{M, N, K, bias, out, aux, aux_i, nullptr, nullptr, nullptr};
-    p.dbg_a = A;
     return gemm_launch(ta, tb, p, operand_dtype, epilogue, (cudaStream_t)stream);
 }
 
 extern "C" void eoe_debug_set(int flags) { g_gemm_debug = flags; }
+extern "C" int eoe_debug_max_clusters(int clp) { return (clp == 1 || clp == 2) ? g_last_max_clusters[clp - 1] : -1; }
 
 
 extern "C" int eoe_gemm_lnfold(const void* A, const void* Wf, const float* c1, const float* c2, const float* stats,

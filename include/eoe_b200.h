@@ -230,7 +230,7 @@ int eoe_vit_fold_layernorm(const float* w_f32, const float* ln_w, const float* l
                            float* c2_out, void* stream);
 
 /* Diagnostics for tools/gemm_probe.py (NOT part of the stable ABI; 0 in production): bit 0 GEMM epilogues only release
- * their accumulators, bit 1 no global stores, bit 2 L2 prefetch of the next A tile, bits 8.. grid size in CTA pairs. */
+ * their accumulators, bit 1 no global stores, bit 4 clusters of two CTA pairs with W multicast, bits 8.. grid size in CTA pairs. */
 void eoe_debug_set(int flags);
 
 /* Building blocks of the encoder, exported so that each kernel is parity-tested through the ABI. */

@@ -153,3 +153,45 @@ def test_clip_trainer_zero_shot_eval():
     feats = enc(torch.cat([b[0] for b in batches]).to(DEV)).cpu().numpy()
     np.testing.assert_allclose(scores.cpu().numpy(), oh.clip_score(feats, tr.center.cpu().numpy()), rtol=1e-3, atol=1e-30)
     assert roc.auc == oauc.roc_auc(labels.cpu().numpy(), scores.cpu().numpy())
+
+
+def test_cfg5_hsc_on_clip_vitb16_features_with_sgd():
+    """BASELINE config 5, the part on the hot path: [n, 512] features of the B200 ViT-B/16 tower (frozen: the encoder is
+    forward-only) -> HSC loss + backward + scores, optimiser = SGD(nesterov, momentum 0.9) as the reference picks for CLIP
+    models (ad_trainer.py:379-381).  A trainable head on top of the features is driven by both arms."""
+    from eoe_b200.encoder import ClipImageEncoder
+    from eoe_b200.synth import random_vit_state_dict
+    from eoe_b200.training import HSCTrainer
+    enc = ClipImageEncoder(random_vit_state_dict(16, seed=4, layers=2), device=DEV, max_batch=32)
+    g = torch.Generator().manual_seed(11)
+    imgs = torch.randn(64, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        feats = enc(imgs.to(DEV)).cpu()                               # [64, 512] image features
+    assert feats.shape == (64, 512) and torch.isfinite(feats).all()
+    lbls = torch.cat([torch.zeros(32, dtype=torch.long), torch.ones(32, dtype=torch.long)])
+    loader = [(feats[i:i + 32] * 0.2, lbls[torch.arange(i, i + 32) % 64].clone(), torch.arange(i, i + 32)) for i in (0, 32)]
+    loader[0][1][16:] = 1                                             # both classes in every batch
+    loader[1][1][:16] = 0
+    torch.manual_seed(0)
+    head = torch.nn.Linear(512, 512)
+    ref_head = copy.deepcopy(head).to(DEV)
+    tr = HSCTrainer(head, epochs=3, lr=1e-2, wdk=1e-4, milestones=[2], batch_size=32, device=DEV, sgd=True)
+    head, roc, losses = tr.train_cls(head, loader, nominal_label=0, clsstr="acorn")
+    opt = torch.optim.SGD(ref_head.parameters(), lr=1e-2, weight_decay=1e-4, momentum=0.9, nesterov=True)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, [2], 0.1)
+    ref_losses = []
+    for ep in range(3):
+        acc = []
+        for x, y, _ in loader:
+            x, y = x.to(DEV), y.to(DEV)
+            opt.zero_grad()
+            loss = _ref_hsc(ref_head(x), y)
+            loss.backward()
+            opt.step()
+            acc.append(loss.item())
+        ref_losses.append(float(np.mean(acc)))
+        sched.step()
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-3)
+    for p, q in zip(head.parameters(), ref_head.parameters()):
+        torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-3, atol=2e-5)
+    assert roc is not None and 0.0 <= roc.auc <= 1.0
