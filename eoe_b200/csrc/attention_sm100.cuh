@@ -157,6 +157,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);     // this warp's TMEM lane quarter
+    ptx::pdl_wait();                 // the prologue above overlapped the QKV GEMM's tail; qkv is complete from here on
+    ptx::pdl_launch_dependents();
 
     constexpr uint32_t idesc_s = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, LP);
     constexpr uint32_t idesc_o = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, 64, 0, 1);     // B = V is MN-major

@@ -175,6 +175,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     ptx::cluster_sync();            // barriers of both CTAs are initialised before anyone signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    // Everything above overlapped the previous kernel's tail (programmatic dependent launch); its results are needed now.
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {

@@ -122,13 +122,15 @@ static int gemm_launch_c(const CUtensorMap& ta, const CUtensorMap& tb, const gem
     cfg.blockDim = dim3(gemm::THREADS, 1, 1);
     cfg.dynamicSmemBytes = gemm::Cfg<EPI>::kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2 * CLP;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // prologue overlaps the previous kernel's tail
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (g_gemm_debug & 32) ? 1 : 2;                           // diagnostics bit 5: no dependent launch
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
     if (e != cudaSuccess) { set_cuda_error(e, "gemm_kernel launch"); return EOE_ERR_CUDA; }
     return check_launch("gemm_kernel");
@@ -620,7 +622,18 @@ static int attention_tc_launch(const CUtensorMap& tm_qkv, void* out, int64_t B, 
     }
     const int64_t items = B * heads;
     const int grid = (int)(items < 2 * (int64_t)num_sms() ? items : 2 * (int64_t)num_sms());
-    kern<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tm_qkv, *tm_o128, *tm_o72, (int)items, heads);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(attn::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = attn::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (g_gemm_debug & 32) ? 0 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_qkv, *tm_o128, *tm_o72, (int)items, heads);
+    if (e != cudaSuccess) { set_cuda_error(e, "attention_tc_kernel launch"); return EOE_ERR_CUDA; }
     return check_launch("attention_tc_kernel");
 }
 

@@ -25,13 +25,24 @@ def main():
     ap.add_argument("--rounds", type=int, default=5)
     ap.add_argument("--patch", type=int, default=16)
     ap.add_argument("--prompts", type=int, default=30)
+    ap.add_argument("--debug-flags", default="", help="name=flags,... : variants that only differ by eoe_debug_set flags (e.g. pdl=0,nopdl=32)")
     a = ap.parse_args()
     from eoe_b200.encoder import ClipImageEncoder
     from eoe_b200.synth import random_vit_state_dict
     dev = torch.device("cuda", 0)
     sd = random_vit_state_dict(a.patch, seed=0)
-    names = a.variants.split(",")
-    encs = {n: ClipImageEncoder(sd, device=dev, max_batch=a.batch, fold_layernorm=(n == "fold")) for n in names}
+    from eoe_b200 import _lib
+    dbg = {}
+    if a.debug_flags:
+        for kv in a.debug_flags.split(","):
+            k, v = kv.split("=")
+            dbg[k] = int(v)
+        names = list(dbg)
+        base = ClipImageEncoder(sd, device=dev, max_batch=a.batch)
+        encs = {n: base for n in names}
+    else:
+        names = a.variants.split(",")
+        encs = {n: ClipImageEncoder(sd, device=dev, max_batch=a.batch, fold_layernorm=(n == "fold")) for n in names}
     imgs = [torch.randn(a.batch, 3, 224, 224, device=dev) for _ in range(2)]
     text = torch.nn.functional.normalize(torch.randn(a.prompts, 512, device=dev), dim=-1)
     out = torch.empty(a.batch, device=dev)
@@ -40,6 +51,8 @@ def main():
     for r in range(a.rounds + 1):
         for n in names:
             enc = encs[n]
+            if dbg:
+                _lib.lib().eoe_debug_set(dbg[n])
             e0.record()
             for k in range(a.block):
                 enc.score(imgs[k & 1], text, out=out)
@@ -54,6 +67,8 @@ def main():
                   "blocks": [round(x, 3) for x in ms[n]]}
     for n in names:
         enc = encs[n]
+        if dbg:
+            _lib.lib().eoe_debug_set(dbg[n])
         enc.profile(True)
         for k in range(a.block):
             enc.score(imgs[k & 1], text, out=out)
