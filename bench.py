@@ -227,7 +227,7 @@ def run_ours(args):
         for k in range(n_steps):
             enc.score(imgs[k & 1], text, out=sc[k * B:(k + 1) * B])
         sc, lb = sc[:n_steps * B], lb[:n_steps * B]
-        s_all, l_all = (edist.all_gather_rows(sc), edist.all_gather_rows(lb)) if ws > 1 else (sc, lb)
+        s_all, l_all = (edist.all_gather_rows(sc, total=ws * n_steps * B), edist.all_gather_rows(lb, total=ws * n_steps * B)) if ws > 1 else (sc, lb)
         return metrics.roc_auc_device(s_all, l_all, workspace=auc_ws)
 
     def sync():
@@ -297,7 +297,8 @@ def run_ours(args):
             enc.score(dbuf[cur], text, out=sc)
             freed[cur].record(main)
             h_scores[k % S].copy_(sc, non_blocking=True)                # D2H of the step's result
-        s_all, l_all = (edist.all_gather_rows(scores[:n_steps * B]), edist.all_gather_rows(labels[:n_steps * B])) \
+        s_all, l_all = (edist.all_gather_rows(scores[:n_steps * B], total=ws * n_steps * B),
+                        edist.all_gather_rows(labels[:n_steps * B], total=ws * n_steps * B)) \
             if ws > 1 else (scores[:n_steps * B], labels[:n_steps * B])
         out, _, _ = metrics.roc_auc_device(s_all, l_all, workspace=auc_ws)
         return out.cpu()                                                 # the AUC is read on the host (sync)

@@ -43,21 +43,31 @@ def shard_range(n: int, rank: int, world_size: int) -> Tuple[int, int]:
     return lo, min(n, lo + per)
 
 
-def all_gather_rows(t: torch.Tensor, group=None) -> torch.Tensor:
-    """Concatenate 1-D (or [n, ...]) per-rank shards of possibly different length, in rank order, on every rank."""
+def all_gather_rows(t: torch.Tensor, group=None, total: Optional[int] = None) -> torch.Tensor:
+    """Concatenate 1-D (or [n, ...]) per-rank shards of possibly different length, in rank order, on every rank.
+    `total`: the global row count when the shards follow `shard_range(total, rank, world)` -- the shard sizes are then
+    known on every rank and the size exchange (a collective plus a host sync) is skipped."""
     rank, ws = world()
     if ws == 1:
         return t
     t = t.contiguous()
-    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    sizes = [torch.zeros_like(n) for _ in range(ws)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if total is not None:
+        sizes = [hi - lo for lo, hi in (shard_range(total, r, ws) for r in range(ws))]
+        if sizes[rank] != t.shape[0]:
+            raise ValueError(f"rank {rank} holds {t.shape[0]} rows, shard_range({total}, {rank}, {ws}) says {sizes[rank]}")
+    else:
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        gathered = torch.zeros(ws, dtype=torch.int64, device=t.device)
+        dist.all_gather_into_tensor(gathered, n, group=group)
+        sizes = [int(v) for v in gathered.cpu().tolist()]                  # one host sync instead of one per rank
     mx = max(sizes)
     if mx == 0:
         return t
-    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    pad[: t.shape[0]] = t
+    if t.shape[0] == mx:
+        pad = t
+    else:
+        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
     out = torch.empty((ws * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     if all(s == mx for s in sizes):
