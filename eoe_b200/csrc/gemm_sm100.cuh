@@ -121,7 +121,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     constexpr bool kLnFold = C::kLnFold, kGelu = C::kGelu, kOut16 = C::kOut16;
     constexpr bool kStatsAsync = C::kStatsAsync, kStatsReg = C::kStatsReg;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by OFFSET arithmetic on the shared array (a round trip through uintptr_t would make every later
+    // access a generic LD / ST instead of LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smem_a = smem;                                   // [STAGES][128 rows][128 B]
     uint8_t* smem_b = smem + STAGES * A_BYTES;                // [STAGES][128 rows][128 B]
     uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;
