@@ -101,6 +101,10 @@ __device__ __forceinline__ float quick_gelu(float x) {
     return __fdividef(x, 1.0f + __expf(-1.702f * x));
 }
 
+// diagnostics (eoe_debug_set bit 2, tools/gemm_probe.py): CTA 0 / epilogue warp 0 / lane 0 accumulates, over its tiles,
+// [0] clocks waiting for the accumulator, [1] clocks from accumulator-ready to end of the tile's epilogue, [2] tiles
+__device__ unsigned long long g_gemm_prof[4];
+
 // 16-byte asynchronous global -> shared copy (LDGSTS); `valid == false` zero-fills the destination
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
@@ -324,6 +328,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         int acc = 0;
         uint32_t acc_phase = 0;
         int tiles_started = 0, pbuf = 0;
+        const bool prof = (p.dbg & 4) && blockIdx.x == 0 && ew == 0 && lane == 0;
+        unsigned long long pc_wait = 0, pc_epi = 0, pc_tiles = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs, pbuf ^= 1) {
             if (kStatsAsync && ew == 0 && lane == 0) *epi_progress = ++tiles_started;
             const int m_blk = m_block(tile), n_blk = tile % num_n;
@@ -372,8 +378,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
+            const long long pt0 = clock64();
             ptx::mbar_wait(ptx::smem_u32(&tmem_full[acc]), acc_phase);
             ptx::tc_fence_after();
+            const long long pt1 = clock64();
             const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)acc * BN + (uint32_t)half * 128;
             if (p.dbg & 1) {                           // diagnostics: main loop only
                 ptx::tc_fence_before();
@@ -607,7 +615,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (prof) { pc_wait += pt1 - pt0; pc_epi += clock64() - pt1; ++pc_tiles; }
         }
+        if (prof) { g_gemm_prof[0] = pc_wait; g_gemm_prof[1] = pc_epi; g_gemm_prof[2] = pc_tiles; }
         cp_async_wait<0>();
     }
     ptx::tc_fence_before();

@@ -142,7 +142,7 @@ static int gemm_launch_c(const CUtensorMap& ta, const CUtensorMap& tb, const gem
 template <int EPI, bool BF16>
 static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p_in, cudaStream_t st) {
     gemm::Params p = p_in;
-    p.dbg = g_gemm_debug & 3;
+    p.dbg = g_gemm_debug & 7;
     if (g_gemm_debug & 16) return gemm_launch_c<EPI, BF16, 2>(ta, tb, p, st);
     return gemm_launch_c<EPI, BF16, 1>(ta, tb, p, st);
 }
@@ -1182,6 +1182,9 @@ extern "C" int eoe_gemm(const void* A, const void* Wt, const float* bias, void* 
 }
 
 extern "C" void eoe_debug_set(int flags) { g_gemm_debug = flags; }
+extern "C" int eoe_debug_gemm_prof(unsigned long long* out4_host) {
+    return cudaMemcpyFromSymbol(out4_host, gemm::g_gemm_prof, 4 * sizeof(unsigned long long)) == cudaSuccess ? 0 : EOE_ERR_CUDA;
+}
 extern "C" int eoe_debug_max_clusters(int clp) { return (clp == 1 || clp == 2) ? g_last_max_clusters[clp - 1] : -1; }
 
 

@@ -41,6 +41,12 @@ def main():
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / n * 1e3
             res[name][f] = {"us": round(us, 1), "tflops": round(2.0 * M * N * K / us / 1e6)}
+            if f & 4:
+                buf = (C.c_ulonglong * 4)()
+                lib.eoe_debug_gemm_prof(buf)
+                t = max(1, buf[2])
+                res[name][f]["epilogue_clks_per_tile"] = {"wait_for_accumulator": buf[0] // t, "epilogue": buf[1] // t, "tiles": buf[2],
+                                                          "mma_floor_clks_per_tile": 128 * 4 * (K // 64)}
             if not isinstance(res[name], dict):
                 continue
             pairs = (f >> 8) or 74
