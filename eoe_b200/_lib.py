@@ -21,6 +21,8 @@ EOE_AUC_STATUS_NONFINITE = 1
 EOE_AUC_STATUS_SINGLE_CLASS = 2
 EOE_EPI_BIAS, EOE_EPI_BIAS_QUICKGELU, EOE_EPI_BIAS_RESIDUAL_F32, EOE_EPI_PATCH_EMBED = 0, 1, 2, 3
 EOE_EPI_LNFOLD_BIAS, EOE_EPI_LNFOLD_QUICKGELU, EOE_EPI_RESIDUAL_STATS = 4, 5, 6
+EOE_EPI_LNFOLD_QUICKGELU_X1702 = 8
+GELU_SLOPE = 1.702
 EOE_ABI_VERSION = 2
 EOE_LAYOUT_NCHW, EOE_LAYOUT_NHWC = 0, 1
 
@@ -35,7 +37,7 @@ class VitLayer(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "ln_1_w", "ln_1_b", "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b",
         "ln_2_w", "ln_2_b", "c_fc_w", "c_fc_b", "c_proj_w", "c_proj_b",
-        "in_proj_wf", "in_proj_c1", "in_proj_c2", "c_fc_wf", "c_fc_c1", "c_fc_c2")]
+        "in_proj_wf", "in_proj_c1", "in_proj_c2", "c_fc_wf", "c_fc_c1", "c_fc_c2", "c_proj_w_div1702")]
 
 
 class VitWeights(C.Structure):

@@ -36,15 +36,32 @@ constexpr int STAGE_LD = 36;                                // row stride (words
 constexpr int STAGE_BUF_BYTES = 32 * STAGE_LD * 4;          // one 32 x 32 fp32 (or 32 x 64 16-bit) block of one epilogue warp
 constexpr int MAX_NCH = 6;                                  // LayerNorm fold: K / 128 chunk sums per row, K <= 768
 constexpr int EPI_RESIDUAL_STATS_ASYNC = 7;                 // internal variant of EOE_EPI_RESIDUAL_STATS (see Cfg)
+// QuickGELU(a) = a * sigmoid(1.702 a) = (1/1.702) * a' (1 + tanh(a')),  a' = 0.851 a.  EOE_EPI_LNFOLD_QUICKGELU_X1702 emits
+// 1.702 * QuickGELU: the 0.851 rides on the per-row rstd and the per-column c2 the folded LayerNorm applies anyway, and the
+// consumer (c_proj) carries weights pre-divided by 1.702 -- two FP32 multiplies fewer per output element.
+constexpr float kGeluHalfSlope = 0.851f, kGeluSlope = 1.702f;
 
 // Per-epilogue shared-memory budget.  Every epilogue warp owns
 //   * `kStageBufs` transpose buffers (RESIDUAL_STATS: 2, they double as the cp.async landing zone of the residual rows)
 //   * a parameter block filled by cp.async one tile ahead: double-buffered {bias|c2 [128], c1 [128]} and (LNFOLD) the
 //     chunk sums of the tile's rows, single-buffered because they are reduced to (mean, rstd) at the top of the tile
 // and the TMA ring takes what is left.
+// 1.702 * QuickGELU(a) given a' = 0.851 a:  a' (1 + tanh a')  (bf16)  |  2 a' / (1 + exp(-2 a'))  (fp16, exact form)
+template <bool BF16>
+__device__ __forceinline__ float quick_gelu_x(float ap) {
+    if (BF16) {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(ap));
+        return fmaf(ap, t, ap);
+    }
+    const float x2 = ap + ap;
+    return __fdividef(x2, 1.0f + __expf(-x2));
+}
+
 template <int EPI>
 struct Cfg {
-    static constexpr bool kLnFold = (EPI == EOE_EPI_LNFOLD_BIAS || EPI == EOE_EPI_LNFOLD_QUICKGELU);
+    static constexpr bool kGeluX = (EPI == EOE_EPI_LNFOLD_QUICKGELU_X1702);
+    static constexpr bool kLnFold = (EPI == EOE_EPI_LNFOLD_BIAS || EPI == EOE_EPI_LNFOLD_QUICKGELU || kGeluX);
     static constexpr bool kGelu = (EPI == EOE_EPI_BIAS_QUICKGELU || EPI == EOE_EPI_LNFOLD_QUICKGELU);
     static constexpr bool kOut16 = (EPI == EOE_EPI_BIAS || EPI == EOE_EPI_BIAS_QUICKGELU || kLnFold);
     // RESIDUAL_STATS has two implementations: the generic one keeps the residual rows in registers one round ahead
@@ -122,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
     using C = Cfg<EPI>;
     constexpr int STAGES = C::kStages;
-    constexpr bool kLnFold = C::kLnFold, kGelu = C::kGelu, kOut16 = C::kOut16;
+    constexpr bool kLnFold = C::kLnFold, kGelu = C::kGelu, kOut16 = C::kOut16, kGeluX = C::kGeluX;
     constexpr bool kStatsAsync = C::kStatsAsync, kStatsReg = C::kStatsReg;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by OFFSET arithmetic on the shared array (a round trip through uintptr_t would make every later
@@ -355,7 +372,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     const float inv_k = 1.0f / (float)p.K;
                     ln_mean = su * inv_k;
                     ln_rstd = rsqrtf(fmaxf(sq * inv_k - ln_mean * ln_mean, 0.f) + 1e-5f);
-                    __syncwarp();                      // the single stats buffer may now be refilled
+                    if (kGeluX) {                      // a' = 0.851 * (rstd * (acc - mean * c1) + c2)
+                        ln_rstd *= kGeluHalfSlope;
+                        float4* c2v = reinterpret_cast<float4*>(pblock + pbuf * C::kColBytes) + lane;
+                        float4 v = *c2v;
+                        v.x *= kGeluHalfSlope; v.y *= kGeluHalfSlope; v.z *= kGeluHalfSlope; v.w *= kGeluHalfSlope;
+                        *c2v = v;
+                    }
+                    __syncwarp();                      // the single stats buffer may now be refilled (and c2' is visible)
                 }
                 prefetch_params(tile + num_pairs, pbuf ^ 1);
                 prefetch_stats(tile + num_pairs);
@@ -424,6 +448,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                             if (kGelu) {                              // QuickGELU (model.py:162-164): x * sigmoid(1.702 x)
                                 a[e] = quick_gelu<BF16>(a[e]);
                                 b[e] = quick_gelu<BF16>(b[e]);
+                            }
+                            if (kGeluX) {                             // 1.702 * QuickGELU from the pre-scaled argument
+                                a[e] = quick_gelu_x<BF16>(a[e]);
+                                b[e] = quick_gelu_x<BF16>(b[e]);
                             }
                         }
                         *reinterpret_cast<uint4*>(strow + (j >> 1)) =

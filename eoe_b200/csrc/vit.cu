@@ -157,6 +157,7 @@ static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const gemm:
         case EOE_EPI_PATCH_EMBED: return bf ? gemm_launch_t<EOE_EPI_PATCH_EMBED, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_PATCH_EMBED, false>(ta, tb, p, st);
         case EOE_EPI_LNFOLD_BIAS: return bf ? gemm_launch_t<EOE_EPI_LNFOLD_BIAS, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_LNFOLD_BIAS, false>(ta, tb, p, st);
         case EOE_EPI_LNFOLD_QUICKGELU: return bf ? gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU, false>(ta, tb, p, st);
+        case EOE_EPI_LNFOLD_QUICKGELU_X1702: return bf ? gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU_X1702, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU_X1702, false>(ta, tb, p, st);
         case EOE_EPI_RESIDUAL_STATS:
             if (p.K <= 1024)      // HBM-bound shapes (out_proj): cp.async residual pipeline; see gemm::Cfg
                 return bf ? gemm_launch_t<gemm::EPI_RESIDUAL_STATS_ASYNC, true>(ta, tb, p, st) : gemm_launch_t<gemm::EPI_RESIDUAL_STATS_ASYNC, false>(ta, tb, p, st);
@@ -844,6 +845,7 @@ struct eoe_vit_plan {
     CUtensorMap tm_patches, tm_h, tm_u, tm_conv, tm_qkv, tm_hc, tm_uc, tm_xb, tm_ho128, tm_ho72;
     CUtensorMap *tm_in, *tm_out, *tm_fc, *tm_proj;     // per layer
     CUtensorMap *tm_inf, *tm_fcf;                      // per layer, LayerNorm-folded weights
+    CUtensorMap* tm_projs;                             // per layer, c_proj weights / 1.702 (optional)
     // optional instrumentation (eoe_vit_profile_*): CUDA event pairs around every GEMM launch
     bool profile;
     struct Span { cudaEvent_t a, b; int kind; double flops; };
@@ -973,6 +975,7 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     p->tm_proj = new CUtensorMap[w->n_layers];
     p->tm_inf = new CUtensorMap[w->n_layers];
     p->tm_fcf = new CUtensorMap[w->n_layers];
+    p->tm_projs = new CUtensorMap[w->n_layers];
     rc = make_tmap(&p->tm_patches, p->patches, max_batch * p->g2, p->kpatch, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_h, p->h, rows, W, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_u, p->u, rows, 4 * W, gemm::CTA_M, dt);
@@ -990,6 +993,7 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
         if (!rc) rc = make_tmap(&p->tm_proj[i], l.c_proj_w, W, 4 * W, gemm::CTA_NB, dt);
         if (!rc && p->fused_ln) rc = make_tmap(&p->tm_inf[i], l.in_proj_wf, 3 * W, W, gemm::CTA_NB, dt);
         if (!rc && p->fused_ln) rc = make_tmap(&p->tm_fcf[i], l.c_fc_wf, 4 * W, W, gemm::CTA_NB, dt);
+        if (!rc && p->fused_ln && l.c_proj_w_div1702) rc = make_tmap(&p->tm_projs[i], l.c_proj_w_div1702, W, 4 * W, gemm::CTA_NB, dt);
     }
     if (!rc && p->fused_ln) rc = make_tmap(&p->tm_xb, p->xb, rows, W, gemm::CTA_M, dt);
     if (rc) { eoe_vit_plan_destroy(p); return rc; }
@@ -1007,6 +1011,7 @@ extern "C" void eoe_vit_plan_destroy(eoe_vit_plan* p) {
     delete[] p->tm_proj;
     delete[] p->tm_inf;
     delete[] p->tm_fcf;
+    delete[] p->tm_projs;
     delete p;
 }
 
@@ -1080,10 +1085,13 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
                 if ((rc = timed_gemm(p, KIND_FC, p->tm_h, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
             } else {
                 gemm::Params g3{M, 4 * W, W, l.c_fc_c2, p->u, l.c_fc_c1, 0, p->stats, nullptr, nullptr};
-                if ((rc = timed_gemm(p, KIND_FC, p->tm_xb, p->tm_fcf[i], g3, dt, EOE_EPI_LNFOLD_QUICKGELU, st))) return rc;
+                const bool gelu_x = l.c_proj_w_div1702 && !(g_gemm_debug & 64);      // diagnostics bit 6: plain QuickGELU epilogue
+                const int epi_fc = gelu_x ? EOE_EPI_LNFOLD_QUICKGELU_X1702 : EOE_EPI_LNFOLD_QUICKGELU;
+                if ((rc = timed_gemm(p, KIND_FC, p->tm_xb, p->tm_fcf[i], g3, dt, epi_fc, st))) return rc;
             }
             gemm::Params g4{M, W, 4 * W, l.c_proj_b, p->x, nullptr, 0, nullptr, p->stats, p->xb};
-            if ((rc = timed_gemm(p, KIND_PROJ, p->tm_u, p->tm_proj[i], g4, dt, epi_res, st))) return rc;
+            const CUtensorMap& tm_pw = (p->fused_ln && l.c_proj_w_div1702 && !(g_gemm_debug & 64)) ? p->tm_projs[i] : p->tm_proj[i];
+            if ((rc = timed_gemm(p, KIND_PROJ, p->tm_u, tm_pw, g4, dt, epi_res, st))) return rc;
         } else {
             // last block: only the class-token rows are needed downstream (model.py:231)
             const unsigned grid = (unsigned)((B * w.heads + 3) / 4);
@@ -1201,7 +1209,8 @@ extern "C" int eoe_gemm_lnfold(const void* A, const void* Wf, const float* c1, c
     if ((rc = make_tmap(&ta, A, M, K, gemm::CTA_M, operand_dtype))) return rc;
     if ((rc = make_tmap(&tb, Wf, N, K, gemm::CTA_NB, operand_dtype))) return rc;
     gemm::Params p{M, N, K, c2, out, c1, 0, reinterpret_cast<const float2*>(stats), nullptr, nullptr};
-    return gemm_launch(ta, tb, p, operand_dtype, quick_gelu ? EOE_EPI_LNFOLD_QUICKGELU : EOE_EPI_LNFOLD_BIAS,
+    return gemm_launch(ta, tb, p, operand_dtype,
+                       quick_gelu == 2 ? EOE_EPI_LNFOLD_QUICKGELU_X1702 : (quick_gelu ? EOE_EPI_LNFOLD_QUICKGELU : EOE_EPI_LNFOLD_BIAS),
                        (cudaStream_t)stream);
 }
 

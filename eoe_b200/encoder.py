@@ -91,6 +91,8 @@ class ClipImageEncoder(nn.Module):
                     f32(sd[p + "attn.in_proj_weight"]), l.ln_1_w, l.ln_1_b, l.in_proj_b, put)
                 l.c_fc_wf, l.c_fc_c1, l.c_fc_c2 = self._fold(
                     f32(sd[p + "mlp.c_fc.weight"]), l.ln_2_w, l.ln_2_b, l.c_fc_b, put)
+                if i < self.n_layers - 1:          # the c_fc epilogue then emits 1.702 * QuickGELU (2 multiplies fewer per element)
+                    l.c_proj_w_div1702 = put(op(f32(sd[p + "mlp.c_proj.weight"]) / L.GELU_SLOPE))
         w.layers_host = C.cast(layers, C.POINTER(L.VitLayer))
         self._layers, self._w = layers, w
 
@@ -230,6 +232,7 @@ def gemm_lnfold(A, Wf, c1, c2, stats, quick_gelu=False):
     M, K = A.shape
     N = Wf.shape[0]
     out = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    # quick_gelu: False / True, or 2 for 1.702 * QuickGELU (EOE_EPI_LNFOLD_QUICKGELU_X1702)
     L.check(L.lib().eoe_gemm_lnfold(L.ptr(A), L.ptr(Wf), L.ptr(c1), L.ptr(c2), L.ptr(stats), L.ptr(out), M, N, K,
                                     L.DTYPE_CODE[A.dtype], int(quick_gelu), L.stream_ptr(A.device)), "eoe_gemm_lnfold")
     return out

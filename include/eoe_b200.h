@@ -169,6 +169,10 @@ typedef struct eoe_vit_layer {
      * QKV / c_fc GEMMs apply  rstd*(acc - mean*c1) + c2  in their epilogue (see DESIGN.md "LayerNorm fold"). */
     const void*  in_proj_wf; const float* in_proj_c1; const float* in_proj_c2;   /* [3*width,width], [3*width] x2 */
     const void*  c_fc_wf;    const float* c_fc_c1;    const float* c_fc_c2;      /* [4*width,width], [4*width] x2 */
+    /* Optional (only used together with the folded tensors): c_proj weights pre-divided by 1.702, operand dtype,
+     * rounded once from the fp32 master.  When present the c_fc epilogue emits 1.702 * QuickGELU (see
+     * EOE_EPI_LNFOLD_QUICKGELU_X1702) and c_proj multiplies by these weights -- same product, fewer instructions. */
+    const void*  c_proj_w_div1702;
 } eoe_vit_layer;
 
 typedef struct eoe_vit_weights {
@@ -235,7 +239,8 @@ void eoe_debug_set(int flags);
 
 /* Building blocks of the encoder, exported so that each kernel is parity-tested through the ABI. */
 enum { EOE_EPI_BIAS = 0, EOE_EPI_BIAS_QUICKGELU = 1, EOE_EPI_BIAS_RESIDUAL_F32 = 2, EOE_EPI_PATCH_EMBED = 3,
-       EOE_EPI_LNFOLD_BIAS = 4, EOE_EPI_LNFOLD_QUICKGELU = 5, EOE_EPI_RESIDUAL_STATS = 6 };
+       EOE_EPI_LNFOLD_BIAS = 4, EOE_EPI_LNFOLD_QUICKGELU = 5, EOE_EPI_RESIDUAL_STATS = 6,
+       EOE_EPI_LNFOLD_QUICKGELU_X1702 = 8 /* 7 is internal */ };
 /* out = epilogue(A[M,K] @ W[N,K]^T): tcgen05 GEMM, A/W operand dtype (BF16/F16), K % 64 == 0, N % 256 == 0.
  *   EOE_EPI_BIAS / _QUICKGELU: out [M,N] operand dtype;  _RESIDUAL_F32: out [M,N] fp32 += (in place);
  *   _PATCH_EMBED: out fp32 row (m/g2)*(g2+1)+1+(m%g2) = acc + pos_emb[1+m%g2] (aux = pos_emb, aux_i = g2). */
@@ -244,7 +249,8 @@ int eoe_gemm(const void* A, const void* W, const float* bias, void* out, int64_t
 /* LayerNorm-folded GEMM (QKV / c_fc with ln_1 / ln_2 folded in): A [M,K] = 16-bit copy of the residual stream,
  * Wf / c1 / c2 from eoe_vit_fold_layernorm, stats [M, K/128] float2 = per-row (sum, sum of squares) of the fp32
  * residual stream over each 128-column chunk.  out [M,N] operand dtype = rstd*(A@Wf^T - mean*c1) + c2, then
- * QuickGELU if quick_gelu != 0.  K % 256 == 0, K <= 768; c1, c2, stats 16-byte aligned. */
+ * QuickGELU if quick_gelu == 1; quick_gelu == 2 emits 1.702 * QuickGELU (for a consumer whose weights are pre-divided by
+ * 1.702: two FP32 multiplies fewer per element).  K % 256 == 0, K <= 768; c1, c2, stats 16-byte aligned. */
 int eoe_gemm_lnfold(const void* A, const void* Wf, const float* c1, const float* c2, const float* stats,
                     void* out, int64_t M, int64_t N, int64_t K, int operand_dtype, int quick_gelu, void* stream);
 /* Residual GEMM that also prepares the next folded LayerNorm: x [M,N] fp32 += A@W^T + bias (in place),

@@ -24,7 +24,8 @@ statistics -- the "precision-matched" oracle used to separate kernel bugs from r
 LayerNorm-folded path does (DESIGN.md "LayerNorm fold"): ln_1 / ln_2 are applied as
     rstd * ( round(x) @ round(W*ln_w)^T - mean * c1 ) + c2,   c1 = rowsum(round(W*ln_w)),  c2 = W @ ln_b + bias
 with mean / rstd taken from the fp32 residual stream; in exact arithmetic this IS LayerNorm followed by the Linear.
-The last block's ln_2 stays unfolded (the CUDA path evaluates it for the class-token rows only).
+The last block's ln_2 stays unfolded (the CUDA path evaluates it for the class-token rows only).  In the folded blocks
+the GELU output is stored as 1.702 * QuickGELU and c_proj's weights are pre-divided by 1.702 (same product).
 """
 import math
 import torch
@@ -143,10 +144,16 @@ def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens
         o = _r(o.transpose(1, 2).reshape(B, L, width), dt)
         x = x + F.linear(o, _r(w[p + "attn.out_proj.weight"], dt), w[p + "attn.out_proj.bias"])
         # model.py:187  x = x + mlp(ln_2(x)),  mlp = c_proj(QuickGELU(c_fc(.)))  (model.py:173-177)
+        fold_mlp = fold_layernorm and dt is not None and i < layers - 1
         u = _ln_linear(x, w[p + "ln_2.weight"], w[p + "ln_2.bias"], w[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"], dt,
-                       fold_layernorm and i < layers - 1)
-        u = _r(u * torch.sigmoid(1.702 * u), dt)
-        x = x + F.linear(u, _r(w[p + "mlp.c_proj.weight"], dt), w[p + "mlp.c_proj.bias"])
+                       fold_mlp)
+        if fold_mlp:
+            # the folded path stores 1.702 * QuickGELU and multiplies by c_proj weights pre-divided by 1.702
+            u = _r(1.702 * u * torch.sigmoid(1.702 * u), dt)
+            x = x + F.linear(u, _r(w[p + "mlp.c_proj.weight"] / 1.702, dt), w[p + "mlp.c_proj.bias"])
+        else:
+            u = _r(u * torch.sigmoid(1.702 * u), dt)
+            x = x + F.linear(u, _r(w[p + "mlp.c_proj.weight"], dt), w[p + "mlp.c_proj.bias"])
     if return_tokens:
         return x
     # model.py:231-234  ln_post on the class token, then @ proj

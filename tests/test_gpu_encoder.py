@@ -80,7 +80,7 @@ def test_fold_layernorm_kernel(dtype):
 
 @pytest.mark.parametrize("M,N,K", [(100, 256, 768), (6400, 2304, 768), (25216, 3072, 768), (777, 768, 512)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("gelu", [False, True])
+@pytest.mark.parametrize("gelu", [False, True, 2])
 def test_gemm_lnfold_vs_torch(M, N, K, dtype, gelu):
     """LayerNorm folded into the GEMM epilogue == torch LayerNorm(fp32) -> Linear on the same rounded operands."""
     from eoe_b200 import encoder as E
@@ -102,8 +102,9 @@ def test_gemm_lnfold_vs_torch(M, N, K, dtype, gelu):
     # and plain LayerNorm -> Linear in fp32 (what the reference computes, model.py:153-159,171)
     plain = torch.nn.functional.layer_norm(x, (K,), ln_w, ln_b, 1e-5) @ W.t() + bias
     if gelu:
-        ref = ref * torch.sigmoid(1.702 * ref)
-        plain = plain * torch.sigmoid(1.702 * plain)
+        k = 1.702 if gelu == 2 else 1.0                   # gelu == 2: EOE_EPI_LNFOLD_QUICKGELU_X1702 emits 1.702 * QuickGELU
+        ref = k * ref * torch.sigmoid(1.702 * ref)
+        plain = k * plain * torch.sigmoid(1.702 * plain)
     tol = 3e-3 if dtype == torch.bfloat16 else 4e-4       # output rounding to the 16-bit operand dtype
     assert _rel(got, ref.float()) < tol
     assert _rel(got, plain) < (8e-3 if dtype == torch.bfloat16 else 1e-3)   # + operand rounding of x and W*ln_w
