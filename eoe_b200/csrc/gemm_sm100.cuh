@@ -75,7 +75,9 @@ struct Cfg {
     // one warp's parameters: double-buffered {bias|c2 [128], c1 [128]} + single-buffered stats [32][MAX_NCH] float2
     static constexpr int kColBytes = kLnFold ? 1024 : 512;
     static constexpr int kParamBytes = 2 * kColBytes + (kLnFold ? 32 * MAX_NCH * 8 : 0);
-    static constexpr size_t kEpiStageBytes = (size_t)EPI_WARPS * kStageBufs * STAGE_BUF_BYTES;
+    // 16-bit outputs leave through TMA tile stores from a 1024-byte aligned, 128B-swizzled 32 x 128 B block per warp
+    static constexpr int kStageBufBytes = kOut16 ? 4096 : STAGE_BUF_BYTES;
+    static constexpr size_t kEpiStageBytes = (size_t)EPI_WARPS * kStageBufs * kStageBufBytes;
     static constexpr size_t kEpiParamBytes = (size_t)EPI_WARPS * kParamBytes;
     static constexpr size_t kSmemBytes = (size_t)kStages * STAGE_BYTES + kEpiStageBytes + kEpiParamBytes + 256 /*barriers*/ +
                                          1024 /*alignment slack*/;
@@ -136,7 +138,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // loop is bound by L2 -> SM bandwidth (12.6 TB/s at 1.6 PFLOP/s with 256 x 256 tiles).
 template <int EPI, bool BF16, int CLP>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_c, const Params p) {
     using C = Cfg<EPI>;
     constexpr int STAGES = C::kStages;
     constexpr bool kLnFold = C::kLnFold, kGelu = C::kGelu, kOut16 = C::kOut16, kGeluX = C::kGeluX;
@@ -285,7 +288,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int ew = warp - 4;
         const int wq = warp & 3;                       // TMEM lane quarter this warp may access (warp id % 4)
         const int half = ew >> 2;                      // which 128 of the 256 accumulator columns
-        float* st = reinterpret_cast<float*>(epi_stage + (size_t)ew * C::kStageBufs * STAGE_BUF_BYTES);
+        float* st = reinterpret_cast<float*>(epi_stage + (size_t)ew * C::kStageBufs * C::kStageBufBytes);
         uint8_t* pblock = epi_param + (size_t)ew * C::kParamBytes;         // parameter block of this warp
         uint8_t* pstats = pblock + 2 * C::kColBytes;
         const int sub = lane >> 3, grp = lane & 7;
@@ -416,8 +419,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             const bool do_store = !(p.dbg & 2);
             if (kOut16) {
-                // 16-bit output: 64 columns per round = 32 packed words per row
-                uint16_t* out16 = reinterpret_cast<uint16_t*>(p.out);
+                // 16-bit output: 64 columns per round.  The row owner packs its 64 values into the 128-byte row of a
+                // swizzled 32 x 128 B block (conflict-free 16-byte stores) and one lane hands the block to the TMA unit:
+                // no transposed read-back, no per-lane addresses or row predicates (rows past M are clipped by the map).
+                const uint32_t srow = ptx::smem_u32(st) + lane * 128;
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
                     uint32_t r0[32], r1[32];
@@ -429,8 +434,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tmem_empty[acc]), leader_rank);
                     }
-                    __syncwarp();                      // previous round's readers are done with `st`
-                    uint32_t* strow = reinterpret_cast<uint32_t*>(st) + lane * STAGE_LD;
+                    if (lane == 0) ptx::bulk_wait_group_read0();       // the previous block has left shared memory
+                    __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         float a[8], b[8];
@@ -454,18 +459,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                 b[e] = quick_gelu_x<BF16>(b[e]);
                             }
                         }
-                        *reinterpret_cast<uint4*>(strow + (j >> 1)) =
-                            make_uint4(pack2<BF16>(a[0], a[1]), pack2<BF16>(a[2], a[3]), pack2<BF16>(a[4], a[5]), pack2<BF16>(a[6], a[7]));
-                        *reinterpret_cast<uint4*>(strow + 16 + (j >> 1)) =
-                            make_uint4(pack2<BF16>(b[0], b[1]), pack2<BF16>(b[2], b[3]), pack2<BF16>(b[4], b[5]), pack2<BF16>(b[6], b[7]));
+                        const uint32_t ka = (uint32_t)(((j >> 3)) ^ (lane & 7)) << 4, kb = (uint32_t)((4 + (j >> 3)) ^ (lane & 7)) << 4;
+                        if (do_store) {
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ka), "r"(pack2<BF16>(a[0], a[1])),
+                                         "r"(pack2<BF16>(a[2], a[3])), "r"(pack2<BF16>(a[4], a[5])), "r"(pack2<BF16>(a[6], a[7])) : "memory");
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + kb), "r"(pack2<BF16>(b[0], b[1])),
+                                         "r"(pack2<BF16>(b[2], b[3])), "r"(pack2<BF16>(b[4], b[5])), "r"(pack2<BF16>(b[6], b[7])) : "memory");
+                        }
                     }
+                    ptx::fence_proxy_async_smem();
                     __syncwarp();
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int r = it * 4 + sub;
-                        const int64_t row = row0 + r;
-                        const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(st) + r * STAGE_LD + grp * 4);
-                        if (row < p.M && do_store) *reinterpret_cast<uint4*>(out16 + row * p.N + nb + c * 64 + grp * 8) = q;
+                    if (lane == 0 && do_store) {
+                        ptx::tma_store_2d(&tma_c, ptx::smem_u32(st), (int)(nb + c * 64), (int)row0);
+                        ptx::bulk_commit_group();
                     }
                 }
             } else if (kStatsReg) {
@@ -647,6 +653,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         if (prof) { g_gemm_prof[0] = pc_wait; g_gemm_prof[1] = pc_epi; g_gemm_prof[2] = pc_tiles; }
         cp_async_wait<0>();
+        if (kOut16 && lane == 0) ptx::bulk_wait_group_read0();
     }
     ptx::tc_fence_before();
     ptx::cluster_sync();            // the peer may still be reading this CTA's smem / signalling its barriers

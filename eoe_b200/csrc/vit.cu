@@ -88,7 +88,7 @@ static int g_gemm_debug = 0;            // eoe_debug_set(): diagnostics only, 0 
 static int g_last_max_clusters[2] = {0, 0};
 
 template <int EPI, bool BF16, int CLP>
-static int gemm_launch_c(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, cudaStream_t st) {
+static int gemm_launch_c(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p, cudaStream_t st) {
     auto kern = gemm::gemm_kernel<EPI, BF16, CLP>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -131,7 +131,7 @@ static int gemm_launch_c(const CUtensorMap& ta, const CUtensorMap& tb, const gem
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (g_gemm_debug & 32) ? 1 : 2;                           // diagnostics bit 5: no dependent launch
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p);
     if (e != cudaSuccess) { set_cuda_error(e, "gemm_kernel launch"); return EOE_ERR_CUDA; }
     return check_launch("gemm_kernel");
 }
@@ -140,28 +140,37 @@ static int gemm_launch_c(const CUtensorMap& ta, const CUtensorMap& tb, const gem
 // tile by TMA multicast: -25 % operand traffic and +8 % per SM, but only 33 clusters of 4 fit the GPCs (132 SMs), so it
 // does not pay on B200 (profiles/r1_gemm_probe_multicast.json).
 template <int EPI, bool BF16>
-static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p_in, cudaStream_t st) {
+static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p_in, cudaStream_t st,
+                         const CUtensorMap* tc) {
     gemm::Params p = p_in;
     p.dbg = g_gemm_debug & 7;
-    if (g_gemm_debug & 16) return gemm_launch_c<EPI, BF16, 2>(ta, tb, p, st);
-    return gemm_launch_c<EPI, BF16, 1>(ta, tb, p, st);
+    // 16-bit outputs leave through TMA tile stores: box 32 rows x 64 columns over out [M, N] (rows >= M are clipped)
+    CUtensorMap local;
+    if (gemm::Cfg<EPI>::kOut16 && !tc) {
+        int rc = make_tmap(&local, p.out, p.M, p.N, 32, BF16 ? EOE_BF16 : EOE_F16);
+        if (rc) return rc;
+        tc = &local;
+    }
+    if (!tc) tc = &ta;                                       // unused by the fp32-output epilogues
+    if (g_gemm_debug & 16) return gemm_launch_c<EPI, BF16, 2>(ta, tb, *tc, p, st);
+    return gemm_launch_c<EPI, BF16, 1>(ta, tb, *tc, p, st);
 }
 
 static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int dtype, int epi,
-                       cudaStream_t st) {
+                       cudaStream_t st, const CUtensorMap* tc = nullptr) {
     const bool bf = dtype == EOE_BF16;
     switch (epi) {
-        case EOE_EPI_BIAS: return bf ? gemm_launch_t<EOE_EPI_BIAS, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_BIAS, false>(ta, tb, p, st);
-        case EOE_EPI_BIAS_QUICKGELU: return bf ? gemm_launch_t<EOE_EPI_BIAS_QUICKGELU, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_BIAS_QUICKGELU, false>(ta, tb, p, st);
-        case EOE_EPI_BIAS_RESIDUAL_F32: return bf ? gemm_launch_t<EOE_EPI_BIAS_RESIDUAL_F32, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_BIAS_RESIDUAL_F32, false>(ta, tb, p, st);
-        case EOE_EPI_PATCH_EMBED: return bf ? gemm_launch_t<EOE_EPI_PATCH_EMBED, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_PATCH_EMBED, false>(ta, tb, p, st);
-        case EOE_EPI_LNFOLD_BIAS: return bf ? gemm_launch_t<EOE_EPI_LNFOLD_BIAS, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_LNFOLD_BIAS, false>(ta, tb, p, st);
-        case EOE_EPI_LNFOLD_QUICKGELU: return bf ? gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU, false>(ta, tb, p, st);
-        case EOE_EPI_LNFOLD_QUICKGELU_X1702: return bf ? gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU_X1702, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU_X1702, false>(ta, tb, p, st);
+        case EOE_EPI_BIAS: return bf ? gemm_launch_t<EOE_EPI_BIAS, true>(ta, tb, p, st, tc) : gemm_launch_t<EOE_EPI_BIAS, false>(ta, tb, p, st, tc);
+        case EOE_EPI_BIAS_QUICKGELU: return bf ? gemm_launch_t<EOE_EPI_BIAS_QUICKGELU, true>(ta, tb, p, st, tc) : gemm_launch_t<EOE_EPI_BIAS_QUICKGELU, false>(ta, tb, p, st, tc);
+        case EOE_EPI_BIAS_RESIDUAL_F32: return bf ? gemm_launch_t<EOE_EPI_BIAS_RESIDUAL_F32, true>(ta, tb, p, st, tc) : gemm_launch_t<EOE_EPI_BIAS_RESIDUAL_F32, false>(ta, tb, p, st, tc);
+        case EOE_EPI_PATCH_EMBED: return bf ? gemm_launch_t<EOE_EPI_PATCH_EMBED, true>(ta, tb, p, st, tc) : gemm_launch_t<EOE_EPI_PATCH_EMBED, false>(ta, tb, p, st, tc);
+        case EOE_EPI_LNFOLD_BIAS: return bf ? gemm_launch_t<EOE_EPI_LNFOLD_BIAS, true>(ta, tb, p, st, tc) : gemm_launch_t<EOE_EPI_LNFOLD_BIAS, false>(ta, tb, p, st, tc);
+        case EOE_EPI_LNFOLD_QUICKGELU: return bf ? gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU, true>(ta, tb, p, st, tc) : gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU, false>(ta, tb, p, st, tc);
+        case EOE_EPI_LNFOLD_QUICKGELU_X1702: return bf ? gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU_X1702, true>(ta, tb, p, st, tc) : gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU_X1702, false>(ta, tb, p, st, tc);
         case EOE_EPI_RESIDUAL_STATS:
             if (p.K <= 1024)      // HBM-bound shapes (out_proj): cp.async residual pipeline; see gemm::Cfg
-                return bf ? gemm_launch_t<gemm::EPI_RESIDUAL_STATS_ASYNC, true>(ta, tb, p, st) : gemm_launch_t<gemm::EPI_RESIDUAL_STATS_ASYNC, false>(ta, tb, p, st);
-            return bf ? gemm_launch_t<EOE_EPI_RESIDUAL_STATS, true>(ta, tb, p, st) : gemm_launch_t<EOE_EPI_RESIDUAL_STATS, false>(ta, tb, p, st);
+                return bf ? gemm_launch_t<gemm::EPI_RESIDUAL_STATS_ASYNC, true>(ta, tb, p, st, tc) : gemm_launch_t<gemm::EPI_RESIDUAL_STATS_ASYNC, false>(ta, tb, p, st, tc);
+            return bf ? gemm_launch_t<EOE_EPI_RESIDUAL_STATS, true>(ta, tb, p, st, tc) : gemm_launch_t<EOE_EPI_RESIDUAL_STATS, false>(ta, tb, p, st, tc);
         default: return EOE_ERR_ARG;
     }
 }
@@ -843,6 +852,7 @@ struct eoe_vit_plan {
     float2* stats;       // [B*L, width/128] per-row chunk (sum, sum of squares) of the residual stream
     bool fused_ln;       // every layer carries folded in_proj / c_fc weights: no stand-alone ln_1 / ln_2 launches
     CUtensorMap tm_patches, tm_h, tm_u, tm_conv, tm_qkv, tm_hc, tm_uc, tm_xb, tm_ho128, tm_ho72;
+    CUtensorMap tm_qkv_st, tm_u_st, tm_uc_st;          // 32-row store boxes over the 16-bit GEMM outputs
     CUtensorMap *tm_in, *tm_out, *tm_fc, *tm_proj;     // per layer
     CUtensorMap *tm_inf, *tm_fcf;                      // per layer, LayerNorm-folded weights
     CUtensorMap* tm_projs;                             // per layer, c_proj weights / 1.702 (optional)
@@ -856,8 +866,8 @@ struct eoe_vit_plan {
 enum { KIND_PATCH = 0, KIND_QKV = 1, KIND_OUT = 2, KIND_FC = 3, KIND_PROJ = 4 };
 
 static int timed_gemm(eoe_vit_plan* p, int kind, const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& gp,
-                      int dt, int epi, cudaStream_t st) {
-    if (!p->profile) return gemm_launch(ta, tb, gp, dt, epi, st);
+                      int dt, int epi, cudaStream_t st, const CUtensorMap* tc = nullptr) {
+    if (!p->profile) return gemm_launch(ta, tb, gp, dt, epi, st, tc);
     if (p->spans_used == p->spans.size()) {
         eoe_vit_plan::Span s;
         if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return EOE_ERR_CUDA;
@@ -867,7 +877,7 @@ static int timed_gemm(eoe_vit_plan* p, int kind, const CUtensorMap& ta, const CU
     s.kind = kind;
     s.flops = 2.0 * (double)gp.M * (double)gp.N * (double)gp.K;
     cudaEventRecord(s.a, st);
-    int rc = gemm_launch(ta, tb, gp, dt, epi, st);
+    int rc = gemm_launch(ta, tb, gp, dt, epi, st, tc);
     cudaEventRecord(s.b, st);
     return rc;
 }
@@ -984,6 +994,9 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     if (!rc && p->L == 197) rc = make_tmap_tokens(&p->tm_ho128, p->h, max_batch, p->L, W, 128, dt);
     if (!rc && p->L == 197) rc = make_tmap_tokens(&p->tm_ho72, p->h, max_batch, p->L, W, 72, dt);
     if (!rc) rc = make_tmap(&p->tm_hc, p->h_cls, max_batch, W, gemm::CTA_M, dt);
+    if (!rc) rc = make_tmap(&p->tm_qkv_st, p->qkv, rows, 3 * W, 32, dt);
+    if (!rc) rc = make_tmap(&p->tm_u_st, p->u, rows, 4 * W, 32, dt);
+    if (!rc) rc = make_tmap(&p->tm_uc_st, p->u_cls, max_batch, 4 * W, 32, dt);
     if (!rc) rc = make_tmap(&p->tm_uc, p->u_cls, max_batch, 4 * W, gemm::CTA_M, dt);
     for (int i = 0; i < w->n_layers && !rc; ++i) {
         const eoe_vit_layer& l = p->layers[i];
@@ -1069,11 +1082,11 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
         if (!p->fused_ln) {
             if ((rc = layernorm_dispatch(p->x, l.ln_1_w, l.ln_1_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
             gemm::Params g1{M, 3 * W, W, l.in_proj_b, p->qkv, nullptr, 0, nullptr, nullptr, nullptr};
-            if ((rc = timed_gemm(p, KIND_QKV, p->tm_h, p->tm_in[i], g1, dt, EOE_EPI_BIAS, st))) return rc;
+            if ((rc = timed_gemm(p, KIND_QKV, p->tm_h, p->tm_in[i], g1, dt, EOE_EPI_BIAS, st, &p->tm_qkv_st))) return rc;
         } else {
             // ln_1 folded into the QKV GEMM: A = 16-bit residual stream, epilogue rstd*(acc - mean*c1) + c2
             gemm::Params g1{M, 3 * W, W, l.in_proj_c2, p->qkv, l.in_proj_c1, 0, p->stats, nullptr, nullptr};
-            if ((rc = timed_gemm(p, KIND_QKV, p->tm_xb, p->tm_inf[i], g1, dt, EOE_EPI_LNFOLD_BIAS, st))) return rc;
+            if ((rc = timed_gemm(p, KIND_QKV, p->tm_xb, p->tm_inf[i], g1, dt, EOE_EPI_LNFOLD_BIAS, st, &p->tm_qkv_st))) return rc;
         }
         if (!last) {
             if ((rc = attention_dispatch(p->qkv, p->h, B, L, w.heads, dt, st, &p->tm_qkv, &p->tm_ho128, &p->tm_ho72))) return rc;
@@ -1082,12 +1095,12 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
             if (!p->fused_ln) {
                 if ((rc = layernorm_dispatch(p->x, l.ln_2_w, l.ln_2_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
                 gemm::Params g3{M, 4 * W, W, l.c_fc_b, p->u, nullptr, 0, nullptr, nullptr, nullptr};
-                if ((rc = timed_gemm(p, KIND_FC, p->tm_h, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
+                if ((rc = timed_gemm(p, KIND_FC, p->tm_h, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st, &p->tm_u_st))) return rc;
             } else {
                 gemm::Params g3{M, 4 * W, W, l.c_fc_c2, p->u, l.c_fc_c1, 0, p->stats, nullptr, nullptr};
                 const bool gelu_x = l.c_proj_w_div1702 && !(g_gemm_debug & 64);      // diagnostics bit 6: plain QuickGELU epilogue
                 const int epi_fc = gelu_x ? EOE_EPI_LNFOLD_QUICKGELU_X1702 : EOE_EPI_LNFOLD_QUICKGELU;
-                if ((rc = timed_gemm(p, KIND_FC, p->tm_xb, p->tm_fcf[i], g3, dt, epi_fc, st))) return rc;
+                if ((rc = timed_gemm(p, KIND_FC, p->tm_xb, p->tm_fcf[i], g3, dt, epi_fc, st, &p->tm_u_st))) return rc;
             }
             gemm::Params g4{M, W, 4 * W, l.c_proj_b, p->x, nullptr, 0, nullptr, p->stats, p->xb};
             const CUtensorMap& tm_pw = (p->fused_ln && l.c_proj_w_div1702 && !(g_gemm_debug & 64)) ? p->tm_projs[i] : p->tm_proj[i];
@@ -1102,7 +1115,7 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
             if ((rc = timed_gemm(p, KIND_OUT, p->tm_hc, p->tm_out[i], g2, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
             if ((rc = layernorm_dispatch(p->x_cls, l.ln_2_w, l.ln_2_b, p->h_cls, dt, B, W, nullptr, nullptr, 1, st))) return rc;
             gemm::Params g3{B, 4 * W, W, l.c_fc_b, p->u_cls, nullptr, 0, nullptr, nullptr, nullptr};
-            if ((rc = timed_gemm(p, KIND_FC, p->tm_hc, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st))) return rc;
+            if ((rc = timed_gemm(p, KIND_FC, p->tm_hc, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st, &p->tm_uc_st))) return rc;
             gemm::Params g4{B, W, 4 * W, l.c_proj_b, p->x_cls, nullptr, 0, nullptr, nullptr, nullptr};
             if ((rc = timed_gemm(p, KIND_PROJ, p->tm_uc, p->tm_proj[i], g4, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;
             x_tail = p->x_cls;
