@@ -187,23 +187,29 @@ static int gemm_check(int64_t M, int64_t N, int64_t K, int dtype) {
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ imgs, uint16_t* __restrict__ patches, int64_t B, int R, int P) {
+    // one thread: 8 consecutive pixels of a patch row (two 16-byte loads, one 16-byte store); 8 | P
     const int g = R / P;
-    const int pq = P / 4;
-    const int64_t total = B * 3 * (int64_t)R * R / 4;
+    const int pq = P / 8;
+    const int64_t total = B * 3 * (int64_t)R * R / 8;
     for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
         int64_t t = idx;
-        const int px4 = (int)(t % pq); t /= pq;
+        const int px8 = (int)(t % pq); t /= pq;
         const int py = (int)(t % P); t /= P;
         const int c = (int)(t % 3); t /= 3;
         const int gx = (int)(t % g); t /= g;
         const int gy = (int)(t % g); t /= g;
         const int64_t b = t;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(
-            imgs + ((b * 3 + c) * R + (gy * P + py)) * (int64_t)R + gx * P + px4 * 4));
-        uint2 o;
-        o.x = gemm::pack2<BF16>(v.x, v.y);
-        o.y = gemm::pack2<BF16>(v.z, v.w);
-        *reinterpret_cast<uint2*>(patches + idx * 4) = o;      // idx*4 == ((b*g+gy)*g+gx)*3*P*P + c*P*P + py*P + px4*4
+        const float4* src = reinterpret_cast<const float4*>(
+            imgs + ((b * 3 + c) * R + (gy * P + py)) * (int64_t)R + gx * P + px8 * 8);
+        float v0[4], v1[4];
+        load4_stream<float>(reinterpret_cast<const float*>(src), v0);
+        load4_stream<float>(reinterpret_cast<const float*>(src + 1), v1);
+        uint4 o;
+        o.x = gemm::pack2<BF16>(v0[0], v0[1]);
+        o.y = gemm::pack2<BF16>(v0[2], v0[3]);
+        o.z = gemm::pack2<BF16>(v1[0], v1[1]);
+        o.w = gemm::pack2<BF16>(v1[2], v1[3]);
+        *reinterpret_cast<uint4*>(patches + idx * 8) = o;      // idx*8 == ((b*g+gy)*g+gx)*3*P*P + c*P*P + py*P + px8*8
     }
 }
 
@@ -887,7 +893,7 @@ static size_t rup(size_t x) { return (x + 1023) / 1024 * 1024; }
 static int vit_check(const eoe_vit_weights* w) {
     if (!w || !w->layers_host) return EOE_ERR_ARG;
     if (w->operand_dtype != EOE_BF16 && w->operand_dtype != EOE_F16) return EOE_ERR_DTYPE;
-    if (w->patch <= 0 || w->resolution % w->patch != 0 || w->patch % 4 != 0) return EOE_ERR_SHAPE;
+    if (w->patch <= 0 || w->resolution % w->patch != 0 || w->patch % 8 != 0) return EOE_ERR_SHAPE;
     if (w->width != w->heads * 64 || w->width % 256 != 0 || w->width > 1024) return EOE_ERR_SHAPE;
     if ((3 * w->patch * w->patch) % 64 != 0 || w->embed_dim > 1024 || w->embed_dim % 4 != 0 || w->width % 2 != 0) return EOE_ERR_SHAPE;
     const int g = w->resolution / w->patch;
@@ -1039,7 +1045,7 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
     int rc;
     // 1. patchify
     if (imgs_f32) {
-        const int64_t total = B * 3 * (int64_t)w.resolution * w.resolution / 4;
+        const int64_t total = B * 3 * (int64_t)w.resolution * w.resolution / 8;
         int grid = (int)((total + 255) / 256 < (int64_t)num_sms() * 16 ? (total + 255) / 256 : (int64_t)num_sms() * 16);
         if (dt == EOE_BF16) im2col_kernel<true><<<grid, 256, 0, st>>>(imgs_f32, p->patches, B, w.resolution, w.patch);
         else im2col_kernel<false><<<grid, 256, 0, st>>>(imgs_f32, p->patches, B, w.resolution, w.patch);
