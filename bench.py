@@ -328,6 +328,22 @@ def run_ours(args):
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
     e2e_u8_val = ws * S * B / float(t.item())
 
+    # ---- e2e from RAW decoded images of the dataset's native size: Resize(bicubic) + CenterCrop + ToTensor + Normalize
+    # (all of CLIP's `_transform`) run inside the patchify kernel (eoe_vit_encode_u8_resize)
+    rh, rw = (32, 32) if P == 32 else (375, 500)              # CIFAR-10-shaped (config 2) / ImageNet-shaped (config 3)
+    hostr = [torch.randint(0, 256, (B, rh, rw, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    dbufr = [torch.empty(B, rh, rw, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+    e2e_job(min(W, S), hostr, dbufr)
+    sync()
+    t0 = time.perf_counter()
+    e2e_job(S, hostr, dbufr)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if ws > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    e2e_raw_val = ws * S * B / float(t.item())
+
     if rank != 0:
         if ws > 1:
             tdist.barrier()
@@ -375,6 +391,9 @@ def run_ours(args):
                 "note": "pinned fp32 host batches, double-buffered H2D on a copy stream, scores + AUC read on host"},
         "e2e_u8": {"value": e2e_u8_val, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224, "d2h_bytes_per_step": B * 4,
                    "note": "same job from raw uint8 NHWC pixels: ToTensor + Normalize fused into the patchify kernel (eoe_vit_encode_u8)"},
+        "e2e_raw": {"value": e2e_raw_val, "unit": UNIT, "h2d_bytes_per_step": B * rh * rw * 3, "d2h_bytes_per_step": B * 4,
+                    "note": f"same job from raw uint8 {rh}x{rw} images: Resize(bicubic, Pillow-exact) + CenterCrop + ToTensor + "
+                            "Normalize fused into the patchify kernel (eoe_vit_encode_u8_resize)"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "auc": auc_val,

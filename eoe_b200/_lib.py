@@ -25,6 +25,7 @@ EOE_EPI_LNFOLD_QUICKGELU_X1702 = 8
 GELU_SLOPE = 1.702
 EOE_ABI_VERSION = 2
 EOE_LAYOUT_NCHW, EOE_LAYOUT_NHWC = 0, 1
+LAYOUT_RESIZE = 2            # host-side tag only: raw [B,H,W,3] pixels of another size -> eoe_vit_encode_u8_resize
 
 DTYPE_CODE = {torch.float32: EOE_F32, torch.float16: EOE_F16, torch.bfloat16: EOE_BF16}
 
@@ -74,6 +75,8 @@ SIGNATURES = {
     "eoe_vit_plan_destroy": (None, [_P]),
     "eoe_vit_encode": (_I, [_P, _P, _I64, _P, _P, _I64, _F, _P, _P]),
     "eoe_vit_encode_u8": (_I, [_P, _P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _I64, _P, _P, _I64, _F, _P, _P]),
+    "eoe_vit_encode_u8_resize": (_I, [_P, _P, _I64, _I64, C.POINTER(C.c_float), C.POINTER(C.c_float), _I64, _P, _P, _I64, _F, _P, _P]),
+    "eoe_resize_geometry": (_I, [_I64, _I64, _I, C.POINTER(C.c_int)]),
     "eoe_vit_profile_enable": (_I, [_P, _I]),
     "eoe_vit_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(C.c_double)]),
     "eoe_debug_set": (None, [_I]),

@@ -278,6 +278,156 @@ im2col_u8_kernel(const uint8_t* __restrict__ imgs, uint16_t* __restrict__ patche
     }
 }
 
+// Raw image -> patches with the WHOLE of CLIP's `_transform` fused in (clip_official/clip/clip.py:58-65):
+//   Resize(n_px, BICUBIC) -> CenterCrop(n_px) -> ToTensor -> Normalize
+// Resize is Pillow's two-pass fixed-point resampler (libImaging/Resample.c) reproduced bit for bit: Keys bicubic a = -0.5,
+// support 2 * max(scale, 1), coefficients normalised in double precision (explicit _rn intrinsics: no FMA contraction) and
+// truncated to 22-bit fixed point, horizontal pass first into an 8-bit intermediate, clip8((2^21 + sum) >> 22); size and
+// crop rules are torchvision's (host side, resize_geometry()).  One CTA = one image x one row of patches (P output rows):
+// it tabulates the coefficients it needs, resamples the source rows those P output rows touch into shared memory, then
+// runs the vertical pass, the uint8 -> normalised 16-bit LUT of im2col_u8_kernel and the patch scatter.
+struct ResizeGeom { int H, W, nh, nw, top, left, ksh, ksv; double sch, scv; };   // source, resized, crop offset, taps, scales
+
+__device__ __forceinline__ double pil_bicubic(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(a + 2.0, x), a + 3.0), x), x), 1.0);
+    if (x < 2.0) return __dmul_rn(__dsub_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dsub_rn(x, 5.0), x), 8.0), x), 4.0), a);
+    return 0.0;
+}
+// Resample.c precompute_coeffs + normalize_coeffs_8bpc for output index xx (box = whole axis): first tap, tap count, taps
+__device__ void pil_coeffs(int xx, int in_size, double scale, int ksize, int* first, int* count, int* kk) {
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    const double support = __dmul_rn(2.0, filterscale);
+    const double ss = __ddiv_rn(1.0, filterscale);
+    const double center = __dmul_rn(__dadd_rn((double)xx, 0.5), scale);
+    int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x)
+        ww = __dadd_rn(ww, pil_bicubic(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss)));
+    for (int x = 0; x < ksize; ++x) {
+        int v = 0;
+        if (x < xmax) {
+            double w = pil_bicubic(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss));
+            if (ww != 0.0) w = __ddiv_rn(w, ww);
+            const double f = __dmul_rn(w, (double)(1 << 22));
+            v = w < 0 ? (int)__dadd_rn(-0.5, f) : (int)__dadd_rn(0.5, f);
+        }
+        kk[x] = v;
+    }
+    *first = xmin;
+    *count = xmax;
+}
+__device__ __forceinline__ int pil_clip8(int acc) {
+    const int v = acc >> 22;                       // arithmetic shift, as clip8_lookups is indexed
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+resize_patchify_kernel(const uint8_t* __restrict__ imgs, uint16_t* __restrict__ patches, int R, int P, ResizeGeom gm,
+                       NormParams np, int max_rows) {
+    extern __shared__ uint8_t rs_smem[];
+    __shared__ uint16_t lut[3][256];
+    __shared__ int s_vfirst[32], s_vcount[32];
+    __shared__ int s_rlo, s_rhi;
+    const int g = R / P, gy = blockIdx.x;
+    const int64_t b = blockIdx.y;
+    int* hfirst = reinterpret_cast<int*>(rs_smem);                 // [R]
+    int* hcount = hfirst + R;                                      // [R]
+    int* hk = hcount + R;                                          // [R][ksh]
+    int* vk = hk + R * gm.ksh;                                     // [P][ksv]
+    uint8_t* tmp = reinterpret_cast<uint8_t*>(vk + P * gm.ksv);    // [rows][R][3]
+    for (int i = threadIdx.x; i < 768; i += 256) {
+        const int c = i >> 8, v = i & 255;
+        const float x = __fdiv_rn(__fdiv_rn((float)v, 255.0f) - np.mean[c], np.stdv[c]);
+        lut[c][v] = (uint16_t)(gemm::pack2<BF16>(x, 0.f) & 0xffffu);
+    }
+    // coefficient tables: R cropped output columns, P output rows of this patch row
+    for (int i = threadIdx.x; i < R + P; i += 256) {
+        if (i < R) {
+            if (gm.nw != gm.W) pil_coeffs(gm.left + i, gm.W, gm.sch, gm.ksh, &hfirst[i], &hcount[i], hk + i * gm.ksh);
+            else { hfirst[i] = gm.left + i; hcount[i] = 1; hk[i * gm.ksh] = 1 << 22; for (int k = 1; k < gm.ksh; ++k) hk[i * gm.ksh + k] = 0; }
+        } else {
+            const int j = i - R;
+            if (gm.nh != gm.H) pil_coeffs(gm.top + gy * P + j, gm.H, gm.scv, gm.ksv, &s_vfirst[j], &s_vcount[j], vk + j * gm.ksv);
+            else { s_vfirst[j] = gm.top + gy * P + j; s_vcount[j] = 1; vk[j * gm.ksv] = 1 << 22; for (int k = 1; k < gm.ksv; ++k) vk[j * gm.ksv + k] = 0; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { s_rlo = s_vfirst[0]; s_rhi = s_vfirst[P - 1] + s_vcount[P - 1]; }
+    __syncthreads();
+    const int rlo = s_rlo, rows = min(s_rhi - s_rlo, max_rows);
+    const uint8_t* img = imgs + b * (int64_t)gm.H * gm.W * 3;
+    // horizontal pass (identity copy when the width is unchanged: hk = {2^22}) -> 8-bit intermediate, as Pillow keeps it
+    for (int i = threadIdx.x; i < rows * R; i += 256) {
+        const int r = i / R, xx = i % R;
+        const uint8_t* src = img + ((int64_t)(rlo + r) * gm.W + hfirst[xx]) * 3;
+        const int n = hcount[xx];
+        const int* k = hk + xx * gm.ksh;
+        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+        for (int t = 0; t < n; ++t) {
+            const int w = k[t];
+            a0 += (int)src[3 * t] * w; a1 += (int)src[3 * t + 1] * w; a2 += (int)src[3 * t + 2] * w;
+        }
+        uint8_t* d = tmp + (r * R + xx) * 3;
+        d[0] = (uint8_t)pil_clip8(a0); d[1] = (uint8_t)pil_clip8(a1); d[2] = (uint8_t)pil_clip8(a2);
+    }
+    __syncthreads();
+    // vertical pass + ToTensor/Normalize LUT + patch scatter: one task = 8 consecutive output pixels of one row and channel
+    const int segs = R / 8;
+    for (int i = threadIdx.x; i < P * segs * 3; i += 256) {
+        const int seg = i % segs, c = (i / segs) % 3, py = i / (segs * 3);
+        const int n = s_vcount[py], r0 = s_vfirst[py] - rlo;
+        const int* k = vk + py * gm.ksv;
+        int acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 1 << 21;
+        for (int t = 0; t < n; ++t) {
+            const int w = k[t];
+            const uint8_t* srow = tmp + ((r0 + t) * R + seg * 8) * 3 + c;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += (int)srow[3 * e] * w;
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            o[e] = lut[c][pil_clip8(acc[2 * e])] | ((uint32_t)lut[c][pil_clip8(acc[2 * e + 1])] << 16);
+        const int xx = seg * 8, gx = xx / P, px = xx % P;
+        uint16_t* dst = patches + (((b * g + gy) * g + gx) * 3 + c) * (int64_t)(P * P) + py * P + px;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// torchvision's size rules: Resize(int) scales the shorter side to n_px and the longer to int(n_px * long / short);
+// CenterCrop offsets are int(round((size - n_px) / 2.0)) with Python's round-half-even.
+static int round_half_even_half(int d) {           // round(d / 2.0) for integer d
+    if (d % 2 == 0) return d / 2;
+    const int lo = (d - 1) / 2;                    // floor for positive and negative odd d ((d-1)/2 is exact)
+    return (lo % 2 == 0) ? lo : lo + 1;
+}
+static int resize_geometry(int64_t H, int64_t W, int n_px, ResizeGeom* gm) {
+    if (H <= 0 || W <= 0 || H > (1 << 20) || W > (1 << 20)) return EOE_ERR_SHAPE;
+    const int64_t short_ = W <= H ? W : H, long_ = W <= H ? H : W;
+    const int new_long = (int)((double)((int64_t)n_px * long_) / (double)short_);
+    gm->H = (int)H; gm->W = (int)W;
+    gm->nh = W <= H ? new_long : n_px;
+    gm->nw = W <= H ? n_px : new_long;
+    if (gm->nh < n_px || gm->nw < n_px) return EOE_ERR_SHAPE;
+    gm->top = round_half_even_half(gm->nh - n_px);
+    gm->left = round_half_even_half(gm->nw - n_px);
+    gm->sch = (double)gm->W / (double)gm->nw;
+    gm->scv = (double)gm->H / (double)gm->nh;
+    const double fh = gm->sch < 1.0 ? 1.0 : gm->sch, fv = gm->scv < 1.0 ? 1.0 : gm->scv;
+    gm->ksh = (int)ceil(2.0 * fh) * 2 + 1;
+    gm->ksv = (int)ceil(2.0 * fv) * 2 + 1;
+    return EOE_OK;
+}
+
 // ------------------------------------------------------------------------------------------ LayerNorm
 // fp32 statistics over `width` (model.py:153-159, eps 1e-5); one warp per row, row kept in registers.
 // cls_emb != null: rows with row % L == 0 are synthesised as class_embedding + positional_embedding[0]
@@ -1037,7 +1187,7 @@ extern "C" void eoe_vit_plan_destroy(eoe_vit_plan* p) {
 // imgs_f32 != null: normalised fp32 NCHW input; else imgs_u8 (+ layout, norm): raw pixels, ToTensor + Normalize fused
 static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t* imgs_u8, int layout, const NormParams& norm,
                            int64_t B, float* feats_out, const float* text, int64_t K, float scale, float* scores_out,
-                           void* stream) {
+                           void* stream, const ResizeGeom* geom = nullptr) {
     cudaStream_t st = (cudaStream_t)stream;
     const eoe_vit_weights& w = p->w;
     const int W = w.width, dt = w.operand_dtype, L = p->L;
@@ -1050,6 +1200,18 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
         if (dt == EOE_BF16) im2col_kernel<true><<<grid, 256, 0, st>>>(imgs_f32, p->patches, B, w.resolution, w.patch);
         else im2col_kernel<false><<<grid, 256, 0, st>>>(imgs_f32, p->patches, B, w.resolution, w.patch);
         if ((rc = check_launch("im2col_kernel"))) return rc;
+    } else if (geom) {
+        // raw [B, H, W, 3] pixels of any size: Resize + CenterCrop + ToTensor + Normalize + patchify in one kernel
+        const int R = w.resolution, P = w.patch;
+        const double fv = geom->scv < 1.0 ? 1.0 : geom->scv;
+        const int max_rows = (int)(P * geom->scv + 4.0 * fv) + 4;               // source rows one row of patches can touch
+        const size_t smem = (size_t)(2 * R + R * geom->ksh + P * geom->ksv) * sizeof(int) + (size_t)max_rows * R * 3;
+        if (P > 32 || smem > 200 * 1024) return EOE_ERR_SHAPE;                   // down-scaling beyond ~12x per patch row
+        auto kern = dt == EOE_BF16 ? resize_patchify_kernel<true> : resize_patchify_kernel<false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_cuda_error(e, "resize_patchify smem attr"); return EOE_ERR_CUDA; }
+        kern<<<dim3((unsigned)(R / P), (unsigned)B), 256, smem, st>>>(imgs_u8, p->patches, R, P, *geom, norm, max_rows);
+        if ((rc = check_launch("resize_patchify_kernel"))) return rc;
     } else {
         const int R = w.resolution;
         const int64_t total = (layout ? 1 : 3) * B * (int64_t)R * (R / 16);
@@ -1166,6 +1328,34 @@ extern "C" int eoe_vit_encode_u8(eoe_vit_plan* p, const uint8_t* imgs, int layou
         if (!(std_host[c] > 0.f)) return EOE_ERR_ARG;
     }
     return vit_encode_impl(p, nullptr, imgs, layout == EOE_LAYOUT_NHWC, np, B, feats_out, text, K, scale, scores_out, stream);
+}
+
+extern "C" int eoe_vit_encode_u8_resize(eoe_vit_plan* p, const uint8_t* imgs, int64_t H, int64_t W, const float* mean_host,
+                                        const float* std_host, int64_t B, float* feats_out, const float* text, int64_t K,
+                                        float scale, float* scores_out, void* stream) {
+    if (!p || !imgs || !mean_host || !std_host || B <= 0 || B > p->max_batch) return EOE_ERR_ARG;
+    if ((text == nullptr) != (scores_out == nullptr)) return EOE_ERR_ARG;
+    if (p->w.patch % 8 != 0 || p->w.resolution % 8 != 0) return EOE_ERR_SHAPE;
+    ResizeGeom gm;
+    int rc = resize_geometry(H, W, p->w.resolution, &gm);
+    if (rc) return rc;
+    NormParams np;
+    for (int c = 0; c < 3; ++c) {
+        np.mean[c] = mean_host[c];
+        np.stdv[c] = std_host[c];
+        if (!(std_host[c] > 0.f)) return EOE_ERR_ARG;
+    }
+    return vit_encode_impl(p, nullptr, imgs, 1, np, B, feats_out, text, K, scale, scores_out, stream, &gm);
+}
+
+// Test hook: the transform alone.  out [B, R, R, 3] uint8 = CenterCrop(Resize(imgs [B, H, W, 3])) reconstructed from the
+// patches the kernel wrote (mean 0 / std 1/255 make the LUT the identity on the pixel value).
+extern "C" int eoe_resize_geometry(int64_t H, int64_t W, int n_px, int* out6_host) {
+    ResizeGeom gm;
+    int rc = resize_geometry(H, W, n_px, &gm);
+    if (rc) return rc;
+    out6_host[0] = gm.nh; out6_host[1] = gm.nw; out6_host[2] = gm.top; out6_host[3] = gm.left; out6_host[4] = gm.ksh; out6_host[5] = gm.ksv;
+    return EOE_OK;
 }
 
 extern "C" int eoe_vit_profile_enable(eoe_vit_plan* p, int enable) {

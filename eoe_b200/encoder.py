@@ -121,13 +121,13 @@ class ClipImageEncoder(nn.Module):
         return put(wf), put(c1), put(c2)
 
     def __del__(self):
-        plan = getattr(self, "_plan", None)
-        if plan:
-            try:
+        try:
+            plan = self.__dict__.get("_plan")
+            if plan:
+                self.__dict__["_plan"] = None       # not through nn.Module.__setattr__: it may be half torn down at exit
                 L.lib().eoe_vit_plan_destroy(plan)
-            except Exception:
-                pass
-            self._plan = None
+        except Exception:
+            pass
 
     @property
     def flops_per_image(self) -> float:
@@ -139,7 +139,8 @@ class ClipImageEncoder(nn.Module):
 
     def _prep(self, imgs):
         """-> (contiguous tensor, layout or None).  float tensors [B,3,R,R] are already normalised (what the reference
-        hands to model(imgs), ad_trainer.py:507); uint8 tensors [B,3,R,R] or [B,R,R,3] are raw pixels."""
+        hands to model(imgs), ad_trainer.py:507); uint8 tensors [B,3,R,R] or [B,R,R,3] are raw pixels at the model's
+        resolution; uint8 [B,H,W,3] of any other size goes through CLIP's Resize(bicubic) + CenterCrop on the device."""
         L.require_cuda(imgs)
         R = self.resolution
         if imgs.dim() != 4:
@@ -149,7 +150,9 @@ class ClipImageEncoder(nn.Module):
                 return imgs.detach().contiguous(), L.EOE_LAYOUT_NCHW
             if tuple(imgs.shape[1:]) == (R, R, 3):
                 return imgs.detach().contiguous(), L.EOE_LAYOUT_NHWC
-            raise L.EoeError(f"uint8 images must be [B,3,{R},{R}] or [B,{R},{R},3], got {tuple(imgs.shape)}")
+            if imgs.shape[3] == 3:              # raw decoded images of another size: Resize + CenterCrop run on the device too
+                return imgs.detach().contiguous(), L.LAYOUT_RESIZE
+            raise L.EoeError(f"uint8 images must be [B,3,{R},{R}], [B,{R},{R},3] or raw [B,H,W,3], got {tuple(imgs.shape)}")
         if tuple(imgs.shape[1:]) != (3, R, R):
             raise L.EoeError(f"images must be [B,3,{R},{R}], got {tuple(imgs.shape)}")
         return imgs.detach().to(torch.float32).contiguous(), None     # encode_image casts to the weight dtype (model.py:337)
@@ -159,6 +162,10 @@ class ClipImageEncoder(nn.Module):
         if layout is None:
             L.check(lib.eoe_vit_encode(self._plan, L.ptr(imgs), n, L.ptr(feats), L.ptr(text), K, float(scale), L.ptr(scores),
                                        L.stream_ptr(imgs.device)), "eoe_vit_encode")
+        elif layout == L.LAYOUT_RESIZE:
+            L.check(lib.eoe_vit_encode_u8_resize(self._plan, L.ptr(imgs), imgs.shape[1], imgs.shape[2], self._mean, self._std, n,
+                                                 L.ptr(feats), L.ptr(text), K, float(scale), L.ptr(scores),
+                                                 L.stream_ptr(imgs.device)), "eoe_vit_encode_u8_resize")
         else:
             L.check(lib.eoe_vit_encode_u8(self._plan, L.ptr(imgs), layout, self._mean, self._std, n, L.ptr(feats), L.ptr(text),
                                           K, float(scale), L.ptr(scores), L.stream_ptr(imgs.device)), "eoe_vit_encode_u8")

@@ -218,6 +218,19 @@ int eoe_vit_encode_u8(eoe_vit_plan* plan, const uint8_t* imgs, int layout, const
                       const float* std_host, int64_t B, float* feats_out, const float* text, int64_t K,
                       float scale, float* scores_out, void* stream);
 
+/* The whole of CLIP's `_transform` (clip_official/clip/clip.py:58-65) in front of the encoder, on the device:
+ *   Resize(R, BICUBIC) -> CenterCrop(R) -> ToTensor -> Normalize -> patchify,   imgs [B, H, W, 3] uint8 of ANY size H x W.
+ * Resize reproduces Pillow's fixed-point two-pass resampler (libImaging/Resample.c) and torchvision's size / crop rules
+ * bit for bit (oracle/resize.py is pinned against both), so the features equal those of the reference pipeline run on
+ * the host followed by eoe_vit_encode_u8.  Limit: one row of patches may touch at most ~200 KB of resampled source rows
+ * (down-scaling factors up to ~12). */
+int eoe_vit_encode_u8_resize(eoe_vit_plan* plan, const uint8_t* imgs, int64_t H, int64_t W, const float* mean_host,
+                             const float* std_host, int64_t B, float* feats_out, const float* text, int64_t K,
+                             float scale, float* scores_out, void* stream);
+/* torchvision's geometry for Resize(n_px) + CenterCrop(n_px) of an H x W image:
+ * out6_host = {resized height, resized width, crop top, crop left, horizontal taps, vertical taps}. */
+int eoe_resize_geometry(int64_t H, int64_t W, int n_px, int* out6_host);
+
 /* Optional instrumentation for roofline reporting: while enabled, eoe_vit_encode brackets every GEMM launch with a
  * CUDA event pair on `stream` (no synchronisation). eoe_vit_profile_read waits for the recorded events and returns,
  * per GEMM kind (0 patch-embed, 1 qkv, 2 out-proj, 3 c_fc, 4 c_proj), accumulated milliseconds, launches and

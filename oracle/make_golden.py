@@ -109,6 +109,23 @@ def make_vit(h):
                             img_sum=np.float64(imgs.double().sum()), w_sum=np.float64(w_sum))
 
 
+def make_resize():
+    """CLIP `_transform` head (clip.py:58-61) run by Pillow + torchvision on seeded images (tests/test_oracle_resize._img)."""
+    from PIL import Image
+    from torchvision import transforms as T
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("t", os.path.join(os.path.dirname(OUT), "test_oracle_resize.py"))
+    t = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(t)
+    tr = T.Compose([T.Resize(224, interpolation=Image.BICUBIC), T.CenterCrop(224)])
+    out = {}
+    for h, w in [(32, 32), (375, 500), (233, 350)]:
+        r = np.asarray(tr(Image.fromarray(t._img(h, w))))
+        out[f"sum_{h}x{w}"] = np.int64(r.astype(np.int64).sum())
+        out[f"sample_{h}x{w}"] = r[::37, ::41].copy()
+    np.savez_compressed(os.path.join(OUT, "resize.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     h = _ref_import.hooks()
@@ -116,6 +133,7 @@ def main():
     make_heads(h)
     make_auc()
     make_vit(h)
+    make_resize()
     print("golden fixtures written to", OUT)
 
 

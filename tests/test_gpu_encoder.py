@@ -221,3 +221,34 @@ def test_encoder_uint8_input_is_bit_identical_to_host_normalisation(tower, layou
     assert torch.equal(got, want)
     text = torch.nn.functional.normalize(torch.randn(5, 512, generator=g), dim=-1).to(DEV)
     assert torch.equal(enc.score(inp.to(DEV), text), enc.score(normed.to(DEV), text))
+
+
+@pytest.mark.parametrize("h,w", [(32, 32), (375, 500), (500, 375), (224, 300), (229, 229), (64, 100), (233, 350)])
+def test_encoder_raw_images_resize_crop_on_device(tower, h, w):
+    """CLIP's whole `_transform` (Resize bicubic + CenterCrop + ToTensor + Normalize, clip.py:58-65) fused in front of the
+    encoder: features from raw [B,H,W,3] pixels are bit-identical to resizing with the oracle (= Pillow + torchvision,
+    tests/test_oracle_resize.py) and feeding the uint8 path."""
+    from eoe_b200.encoder import ClipImageEncoder
+    from oracle import resize as orz
+    patch, sd = tower
+    rng = np.random.default_rng(h * 31 + w)
+    raw = rng.integers(0, 256, (3, h, w, 3), dtype=np.uint8)
+    raw[0, : h // 3, : w // 3] = 255
+    raw[0, h // 2:, w // 2:] = 0
+    resized = np.stack([orz.clip_resize_center_crop(im, 224) for im in raw])
+    enc = ClipImageEncoder(sd, device=DEV, max_batch=2)
+    want = enc(torch.from_numpy(resized).to(DEV))            # [B,224,224,3] uint8 -> eoe_vit_encode_u8
+    got = enc(torch.from_numpy(raw).to(DEV))                 # raw size -> eoe_vit_encode_u8_resize
+    assert torch.equal(got, want)
+
+
+def test_resize_geometry_matches_torchvision_rules():
+    import ctypes as C
+    from eoe_b200 import _lib as L
+    from oracle import resize as orz
+    out = (C.c_int * 6)()
+    for h, w in [(375, 500), (500, 375), (32, 32), (229, 224), (224, 231), (1000, 1500), (233, 350)]:
+        L.check(L.lib().eoe_resize_geometry(h, w, 224, out), "eoe_resize_geometry")
+        nh, nw = orz.resized_size(h, w, 224)
+        top, left = orz.center_crop_offsets(nh, nw, 224)
+        assert (out[0], out[1], out[2], out[3]) == (nh, nw, top, left)
