@@ -23,7 +23,7 @@ EOE_EPI_BIAS, EOE_EPI_BIAS_QUICKGELU, EOE_EPI_BIAS_RESIDUAL_F32, EOE_EPI_PATCH_E
 EOE_EPI_LNFOLD_BIAS, EOE_EPI_LNFOLD_QUICKGELU, EOE_EPI_RESIDUAL_STATS = 4, 5, 6
 EOE_EPI_LNFOLD_QUICKGELU_X1702 = 8
 GELU_SLOPE = 1.702
-EOE_ABI_VERSION = 2
+EOE_ABI_VERSION = 3
 EOE_LAYOUT_NCHW, EOE_LAYOUT_NHWC = 0, 1
 LAYOUT_RESIZE = 2            # host-side tag only: raw [B,H,W,3] pixels of another size -> eoe_vit_encode_u8_resize
 
@@ -82,8 +82,8 @@ SIGNATURES = {
     "eoe_debug_set": (None, [_I]),
     "eoe_gemm": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _I, _I, _P, _I64, _P]),
     "eoe_vit_fold_layernorm": (_I, [_P, _P, _P, _P, _I64, _I64, _I, _P, _P, _P, _P]),
-    "eoe_gemm_lnfold": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _I, _P]),
-    "eoe_gemm_residual_stats": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P]),
+    "eoe_gemm_lnfold": (_I, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _I, _P]),
+    "eoe_gemm_residual_stats": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P]),
     "eoe_layernorm": (_I, [_P, _P, _P, _P, _I, _I64, _I64, _P]),
     "eoe_attention": (_I, [_P, _P, _I64, _I64, _I64, _I, _P]),
 }

@@ -74,7 +74,9 @@ struct Cfg {
     static constexpr int kStageBufs = kStatsAsync ? 2 : 1;
     // one warp's parameters: double-buffered {bias|c2 [128], c1 [128]} + single-buffered stats [32][MAX_NCH] float2
     static constexpr int kColBytes = kLnFold ? 1024 : 512;
-    static constexpr int kParamBytes = 2 * kColBytes + (kLnFold ? 32 * MAX_NCH * 8 : 0);
+    // + single-buffered per-row data: chunk sums of the tile's 32 rows and 32 row shifts
+    static constexpr int kRowBytes = (kLnFold || kStats) ? 32 * MAX_NCH * 8 + 128 : 0;
+    static constexpr int kParamBytes = 2 * kColBytes + kRowBytes;
     // 16-bit outputs leave through TMA tile stores from a 1024-byte aligned, 128B-swizzled 32 x 128 B block per warp
     static constexpr int kStageBufBytes = kOut16 ? 4096 : STAGE_BUF_BYTES;
     static constexpr size_t kEpiStageBytes = (size_t)EPI_WARPS * kStageBufs * kStageBufBytes;
@@ -92,7 +94,9 @@ struct Params {
     int64_t aux_i;          // PATCH_EMBED: g2 (patches per image)
     const float2* stats_in; // LNFOLD_*: [M, K/128] per-row (sum, sum of squares) of the fp32 residual stream per chunk
     float2* stats_out;      // RESIDUAL_STATS: [M, N/128]
-    uint16_t* xb_out;       // RESIDUAL_STATS: [M, N] operand-dtype copy of the updated residual stream
+    uint16_t* xb_out;       // RESIDUAL_STATS: [M, N] operand-dtype copy of the updated residual stream, CENTRED on shift_out
+    const float* shift_in;  // LNFOLD_*: [M] value that was subtracted from every element of the row of A (null: 0)
+    float* shift_out;       // RESIDUAL_STATS: [M] = the row's mean BEFORE this update (from stats_in; null stats_in: 0)
     int dbg;                // diagnostics (eoe_debug_set): 1 epilogue only releases accumulators, 2 no global stores
 };
 
@@ -127,6 +131,10 @@ __device__ unsigned long long g_gemm_prof[4];
 // 16-byte asynchronous global -> shared copy (LDGSTS); `valid == false` zero-fills the destination
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
+}
+// same with an explicit number of source bytes (0..16); the remainder of the 16 bytes is zero-filled
+__device__ __forceinline__ void cp_async16n(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -291,8 +299,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         float* st = reinterpret_cast<float*>(epi_stage + (size_t)ew * C::kStageBufs * C::kStageBufBytes);
         uint8_t* pblock = epi_param + (size_t)ew * C::kParamBytes;         // parameter block of this warp
         uint8_t* pstats = pblock + 2 * C::kColBytes;
+        float* sshift = reinterpret_cast<float*>(pstats + 32 * MAX_NCH * 8);   // [32] row shifts (consumed / produced)
         const int sub = lane >> 3, grp = lane & 7;
-        const int nch = (int)(p.K >> 7);               // LNFOLD: chunk sums per row
+        // chunk sums per row of stats_in: rows of A (LNFOLD, width K) or rows of the residual stream (RESIDUAL_STATS, width N)
+        const int nch = (int)((C::kStats ? p.N : p.K) >> 7);
         const float* x32 = reinterpret_cast<const float*>(p.out);
 
         // Parameters of tile `t` -> buffer `buf` (asynchronous; the caller commits the group)
@@ -306,13 +316,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         };
         // LNFOLD: chunk sums of the 32 rows of tile `t` (contiguous; nch is even, so a 16-byte chunk never straddles rows)
         auto prefetch_stats = [&](int t) {
-            if (!kLnFold || t >= num_tiles) return;
+            if (!(kLnFold || C::kStats) || !p.stats_in || t >= num_tiles) return;
             const int64_t r0 = (int64_t)m_block(t) * BM + (int64_t)cta_rank * CTA_M + wq * 32;
             const int chunks = 16 * nch;               // 32 rows * nch * 8 B / 16 B
             for (int ch = lane; ch < chunks; ch += 32) {
                 const bool ok = r0 + (ch * 2) / nch < p.M;
                 cp_async16(pstats + ch * 16,
                            ok ? reinterpret_cast<const uint8_t*>(p.stats_in + r0 * nch) + ch * 16 : reinterpret_cast<const uint8_t*>(p.stats_in), ok);
+            }
+            if (kLnFold && p.shift_in && lane < 8) {   // 32 row shifts; a partially valid group of 4 is zero-filled past M
+                const int64_t r = r0 + lane * 4;
+                const int64_t left = p.M - r;
+                const int nbytes = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
+                cp_async16n(sshift + lane * 4, p.shift_in + (nbytes ? r : 0), nbytes);
             }
         };
         // RESIDUAL_STATS: residual block (32 rows x 32 fp32 columns) of round `c` of tile `t` -> transpose buffer `buf`
@@ -330,6 +346,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
         };
 
+        if (kLnFold || C::kStats) {                     // no shift / no previous statistics: the shifts stay zero
+            sshift[lane] = 0.f;
+            __syncwarp();
+        }
         if (!p.bias) {                                  // no bias: both parameter buffers hold zeros for the whole launch
             for (int b = 0; b < 2; ++b) reinterpret_cast<float4*>(pblock + b * C::kColBytes)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();
@@ -375,6 +395,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     const float inv_k = 1.0f / (float)p.K;
                     ln_mean = su * inv_k;
                     ln_rstd = rsqrtf(fmaxf(sq * inv_k - ln_mean * ln_mean, 0.f) + 1e-5f);
+                    // A holds x - shift (the producer centred the 16-bit copy on the row's previous mean), so
+                    // sum_k (x_k - mean) W'_k = acc - (mean - shift) * c1
+                    ln_mean -= sshift[lane];
                     if (kGeluX) {                      // a' = 0.851 * (rstd * (acc - mean * c1) + c2)
                         ln_rstd *= kGeluHalfSlope;
                         float4* c2v = reinterpret_cast<float4*>(pblock + pbuf * C::kColBytes) + lane;
@@ -383,6 +406,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         *c2v = v;
                     }
                     __syncwarp();                      // the single stats buffer may now be refilled (and c2' is visible)
+                }
+                if (kStatsReg) {
+                    // centre the 16-bit copy on the row's mean BEFORE this update (from the previous producer's chunk sums):
+                    // the rounding of xb then acts on x - mean, like the rounding of LayerNorm's output would
+                    float mu = 0.f;
+                    if (p.stats_in) {
+                        const float2* srow = reinterpret_cast<const float2*>(pstats) + lane * nch;
+                        for (int ch = 0; ch < nch; ++ch) mu += srow[ch].x;
+                        mu *= 1.0f / (float)p.N;
+                    }
+                    __syncwarp();
+                    sshift[lane] = mu;
+                    __syncwarp();
                 }
                 prefetch_params(tile + num_pairs, pbuf ^ 1);
                 prefetch_stats(tile + num_pairs);
@@ -481,6 +517,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 float ssum[8], ssq[8];
 #pragma unroll
                 for (int it = 0; it < 8; ++it) ssum[it] = ssq[it] = 0.f;
+                float mu8[8];                          // previous mean of the 8 rows this lane stores in the coalesced phase
+#pragma unroll
+                for (int it = 0; it < 8; ++it) mu8[it] = sshift[it * 4 + sub];
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     __syncwarp();                      // previous round's readers are done with `st`
@@ -519,10 +558,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         if (row0 + r < p.M && do_store) {
                             *reinterpret_cast<float4*>(xout + (row0 + r) * p.N + col) = xn;
                             *reinterpret_cast<uint2*>(p.xb_out + (row0 + r) * p.N + col) =
-                                make_uint2(pack2<BF16>(xn.x, xn.y), pack2<BF16>(xn.z, xn.w));
+                                make_uint2(pack2<BF16>(xn.x - mu8[it], xn.y - mu8[it]), pack2<BF16>(xn.z - mu8[it], xn.w - mu8[it]));
                         }
                     }
                 }
+                if (p.shift_out && n_blk == 0 && half == 0 && row0 + lane < p.M) p.shift_out[row0 + lane] = sshift[lane];
                 const int nch_out = (int)(p.N >> 7);
                 const int chunk = n_blk * 2 + half;
 #pragma unroll
@@ -543,10 +583,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 // accumulator row in place (and owns the row statistics: no shuffles), then the block leaves coalesced.
                 float* xout = reinterpret_cast<float*>(p.out);
                 float rs = 0.f, rq = 0.f;
+                float mu8[8];                          // previous mean of the 8 rows this lane stores in the coalesced phase
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     cp_async_wait<1>();                // the group of this round has landed (the next round's may be pending)
                     __syncwarp();
+                    if (c == 0) {
+                        // centre the 16-bit copy on the row's mean BEFORE this update (chunk sums of the previous producer,
+                        // prefetched with this tile's parameters)
+                        float mu = 0.f;
+                        if (p.stats_in) {
+                            const float2* srow = reinterpret_cast<const float2*>(pstats) + lane * nch;
+                            for (int ch = 0; ch < nch; ++ch) mu += srow[ch].x;
+                            mu *= 1.0f / (float)p.N;
+                        }
+                        sshift[lane] = mu;
+                        __syncwarp();
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) mu8[it] = sshift[it * 4 + sub];
+                    }
                     float* xb = st + (c & 1) * (32 * STAGE_LD);
                     float* xrow = xb + lane * STAGE_LD;
 #pragma unroll
@@ -580,20 +635,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         if (row0 + r < p.M && do_store) {
                             *reinterpret_cast<float4*>(xout + (row0 + r) * p.N + col) = xn;
                             *reinterpret_cast<uint2*>(p.xb_out + (row0 + r) * p.N + col) =
-                                make_uint2(pack2<BF16>(xn.x, xn.y), pack2<BF16>(xn.z, xn.w));
+                                make_uint2(pack2<BF16>(xn.x - mu8[it], xn.y - mu8[it]), pack2<BF16>(xn.z - mu8[it], xn.w - mu8[it]));
                         }
                     }
                     __syncwarp();                      // every lane is done with this buffer: refill it two rounds ahead
                     if (c < 2) {
                         prefetch_x(tile, c + 2, c & 1);
-                        if (c == 0) prefetch_params(tile + num_pairs, pbuf ^ 1);
+                        if (c == 0) { prefetch_params(tile + num_pairs, pbuf ^ 1); prefetch_stats(tile + num_pairs); }
                     } else {
                         prefetch_x(tile + num_pairs, c - 2, c & 1);
                     }
                     cp_async_commit();
                 }
-                if (row0 + lane < p.M)
+                if (row0 + lane < p.M) {
                     p.stats_out[(row0 + lane) * (p.N >> 7) + n_blk * 2 + half] = make_float2(rs, rq);
+                    if (p.shift_out && n_blk == 0 && half == 0) p.shift_out[row0 + lane] = sshift[lane];
+                }
             } else {
                 // fp32 output (residual += or patch-embed scatter): 32 columns per round
                 float* out32 = reinterpret_cast<float*>(p.out);

@@ -521,7 +521,7 @@ static int layernorm_dispatch(const float* x, const float* w, const float* b, vo
 template <bool BF16, int ITERS>
 __global__ void __launch_bounds__(256)
 ln_pre_stats_kernel(float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                    uint16_t* __restrict__ xb, float2* __restrict__ stats, int64_t M, int width,
+                    uint16_t* __restrict__ xb, float2* __restrict__ stats, float* __restrict__ shift, int64_t M, int width,
                     const float* __restrict__ cls_emb, const float* __restrict__ pos0, int L) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -565,19 +565,27 @@ ln_pre_stats_kernel(float* __restrict__ x, const float* __restrict__ w, const fl
         if (vi < nvec) {
             const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + vi);
             const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + vi);
-            const float o[4] = {(v[it][0] - mean) * rstd * ww.x + bb.x, (v[it][1] - mean) * rstd * ww.y + bb.y,
-                                (v[it][2] - mean) * rstd * ww.z + bb.z, (v[it][3] - mean) * rstd * ww.w + bb.w};
-            *reinterpret_cast<float4*>(x + row * width + vi * 4) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint2*>(xb + row * width + vi * 4) =
-                make_uint2(gemm::pack2<BF16>(o[0], o[1]), gemm::pack2<BF16>(o[2], o[3]));
-            ys += (o[0] + o[1]) + (o[2] + o[3]);
-            yq += (o[0] * o[0] + o[1] * o[1]) + (o[2] * o[2] + o[3] * o[3]);
+            v[it][0] = (v[it][0] - mean) * rstd * ww.x + bb.x; v[it][1] = (v[it][1] - mean) * rstd * ww.y + bb.y;
+            v[it][2] = (v[it][2] - mean) * rstd * ww.z + bb.z; v[it][3] = (v[it][3] - mean) * rstd * ww.w + bb.w;
+            *reinterpret_cast<float4*>(x + row * width + vi * 4) = make_float4(v[it][0], v[it][1], v[it][2], v[it][3]);
+            ys += (v[it][0] + v[it][1]) + (v[it][2] + v[it][3]);
+            yq += (v[it][0] * v[it][0] + v[it][1] * v[it][1]) + (v[it][2] * v[it][2] + v[it][3] * v[it][3]);
         }
     }
     ys = warp_sum(ys);
     yq = warp_sum(yq);
+    // the 16-bit copy is centred on the row's own mean (exact here: the whole row is in registers); the folded GEMM is told
+    const float ymean = ys / (float)width;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int vi = it * 32 + lane;
+        if (vi < nvec)
+            *reinterpret_cast<uint2*>(xb + row * width + vi * 4) =
+                make_uint2(gemm::pack2<BF16>(v[it][0] - ymean, v[it][1] - ymean), gemm::pack2<BF16>(v[it][2] - ymean, v[it][3] - ymean));
+    }
     const int nch = width >> 7;
     if (lane < nch) stats[row * nch + lane] = lane == 0 ? make_float2(ys, yq) : make_float2(0.f, 0.f);
+    if (lane == 0) shift[row] = ymean;
 }
 
 // LayerNorm fold of one Linear (eoe_vit_fold_layernorm): one warp per output row n.
@@ -1005,7 +1013,10 @@ struct eoe_vit_plan {
     uint16_t* h_cls;     // [B, width]
     uint16_t* u_cls;     // [B, 4*width]
     uint16_t* xb;        // [B*L, width] 16-bit copy of the residual stream (LayerNorm-folded path)
-    float2* stats;       // [B*L, width/128] per-row chunk (sum, sum of squares) of the residual stream
+    float2* stats;       // [2][B*L, width/128] per-row chunk (sum, sum of squares) of the residual stream, ping-pong:
+                         // a residual GEMM reads the previous producer's sums (row means) while it writes its own
+    float2* stats2;
+    float* shift;        // [B*L] what was subtracted from the row of xb (the row's mean before the last update)
     bool fused_ln;       // every layer carries folded in_proj / c_fc weights: no stand-alone ln_1 / ln_2 launches
     CUtensorMap tm_patches, tm_h, tm_u, tm_conv, tm_qkv, tm_hc, tm_uc, tm_xb, tm_ho128, tm_ho72;
     CUtensorMap tm_qkv_st, tm_u_st, tm_uc_st;          // 32-row store boxes over the 16-bit GEMM outputs
@@ -1068,7 +1079,7 @@ static int vit_check(const eoe_vit_weights* w) {
 }
 static bool vit_fused_ln(const eoe_vit_weights* w) { return w->layers_host[0].in_proj_wf != nullptr; }
 
-struct VitLayout { size_t patches, x, h, qkv, u, feats, x_cls, h_cls, u_cls, xb, stats, total; };
+struct VitLayout { size_t patches, x, h, qkv, u, feats, x_cls, h_cls, u_cls, xb, stats, stats2, shift, total; };
 static VitLayout vit_layout(const eoe_vit_weights* w, int64_t B) {
     const int g = w->resolution / w->patch;
     const int64_t g2 = g * g, L = g2 + 1, W = w->width;
@@ -1084,10 +1095,12 @@ static VitLayout vit_layout(const eoe_vit_weights* w, int64_t B) {
     l.x_cls = o; o += rup((size_t)B * W * 4);                  // last block, class-token rows only
     l.h_cls = o; o += rup((size_t)(B + 256) * W * 2);
     l.u_cls = o; o += rup((size_t)(B + 256) * 4 * W * 2);
-    l.xb = o; l.stats = o;
+    l.xb = o; l.stats = o; l.stats2 = o; l.shift = o;
     if (vit_fused_ln(w)) {
         o += rup((size_t)(B * L + 256) * W * 2);
         l.stats = o; o += rup((size_t)(B * L) * (W / 128) * sizeof(float2));
+        l.stats2 = o; o += rup((size_t)(B * L) * (W / 128) * sizeof(float2));
+        l.shift = o; o += rup((size_t)(B * L + 256) * sizeof(float));
     }
     l.total = o;
     return l;
@@ -1133,6 +1146,8 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     p->fused_ln = vit_fused_ln(w);
     p->xb = (uint16_t*)(p->ws + lay.xb);
     p->stats = (float2*)(p->ws + lay.stats);
+    p->stats2 = (float2*)(p->ws + lay.stats2);
+    p->shift = (float*)(p->ws + lay.shift);
     const int W = w->width, dt = w->operand_dtype;
     const int64_t rows = max_batch * p->L;
     p->tm_in = new CUtensorMap[w->n_layers];
@@ -1234,7 +1249,7 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
     } else {
         const int grid = (int)((M + 7) / 8);
 #define EOE_LN_PRE(BF, IT) ln_pre_stats_kernel<BF, IT><<<grid, 256, 0, st>>>( \
-        p->x, w.ln_pre_w, w.ln_pre_b, p->xb, p->stats, M, W, w.class_embedding, w.positional_embedding, L)
+        p->x, w.ln_pre_w, w.ln_pre_b, p->xb, p->stats, p->shift, M, W, w.class_embedding, w.positional_embedding, L)
         if (dt == EOE_BF16) { if (W <= 768) EOE_LN_PRE(true, 6); else EOE_LN_PRE(true, 8); }
         else { if (W <= 768) EOE_LN_PRE(false, 6); else EOE_LN_PRE(false, 8); }
 #undef EOE_LN_PRE
@@ -1244,6 +1259,8 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
     const float* x_tail = p->x;          // rows that feed ln_post: token 0 of every image
     int64_t tail_stride_rows = L;
     const int epi_res = p->fused_ln ? EOE_EPI_RESIDUAL_STATS : EOE_EPI_BIAS_RESIDUAL_F32;
+    float2* st_cur = p->stats;           // chunk sums of the residual stream as it is now (written by ln_pre)
+    float2* st_nxt = p->stats2;
     for (int i = 0; i < w.n_layers; ++i) {
         const eoe_vit_layer& l = p->layers[i];
         const bool last = (i == w.n_layers - 1);
@@ -1253,26 +1270,28 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
             if ((rc = timed_gemm(p, KIND_QKV, p->tm_h, p->tm_in[i], g1, dt, EOE_EPI_BIAS, st, &p->tm_qkv_st))) return rc;
         } else {
             // ln_1 folded into the QKV GEMM: A = 16-bit residual stream, epilogue rstd*(acc - mean*c1) + c2
-            gemm::Params g1{M, 3 * W, W, l.in_proj_c2, p->qkv, l.in_proj_c1, 0, p->stats, nullptr, nullptr};
+            gemm::Params g1{M, 3 * W, W, l.in_proj_c2, p->qkv, l.in_proj_c1, 0, st_cur, nullptr, nullptr, p->shift, nullptr};
             if ((rc = timed_gemm(p, KIND_QKV, p->tm_xb, p->tm_inf[i], g1, dt, EOE_EPI_LNFOLD_BIAS, st, &p->tm_qkv_st))) return rc;
         }
         if (!last) {
             if ((rc = attention_dispatch(p->qkv, p->h, B, L, w.heads, dt, st, &p->tm_qkv, &p->tm_ho128, &p->tm_ho72))) return rc;
-            gemm::Params g2{M, W, W, l.out_proj_b, p->x, nullptr, 0, nullptr, p->stats, p->xb};
+            gemm::Params g2{M, W, W, l.out_proj_b, p->x, nullptr, 0, st_cur, st_nxt, p->xb, nullptr, p->shift};
             if ((rc = timed_gemm(p, KIND_OUT, p->tm_h, p->tm_out[i], g2, dt, epi_res, st))) return rc;
+            { float2* t = st_cur; st_cur = st_nxt; st_nxt = t; }
             if (!p->fused_ln) {
                 if ((rc = layernorm_dispatch(p->x, l.ln_2_w, l.ln_2_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
                 gemm::Params g3{M, 4 * W, W, l.c_fc_b, p->u, nullptr, 0, nullptr, nullptr, nullptr};
                 if ((rc = timed_gemm(p, KIND_FC, p->tm_h, p->tm_fc[i], g3, dt, EOE_EPI_BIAS_QUICKGELU, st, &p->tm_u_st))) return rc;
             } else {
-                gemm::Params g3{M, 4 * W, W, l.c_fc_c2, p->u, l.c_fc_c1, 0, p->stats, nullptr, nullptr};
+                gemm::Params g3{M, 4 * W, W, l.c_fc_c2, p->u, l.c_fc_c1, 0, st_cur, nullptr, nullptr, p->shift, nullptr};
                 const bool gelu_x = l.c_proj_w_div1702 && !(g_gemm_debug & 64);      // diagnostics bit 6: plain QuickGELU epilogue
                 const int epi_fc = gelu_x ? EOE_EPI_LNFOLD_QUICKGELU_X1702 : EOE_EPI_LNFOLD_QUICKGELU;
                 if ((rc = timed_gemm(p, KIND_FC, p->tm_xb, p->tm_fcf[i], g3, dt, epi_fc, st, &p->tm_u_st))) return rc;
             }
-            gemm::Params g4{M, W, 4 * W, l.c_proj_b, p->x, nullptr, 0, nullptr, p->stats, p->xb};
+            gemm::Params g4{M, W, 4 * W, l.c_proj_b, p->x, nullptr, 0, st_cur, st_nxt, p->xb, nullptr, p->shift};
             const CUtensorMap& tm_pw = (p->fused_ln && l.c_proj_w_div1702 && !(g_gemm_debug & 64)) ? p->tm_projs[i] : p->tm_proj[i];
             if ((rc = timed_gemm(p, KIND_PROJ, p->tm_u, tm_pw, g4, dt, epi_res, st))) return rc;
+            { float2* t = st_cur; st_cur = st_nxt; st_nxt = t; }
         } else {
             // last block: only the class-token rows are needed downstream (model.py:231)
             const unsigned grid = (unsigned)((B * w.heads + 3) / 4);
@@ -1406,27 +1425,30 @@ extern "C" int eoe_debug_max_clusters(int clp) { return (clp == 1 || clp == 2) ?
 
 
 extern "C" int eoe_gemm_lnfold(const void* A, const void* Wf, const float* c1, const float* c2, const float* stats,
-                               void* out, int64_t M, int64_t N, int64_t K, int operand_dtype, int quick_gelu,
-                               void* stream) {
+                               const float* shift, void* out, int64_t M, int64_t N, int64_t K, int operand_dtype,
+                               int quick_gelu, void* stream) {
     if (!A || !Wf || !c1 || !c2 || !stats || !out) return EOE_ERR_ARG;
     int rc = gemm_check(M, N, K, operand_dtype);
     if (rc) return rc;
     if (K % 256 != 0 || K > 128 * gemm::MAX_NCH) return EOE_ERR_SHAPE;      // K in {256, 512, 768}
     if ((uintptr_t)A % 16 != 0 || (uintptr_t)Wf % 16 != 0 || (uintptr_t)out % 16 != 0 || (uintptr_t)stats % 16 != 0 ||
-        (uintptr_t)c1 % 16 != 0 || (uintptr_t)c2 % 16 != 0) return EOE_ERR_ALIGN;
+        (uintptr_t)c1 % 16 != 0 || (uintptr_t)c2 % 16 != 0 || (uintptr_t)shift % 16 != 0) return EOE_ERR_ALIGN;
     CUtensorMap ta, tb;
     if ((rc = make_tmap(&ta, A, M, K, gemm::CTA_M, operand_dtype))) return rc;
     if ((rc = make_tmap(&tb, Wf, N, K, gemm::CTA_NB, operand_dtype))) return rc;
-    gemm::Params p{M, N, K, c2, out, c1, 0, reinterpret_cast<const float2*>(stats), nullptr, nullptr};
+    gemm::Params p{M, N, K, c2, out, c1, 0, reinterpret_cast<const float2*>(stats), nullptr, nullptr, shift, nullptr};
     return gemm_launch(ta, tb, p, operand_dtype,
                        quick_gelu == 2 ? EOE_EPI_LNFOLD_QUICKGELU_X1702 : (quick_gelu ? EOE_EPI_LNFOLD_QUICKGELU : EOE_EPI_LNFOLD_BIAS),
                        (cudaStream_t)stream);
 }
 
-extern "C" int eoe_gemm_residual_stats(const void* A, const void* Wt, const float* bias, float* x, void* xb_out,
-                                       float* stats_out, int64_t M, int64_t N, int64_t K, int operand_dtype,
-                                       void* stream) {
+extern "C" int eoe_gemm_residual_stats(const void* A, const void* Wt, const float* bias, const float* stats_in, float* x,
+                                       void* xb_out, float* stats_out, float* shift_out, int64_t M, int64_t N, int64_t K,
+                                       int operand_dtype, void* stream) {
     if (!A || !Wt || !x || !xb_out || !stats_out) return EOE_ERR_ARG;
+    if (stats_in == stats_out) return EOE_ERR_ARG;          // other CTAs still read the previous sums while these are written
+    if (N > 128 * gemm::MAX_NCH && stats_in) return EOE_ERR_SHAPE;
+    if ((uintptr_t)stats_in % 16 != 0) return EOE_ERR_ALIGN;
     int rc = gemm_check(M, N, K, operand_dtype);
     if (rc) return rc;
     if ((uintptr_t)A % 16 != 0 || (uintptr_t)Wt % 16 != 0 || (uintptr_t)x % 16 != 0 || (uintptr_t)xb_out % 8 != 0 || (uintptr_t)bias % 16 != 0 ||
@@ -1434,8 +1456,8 @@ extern "C" int eoe_gemm_residual_stats(const void* A, const void* Wt, const floa
     CUtensorMap ta, tb;
     if ((rc = make_tmap(&ta, A, M, K, gemm::CTA_M, operand_dtype))) return rc;
     if ((rc = make_tmap(&tb, Wt, N, K, gemm::CTA_NB, operand_dtype))) return rc;
-    gemm::Params p{M, N, K, bias, x, nullptr, 0, nullptr, reinterpret_cast<float2*>(stats_out),
-                   reinterpret_cast<uint16_t*>(xb_out)};
+    gemm::Params p{M, N, K, bias, x, nullptr, 0, reinterpret_cast<const float2*>(stats_in), reinterpret_cast<float2*>(stats_out),
+                   reinterpret_cast<uint16_t*>(xb_out), nullptr, shift_out};
     return gemm_launch(ta, tb, p, operand_dtype, EOE_EPI_RESIDUAL_STATS, (cudaStream_t)stream);
 }
 

@@ -233,28 +233,32 @@ def fold_layernorm(w32, ln_w, ln_b, bias, operand_dtype=torch.bfloat16):
     return wf, c1, c2
 
 
-def gemm_lnfold(A, Wf, c1, c2, stats, quick_gelu=False):
-    """rstd*(A @ Wf^T - mean*c1) + c2 with (mean, rstd) from the per-row chunk sums `stats` [M, K/128, 2]."""
+def gemm_lnfold(A, Wf, c1, c2, stats, quick_gelu=False, shift=None):
+    """rstd*(A @ Wf^T - (mean - shift)*c1) + c2 with (mean, rstd) from the per-row chunk sums `stats` [M, K/128, 2];
+    `shift` [M] is what was subtracted from the rows of A (None: nothing)."""
     L.require_cuda(A, Wf, stats)
     M, K = A.shape
     N = Wf.shape[0]
     out = torch.empty(M, N, dtype=A.dtype, device=A.device)
     # quick_gelu: False / True, or 2 for 1.702 * QuickGELU (EOE_EPI_LNFOLD_QUICKGELU_X1702)
-    L.check(L.lib().eoe_gemm_lnfold(L.ptr(A), L.ptr(Wf), L.ptr(c1), L.ptr(c2), L.ptr(stats), L.ptr(out), M, N, K,
+    L.check(L.lib().eoe_gemm_lnfold(L.ptr(A), L.ptr(Wf), L.ptr(c1), L.ptr(c2), L.ptr(stats), L.ptr(shift), L.ptr(out), M, N, K,
                                     L.DTYPE_CODE[A.dtype], int(quick_gelu), L.stream_ptr(A.device)), "eoe_gemm_lnfold")
     return out
 
 
-def gemm_residual_stats(A, W, bias, x):
-    """x += A @ W^T + bias in place; returns (xb = x rounded to A.dtype, stats [M, N/128, 2] chunk sums of x)."""
+def gemm_residual_stats(A, W, bias, x, stats_in=None):
+    """x += A @ W^T + bias in place; returns (xb, stats, shift): stats [M, N/128, 2] chunk sums of the updated x, shift [M] =
+    row means of x BEFORE the update (from `stats_in`, the previous sums; None: zeros), xb = (x - shift) rounded to A.dtype."""
     L.require_cuda(A, W, x)
     M, K = A.shape
     N = W.shape[0]
     xb = torch.empty(M, N, dtype=A.dtype, device=A.device)
     stats = torch.empty(M, N // 128, 2, dtype=torch.float32, device=A.device)
-    L.check(L.lib().eoe_gemm_residual_stats(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(x), L.ptr(xb), L.ptr(stats), M, N, K,
-                                            L.DTYPE_CODE[A.dtype], L.stream_ptr(A.device)), "eoe_gemm_residual_stats")
-    return xb, stats
+    shift = torch.empty(M, dtype=torch.float32, device=A.device)
+    L.check(L.lib().eoe_gemm_residual_stats(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(stats_in), L.ptr(x), L.ptr(xb), L.ptr(stats),
+                                            L.ptr(shift), M, N, K, L.DTYPE_CODE[A.dtype], L.stream_ptr(A.device)),
+            "eoe_gemm_residual_stats")
+    return xb, stats, shift
 
 
 def layernorm(x, w, b, out_dtype=torch.bfloat16):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EOE_ABI_VERSION 2
+#define EOE_ABI_VERSION 3
 
 enum { EOE_F32 = 0, EOE_F16 = 1, EOE_BF16 = 2 };
 
@@ -259,17 +259,23 @@ enum { EOE_EPI_BIAS = 0, EOE_EPI_BIAS_QUICKGELU = 1, EOE_EPI_BIAS_RESIDUAL_F32 =
  *   _PATCH_EMBED: out fp32 row (m/g2)*(g2+1)+1+(m%g2) = acc + pos_emb[1+m%g2] (aux = pos_emb, aux_i = g2). */
 int eoe_gemm(const void* A, const void* W, const float* bias, void* out, int64_t M, int64_t N, int64_t K,
              int operand_dtype, int epilogue, const float* aux, int64_t aux_i, void* stream);
-/* LayerNorm-folded GEMM (QKV / c_fc with ln_1 / ln_2 folded in): A [M,K] = 16-bit copy of the residual stream,
- * Wf / c1 / c2 from eoe_vit_fold_layernorm, stats [M, K/128] float2 = per-row (sum, sum of squares) of the fp32
- * residual stream over each 128-column chunk.  out [M,N] operand dtype = rstd*(A@Wf^T - mean*c1) + c2, then
+/* LayerNorm-folded GEMM (QKV / c_fc with ln_1 / ln_2 folded in): A [M,K] = 16-bit copy of the residual stream MINUS
+ * shift[m] (null: no shift), Wf / c1 / c2 from eoe_vit_fold_layernorm, stats [M, K/128] float2 = per-row (sum, sum of
+ * squares) of the fp32 residual stream over each 128-column chunk.
+ * out [M,N] operand dtype = rstd*(A@Wf^T - (mean - shift)*c1) + c2, then
  * QuickGELU if quick_gelu == 1; quick_gelu == 2 emits 1.702 * QuickGELU (for a consumer whose weights are pre-divided by
- * 1.702: two FP32 multiplies fewer per element).  K % 256 == 0, K <= 768; c1, c2, stats 16-byte aligned. */
+ * 1.702: two FP32 multiplies fewer per element).  K % 256 == 0, K <= 768; c1, c2, stats, shift 16-byte aligned. */
 int eoe_gemm_lnfold(const void* A, const void* Wf, const float* c1, const float* c2, const float* stats,
-                    void* out, int64_t M, int64_t N, int64_t K, int operand_dtype, int quick_gelu, void* stream);
+                    const float* shift, void* out, int64_t M, int64_t N, int64_t K, int operand_dtype, int quick_gelu,
+                    void* stream);
 /* Residual GEMM that also prepares the next folded LayerNorm: x [M,N] fp32 += A@W^T + bias (in place),
- * xb_out [M,N] operand dtype = round(x), stats_out [M, N/128] float2 = per-row (sum, sum of squares) per chunk. */
-int eoe_gemm_residual_stats(const void* A, const void* W, const float* bias, float* x, void* xb_out,
-                            float* stats_out, int64_t M, int64_t N, int64_t K, int operand_dtype, void* stream);
+ * stats_out [M, N/128] float2 = per-row (sum, sum of squares) per chunk of the updated x,
+ * shift_out [M] (nullable) = the row's mean BEFORE the update, taken from stats_in [M, N/128] (the previous producer's
+ * sums; null: 0; must not alias stats_out), xb_out [M,N] operand dtype = round(x - shift): the 16-bit copy is rounded
+ * around the row's (previous) mean, as LayerNorm's own output would be. */
+int eoe_gemm_residual_stats(const void* A, const void* W, const float* bias, const float* stats_in, float* x, void* xb_out,
+                            float* stats_out, float* shift_out, int64_t M, int64_t N, int64_t K, int operand_dtype,
+                            void* stream);
 /* y[M,width] (out_dtype) = LayerNorm_fp32(x[M,width]) * w + b, eps 1e-5 (model.py:153-159) */
 int eoe_layernorm(const float* x, const float* w, const float* b, void* y, int out_dtype, int64_t M,
                   int64_t width, void* stream);

@@ -24,6 +24,8 @@ statistics -- the "precision-matched" oracle used to separate kernel bugs from r
 LayerNorm-folded path does (DESIGN.md "LayerNorm fold"): ln_1 / ln_2 are applied as
     rstd * ( round(x) @ round(W*ln_w)^T - mean * c1 ) + c2,   c1 = rowsum(round(W*ln_w)),  c2 = W @ ln_b + bias
 with mean / rstd taken from the fp32 residual stream; in exact arithmetic this IS LayerNorm followed by the Linear.
+round(x) is really round(x - shift) with shift = the row's mean before its last update (the producers cannot know the new
+mean), and the epilogue uses (mean - shift): the 16-bit rounding acts on an (almost) centred row, as LayerNorm's would.
 The last block's ln_2 stays unfolded (the CUDA path evaluates it for the class-token rows only).  In the folded blocks
 the GELU output is stored as 1.702 * QuickGELU and c_proj's weights are pre-divided by 1.702 (same product).
 """
@@ -88,8 +90,9 @@ def _r(t, dt):
     return t if dt is None else t.to(dt).to(torch.float32)
 
 
-def _ln_linear(x, ln_w, ln_b, W, bias, dt, fold):
-    """Linear(LayerNorm(x)) with the rounding points of the selected CUDA path."""
+def _ln_linear(x, ln_w, ln_b, W, bias, dt, fold, shift=None):
+    """Linear(LayerNorm(x)) with the rounding points of the selected CUDA path.  `shift` [.., 1]: what the producer
+    subtracted from the row before rounding the 16-bit copy (the row's mean before its last update)."""
     width = x.shape[-1]
     if not fold or dt is None:
         h = F.layer_norm(x, (width,), ln_w, ln_b, 1e-5)
@@ -100,7 +103,9 @@ def _ln_linear(x, ln_w, ln_b, W, bias, dt, fold):
     mean = x.mean(dim=-1, keepdim=True)
     var = (x * x).mean(dim=-1, keepdim=True) - mean * mean
     rstd = torch.rsqrt(var.clamp_min(0) + 1e-5)
-    return rstd * (_r(x, dt) @ wf.t() - mean * c1) + c2
+    if shift is None:
+        shift = torch.zeros_like(mean)
+    return rstd * (_r(x - shift, dt) @ wf.t() - (mean - shift) * c1) + c2
 
 
 @torch.no_grad()
@@ -123,11 +128,12 @@ def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens
     x = F.layer_norm(x, (width,), w["visual.ln_pre.weight"], w["visual.ln_pre.bias"], 1e-5)
     L = x.shape[1]
     dh = width // heads
+    shift = x.mean(dim=-1, keepdim=True)          # ln_pre centres its 16-bit copy on the row's own mean
     for i in range(layers):
         p = f"visual.transformer.resblocks.{i}."
         # model.py:186  x = x + attn(ln_1(x))
         qkv = _ln_linear(x, w[p + "ln_1.weight"], w[p + "ln_1.bias"], w[p + "attn.in_proj_weight"],
-                         w[p + "attn.in_proj_bias"], dt, fold_layernorm)
+                         w[p + "attn.in_proj_bias"], dt, fold_layernorm, shift)
         qkv = _r(qkv, dt)
         q, k, v = qkv.split(width, dim=-1)
         q = q.reshape(B, L, heads, dh).transpose(1, 2)
@@ -142,11 +148,13 @@ def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens
             e = torch.exp(s - s.amax(dim=-1, keepdim=True))
             o = (_r(e, dt) @ v) / e.sum(dim=-1, keepdim=True)
         o = _r(o.transpose(1, 2).reshape(B, L, width), dt)
+        shift = x.mean(dim=-1, keepdim=True)      # the residual GEMM centres xb on the row's mean BEFORE its update
         x = x + F.linear(o, _r(w[p + "attn.out_proj.weight"], dt), w[p + "attn.out_proj.bias"])
         # model.py:187  x = x + mlp(ln_2(x)),  mlp = c_proj(QuickGELU(c_fc(.)))  (model.py:173-177)
         fold_mlp = fold_layernorm and dt is not None and i < layers - 1
         u = _ln_linear(x, w[p + "ln_2.weight"], w[p + "ln_2.bias"], w[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"], dt,
-                       fold_mlp)
+                       fold_mlp, shift)
+        shift = x.mean(dim=-1, keepdim=True)
         if fold_mlp:
             # the folded path stores 1.702 * QuickGELU and multiplies by c_proj weights pre-divided by 1.702
             u = _r(1.702 * u * torch.sigmoid(1.702 * u), dt)

@@ -81,8 +81,10 @@ def test_fold_layernorm_kernel(dtype):
 @pytest.mark.parametrize("M,N,K", [(100, 256, 768), (6400, 2304, 768), (25216, 3072, 768), (777, 768, 512)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("gelu", [False, True, 2])
-def test_gemm_lnfold_vs_torch(M, N, K, dtype, gelu):
-    """LayerNorm folded into the GEMM epilogue == torch LayerNorm(fp32) -> Linear on the same rounded operands."""
+@pytest.mark.parametrize("shifted", [False, True])
+def test_gemm_lnfold_vs_torch(M, N, K, dtype, gelu, shifted):
+    """LayerNorm folded into the GEMM epilogue == torch LayerNorm(fp32) -> Linear on the same rounded operands.
+    shifted: A holds round(x - shift[m]) (the producer centred the 16-bit copy) and the epilogue uses mean - shift."""
     from eoe_b200 import encoder as E
     g = torch.Generator(device=DEV).manual_seed(M + N + K)
     x = torch.randn(M, K, device=DEV, generator=g) * 1.5 + 0.2
@@ -93,12 +95,14 @@ def test_gemm_lnfold_vs_torch(M, N, K, dtype, gelu):
     wf, c1, c2 = E.fold_layernorm(W, ln_w, ln_b, bias, dtype)
     xc = x.reshape(M, K // 128, 128)
     stats = torch.stack([xc.sum(-1), (xc * xc).sum(-1)], dim=-1).contiguous()       # [M, K/128, 2]
-    xb = x.to(dtype)
-    got = E.gemm_lnfold(xb, wf, c1, c2, stats, quick_gelu=gelu)
+    shift = (0.2 + 0.1 * torch.randn(M, device=DEV, generator=g)) if shifted else None
+    xb = (x - shift[:, None]).to(dtype) if shifted else x.to(dtype)
+    got = E.gemm_lnfold(xb, wf, c1, c2, stats, quick_gelu=gelu, shift=shift)
     # the same algebra in fp64 on the same rounded operands (separates kernel bugs from the moved rounding point)
     mean = x.double().mean(-1, keepdim=True)
     rstd = torch.rsqrt(x.double().var(-1, unbiased=False, keepdim=True) + 1e-5)
-    ref = rstd * (xb.double() @ wf.double().t() - mean * c1.double()) + c2.double()
+    sh = shift.double()[:, None] if shifted else 0.0
+    ref = rstd * (xb.double() @ wf.double().t() - (mean - sh) * c1.double()) + c2.double()
     # and plain LayerNorm -> Linear in fp32 (what the reference computes, model.py:153-159,171)
     plain = torch.nn.functional.layer_norm(x, (K,), ln_w, ln_b, 1e-5) @ W.t() + bias
     if gelu:
@@ -110,23 +114,62 @@ def test_gemm_lnfold_vs_torch(M, N, K, dtype, gelu):
     assert _rel(got, plain) < (8e-3 if dtype == torch.bfloat16 else 1e-3)   # + operand rounding of x and W*ln_w
 
 
-@pytest.mark.parametrize("M,N,K", [(100, 768, 768), (6400, 768, 3072), (25216, 768, 768), (333, 1024, 256)])
+@pytest.mark.parametrize("M,N,K", [(100, 768, 768), (6400, 768, 3072), (25216, 768, 768), (333, 1024, 256), (515, 512, 3072)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_gemm_residual_stats_vs_torch(M, N, K, dtype):
-    """x += A@W^T + bias (fp32), xb = round(x), per-row chunk sums of the updated x."""
+@pytest.mark.parametrize("with_prev", [False, True])
+def test_gemm_residual_stats_vs_torch(M, N, K, dtype, with_prev):
+    """x += A@W^T + bias (fp32), per-row chunk sums of the updated x, shift = the row's mean BEFORE the update (from the
+    previous producer's chunk sums; zeros without them), xb = round(x - shift)."""
     from eoe_b200 import encoder as E
+    if with_prev and N > 768:
+        pytest.skip("previous chunk sums are staged for N <= 768 (EOE_ERR_SHAPE above)")
     g = torch.Generator(device=DEV).manual_seed(M + N + K + 1)
     A = (torch.randn(M, K, device=DEV, generator=g) * 0.5).to(dtype)
     W = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(dtype)
     bias = torch.randn(N, device=DEV, generator=g)
-    x = torch.randn(M, N, device=DEV, generator=g)
+    x = torch.randn(M, N, device=DEV, generator=g) + 0.7 * torch.randn(M, 1, device=DEV, generator=g)
+    prev = None
+    want_shift = torch.zeros(M, device=DEV)
+    if with_prev:
+        xc0 = x.reshape(M, N // 128, 128)
+        prev = torch.stack([xc0.sum(-1), (xc0 * xc0).sum(-1)], dim=-1).contiguous()
+        want_shift = prev[..., 0].sum(-1) / N
     ref = x + A.float() @ W.float().t() + bias
-    xb, stats = E.gemm_residual_stats(A, W, bias, x)
+    xb, stats, shift = E.gemm_residual_stats(A, W, bias, x, stats_in=prev)
     assert _rel(x, ref) < 2e-5
-    assert torch.equal(xb, x.to(dtype))                   # the 16-bit copy is the rounding of exactly what was stored
+    torch.testing.assert_close(shift, want_shift, rtol=1e-5, atol=1e-6)
+    # the 16-bit copy is the rounding of exactly what was stored minus exactly the shift that is reported
+    assert torch.equal(xb, (x - shift[:, None]).to(dtype))
     xc = x.reshape(M, N // 128, 128).double()
     torch.testing.assert_close(stats[..., 0].double(), xc.sum(-1), rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(stats[..., 1].double(), (xc * xc).sum(-1), rtol=1e-4, atol=1e-3)
+
+
+def test_lnfold_chain_is_insensitive_to_row_offsets():
+    """The point of the centred 16-bit copy: a common-mode offset of a token row (|mean| >> std) no longer costs operand
+    precision.  residual GEMM -> folded GEMM on rows with mean = 20 * std: error vs fp32 LayerNorm -> Linear stays at the
+    level of rows without an offset (an uncentred bf16 copy would lose ~4 bits: > 5e-2)."""
+    from eoe_b200 import encoder as E
+    dtype, M, W_ = torch.bfloat16, 2048, 768
+    g = torch.Generator(device=DEV).manual_seed(77)
+    errs = {}
+    for off in (0.0, 20.0):
+        x = torch.randn(M, W_, device=DEV, generator=g) + off
+        xc0 = x.reshape(M, W_ // 128, 128)
+        prev = torch.stack([xc0.sum(-1), (xc0 * xc0).sum(-1)], dim=-1).contiguous()
+        A = (torch.randn(M, W_, device=DEV, generator=g) * 0.5).to(dtype)
+        Wo = (torch.randn(W_, W_, device=DEV, generator=g) * 0.02).to(dtype)
+        xb, stats, shift = E.gemm_residual_stats(A, Wo, None, x, stats_in=prev)
+        Wq = torch.randn(2304, W_, device=DEV, generator=g) * 0.04
+        ln_w = 1 + 0.1 * torch.randn(W_, device=DEV, generator=g)
+        ln_b = 0.1 * torch.randn(W_, device=DEV, generator=g)
+        bias = torch.randn(2304, device=DEV, generator=g)
+        wf, c1, c2 = E.fold_layernorm(Wq, ln_w, ln_b, bias, dtype)
+        got = E.gemm_lnfold(xb, wf, c1, c2, stats, shift=shift)
+        plain = torch.nn.functional.layer_norm(x, (W_,), ln_w, ln_b, 1e-5) @ Wq.t() + bias
+        errs[off] = _rel(got, plain)
+    assert errs[0.0] < 8e-3
+    assert errs[20.0] < 1.25 * errs[0.0] + 1e-3, errs
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 4e-3), (torch.float16, 5e-4)])
