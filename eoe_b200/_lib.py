@@ -23,7 +23,7 @@ EOE_EPI_BIAS, EOE_EPI_BIAS_QUICKGELU, EOE_EPI_BIAS_RESIDUAL_F32, EOE_EPI_PATCH_E
 EOE_EPI_LNFOLD_BIAS, EOE_EPI_LNFOLD_QUICKGELU, EOE_EPI_RESIDUAL_STATS = 4, 5, 6
 EOE_EPI_LNFOLD_QUICKGELU_X1702 = 8
 GELU_SLOPE = 1.702
-EOE_ABI_VERSION = 3
+EOE_ABI_VERSION = 4
 EOE_LAYOUT_NCHW, EOE_LAYOUT_NHWC = 0, 1
 LAYOUT_RESIZE = 2            # host-side tag only: raw [B,H,W,3] pixels of another size -> eoe_vit_encode_u8_resize
 
@@ -86,6 +86,9 @@ SIGNATURES = {
     "eoe_gemm_residual_stats": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I, _P]),
     "eoe_layernorm": (_I, [_P, _P, _P, _P, _I, _I64, _I64, _P]),
     "eoe_attention": (_I, [_P, _P, _I64, _I64, _I64, _I, _P]),
+    "eoe_attention_causal": (_I, [_P, _P, _I64, _I64, _I64, _I, _P]),
+    "eoe_text_embed": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "eoe_text_tail": (_I, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
 }
 
 _lib = None

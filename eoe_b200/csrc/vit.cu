@@ -650,7 +650,8 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 
 constexpr int kAttnThreads = 128;
 
-template <bool BF16, int LP>
+// CAUSAL: key j is visible to query i only if j <= i (the text tower's additive -inf mask, model.py:324-331).
+template <bool BF16, int LP, bool CAUSAL = false>
 __global__ void __launch_bounds__(kAttnThreads)
 attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int L, int heads) {
     extern __shared__ __align__(128) uint8_t sm[];
@@ -709,6 +710,13 @@ attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, i
             const int col = nt * 8 + (lane & 3) * 2;
             if (col >= L) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
             if (col + 1 >= L) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+            if (CAUSAL) {                            // rows q0 + lane/4 (e = 0, 1) and + 8 (e = 2, 3); key 0 is always visible
+                const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
+                if (col > r0) s[nt][0] = -INFINITY;
+                if (col + 1 > r0) s[nt][1] = -INFINITY;
+                if (col > r1) s[nt][2] = -INFINITY;
+                if (col + 1 > r1) s[nt][3] = -INFINITY;
+            }
             m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
             m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
         }
@@ -761,9 +769,9 @@ attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, i
     }
 }
 
-template <bool BF16, int LP>
+template <bool BF16, int LP, bool CAUSAL = false>
 static int attention_launch_t(const void* qkv, void* out, int64_t B, int L, int heads, cudaStream_t st) {
-    auto kern = attention_kernel<BF16, LP>;
+    auto kern = attention_kernel<BF16, LP, CAUSAL>;
     const int smem = 3 * LP * 128;
     static bool attr_done = false;
     if (!attr_done) {
@@ -813,10 +821,15 @@ static int attention_tc_launch(const CUtensorMap& tm_qkv, void* out, int64_t B, 
 
 static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int dtype, cudaStream_t st,
                               const CUtensorMap* tm_qkv = nullptr, const CUtensorMap* tm_o128 = nullptr,
-                              const CUtensorMap* tm_o72 = nullptr) {
+                              const CUtensorMap* tm_o72 = nullptr, bool causal = false) {
     if (dtype != EOE_BF16 && dtype != EOE_F16) return EOE_ERR_DTYPE;
     if (B <= 0 || L <= 0 || heads <= 0 || B * heads > 0x7fffffff) return EOE_ERR_ARG;
     const bool bf = dtype == EOE_BF16;
+    if (causal) {                                    // text tower (context 77): warp-level kernel, keys in shared memory
+        if (L <= 80) return bf ? attention_launch_t<true, 80, true>(qkv, out, B, (int)L, (int)heads, st) : attention_launch_t<false, 80, true>(qkv, out, B, (int)L, (int)heads, st);
+        if (L <= 208) return bf ? attention_launch_t<true, 208, true>(qkv, out, B, (int)L, (int)heads, st) : attention_launch_t<false, 208, true>(qkv, out, B, (int)L, (int)heads, st);
+        return EOE_ERR_SHAPE;
+    }
     if (L == 197) {
         CUtensorMap local;
         if (!tm_qkv) {
@@ -942,7 +955,8 @@ constexpr int kTailImgs = 4;
 constexpr int kTailCols = 128;
 __global__ void __launch_bounds__(256)
 tail_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-            const float* __restrict__ proj, float* __restrict__ feats, int64_t B, int L, int width, int embed) {
+            const float* __restrict__ proj, float* __restrict__ feats, int64_t B, int L, int width, int embed,
+            const int64_t* __restrict__ tokens = nullptr) {
     extern __shared__ float s_h[];        // [kTailImgs][width] then [kTailImgs][kTailCols] partials
     float* s_part = s_h + kTailImgs * width;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -954,6 +968,22 @@ tail_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
         float* h = s_h + warp * width;
         if (img < B) {
             const float* xr = x + img * L * (int64_t)width;
+            if (tokens) {
+                // text tower (model.py:350): the row of the <eot> token = first position of the largest token id
+                long long best = -1;
+                int pos = 0;
+                for (int j = lane; j < L; j += 32) {
+                    const long long t = tokens[img * L + j];
+                    if (t > best) { best = t; pos = j; }         // strictly greater: keeps this lane's first maximum
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const long long ob = __shfl_xor_sync(kFullMask, best, o);
+                    const int op = __shfl_xor_sync(kFullMask, pos, o);
+                    if (ob > best || (ob == best && op < pos)) { best = ob; pos = op; }
+                }
+                xr += (int64_t)pos * width;
+            }
             float s = 0.f;
             for (int i = lane; i < width; i += 32) s += xr[i];
             const float mean = warp_sum(s) / (float)width;
@@ -987,6 +1017,26 @@ tail_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
 #pragma unroll
         for (int g = 0; g < kTailImgs; ++g)
             if (img0 + g < B) feats[(img0 + g) * embed + col] = acc[g] + s_part[g * kTailCols + (threadIdx.x & (kTailCols - 1))];
+    }
+}
+
+// Text tower input (model.py:340-342): x[row] = token_embedding[tokens[row]] + positional_embedding[row % ctx], fp32.
+// One warp per row, 16-byte accesses; ids outside [0, vocab) give NaN rows (the host wrapper rejects them first).
+__global__ void __launch_bounds__(256)
+text_embed_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ tok_emb, const float* __restrict__ pos,
+                  float* __restrict__ x, int64_t rows, int ctx, int width, int64_t vocab) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int64_t t = tokens[row];
+    const bool ok = t >= 0 && t < vocab;
+    const float4* e = reinterpret_cast<const float4*>(tok_emb + (ok ? t : 0) * width);
+    const float4* pe = reinterpret_cast<const float4*>(pos + (row % ctx) * width);
+    float4* xo = reinterpret_cast<float4*>(x + row * width);
+    const float nan = __int_as_float(0x7fc00000);
+    for (int i = lane; i < width / 4; i += 32) {
+        const float4 a = __ldg(e + i), q = __ldg(pe + i);
+        xo[i] = ok ? make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w) : make_float4(nan, nan, nan, nan);
     }
 }
 
@@ -1488,4 +1538,32 @@ extern "C" int eoe_attention(const void* qkv, void* out, int64_t B, int64_t L, i
                              void* stream) {
     if (!qkv || !out) return EOE_ERR_ARG;
     return attention_dispatch(qkv, out, B, L, heads, operand_dtype, (cudaStream_t)stream);
+}
+
+extern "C" int eoe_attention_causal(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int operand_dtype,
+                                    void* stream) {
+    if (!qkv || !out) return EOE_ERR_ARG;
+    if ((uintptr_t)qkv % 16 != 0) return EOE_ERR_ALIGN;
+    return attention_dispatch(qkv, out, B, L, heads, operand_dtype, (cudaStream_t)stream, nullptr, nullptr, nullptr, true);
+}
+
+extern "C" int eoe_text_embed(const int64_t* tokens, const float* token_embedding, const float* positional_embedding,
+                              float* x, int64_t n, int64_t ctx, int64_t width, int64_t vocab, void* stream) {
+    if (!tokens || !token_embedding || !positional_embedding || !x || n <= 0 || ctx <= 0 || vocab <= 0) return EOE_ERR_ARG;
+    if (width <= 0 || width % 4 != 0) return EOE_ERR_SHAPE;
+    if ((uintptr_t)token_embedding % 16 != 0 || (uintptr_t)positional_embedding % 16 != 0 || (uintptr_t)x % 16 != 0) return EOE_ERR_ALIGN;
+    const int64_t rows = n * ctx;
+    text_embed_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        tokens, token_embedding, positional_embedding, x, rows, (int)ctx, (int)width, vocab);
+    return check_launch("text_embed_kernel");
+}
+
+extern "C" int eoe_text_tail(const float* x, const int64_t* tokens, const float* ln_w, const float* ln_b, const float* proj,
+                             float* feats, int64_t n, int64_t ctx, int64_t width, int64_t embed, void* stream) {
+    if (!x || !tokens || !ln_w || !ln_b || !proj || !feats || n <= 0 || ctx <= 0) return EOE_ERR_ARG;
+    if (width <= 0 || width % 2 != 0 || embed <= 0 || width > 2048) return EOE_ERR_SHAPE;     // 4 rows of fp32 in static-limit shared memory
+    const dim3 grid((unsigned)((n + kTailImgs - 1) / kTailImgs), (unsigned)((embed + kTailCols - 1) / kTailCols));
+    tail_kernel<<<grid, 256, (kTailImgs * width + kTailImgs * kTailCols) * sizeof(float), (cudaStream_t)stream>>>(
+        x, ln_w, ln_b, proj, feats, n, (int)ctx, (int)width, (int)embed, tokens);
+    return check_launch("tail_kernel(text)");
 }

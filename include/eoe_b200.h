@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EOE_ABI_VERSION 3
+#define EOE_ABI_VERSION 4
 
 enum { EOE_F32 = 0, EOE_F16 = 1, EOE_BF16 = 2 };
 
@@ -283,6 +283,21 @@ int eoe_layernorm(const float* x, const float* w, const float* b, void* y, int o
  * model.py:171 in_proj layout), out [B*L, width] operand dtype */
 int eoe_attention(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int operand_dtype,
                   void* stream);
+
+/* ---- CLIP text tower building blocks (CLIP.encode_text, clip_official/clip/model.py:339-352; run once per class by
+ * ADClipTrainer.prepare_metric, training/clip.py:50-64).  The blocks between these calls are eoe_layernorm, eoe_gemm and
+ * eoe_attention_causal; eoe_b200/text_encoder.py composes them. ---- */
+/* eoe_attention with the text tower's causal mask (model.py:324-331: key j is visible to query i iff j <= i). L <= 208. */
+int eoe_attention_causal(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int operand_dtype,
+                         void* stream);
+/* x [n*ctx, width] fp32 = token_embedding[tokens] + positional_embedding (model.py:340-342).  tokens [n, ctx] int64;
+ * ids outside [0, vocab) produce NaN rows.  width % 4 == 0, fp32 pointers 16-byte aligned. */
+int eoe_text_embed(const int64_t* tokens, const float* token_embedding, const float* positional_embedding, float* x,
+                   int64_t n, int64_t ctx, int64_t width, int64_t vocab, void* stream);
+/* feats [n, embed] fp32 = ln_final(x[i, argmax_j tokens[i, j]]) @ text_projection [width, embed] (model.py:346-350;
+ * first position of the largest id, as torch.argmax).  All fp32. */
+int eoe_text_tail(const float* x, const int64_t* tokens, const float* ln_w, const float* ln_b, const float* proj,
+                  float* feats, int64_t n, int64_t ctx, int64_t width, int64_t embed, void* stream);
 
 #ifdef __cplusplus
 }

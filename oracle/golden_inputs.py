@@ -13,6 +13,8 @@ import torch
 
 VIT_WEIGHT_SEED = 1
 VIT_IMAGE_SEED = 3
+TEXT_WEIGHT_SEED = 6
+TEXT_TOKEN_SEED = 7
 AUC_CASES = ("f32_2000", "f16ties_2000", "few_distinct_5000", "tiny_9", "allties_64", "negzero_300")
 
 
@@ -99,3 +101,9 @@ def hash_name(name):
 def vit_images(B=2, res=224, seed=VIT_IMAGE_SEED):
     g = torch.Generator().manual_seed(seed)
     return torch.randn(B, 3, res, res, generator=g)
+
+
+def text_tokens(n=10, seed=TEXT_TOKEN_SEED):
+    """[n, 77] prompt rows shaped like `tokenize` output (leave-one-out prompt set of cfg2: 10 prompts)."""
+    from oracle import text as otext
+    return otext.synth_tokens(n, seed=seed)

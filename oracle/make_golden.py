@@ -10,6 +10,8 @@ are created from the reference's own code executed here on seeded synthetic inpu
              src/eoe/training/ad_trainer.py:453-454,517-521
   vit_*.npz  CLIP(...).encode_image (clip_official/clip/model.py:219-236,336-337) with the seeded
              weights of oracle.vit.synth_state_dict loaded into the reference module
+  text.npz   CLIP(...).encode_text (clip_official/clip/model.py:339-352) with the seeded weights of
+             oracle.text.synth_text_state_dict on seeded token rows
 Inputs are re-derived from seeds at test time (oracle.golden_inputs) so fixtures stay small;
 each file also stores input checksums so generator drift is detected, not silently accepted.
 """
@@ -17,7 +19,7 @@ import os
 import numpy as np
 import torch
 
-from oracle import _ref_import, golden_inputs as gi, vit
+from oracle import _ref_import, golden_inputs as gi, text as otext, vit
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -109,6 +111,19 @@ def make_vit(h):
                             img_sum=np.float64(imgs.double().sum()), w_sum=np.float64(w_sum))
 
 
+def make_text(h):
+    sd = otext.synth_text_state_dict(seed=gi.TEXT_WEIGHT_SEED)
+    tokens = gi.text_tokens()
+    m = h["CLIP"](512, 224, 2, 768, 32, 77, 49408, 512, 8, 12).eval()       # a 2-layer visual tower: unused here
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("visual.") or k == "logit_scale" for k in missing)
+    with torch.no_grad():
+        feats = m.encode_text(tokens).numpy()
+    w_sum = float(sum(v.double().sum() for v in sd.values()))
+    np.savez_compressed(os.path.join(OUT, "text.npz"), features=feats, tok_sum=np.int64(tokens.sum()),
+                        w_sum=np.float64(w_sum))
+
+
 def make_resize():
     """CLIP `_transform` head (clip.py:58-61) run by Pillow + torchvision on seeded images (tests/test_oracle_resize._img)."""
     from PIL import Image
@@ -133,6 +148,7 @@ def main():
     make_heads(h)
     make_auc()
     make_vit(h)
+    make_text(h)
     make_resize()
     print("golden fixtures written to", OUT)
 

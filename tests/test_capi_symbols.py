@@ -40,7 +40,7 @@ def test_python_binding_covers_header_and_loads():
     assert sorted(_lib.SIGNATURES) == _declared()
     l = _lib.lib()
     assert not _lib.MISSING
-    assert l.eoe_abi_version() == 3
+    assert l.eoe_abi_version() == _lib.EOE_ABI_VERSION
     assert l.eoe_strerror(0) == b"ok" and b"dtype" in l.eoe_strerror(-2)
     assert l.eoe_auc_workspace_bytes(1000) > 12 * 1000
     assert l.eoe_auc_workspace_bytes(0) == 0

@@ -132,6 +132,18 @@ def test_vit_oracle_matches_reference_fixture(golden_dir, patch):
     np.testing.assert_allclose(feats, g["features"], rtol=0, atol=2e-5)
 
 
+def test_text_oracle_matches_reference_fixture(golden_dir):
+    from oracle import text as otext
+    g = _load(golden_dir, "text.npz")
+    sd = otext.synth_text_state_dict(seed=gi.TEXT_WEIGHT_SEED)
+    tokens = gi.text_tokens()
+    assert int(g["tok_sum"]) == int(tokens.sum())
+    assert abs(float(g["w_sum"]) - float(sum(v.double().sum() for v in sd.values()))) < 1e-6
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    feats = otext.encode_text(sd, tokens).numpy()
+    np.testing.assert_allclose(feats, g["features"], rtol=0, atol=2e-5)
+
+
 def test_vit_flop_counts():
     assert abs(ovit.flops_per_image(32) / 1e9 - 8.818) < 1e-3
     assert abs(ovit.flops_per_image(16) / 1e9 - 35.127) < 1e-3

@@ -6,6 +6,7 @@ import torch
 
 from oracle import _ref_import
 from oracle import heads as oh
+from oracle import text as otext
 from oracle import vit as ovit
 
 pytestmark = pytest.mark.reference
@@ -127,3 +128,25 @@ def test_vit_live_small(ref):
             want = m(x)
         got = ovit.encode_image(sd, x)
         assert (want - got).abs().max().item() < 2e-5
+
+
+def test_text_live_small(ref):
+    """CLIP.encode_text (model.py:339-352) on a 2-layer, small-vocabulary tower; the 12-layer tower is pinned by
+    tests/golden/text.npz.  Rows cover the shortest prompt (<sot><eot>) and one that fills the context."""
+    sd = otext.synth_text_state_dict(seed=5, layers=2, vocab=1000)
+    m = ref["CLIP"](512, 224, 2, 768, 32, 77, 1000, 512, 8, 2).eval()
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("visual.") or k == "logit_scale" for k in missing)
+    tok = otext.synth_tokens(6, seed=2, vocab=1000)
+    assert tok[0].argmax() == 1 and tok[-1].argmax() == 76
+    with torch.no_grad():
+        want = m.encode_text(tok)
+    got = otext.encode_text(sd, tok)
+    assert (want - got).abs().max().item() < 2e-5
+    # a repeated maximum: argmax takes the first (the reference indexes with text.argmax(dim=-1))
+    tok2 = tok.clone()
+    tok2[2, 40] = 999
+    tok2[2, 50] = 999
+    with torch.no_grad():
+        want2 = m.encode_text(tok2)
+    assert (want2 - otext.encode_text(sd, tok2)).abs().max().item() < 2e-5
