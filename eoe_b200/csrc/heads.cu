@@ -523,9 +523,490 @@ clip_oe_loss_kernel(const T* __restrict__ z, const float* __restrict__ text, con
     grid_mean_finish<kHeadBlock>(loss_acc, ws, loss_out, inv_n);
 }
 
+// ------------------------------------------------------------------------------------------ CLIP score head on tensor cores
+// logits = z [n, d] @ T^T [d, K] is a dense contraction: at K = 10 / 30 the FP32-FMA kernel above needs 5 / 15 kFMA per row
+// and runs at 28 % / 12 % of HBM bandwidth.  Here a warp owns 16 rows and feeds them to mma.sync.m16n8k16 straight from
+// its coalesced 16-byte global loads -- no shared-memory staging of z at all: the k dimension of a dot product may be
+// permuted freely, so the four consecutive features a lane loads ARE its four k-slots (2t, 2t+1, 2t+8, 2t+9) of one
+// k-step, and the text rows are laid out once per CTA in the matching fragment order (one conflict-free LDS.128 per
+// (k-step, 8-prompt tile) yields the hi and lo B fragments).
+// Precision: products must carry ~1e-6 (logits are 100 * cos): fp32 features are split z = hi + lo (two bf16), unit text
+// rows t = hi + lo likewise, and acc += hi*hi + lo*hi + hi*lo in fp32 (the dropped lo*lo term is 2^-18 relative);
+// 16-bit features are exact operands and only the text is split.  Row norms are fp32 sums of the original values.
+template <typename T>
+struct ClipMma {
+    static constexpr bool kBF16 = !std::is_same<T, __half>::value;          // operand type: bf16 for fp32 / bf16 features
+    static constexpr bool kSplitA = std::is_same<T, float>::value;
+};
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t clip_pack2(float a, float b) {
+    if (BF16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ float2 clip_unpack2(uint32_t w) {
+    if (BF16) return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+    return __half22float2(*reinterpret_cast<__half2*>(&w));
+}
+template <bool BF16>
+__device__ __forceinline__ void clip_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if (BF16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// feature column of k-step j, lane quad position t, slot s (0..3): what the A-side loads below put into that k-slot
+template <typename T>
+__device__ __forceinline__ int clip_frag_col(int j, int t) {
+    if (sizeof(T) == 4) return 16 * j + 4 * t;                        // one 16-byte load = 4 fp32 = one k-step
+    return 32 * (j >> 1) + 8 * t + 4 * (j & 1);                      // one 16-byte load = 8 x 16 bit = two k-steps
+}
+
+// s_frag [d/16][NT][32] uint4 = {hi(s0,s1), hi(s2,s3), lo(s0,s1), lo(s2,s3)} of prompt nt*8 + lane/4 (zero rows past K)
+template <typename T, int NT>
+__device__ __forceinline__ void clip_stage_fragments(const float* __restrict__ text, int d, int K, bool renorm,
+                                                     uint4* s_frag, float* s_inv) {
+    constexpr bool BF = ClipMma<T>::kBF16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < NT * 8; k += (int)(blockDim.x >> 5)) {
+        float s = 0.f;
+        if (k < K && renorm)
+            for (int i = lane; i < d; i += 32) { const float v = __ldg(text + (int64_t)k * d + i); s += v * v; }
+        s = warp_sum(s);
+        if (lane == 0) s_inv[k] = (k < K) ? (renorm ? 1.0f / sqrtf(s) : 1.0f) : 0.f;
+    }
+    __syncthreads();
+    const int total = (d >> 4) * NT * 32;
+    for (int i = threadIdx.x; i < total; i += (int)blockDim.x) {
+        const int ln = i & 31, nt = (i >> 5) % NT, j = (i >> 5) / NT;
+        const int k = nt * 8 + (ln >> 2);
+        uint4 f = make_uint4(0u, 0u, 0u, 0u);
+        if (k < K) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(text + (int64_t)k * d + clip_frag_col<T>(j, ln & 3)));
+            const float inv = s_inv[k];
+            const float e[4] = {v.x * inv, v.y * inv, v.z * inv, v.w * inv};
+            f.x = clip_pack2<BF>(e[0], e[1]);
+            f.y = clip_pack2<BF>(e[2], e[3]);
+            const float2 h0 = clip_unpack2<BF>(f.x), h1 = clip_unpack2<BF>(f.y);
+            f.z = clip_pack2<BF>(e[0] - h0.x, e[1] - h0.y);
+            f.w = clip_pack2<BF>(e[2] - h1.x, e[3] - h1.y);
+        }
+        s_frag[i] = f;
+    }
+    __syncthreads();
+}
+
+// acc[nt][2r + e] += z[row r] . T[prompt nt*8 + 2t + e] over all d features (this lane's quarter of each row is summed by
+// the tensor core), ss[r] = this lane's share of sum z^2.  Rows g and g + 8 of the warp's 16-row tile.
+// KEEP: the rows are read again by the caller (loss backward): ask L2 to keep them (evict_last policy)
+template <typename T, int NT, bool KEEP = false>
+__device__ __forceinline__ void clip_forward_tile(const T* __restrict__ z, const int64_t (&row)[2], const bool (&ok)[2], int d,
+                                                  const uint4* s_frag, int lane, float (&acc)[NT][4], float (&ss)[2],
+                                                  uint64_t keep_policy = 0) {
+    constexpr bool BF = ClipMma<T>::kBF16;
+    constexpr bool SPLIT = ClipMma<T>::kSplitA;
+    const int t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    ss[0] = ss[1] = 0.f;
+    for (int c0 = 0; c0 < d; c0 += 128) {                       // 8 k-steps per batch: 8 KB (fp32) of loads in flight per warp
+        constexpr int LOADS = sizeof(T) == 4 ? 8 : 4;           // 16-byte loads per row per batch
+        uint4 raw[2][LOADS];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < LOADS; ++q) {
+                const int col = c0 + (sizeof(T) == 4 ? 16 * q + 4 * t : 32 * q + 8 * t);
+                if (!ok[r]) raw[r][q] = make_uint4(0u, 0u, 0u, 0u);
+                else if (KEEP)
+                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                                 : "=r"(raw[r][q].x), "=r"(raw[r][q].y), "=r"(raw[r][q].z), "=r"(raw[r][q].w)
+                                 : "l"(z + row[r] * d + col), "l"(keep_policy));
+                else
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(raw[r][q].x), "=r"(raw[r][q].y), "=r"(raw[r][q].z), "=r"(raw[r][q].w)
+                                 : "l"(z + row[r] * d + col));
+            }
+#pragma unroll
+        for (int js = 0; js < 8; ++js) {
+            uint32_t a_hi[4], a_lo[4];
+            if (SPLIT) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const uint4 w = raw[r][js];
+                    const float e[4] = {__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w)};
+                    ss[r] += (e[0] * e[0] + e[1] * e[1]) + (e[2] * e[2] + e[3] * e[3]);
+                    a_hi[r] = clip_pack2<true>(e[0], e[1]);
+                    a_hi[2 + r] = clip_pack2<true>(e[2], e[3]);
+                    const float2 h0 = clip_unpack2<true>(a_hi[r]), h1 = clip_unpack2<true>(a_hi[2 + r]);
+                    a_lo[r] = clip_pack2<true>(e[0] - h0.x, e[1] - h0.y);
+                    a_lo[2 + r] = clip_pack2<true>(e[2] - h1.x, e[3] - h1.y);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const uint4 w = raw[r][js >> 1];
+                    a_hi[r] = (js & 1) ? w.z : w.x;
+                    a_hi[2 + r] = (js & 1) ? w.w : w.y;
+                    const float2 f0 = clip_unpack2<BF>(a_hi[r]), f1 = clip_unpack2<BF>(a_hi[2 + r]);
+                    ss[r] += (f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y);
+                }
+            }
+            const uint4* fr = s_frag + ((size_t)((c0 >> 4) + js) * NT) * 32 + lane;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const uint4 f = fr[nt * 32];
+                clip_mma<BF>(acc[nt], a_hi, f.z, f.w);          // small terms first
+                if (SPLIT) clip_mma<BF>(acc[nt], a_lo, f.x, f.y);
+                clip_mma<BF>(acc[nt], a_hi, f.x, f.y);
+            }
+        }
+    }
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(kHeadBlock, 2)
+clip_score_mma_kernel(const T* __restrict__ z, const float* __restrict__ text, int64_t n, int d, int K, float scale,
+                      float* __restrict__ scores) {
+    extern __shared__ __align__(16) uint8_t s_clip_raw[];
+    uint4* s_frag = reinterpret_cast<uint4*>(s_clip_raw);
+    float* s_inv = reinterpret_cast<float*>(s_clip_raw + (size_t)(d >> 4) * NT * 32 * sizeof(uint4));
+    clip_stage_fragments<T, NT>(text, d, K, true, s_frag, s_inv);
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int64_t warp0 = (int64_t)blockIdx.x * kHeadWarps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kHeadWarps;
+    const int64_t tiles = (n + 15) >> 4;
+    const int k_last = K - 1;
+    for (int64_t tile = warp0; tile < tiles; tile += nwarps) {
+        const int64_t row[2] = {tile * 16 + g, tile * 16 + g + 8};
+        const bool ok[2] = {row[0] < n, row[1] < n};
+        float acc[NT][4];
+        float ss[2];
+        clip_forward_tile<T, NT>(z, row, ok, d, s_frag, lane, acc, ss);
+        // rows g (accumulator slots 0, 1) and g + 8 (slots 2, 3): prompt nt*8 + 2t + e lives in this lane
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float s = ss[r];
+            s += __shfl_xor_sync(kFullMask, s, 1);
+            s += __shfl_xor_sync(kFullMask, s, 2);
+            const float inv = scale / sqrtf(s);
+            float mx = -INFINITY, last = 0.f;
+            float l[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = nt * 8 + 2 * t + e;
+                    l[nt][e] = (k < K) ? acc[nt][2 * r + e] * inv : -INFINITY;     // logit_k = scale * z^ . T^_k
+                    mx = fmaxf(mx, l[nt][e]);
+                    if (k == k_last) last = l[nt][e];
+                }
+            mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, 2));
+            float se = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) se += expf(l[nt][0] - mx) + expf(l[nt][1] - mx);   // NaN logits stick here
+            se += __shfl_xor_sync(kFullMask, se, 1);
+            se += __shfl_xor_sync(kFullMask, se, 2);
+            last = __shfl_sync(kFullMask, last, (lane & ~3) | ((k_last & 7) >> 1));
+            if (t == 0 && ok[r]) scores[row[r]] = expf(last - mx) / se;
+        }
+    }
+}
+
+// ---- CLIP OE loss + backward on tensor cores (clip.py:81-103).  Forward as above (text rows used as given).  Backward:
+// g = scale * G @ C is the second small GEMM; the forward accumulator layout (row g / g+8, prompts nt*8 + 2t + e) IS the
+// A-fragment layout of a k-step over prompts, so G goes from registers straight back into mma.sync.  The output tile's
+// n index is mapped to feature columns such that every lane ends up with the same 16-byte run of columns it loads z in
+// (clip_out_col), and g . z^ = sum_k G_k logit_k needs no pass over g:  dz = (g - (sum_k G_k l_k) z^) / ||z||.
+constexpr int kClipLossBlock = 512;
+
+template <typename T>
+__device__ __forceinline__ int clip_out_col(int ct, int nn) {       // feature column of output tile ct, tile column nn
+    if (sizeof(T) == 4) return 16 * (ct >> 1) + 4 * (nn >> 1) + 2 * (ct & 1) + (nn & 1);
+    return 32 * (ct >> 2) + 8 * (nn >> 1) + 2 * (ct & 3) + (nn & 1);
+}
+
+// s_fragT [d/8][KS][32] uint4 = B fragments (k = prompt, n = feature) {hi b0, hi b1, lo b0, lo b1}
+template <typename T, int KS>
+__device__ __forceinline__ void clip_stage_fragments_bwd(const float* __restrict__ text, int d, int K, uint4* s_fragT) {
+    constexpr bool BF = ClipMma<T>::kBF16;
+    const int total = (d >> 3) * KS * 32;
+    for (int i = threadIdx.x; i < total; i += (int)blockDim.x) {
+        const int ln = i & 31, ks = (i >> 5) % KS, ct = (i >> 5) / KS;
+        const int col = clip_out_col<T>(ct, ln >> 2);
+        const int k0 = 16 * ks + 2 * (ln & 3);
+        float e[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + (q & 1) + (q >> 1) * 8;
+            e[q] = (k < K) ? __ldg(text + (int64_t)k * d + col) : 0.f;
+        }
+        uint4 f;
+        f.x = clip_pack2<BF>(e[0], e[1]);
+        f.y = clip_pack2<BF>(e[2], e[3]);
+        const float2 h0 = clip_unpack2<BF>(f.x), h1 = clip_unpack2<BF>(f.y);
+        f.z = clip_pack2<BF>(e[0] - h0.x, e[1] - h0.y);
+        f.w = clip_pack2<BF>(e[2] - h1.x, e[3] - h1.y);
+        s_fragT[i] = f;
+    }
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(kClipLossBlock, 1)
+clip_oe_loss_mma_kernel(const T* __restrict__ z, const float* __restrict__ text, const int64_t* __restrict__ labels,
+                        int64_t n, int d, int K, float scale, int64_t nominal_label, int loo, T* __restrict__ grad,
+                        HeadWorkspace* ws, float* loss_out, float inv_n_f, double inv_n) {
+    constexpr bool BF = ClipMma<T>::kBF16;
+    constexpr int KS = (NT + 1) / 2;                                // k-steps of 16 prompts in the backward product
+    constexpr int GROUP = sizeof(T) == 4 ? 2 : 4;                    // output tiles (8 columns each) per 16-byte run of a lane
+    extern __shared__ __align__(16) uint8_t s_clip_raw[];
+    uint4* s_frag = reinterpret_cast<uint4*>(s_clip_raw);
+    uint4* s_fragT = s_frag + (size_t)(d >> 4) * NT * 32;
+    float* s_inv = reinterpret_cast<float*>(s_fragT + (size_t)(grad ? (d >> 3) * KS * 32 : 0));
+    clip_stage_fragments<T, NT>(text, d, K, false, s_frag, s_inv);
+    if (grad) clip_stage_fragments_bwd<T, KS>(text, d, K, s_fragT);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int wpb = kClipLossBlock / 32;
+    const int64_t warp0 = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
+    const int64_t tiles = (n + 15) >> 4;
+    const int64_t anom_label = 1 - nominal_label;
+    float loss_acc = 0.f;
+    // L2 policies: the forward pass asks L2 to keep the tile (it is read again ~10 us later by the backward pass), the
+    // second read and the gradient stores are marked evict_first so that they do not push waiting tiles out
+    uint64_t pol_keep, pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    for (int64_t tile = warp0; tile < tiles; tile += nwarps) {
+        const int64_t row[2] = {tile * 16 + g, tile * 16 + g + 8};
+        const bool ok[2] = {row[0] < n, row[1] < n};
+        float acc[NT][4];
+        float ss[2];
+        if (grad) clip_forward_tile<T, NT, true>(z, row, ok, d, s_frag, lane, acc, ss, pol_keep);
+        else clip_forward_tile<T, NT>(z, row, ok, d, s_frag, lane, acc, ss);
+        uint32_t a_hi[KS][4], a_lo[KS][4];
+        float gdz[2], osc[2];                                        // (g . z^) / ||z||  and  1 / (n ||z||) per row
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float s = ss[r];
+            s += __shfl_xor_sync(kFullMask, s, 1);
+            s += __shfl_xor_sync(kFullMask, s, 2);
+            const float inv_nrm = 1.0f / sqrtf(s);
+            const float sc = scale * inv_nrm;
+            float l[NT][2];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    l[nt][e] = (nt * 8 + 2 * t + e < K) ? acc[nt][2 * r + e] * sc : -INFINITY;    // logit_k = scale * z^ . c_k
+                    mx = fmaxf(mx, l[nt][e]);
+                }
+            mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, 2));
+            float pr[NT][2];
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                pr[nt][0] = expf(l[nt][0] - mx);
+                pr[nt][1] = expf(l[nt][1] - mx);
+                sum += pr[nt][0] + pr[nt][1];
+            }
+            sum += __shfl_xor_sync(kFullMask, sum, 1);
+            sum += __shfl_xor_sync(kFullMask, sum, 2);
+            const float lse = mx + logf(sum);
+            const int64_t lab = ok[r] ? labels[row[r]] : 0;
+            // argmax over k < K-1, first maximal index (clip.py:95) -- evaluated by every lane: the shuffles below must
+            // not sit inside the per-row label branch (rows of one warp carry different labels)
+            int loo_t = 0;
+            if (loo) {
+                float best = -INFINITY;
+                int bi = 0x7fffffff;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int k = nt * 8 + 2 * t + e;
+                        if (k < K - 1 && (l[nt][e] > best || bi == 0x7fffffff)) { best = l[nt][e]; bi = k; }
+                    }
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const float ob = __shfl_xor_sync(kFullMask, best, o);
+                    const int oi = __shfl_xor_sync(kFullMask, bi, o);
+                    if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+                }
+                loo_t = bi == 0x7fffffff ? 0 : bi;
+            }
+            int tg = -1;
+            if (ok[r] && lab == anom_label) tg = K - 1;
+            else if (ok[r] && lab == nominal_label) tg = loo_t;
+            float lt = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (nt * 8 + 2 * t + e == tg) lt = l[nt][e];
+            lt = __shfl_sync(kFullMask, lt, (lane & ~3) | (((tg < 0 ? 0 : tg) & 7) >> 1));
+            if (tg >= 0 && t == 0) loss_acc += lse - lt;
+            // G_k = softmax_k - [k == t] (x scale as the operand; 1/n is applied to the result), gd = sum_k G_k l_k
+            float gd = 0.f;
+            float G[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = nt * 8 + 2 * t + e;
+                    const float gk = (tg >= 0 && k < K) ? (pr[nt][e] / sum - (k == tg ? 1.f : 0.f)) : 0.f;
+                    if (tg >= 0 && k < K) gd += gk * l[nt][e];
+                    G[nt][e] = gk * scale;
+                }
+            gd += __shfl_xor_sync(kFullMask, gd, 1);
+            gd += __shfl_xor_sync(kFullMask, gd, 2);
+            gdz[r] = gd * inv_nrm;
+            osc[r] = inv_nrm * inv_n_f;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {                     // prompts 16ks + 2t + e (a0 / a1) and + 8 (a2 / a3)
+                    const int nt = 2 * ks + hf;
+                    const float g0 = nt < NT ? G[nt < NT ? nt : 0][0] : 0.f, g1 = nt < NT ? G[nt < NT ? nt : 0][1] : 0.f;
+                    const uint32_t hi = clip_pack2<BF>(g0, g1);
+                    const float2 hv = clip_unpack2<BF>(hi);
+                    a_hi[ks][2 * hf + r] = hi;
+                    a_lo[ks][2 * hf + r] = clip_pack2<BF>(g0 - hv.x, g1 - hv.y);
+                }
+            }
+        }
+        if (!grad) continue;
+        // pass 2: per 16-byte run of columns, g = G @ C on the tensor core, z again (L2), dz out
+        const int runs = d / (8 * GROUP);
+#pragma unroll 2
+        for (int q = 0; q < runs; ++q) {
+            uint4 zr[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int col = q * 8 * GROUP + (sizeof(T) == 4 ? 4 : 8) * t;
+                if (ok[r])
+                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                                 : "=r"(zr[r].x), "=r"(zr[r].y), "=r"(zr[r].z), "=r"(zr[r].w)
+                                 : "l"(z + row[r] * d + col), "l"(pol_stream));
+                else zr[r] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            float c[GROUP][4];
+#pragma unroll
+            for (int i = 0; i < GROUP; ++i) {
+                c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+                const uint4* fr = s_fragT + ((size_t)(q * GROUP + i) * KS) * 32 + lane;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint4 f = fr[ks * 32];
+                    clip_mma<BF>(c[i], a_hi[ks], f.z, f.w);
+                    clip_mma<BF>(c[i], a_lo[ks], f.x, f.y);
+                    clip_mma<BF>(c[i], a_hi[ks], f.x, f.y);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (!ok[r]) continue;
+                const int col = q * 8 * GROUP + (sizeof(T) == 4 ? 4 : 8) * t;
+                if (sizeof(T) == 4) {
+                    const float zv[4] = {__uint_as_float(zr[r].x), __uint_as_float(zr[r].y), __uint_as_float(zr[r].z), __uint_as_float(zr[r].w)};
+                    float o[4];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) o[2 * i + e] = (c[i][2 * r + e] - gdz[r] * zv[2 * i + e]) * osc[r];
+                    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                                 :: "l"(grad + row[r] * d + col), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "l"(pol_stream) : "memory");
+                } else {
+                    const uint32_t zw[4] = {zr[r].x, zr[r].y, zr[r].z, zr[r].w};
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 zv = clip_unpack2<BF>(zw[i]);
+                        ow[i] = clip_pack2<BF>((c[i & (GROUP - 1)][2 * r] - gdz[r] * zv.x) * osc[r],
+                                               (c[i & (GROUP - 1)][2 * r + 1] - gdz[r] * zv.y) * osc[r]);
+                    }
+                    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+                                 :: "l"(grad + row[r] * d + col), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "l"(pol_stream) : "memory");
+                }
+            }
+        }
+    }
+    grid_mean_finish<kClipLossBlock>(loss_acc, ws, loss_out, inv_n);
+}
+
+template <typename T>
+static int clip_loss_mma_launch(const void* z, const float* text, const int64_t* labels, int64_t n, int64_t d, int64_t K,
+                                float scale, int64_t nominal, int loo, float* loss_out, void* grad, void* ws,
+                                cudaStream_t st) {
+    const int nt = (int)((K + 7) / 8), ks = (nt + 1) / 2;
+    const size_t smem = (size_t)(d / 16) * nt * 512 + (grad ? (size_t)(d / 8) * ks * 512 : 0) + 32 * sizeof(float);
+    const int64_t tiles = (n + 15) / 16;
+    const int wpb = kClipLossBlock / 32;
+    int grid = (int)((tiles + wpb - 1) / wpb);
+    if (grid > kNumSMs) grid = kNumSMs;
+    const float inv_n_f = 1.0f / (float)n;
+    const double inv_n = 1.0 / (double)n;
+#define EOE_CLIPL_MMA_CASE(NT)                                                                           \
+    {                                                                                                    \
+        auto kern = clip_oe_loss_mma_kernel<T, NT>;                                                      \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) { set_cuda_error(e, "clip_oe_loss_mma smem attr"); return EOE_ERR_CUDA; }  \
+        kern<<<grid, kClipLossBlock, smem, st>>>((const T*)z, text, labels, n, (int)d, (int)K, scale, nominal, loo, \
+                                                 (T*)grad, (HeadWorkspace*)ws, loss_out, inv_n_f, inv_n); \
+    }
+    if (nt == 1) EOE_CLIPL_MMA_CASE(1)
+    else if (nt == 2) EOE_CLIPL_MMA_CASE(2)
+    else if (nt == 3) EOE_CLIPL_MMA_CASE(3)
+    else EOE_CLIPL_MMA_CASE(4)
+#undef EOE_CLIPL_MMA_CASE
+    return check_launch("clip_oe_loss_mma_kernel");
+}
+
+template <typename T>
+static bool clip_mma_ok(const void* z, const float* text, int64_t n, int64_t d, int64_t K) {
+    return n >= 2048 && d % 128 == 0 && d <= 1024 && K >= 1 && K <= 32 && (uintptr_t)z % 16 == 0 && (uintptr_t)text % 16 == 0;
+}
+
+template <typename T>
+static int clip_score_mma_launch(const void* z, const float* text, int64_t n, int64_t d, int64_t K, float scale,
+                                 float* scores, cudaStream_t st) {
+    const int nt = (int)((K + 7) / 8);
+    const size_t smem = (size_t)(d / 16) * nt * 32 * sizeof(uint4) + 32 * sizeof(float);
+    const int64_t tiles = (n + 15) / 16;
+    int grid = (int)((tiles + kHeadWarps - 1) / kHeadWarps);
+    if (grid > kNumSMs * 2) grid = kNumSMs * 2;
+#define EOE_CLIP_MMA_CASE(NT)                                                                            \
+    {                                                                                                    \
+        auto kern = clip_score_mma_kernel<T, NT>;                                                        \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) { set_cuda_error(e, "clip_score_mma smem attr"); return EOE_ERR_CUDA; }    \
+        kern<<<grid, kHeadBlock, smem, st>>>((const T*)z, text, n, (int)d, (int)K, scale, scores);       \
+    }
+    if (nt == 1) EOE_CLIP_MMA_CASE(1)
+    else if (nt == 2) EOE_CLIP_MMA_CASE(2)
+    else if (nt == 3) EOE_CLIP_MMA_CASE(3)
+    else EOE_CLIP_MMA_CASE(4)
+#undef EOE_CLIP_MMA_CASE
+    return check_launch("clip_score_mma_kernel");
+}
+
 template <typename T>
 static int clip_score_launch(const void* z, const float* text, int64_t n, int64_t d, int64_t K, float scale,
                              float* scores, cudaStream_t st) {
+    if (clip_mma_ok<T>(z, text, n, d, K)) return clip_score_mma_launch<T>(z, text, n, d, K, scale, scores, st);
     const int iters = (int)((d / 4 + 31) / 32);
     const int it_pad = iters <= 2 ? 2 : (iters <= 4 ? 4 : 8);
     const size_t smem = (size_t)K * it_pad * 128 * sizeof(float);
@@ -549,6 +1030,8 @@ template <typename T>
 static int clip_loss_launch(const void* z, const float* text, const int64_t* labels, int64_t n, int64_t d,
                             int64_t K, float scale, int64_t nominal, int loo, float* loss_out, void* grad,
                             void* ws, cudaStream_t st) {
+    if (clip_mma_ok<T>(z, text, n, d, K) && (uintptr_t)grad % 16 == 0 && d <= 512)
+        return clip_loss_mma_launch<T>(z, text, labels, n, d, K, scale, nominal, loo, loss_out, grad, ws, st);
     const int iters = (int)((d / 4 + 31) / 32);
     const int it_pad = iters <= 2 ? 2 : (iters <= 4 ? 4 : 8);
     const size_t smem = (size_t)K * it_pad * 128 * sizeof(float);

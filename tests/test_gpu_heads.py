@@ -146,6 +146,80 @@ def test_clip_vs_oracle(n, d, K, dtype):
         _close(_np(zz.grad), oh.clip_oe_grad(zq, y, cu, 0, loo), rtol=gtol, atol=1e-5)
 
 
+@pytest.mark.parametrize("n,d,K", [(2048, 512, 2), (4099, 512, 10), (5000, 512, 30), (2050, 512, 32), (3001, 1024, 17),
+                                   (2100, 128, 9), (2048, 256, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_clip_score_tensor_core_path_vs_oracle(n, d, K, dtype):
+    """n >= 2048, d % 128 == 0, K <= 32: clip_score_mma_kernel (mma.sync, hi/lo split operands).  Same 1e-3 bar on the
+    scores as the FP32-FMA kernel, including far-tail scores (atol 1e-30): the split must keep the logits to ~1e-4."""
+    from eoe_b200 import ops
+    rng = np.random.default_rng(n + d + K)
+    z = rng.standard_normal((n, d)).astype(np.float32) * rng.uniform(0.01, 30.0, (n, 1)).astype(np.float32)
+    c = (rng.standard_normal((K, d)) * 1.7).astype(np.float32)      # non-unit: the score path must renormalise
+    z[: n // 3] += 0.2 * np.sqrt(d) * c[rng.integers(0, K, n // 3)]    # some prompts win clearly: scores down to ~1e-10
+    zt = _t(z, dtype)
+    zq = _np(zt)
+    got = _np(ops.clip_score(zt, _t(c)))
+    want = oh.clip_score(zq, c)
+    _close(got, want, rtol=1e-3, atol=1e-30)
+    # the small-n kernel (FP32 FMA) on a slice gives the same scores
+    _close(_np(ops.clip_score(zt[:100].contiguous(), _t(c))), got[:100], rtol=1e-3, atol=1e-30)
+
+
+@pytest.mark.parametrize("n,d,K", [(2048, 512, 2), (4099, 512, 10), (5000, 512, 30), (2050, 256, 32), (2100, 128, 17)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("loo", [False, True])
+def test_clip_oe_loss_tensor_core_path_vs_oracle(n, d, K, dtype, loo):
+    """clip_oe_loss_mma_kernel (forward and backward products on mma.sync): loss 1e-4, gradients at the FP32-FMA kernel's
+    bars.  Leave-one-out rows whose two best nominal logits are closer than 1e-3 are excluded from the gradient check: the
+    argmax target (clip.py:95) may legitimately differ between two roundings of the same logits."""
+    from eoe_b200 import ops
+    rng = np.random.default_rng(n + d + K + loo)
+    z = rng.standard_normal((n, d)).astype(np.float32) * rng.uniform(0.05, 20.0, (n, 1)).astype(np.float32)
+    cu = rng.standard_normal((K, d)).astype(np.float32)
+    cu = (cu / np.linalg.norm(cu, axis=1, keepdims=True)).astype(np.float32)
+    z[: n // 3] += 0.1 * np.sqrt(d) * cu[rng.integers(0, K, n // 3)] * np.linalg.norm(z[: n // 3], axis=1, keepdims=True) / np.sqrt(d)
+    y = rng.integers(0, 2, n)
+    y[5] = 2                                             # label outside {0,1}: contributes 0 (clip.py:90-92)
+    zt = _t(z, dtype)
+    zq = _np(zt)
+    for nom in (0, 1):
+        zz = zt.clone().requires_grad_(True)
+        loss = ops.clip_oe_loss(zz, _t(y), _t(cu), nominal_label=nom, leave_one_out=loo)
+        loss.backward()
+        _close(loss.item(), oh.clip_oe_loss(zq, y, cu, nom, loo), rtol=1e-4)
+        got, want = _np(zz.grad), oh.clip_oe_grad(zq, y, cu, nom, loo)
+        keep = np.ones(n, bool)
+        if loo and K > 2:
+            lg = np.sort(oh.clip_logits(zq, cu, False, 100.0)[:, : K - 1], axis=1)
+            keep = (lg[:, -1] - lg[:, -2]) > 1e-3
+            assert keep.mean() > 0.99
+        assert np.all(got[5] == 0)
+        gtol = 2e-3 if dtype == torch.float32 else 2e-2
+        _close(got[keep], want[keep], rtol=gtol, atol=1e-5 / n * 128)
+        # loss only (no gradient buffer) takes the same forward
+        l2, g2 = ops.clip_oe_fused(zt, _t(y), _t(cu), nom, loo, want_grad=False)
+        assert g2 is None and l2.item() == loss.item()
+
+
+def test_clip_score_tensor_core_path_special_rows():
+    """NaN / Inf / zero rows give NaN scores (z / ||z|| in the reference, clip.py:70), neighbours are untouched."""
+    from eoe_b200 import ops
+    rng = np.random.default_rng(3)
+    n, d, K = 2048 + 5, 512, 10
+    z = rng.standard_normal((n, d)).astype(np.float32)
+    c = rng.standard_normal((K, d)).astype(np.float32)
+    z[7, 100] = np.nan
+    z[8, 5] = np.inf
+    z[24] = 0.0
+    z[n - 1, 511] = np.nan
+    got = _np(ops.clip_score(_t(z), _t(c)))
+    bad = np.zeros(n, bool)
+    bad[[7, 8, 24, n - 1]] = True
+    assert np.isnan(got[bad]).all() and np.isfinite(got[~bad]).all()
+    _close(got[~bad], oh.clip_score(z[~bad], c), rtol=1e-3, atol=1e-30)
+
+
 def test_bad_arguments_raise():
     from eoe_b200 import _lib, ops
     with pytest.raises(_lib.EoeError):
