@@ -77,7 +77,8 @@ __device__ __forceinline__ HscRow row_math(float sumsq, bool nominal, float inv_
     return r;
 }
 
-template <typename T, int VEC, int ITERS, int ROWS, int MODE>
+// GRAD = false (score only, grad == nullptr): nothing outlives the reduction pass, so the rows need not stay in registers.
+template <typename T, int VEC, int ITERS, int ROWS, int MODE, bool GRAD = true>
 __global__ void __launch_bounds__(kHeadBlock)
 hsc_rows_kernel(const T* __restrict__ z, const int64_t* __restrict__ labels, int64_t n, int d,
                 int64_t nominal_label, float* __restrict__ scores, T* __restrict__ grad,
@@ -131,7 +132,7 @@ hsc_rows_kernel(const T* __restrict__ z, const int64_t* __restrict__ labels, int
                 if (scores) scores[row] = h.score;
                 loss_acc += h.loss;
             }
-            if (grad) {
+            if (GRAD && grad) {
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) {
                     const int vi = it * 32 + lane;
@@ -206,12 +207,14 @@ static int hsc_launch(const void* z_, const int64_t* labels, int64_t n, int64_t 
     }
     const int iters = (int)((d / VEC + 31) / 32);
 #define EOE_HSC_CASE(IT, RW)                                                                           \
-    hsc_rows_kernel<T, VEC, IT, RW, MODE><<<head_grid(n, kHeadWarps * RW), kHeadBlock, 0, st>>>(        \
+    if (grad) hsc_rows_kernel<T, VEC, IT, RW, MODE, true><<<head_grid(n, kHeadWarps * RW), kHeadBlock, 0, st>>>(     \
+        z, labels, n, (int)d, nominal, scores, grad, ws, loss_out, inv_n_f, inv_n, center);            \
+    else hsc_rows_kernel<T, VEC, IT, RW, MODE, false><<<head_grid(n, kHeadWarps * RW), kHeadBlock, 0, st>>>(         \
         z, labels, n, (int)d, nominal, scores, grad, ws, loss_out, inv_n_f, inv_n, center)
-    if (iters <= 1) EOE_HSC_CASE(1, 4);
-    else if (iters <= 2) EOE_HSC_CASE(2, VEC == 4 ? 4 : 2);
-    else if (iters <= 4) EOE_HSC_CASE(4, VEC == 4 ? 2 : 1);
-    else EOE_HSC_CASE(8, 1);
+    if (iters <= 1) { EOE_HSC_CASE(1, 4); }
+    else if (iters <= 2) { EOE_HSC_CASE(2, VEC == 4 ? 4 : 2); }
+    else if (iters <= 4) { EOE_HSC_CASE(4, VEC == 4 ? 2 : 1); }
+    else { EOE_HSC_CASE(8, 1); }
 #undef EOE_HSC_CASE
     return check_launch("hsc_rows_kernel");
 }
@@ -890,56 +893,63 @@ clip_oe_loss_mma_kernel(const T* __restrict__ z, const float* __restrict__ text,
         }
         if (!grad) continue;
         // pass 2: per 16-byte run of columns, g = G @ C on the tensor core, z again (L2), dz out
-        const int runs = d / (8 * GROUP);
-#pragma unroll 2
-        for (int q = 0; q < runs; ++q) {
-            uint4 zr[2];
+        const int runs = d / (8 * GROUP);                          // d % 128 == 0: a multiple of QB
+        constexpr int QB = 4;                                        // runs whose z loads are in flight together
+        for (int q0 = 0; q0 < runs; q0 += QB) {
+            uint4 zr[QB][2];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int col = q * 8 * GROUP + (sizeof(T) == 4 ? 4 : 8) * t;
-                if (ok[r])
-                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                                 : "=r"(zr[r].x), "=r"(zr[r].y), "=r"(zr[r].z), "=r"(zr[r].w)
-                                 : "l"(z + row[r] * d + col), "l"(pol_stream));
-                else zr[r] = make_uint4(0u, 0u, 0u, 0u);
-            }
-            float c[GROUP][4];
+            for (int qq = 0; qq < QB; ++qq)
 #pragma unroll
-            for (int i = 0; i < GROUP; ++i) {
-                c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
-                const uint4* fr = s_fragT + ((size_t)(q * GROUP + i) * KS) * 32 + lane;
-#pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
-                    const uint4 f = fr[ks * 32];
-                    clip_mma<BF>(c[i], a_hi[ks], f.z, f.w);
-                    clip_mma<BF>(c[i], a_lo[ks], f.x, f.y);
-                    clip_mma<BF>(c[i], a_hi[ks], f.x, f.y);
+                for (int r = 0; r < 2; ++r) {
+                    const int col = (q0 + qq) * 8 * GROUP + (sizeof(T) == 4 ? 4 : 8) * t;
+                    if (ok[r])
+                        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                                     : "=r"(zr[qq][r].x), "=r"(zr[qq][r].y), "=r"(zr[qq][r].z), "=r"(zr[qq][r].w)
+                                     : "l"(z + row[r] * d + col), "l"(pol_stream));
+                    else zr[qq][r] = make_uint4(0u, 0u, 0u, 0u);
                 }
-            }
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (!ok[r]) continue;
-                const int col = q * 8 * GROUP + (sizeof(T) == 4 ? 4 : 8) * t;
-                if (sizeof(T) == 4) {
-                    const float zv[4] = {__uint_as_float(zr[r].x), __uint_as_float(zr[r].y), __uint_as_float(zr[r].z), __uint_as_float(zr[r].w)};
-                    float o[4];
+            for (int qq = 0; qq < QB; ++qq) {
+                const int q = q0 + qq;
+                float c[GROUP][4];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)
+                for (int i = 0; i < GROUP; ++i) {
+                    c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+                    const uint4* fr = s_fragT + ((size_t)(q * GROUP + i) * KS) * 32 + lane;
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) o[2 * i + e] = (c[i][2 * r + e] - gdz[r] * zv[2 * i + e]) * osc[r];
-                    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
-                                 :: "l"(grad + row[r] * d + col), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "l"(pol_stream) : "memory");
-                } else {
-                    const uint32_t zw[4] = {zr[r].x, zr[r].y, zr[r].z, zr[r].w};
-                    uint32_t ow[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 zv = clip_unpack2<BF>(zw[i]);
-                        ow[i] = clip_pack2<BF>((c[i & (GROUP - 1)][2 * r] - gdz[r] * zv.x) * osc[r],
-                                               (c[i & (GROUP - 1)][2 * r + 1] - gdz[r] * zv.y) * osc[r]);
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const uint4 f = fr[ks * 32];
+                        clip_mma<BF>(c[i], a_hi[ks], f.z, f.w);
+                        clip_mma<BF>(c[i], a_lo[ks], f.x, f.y);
+                        clip_mma<BF>(c[i], a_hi[ks], f.x, f.y);
                     }
-                    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
-                                 :: "l"(grad + row[r] * d + col), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "l"(pol_stream) : "memory");
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (!ok[r]) continue;
+                    const int col = q * 8 * GROUP + (sizeof(T) == 4 ? 4 : 8) * t;
+                    const uint4 zq = zr[qq][r];
+                    if (sizeof(T) == 4) {
+                        const float zv[4] = {__uint_as_float(zq.x), __uint_as_float(zq.y), __uint_as_float(zq.z), __uint_as_float(zq.w)};
+                        float o[4];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) o[2 * i + e] = (c[i][2 * r + e] - gdz[r] * zv[2 * i + e]) * osc[r];
+                        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                                     :: "l"(grad + row[r] * d + col), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "l"(pol_stream) : "memory");
+                    } else {
+                        const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 zv = clip_unpack2<BF>(zw[i]);
+                            ow[i] = clip_pack2<BF>((c[i & (GROUP - 1)][2 * r] - gdz[r] * zv.x) * osc[r],
+                                                   (c[i & (GROUP - 1)][2 * r + 1] - gdz[r] * zv.y) * osc[r]);
+                        }
+                        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+                                     :: "l"(grad + row[r] * d + col), "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3]), "l"(pol_stream) : "memory");
+                    }
                 }
             }
         }
