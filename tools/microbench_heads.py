@@ -80,6 +80,27 @@ def main():
         s16 = s.half()
         med, best = timeit(lambda: metrics.roc_auc_device(s16, y, workspace=ws), flush=flush)
         out.append(dict(kernel="auc_f16ties", n=n, ms=med, best_ms=best, ms_per_1m=med * 1e6 / n))
+    # CLIP text tower (prepare_metric, once per class): K prompts of 77 tokens through 12 blocks of width 512
+    from eoe_b200.text_encoder import ClipTextEncoder
+    g = torch.Generator().manual_seed(0)
+    sd = {"token_embedding.weight": torch.randn(49408, 512, generator=g) * 0.02, "positional_embedding": torch.randn(77, 512, generator=g) * 0.01,
+          "ln_final.weight": torch.ones(512), "ln_final.bias": torch.zeros(512), "text_projection": torch.randn(512, 512, generator=g) * 512 ** -0.5}
+    for i in range(12):
+        p = f"transformer.resblocks.{i}."
+        for nm, shp, std in (("attn.in_proj_weight", (1536, 512), 512 ** -0.5), ("attn.out_proj.weight", (512, 512), 0.01),
+                             ("mlp.c_fc.weight", (2048, 512), 0.03), ("mlp.c_proj.weight", (512, 2048), 0.01)):
+            sd[p + nm] = torch.randn(*shp, generator=g) * std
+        for nm, k in (("attn.in_proj_bias", 1536), ("attn.out_proj.bias", 512), ("mlp.c_fc.bias", 2048), ("mlp.c_proj.bias", 512),
+                      ("ln_1.bias", 512), ("ln_2.bias", 512)):
+            sd[p + nm] = torch.zeros(k)
+        sd[p + "ln_1.weight"], sd[p + "ln_2.weight"] = torch.ones(512), torch.ones(512)
+    enc = ClipTextEncoder(sd, device=dev)
+    for K in (2, 10, 30):
+        tok = torch.zeros(K, 77, dtype=torch.int64)
+        tok[:, 0], tok[:, 1:6], tok[:, 6] = 49406, 1000, 49407
+        tok = tok.to(dev)
+        med, best = timeit(lambda: enc(tok))
+        out.append(dict(kernel="text_tower", prompts=K, ms=med, best_ms=best, launches=2 + 12 * 7))
     for o in out:
         print(json.dumps(o))
 
