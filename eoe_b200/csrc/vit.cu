@@ -795,12 +795,15 @@ static int attention_tc_launch(const CUtensorMap& tm_qkv, void* out, int64_t B, 
         tm_o128 = &l128;
         tm_o72 = &l72;
     }
-    auto kern = attn::attention_tc_kernel<BF16, 197>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // bf16: key-split softmax (S in two halves, the tensor pipe works under the softmax); diagnostics bit 7 selects the
+    // single-pass form for A/B timing.  fp16 probabilities need the exact row maximum and keep the two-pass form.
+    const bool split = BF16 && !(g_gemm_debug & 128);
+    auto kern = split ? attn::attention_tc_kernel<BF16, 197, BF16> : attn::attention_tc_kernel<BF16, 197, false>;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[split]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::SMEM_BYTES);
         if (e != cudaSuccess) { set_cuda_error(e, "attention_tc smem attr"); return EOE_ERR_CUDA; }
-        attr_done = true;
+        attr_done[split] = true;
     }
     const int64_t items = B * heads;
     const int grid = (int)(items < 2 * (int64_t)num_sms() ? items : 2 * (int64_t)num_sms());

@@ -14,7 +14,7 @@ python bench.py > gpurun_out/bench_${tag}_b16.json 2> gpurun_out/bench_${tag}.er
 python bench.py --patch 32 --prompts 10 --no-cpu-baseline --no-side > gpurun_out/bench_${tag}_b32.json 2>> gpurun_out/bench_${tag}.err
 python bench.py --impl reference --steps 2 --warmup 3 > gpurun_out/bench_${tag}_reference.json 2>> gpurun_out/bench_${tag}.err
 python tools/microbench_heads.py > gpurun_out/microbench_heads_${tag}.jsonl 2>> gpurun_out/bench_${tag}.err
-# head kernels: one ncu --set full pass over the tensor-core CLIP heads and the HSC / BCE row kernels (first launches only)
-python tools/microbench_heads.py > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"clip_score_mma|clip_oe_loss_mma|hsc_rows_kernel|bce_kernel" -c 8 -o gpurun_out/prof_heads_$tag python tools/microbench_heads.py > gpurun_out/ncu3_$tag.log 2>&1
+# head kernels: one ncu --set full pass over every head kernel family at its microbenchmark size (second launch of each)
+python tools/heads_once.py > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"clip_score_mma|clip_oe_loss_mma|hsc_rows_kernel|bce_kernel|auc_sort_pass" -c 28 -o gpurun_out/prof_heads_$tag python tools/heads_once.py > gpurun_out/ncu3_$tag.log 2>&1
 echo heads rc=$?

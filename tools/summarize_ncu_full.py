@@ -17,6 +17,9 @@ def main(rep, title, cmd):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
+    units = rows[1]
+    to_mb = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+    to_us = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
     print(f"# {title}\n\nCommand: `{cmd}` (after the same command exited 0 without ncu)\n")
     print("| # | kernel | " + " | ".join(n for _, n in WANT) + " |")
     print("|---|---|" + "---:|" * len(WANT))
@@ -26,7 +29,13 @@ def main(rep, title, cmd):
         for k, _ in WANT:
             v = r[hdr.index(k)] if k in hdr else ""
             try:
-                vals.append(f"{float(v.replace(',', '')):.1f}")
+                x = float(v.replace(',', ''))
+                u = units[hdr.index(k)] if k in hdr else ""
+                if k.startswith("dram__bytes"):
+                    x *= to_mb.get(u, 1.0)
+                if k == "gpu__time_duration.sum":
+                    x *= to_us.get(u, 1.0)
+                vals.append(f"{x:.1f}")
             except ValueError:
                 vals.append(v)
         print(f"| {i} | `{name}` | " + " | ".join(vals) + " |")
