@@ -210,6 +210,8 @@ def run_ours(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     dev = torch.device("cuda", local)
     pk = peaks()
+    if args.batch is None:
+        args.batch = 512 if args.patch == 16 else 1514
     B, K, S, W, P = args.batch, args.prompts, args.steps, args.warmup, args.patch
     op_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
 
@@ -418,7 +420,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="images per GPU per step; default 512 (ViT-B/16: 394 m-tiles of 256 rows = 16 waves of 74 CTA pairs at "
+                         "N = 768) or 1514 (ViT-B/32: 296 m-tiles = 4 x 74; 512 images leave the N = 768 GEMMs at 4.05 waves)")
     ap.add_argument("--patch", type=int, default=16, choices=[16, 32])
     ap.add_argument("--prompts", type=int, default=30)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16"])
