@@ -135,3 +135,26 @@ def test_clip_prompts_follow_reference():
     t2 = ADClipTrainer(None, device="cpu", text_encoder=enc, anom_tkn_ptn="a photo of something that is not a {}")
     t2.prepare_metric("dog", None, None, 0)
     assert seen["t"] == ["a photo of a dog", "a photo of something that is not a dog"]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU port arm the driver runs beside ours): one JSON line with the contract's keys;
+    under a multi-rank launch only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--ref-images", "2", "--patch", "32", "--prompts", "10"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "clip_zero_shot_ad_images_per_s" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] == "clip_vitb32_zero_shot_ad_224px_10prompts"
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "1"})
+    assert r1.returncode == 0 and not [l for l in r1.stdout.splitlines() if l.startswith("{")]
