@@ -377,5 +377,183 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// tcgen05 attention for short sequences (L <= 64: ViT-B/32 has 50 tokens).  One 128-row UMMA tile holds TWO (image, head)
+// items of the same image (heads h and h + 1: rows 0..63 and 64..127); their keys are concatenated to 128 "keys", so one
+//   S[128 x 128] = [Q_h; Q_h+1] [K_h; K_h+1]^T
+// produces both score blocks on the diagonal (the off-diagonal blocks are computed and ignored: tensor work is not what
+// bounds this kernel), and one
+//   O[128 x 64] = P[128 x 128] [V_h; V_h+1]
+// with P zero off the diagonal gives both outputs.  A thread owns one query row and only ever reads its own block's 64
+// score columns (two tcgen05.ld), so the whole row lives in registers: exact row maximum, one pass.  TMEM plan (128 columns,
+// four CTAs per SM): S [0, 128) -> P packed over [0, 64) (own block's 32 columns, zeros in the other block's 32),
+// O over [64, 128) once every row has been read.  Loads and stores go through 3-D [image][token][column] maps with
+// 64-token boxes: tokens >= L are zero-filled on load and clipped on store.
+namespace tc64 {
+constexpr int THREADS = 128;
+constexpr uint32_t SMEM_BYTES = 3 * TILE_BYTES + 64 + 1024;     // Q, K, V tiles of 128 rows x 128 B, barriers, alignment
+constexpr uint32_t TMEM_COLS = 128;
+constexpr uint32_t O_COL = 64;
+}  // namespace tc64
+
+template <bool BF16>
+__global__ void __launch_bounds__(tc64::THREADS, 4)
+attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, int num_pairs,
+                      int heads, int L) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;                         // [128][128 B]: rows 0..63 head h, rows 64..127 head h + 1
+    uint8_t* sK = smem + TILE_BYTES;
+    uint8_t* sV = smem + 2 * TILE_BYTES;
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 3 * TILE_BYTES);
+    uint64_t* bar_mma = bar_load + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int width = heads * 64;
+    const int hp = heads >> 1;                  // head pairs per image
+    if (tid == 0) {
+        ptx::prefetch_tensormap(&tm_qkv);
+        ptx::prefetch_tensormap(&tm_out);
+        ptx::mbar_init(ptx::smem_u32(bar_load), 1);
+        ptx::mbar_init(ptx::smem_u32(bar_mma), 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 0) {
+        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_slot), tc64::TMEM_COLS);
+        ptx::tmem_relinquish<1>();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t own = (uint32_t)(warp >> 1) * 64;          // first score column of this row's own block
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
+
+    constexpr uint32_t idesc_s = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, 128);
+    constexpr uint32_t idesc_o = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, 64, 0, 1);     // B = V is MN-major
+    const float sl2 = 0.125f * 1.4426950408889634f;                   // 1/sqrt(64) * log2(e)
+
+    uint32_t load_phase = 0, mma_phase = 0;
+    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        const int b = pair / hp, h = 2 * (pair % hp);
+        if (tid == 0) {
+            ptx::bulk_wait_group_read0();        // the previous pair's output (staged in the Q tile) has left
+            const uint32_t lb = ptx::smem_u32(bar_load);
+            ptx::mbar_arrive_expect_tx(lb, 3 * TILE_BYTES);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {        // 64-token boxes: tokens >= L arrive as zeros
+                ptx::tma_load_3d(ptx::smem_u32(sQ + i * (TILE_BYTES / 2)), &tm_qkv, lb, (h + i) * 64, 0, b);
+                ptx::tma_load_3d(ptx::smem_u32(sK + i * (TILE_BYTES / 2)), &tm_qkv, lb, width + (h + i) * 64, 0, b);
+                ptx::tma_load_3d(ptx::smem_u32(sV + i * (TILE_BYTES / 2)), &tm_qkv, lb, 2 * width + (h + i) * 64, 0, b);
+            }
+        }
+        ptx::mbar_wait(ptx::smem_u32(bar_load), load_phase);
+        load_phase ^= 1;
+        if (tid == 0) {
+            ptx::tc_fence_after();
+            const uint64_t a_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ));
+            const uint64_t b_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sK));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+            ptx::umma_commit(ptx::smem_u32(bar_mma));
+        }
+        ptx::mbar_wait(ptx::smem_u32(bar_mma), mma_phase);
+        mma_phase ^= 1;
+        ptx::tc_fence_after();
+        // softmax of this thread's row over its own block's keys: the 64 scores fit in registers
+        float inv_sum;
+        {
+            uint32_t r0[32], r1[32];
+            ptx::tmem_ld_32x32b_x32(t_lane + own, r0);
+            ptx::tmem_ld_32x32b_x32(t_lane + own + 32, r1);
+            ptx::tmem_ld_wait();
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j < L) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r0[j]));
+                if (32 + j < L) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r1[j]));
+            }
+            const float ms = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sl2;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t pk[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const float p0 = (j < L) ? fast_exp2(fmaf(__uint_as_float(r0[j]), sl2, -ms)) : 0.f;
+                const float p1 = (j + 1 < L) ? fast_exp2(fmaf(__uint_as_float(r0[j + 1]), sl2, -ms)) : 0.f;
+                const float p2 = (32 + j < L) ? fast_exp2(fmaf(__uint_as_float(r1[j]), sl2, -ms)) : 0.f;
+                const float p3 = (33 + j < L) ? fast_exp2(fmaf(__uint_as_float(r1[j + 1]), sl2, -ms)) : 0.f;
+                s4[(j >> 1) & 3] += (p0 + p1) + (p2 + p3);
+                pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
+                pk[16 + (j >> 1)] = gemm::pack2<BF16>(p2, p3);
+            }
+            inv_sum = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+            // P over columns [0, 64): keys 2c, 2c+1 in column c; this row's block at [own / 2, +32), zeros in the other block
+            uint32_t zero[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) zero[j] = 0u;
+            const uint32_t pcol = own >> 1, zcol = 32 - pcol;
+            ptx::tmem_st_32x32b_x16(t_lane + pcol, reinterpret_cast<const uint32_t(&)[16]>(pk[0]));
+            ptx::tmem_st_32x32b_x16(t_lane + pcol + 16, reinterpret_cast<const uint32_t(&)[16]>(pk[16]));
+            ptx::tmem_st_32x32b_x16(t_lane + zcol, zero);
+            ptx::tmem_st_32x32b_x16(t_lane + zcol + 16, zero);
+            ptx::tmem_st_wait();
+        }
+        ptx::tc_fence_before();
+        __syncthreads();                           // P of all rows is in TMEM, every S column has been read
+        if (tid == 0) {
+            ptx::tc_fence_after();
+            const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sV));
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)         // 16 keys per step: 8 packed columns of P, 16 rows (2 KB) of V
+                ptx::umma_f16_ts(tmem + tc64::O_COL, tmem + kk * 8, v_desc + (uint64_t)(kk * 2048 >> 4), idesc_o, kk != 0 ? 1u : 0u);
+            ptx::umma_commit(ptx::smem_u32(bar_mma));
+        }
+        ptx::mbar_wait(ptx::smem_u32(bar_mma), mma_phase);
+        mma_phase ^= 1;
+        ptx::tc_fence_after();
+        // O * (1 / row sum) -> 16 bit -> the dead Q tile (128-byte swizzle) -> two TMA tile stores (rows >= L clipped)
+        {
+            uint32_t o0[32], o1[32];
+            ptx::tmem_ld_32x32b_x32(t_lane + tc64::O_COL, o0);
+            ptx::tmem_ld_32x32b_x32(t_lane + tc64::O_COL + 32, o1);
+            ptx::tmem_ld_wait();
+            const uint32_t srow = ptx::smem_u32(sQ + tid * 128);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const uint32_t q0 = gemm::pack2<BF16>(__uint_as_float(o0[j]) * inv_sum, __uint_as_float(o0[j + 1]) * inv_sum);
+                const uint32_t q1 = gemm::pack2<BF16>(__uint_as_float(o0[j + 2]) * inv_sum, __uint_as_float(o0[j + 3]) * inv_sum);
+                const uint32_t q2 = gemm::pack2<BF16>(__uint_as_float(o0[j + 4]) * inv_sum, __uint_as_float(o0[j + 5]) * inv_sum);
+                const uint32_t q3 = gemm::pack2<BF16>(__uint_as_float(o0[j + 6]) * inv_sum, __uint_as_float(o0[j + 7]) * inv_sum);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((((j >> 3)) ^ (tid & 7)) << 4)), "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const uint32_t q0 = gemm::pack2<BF16>(__uint_as_float(o1[j]) * inv_sum, __uint_as_float(o1[j + 1]) * inv_sum);
+                const uint32_t q1 = gemm::pack2<BF16>(__uint_as_float(o1[j + 2]) * inv_sum, __uint_as_float(o1[j + 3]) * inv_sum);
+                const uint32_t q2 = gemm::pack2<BF16>(__uint_as_float(o1[j + 4]) * inv_sum, __uint_as_float(o1[j + 5]) * inv_sum);
+                const uint32_t q3 = gemm::pack2<BF16>(__uint_as_float(o1[j + 6]) * inv_sum, __uint_as_float(o1[j + 7]) * inv_sum);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + (((4 + (j >> 3)) ^ (tid & 7)) << 4)), "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
+            }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncthreads();                           // O has been read and staged: TMEM and the K / V tiles are free
+        if (tid == 0) {
+            ptx::tma_store_3d(&tm_out, ptx::smem_u32(sQ), h * 64, 0, b);
+            ptx::tma_store_3d(&tm_out, ptx::smem_u32(sQ + TILE_BYTES / 2), (h + 1) * 64, 0, b);
+            ptx::bulk_commit_group();
+        }
+    }
+    if (tid == 0) ptx::bulk_wait_group_read0();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<1>(tmem, tc64::TMEM_COLS);
+    }
+}
+
 }  // namespace attn
 }  // namespace eoe

@@ -823,6 +823,42 @@ static int attention_tc_launch(const CUtensorMap& tm_qkv, void* out, int64_t B, 
     return check_launch("attention_tc_kernel");
 }
 
+// tcgen05 path for L <= 64 (ViT-B/32: 50 tokens): two heads of an image per 128-row tile, 64-token TMA boxes
+template <bool BF16>
+static int attention_tc64_launch(const void* qkv, void* out, int64_t B, int L, int heads, int dtype, cudaStream_t st,
+                                 const CUtensorMap* tm_qkv64 = nullptr, const CUtensorMap* tm_o64 = nullptr) {
+    CUtensorMap lq, lo;
+    if (!tm_qkv64) {
+        int rc = make_tmap_tokens(&lq, qkv, B, L, 3 * heads * 64, 64, dtype);
+        if (!rc) rc = make_tmap_tokens(&lo, out, B, L, heads * 64, 64, dtype);
+        if (rc) return rc;
+        tm_qkv64 = &lq;
+        tm_o64 = &lo;
+    }
+    auto kern = attn::attention_tc64_kernel<BF16>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::tc64::SMEM_BYTES);
+        if (e != cudaSuccess) { set_cuda_error(e, "attention_tc64 smem attr"); return EOE_ERR_CUDA; }
+        attr_done = true;
+    }
+    const int64_t pairs = B * (heads / 2);
+    const int grid = (int)(pairs < 4 * (int64_t)num_sms() ? pairs : 4 * (int64_t)num_sms());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(attn::tc64::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = attn::tc64::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (g_gemm_debug & 32) ? 0 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, *tm_qkv64, *tm_o64, (int)pairs, heads, L);
+    if (e != cudaSuccess) { set_cuda_error(e, "attention_tc64_kernel launch"); return EOE_ERR_CUDA; }
+    return check_launch("attention_tc64_kernel");
+}
+
 static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int dtype, cudaStream_t st,
                               const CUtensorMap* tm_qkv = nullptr, const CUtensorMap* tm_o128 = nullptr,
                               const CUtensorMap* tm_o72 = nullptr, bool causal = false) {
@@ -843,6 +879,11 @@ static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, 
         }
         return bf ? attention_tc_launch<true>(*tm_qkv, out, B, (int)heads, dtype, st, tm_o128, tm_o72)
                   : attention_tc_launch<false>(*tm_qkv, out, B, (int)heads, dtype, st, tm_o128, tm_o72);
+    }
+    if (L <= 64 && heads % 2 == 0 && (uintptr_t)qkv % 16 == 0 && (uintptr_t)out % 16 == 0 && !(g_gemm_debug & 128)) {
+        // (diagnostics bit 7 keeps the warp-level kernel for A/B timing)
+        return bf ? attention_tc64_launch<true>(qkv, out, B, (int)L, (int)heads, dtype, st, tm_qkv, tm_o128)
+                  : attention_tc64_launch<false>(qkv, out, B, (int)L, (int)heads, dtype, st, tm_qkv, tm_o128);
     }
     if (L <= 64) return bf ? attention_launch_t<true, 64>(qkv, out, B, (int)L, (int)heads, st) : attention_launch_t<false, 64>(qkv, out, B, (int)L, (int)heads, st);
     if (L <= 208) return bf ? attention_launch_t<true, 208>(qkv, out, B, (int)L, (int)heads, st) : attention_launch_t<false, 208>(qkv, out, B, (int)L, (int)heads, st);
@@ -1215,7 +1256,9 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     if (!rc) rc = make_tmap(&p->tm_h, p->h, rows, W, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_u, p->u, rows, 4 * W, gemm::CTA_M, dt);
     if (!rc) rc = make_tmap(&p->tm_conv, w->conv1_w, W, p->kpatch, gemm::CTA_NB, dt);
-    if (!rc) rc = make_tmap_tokens(&p->tm_qkv, p->qkv, max_batch, p->L, 3 * W, 128, dt);
+    // attention maps: 128-token boxes for the L = 197 kernel, 64-token boxes (loads and stores) for the L <= 64 kernel
+    if (!rc) rc = make_tmap_tokens(&p->tm_qkv, p->qkv, max_batch, p->L, 3 * W, p->L <= 64 ? 64 : 128, dt);
+    if (!rc && p->L <= 64) rc = make_tmap_tokens(&p->tm_ho128, p->h, max_batch, p->L, W, 64, dt);
     if (!rc && p->L == 197) rc = make_tmap_tokens(&p->tm_ho128, p->h, max_batch, p->L, W, 128, dt);
     if (!rc && p->L == 197) rc = make_tmap_tokens(&p->tm_ho72, p->h, max_batch, p->L, W, 72, dt);
     if (!rc) rc = make_tmap(&p->tm_hc, p->h_cls, max_batch, W, gemm::CTA_M, dt);

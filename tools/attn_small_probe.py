@@ -10,7 +10,10 @@ from eoe_b200 import encoder as E  # noqa: E402
 
 
 def main():
+    from eoe_b200 import _lib as L
     res = {}
+    flag = int(sys.argv[1]) if len(sys.argv) > 1 else 0         # 128: warp-level kernel instead of the tcgen05 pair kernel
+    L.lib().eoe_debug_set(flag)
     for B, Lq, H in ((1514, 50, 12), (512, 50, 12), (30, 64, 8)):
         W = H * 64
         g = torch.Generator(device="cuda").manual_seed(0)
