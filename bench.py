@@ -415,7 +415,7 @@ def run_ours(args):
     }
     if ws == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_img = args.ref_images
+        n_img = args.cpu_baseline_images
         ips, dt = cpu_port_images_per_s(P, K, n_img, threads)
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{n_img} images of the same workload, {dt:.1f} s (oracle port, fp32, torch CPU)"}
@@ -440,6 +440,8 @@ def main():
     ap.add_argument("--prompts", type=int, default=30)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16"])
     ap.add_argument("--ref-images", type=int, default=64, help="images per step of the CPU port (bounded sample)")
+    ap.add_argument("--cpu-baseline-images", type=int, default=384,
+                    help="bounded sample of the cpu_baseline leg inside our arm (about 10 s of CPU work on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side", action="store_true")
     ap.add_argument("--no-fold", action="store_true", help="stand-alone ln_1 / ln_2 kernels instead of the LayerNorm fold (A/B)")
