@@ -243,6 +243,28 @@ def test_encoder_batching_and_fused_score(tower):
     np.testing.assert_allclose(s_fused.cpu().numpy(), want, rtol=1e-3, atol=1e-30)   # head: 1e-3 given identical features
 
 
+def test_encoder_full_batch_properties():
+    """BASELINE-size step (512 images, ViT-B/16, 100 864 token rows, 16 waves of GEMM tiles): size-independent properties
+    instead of a CPU oracle pass -- images are independent, so a permuted batch gives permuted features BIT FOR BIT, a
+    batch split in two calls gives the same rows, and the fused score equals the score head applied to the features."""
+    from eoe_b200 import ops
+    from eoe_b200.encoder import ClipImageEncoder
+    from eoe_b200.synth import random_vit_state_dict
+    sd = random_vit_state_dict(16, seed=0)
+    enc = ClipImageEncoder(sd, device=DEV, max_batch=512)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    imgs = torch.randn(512, 3, 224, 224, device=DEV, generator=g)
+    f = enc(imgs)
+    assert torch.isfinite(f).all()
+    perm = torch.randperm(512, device=DEV, generator=g)
+    assert torch.equal(enc(imgs[perm]), f[perm])
+    assert torch.equal(torch.cat([enc(imgs[:200]), enc(imgs[200:])]), f)
+    text = torch.nn.functional.normalize(torch.randn(30, 512, device=DEV, generator=g), dim=-1)
+    assert torch.equal(enc.score(imgs, text), ops.clip_score(f, text))
+    # features of distinct random images are distinct and well conditioned (no dead rows from tile tails)
+    assert f.norm(dim=-1).min().item() > 1e-3 and torch.unique(f[:, 0]).numel() == 512
+
+
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_encoder_uint8_input_is_bit_identical_to_host_normalisation(tower, layout, dtype):
