@@ -124,64 +124,7 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
     return 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
 }
 
-// Key-split form (bf16 probabilities only): the fixed exponent reference makes the two key halves of a row independent, so
-// S is produced by two MMAs (keys [0, 112) and [112, 208)) and the softmax of the first half runs while the tensor pipe is
-// still busy with the second, P0 . V0 runs under the softmax of the second half.  One part = NCOLS fp32 score columns at
-// TMEM column `t_base` (valid keys: the first VALID), P written back over the first NCOLS / 2 columns of the same region.
-// FIRST: derive the exponent reference `ms` from the part's first 32 keys (see softmax_row_tmem).
-template <int NCOLS, int VALID, bool FIRST>
-__device__ __forceinline__ void softmax_part_tmem(uint32_t t_base, float sl2, float& ms, float (&s4)[4]) {
-    constexpr int NC = NCOLS / 32;
-    constexpr bool TAIL = (NCOLS % 32) == 16;
-    static_assert(NC >= 2 && (NCOLS % 32 == 0 || TAIL), "chunking");
-    uint32_t r[2][32];
-    ptx::tmem_ld_32x32b_x32(t_base, r[0]);
-    ptx::tmem_ld_wait();
-    ptx::tmem_ld_32x32b_x32(t_base + 32, r[1]);
-    if (FIRST) {
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[0][j]));
-        ms = fmaf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), sl2, 32.0f);
-    }
-    auto prob = [&](uint32_t bits) {
-        float e = fmaf(__uint_as_float(bits), sl2, -ms);
-        e = e > 110.0f ? 110.0f : e;                    // NaN stays NaN (fminf would drop it)
-        return fast_exp2(e);
-    };
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        uint32_t pk[16];
-        if (c > 0) {
-            ptx::tmem_ld_wait();
-            if (c + 1 < NC) ptx::tmem_ld_32x32b_x32(t_base + (c + 1) * 32, r[(c + 1) & 1]);
-            else if (TAIL) ptx::tmem_ld_32x32b_x16(t_base + NC * 32, reinterpret_cast<uint32_t(&)[16]>(r[(c + 1) & 1]));
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-            const float p0 = (c * 32 + j < VALID) ? prob(r[c & 1][j]) : 0.f;
-            const float p1 = (c * 32 + j + 1 < VALID) ? prob(r[c & 1][j + 1]) : 0.f;
-            s4[(j >> 1) & 3] += p0 + p1;
-            pk[j >> 1] = gemm::pack2<true>(p0, p1);
-        }
-        ptx::tmem_st_32x32b_x16(t_base + c * 16, pk);    // same no-clobber argument as in softmax_row_tmem
-    }
-    if (TAIL) {
-        uint32_t pk[8];
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-            const float p0 = (NC * 32 + j < VALID) ? prob(r[NC & 1][j]) : 0.f;
-            const float p1 = (NC * 32 + j + 1 < VALID) ? prob(r[NC & 1][j + 1]) : 0.f;
-            s4[(j >> 1) & 3] += p0 + p1;
-            pk[j >> 1] = gemm::pack2<true>(p0, p1);
-        }
-        ptx::tmem_st_32x32b_x8(t_base + NC * 16, pk);
-    }
-    ptx::tmem_st_wait();
-}
-
-template <bool BF16, int L, bool SPLIT = false>
+template <bool BF16, int L>
 __global__ void __launch_bounds__(THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out128,
                     const __grid_constant__ CUtensorMap tm_out72, int num_items, int heads) {
@@ -193,25 +136,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     uint8_t* sQ = smem;                         // [2][128][128 B]
     uint8_t* sK = smem + 2 * TILE_BYTES;        // [256][128 B]
     uint8_t* sV = smem + 4 * TILE_BYTES;        // [256][128 B]
-    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES);
-    uint64_t* bar_mma = bar_load + 1;
-    uint64_t* bar_s1 = bar_load + 2;            // SPLIT: second key half of S
-    uint64_t* bar_pv = bar_load + 3;            // SPLIT: P . V (both halves)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 4);
-    // SPLIT column plan (216 of 256): S0 [0, 112) -> P0 [0, 56); O [56, 120) (free once S0 has been read); S1 [120, 216) -> P1 [120, 168)
-    static_assert(!SPLIT || (BF16 && LP == 208), "key split: bf16 probabilities, 208 padded keys");
-    constexpr int N0 = 112, N1 = LP - N0;
-    constexpr uint32_t S1_COL = 120, O_COL_S = 56;
-    constexpr uint32_t o_col = SPLIT ? O_COL_S : O_COL;
+    // One load barrier per buffer, so that every buffer of the NEXT item is refilled as soon as this item is done with it
+    // (K after the last S product, Q0 once its staged output has left, V after the last P.V product, Q1 at the item
+    // boundary): the first S product of an item never waits for HBM.  Only the MMA-issuing thread waits on them.
+    uint64_t* bar_q0 = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES);
+    uint64_t* bar_q1 = bar_q0 + 1;
+    uint64_t* bar_k = bar_q0 + 2;
+    uint64_t* bar_v = bar_q0 + 3;
+    uint64_t* bar_mma = bar_q0 + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q0 + 5);
+    constexpr uint32_t o_col = O_COL;
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int width = heads * 64;
     if (tid == 0) {
         ptx::prefetch_tensormap(&tm_qkv);
-        ptx::mbar_init(ptx::smem_u32(bar_load), 1);
+        ptx::mbar_init(ptx::smem_u32(bar_q0), 1);
+        ptx::mbar_init(ptx::smem_u32(bar_q1), 1);
+        ptx::mbar_init(ptx::smem_u32(bar_k), 1);
+        ptx::mbar_init(ptx::smem_u32(bar_v), 1);
         ptx::mbar_init(ptx::smem_u32(bar_mma), 1);
-        ptx::mbar_init(ptx::smem_u32(bar_s1), 1);
-        ptx::mbar_init(ptx::smem_u32(bar_pv), 1);
         ptx::fence_barrier_init();
     }
     if (warp == 0) {
@@ -228,49 +172,50 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 
     constexpr uint32_t idesc_s = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, LP);
     constexpr uint32_t idesc_o = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, 64, 0, 1);     // B = V is MN-major
-    constexpr uint32_t idesc_s0 = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, N0);
-    constexpr uint32_t idesc_s1 = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, N1);
     const float sl2 = 0.125f * 1.4426950408889634f;                   // 1/sqrt(64) * log2(e)
 
-    uint32_t load_phase = 0, mma_phase = 0, split_phase = 0;
+    uint32_t load_phase = 0, mma_phase = 0;
+    // 3-D map [image][token][3*width]: tokens >= L of a box are zero-filled without touching memory, so K / V rows
+    // L..255 cost no traffic and meet P == 0 with finite values
+    auto load_q = [&](int tile, int bb, int hh, int row0) {
+        const uint32_t lb = ptx::smem_u32(tile ? bar_q1 : bar_q0);
+        ptx::mbar_arrive_expect_tx(lb, TILE_BYTES);
+        ptx::tma_load_3d(ptx::smem_u32(sQ + tile * TILE_BYTES), &tm_qkv, lb, hh * 64, row0, bb);
+    };
+    auto load_kv = [&](int which, int bb, int hh) {         // which: 0 = K, 1 = V
+        const uint32_t lb = ptx::smem_u32(which ? bar_v : bar_k);
+        uint8_t* dst = which ? sV : sK;
+        ptx::mbar_arrive_expect_tx(lb, 2 * TILE_BYTES);
+        ptx::tma_load_3d(ptx::smem_u32(dst), &tm_qkv, lb, (1 + which) * width + hh * 64, 0, bb);
+        ptx::tma_load_3d(ptx::smem_u32(dst + TILE_BYTES), &tm_qkv, lb, (1 + which) * width + hh * 64, 128, bb);
+    };
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int b = item / heads, h = item % heads;
         const int t1_start = (it & 1) ? (L - 128) : 128;              // first query row of the second tile
+        const int next = item + gridDim.x;
+        const bool has_next = next < num_items;
+        const int nb = next / heads, nh = next % heads;
         if (tid == 0) {
             ptx::bulk_wait_group_read0();        // the previous item's output tiles (staged in the Q buffers) have left
-            const uint32_t lb = ptx::smem_u32(bar_load);
-            ptx::mbar_arrive_expect_tx(lb, 6 * TILE_BYTES);
-            // 3-D map [image][token][3*width]: tokens >= L of a box are zero-filled without touching memory, so K / V rows
-            // L..255 cost no traffic and meet P == 0 with finite values
-            ptx::tma_load_3d(ptx::smem_u32(sQ), &tm_qkv, lb, h * 64, 0, b);
-            ptx::tma_load_3d(ptx::smem_u32(sQ + TILE_BYTES), &tm_qkv, lb, h * 64, t1_start, b);
-            ptx::tma_load_3d(ptx::smem_u32(sK), &tm_qkv, lb, width + h * 64, 0, b);
-            ptx::tma_load_3d(ptx::smem_u32(sK + TILE_BYTES), &tm_qkv, lb, width + h * 64, 128, b);
-            ptx::tma_load_3d(ptx::smem_u32(sV), &tm_qkv, lb, 2 * width + h * 64, 0, b);
-            ptx::tma_load_3d(ptx::smem_u32(sV + TILE_BYTES), &tm_qkv, lb, 2 * width + h * 64, 128, b);
+            if (it == 0) {                       // later items find Q0, K and V already requested (see below)
+                load_q(0, b, h, 0);
+                load_kv(0, b, h);
+                load_kv(1, b, h);
+            }
+            load_q(1, b, h, t1_start);
         }
-        ptx::mbar_wait(ptx::smem_u32(bar_load), load_phase);
-        load_phase ^= 1;
 #pragma unroll 1
         for (int tile = 0; tile < 2; ++tile) {
             if (tid == 0) {
+                ptx::mbar_wait(ptx::smem_u32(tile ? bar_q1 : bar_q0), load_phase);
+                if (tile == 0) ptx::mbar_wait(ptx::smem_u32(bar_k), load_phase);
                 ptx::tc_fence_after();
                 const uint64_t a_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ + tile * TILE_BYTES));
                 const uint64_t b_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sK));
-                if (SPLIT) {
-                    const uint64_t b1_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sK + N0 * 128));   // key row 112: 8-row atom aligned
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_s0, k != 0 ? 1u : 0u);
-                    ptx::umma_commit(ptx::smem_u32(bar_mma));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(tmem + S1_COL, a_desc + 2 * k, b1_desc + 2 * k, idesc_s1, k != 0 ? 1u : 0u);
-                    ptx::umma_commit(ptx::smem_u32(bar_s1));
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-                    ptx::umma_commit(ptx::smem_u32(bar_mma));
-                }
+                for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                ptx::umma_commit(ptx::smem_u32(bar_mma));
             }
             // query row owned by this thread, and whether its warp has any row to compute
             const int wfirst = (tile == 0 ? 0 : t1_start) + warp * 32;
@@ -278,45 +223,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             ptx::mbar_wait(ptx::smem_u32(bar_mma), mma_phase);
             mma_phase ^= 1;
             ptx::tc_fence_after();
+            if (tile == 1 && tid == 0 && has_next) {
+                // the last S product of this item is done: K is free, and tile 0's staged output has long left Q0
+                ptx::bulk_wait_group_read0();
+                load_q(0, nb, nh, 0);
+                load_kv(0, nb, nh);
+            }
             float inv_sum = 0.f;
-            if (SPLIT) {
-                float ms = 0.f, s4[4] = {0.f, 0.f, 0.f, 0.f};
-                if (warp_active) softmax_part_tmem<N0, N0, true>(t_lane, sl2, ms, s4);
-                ptx::tc_fence_before();
-                __syncthreads();                   // P0 of all rows is in TMEM, S0 has been read: O's columns are free
-                if (tid == 0) {
-                    ptx::tc_fence_after();
-                    const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sV));
-#pragma unroll
-                    for (int kk = 0; kk < N0 / 16; ++kk)
-                        ptx::umma_f16_ts(tmem + o_col, tmem + kk * 8, v_desc + (uint64_t)(kk * 2048 >> 4), idesc_o, kk != 0 ? 1u : 0u);
-                }
-                ptx::mbar_wait(ptx::smem_u32(bar_s1), split_phase);
-                ptx::tc_fence_after();
-                if (warp_active) {
-                    softmax_part_tmem<N1, L - N0, false>(t_lane + S1_COL, sl2, ms, s4);
-                    inv_sum = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
-                }
-                ptx::tc_fence_before();
-                __syncthreads();                   // P1 of all rows is in TMEM
-                if (tid == 0) {
-                    ptx::tc_fence_after();
-                    const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sV + N0 * 128));
-#pragma unroll
-                    for (int kk = 0; kk < N1 / 16; ++kk)
-                        ptx::umma_f16_ts(tmem + o_col, tmem + S1_COL + kk * 8, v_desc + (uint64_t)(kk * 2048 >> 4), idesc_o, 1u);
-                    ptx::umma_commit(ptx::smem_u32(bar_pv));
-                }
-                ptx::mbar_wait(ptx::smem_u32(bar_pv), split_phase);
-                split_phase ^= 1;
-                ptx::tc_fence_after();
-            } else {
             if (warp_active) {
                 inv_sum = softmax_row_tmem<BF16, L>(t_lane, sl2);
             }
             ptx::tc_fence_before();
             __syncthreads();                       // P of all rows is in TMEM (and the V tail is zeroed)
             if (tid == 0) {
+                if (tile == 0) ptx::mbar_wait(ptx::smem_u32(bar_v), load_phase);
                 ptx::tc_fence_after();
                 const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sV));
 #pragma unroll
@@ -327,7 +247,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             ptx::mbar_wait(ptx::smem_u32(bar_mma), mma_phase);
             mma_phase ^= 1;
             ptx::tc_fence_after();
-            }
+            if (tile == 1 && tid == 0 && has_next) load_kv(1, nb, nh);      // the last P.V product is done: V is free
             // Epilogue: O * (1 / row sum) -> 16 bit, staged row-major in the (now dead) Q tile with the 128-byte swizzle
             // and written by ONE TMA tile store: full 128-byte lines instead of 32 half-sector writes per instruction.
             // The output map is 3-D [image][token][width], so rows past the image's last token are clipped by the TMA unit.
@@ -369,6 +289,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 ptx::bulk_commit_group();
             }
         }
+        load_phase ^= 1;                           // each of the four load barriers completed exactly one phase for this item
     }
     if (tid == 0) ptx::bulk_wait_group_read0();
     if (warp == 0) {

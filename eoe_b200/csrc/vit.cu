@@ -795,16 +795,12 @@ static int attention_tc_launch(const CUtensorMap& tm_qkv, void* out, int64_t B, 
         tm_o128 = &l128;
         tm_o72 = &l72;
     }
-    // diagnostics bit 7 (bf16 only): key-split softmax (S in two halves, the tensor pipe works under the softmax of the
-    // other half).  Bit-identical results, measured 164 us vs 157 us per layer for the default single-pass form (the second
-    // resident CTA already fills those gaps; the extra __syncthreads costs more): kept for A/B, not the default.
-    const bool split = BF16 && (g_gemm_debug & 128);
-    auto kern = split ? attn::attention_tc_kernel<BF16, 197, BF16> : attn::attention_tc_kernel<BF16, 197, false>;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[split]) {
+    auto kern = attn::attention_tc_kernel<BF16, 197>;
+    static bool attr_done = false;
+    if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::SMEM_BYTES);
         if (e != cudaSuccess) { set_cuda_error(e, "attention_tc smem attr"); return EOE_ERR_CUDA; }
-        attr_done[split] = true;
+        attr_done = true;
     }
     const int64_t items = B * heads;
     const int grid = (int)(items < 2 * (int64_t)num_sms() ? items : 2 * (int64_t)num_sms());

@@ -19,7 +19,7 @@ def main():
     res = {}
     outs = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for name, flag in (("single", 0), ("split", 128)):
+    for name, flag in (("cur", 0),):
         lib.eoe_debug_set(flag)
         for i in range(3):
             o = E.attention(qkvs[i & 1], B, Lq, H)
