@@ -127,3 +127,24 @@ def test_prepare_metric_through_the_text_tower():
     assert center.shape == (3, 512)
     torch.testing.assert_close(center.cpu(), want, rtol=0, atol=2e-4)
     torch.testing.assert_close(center.norm(dim=-1).cpu(), torch.ones(3), rtol=0, atol=1e-6)
+
+
+def test_clip_model_has_the_reference_surface():
+    """ClipModel: encode_image / encode_text / forward = encode_image (clip.py:33) over both kernels' towers; an image-only
+    state_dict refuses encode_text loudly."""
+    from eoe_b200 import _lib as L
+    from eoe_b200.clip_model import ClipModel
+    from oracle import vit as ovit
+    sd = {**ovit.synth_state_dict(32, seed=3, layers=1), **otext.synth_text_state_dict(seed=4, layers=1, vocab=200)}
+    m = ClipModel(sd, device=DEV, max_batch=4)
+    imgs = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(1)).to(DEV)
+    tok = otext.synth_tokens(4, seed=5, vocab=200).to(DEV)
+    f, t = m(imgs), m.encode_text(tok)
+    assert f.shape == (3, 512) and t.shape == (4, 512) and torch.equal(f, m.encode_image(imgs))
+    want_t = otext.encode_text(sd, tok.cpu(), operand_dtype=torch.bfloat16)
+    assert _rel(t.cpu(), want_t) < 3e-3
+    center = torch.nn.functional.normalize(t, dim=-1)
+    from eoe_b200 import ops
+    assert torch.equal(m.score(imgs, center), ops.clip_score(f, center))
+    with pytest.raises(L.EoeError):
+        ClipModel(ovit.synth_state_dict(32, seed=3, layers=1), device=DEV, max_batch=2).encode_text(tok)
