@@ -222,6 +222,7 @@ def run_ours(args):
         if ws == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     dev = torch.device("cuda", local)
+    numa_cpus = edist.bind_to_gpu_numa(local) if ws > 1 else None      # pinned host buffers land on the GPU's NUMA node
     pk = peaks()
     if args.batch is None:
         args.batch = 512 if args.patch == 16 else 1514
@@ -293,7 +294,7 @@ def run_ours(args):
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
 
-    def e2e_job(n_steps, host=host, dbuf=dbuf):
+    def e2e_job(n_steps, host, dbuf):
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
         with torch.cuda.stream(copy_stream):
@@ -318,46 +319,57 @@ def run_ours(args):
         out, _, _ = metrics.roc_auc_device(s_all, l_all, workspace=auc_ws)
         return out.cpu()                                                 # the AUC is read on the host (sync)
 
-    e2e_job(min(W, S))
-    sync()
-    t0 = time.perf_counter()
-    e2e_job(S)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if ws > 1:
-        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-    e2e_val = ws * S * B / float(t.item())
+    def time_e2e(hbufs, dbufs):
+        e2e_job(min(W, S), hbufs, dbufs)
+        sync()
+        t0 = time.perf_counter()
+        e2e_job(S, hbufs, dbufs)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if ws > 1:
+            tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
+        return ws * S * B / float(tt.item())
 
-    # ---- e2e from RAW pixels: uint8 NHWC host batches, ToTensor + Normalize fused into the patchify kernel
+    # ---- headline e2e: the dataset's decoded pixels as they sit in host memory -- uint8 NHWC at 224 x 224 -- with ToTensor
+    # + Normalize fused into the patchify kernel (eoe_vit_encode_u8)
     host8 = [torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
     dbuf8 = [torch.empty(B, 224, 224, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
-    e2e_job(min(W, S), host8, dbuf8)
-    sync()
-    t0 = time.perf_counter()
-    e2e_job(S, host8, dbuf8)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if ws > 1:
-        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-    e2e_u8_val = ws * S * B / float(t.item())
+    e2e_u8_val = time_e2e(host8, dbuf8)
+    del host8, dbuf8
+    # ---- the same job from fp32 NCHW host batches (what the reference's DataLoader hands over after ToTensor + Normalize)
+    e2e_val = time_e2e(host, dbuf)
+    del host, dbuf
 
     # ---- e2e from RAW decoded images of the dataset's native size: Resize(bicubic) + CenterCrop + ToTensor + Normalize
     # (all of CLIP's `_transform`) run inside the patchify kernel (eoe_vit_encode_u8_resize)
     rh, rw = (32, 32) if P == 32 else (375, 500)              # CIFAR-10-shaped (config 2) / ImageNet-shaped (config 3)
     hostr = [torch.randint(0, 256, (B, rh, rw, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
     dbufr = [torch.empty(B, rh, rw, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
-    e2e_job(min(W, S), hostr, dbufr)
-    sync()
-    t0 = time.perf_counter()
-    e2e_job(S, hostr, dbufr)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if ws > 1:
-        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-    e2e_raw_val = ws * S * B / float(t.item())
+    e2e_raw_val = time_e2e(hostr, dbufr)
+    del hostr, dbufr
+
+    # ---- the other operand dtype, device-resident, same K steps (side metric; parity of both: DESIGN.md section 5)
+    other = None
+    if not args.no_side:
+        o_name = "bf16" if args.dtype == "f16" else "f16"
+        enc_o = ClipImageEncoder(sd, device=dev, operand_dtype=torch.bfloat16 if o_name == "bf16" else torch.float16,
+                                 max_batch=B, fold_layernorm=not args.no_fold)
+
+        def job_o(n_steps):
+            for k in range(n_steps):
+                enc_o.score(imgs[k & 1], text, out=scores[k * B:(k + 1) * B])
+        job_o(W)
+        sync()
+        e0.record()
+        job_o(S)
+        e1.record()
+        sync()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if ws > 1:
+            tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
+        other = {"dtype": o_name, "value": ws * S * B / (float(tt.item()) / 1e3), "unit": UNIT,
+                 "note": "same K steps, device-resident, encoder + fused score only (no all-gather / AUC)"}
+        del enc_o
 
     if rank != 0:
         if ws > 1:
@@ -371,14 +383,22 @@ def run_ours(args):
     g_n = sum(v[1] for v in prof.values())
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     traffic, traffic_note = None, None
+    build_id = _lib.lib().eoe_build_id().decode()
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("batch") == B and P == 16:          # ncu capture of the c_fc GEMM at this batch size
-            traffic = tj.get("dram_bytes_per_launch")
-            traffic_note = {"kernel": tj.get("kernel"), "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"),
-                            "source": tj.get("source")}
+        ent = (tj.get("by_dtype") or {}).get(args.dtype, tj)
+        if tj.get("build_id") != build_id:
+            # an ncu capture of ANOTHER build says nothing about this one: refuse it instead of quoting a stale figure
+            traffic_note = {"refused": f"profiles/gemm_traffic.json was captured on build {tj.get('build_id')}, "
+                                       f"this library is build {build_id}"}
+        elif tj.get("batch") == B and P == 16 and ent.get("dram_bytes_per_launch"):
+            traffic = ent.get("dram_bytes_per_launch")         # ncu --set full capture of the c_fc GEMM at this batch size
+            traffic_note = {"kernel": ent.get("kernel"), "algorithmic_bytes_per_launch": ent.get("algorithmic_bytes_per_launch"),
+                            "source": ent.get("source"), "build_id": build_id, "note": ent.get("note")}
     fc = prof.get("c_fc", (0.0, 0, 0.0))
+    Lt = (224 // P) ** 2 + 1
+    exec_gflop = (g_fl / (S * B) + (enc.n_layers - 1) * 4.0 * Lt * Lt * enc.width + 4.0 * Lt * enc.width) / 1e9
     roofline = {
         "bound": "tensor", "kernel": "eoe::gemm::gemm_kernel (tcgen05, all 49 GEMM launches per step)",
         "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
@@ -391,6 +411,13 @@ def run_ours(args):
         "ms_per_step_instrumented": ms_prof / S,
         "per_kind_tflops": {k: (v[2] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else None) for k, v in prof.items()},
         "encoder_tensor_frac": value / ws * GFLOP_PER_IMG[P] * 1e9 / 1e12 / pk["tf_sust"],
+        "encoder_tensor_frac_burst": value / ws * GFLOP_PER_IMG[P] * 1e9 / 1e12 / pk["tf_burst"],
+        # the last block is evaluated for the class-token rows only (identical output): EXECUTED flops per image =
+        # GEMM launches of the timed region + attention (full L x L in all but the last block, one query row there)
+        "executed_gflop_per_image": exec_gflop, "algorithmic_gflop_per_image": GFLOP_PER_IMG[P],
+        "encoder_tensor_frac_executed": value / ws * exec_gflop * 1e9 / 1e12 / pk["tf_sust"],
+        "encoder_tensor_frac_executed_burst": value / ws * exec_gflop * 1e9 / 1e12 / pk["tf_burst"],
+        "build_id": build_id,
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": S, "warmup": W,
@@ -402,10 +429,13 @@ def run_ours(args):
                    "parallelism": f"dp{ws}: images sharded by rank, all_gather(scores, labels) -> global device AUC",
                    "timed_region": "K x (patchify + ViT encoder + fused score head) + all-gather + ROC-AUC"},
         "roofline": roofline,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4,
-                "note": "pinned fp32 host batches, double-buffered H2D on a copy stream, scores + AUC read on host"},
-        "e2e_u8": {"value": e2e_u8_val, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224, "d2h_bytes_per_step": B * 4,
-                   "note": "same job from raw uint8 NHWC pixels: ToTensor + Normalize fused into the patchify kernel (eoe_vit_encode_u8)"},
+        "e2e": {"value": e2e_u8_val, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224, "d2h_bytes_per_step": B * 4 + 8,
+                "note": "public API (ClipImageEncoder.score + metrics.roc_auc_device) from pinned HOST batches of decoded uint8 "
+                        "NHWC pixels (ToTensor + Normalize fused into the patchify kernel, eoe_vit_encode_u8), double-buffered "
+                        "H2D on a copy stream, every step's scores and the final AUC read back to the host",
+                "numa_cpus": numa_cpus},
+        "e2e_f32": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4 + 8,
+                    "note": "same job from pinned fp32 NCHW host batches (the reference DataLoader's output format): 4x the PCIe bytes"},
         "e2e_raw": {"value": e2e_raw_val, "unit": UNIT, "h2d_bytes_per_step": B * rh * rw * 3, "d2h_bytes_per_step": B * 4,
                     "note": f"same job from raw uint8 {rh}x{rw} images: Resize(bicubic, Pillow-exact) + CenterCrop + ToTensor + "
                             "Normalize fused into the patchify kernel (eoe_vit_encode_u8_resize)"},
@@ -421,6 +451,7 @@ def run_ours(args):
                                 "sample": f"{n_img} images of the same workload, {dt:.1f} s (oracle port, fp32, torch CPU)"}
     if not args.no_side:
         line["side_metrics"] = side_metrics(dev, pk)
+        line["side_metrics"]["other_dtype"] = other
     emit(line)
     if ws > 1:
         tdist.barrier()
@@ -438,7 +469,9 @@ def main():
                          "N = 768) or 1514 (ViT-B/32: 296 m-tiles = 4 x 74; 512 images leave the N = 768 GEMMs at 4.05 waves)")
     ap.add_argument("--patch", type=int, default=16, choices=[16, 32])
     ap.add_argument("--prompts", type=int, default=30)
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16"])
+    ap.add_argument("--dtype", default="f16", choices=["bf16", "f16"],
+                    help="GEMM operand dtype.  f16 (default) is the reference's own GPU dtype and the one whose end-to-end scores "
+                         "are closer to the fp32 reference than the reference's GPU path (DESIGN.md section 5); bf16 is ~5 %% faster")
     ap.add_argument("--ref-images", type=int, default=64, help="images per step of the CPU port (bounded sample)")
     ap.add_argument("--cpu-baseline-images", type=int, default=384,
                     help="bounded sample of the cpu_baseline leg inside our arm (about 10 s of CPU work on 16 cores)")

@@ -17,13 +17,15 @@ EOE_F32, EOE_F16, EOE_BF16 = 0, 1, 2
 EOE_HEAD_WS_BYTES = 32768
 EOE_AUC_IGNORE_NEGATIVE_LABELS = 1
 EOE_AUC_WITH_PRC = 2
+EOE_AUC_FORCE_TILED = 4
+EOE_AUC_SINGLE_LAUNCH_MAX = 16384
 EOE_AUC_STATUS_NONFINITE = 1
 EOE_AUC_STATUS_SINGLE_CLASS = 2
 EOE_EPI_BIAS, EOE_EPI_BIAS_QUICKGELU, EOE_EPI_BIAS_RESIDUAL_F32, EOE_EPI_PATCH_EMBED = 0, 1, 2, 3
 EOE_EPI_LNFOLD_BIAS, EOE_EPI_LNFOLD_QUICKGELU, EOE_EPI_RESIDUAL_STATS = 4, 5, 6
 EOE_EPI_LNFOLD_QUICKGELU_X1702 = 8
 GELU_SLOPE = 1.702
-EOE_ABI_VERSION = 4
+EOE_ABI_VERSION = 5
 EOE_LAYOUT_NCHW, EOE_LAYOUT_NHWC = 0, 1
 LAYOUT_RESIZE = 2            # host-side tag only: raw [B,H,W,3] pixels of another size -> eoe_vit_encode_u8_resize
 
@@ -59,6 +61,7 @@ SIGNATURES = {
     "eoe_strerror": (C.c_char_p, [_I]),
     "eoe_last_cuda_error": (C.c_char_p, []),
     "eoe_launch_count": (C.c_longlong, []),
+    "eoe_build_id": (C.c_char_p, []),
     "eoe_hsc_fwd_bwd": (_I, [_P, _I, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P]),
     "eoe_hsc_score": (_I, [_P, _I, _I64, _I64, _P, _P]),
     "eoe_bce_fwd_bwd": (_I, [_P, _I, _P, _I64, _I64, _P, _P, _P, _P, _P]),
@@ -69,7 +72,7 @@ SIGNATURES = {
     "eoe_clip_score": (_I, [_P, _I, _P, _I64, _I64, _I64, _F, _P, _P]),
     "eoe_clip_oe_loss_fwd_bwd": (_I, [_P, _I, _P, _P, _I64, _I64, _I64, _F, _I64, _I, _P, _P, _P, _P]),
     "eoe_auc_workspace_bytes": (_SZ, [_I64]),
-    "eoe_auc": (_I, [_P, _I, _P, _I64, _I, _P, _SZ, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "eoe_auc": (_I, [_P, _I, _P, _I64, _I, _P, _SZ, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "eoe_vit_workspace_bytes": (_SZ, [C.POINTER(VitWeights), _I64]),
     "eoe_vit_plan_create": (_I, [C.POINTER(VitWeights), _I64, _P, _SZ, C.POINTER(_P)]),
     "eoe_vit_plan_destroy": (None, [_P]),

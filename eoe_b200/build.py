@@ -35,8 +35,25 @@ def _deps_mtime():
     return max(os.path.getmtime(p) for p in paths)
 
 
+def source_id() -> str:
+    """sha256 over csrc/* and include/eoe_b200.h: the identity of the kernels a library was built from.  Baked into the
+    library (eoe_build_id()) so that profile artefacts (profiles/gemm_traffic.json) can be tied to the build they measured."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(os.path.dirname(HERE), "include", "eoe_b200.h")]:
+        h.update(os.path.basename(path).encode() + b"\0")
+        h.update(open(path, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def _compile(src):
     obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    if os.path.basename(src) == "capi.cu":       # carries the build id: always rebuilt with the link (a 1 s compile)
+        cmd = [_nvcc(), *NVCC_FLAGS, f'-DEOE_BUILD_ID="{source_id()}"', "-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj, r.stderr
     hdr_m = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     hdr_m = max(hdr_m, os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", "eoe_b200.h")))
     if os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_m):

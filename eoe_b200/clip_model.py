@@ -18,7 +18,7 @@ from .text_encoder import ClipTextEncoder
 
 
 class ClipModel(nn.Module):
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", operand_dtype=torch.bfloat16, max_batch: int = 256,
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", operand_dtype=torch.float16, max_batch: int = 256,
                  **image_encoder_kwargs):
         super().__init__()
         self.visual = ClipImageEncoder(state_dict, device=device, operand_dtype=operand_dtype, max_batch=max_batch,

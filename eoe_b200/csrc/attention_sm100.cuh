@@ -38,29 +38,59 @@ __device__ __forceinline__ float fast_exp2(float x) {      // x <= 0 here; MUFU.
 // Softmax of one query row held in TMEM lane `t_lane` (S in fp32 over columns [0, LP)): un-normalised P is written back
 // over columns [0, LP/2) as packed 16-bit pairs, the fp32 row sum's reciprocal is returned.
 //
-// TMEM reads are the attention kernel's bottleneck (64 B/clk/SM: two passes over S cost 3 us per (image, head)), so
-// with bf16 probabilities S is read ONCE: the exponent reference is the maximum of the first 32 keys (held in
-// registers) plus 32 instead of the row maximum.  softmax is invariant to the reference; bf16 / fp32 keep full relative
-// precision at any magnitude; a key may exceed the reference by 2^142 before the (NaN-preserving) clamp at 2^110
-// engages, i.e. scores more than ~100 above the first 32 keys' maximum -- far beyond what the reference's own fp16
-// GPU path can represent.  fp16 probabilities (max 65504) keep the exact two-pass form.
+// TMEM reads are the attention kernel's bottleneck (64 B/clk/SM: two passes over S cost 3 us per (image, head)), so S is
+// read ONCE: the exponent reference starts as (a function of) the maximum of the first 32 keys, held in registers,
+// instead of the row maximum -- softmax is invariant to the reference.
+//   bf16 probabilities: reference = that maximum + 32 (log2 units).  bf16 / fp32 keep full relative precision at any
+//     magnitude; a key may exceed the reference by 2^142 before the (NaN-preserving) clamp at 2^110 engages, i.e. scores
+//     more than ~100 above the first 32 keys' maximum -- far beyond what the reference's own fp16 GPU path can represent.
+//   fp16 probabilities (largest finite value 65504): reference = that maximum, so the first chunk's P <= 1; a later chunk
+//     whose fp32 partial sum reaches 2^15 (which every element >= 2^15 forces) raises the reference to that chunk's maximum,
+//     rescales the P already stored in TMEM and the running sum by 2^(old - new) and recomputes the chunk -- the
+//     flash-attention rescale, taken only when needed and warp-uniformly (tcgen05.ld / .st are warp-collective; lanes
+//     that did not overflow rescale by exactly 1).  Exact for any finite scores; never taken when the row maximum is within
+//     ~10 nats of the first 32 keys' (always, at random initialisation).  EOE_F16_ATTN_TWOPASS=1 restores the two-pass form
+//     (exact row maximum first) for A/B timing.
+#ifndef EOE_F16_ATTN_TWOPASS
+#define EOE_F16_ATTN_TWOPASS 0
+#endif
+
+// rare path of the fp16 single-pass softmax: P of chunks < c (columns [16 cc, 16 cc + 16)) times f (warp-collective)
+__device__ __noinline__ void softmax_rescale_stored_p(uint32_t t_lane, int c, float f) {
+    const __half2 f2 = __float2half2_rn(f);
+#pragma unroll 1
+    for (int cc = 0; cc < c; ++cc) {
+        uint32_t pk[16];
+        ptx::tmem_ld_32x32b_x16(t_lane + cc * 16, pk);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            __half2 h = __hmul2(*reinterpret_cast<__half2*>(&pk[j]), f2);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        ptx::tmem_st_32x32b_x16(t_lane + cc * 16, pk);
+    }
+    ptx::tmem_st_wait();
+}
+
 template <bool BF16, int L>
 __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
     constexpr int LP = (L + 15) / 16 * 16;
     constexpr int NC = LP / 32;                 // full 32-column chunks; LP % 32 == 16 leaves one half chunk
+    constexpr bool ONEPASS = BF16 || !EOE_F16_ATTN_TWOPASS;
     static_assert(LP % 32 == 0 || LP % 32 == 16, "chunking");
     static_assert(L >= 32, "first chunk fully valid");
     uint32_t r[2][32];
     float s4[4] = {0.f, 0.f, 0.f, 0.f};
     float ms;
-    if (BF16) {
+    if (ONEPASS) {
         ptx::tmem_ld_32x32b_x32(t_lane, r[0]);
         ptx::tmem_ld_wait();
         if (NC > 1) ptx::tmem_ld_32x32b_x32(t_lane + 32, r[1]);
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r[0][j]));
-        ms = fmaf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), sl2, 32.0f);
+        ms = fmaf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), sl2, BF16 ? 32.0f : 0.0f);
     } else {
         // pass 1: exact row maximum (TMEM loads software pipelined, four independent accumulators)
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -89,21 +119,49 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
         if (BF16) e = e > 110.0f ? 110.0f : e;          // NaN stays NaN (fminf would drop it)
         return fast_exp2(e);
     };
+    constexpr bool RESCALE = !BF16 && ONEPASS;          // fp16, single pass: the reference may have to rise
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         uint32_t pk[16];
-        if (!(BF16 && c == 0)) {                        // bf16: chunk 0 is already in registers, chunk 1 in flight
+        if (!(ONEPASS && c == 0)) {                     // single pass: chunk 0 is already in registers, chunk 1 in flight
             ptx::tmem_ld_wait();
             if (c + 1 < NC) ptx::tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, r[(c + 1) & 1]);
             else if (LP % 32) ptx::tmem_ld_32x32b_x16(t_lane + NC * 32, reinterpret_cast<uint32_t(&)[16]>(r[(c + 1) & 1]));
         }
+        float c4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
             const float p0 = (c * 32 + j < L) ? prob(r[c & 1][j]) : 0.f;
             const float p1 = (c * 32 + j + 1 < L) ? prob(r[c & 1][j + 1]) : 0.f;
-            s4[(j >> 1) & 3] += p0 + p1;
+            c4[(j >> 1) & 3] += p0 + p1;
             pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
         }
+        if (RESCALE && c > 0) {
+            const bool ovf = (c4[0] + c4[1]) + (c4[2] + c4[3]) >= 32768.0f;
+            if (__any_sync(0xffffffffu, ovf)) {
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c * 32 + j < L) m = fmaxf(m, __uint_as_float(r[c & 1][j]));
+                const float new_ms = ovf ? fmaxf(ms, m * sl2) : ms;
+                const float f = fast_exp2(ms - new_ms);          // exactly 1 for lanes that keep their reference
+                ms = new_ms;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] *= f;
+                softmax_rescale_stored_p(t_lane, c, f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c4[i] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = (c * 32 + j < L) ? prob(r[c & 1][j]) : 0.f;
+                    const float p1 = (c * 32 + j + 1 < L) ? prob(r[c & 1][j + 1]) : 0.f;
+                    c4[(j >> 1) & 3] += p0 + p1;
+                    pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s4[i] += c4[i];
         // columns [16c, 16c+16) hold scores consumed in rounds <= c; the in-flight load of round c+1 reads
         // columns >= 32(c+1) > 16c+16, so the store cannot clobber unread scores
         ptx::tmem_st_32x32b_x16(t_lane + c * 16, pk);
@@ -111,13 +169,40 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
     if (LP % 32) {
         uint32_t pk[8];
         ptx::tmem_ld_wait();
+        float c4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
             const float p0 = (NC * 32 + j < L) ? prob(r[NC & 1][j]) : 0.f;
             const float p1 = (NC * 32 + j + 1 < L) ? prob(r[NC & 1][j + 1]) : 0.f;
-            s4[(j >> 1) & 3] += p0 + p1;
+            c4[(j >> 1) & 3] += p0 + p1;
             pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
         }
+        if (RESCALE) {
+            const bool ovf = (c4[0] + c4[1]) + (c4[2] + c4[3]) >= 32768.0f;
+            if (__any_sync(0xffffffffu, ovf)) {
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (NC * 32 + j < L) m = fmaxf(m, __uint_as_float(r[NC & 1][j]));
+                const float new_ms = ovf ? fmaxf(ms, m * sl2) : ms;
+                const float f = fast_exp2(ms - new_ms);
+                ms = new_ms;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] *= f;
+                softmax_rescale_stored_p(t_lane, NC, f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c4[i] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const float p0 = (NC * 32 + j < L) ? prob(r[NC & 1][j]) : 0.f;
+                    const float p1 = (NC * 32 + j + 1 < L) ? prob(r[NC & 1][j + 1]) : 0.f;
+                    c4[(j >> 1) & 3] += p0 + p1;
+                    pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s4[i] += c4[i];
         ptx::tmem_st_32x32b_x8(t_lane + NC * 16, pk);
     }
     ptx::tmem_st_wait();

@@ -458,15 +458,12 @@ __device__ __forceinline__ int dev_pairwise_depth(int64_t n) {
     return d;
 }
 
-// One group of 8 lanes per leaf slot of the virtual complete tree of depth D; lane j owns accumulator r[j].
-__global__ void __launch_bounds__(256)
-pairwise_leaves_kernel(const double* __restrict__ a, const unsigned long long* n_ptr, int64_t n_minus,
-                       double* __restrict__ nodes) {
-    const int64_t T = (int64_t)(*n_ptr) - n_minus;   // number of terms
-    if (T <= 0) { if (blockIdx.x == 0 && threadIdx.x == 0) nodes[1] = 0.0; return; }
-    const int D = dev_pairwise_depth(T);
-    const int64_t g = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
-    const int j = threadIdx.x & 7;
+// One group of 8 lanes per leaf slot g of the virtual complete tree of depth D over T terms; lane j owns accumulator r[j].
+// All 8 lanes of a group take the same path.
+// (no __restrict__ on `a`: the single-launch kernel reads terms it wrote itself -- they must not go through the
+// non-coherent load path)
+__device__ __forceinline__ void pairwise_leaf_slot(const double* a, int64_t T, int D, int64_t g, int j,
+                                                   unsigned gmask, double* nodes) {
     if (g >= ((int64_t)1 << D)) return;
     int64_t off = 0, len = T;
     int lvl = 0;
@@ -479,7 +476,6 @@ pairwise_leaves_kernel(const double* __restrict__ a, const unsigned long long* n
     if (g & (((int64_t)1 << rem) - 1)) return;        // this leaf is represented by its left-most slot only
     const int64_t heap = ((int64_t)1 << lvl) + (g >> rem);
     const double* p = a + off;
-    const unsigned gmask = 0xffu << (threadIdx.x & 24);   // the 8 lanes of this group (all take the same path)
     double res;
     if (len < 8) {
         if (j != 0) return;
@@ -505,14 +501,21 @@ pairwise_leaves_kernel(const double* __restrict__ a, const unsigned long long* n
     }
 }
 
-// Internal nodes bottom-up (single block); finally writes the result (NaN if the curve is undefined).
-__global__ void __launch_bounds__(1024)
-pairwise_tree_kernel(const unsigned long long* n_ptr, int64_t n_minus, double* __restrict__ nodes, AucControl* c,
-                     double* __restrict__ out, int negate_clip) {
-    const int64_t T = (int64_t)(*n_ptr) - n_minus;
-    const int D = (T > 0) ? dev_pairwise_depth(T) : 0;
+__global__ void __launch_bounds__(256)
+pairwise_leaves_kernel(const double* __restrict__ a, const unsigned long long* n_ptr, int64_t n_minus,
+                       double* __restrict__ nodes) {
+    const int64_t T = (int64_t)(*n_ptr) - n_minus;   // number of terms
+    if (T <= 0) { if (blockIdx.x == 0 && threadIdx.x == 0) nodes[1] = 0.0; return; }
+    const int D = dev_pairwise_depth(T);
+    const int64_t g = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
+    pairwise_leaf_slot(a, T, D, g, threadIdx.x & 7, 0xffu << (threadIdx.x & 24), nodes);
+}
+
+// internal nodes of the numpy pairwise tree, bottom-up, by one block of NT threads (barrier per level)
+template <int NT>
+__device__ __forceinline__ void pairwise_tree_levels(int64_t T, int D, double* nodes) {
     for (int lvl = D - 1; lvl >= 0; --lvl) {
-        for (int64_t p = threadIdx.x; p < ((int64_t)1 << lvl); p += 1024) {
+        for (int64_t p = threadIdx.x; p < ((int64_t)1 << lvl); p += NT) {
             int64_t len = T;
             bool exists = true;
             for (int s = 0; s < lvl; ++s) {
@@ -527,6 +530,15 @@ pairwise_tree_kernel(const unsigned long long* n_ptr, int64_t n_minus, double* _
         }
         __syncthreads();
     }
+}
+
+// Internal nodes bottom-up (single block); finally writes the result (NaN if the curve is undefined).
+__global__ void __launch_bounds__(1024)
+pairwise_tree_kernel(const unsigned long long* n_ptr, int64_t n_minus, double* __restrict__ nodes, AucControl* c,
+                     double* __restrict__ out, int negate_clip) {
+    const int64_t T = (int64_t)(*n_ptr) - n_minus;
+    const int D = (T > 0) ? dev_pairwise_depth(T) : 0;
+    pairwise_tree_levels<1024>(T, D, nodes);
     if (threadIdx.x == 0) {
         double v = nodes[1];
         if (negate_clip) v = fmax(0.0, -v);
@@ -541,8 +553,9 @@ pairwise_tree_kernel(const unsigned long long* n_ptr, int64_t n_minus, double* _
 // precision_recall_curve (reversed, (1,0) appended) and average_precision_score = max(0, -sum(diff(recall)*precision[:-1])).
 // With m distinct thresholds j = 0..m-1 (descending score): reversed index i = m-1-j.
 __global__ void __launch_bounds__(256)
-auc_prc_terms_kernel(const uint32_t* __restrict__ d_tps, const uint32_t* __restrict__ d_fps, AucControl* c,
-                     double* __restrict__ terms, double* __restrict__ prec_out, double* __restrict__ rec_out) {
+auc_prc_terms_kernel(const uint32_t* __restrict__ d_tps, const uint32_t* __restrict__ d_fps,
+                     const uint32_t* __restrict__ d_key, AucControl* c, double* __restrict__ terms,
+                     double* __restrict__ prec_out, double* __restrict__ rec_out, float* __restrict__ pthr_out) {
     const int64_t m = (int64_t)c->n_distinct;
     const double ttot = (double)c->n_pos;
     auto prec = [&](int64_t j) {
@@ -556,6 +569,7 @@ auc_prc_terms_kernel(const uint32_t* __restrict__ d_tps, const uint32_t* __restr
         const double r_next = (i + 1 < m) ? rec(j - 1) : 0.0;
         terms[i] = __dmul_rn(__dsub_rn(r_next, r), p);
         if (prec_out) { prec_out[i] = p; rec_out[i] = r; }
+        if (pthr_out) pthr_out[i] = key_to_score(d_key[j]);     // thresholds[::-1]: the distinct scores, increasing
     }
     if (prec_out && blockIdx.x == 0 && threadIdx.x == 0) { prec_out[m] = 1.0; rec_out[m] = 0.0; }
 }
@@ -565,10 +579,309 @@ __global__ void auc_info_kernel(const AucControl* c, int64_t* info) {
     info[3] = (int64_t)c->n_kept + 1; info[4] = (int64_t)c->status; info[5] = info[6] = info[7] = 0;
 }
 
+
+// ------------------------------------------------------------------------------------------ single-launch path
+// The reference evaluates the AUC on 3 000 - 10 000 scores per class and epoch (ad_trainer.py:452-455, 516-522): there the
+// multi-kernel pipeline above is pure launch latency (15 launches, ~0.1 ms).  For n <= kSmallMax the whole computation
+// runs in ONE launch of ONE CTA: keys and label bits live in shared memory, 4 (or fewer) LSD radix passes with the same
+// match_any ranking as the tiled sort, then the tie / corner scans, the fp64 terms and numpy's pairwise tree, phase after
+// phase behind __syncthreads().  Every arithmetic step is the one of the multi-kernel path (same __d*_rn sequence, same
+// tree), so the result is bit-identical to it and to scikit-learn.
+constexpr int kSmallThreads = 1024;
+constexpr int kSmallItems = 16;
+constexpr int kSmallMax = kSmallThreads * kSmallItems;        // 16 384 scores
+
+struct SmallShared {
+    uint32_t keys[kSmallMax];
+    uint16_t warp_hist[32][256];
+    uint8_t labs[kSmallMax];
+    uint32_t digit_base[256];
+    uint32_t scan_tmp[32];
+    uint32_t and_all, or_all, n_valid, n_pos, status, pad[3];
+    double nodes[1024];                                       // pairwise tree: depth <= 8 for <= 16 385 terms
+};
+
+// exclusive prefix of one u32 per thread over the 1024 threads of the block; *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_tmp /*[32]*/, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_tmp[warp] = inc;
+    __syncthreads();
+    const uint32_t wt = s_tmp[lane];
+    uint32_t winc = wt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, winc, o);
+        if (lane >= o) winc += t;
+    }
+    const uint32_t woff = __shfl_sync(kFullMask, winc - wt, warp);
+    if (total) *total = __shfl_sync(kFullMask, winc, 31);
+    __syncthreads();
+    return woff + inc - v;
+}
+
+// numpy pairwise sum of a[0..T) by the whole block (nodes: shared memory, >= 2 << depth doubles); result in nodes[1]
+__device__ __forceinline__ double block_pairwise_sum(const double* a, int64_t T, double* nodes) {
+    if (T <= 0) return 0.0;
+    const int D = dev_pairwise_depth(T);
+    for (int64_t g0 = 0; g0 < ((int64_t)1 << D); g0 += kSmallThreads / 8)
+        pairwise_leaf_slot(a, T, D, g0 + (threadIdx.x >> 3), threadIdx.x & 7, 0xffu << (threadIdx.x & 24), nodes);
+    __syncthreads();
+    pairwise_tree_levels<kSmallThreads>(T, D, nodes);
+    const double v = nodes[1];
+    __syncthreads();
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSmallThreads, 1)
+auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ labels, int n, int flags,
+                 uint32_t* __restrict__ d_tps, uint32_t* __restrict__ d_fps, uint32_t* __restrict__ d_key,
+                 uint32_t* __restrict__ k_tps, uint32_t* __restrict__ k_fps, double* __restrict__ terms,
+                 double* __restrict__ auc_out, int64_t* __restrict__ info_out, double* __restrict__ fpr_out,
+                 double* __restrict__ tpr_out, float* __restrict__ thr_out, double* __restrict__ prec_out,
+                 double* __restrict__ rec_out, float* __restrict__ pthr_out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    SmallShared& sh = *reinterpret_cast<SmallShared*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int items = (n + kSmallThreads - 1) / kSmallThreads;      // <= kSmallItems, uniform
+    const int wbase = warp * items * 32;                             // this warp's contiguous chunk
+    if (tid == 0) { sh.and_all = 0xffffffffu; sh.or_all = 0u; sh.n_valid = 0; sh.n_pos = 0; sh.status = 0; }
+    __syncthreads();
+
+    // ---- 1 keys: score -> descending-sortable key, label bit, counts, constant-bit masks (to skip radix passes)
+    {
+        const bool ignore_neg = flags & EOE_AUC_IGNORE_NEGATIVE_LABELS;
+        uint32_t nv = 0, np = 0, bad = 0, a_and = 0xffffffffu, a_or = 0u;
+#pragma unroll
+        for (int j = 0; j < kSmallItems; ++j) {
+            const int idx = wbase + j * 32 + lane;
+            if (j < items && idx < n) {
+                const float f = to_f32<T>(scores[idx]);
+                const int64_t l = labels[idx];
+                uint32_t key = 0xffffffffu;          // dropped rows sort behind every finite score
+                uint8_t lb = 0;
+                if (!(ignore_neg && l < 0)) {
+                    if (!isfinite(f)) bad = 1;
+                    key = desc_key(f);
+                    lb = (l == 1);
+                    nv++;
+                    np += lb;
+                }
+                sh.keys[idx] = key;
+                sh.labs[idx] = lb;
+                a_and &= key;
+                a_or |= key;
+            }
+        }
+        nv = __reduce_add_sync(kFullMask, nv);
+        np = __reduce_add_sync(kFullMask, np);
+        bad = __reduce_or_sync(kFullMask, bad);
+        a_and = __reduce_and_sync(kFullMask, a_and);
+        a_or = __reduce_or_sync(kFullMask, a_or);
+        if (lane == 0) {
+            atomicAdd(&sh.n_valid, nv);
+            atomicAdd(&sh.n_pos, np);
+            if (bad) atomicOr(&sh.status, (uint32_t)EOE_AUC_STATUS_NONFINITE);
+            atomicAnd(&sh.and_all, a_and);
+            atomicOr(&sh.or_all, a_or);
+        }
+    }
+    __syncthreads();
+    const uint32_t varying = sh.and_all ^ sh.or_all;               // bits that differ between at least two keys
+
+    // ---- 2 sort: LSD radix, 8 bits per pass, in place in shared memory (keys are held in registers across the scatter)
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = pass * 8;
+        if (((varying >> shift) & 255u) == 0u) continue;           // every key has the same digit: the pass is the identity
+        reinterpret_cast<uint4*>(&sh.warp_hist[0][0])[tid] = make_uint4(0u, 0u, 0u, 0u);      // 32 x 256 x 2 B = 1024 x 16 B
+        uint32_t key[kSmallItems], rl[kSmallItems];                 // rl = rank within the warp's digit run | label << 16
+#pragma unroll
+        for (int j = 0; j < kSmallItems; ++j) {
+            const int idx = wbase + j * 32 + lane;
+            const bool valid = j < items && idx < n;
+            key[j] = valid ? sh.keys[idx] : 0xffffffffu;
+            rl[j] = valid ? ((uint32_t)sh.labs[idx] << 16) : 0u;
+        }
+        __syncthreads();
+        const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+        for (int j = 0; j < kSmallItems; ++j) {
+            if (j < items) {
+                const bool valid = (wbase + j * 32 + lane) < n;
+                const uint32_t d = (key[j] >> shift) & 255u;
+                const uint32_t mask = __match_any_sync(kFullMask, valid ? d : (256u + lane));
+                const int leader = __ffs(mask) - 1;
+                uint32_t old = 0;
+                if (lane == leader && valid) {
+                    old = sh.warp_hist[warp][d];
+                    sh.warp_hist[warp][d] = (uint16_t)(old + __popc(mask));
+                }
+                old = __shfl_sync(kFullMask, old, leader);
+                rl[j] |= old + __popc(mask & lt_mask);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        uint32_t run = 0;
+        if (tid < 256) {                                            // thread = digit: exclusive prefix over the 32 warps
+#pragma unroll 8
+            for (int w = 0; w < 32; ++w) {
+                const uint32_t t = sh.warp_hist[w][tid];
+                sh.warp_hist[w][tid] = (uint16_t)run;
+                run += t;
+            }
+        }
+        const uint32_t dstart = block_excl_scan_1024(run, sh.scan_tmp, nullptr);
+        if (tid < 256) sh.digit_base[tid] = dstart;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kSmallItems; ++j) {
+            if (j < items && (wbase + j * 32 + lane) < n) {
+                const uint32_t d = (key[j] >> shift) & 255u;
+                const uint32_t pos = sh.digit_base[d] + sh.warp_hist[warp][d] + (rl[j] & 0xffffu);
+                sh.keys[pos] = key[j];
+                sh.labs[pos] = (uint8_t)(rl[j] >> 16);
+            }
+        }
+        __syncthreads();
+    }
+
+    const int nv = (int)sh.n_valid;
+    const int npos = (int)sh.n_pos;
+    // ---- 3 distinct thresholds (blocked arrangement: thread t owns rows [t * per, (t + 1) * per))
+    int m = 0;
+    {
+        const int per = (nv + kSmallThreads - 1) / kSmallThreads;
+        const int lo = min(nv, tid * per), hi = min(nv, lo + per);
+        uint32_t fc = 0, lc = 0;
+        for (int i = lo; i < hi; ++i) {
+            fc += (i == nv - 1) || (sh.keys[i] != sh.keys[i + 1]);
+            lc += sh.labs[i];
+        }
+        uint32_t tot_f;
+        uint32_t slot = block_excl_scan_1024(fc, sh.scan_tmp, &tot_f);
+        uint32_t tps = block_excl_scan_1024(lc, sh.scan_tmp, nullptr);
+        m = (int)tot_f;
+        for (int i = lo; i < hi; ++i) {
+            tps += sh.labs[i];
+            if ((i == nv - 1) || (sh.keys[i] != sh.keys[i + 1])) {
+                d_tps[slot] = tps;
+                d_fps[slot] = 1u + (uint32_t)i - tps;
+                d_key[slot] = sh.keys[i];
+                ++slot;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 4 corners (roc_curve drop_intermediate=True), origin prepended
+    int kept = 0;
+    {
+        const int per = (m + kSmallThreads - 1) / kSmallThreads;
+        const int lo = min(m, tid * per), hi = min(m, lo + per);
+        auto keep_at = [&](int i) {
+            if (m <= 2 || i == 0 || i == m - 1) return true;
+            const int64_t f0 = d_fps[i - 1], f1 = d_fps[i], f2 = d_fps[i + 1];
+            const int64_t t0 = d_tps[i - 1], t1 = d_tps[i], t2 = d_tps[i + 1];
+            return (f0 - 2 * f1 + f2 != 0) || (t0 - 2 * t1 + t2 != 0);
+        };
+        uint32_t kc = 0;
+        for (int i = lo; i < hi; ++i) kc += keep_at(i);
+        uint32_t tot;
+        uint32_t slot = block_excl_scan_1024(kc, sh.scan_tmp, &tot) + 1;      // +1: the prepended origin
+        kept = (int)tot;
+        if (tid == 0) {
+            k_tps[0] = 0; k_fps[0] = 0;
+            if (thr_out) thr_out[0] = INFINITY;
+        }
+        for (int i = lo; i < hi; ++i) {
+            if (keep_at(i)) {
+                k_tps[slot] = d_tps[i];
+                k_fps[slot] = d_fps[i];
+                if (thr_out) thr_out[slot] = key_to_score(d_key[i]);
+                ++slot;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 5 terms (same operation sequence as auc_terms_kernel)
+    {
+        const int P = kept + 1;
+        const double ftot = (double)(nv - npos), ttot = (double)npos;
+        for (int i = tid; i < P; i += kSmallThreads) {
+            const double f0 = __ddiv_rn((double)k_fps[i], ftot), t0 = __ddiv_rn((double)k_tps[i], ttot);
+            if (fpr_out) { fpr_out[i] = f0; tpr_out[i] = t0; }
+            if (i + 1 < P) {
+                const double f1 = __ddiv_rn((double)k_fps[i + 1], ftot), t1 = __ddiv_rn((double)k_tps[i + 1], ttot);
+                terms[i] = __ddiv_rn(__dmul_rn(__dsub_rn(f1, f0), __dadd_rn(t1, t0)), 2.0);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 6/7 numpy pairwise sum
+    const bool single = (npos == 0) || (npos == nv);
+    const uint32_t status = sh.status | (single ? (uint32_t)EOE_AUC_STATUS_SINGLE_CLASS : 0u);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const bool undefined = single || (status & ~(uint32_t)EOE_AUC_STATUS_SINGLE_CLASS);
+    {
+        const double v = block_pairwise_sum(terms, kept, sh.nodes);
+        if (tid == 0) auc_out[0] = undefined ? qnan : v;
+    }
+    // ---- PRC / average precision (same operation sequence as auc_prc_terms_kernel)
+    if (flags & EOE_AUC_WITH_PRC) {
+        const double ttot = (double)npos;
+        auto prec = [&](int j) {
+            const double tp = (double)d_tps[j], ps = __dadd_rn(tp, (double)d_fps[j]);
+            return ps != 0.0 ? __ddiv_rn(tp, ps) : 0.0;
+        };
+        auto rec = [&](int j) { return ttot == 0.0 ? 1.0 : __ddiv_rn((double)d_tps[j], ttot); };
+        for (int i = tid; i < m; i += kSmallThreads) {
+            const int j = m - 1 - i;
+            const double p = prec(j), r = rec(j);
+            const double r_next = (i + 1 < m) ? rec(j - 1) : 0.0;
+            terms[i] = __dmul_rn(__dsub_rn(r_next, r), p);
+            if (prec_out) { prec_out[i] = p; rec_out[i] = r; }
+            if (pthr_out) pthr_out[i] = key_to_score(d_key[j]);
+        }
+        if (prec_out && tid == 0) { prec_out[m] = 1.0; rec_out[m] = 0.0; }
+        __syncthreads();
+        const double v = block_pairwise_sum(terms, m, sh.nodes);
+        if (tid == 0) auc_out[1] = undefined ? qnan : fmax(0.0, -v);
+    }
+    if (info_out && tid == 0) {
+        info_out[0] = nv; info_out[1] = npos; info_out[2] = m; info_out[3] = kept + 1; info_out[4] = (int64_t)status;
+        info_out[5] = info_out[6] = info_out[7] = 0;
+    }
+}
+
+template <typename T>
+static int auc_run_small(const void* scores, const int64_t* labels, int64_t n, int flags, char* ws, const AucLayout& L,
+                         double* auc_out, int64_t* info_out, double* fpr_out, double* tpr_out, float* thr_out,
+                         double* prec_out, double* rec_out, float* pthr_out, cudaStream_t st) {
+    static bool attr_set = false;                      // per process and instantiation; the attribute is per function
+    auto kern = auc_small_kernel<T>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
+        if (e != cudaSuccess) { set_cuda_error(e, "auc small attribute"); return EOE_ERR_CUDA; }
+        attr_set = true;
+    }
+    kern<<<1, kSmallThreads, sizeof(SmallShared), st>>>(
+        (const T*)scores, labels, (int)n, flags, (uint32_t*)(ws + L.d_tps), (uint32_t*)(ws + L.d_fps),
+        (uint32_t*)(ws + L.keys_b), (uint32_t*)(ws + L.k_tps), (uint32_t*)(ws + L.k_fps), (double*)(ws + L.terms), auc_out,
+        info_out, fpr_out, tpr_out, thr_out, prec_out, rec_out, pthr_out);
+    return check_launch("auc (single launch)", 1);
+}
+
 template <typename T>
 static int auc_run(const void* scores, const int64_t* labels, int64_t n, int flags, char* ws, const AucLayout& L,
                    double* auc_out, int64_t* info_out, double* fpr_out, double* tpr_out, float* thr_out,
-                   double* prec_out, double* rec_out, cudaStream_t st) {
+                   double* prec_out, double* rec_out, float* pthr_out, cudaStream_t st) {
     AucControl* c = (AucControl*)(ws + L.control);
     uint32_t* keys_a = (uint32_t*)(ws + L.keys_a);
     uint32_t* keys_b = (uint32_t*)(ws + L.keys_b);
@@ -604,7 +917,7 @@ static int auc_run(const void* scores, const int64_t* labels, int64_t n, int fla
     pairwise_leaves_kernel<<<lgrid, 256, 0, st>>>(terms, &c->n_kept, 0, nodes);
     pairwise_tree_kernel<<<1, 1024, 0, st>>>(&c->n_kept, 0, nodes, c, auc_out, 0);
     if (flags & EOE_AUC_WITH_PRC) {
-        auc_prc_terms_kernel<<<tgrid, 256, 0, st>>>(d_tps, d_fps, c, terms, prec_out, rec_out);
+        auc_prc_terms_kernel<<<tgrid, 256, 0, st>>>(d_tps, d_fps, keys_b, c, terms, prec_out, rec_out, pthr_out);
         pairwise_leaves_kernel<<<lgrid, 256, 0, st>>>(terms, &c->n_distinct, 0, nodes);
         pairwise_tree_kernel<<<1, 1024, 0, st>>>(&c->n_distinct, 0, nodes, c, auc_out + 1, 1);
     }
@@ -624,7 +937,7 @@ extern "C" size_t eoe_auc_workspace_bytes(int64_t n) {
 extern "C" int eoe_auc(const void* scores, int score_dtype, const int64_t* labels, int64_t n, int flags,
                        void* workspace, size_t workspace_bytes, double* auc_out, int64_t* info_out,
                        double* fpr_out, double* tpr_out, float* thr_out, double* prec_out, double* rec_out,
-                       void* stream) {
+                       float* prc_thr_out, void* stream) {
     if (!scores || !labels || !auc_out || n <= 0) return EOE_ERR_ARG;
     if (n >= ((int64_t)1 << 30)) return EOE_ERR_SHAPE;
     if ((fpr_out == nullptr) != (tpr_out == nullptr)) return EOE_ERR_ARG;
@@ -633,10 +946,18 @@ extern "C" int eoe_auc(const void* scores, int score_dtype, const int64_t* label
     if (!workspace || workspace_bytes < L.total) return EOE_ERR_WORKSPACE;
     if ((uintptr_t)workspace % 256 != 0) return EOE_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    const bool small = n <= kSmallMax && !(flags & EOE_AUC_FORCE_TILED);
+#define EOE_AUC_DISPATCH(T)                                                                                              \
+    return small ? auc_run_small<T>(scores, labels, n, flags, ws, L, auc_out, info_out, fpr_out, tpr_out, thr_out,       \
+                                    prec_out, rec_out, prc_thr_out, st)                                                  \
+                 : auc_run<T>(scores, labels, n, flags, ws, L, auc_out, info_out, fpr_out, tpr_out, thr_out, prec_out,   \
+                              rec_out, prc_thr_out, st)
     switch (score_dtype) {
-        case EOE_F32: return auc_run<float>(scores, labels, n, flags, (char*)workspace, L, auc_out, info_out, fpr_out, tpr_out, thr_out, prec_out, rec_out, st);
-        case EOE_F16: return auc_run<__half>(scores, labels, n, flags, (char*)workspace, L, auc_out, info_out, fpr_out, tpr_out, thr_out, prec_out, rec_out, st);
-        case EOE_BF16: return auc_run<__nv_bfloat16>(scores, labels, n, flags, (char*)workspace, L, auc_out, info_out, fpr_out, tpr_out, thr_out, prec_out, rec_out, st);
+        case EOE_F32: EOE_AUC_DISPATCH(float);
+        case EOE_F16: EOE_AUC_DISPATCH(__half);
+        case EOE_BF16: EOE_AUC_DISPATCH(__nv_bfloat16);
         default: return EOE_ERR_DTYPE;
     }
+#undef EOE_AUC_DISPATCH
 }

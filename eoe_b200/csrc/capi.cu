@@ -30,6 +30,11 @@ int check_launch(const char* where, int n_launched) {
 
 extern "C" int eoe_abi_version(void) { return EOE_ABI_VERSION; }
 
+#ifndef EOE_BUILD_ID
+#define EOE_BUILD_ID "unknown"
+#endif
+extern "C" const char* eoe_build_id(void) { return EOE_BUILD_ID; }
+
 extern "C" long long eoe_launch_count(void) { return eoe::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* eoe_last_cuda_error(void) { return eoe::g_cuda_err; }

@@ -47,9 +47,12 @@ constexpr float kGeluHalfSlope = 0.851f, kGeluSlope = 1.702f;
 //     chunk sums of the tile's rows, single-buffered because they are reduced to (mean, rstd) at the top of the tile
 // and the TMA ring takes what is left.
 // 1.702 * QuickGELU(a) given a' = 0.851 a:  a' (1 + tanh a')  (bf16)  |  2 a' / (1 + exp(-2 a'))  (fp16, exact form)
+#ifndef EOE_F16_GELU_EXACT
+#define EOE_F16_GELU_EXACT 0       // 1: fp16 outputs use exp + divide (2 MUFU per element) instead of the single tanh.approx
+#endif
 template <bool BF16>
 __device__ __forceinline__ float quick_gelu_x(float ap) {
-    if (BF16) {
+    if (BF16 || !EOE_F16_GELU_EXACT) {
         float t;
         asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(ap));
         return fmaf(ap, t, ap);
@@ -115,7 +118,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // tanh.approx (abs error ~5e-4 on the sigmoid, below the output rounding); fp16 output keeps exp + divide.
 template <bool BF16>
 __device__ __forceinline__ float quick_gelu(float x) {
-    if (BF16) {
+    if (BF16 || !EOE_F16_GELU_EXACT) {
         float t;
         asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
         const float hx = 0.5f * x;

@@ -18,6 +18,31 @@ def world() -> Tuple[int, int]:
     return 0, 1
 
 
+def bind_to_gpu_numa(local_rank: int) -> Optional[List[int]]:
+    """Pin this process to the CPUs local to its GPU's PCIe root (sysfs `local_cpulist`), so that pinned host buffers
+    allocated afterwards are first-touched on the GPU's NUMA node and the H2D feed does not cross the socket interconnect
+    (the e2e feed of N ranks on one host).  Returns the CPU list, or None when the topology is not
+    exposed (single-node VMs): then nothing is changed."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (int(pr.pci_domain_id), int(pr.pci_bus_id), int(pr.pci_device_id))
+        path = f"/sys/bus/pci/devices/{bdf}/local_cpulist"
+        cpus: List[int] = []
+        for part in open(path).read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     """torchrun contract: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT. Returns (rank, local_rank, world)."""
     ws = int(os.environ.get("WORLD_SIZE", "1"))

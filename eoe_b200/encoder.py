@@ -23,7 +23,7 @@ def _strip(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
 
 
 class ClipImageEncoder(nn.Module):
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", operand_dtype=torch.bfloat16,
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", operand_dtype=torch.float16,
                  max_batch: int = 256, heads: Optional[int] = None, resolution: Optional[int] = None,
                  fold_layernorm: bool = True, input_mean=(0.48145466, 0.4578275, 0.40821073),
                  input_std=(0.26862954, 0.26130258, 0.27577711)):

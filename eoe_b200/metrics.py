@@ -65,12 +65,14 @@ _default_ws = AucWorkspace()
 
 
 def roc_auc_device(scores: torch.Tensor, labels: torch.Tensor, *, ignore_negative_labels: bool = False,
-                   with_prc: bool = False, curves: bool = False, workspace: Optional[AucWorkspace] = None):
+                   with_prc: bool = False, curves: bool = False, workspace: Optional[AucWorkspace] = None,
+                   force_tiled: bool = False):
     """Launch the AUC pipeline asynchronously on the current stream.
 
     Returns (out, info, arrays): `out` float64[2] device = (auc, average precision), `info` int64[8] device
     (n kept, n pos, n distinct, n ROC points, status bits), `arrays` dict of device curve buffers or None.
-    No host synchronisation happens here."""
+    No host synchronisation happens here.  Up to EOE_AUC_SINGLE_LAUNCH_MAX scores this is ONE kernel launch
+    (`force_tiled` selects the multi-kernel radix-sort pipeline anyway: tests compare the two bit for bit)."""
     L.require_cuda(scores, labels)
     scores = scores.detach().reshape(-1).contiguous()
     if scores.dtype not in L.DTYPE_CODE:
@@ -84,7 +86,7 @@ def roc_auc_device(scores: torch.Tensor, labels: torch.Tensor, *, ignore_negativ
         raise L.EoeError("scores and labels differ in length")
     w = (workspace or _default_ws).ensure(n, scores.device)
     arrays = None
-    fpr = tpr = thr = prec = rec = None
+    fpr = tpr = thr = prec = rec = pthr = None
     if curves:
         fpr = torch.empty(n + 1, dtype=torch.float64, device=scores.device)
         tpr = torch.empty(n + 1, dtype=torch.float64, device=scores.device)
@@ -93,11 +95,13 @@ def roc_auc_device(scores: torch.Tensor, labels: torch.Tensor, *, ignore_negativ
         if with_prc:
             prec = torch.empty(n + 1, dtype=torch.float64, device=scores.device)
             rec = torch.empty(n + 1, dtype=torch.float64, device=scores.device)
-            arrays.update(prec=prec, rec=rec)
-    flags = (L.EOE_AUC_IGNORE_NEGATIVE_LABELS if ignore_negative_labels else 0) | (L.EOE_AUC_WITH_PRC if with_prc else 0)
+            pthr = torch.empty(n, dtype=torch.float32, device=scores.device)
+            arrays.update(prec=prec, rec=rec, pthr=pthr)
+    flags = ((L.EOE_AUC_IGNORE_NEGATIVE_LABELS if ignore_negative_labels else 0) | (L.EOE_AUC_WITH_PRC if with_prc else 0)
+             | (L.EOE_AUC_FORCE_TILED if force_tiled else 0))
     L.check(L.lib().eoe_auc(L.ptr(scores), L.dtype_code(scores), L.ptr(labels), n, flags, L.ptr(w.ws),
                             w.ws.numel(), L.ptr(w.out), L.ptr(w.info), L.ptr(fpr), L.ptr(tpr), L.ptr(thr),
-                            L.ptr(prec), L.ptr(rec), L.stream_ptr(scores.device)), "eoe_auc")
+                            L.ptr(prec), L.ptr(rec), L.ptr(pthr), L.stream_ptr(scores.device)), "eoe_auc")
     return w.out, w.info, arrays
 
 
@@ -116,11 +120,11 @@ def roc_auc(scores, labels, **kw) -> float:
     return float(host[:2].view(torch.float64)[0])
 
 
-def roc_curve_auc(scores, labels, with_prc: bool = False, ignore_negative_labels: bool = False
+def roc_curve_auc(scores, labels, with_prc: bool = False, ignore_negative_labels: bool = False, force_tiled: bool = False
                   ) -> Tuple[Optional[ROC], Optional[PRC]]:
     """What eval_cls keeps (ad_trainer.py:516-527): (ROC, PRC) or (None, None) if a class is missing."""
     out, info, arr = roc_auc_device(scores, labels, with_prc=with_prc, curves=True,
-                                    ignore_negative_labels=ignore_negative_labels)
+                                    ignore_negative_labels=ignore_negative_labels, force_tiled=force_tiled)
     info_h = info.cpu()
     _raise_on_status(int(info_h[4]))
     if int(info_h[4]) & L.EOE_AUC_STATUS_SINGLE_CLASS:
@@ -132,7 +136,8 @@ def roc_curve_auc(scores, labels, with_prc: bool = False, ignore_negative_labels
               arr["thr"][:npts].cpu().numpy().astype(score_np_dtype), float(out_h[0]))
     prc = None
     if with_prc:
-        # thresholds of precision_recall_curve: the distinct scores in increasing order; not needed by the
-        # reference beyond storage, recomputed on request from the ROC-independent distinct list is future work
-        prc = PRC(arr["prec"][:m + 1].cpu().numpy(), arr["rec"][:m + 1].cpu().numpy(), None, float(out_h[1]))
+        # thresholds of precision_recall_curve: the distinct scores in increasing order (the reference's logger averages
+        # them over seeds / classes, utils/logger.py:103-111, so they must be an array like sklearn's)
+        prc = PRC(arr["prec"][:m + 1].cpu().numpy(), arr["rec"][:m + 1].cpu().numpy(),
+                  arr["pthr"][:m].cpu().numpy().astype(score_np_dtype), float(out_h[1]))
     return roc, prc

@@ -7,7 +7,7 @@ building blocks, one call per block, instead of a fused plan:
     12 x [ eoe_layernorm -> eoe_gemm(bias) -> eoe_attention_causal -> eoe_gemm(+= residual)
            eoe_layernorm -> eoe_gemm(bias, QuickGELU) -> eoe_gemm(+= residual) ]  (model.py:167-188, mask :324-331)
     eoe_text_tail                       ln_final at the <eot> row @ text_projection (model.py:346-350)
-Residual stream, LayerNorm statistics and the tail are fp32; GEMM operands bf16 (default) or fp16.  Weights load from
+Residual stream, LayerNorm statistics and the tail are fp32; GEMM operands fp16 (default: the reference GPU dtype, clip_official/clip/model.py:371-392) or bf16.  Weights load from
 the reference's state_dict keys (`token_embedding.weight`, `positional_embedding`, `transformer.resblocks.*`,
 `ln_final.*`, `text_projection`).  Tokenisation is host string processing and stays with the caller
 (`clip_official/clip/clip.py:164-197` `tokenize`, or any function returning `[K, 77]` int64 ids)."""
@@ -21,7 +21,7 @@ from . import encoder as E
 
 
 class ClipTextEncoder(nn.Module):
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", operand_dtype=torch.bfloat16, heads: int = None):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", operand_dtype=torch.float16, heads: int = None):
         super().__init__()
         if operand_dtype not in (torch.bfloat16, torch.float16):
             raise L.EoeError("operand_dtype must be torch.bfloat16 or torch.float16")

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EOE_ABI_VERSION 4
+#define EOE_ABI_VERSION 5
 
 enum { EOE_F32 = 0, EOE_F16 = 1, EOE_BF16 = 2 };
 
@@ -49,6 +49,10 @@ const char* eoe_strerror(int code);
 const char* eoe_last_cuda_error(void);
 /* number of CUDA kernels this library has launched in this process so far (bench.py's `gpu_launches`) */
 long long eoe_launch_count(void);
+/* identity of the kernel sources this library was built from (first 16 hex digits of a sha256 over csrc/ and this header;
+ * eoe_b200/build.py:source_id).  bench.py only quotes ncu-derived figures (profiles/gemm_traffic.json) whose recorded id
+ * equals this one. */
+const char* eoe_build_id(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Loss / score heads.  `head_ws` is a zero-initialised device buffer of EOE_HEAD_WS_BYTES bytes
@@ -130,8 +134,12 @@ int eoe_clip_oe_loss_fwd_bwd(const void* z, int z_dtype, const float* text, cons
  * ---------------------------------------------------------------------------------------------- */
 enum {
     EOE_AUC_IGNORE_NEGATIVE_LABELS = 1,   /* drop rows with label < 0 (ad_trainer.py:517 filter)   */
-    EOE_AUC_WITH_PRC = 2                  /* also compute average precision (+ PRC arrays if given) */
+    EOE_AUC_WITH_PRC = 2,                 /* also compute average precision (+ PRC arrays if given) */
+    EOE_AUC_FORCE_TILED = 4               /* n <= EOE_AUC_SINGLE_LAUNCH_MAX: use the multi-kernel pipeline anyway (tests) */
 };
+#define EOE_AUC_SINGLE_LAUNCH_MAX 16384   /* up to here eoe_auc is ONE kernel launch of one CTA (the reference's sizes:
+                                             3 000 - 10 000 scores per class and epoch, ad_trainer.py:452-455,516-522);
+                                             larger inputs run the tiled radix-sort pipeline (15 launches) */
 enum {                                    /* bits of info_out[4]                                    */
     EOE_AUC_STATUS_NONFINITE = 1,         /* a kept score is NaN/Inf (sklearn raises ValueError)     */
     EOE_AUC_STATUS_SINGLE_CLASS = 2       /* only one class present: AUC undefined (NaN)             */
@@ -142,11 +150,13 @@ size_t eoe_auc_workspace_bytes(int64_t n);
  *   info_out [8] int64 device: [0] n kept, [1] n positives, [2] n distinct scores,
  *                               [3] n ROC points (incl. the prepended origin), [4] status bits
  *   fpr_out, tpr_out [n+1] fp64, thr_out [n+1] fp32 (thr[0] = +inf): ROC curve, nullable (all three or none)
- *   prec_out, rec_out [n+1] fp64: PRC in sklearn's (reversed, (1,0)-terminated) order, nullable */
+ *   prec_out, rec_out [n+1] fp64: PRC in sklearn's (reversed, (1,0)-terminated) order, nullable
+ *   prc_thr_out [n] fp32: precision_recall_curve's thresholds (the distinct scores, increasing; info_out[2] of them),
+ *                         nullable; needs EOE_AUC_WITH_PRC (what eoe.utils.logger.PRC.ths holds, logger.py:65-91) */
 int eoe_auc(const void* scores, int score_dtype, const int64_t* labels, int64_t n, int flags,
             void* workspace, size_t workspace_bytes, double* auc_out, int64_t* info_out,
             double* fpr_out, double* tpr_out, float* thr_out, double* prec_out, double* rec_out,
-            void* stream);
+            float* prc_thr_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * CLIP ViT-B image encoder forward (+ optional fused zero-shot score head).

@@ -103,6 +103,21 @@ def vit_images(B=2, res=224, seed=VIT_IMAGE_SEED):
     return torch.randn(B, 3, res, res, generator=g)
 
 
+SCORE_PARITY_IMAGES = 64
+SCORE_PARITY_CFGS = ((32, 10), (16, 30))        # BASELINE configs 2 and 3: (patch, prompts)
+
+
+def score_parity_inputs(K, n_img=SCORE_PARITY_IMAGES, seed=17):
+    """End-to-end score parity: seeded 224x224 images, K unit prompt rows (SURVEY 8d cfg2/cfg3:
+    `normalize(randn(K,512))`), Bernoulli(0.9 anomalous) labels for the AUC of the scores."""
+    imgs = vit_images(B=n_img, seed=VIT_IMAGE_SEED + 100)
+    g = torch.Generator().manual_seed(seed + K)
+    text = torch.nn.functional.normalize(torch.randn(K, 512, generator=g), dim=-1).numpy().astype(np.float32)
+    labels = (torch.rand(n_img, generator=g) < 0.9).numpy().astype(np.int64)
+    labels[0], labels[1] = 0, 1                    # both classes present whatever the draw
+    return imgs, text, labels
+
+
 def text_tokens(n=10, seed=TEXT_TOKEN_SEED):
     """[n, 77] prompt rows shaped like `tokenize` output (leave-one-out prompt set of cfg2: 10 prompts)."""
     from oracle import text as otext

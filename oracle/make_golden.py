@@ -10,6 +10,7 @@ are created from the reference's own code executed here on seeded synthetic inpu
              src/eoe/training/ad_trainer.py:453-454,517-521
   vit_*.npz  CLIP(...).encode_image (clip_official/clip/model.py:219-236,336-337) with the seeded
              weights of oracle.vit.synth_state_dict loaded into the reference module
+  score_parity_b*.npz  encode_image (fp32 and half) -> ADClipTrainer.compute_anomaly_score on 64 images (cfg2 / cfg3)
   text.npz   CLIP(...).encode_text (clip_official/clip/model.py:339-352) with the seeded weights of
              oracle.text.synth_text_state_dict on seeded token rows
 Inputs are re-derived from seeds at test time (oracle.golden_inputs) so fixtures stay small;
@@ -111,6 +112,39 @@ def make_vit(h):
                             img_sum=np.float64(imgs.double().sum()), w_sum=np.float64(w_sum))
 
 
+def live_half_features(h, patch, sd, imgs):
+    """The reference's own GPU precision, executed by the live reference on the CPU: `convert_weights` (model.py:371-392)
+    + fp16 images (model.py:337).  Rounding points are the reference's; only accumulation order differs from cuBLAS."""
+    from eoe.models.clip_official.clip.model import convert_weights
+    m = h["CLIP"](512, 224, 12, 768, patch, 77, 49408, 512, 8, 12).eval()
+    m.load_state_dict(sd, strict=False)
+    convert_weights(m)
+    out = []
+    with torch.no_grad():
+        for s in range(0, imgs.shape[0], 16):
+            out.append(m.encode_image(imgs[s:s + 16].half()).float())
+    return torch.cat(out).numpy()
+
+
+def make_score_parity(h):
+    """score_parity_b{32,16}.npz: the zero-shot path END TO END through the live reference -- CLIP.encode_image (fp32, and
+    in half = the reference's GPU precision) followed by ADClipTrainer.compute_anomaly_score (clip.py:66-79) -- on
+    gi.score_parity_inputs.  tests/test_gpu_encoder.py::test_end_to_end_scores compares enc.score() with these."""
+    for patch, K in gi.SCORE_PARITY_CFGS:
+        sd = vit.synth_state_dict(patch, seed=gi.VIT_WEIGHT_SEED)
+        imgs, text, labels = gi.score_parity_inputs(K)
+        m = h["CLIP"](512, 224, 12, 768, patch, 77, 49408, 512, 8, 12).eval()
+        m.load_state_dict(sd, strict=False)
+        with torch.no_grad():
+            f32 = torch.cat([m.encode_image(imgs[s:s + 16]) for s in range(0, imgs.shape[0], 16)])
+        f16 = torch.from_numpy(live_half_features(h, patch, sd, imgs))
+        tt = torch.from_numpy(text)
+        score = lambda f: h["ADClipTrainer"].compute_anomaly_score(_Self("leave_one_out"), f, tt).numpy()
+        np.savez_compressed(os.path.join(OUT, f"score_parity_b{patch}.npz"), features=f32.numpy(), scores=score(f32),
+                            features_ref_half=f16.numpy(), scores_ref_half=score(f16), text=text, labels=labels,
+                            img_sum=np.float64(imgs.double().sum()))
+
+
 def make_text(h):
     sd = otext.synth_text_state_dict(seed=gi.TEXT_WEIGHT_SEED)
     tokens = gi.text_tokens()
@@ -148,6 +182,7 @@ def main():
     make_heads(h)
     make_auc()
     make_vit(h)
+    make_score_parity(h)
     make_text(h)
     make_resize()
     print("golden fixtures written to", OUT)

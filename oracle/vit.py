@@ -86,8 +86,14 @@ def n_layers_of(sd):
     return len({k.split(".")[3] for k in sd if k.startswith("visual.transformer.resblocks.")})
 
 
-def _r(t, dt):
-    return t if dt is None else t.to(dt).to(torch.float32)
+ROUND_POINTS = ("patch", "w", "xb", "qkv", "p", "h", "u")
+_active_points = None          # None = every point; else the subset that is rounded (error attribution, tools/score_parity.py)
+
+
+def _r(t, dt, point=None):
+    if dt is None or (_active_points is not None and point is not None and point not in _active_points):
+        return t
+    return t.to(dt).to(torch.float32)
 
 
 def _ln_linear(x, ln_w, ln_b, W, bias, dt, fold, shift=None):
@@ -96,8 +102,8 @@ def _ln_linear(x, ln_w, ln_b, W, bias, dt, fold, shift=None):
     width = x.shape[-1]
     if not fold or dt is None:
         h = F.layer_norm(x, (width,), ln_w, ln_b, 1e-5)
-        return F.linear(_r(h, dt), _r(W, dt), bias)
-    wf = _r(W * ln_w, dt)
+        return F.linear(_r(h, dt, "xb"), _r(W, dt, "w"), bias)
+    wf = _r(W * ln_w, dt, "w")
     c1 = wf.sum(dim=1)
     c2 = W @ ln_b + bias
     mean = x.mean(dim=-1, keepdim=True)
@@ -105,13 +111,23 @@ def _ln_linear(x, ln_w, ln_b, W, bias, dt, fold, shift=None):
     rstd = torch.rsqrt(var.clamp_min(0) + 1e-5)
     if shift is None:
         shift = torch.zeros_like(mean)
-    return rstd * (_r(x - shift, dt) @ wf.t() - (mean - shift) * c1) + c2
+    return rstd * (_r(x - shift, dt, "xb") @ wf.t() - (mean - shift) * c1) + c2
 
 
 @torch.no_grad()
 def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens: bool = False,
-                 fold_layernorm: bool = False):
-    """model.py:219-236. imgs [B,3,R,R] float32 (already CLIP-normalised) -> features [B, embed]."""
+                 fold_layernorm: bool = False, points=None):
+    """model.py:219-236. imgs [B,3,R,R] float32 (already CLIP-normalised) -> features [B, embed].
+    points: subset of ROUND_POINTS that is rounded to operand_dtype (None = all of them)."""
+    global _active_points
+    _active_points = None if points is None else set(points)
+    try:
+        return _encode_image(sd, imgs, operand_dtype, heads, return_tokens, fold_layernorm)
+    finally:
+        _active_points = None
+
+
+def _encode_image(sd, imgs, operand_dtype, heads, return_tokens, fold_layernorm):
     dt = operand_dtype
     f32 = torch.float32
     w = {k: v.to(f32) for k, v in sd.items()}
@@ -120,7 +136,7 @@ def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens
     B = imgs.shape[0]
     layers = n_layers_of(sd)
     # model.py:220-222  conv1 (stride = kernel = P, no bias) -> [B, g*g, width]
-    x = F.conv2d(_r(imgs.to(f32), dt), _r(conv_w, dt), stride=P)
+    x = F.conv2d(_r(imgs.to(f32), dt, "patch"), _r(conv_w, dt, "w"), stride=P)
     x = x.reshape(B, width, -1).permute(0, 2, 1)
     # model.py:223-225  class token, positional embedding, ln_pre
     cls = w["visual.class_embedding"].expand(B, 1, width)
@@ -134,7 +150,7 @@ def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens
         # model.py:186  x = x + attn(ln_1(x))
         qkv = _ln_linear(x, w[p + "ln_1.weight"], w[p + "ln_1.bias"], w[p + "attn.in_proj_weight"],
                          w[p + "attn.in_proj_bias"], dt, fold_layernorm, shift)
-        qkv = _r(qkv, dt)
+        qkv = _r(qkv, dt, "qkv")
         q, k, v = qkv.split(width, dim=-1)
         q = q.reshape(B, L, heads, dh).transpose(1, 2)
         k = k.reshape(B, L, heads, dh).transpose(1, 2)
@@ -146,10 +162,10 @@ def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens
         else:
             # CUDA path: un-normalised exp in 16 bit for the PV product, fp32 row sum, divide after
             e = torch.exp(s - s.amax(dim=-1, keepdim=True))
-            o = (_r(e, dt) @ v) / e.sum(dim=-1, keepdim=True)
-        o = _r(o.transpose(1, 2).reshape(B, L, width), dt)
+            o = (_r(e, dt, "p") @ v) / e.sum(dim=-1, keepdim=True)
+        o = _r(o.transpose(1, 2).reshape(B, L, width), dt, "h")
         shift = x.mean(dim=-1, keepdim=True)      # the residual GEMM centres xb on the row's mean BEFORE its update
-        x = x + F.linear(o, _r(w[p + "attn.out_proj.weight"], dt), w[p + "attn.out_proj.bias"])
+        x = x + F.linear(o, _r(w[p + "attn.out_proj.weight"], dt, "w"), w[p + "attn.out_proj.bias"])
         # model.py:187  x = x + mlp(ln_2(x)),  mlp = c_proj(QuickGELU(c_fc(.)))  (model.py:173-177)
         fold_mlp = fold_layernorm and dt is not None and i < layers - 1
         u = _ln_linear(x, w[p + "ln_2.weight"], w[p + "ln_2.bias"], w[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"], dt,
@@ -157,16 +173,68 @@ def encode_image(sd, imgs, operand_dtype=None, heads: int = HEADS, return_tokens
         shift = x.mean(dim=-1, keepdim=True)
         if fold_mlp:
             # the folded path stores 1.702 * QuickGELU and multiplies by c_proj weights pre-divided by 1.702
-            u = _r(1.702 * u * torch.sigmoid(1.702 * u), dt)
-            x = x + F.linear(u, _r(w[p + "mlp.c_proj.weight"] / 1.702, dt), w[p + "mlp.c_proj.bias"])
+            u = _r(1.702 * u * torch.sigmoid(1.702 * u), dt, "u")
+            x = x + F.linear(u, _r(w[p + "mlp.c_proj.weight"] / 1.702, dt, "w"), w[p + "mlp.c_proj.bias"])
         else:
-            u = _r(u * torch.sigmoid(1.702 * u), dt)
-            x = x + F.linear(u, _r(w[p + "mlp.c_proj.weight"], dt), w[p + "mlp.c_proj.bias"])
+            u = _r(u * torch.sigmoid(1.702 * u), dt, "u")
+            x = x + F.linear(u, _r(w[p + "mlp.c_proj.weight"], dt, "w"), w[p + "mlp.c_proj.bias"])
     if return_tokens:
         return x
     # model.py:231-234  ln_post on the class token, then @ proj
     c = F.layer_norm(x[:, 0, :], (width,), w["visual.ln_post.weight"], w["visual.ln_post.bias"], 1e-5)
     return c @ w["visual.proj"]
+
+
+@torch.no_grad()
+def encode_image_ref_fp16(sd, imgs, heads: int = HEADS):
+    """Emulation of the reference's OWN GPU precision (model.py:371-392 `convert_weights`: Conv / Linear /
+    MultiheadAttention weights + biases and `proj` in fp16; clip_official/clip/clip.py:115-116 keeps fp32 only on CPU):
+    the image is cast to fp16 (model.py:337), class / positional embeddings are cast to the activation dtype
+    (model.py:222-223), so the residual stream and every activation are fp16 tensors; LayerNorm computes in fp32 from
+    the fp16 input and casts back (model.py:156-159).  Arithmetic INSIDE an op is fp32 here (cuBLAS / SDPA accumulate in
+    fp32), each op's output is rounded to fp16 -- the favourable reading of that path.  Pinned against the live reference
+    run in half on the CPU (tests/test_oracle_vs_reference.py::test_ref_fp16_emulation).  Used to bound our 16-bit
+    paths: "no further from the fp32 answer than the reference's own GPU path"."""
+    h16, f32 = torch.float16, torch.float32
+
+    def r(t):
+        return t.to(h16).to(f32)
+
+    w = {k: v.to(f32) for k, v in sd.items()}
+    for k in w:
+        if k.endswith(("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias", "c_fc.weight", "c_fc.bias",
+                       "c_proj.weight", "c_proj.bias", "conv1.weight")) or k == "visual.proj":
+            w[k] = r(w[k])
+
+    def ln(x, name):
+        return r(F.layer_norm(x, (x.shape[-1],), w[name + ".weight"], w[name + ".bias"], 1e-5))
+
+    conv_w = w["visual.conv1.weight"]
+    width, _, P, _ = conv_w.shape
+    B = imgs.shape[0]
+    layers = n_layers_of(sd)
+    x = r(F.conv2d(r(imgs.to(f32)), conv_w, stride=P))
+    x = x.reshape(B, width, -1).permute(0, 2, 1)
+    x = torch.cat([r(w["visual.class_embedding"]).expand(B, 1, width), x], dim=1)
+    x = r(x + r(w["visual.positional_embedding"]))
+    x = ln(x, "visual.ln_pre")
+    L = x.shape[1]
+    dh = width // heads
+    for i in range(layers):
+        p = f"visual.transformer.resblocks.{i}."
+        qkv = r(F.linear(ln(x, p + "ln_1"), w[p + "attn.in_proj_weight"], w[p + "attn.in_proj_bias"]))
+        q, k, v = qkv.split(width, dim=-1)
+        q = q.reshape(B, L, heads, dh).transpose(1, 2)
+        k = k.reshape(B, L, heads, dh).transpose(1, 2)
+        v = v.reshape(B, L, heads, dh).transpose(1, 2)
+        s = r((q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(dh)))
+        o = r(r(s.softmax(dim=-1)) @ v)
+        o = o.transpose(1, 2).reshape(B, L, width)
+        x = r(x + r(F.linear(o, w[p + "attn.out_proj.weight"], w[p + "attn.out_proj.bias"])))
+        u = r(F.linear(ln(x, p + "ln_2"), w[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"]))
+        u = r(u * r(torch.sigmoid(r(1.702 * u))))
+        x = r(x + r(F.linear(u, w[p + "mlp.c_proj.weight"], w[p + "mlp.c_proj.bias"])))
+    return r(ln(x[:, 0, :], "visual.ln_post") @ w["visual.proj"])
 
 
 def flops_per_image(patch: int, res: int = 224, layers: int = N_LAYERS, width: int = WIDTH,

@@ -100,3 +100,59 @@ def test_auc_ignore_negative_labels_and_errors():
         metrics.roc_auc(torch.from_numpy(s2).to(DEV), torch.from_numpy((y > 0).astype(np.int64)).to(DEV))
     roc, prc = metrics.roc_curve_auc(st, torch.ones(n, dtype=torch.int64, device=DEV))
     assert roc is None and prc is None                   # ad_trainer.py:516,523-527: single class -> None
+
+
+@pytest.mark.parametrize("n", [2, 5, 100, 1023, 1024, 1025, 3000, 10000, 16383, 16384])
+@pytest.mark.parametrize("kind", ["f32", "f16", "coarse", "signed", "unlabeled"])
+def test_auc_single_launch_equals_tiled_pipeline(n, kind):
+    """n <= EOE_AUC_SINGLE_LAUNCH_MAX runs as ONE kernel launch (the sizes the reference evaluates, ad_trainer.py:452-455,
+    516-522); the multi-kernel radix-sort pipeline (EOE_AUC_FORCE_TILED) must give the same bits for every output."""
+    from eoe_b200 import _lib, metrics
+    assert n <= _lib.EOE_AUC_SINGLE_LAUNCH_MAX
+    rng = np.random.default_rng(n * 17 + len(kind))
+    s = (1 - np.exp(-np.abs(rng.standard_normal(n)))).astype(np.float32)
+    y = (rng.random(n) < 0.35).astype(np.int64)
+    y[0], y[-1] = 1, 0
+    if kind == "f16":
+        s = s.astype(np.float16)
+    elif kind == "coarse":
+        s = (np.round(s * 20) / np.float32(20)).astype(np.float32)
+    elif kind == "signed":
+        s = rng.standard_normal(n).astype(np.float32) * np.float32(1e3)
+    elif kind == "unlabeled" and n > 5:
+        y[2::5] = -1
+    st, yt = torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV)
+    ign = kind == "unlabeled"
+    launches0 = _lib.lib().eoe_launch_count()
+    a = metrics.roc_curve_auc(st, yt, with_prc=True, ignore_negative_labels=ign)
+    assert _lib.lib().eoe_launch_count() - launches0 == 1
+    b = metrics.roc_curve_auc(st, yt, with_prc=True, ignore_negative_labels=ign, force_tiled=True)
+    assert _lib.lib().eoe_launch_count() - launches0 > 10
+    for x, w in zip(a, b):
+        for f in ("auc", "avg_prec"):
+            if hasattr(x, f):
+                assert getattr(x, f) == getattr(w, f)
+        for f in ("tpr", "fpr", "prec", "rec", "ths"):
+            if hasattr(x, f):
+                assert np.array_equal(getattr(x, f), getattr(w, f)), f
+    keep = y >= 0
+    assert a[0].auc == oauc.roc_auc(y[keep], s[keep])
+
+
+@pytest.mark.parametrize("n", [50, 3000, 40000])
+def test_prc_thresholds_like_sklearn_and_reference_logger(n):
+    """PRC.ths = precision_recall_curve's thresholds (distinct scores, increasing): the reference's logger averages
+    np.asarray(res.ths) over seeds and classes (utils/logger.py:103-111), so None would break its own aggregation."""
+    from sklearn.metrics import precision_recall_curve
+    rng = np.random.default_rng(n)
+    s = (np.round((1 - np.exp(-np.abs(rng.standard_normal(n)))) * 500) / 500).astype(np.float32)
+    y = (rng.random(n) < 0.4).astype(np.int64)
+    roc, prc = _run(y, s)
+    p, r, t = precision_recall_curve(y, s)
+    assert np.array_equal(prc.ths, t) and prc.ths.dtype == t.dtype
+    assert np.array_equal(prc.prec, p) and np.array_equal(prc.rec, r)
+    # what mean_plot does with a list of curves (logger.py:103-118): index y, x and ths with picks from range(len(ths))
+    for res in (roc, prc):
+        ths = np.asarray(res.ths)
+        pick = sorted(np.random.default_rng(0).choice(len(ths), size=min(len(ths), 20), replace=False))
+        assert np.asarray(res.get_y())[pick].shape == np.asarray(res.get_x())[pick].shape == ths[pick].shape

@@ -141,8 +141,8 @@ def test_clip_model_has_the_reference_surface():
     tok = otext.synth_tokens(4, seed=5, vocab=200).to(DEV)
     f, t = m(imgs), m.encode_text(tok)
     assert f.shape == (3, 512) and t.shape == (4, 512) and torch.equal(f, m.encode_image(imgs))
-    want_t = otext.encode_text(sd, tok.cpu(), operand_dtype=torch.bfloat16)
-    assert _rel(t.cpu(), want_t) < 3e-3
+    want_t = otext.encode_text(sd, tok.cpu(), operand_dtype=torch.float16)      # the default operand dtype
+    assert _rel(t.cpu(), want_t) < 4e-4
     center = torch.nn.functional.normalize(t, dim=-1)
     from eoe_b200 import ops
     assert torch.equal(m.score(imgs, center), ops.clip_score(f, center))

@@ -132,6 +132,34 @@ def test_vit_oracle_matches_reference_fixture(golden_dir, patch):
     np.testing.assert_allclose(feats, g["features"], rtol=0, atol=2e-5)
 
 
+def score_errors(scores, want):
+    """relative score errors (north_star's measure): median, max, fraction within 1e-3."""
+    rel = np.abs(scores.astype(np.float64) - want.astype(np.float64)) / np.abs(want.astype(np.float64))
+    return float(np.median(rel)), float(rel.max()), float((rel <= 1e-3).mean())
+
+
+@pytest.mark.parametrize("patch,K", gi.SCORE_PARITY_CFGS)
+def test_end_to_end_score_fixture(golden_dir, patch, K):
+    """score_parity_b*.npz (live reference: encode_image -> ADClipTrainer.compute_anomaly_score on 64 images, cfg2 / cfg3):
+    (a) the head oracle reproduces the fixture's scores from the fixture's features (1e-3 relative, far-tail scores);
+    (b) the fp32 encoder oracle reproduces them END TO END on a 16-image slice (kept small: CPU time);
+    (c) the reference's own GPU precision (half run of the live reference) is itself 3e-3 ... 5e-3 (median) away from its
+        fp32 answer on these scores -- the yardstick tests/test_gpu_encoder.py::test_end_to_end_scores holds us to."""
+    g = _load(golden_dir, f"score_parity_b{patch}.npz")
+    imgs, text, labels = gi.score_parity_inputs(K)
+    assert abs(float(g["img_sum"]) - float(imgs.double().sum())) < 1e-9
+    assert np.array_equal(g["text"], text) and np.array_equal(g["labels"], labels)
+    np.testing.assert_allclose(oh.clip_score(g["features"], text), g["scores"], rtol=1e-3, atol=1e-30)
+    sd = ovit.synth_state_dict(patch, seed=gi.VIT_WEIGHT_SEED)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    feats = ovit.encode_image(sd, imgs[:16]).numpy()
+    med, mx, _ = score_errors(oh.clip_score(feats, text), g["scores"][:16])
+    assert mx < 1e-3, (med, mx)                       # fp32 oracle end to end: within north_star's 1e-3 on every score
+    med_h, mx_h, frac_h = score_errors(g["scores_ref_half"], g["scores"])
+    assert 2e-3 < med_h < 8e-3 and frac_h < 0.3, (med_h, mx_h, frac_h)
+    assert oauc.roc_auc(labels, g["scores"]) == oauc.roc_auc(labels, g["scores_ref_half"])
+
+
 def test_text_oracle_matches_reference_fixture(golden_dir):
     from oracle import text as otext
     g = _load(golden_dir, "text.npz")

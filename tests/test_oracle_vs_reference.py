@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from oracle import _ref_import
+from oracle import golden_inputs as gi
 from oracle import heads as oh
 from oracle import text as otext
 from oracle import vit as ovit
@@ -128,6 +129,23 @@ def test_vit_live_small(ref):
             want = m(x)
         got = ovit.encode_image(sd, x)
         assert (want - got).abs().max().item() < 2e-5
+
+
+def test_ref_fp16_emulation(ref):
+    """oracle.vit.encode_image_ref_fp16 (the reference's GPU precision, model.py:371-392) against the live reference run
+    in half on the CPU: individual roundings decorrelate the two (they differ by ~1e-3, like two noise draws), so the pin
+    is statistical: both sit at the same distance from the fp32 answer (within 15 %)."""
+    from oracle.make_golden import live_half_features
+    for patch in (32, 16):
+        sd = ovit.synth_state_dict(patch, seed=gi.VIT_WEIGHT_SEED)
+        imgs = gi.vit_images(B=4, seed=77)
+        f32 = ovit.encode_image(sd, imgs)
+        live = torch.from_numpy(live_half_features(ref, patch, sd, imgs))
+        emu = ovit.encode_image_ref_fp16(sd, imgs)
+        d_live = ((live - f32).norm() / f32.norm()).item()
+        d_emu = ((emu - f32).norm() / f32.norm()).item()
+        assert 0.85 < d_emu / d_live < 1.15, (d_emu, d_live)
+        assert 8e-4 < d_live < 2e-3
 
 
 def test_text_live_small(ref):
