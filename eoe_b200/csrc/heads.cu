@@ -375,13 +375,30 @@ __device__ __forceinline__ void clip_stage_text(const float* __restrict__ text, 
     __syncthreads();
 }
 
-template <typename T, int ITERS, int ROWS>
+// Large prompt sets (leave-one-out on cifar100 / cub / dtd builds 100 / 200 / 47 prompts, clip.py:53-54) do not fit the
+// shared-memory text tile: GTEXT reads the text rows through the read-only path from L2 / L1 instead (K * d * 4 <= 1 MB)
+// and keeps only 1 / ||t_k|| (score head: clip.py:69 re-normalises) per prompt in shared memory.
+template <bool RENORM>
+__device__ __forceinline__ void clip_stage_inv_norms(const float* __restrict__ text, int d, int K, float* s_inv) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < K; k += kHeadWarps) {
+        float s = 0.f;
+        if (RENORM)
+            for (int i = lane; i < d; i += 32) { const float v = __ldg(text + (int64_t)k * d + i); s += v * v; }
+        s = warp_sum(s);
+        if (lane == 0) s_inv[k] = RENORM ? 1.0f / sqrtf(s) : 1.0f;
+    }
+    __syncthreads();
+}
+
+template <typename T, int ITERS, int ROWS, bool GTEXT = false>
 __global__ void __launch_bounds__(kHeadBlock)
 clip_score_kernel(const T* __restrict__ z, const float* __restrict__ text, int64_t n, int d, int K, float scale,
                   float* __restrict__ scores) {
     extern __shared__ __align__(16) float s_text[];
     constexpr int DP = ITERS * 128;
-    clip_stage_text<ITERS>(text, d, K, true, s_text);
+    if (GTEXT) clip_stage_inv_norms<true>(text, d, K, s_text);
+    else clip_stage_text<ITERS>(text, d, K, true, s_text);
     const int lane = threadIdx.x & 31;
     const int nvec = d >> 2;
     const int64_t warp0 = (int64_t)blockIdx.x * kHeadWarps + (threadIdx.x >> 5);
@@ -410,14 +427,21 @@ clip_score_kernel(const T* __restrict__ z, const float* __restrict__ text, int64
             for (int r = 0; r < ROWS; ++r) dot[r] = 0.f;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
-                const float4 t = reinterpret_cast<const float4*>(s_text + k * DP)[it * 32 + lane];
+                float4 t;
+                if (GTEXT) {
+                    const int vi = it * 32 + lane;
+                    t = (vi < nvec) ? __ldg(reinterpret_cast<const float4*>(text + (int64_t)k * d) + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    t = reinterpret_cast<const float4*>(s_text + k * DP)[it * 32 + lane];
+                }
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r)
                     dot[r] += v[r][it][0] * t.x + v[r][it][1] * t.y + v[r][it][2] * t.z + v[r][it][3] * t.w;
             }
+            const float tk = GTEXT ? s_text[k] : 1.0f;               // 1 / ||t_k|| when the rows are not pre-normalised
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
-                const float l = warp_sum(dot[r]) * inv_nrm[r];       // logit_k = scale * z^ . T^_k
+                const float l = warp_sum(dot[r]) * inv_nrm[r] * tk;  // logit_k = scale * z^ . T^_k
                 if (l > mx[r]) { se[r] = se[r] * expf(mx[r] - l) + 1.0f; mx[r] = l; }
                 else se[r] += expf(l - mx[r]);                         // NaN falls through here and sticks
                 last[r] = l;
@@ -431,20 +455,28 @@ clip_score_kernel(const T* __restrict__ z, const float* __restrict__ text, int64
     }
 }
 
-// clip.py:81-103 + backward.  One warp per row; logit k lives in lane k%32, slot k/32 (K <= 64).
-template <typename T, int ITERS>
+// clip.py:81-103 + backward.  One warp per row; logit k lives in lane k%32, slot k/32 (K <= 32 * SLOTS).
+// GTEXT: text rows come from global memory (L2 / L1) instead of the shared-memory tile (large prompt sets).
+template <typename T, int ITERS, int SLOTS = 2, bool GTEXT = false>
 __global__ void __launch_bounds__(kHeadBlock)
 clip_oe_loss_kernel(const T* __restrict__ z, const float* __restrict__ text, const int64_t* __restrict__ labels,
                     int64_t n, int d, int K, float scale, int64_t nominal_label, int loo, T* __restrict__ grad,
                     HeadWorkspace* ws, float* loss_out, float inv_n_f, double inv_n) {
     extern __shared__ __align__(16) float s_text[];
     constexpr int DP = ITERS * 128;
-    clip_stage_text<ITERS>(text, d, K, false, s_text);
+    if (!GTEXT) clip_stage_text<ITERS>(text, d, K, false, s_text);
     const int lane = threadIdx.x & 31;
     const int nvec = d >> 2;
     const int64_t warp0 = (int64_t)blockIdx.x * kHeadWarps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kHeadWarps;
     const int64_t anom_label = 1 - nominal_label;
+    auto text4 = [&](int k, int it) {
+        if (GTEXT) {
+            const int vi = it * 32 + lane;
+            return (vi < nvec) ? __ldg(reinterpret_cast<const float4*>(text + (int64_t)k * d) + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return reinterpret_cast<const float4*>(s_text + k * DP)[it * 32 + lane];
+    };
     float loss_acc = 0.f;
     for (int64_t row = warp0; row < n; row += nwarps) {
         float v[ITERS][4];
@@ -461,21 +493,32 @@ clip_oe_loss_kernel(const T* __restrict__ z, const float* __restrict__ text, con
         for (int it = 0; it < ITERS; ++it) {           // v <- z^
             v[it][0] *= inv_nrm; v[it][1] *= inv_nrm; v[it][2] *= inv_nrm; v[it][3] *= inv_nrm;
         }
-        float lg[2] = {-INFINITY, -INFINITY};
+        float lg[SLOTS];
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) lg[q] = -INFINITY;
         for (int k = 0; k < K; ++k) {
             float dot = 0.f;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
-                const float4 t = reinterpret_cast<const float4*>(s_text + k * DP)[it * 32 + lane];
+                const float4 t = text4(k, it);
                 dot += v[it][0] * t.x + v[it][1] * t.y + v[it][2] * t.z + v[it][3] * t.w;
             }
             const float l = scale * warp_sum(dot);
-            if ((k & 31) == lane) lg[k >> 5] = l;
+#pragma unroll
+            for (int q = 0; q < SLOTS; ++q)
+                if ((k >> 5) == q && (k & 31) == lane) lg[q] = l;
         }
-        const float m = warp_max(fmaxf(lg[0], lg[1]));
-        float p0 = (lane < K) ? expf(lg[0] - m) : 0.f;
-        float p1 = (lane + 32 < K) ? expf(lg[1] - m) : 0.f;
-        const float sum = warp_sum(p0 + p1);
+        float m = lg[0];
+#pragma unroll
+        for (int q = 1; q < SLOTS; ++q) m = fmaxf(m, lg[q]);
+        m = warp_max(m);
+        float p[SLOTS], psum = 0.f;
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) {
+            p[q] = (lane + 32 * q < K) ? expf(lg[q] - m) : 0.f;
+            psum += p[q];
+        }
+        const float sum = warp_sum(psum);
         const float lse = m + logf(sum);
         const int64_t lab = labels[row];
         int t = -1;
@@ -483,27 +526,45 @@ clip_oe_loss_kernel(const T* __restrict__ z, const float* __restrict__ text, con
         else if (lab == nominal_label) {
             t = 0;
             if (loo) {          // argmax over k < K-1, first maximal index (clip.py:95)
-                float a0 = (lane < K - 1) ? lg[0] : -INFINITY;
-                float a1 = (lane + 32 < K - 1) ? lg[1] : -INFINITY;
-                const float am = warp_max(fmaxf(a0, a1));
-                unsigned b0 = __ballot_sync(kFullMask, a0 == am), b1 = __ballot_sync(kFullMask, a1 == am);
-                t = b0 ? (__ffs(b0) - 1) : (b1 ? 32 + __ffs(b1) - 1 : 0);
+                float a[SLOTS], am = -INFINITY;
+#pragma unroll
+                for (int q = 0; q < SLOTS; ++q) {
+                    a[q] = (lane + 32 * q < K - 1) ? lg[q] : -INFINITY;
+                    am = fmaxf(am, a[q]);
+                }
+                am = warp_max(am);
+                bool found = false;
+#pragma unroll
+                for (int q = 0; q < SLOTS; ++q) {
+                    const unsigned bq = __ballot_sync(kFullMask, a[q] == am);
+                    if (!found && bq) { t = 32 * q + __ffs(bq) - 1; found = true; }
+                }
             }
         }
-        float lt = __shfl_sync(kFullMask, (t >= 32) ? lg[1] : lg[0], t < 0 ? 0 : (t & 31));
+        float lt_src = lg[0];
+#pragma unroll
+        for (int q = 1; q < SLOTS; ++q)
+            if ((t >> 5) == q) lt_src = lg[q];
+        const float lt = __shfl_sync(kFullMask, lt_src, t < 0 ? 0 : (t & 31));
         if (t >= 0 && lane == 0) loss_acc += lse - lt;
         if (grad) {
             // G_k = (softmax_k - [k==t]) / n ; g = scale * sum_k G_k c_k ; dz = (g - (g.z^) z^) / ||z||
-            float G0 = (t >= 0 && lane < K) ? (p0 / sum - (lane == t ? 1.f : 0.f)) * inv_n_f : 0.f;
-            float G1 = (t >= 0 && lane + 32 < K) ? (p1 / sum - (lane + 32 == t ? 1.f : 0.f)) * inv_n_f : 0.f;
+            float G[SLOTS];
+#pragma unroll
+            for (int q = 0; q < SLOTS; ++q)
+                G[q] = (t >= 0 && lane + 32 * q < K) ? (p[q] / sum - (lane + 32 * q == t ? 1.f : 0.f)) * inv_n_f : 0.f;
             float g[ITERS][4];
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) g[it][0] = g[it][1] = g[it][2] = g[it][3] = 0.f;
             for (int k = 0; k < K; ++k) {
-                const float Gk = scale * __shfl_sync(kFullMask, (k >= 32) ? G1 : G0, k & 31);
+                float gsrc = G[0];
+#pragma unroll
+                for (int q = 1; q < SLOTS; ++q)
+                    if ((k >> 5) == q) gsrc = G[q];
+                const float Gk = scale * __shfl_sync(kFullMask, gsrc, k & 31);
 #pragma unroll
                 for (int it = 0; it < ITERS; ++it) {
-                    const float4 c = reinterpret_cast<const float4*>(s_text + k * DP)[it * 32 + lane];
+                    const float4 c = text4(k, it);
                     g[it][0] += Gk * c.x; g[it][1] += Gk * c.y; g[it][2] += Gk * c.z; g[it][3] += Gk * c.w;
                 }
             }
@@ -985,6 +1046,15 @@ static int clip_loss_mma_launch(const void* z, const float* text, const int64_t*
     return check_launch("clip_oe_loss_mma_kernel");
 }
 
+// K <= 64 prompts whose fp32 rows fit the shared-memory tile use it; larger prompt sets (up to kClipMaxPrompts) read the
+// text rows from global memory
+constexpr int64_t kClipMaxPrompts = 256;
+static bool clip_text_from_global(int64_t d, int64_t K) {
+    const int iters = (int)((d / 4 + 31) / 32);
+    const int it_pad = iters <= 2 ? 2 : (iters <= 4 ? 4 : 8);
+    return K > 64 || (size_t)K * it_pad * 128 * 4 > 192 * 1024;
+}
+
 template <typename T>
 static bool clip_mma_ok(const void* z, const float* text, int64_t n, int64_t d, int64_t K) {
     return n >= 2048 && d % 128 == 0 && d <= 1024 && K >= 1 && K <= 32 && (uintptr_t)z % 16 == 0 && (uintptr_t)text % 16 == 0;
@@ -1019,9 +1089,14 @@ static int clip_score_launch(const void* z, const float* text, int64_t n, int64_
     if (clip_mma_ok<T>(z, text, n, d, K)) return clip_score_mma_launch<T>(z, text, n, d, K, scale, scores, st);
     const int iters = (int)((d / 4 + 31) / 32);
     const int it_pad = iters <= 2 ? 2 : (iters <= 4 ? 4 : 8);
-    const size_t smem = (size_t)K * it_pad * 128 * sizeof(float);
+    const bool gtext = clip_text_from_global(d, K);
+    const size_t smem = gtext ? (size_t)K * sizeof(float) : (size_t)K * it_pad * 128 * sizeof(float);
 #define EOE_CLIP_CASE(IT, RW)                                                                            \
-    {                                                                                                    \
+    if (gtext) {                                                                                         \
+        int grid = head_grid(n, kHeadWarps * RW);                                                        \
+        if (grid > kNumSMs * 4) grid = kNumSMs * 4;                                                      \
+        clip_score_kernel<T, IT, RW, true><<<grid, kHeadBlock, smem, st>>>((const T*)z, text, n, (int)d, (int)K, scale, scores); \
+    } else {                                                                                             \
         auto kern = clip_score_kernel<T, IT, RW>;                                                        \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) { set_cuda_error(e, "clip_score smem attr"); return EOE_ERR_CUDA; }        \
@@ -1044,11 +1119,17 @@ static int clip_loss_launch(const void* z, const float* text, const int64_t* lab
         return clip_loss_mma_launch<T>(z, text, labels, n, d, K, scale, nominal, loo, loss_out, grad, ws, st);
     const int iters = (int)((d / 4 + 31) / 32);
     const int it_pad = iters <= 2 ? 2 : (iters <= 4 ? 4 : 8);
-    const size_t smem = (size_t)K * it_pad * 128 * sizeof(float);
+    const bool gtext = clip_text_from_global(d, K);
+    const size_t smem = gtext ? 0 : (size_t)K * it_pad * 128 * sizeof(float);
     const float inv_n_f = 1.0f / (float)n;
     const double inv_n = 1.0 / (double)n;
 #define EOE_CLIPL_CASE(IT)                                                                               \
-    {                                                                                                    \
+    if (gtext) {                                                                                         \
+        int grid = head_grid(n, kHeadWarps);                                                             \
+        if (grid > kNumSMs * 4) grid = kNumSMs * 4;                                                      \
+        clip_oe_loss_kernel<T, IT, 8, true><<<grid, kHeadBlock, 0, st>>>((const T*)z, text, labels, n, (int)d, (int)K, scale, \
+            nominal, loo, (T*)grad, (HeadWorkspace*)ws, loss_out, inv_n_f, inv_n);                       \
+    } else {                                                                                             \
         auto kern = clip_oe_loss_kernel<T, IT>;                                                          \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) { set_cuda_error(e, "clip_oe_loss smem attr"); return EOE_ERR_CUDA; }      \
@@ -1063,6 +1144,8 @@ static int clip_loss_launch(const void* z, const float* text, const int64_t* lab
 #undef EOE_CLIPL_CASE
     return check_launch("clip_oe_loss_kernel");
 }
+
+int clip_prompts_ok(int64_t K) { return K >= 1 && K <= kClipMaxPrompts; }      // the fused encoder validates K up front
 
 // called by the fused encoder tail as well
 int clip_score_f32(const float* z, const float* text, int64_t n, int64_t d, int64_t K, float scale, float* scores,
@@ -1139,10 +1222,7 @@ extern "C" int eoe_focal_fwd_bwd(const void* x, int x_dtype, const int64_t* labe
 
 static int clip_check(const void* z, const float* text, int64_t n, int64_t d, int64_t K) {
     if (!z || !text || n <= 0 || d <= 0 || K <= 0) return EOE_ERR_ARG;
-    if (d % 4 != 0 || d > 1024 || K > 64) return EOE_ERR_SHAPE;
-    const int iters = (int)((d / 4 + 31) / 32);
-    const int it_pad = iters <= 2 ? 2 : (iters <= 4 ? 4 : 8);
-    if ((size_t)K * it_pad * 128 * 4 > 192 * 1024) return EOE_ERR_SHAPE;
+    if (d % 4 != 0 || d > 1024 || K > kClipMaxPrompts) return EOE_ERR_SHAPE;
     if ((uintptr_t)z % 16 != 0 || (uintptr_t)text % 16 != 0) return EOE_ERR_ALIGN;
     return EOE_OK;
 }

@@ -15,6 +15,7 @@
 
 namespace eoe {
 
+int clip_prompts_ok(int64_t K);
 int clip_score_f32(const float* z, const float* text, int64_t n, int64_t d, int64_t K, float scale, float* scores,
                    cudaStream_t st);
 
@@ -1301,6 +1302,7 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
     const int W = w.width, dt = w.operand_dtype, L = p->L;
     const int64_t M = B * L, Mp = B * p->g2;
     int rc;
+    if (text && !clip_prompts_ok(K)) return EOE_ERR_SHAPE;      // before any work: not after the whole forward pass
     // 1. patchify
     if (imgs_f32) {
         const int64_t total = B * 3 * (int64_t)w.resolution * w.resolution / 8;
@@ -1411,7 +1413,6 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
         if ((rc = check_launch("tail_kernel"))) return rc;
     }
     if (text) {
-        if (K <= 0 || K > 64) return EOE_ERR_SHAPE;
         if ((rc = clip_score_f32(feats, text, B, w.embed_dim, K, scale, scores_out, st))) return rc;
     }
     return EOE_OK;

@@ -112,7 +112,8 @@ int eoe_focal_fwd_bwd(const void* x, int x_dtype, const int64_t* labels, int64_t
 /* ADClipTrainer.compute_anomaly_score. Replaces src/eoe/training/clip.py:66-79.
  *   z [n,d] image features, text [K,d] fp32 (`center`); text rows are re-normalised (clip.py:69)
  *   scores_out [n] fp32 = softmax_k(scale * z^_i . T^_k)[K-1]     (scale = 100, clip.py:71)
- * Limits: d % 4 == 0, d <= 1024, K*d*4 <= 192 KiB (text lives in shared memory). */
+ * Limits: d % 4 == 0, d <= 1024, K <= 256 prompts (leave_one_out on cub builds 200, clip.py:53-54).  K <= 32 and
+ * n >= 2048 run on tensor cores, K <= 64 keeps the text rows in shared memory, larger prompt sets read them through L2. */
 int eoe_clip_score(const void* z, int z_dtype, const float* text, int64_t n, int64_t d, int64_t K,
                    float scale, float* scores_out, void* stream);
 

@@ -202,6 +202,36 @@ def test_clip_oe_loss_tensor_core_path_vs_oracle(n, d, K, dtype, loo):
         assert g2 is None and l2.item() == loss.item()
 
 
+@pytest.mark.parametrize("n,d,K", [(300, 512, 47), (128, 512, 100), (4500, 512, 200), (33, 512, 256), (70, 768, 65)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_clip_large_prompt_sets(n, d, K, dtype):
+    """leave_one_out builds one prompt per class (+ the anomaly prompt): 47 (dtd), 100 (cifar100), 200 (cub) rows of
+    `center` (clip.py:53-54).  Past 64 prompts the text rows are read from global memory instead of the shared-memory
+    tile and the loss keeps 8 logit slots per lane; same bars as the small-K kernels."""
+    from eoe_b200 import ops
+    rng = np.random.default_rng(n + d + K)
+    z = rng.standard_normal((n, d)).astype(np.float32)
+    c = (rng.standard_normal((K, d)) * 1.7).astype(np.float32)
+    z[: n // 2] += 0.2 * np.sqrt(d) * c[rng.integers(0, K, n // 2)] / 1.7
+    zt = _t(z, dtype)
+    zq = _np(zt)
+    _close(_np(ops.clip_score(zt, _t(c))), oh.clip_score(zq, c), rtol=1e-3, atol=1e-30)
+    cu = (c / np.linalg.norm(c, axis=1, keepdims=True)).astype(np.float32)
+    y = rng.integers(0, 2, n)
+    for loo in (False, True):
+        for nom in (0, 1):
+            zz = zt.clone().requires_grad_(True)
+            loss = ops.clip_oe_loss(zz, _t(y), _t(cu), nominal_label=nom, leave_one_out=loo)
+            loss.backward()
+            _close(loss.item(), oh.clip_oe_loss(zq, y, cu, nom, loo), rtol=1e-4)
+            keep = np.ones(n, bool)
+            if loo:
+                lg = np.sort(oh.clip_logits(zq, cu, False, 100.0)[:, : K - 1], axis=1)
+                keep = (lg[:, -1] - lg[:, -2]) > 1e-3
+            gtol = 2e-3 if dtype == torch.float32 else 2e-2
+            _close(_np(zz.grad)[keep], oh.clip_oe_grad(zq, y, cu, nom, loo)[keep], rtol=gtol, atol=1e-5)
+
+
 def test_clip_score_tensor_core_path_special_rows():
     """NaN / Inf / zero rows give NaN scores (z / ||z|| in the reference, clip.py:70), neighbours are untouched."""
     from eoe_b200 import ops
@@ -227,7 +257,7 @@ def test_bad_arguments_raise():
     with pytest.raises(_lib.EoeError):
         ops.clip_score(torch.zeros(4, 510, device=DEV), torch.zeros(3, 510, device=DEV))   # d % 4 != 0
     with pytest.raises(_lib.EoeError):
-        ops.clip_score(torch.zeros(4, 512, device=DEV), torch.zeros(100, 512, device=DEV))  # K too large
+        ops.clip_score(torch.zeros(4, 512, device=DEV), torch.zeros(257, 512, device=DEV))  # K > 256 prompts
 
 
 def test_heads_large_property():
