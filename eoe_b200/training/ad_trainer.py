@@ -12,6 +12,7 @@ torch.distributed (new; see eoe_b200.dist).  Out of scope:
 snapshots -- `train_cls` / `eval_cls` take a loader yielding the reference's batch triple `(imgs, lbls, idcs)`
 (datasets/bases.py:591-597) instead of a dataset object.
 """
+import weakref
 from abc import ABC, abstractmethod
 from typing import Iterable, List, Optional, Sequence, Tuple
 
@@ -57,21 +58,43 @@ class ADTrainer(ABC):
 
     # scores computed by the fused loss kernel are handed to the compute_anomaly_score call that follows on
     # the same feature tensor (ad_trainer.py:430-436 calls loss, then compute_anomaly_score, on `image_features`)
+    # The entry holds a weak reference to that very tensor object (an address could be recycled by the caching allocator
+    # for the next same-shape batch) plus its version counter, is consumed by the first lookup and dropped by any miss.
     def _remember_scores(self, features, scores, tag=None):
-        self._score_cache = (features.data_ptr(), features._version, tuple(features.shape), tag, scores)
+        self._score_cache = (weakref.ref(features), features._version, tag, scores)
 
     def _cached_scores(self, features, tag=None):
-        c = self._score_cache
-        if c is not None and c[0] == features.data_ptr() and c[1] == features._version and \
-                c[2] == tuple(features.shape) and c[3] == tag:
-            self._score_cache = None
-            return c[4]
+        c, self._score_cache = self._score_cache, None
+        if c is not None and c[0]() is features and c[1] == features._version and c[2] == tag:
+            return c[3]
         return None
+
+    def _sync_metric(self, center):
+        """Data-parallel runs: every rank must optimise the SAME objective, so the tensor prepare_metric returned on
+        rank 0 (computed from rank 0's shard: e.g. the DSVDD centre, dsvdd.py:11-21) is broadcast to all ranks."""
+        _, ws = edist.world()
+        if ws > 1 and self.data_parallel and torch.is_tensor(center):
+            center = center.contiguous()
+            torch.distributed.broadcast(center, src=0)
+        return center
+
+    def _check_equal_batches(self, loader):
+        """Gradient buckets average over ranks (equal weights) and every rank must join every all-reduce: per-rank loaders
+        need the same number of batches (and equal batch sizes for the average to be the global-batch mean)."""
+        _, ws = edist.world()
+        if ws > 1 and self.data_parallel and hasattr(loader, "__len__"):
+            n = torch.tensor([len(loader)], dtype=torch.int64, device=self.device)
+            lo, hi = n.clone(), n.clone()
+            torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+            torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+            if int(lo) != int(hi):
+                raise ValueError(f"data-parallel training needs the same number of batches on every rank (got {int(lo)}..{int(hi)})")
 
     # ---------------------------------------------------------------- training (ad_trainer.py:356-471)
     def train_cls(self, model: torch.nn.Module, loader: Iterable, nominal_label: int = 0, clsstr: str = "",
                   seed: int = 0, epochs: Optional[int] = None) -> Tuple[torch.nn.Module, Optional[metrics.ROC], List[float]]:
         model = model.to(self.device).train()
+        self._score_cache = None
         epochs = self.epochs if epochs is None else epochs
         params = [p for p in model.parameters() if p.requires_grad]
         _, ws = edist.world()
@@ -88,7 +111,8 @@ class ADTrainer(ABC):
             opt = torch.optim.Adam(params, lr=self.lr, weight_decay=self.wdk, amsgrad=False)
         sched = torch.optim.lr_scheduler.MultiStepLR(opt, self.milestones, 0.1)
         buckets = edist.GradBuckets(params) if (self.data_parallel and ws > 1) else None
-        center = self.center = self.prepare_metric(clsstr, loader, model, seed)
+        center = self.center = self._sync_metric(self.prepare_metric(clsstr, loader, model, seed))
+        self._check_equal_batches(loader)
         cls_roc, losses = None, []
         for ep in range(epochs):
             ep_labels, ep_ascores, ep_losses = [], [], []
@@ -132,6 +156,7 @@ class ADTrainer(ABC):
         per-rank score / label shards are all-gathered (rank order == index order for eoe_b200.dist.shard_range)
         and every rank computes the global ROC / PRC."""
         model = model.to(self.device).eval() if isinstance(model, torch.nn.Module) else model
+        self._score_cache = None
         center = self.center
         ep_labels, ep_ascores = [], []
         for imgs, lbls, _idcs in loader:

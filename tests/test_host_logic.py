@@ -80,8 +80,8 @@ def _worker_dp(rank, ws, port, q):
         buckets.zero_grad()
         _hsc_loss_torch(model(x[lo:hi]), y[lo:hi]).backward()
         buckets.finish()
-    grads = [p.grad.clone() for p in model.parameters()]
-    q.put((rank, grads))
+    grads = [p.grad.clone().numpy() for p in model.parameters()]     # numpy: pickled by value (a torch tensor would be
+    q.put((rank, grads))                                              # passed as an fd that dies with this process)
     torch.distributed.destroy_process_group()
 
 
@@ -100,7 +100,7 @@ def test_grad_buckets_average_equals_full_batch_gloo_world2():
     _hsc_loss_torch(model(x), y).backward()       # mean over the global batch == average of equal-shard means
     for r in (0, 1):
         for got, p in zip(res[r], model.parameters()):
-            torch.testing.assert_close(got, p.grad, rtol=1e-5, atol=1e-7)
+            torch.testing.assert_close(torch.from_numpy(got), p.grad, rtol=1e-5, atol=1e-7)
 
 
 def test_trainer_registry_and_hook_signatures():
