@@ -206,6 +206,44 @@ def side_metrics(dev, pk):
         if i >= 3:
             ts.append(a.elapsed_time(b))
     out["auc"] = {"ms_per_1m_scores": statistics.median(ts), "n": n, "note": "device radix sort + scans, L2 flushed"}
+    # ---- latency at the sizes the reference itself runs (n = 256 rows per step, 3 000 - 10 000 scores per AUC)
+    import numpy as np
+
+    def us(fn, iters=30, warm=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        tt = []
+        for _ in range(iters):
+            a.record()
+            fn()
+            b.record(); torch.cuda.synchronize()
+            tt.append(a.elapsed_time(b) * 1e3)
+        return statistics.median(tt)
+    lat = {}
+    try:
+        from sklearn.metrics import auc as sk_auc, roc_curve as sk_roc
+    except Exception:
+        sk_auc = sk_roc = None
+    for n in (3000, 10000):
+        rng = np.random.default_rng(n)
+        s_np = (1 - np.exp(-np.abs(rng.standard_normal(n)))).astype(np.float32)
+        y_np = (rng.random(n) < 0.5).astype(np.int64)
+        sd_, yd_ = torch.from_numpy(s_np).to(dev), torch.from_numpy(y_np).to(dev)
+        ent = {"device_us": us(lambda: metrics.roc_auc_device(sd_, yd_, workspace=ws)), "launches": 1}
+        if sk_auc is not None:
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ref = sk_auc(*sk_roc(y_np, s_np)[:2])
+            ent["sklearn_host_us"] = (time.perf_counter() - t0) / 5 * 1e6
+            ent["bit_exact_vs_sklearn"] = bool(metrics.roc_auc(sd_, yd_) == ref)
+        lat[f"auc_n{n}"] = ent
+    z = 0.05 * torch.randn(256, 256, device=dev)
+    y = (torch.arange(256, device=dev) >= 128).long()
+    lat["hsc_fwd_bwd_score_n256_us"] = us(lambda: ops.hsc_fused(z, y, 0))
+    x = torch.randn(256, 1, device=dev)
+    lat["bce_fwd_bwd_score_n256_us"] = us(lambda: ops.bce_fused(x, y, 0))
+    out["latency_at_reference_sizes"] = lat
     return out
 
 

@@ -486,7 +486,8 @@ __device__ __forceinline__ void pairwise_leaf_slot(const double* a, int64_t T, i
     }
     double r = p[j];
     const int64_t body = len - (len & 7);
-    for (int64_t i = 8; i < body; i += 8) r = __dadd_rn(r, p[i + j]);
+#pragma unroll 8
+    for (int64_t i = 8; i < body; i += 8) r = __dadd_rn(r, p[i + j]);      // (unrolled: the loads of a batch go out together)
     // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
     double o = __shfl_xor_sync(gmask, r, 1);
     r = (j & 1) ? __dadd_rn(o, r) : __dadd_rn(r, o);
@@ -582,24 +583,29 @@ __global__ void auc_info_kernel(const AucControl* c, int64_t* info) {
 
 // ------------------------------------------------------------------------------------------ single-launch path
 // The reference evaluates the AUC on 3 000 - 10 000 scores per class and epoch (ad_trainer.py:452-455, 516-522): there the
-// multi-kernel pipeline above is pure launch latency (15 launches, ~0.1 ms).  For n <= kSmallMax the whole computation
-// runs in ONE launch of ONE CTA: keys and label bits live in shared memory, 4 (or fewer) LSD radix passes with the same
-// match_any ranking as the tiled sort, then the tie / corner scans, the fp64 terms and numpy's pairwise tree, phase after
-// phase behind __syncthreads().  Every arithmetic step is the one of the multi-kernel path (same __d*_rn sequence, same
-// tree), so the result is bit-identical to it and to scikit-learn.
+// multi-kernel pipeline above is pure launch latency (11+ launches, ~0.1 ms).  For n <= kSmallMax the whole computation
+// runs in ONE launch of ONE CTA with everything but the fp64 terms in shared memory: keys and label bits, 4 (or fewer)
+// LSD radix passes, the tie / corner scans, then the fp64 terms and numpy's pairwise tree, phase after phase behind
+// __syncthreads().  Every arithmetic step is the one of the multi-kernel path (same __d*_rn sequence, same tree), so the
+// result is bit-identical to it and to scikit-learn.
+// Ranking uses eight warp ballots per key (the digit's peer mask is the AND of the per-bit ballots): match.any has a
+// throughput of one warp instruction per ~64 clocks per SM, which made a one-SM sort 10x slower than the ballots.
 constexpr int kSmallThreads = 1024;
 constexpr int kSmallItems = 16;
 constexpr int kSmallMax = kSmallThreads * kSmallItems;        // 16 384 scores
 
 struct SmallShared {
-    uint32_t keys[kSmallMax];
+    uint32_t keys[kSmallMax + 8];      // sorted keys; after the distinct phase: kept ROC points packed (tps << 16 | fps)
+    uint16_t d_tps[kSmallMax];         // distinct thresholds: true positives / false positives (<= 16 384: 16 bits)
+    uint16_t d_fps[kSmallMax];
     uint16_t warp_hist[32][256];
-    uint8_t labs[kSmallMax];
+    uint8_t labs[kSmallMax];           // label bits; after the distinct phase: keep flags of the corner filter
     uint32_t digit_base[256];
     uint32_t scan_tmp[32];
     uint32_t and_all, or_all, n_valid, n_pos, status, pad[3];
-    double nodes[1024];                                       // pairwise tree: depth <= 8 for <= 16 385 terms
+    double nodes[1024];                // pairwise tree: depth <= 8 for <= 16 385 terms
 };
+static_assert(sizeof(SmallShared) <= 227 * 1024, "single-launch AUC: shared memory budget");
 
 // exclusive prefix of one u32 per thread over the 1024 threads of the block; *total = block sum
 __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_tmp /*[32]*/, uint32_t* total) {
@@ -641,11 +647,10 @@ __device__ __forceinline__ double block_pairwise_sum(const double* a, int64_t T,
 template <typename T>
 __global__ void __launch_bounds__(kSmallThreads, 1)
 auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ labels, int n, int flags,
-                 uint32_t* __restrict__ d_tps, uint32_t* __restrict__ d_fps, uint32_t* __restrict__ d_key,
-                 uint32_t* __restrict__ k_tps, uint32_t* __restrict__ k_fps, double* __restrict__ terms,
-                 double* __restrict__ auc_out, int64_t* __restrict__ info_out, double* __restrict__ fpr_out,
-                 double* __restrict__ tpr_out, float* __restrict__ thr_out, double* __restrict__ prec_out,
-                 double* __restrict__ rec_out, float* __restrict__ pthr_out) {
+                 uint32_t* __restrict__ d_key, double* terms, double* __restrict__ auc_out,
+                 int64_t* __restrict__ info_out, double* __restrict__ fpr_out, double* __restrict__ tpr_out,
+                 float* __restrict__ thr_out, double* __restrict__ prec_out, double* __restrict__ rec_out,
+                 float* __restrict__ pthr_out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     SmallShared& sh = *reinterpret_cast<SmallShared*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -653,23 +658,31 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
     const int wbase = warp * items * 32;                             // this warp's contiguous chunk
     if (tid == 0) { sh.and_all = 0xffffffffu; sh.or_all = 0u; sh.n_valid = 0; sh.n_pos = 0; sh.status = 0; }
     __syncthreads();
+    const long long clk0 = clock64();       // phase clocks (thread 0) -> info_out[5..7]: diagnostics of this one-CTA pipeline
 
     // ---- 1 keys: score -> descending-sortable key, label bit, counts, constant-bit masks (to skip radix passes)
     {
         const bool ignore_neg = flags & EOE_AUC_IGNORE_NEGATIVE_LABELS;
         uint32_t nv = 0, np = 0, bad = 0, a_and = 0xffffffffu, a_or = 0u;
+        float f[kSmallItems];
+        int64_t l[kSmallItems];
+#pragma unroll
+        for (int j = 0; j < kSmallItems; ++j) {                      // all loads first: one memory round trip
+            const int idx = wbase + j * 32 + lane;
+            const bool in = j < items && idx < n;
+            f[j] = in ? to_f32<T>(scores[idx]) : 0.f;
+            l[j] = in ? labels[idx] : 0;
+        }
 #pragma unroll
         for (int j = 0; j < kSmallItems; ++j) {
             const int idx = wbase + j * 32 + lane;
             if (j < items && idx < n) {
-                const float f = to_f32<T>(scores[idx]);
-                const int64_t l = labels[idx];
                 uint32_t key = 0xffffffffu;          // dropped rows sort behind every finite score
                 uint8_t lb = 0;
-                if (!(ignore_neg && l < 0)) {
-                    if (!isfinite(f)) bad = 1;
-                    key = desc_key(f);
-                    lb = (l == 1);
+                if (!(ignore_neg && l[j] < 0)) {
+                    if (!isfinite(f[j])) bad = 1;
+                    key = desc_key(f[j]);
+                    lb = (l[j] == 1);
                     nv++;
                     np += lb;
                 }
@@ -699,7 +712,8 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
 #pragma unroll 1
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = pass * 8;
-        if (((varying >> shift) & 255u) == 0u) continue;           // every key has the same digit: the pass is the identity
+        const uint32_t vbits = (varying >> shift) & 255u;
+        if (vbits == 0u) continue;                                  // every key has the same digit: the pass is the identity
         reinterpret_cast<uint4*>(&sh.warp_hist[0][0])[tid] = make_uint4(0u, 0u, 0u, 0u);      // 32 x 256 x 2 B = 1024 x 16 B
         uint32_t key[kSmallItems], rl[kSmallItems];                 // rl = rank within the warp's digit run | label << 16
 #pragma unroll
@@ -716,15 +730,24 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
             if (j < items) {
                 const bool valid = (wbase + j * 32 + lane) < n;
                 const uint32_t d = (key[j] >> shift) & 255u;
-                const uint32_t mask = __match_any_sync(kFullMask, valid ? d : (256u + lane));
-                const int leader = __ffs(mask) - 1;
-                uint32_t old = 0;
-                if (lane == leader && valid) {
-                    old = sh.warp_hist[warp][d];
-                    sh.warp_hist[warp][d] = (uint16_t)(old + __popc(mask));
+                uint32_t mask = __ballot_sync(kFullMask, valid);   // peers: valid lanes holding the same digit
+#pragma unroll
+                for (int bit = 0; bit < 8; ++bit) {
+                    if ((vbits >> bit) & 1u) {                      // uniform: constant bits need no ballot
+                        const uint32_t bal = __ballot_sync(kFullMask, (d >> bit) & 1u);
+                        mask &= ((d >> bit) & 1u) ? bal : ~bal;
+                    }
                 }
-                old = __shfl_sync(kFullMask, old, leader);
-                rl[j] |= old + __popc(mask & lt_mask);
+                if (valid) {
+                    const int leader = __ffs(mask) - 1;
+                    uint32_t old = 0;
+                    if (lane == leader) {
+                        old = sh.warp_hist[warp][d];
+                        sh.warp_hist[warp][d] = (uint16_t)(old + __popc(mask));
+                    }
+                    old = __shfl_sync(mask, old, leader);
+                    rl[j] |= old + __popc(mask & lt_mask);
+                }
                 __syncwarp();
             }
         }
@@ -753,6 +776,7 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
         __syncthreads();
     }
 
+    const long long clk1 = clock64();
     const int nv = (int)sh.n_valid;
     const int npos = (int)sh.n_pos;
     // ---- 3 distinct thresholds (blocked arrangement: thread t owns rows [t * per, (t + 1) * per))
@@ -769,58 +793,69 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
         uint32_t slot = block_excl_scan_1024(fc, sh.scan_tmp, &tot_f);
         uint32_t tps = block_excl_scan_1024(lc, sh.scan_tmp, nullptr);
         m = (int)tot_f;
+        const bool want_keys = thr_out || pthr_out;
         for (int i = lo; i < hi; ++i) {
             tps += sh.labs[i];
             if ((i == nv - 1) || (sh.keys[i] != sh.keys[i + 1])) {
-                d_tps[slot] = tps;
-                d_fps[slot] = 1u + (uint32_t)i - tps;
-                d_key[slot] = sh.keys[i];
+                sh.d_tps[slot] = (uint16_t)tps;
+                sh.d_fps[slot] = (uint16_t)(1u + (uint32_t)i - tps);
+                if (want_keys) d_key[slot] = sh.keys[i];
                 ++slot;
             }
         }
     }
     __syncthreads();
-    // ---- 4 corners (roc_curve drop_intermediate=True), origin prepended
+    // ---- 4 corners (roc_curve drop_intermediate=True), origin prepended; kept points -> sh.keys as (tps << 16 | fps)
     int kept = 0;
     {
         const int per = (m + kSmallThreads - 1) / kSmallThreads;
         const int lo = min(m, tid * per), hi = min(m, lo + per);
-        auto keep_at = [&](int i) {
-            if (m <= 2 || i == 0 || i == m - 1) return true;
-            const int64_t f0 = d_fps[i - 1], f1 = d_fps[i], f2 = d_fps[i + 1];
-            const int64_t t0 = d_tps[i - 1], t1 = d_tps[i], t2 = d_tps[i + 1];
-            return (f0 - 2 * f1 + f2 != 0) || (t0 - 2 * t1 + t2 != 0);
-        };
         uint32_t kc = 0;
-        for (int i = lo; i < hi; ++i) kc += keep_at(i);
+        for (int i = lo; i < hi; ++i) {
+            bool kp = true;
+            if (!(m <= 2 || i == 0 || i == m - 1)) {
+                const int f0 = sh.d_fps[i - 1], f1 = sh.d_fps[i], f2 = sh.d_fps[i + 1];
+                const int t0 = sh.d_tps[i - 1], t1 = sh.d_tps[i], t2 = sh.d_tps[i + 1];
+                kp = (f0 - 2 * f1 + f2 != 0) || (t0 - 2 * t1 + t2 != 0);
+            }
+            sh.labs[i] = kp;
+            kc += kp;
+        }
         uint32_t tot;
-        uint32_t slot = block_excl_scan_1024(kc, sh.scan_tmp, &tot) + 1;      // +1: the prepended origin
-        kept = (int)tot;
+        uint32_t slot = block_excl_scan_1024(kc, sh.scan_tmp, &tot) + 1;      // +1: the prepended origin; also orders the
+        kept = (int)tot;                                                       // reads of sh.keys above before the writes below
         if (tid == 0) {
-            k_tps[0] = 0; k_fps[0] = 0;
+            sh.keys[0] = 0u;
             if (thr_out) thr_out[0] = INFINITY;
         }
         for (int i = lo; i < hi; ++i) {
-            if (keep_at(i)) {
-                k_tps[slot] = d_tps[i];
-                k_fps[slot] = d_fps[i];
+            if (sh.labs[i]) {
+                sh.keys[slot] = ((uint32_t)sh.d_tps[i] << 16) | (uint32_t)sh.d_fps[i];
                 if (thr_out) thr_out[slot] = key_to_score(d_key[i]);
                 ++slot;
             }
         }
     }
     __syncthreads();
-    // ---- 5 terms (same operation sequence as auc_terms_kernel)
+    const long long clk2 = clock64();
+    // ---- 5 terms (same operation sequence as auc_terms_kernel): a warp takes 31 consecutive terms = 32 points, one
+    // pair of fp64 divisions per point, the right neighbour's (fpr, tpr) by shuffle
     {
         const int P = kept + 1;
         const double ftot = (double)(nv - npos), ttot = (double)npos;
-        for (int i = tid; i < P; i += kSmallThreads) {
-            const double f0 = __ddiv_rn((double)k_fps[i], ftot), t0 = __ddiv_rn((double)k_tps[i], ttot);
-            if (fpr_out) { fpr_out[i] = f0; tpr_out[i] = t0; }
-            if (i + 1 < P) {
-                const double f1 = __ddiv_rn((double)k_fps[i + 1], ftot), t1 = __ddiv_rn((double)k_tps[i + 1], ttot);
-                terms[i] = __ddiv_rn(__dmul_rn(__dsub_rn(f1, f0), __dadd_rn(t1, t0)), 2.0);
+        for (int base = warp * 31; base < P; base += 32 * 31) {
+            const int i = base + lane;
+            double f0 = 0.0, t0 = 0.0;
+            if (i < P) {
+                const uint32_t pk = sh.keys[i];
+                f0 = __ddiv_rn((double)(pk & 0xffffu), ftot);
+                t0 = __ddiv_rn((double)(pk >> 16), ttot);
+                // lane 31's point is lane 0's point of the next chunk and is written there
+                if (fpr_out && lane < 31) { fpr_out[i] = f0; tpr_out[i] = t0; }
             }
+            const double f1 = __shfl_down_sync(kFullMask, f0, 1), t1 = __shfl_down_sync(kFullMask, t0, 1);
+            if (lane < 31 && i + 1 < P)
+                terms[i] = __dmul_rn(__dmul_rn(__dsub_rn(f1, f0), __dadd_rn(t1, t0)), 0.5);   // x / 2.0 == x * 0.5, bit for bit
         }
     }
     __syncthreads();
@@ -837,10 +872,10 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
     if (flags & EOE_AUC_WITH_PRC) {
         const double ttot = (double)npos;
         auto prec = [&](int j) {
-            const double tp = (double)d_tps[j], ps = __dadd_rn(tp, (double)d_fps[j]);
+            const double tp = (double)sh.d_tps[j], ps = __dadd_rn(tp, (double)sh.d_fps[j]);
             return ps != 0.0 ? __ddiv_rn(tp, ps) : 0.0;
         };
-        auto rec = [&](int j) { return ttot == 0.0 ? 1.0 : __ddiv_rn((double)d_tps[j], ttot); };
+        auto rec = [&](int j) { return ttot == 0.0 ? 1.0 : __ddiv_rn((double)sh.d_tps[j], ttot); };
         for (int i = tid; i < m; i += kSmallThreads) {
             const int j = m - 1 - i;
             const double p = prec(j), r = rec(j);
@@ -856,7 +891,7 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
     }
     if (info_out && tid == 0) {
         info_out[0] = nv; info_out[1] = npos; info_out[2] = m; info_out[3] = kept + 1; info_out[4] = (int64_t)status;
-        info_out[5] = info_out[6] = info_out[7] = 0;
+        info_out[5] = clk1 - clk0; info_out[6] = clk2 - clk1; info_out[7] = clock64() - clk2;
     }
 }
 
@@ -872,8 +907,7 @@ static int auc_run_small(const void* scores, const int64_t* labels, int64_t n, i
         attr_set = true;
     }
     kern<<<1, kSmallThreads, sizeof(SmallShared), st>>>(
-        (const T*)scores, labels, (int)n, flags, (uint32_t*)(ws + L.d_tps), (uint32_t*)(ws + L.d_fps),
-        (uint32_t*)(ws + L.keys_b), (uint32_t*)(ws + L.k_tps), (uint32_t*)(ws + L.k_fps), (double*)(ws + L.terms), auc_out,
+        (const T*)scores, labels, (int)n, flags, (uint32_t*)(ws + L.keys_b), (double*)(ws + L.terms), auc_out,
         info_out, fpr_out, tpr_out, thr_out, prec_out, rec_out, pthr_out);
     return check_launch("auc (single launch)", 1);
 }

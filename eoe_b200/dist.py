@@ -108,6 +108,7 @@ class GradBuckets:
 
     def __init__(self, params, bucket_bytes: int = 32 << 20, group=None):
         self.group = group
+        self.enabled = True          # False: gradients stay local (no collective is launched; A/B timing of the overlap)
         self.rank, self.ws = world()
         self.params = [p for p in params if p.requires_grad]
         self.buckets: List[torch.Tensor] = []
@@ -140,6 +141,8 @@ class GradBuckets:
         self._pending = list(self._counts)
 
     def _hook(self, p):
+        if not self.enabled:
+            return
         bi = self._bucket_of[p]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
@@ -147,7 +150,7 @@ class GradBuckets:
 
     def finish(self):
         """Call after loss.backward(): wait for the in-flight all-reduces, average, re-arm."""
-        if self.ws > 1:
+        if self.ws > 1 and self.enabled:
             for bi, left in enumerate(self._pending):          # parameters that received no gradient this step
                 if left != 0:
                     self._works.append(dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))

@@ -31,7 +31,7 @@ class ADTrainer(ABC):
 
     def __init__(self, model: Optional[torch.nn.Module], epochs: int = 0, lr: float = 1e-3, wdk: float = 0.0,
                  milestones: Sequence[int] = (), batch_size: int = 128, ad_mode: str = "one_vs_rest",
-                 device="cuda", data_parallel: bool = False, sgd: bool = False):
+                 device="cuda", data_parallel: bool = False, sgd: bool = False, graph_step: bool = False):
         if ad_mode not in self.AD_MODES:
             raise NotImplementedError(f"AD mode {ad_mode} unknown. Known modes are {self.AD_MODES}.")
         self.model = model
@@ -41,6 +41,10 @@ class ADTrainer(ABC):
         self.center = None
         self.data_parallel = data_parallel
         self.sgd = sgd                       # the reference uses SGD(nesterov) iff the model is CLIP (:379-383)
+        # graph_step: capture one whole training step (model forward, fused loss + score kernel, backward, optimiser)
+        # into a CUDA graph and replay it per batch: at the reference's batch size (128 + 128 rows of a
+        # small CNN) the step is ~100 kernel launches of a few microseconds each, i.e. bound by the host.
+        self.graph_step = graph_step
         self._score_cache = None
 
     # ---------------------------------------------------------------- hooks (ad_trainer.py:624-662)
@@ -105,20 +109,40 @@ class ADTrainer(ABC):
                 raise ValueError("train_cls with epochs > 0 needs a model with trainable parameters")
             self.center = self.prepare_metric(clsstr, loader, model, seed)
             return model.eval(), None, []
+        use_graph = self.graph_step and self.device.type == "cuda" and not (self.data_parallel and ws > 1)
+        # a captured Adam step reads the learning rate from a device tensor, which MultiStepLR updates in place; SGD's
+        # foreach update needs a python float (it is baked into the graph: the step is re-captured when the schedule moves)
+        lr = torch.tensor(self.lr, dtype=torch.float32, device=self.device) if (use_graph and not self.sgd) else self.lr
         if self.sgd:
-            opt = torch.optim.SGD(params, lr=self.lr, weight_decay=self.wdk, momentum=0.9, nesterov=True)
+            opt = torch.optim.SGD(params, lr=lr, weight_decay=self.wdk, momentum=0.9, nesterov=True)
         else:
-            opt = torch.optim.Adam(params, lr=self.lr, weight_decay=self.wdk, amsgrad=False)
+            opt = torch.optim.Adam(params, lr=lr, weight_decay=self.wdk, amsgrad=False, capturable=use_graph)
         sched = torch.optim.lr_scheduler.MultiStepLR(opt, self.milestones, 0.1)
         buckets = edist.GradBuckets(params) if (self.data_parallel and ws > 1) else None
         center = self.center = self._sync_metric(self.prepare_metric(clsstr, loader, model, seed))
         self._check_equal_batches(loader)
         cls_roc, losses = None, []
+        graph = None            # (CUDAGraph, static imgs, static lbls, static loss, static scores, lr) once captured
         for ep in range(epochs):
             ep_labels, ep_ascores, ep_losses = [], [], []
             for imgs, lbls, _idcs in loader:
                 imgs = imgs.to(self.device, non_blocking=True)
                 lbls = lbls.to(self.device, non_blocking=True)
+                if use_graph:
+                    lr_now = opt.param_groups[0]["lr"]
+                    if graph is not None and not torch.is_tensor(lr_now) and graph[5] != lr_now:
+                        graph = None                                       # lr milestone passed: capture again
+                    if graph is None:
+                        graph = self._capture_step(model, opt, center, imgs, lbls, nominal_label)
+                    if graph[1].shape == imgs.shape and graph[2].shape == lbls.shape:
+                        graph[1].copy_(imgs)
+                        graph[2].copy_(lbls)
+                        graph[0].replay()
+                        ep_labels.append(lbls.detach())
+                        ep_ascores.append(graph[4].clone())
+                        ep_losses.append(graph[3].clone())
+                        continue
+                    # a ragged last batch runs eagerly below
                 if buckets is not None:
                     buckets.zero_grad()
                 else:
@@ -147,6 +171,48 @@ class ADTrainer(ABC):
                 cls_roc = roc if roc is not None else cls_roc
             sched.step()
         return model.eval(), cls_roc, losses
+
+    def _capture_step(self, model, opt, center, imgs, lbls, nominal_label):
+        """Capture `zero_grad -> model -> loss (fused kernel) -> backward -> optimiser step -> scores` once, on static input
+        buffers.  Three eager steps on a side stream first (PyTorch's whole-network capture recipe: lazy initialisations
+        and the optimiser state must exist before capture); they are REAL steps on this batch's data only if the caller
+        accepts that -- so they run on a deep copy of model + optimiser state and are discarded."""
+        import copy
+        s_imgs, s_lbls = imgs.clone(), lbls.clone()
+        saved_model = copy.deepcopy(model.state_dict())
+        saved_opt = {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()} for p, st in opt.state.items()}
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                opt.zero_grad(set_to_none=True)
+                f = model(s_imgs)
+                l = self.loss(f, s_lbls, center, inputs=s_imgs, nominal_label=nominal_label)
+                l.backward()
+                opt.step()
+                self.compute_anomaly_score(f, center, inputs=s_imgs, nominal_label=nominal_label)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        # undo the warm-up IN PLACE (the optimiser's state tensors must exist before capture, or they would be created --
+        # and re-zeroed at every replay -- inside the graph): weights, BatchNorm statistics, moments and step counters
+        # return to their values before it (zero where the state did not exist yet)
+        model.load_state_dict(saved_model)
+        for p, st in opt.state.items():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    old = saved_opt.get(p, {}).get(k)
+                    if torch.is_tensor(old):
+                        v.copy_(old)
+                    else:
+                        v.zero_()
+        g = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(g):
+            f = model(s_imgs)
+            s_loss = self.loss(f, s_lbls, center, inputs=s_imgs, nominal_label=nominal_label)
+            s_loss.backward()
+            opt.step()
+            s_scores = self.compute_anomaly_score(f, center, inputs=s_imgs, nominal_label=nominal_label).detach().reshape(-1)
+        return g, s_imgs, s_lbls, s_loss.detach(), s_scores, opt.param_groups[0]["lr"]
 
     # ---------------------------------------------------------------- evaluation (ad_trainer.py:473-550)
     @torch.no_grad()

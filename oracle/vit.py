@@ -155,10 +155,11 @@ def _encode_image(sd, imgs, operand_dtype, heads, return_tokens, fold_layernorm)
         q = q.reshape(B, L, heads, dh).transpose(1, 2)
         k = k.reshape(B, L, heads, dh).transpose(1, 2)
         v = v.reshape(B, L, heads, dh).transpose(1, 2)
-        s = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(dh))
+        s = None if dt is None else (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(dh))
         if dt is None:
-            pr = s.softmax(dim=-1)
-            o = pr @ v
+            # fused attention, as nn.MultiheadAttention runs it in the live reference (same math; keeps the CPU baseline
+            # this oracle doubles as -- bench.py cpu_baseline -- as fast as the reference itself, tools/anchor_cpu_arm.py)
+            o = F.scaled_dot_product_attention(q, k, v)
         else:
             # CUDA path: un-normalised exp in 16 bit for the PV product, fp32 row sum, divide after
             e = torch.exp(s - s.amax(dim=-1, keepdim=True))

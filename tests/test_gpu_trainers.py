@@ -195,3 +195,51 @@ def test_cfg5_hsc_on_clip_vitb16_features_with_sgd():
     for p, q in zip(head.parameters(), ref_head.parameters()):
         torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-3, atol=2e-5)
     assert roc is not None and 0.0 <= roc.auc <= 1.0
+
+
+def _cnn32_like():
+    """the shape of the reference's CIFAR network (models/cnn.py:44-86: 3 x [conv5x5 - BatchNorm - LeakyReLU - pool],
+    two linear layers, rep_dim 256, BatchNorm everywhere) restated small; the reference model itself stays out of the product"""
+    torch.manual_seed(0)
+    nn = torch.nn
+    return nn.Sequential(
+        nn.Conv2d(3, 32, 5, padding=2, bias=False), nn.BatchNorm2d(32, eps=1e-4, affine=False), nn.LeakyReLU(), nn.MaxPool2d(2),
+        nn.Conv2d(32, 64, 5, padding=2, bias=False), nn.BatchNorm2d(64, eps=1e-4, affine=False), nn.LeakyReLU(), nn.MaxPool2d(2),
+        nn.Conv2d(64, 128, 5, padding=2, bias=False), nn.BatchNorm2d(128, eps=1e-4, affine=False), nn.LeakyReLU(), nn.MaxPool2d(2),
+        nn.Flatten(), nn.Linear(128 * 4 * 4, 512, bias=False), nn.BatchNorm1d(512, eps=1e-4, affine=False), nn.LeakyReLU(),
+        nn.Linear(512, 256, bias=False))
+
+
+@pytest.mark.parametrize("objective,sgd", [("hsc", False), ("bce", False), ("hsc", True)])
+def test_graph_captured_step_equals_eager(objective, sgd):
+    """graph_step=True replays one captured CUDA graph per batch (model forward, fused loss + score kernel, backward,
+    optimiser, BatchNorm statistics, lr schedule through a device tensor): same losses, scores and weights as the eager
+    loop, cfg1's shapes (256 x 3 x 32 x 32 per batch, CNN with BatchNorm), including a ragged last batch run eagerly."""
+    from eoe_b200.training import TRAINER
+    g = torch.Generator().manual_seed(5)
+    loader = []
+    for i in range(5):
+        nb = 256 if i < 4 else 96
+        imgs = torch.randn(nb, 3, 32, 32, generator=g)
+        lbls = (torch.arange(nb) >= nb // 2).long()
+        imgs[lbls == 1] += 0.5
+        loader.append((imgs, lbls, torch.arange(nb)))
+    res = {}
+    for graph in (False, True):
+        model = _cnn32_like()
+        if objective == "bce":
+            model.append(torch.nn.Linear(256, 1))
+        tr = TRAINER[objective](model, epochs=3, lr=1e-3 if not sgd else 1e-2, milestones=[2], device=DEV, graph_step=graph, sgd=sgd)
+        model, roc, losses = tr.train_cls(model, loader, nominal_label=0)
+        res[graph] = (losses, roc.auc, [p.detach().clone() for p in model.parameters()],
+                      [b.detach().clone().float() for b in model.buffers()])
+    # SGD updates are proportional to the gradients: the two runs stay together to rounding.  Adam's first steps move
+    # every weight by ~lr whatever the size of its gradient (m / sqrt(v) = +-1), so weights whose gradient is rounding
+    # noise legitimately end up 2 * lr * steps apart between ANY two runs; the losses still agree to a few 1e-3.
+    np.testing.assert_allclose(res[True][0], res[False][0], rtol=2e-4 if sgd else 5e-3)
+    assert abs(res[True][1] - res[False][1]) < 5e-3
+    if sgd:
+        for a, b in zip(res[True][2], res[False][2]):
+            torch.testing.assert_close(a, b, rtol=2e-3, atol=2e-4)
+    for a, b in zip(res[True][3], res[False][3]):          # BatchNorm running statistics (follow the weights)
+        torch.testing.assert_close(a, b, rtol=5e-3 if sgd else 5e-2, atol=5e-4 if sgd else 5e-3)
