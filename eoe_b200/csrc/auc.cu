@@ -598,9 +598,8 @@ struct SmallShared {
     uint32_t keys[kSmallMax + 8];      // sorted keys; after the distinct phase: kept ROC points packed (tps << 16 | fps)
     uint16_t d_tps[kSmallMax];         // distinct thresholds: true positives / false positives (<= 16 384: 16 bits)
     uint16_t d_fps[kSmallMax];
-    uint16_t warp_hist[32][256];
+    uint32_t cnt[8 * kSmallThreads + 8 * kSmallThreads / 32];   // 16 digit counters per thread, two per word, padded
     uint8_t labs[kSmallMax];           // label bits; after the distinct phase: keep flags of the corner filter
-    uint32_t digit_base[256];
     uint32_t scan_tmp[32];
     uint32_t and_all, or_all, n_valid, n_pos, status, pad[3];
     double nodes[1024];                // pairwise tree: depth <= 8 for <= 16 385 terms
@@ -708,72 +707,69 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
     __syncthreads();
     const uint32_t varying = sh.and_all ^ sh.or_all;               // bits that differ between at least two keys
 
-    // ---- 2 sort: LSD radix, 8 bits per pass, in place in shared memory (keys are held in registers across the scatter)
+    // ---- 2 sort: LSD radix, 4 bits per pass, in place in shared memory.  Thread t owns the S consecutive keys
+    // [t * S, t * S + S) (S odd: conflict-free) and ranks them with 16 thread-private counters packed two per word
+    // (digit w in the low half, digit w + 8 in the high half of word w: no warp votes, no atomics -- one shared-memory
+    // read-modify-write per key); a raking scan over the (digit, thread)-ordered counters turns them into positions.
+    // Passes whose four bits are the same in every key are skipped (fp16 scores: 13 constant low bits).
+    {
+        const int S = items | 1;
+        const int kbase = tid * S;
+        auto cidx = [](int w, int t) { const int lin = w * kSmallThreads + t; return lin + (lin >> 5); };   // padded
 #pragma unroll 1
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = pass * 8;
-        const uint32_t vbits = (varying >> shift) & 255u;
-        if (vbits == 0u) continue;                                  // every key has the same digit: the pass is the identity
-        reinterpret_cast<uint4*>(&sh.warp_hist[0][0])[tid] = make_uint4(0u, 0u, 0u, 0u);      // 32 x 256 x 2 B = 1024 x 16 B
-        uint32_t key[kSmallItems], rl[kSmallItems];                 // rl = rank within the warp's digit run | label << 16
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = pass * 4;
+            if (((varying >> shift) & 15u) == 0u) continue;             // the pass would be the identity
 #pragma unroll
-        for (int j = 0; j < kSmallItems; ++j) {
-            const int idx = wbase + j * 32 + lane;
-            const bool valid = j < items && idx < n;
-            key[j] = valid ? sh.keys[idx] : 0xffffffffu;
-            rl[j] = valid ? ((uint32_t)sh.labs[idx] << 16) : 0u;
-        }
-        __syncthreads();
-        const uint32_t lt_mask = (1u << lane) - 1u;
+            for (int w = 0; w < 8; ++w) sh.cnt[cidx(w, tid)] = 0u;
+            uint32_t key[kSmallItems + 1];
+            uint32_t rl[kSmallItems + 1];                               // rank among the thread's equal digits | label << 8
 #pragma unroll
-        for (int j = 0; j < kSmallItems; ++j) {
-            if (j < items) {
-                const bool valid = (wbase + j * 32 + lane) < n;
-                const uint32_t d = (key[j] >> shift) & 255u;
-                uint32_t mask = __ballot_sync(kFullMask, valid);   // peers: valid lanes holding the same digit
+            for (int j = 0; j <= kSmallItems; ++j) {
+                const bool valid = j < S && kbase + j < n;
+                key[j] = valid ? sh.keys[kbase + j] : 0xffffffffu;
+                rl[j] = valid ? ((uint32_t)sh.labs[kbase + j] << 8) : 0u;
+            }
 #pragma unroll
-                for (int bit = 0; bit < 8; ++bit) {
-                    if ((vbits >> bit) & 1u) {                      // uniform: constant bits need no ballot
-                        const uint32_t bal = __ballot_sync(kFullMask, (d >> bit) & 1u);
-                        mask &= ((d >> bit) & 1u) ? bal : ~bal;
-                    }
+            for (int j = 0; j <= kSmallItems; ++j) {
+                if (j < S && kbase + j < n) {
+                    const uint32_t d = (key[j] >> shift) & 15u;
+                    const int ci = cidx((int)(d & 7u), tid);
+                    const uint32_t hs = (d >> 3) * 16u;
+                    const uint32_t word = sh.cnt[ci];
+                    rl[j] |= (word >> hs) & 0xffu;
+                    sh.cnt[ci] = word + (1u << hs);
                 }
-                if (valid) {
-                    const int leader = __ffs(mask) - 1;
-                    uint32_t old = 0;
-                    if (lane == leader) {
-                        old = sh.warp_hist[warp][d];
-                        sh.warp_hist[warp][d] = (uint16_t)(old + __popc(mask));
-                    }
-                    old = __shfl_sync(mask, old, leader);
-                    rl[j] |= old + __popc(mask & lt_mask);
-                }
-                __syncwarp();
             }
-        }
-        __syncthreads();
-        uint32_t run = 0;
-        if (tid < 256) {                                            // thread = digit: exclusive prefix over the 32 warps
-#pragma unroll 8
-            for (int w = 0; w < 32; ++w) {
-                const uint32_t t = sh.warp_hist[w][tid];
-                sh.warp_hist[w][tid] = (uint16_t)run;
-                run += t;
-            }
-        }
-        const uint32_t dstart = block_excl_scan_1024(run, sh.scan_tmp, nullptr);
-        if (tid < 256) sh.digit_base[tid] = dstart;
-        __syncthreads();
+            __syncthreads();                                            // every key is in registers, every count is final
+            // raking scan: thread r owns the 8 consecutive entries [8 r, 8 r + 8) of the (digit word, thread) order
+            uint32_t c8[8], tot = 0;
+            {
+                const int lin0 = tid * 8, p0 = lin0 + (lin0 >> 5);     // 8 consecutive entries never straddle a padding slot
 #pragma unroll
-        for (int j = 0; j < kSmallItems; ++j) {
-            if (j < items && (wbase + j * 32 + lane) < n) {
-                const uint32_t d = (key[j] >> shift) & 255u;
-                const uint32_t pos = sh.digit_base[d] + sh.warp_hist[warp][d] + (rl[j] & 0xffffu);
-                sh.keys[pos] = key[j];
-                sh.labs[pos] = (uint8_t)(rl[j] >> 16);
+                for (int i = 0; i < 8; ++i) { c8[i] = sh.cnt[p0 + i]; tot += c8[i]; }
+                uint32_t block_tot;
+                uint32_t run = block_excl_scan_1024(tot, sh.scan_tmp, &block_tot);     // packed halves: no carry (<= 16 384)
+                const uint32_t low_total = block_tot & 0xffffu;         // keys whose digit is 0..7 precede every digit 8..15
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    sh.cnt[p0 + i] = run + (low_total << 16);
+                    run += c8[i];
+                }
             }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j <= kSmallItems; ++j) {
+                if (j < S && kbase + j < n) {
+                    const uint32_t d = (key[j] >> shift) & 15u;
+                    const uint32_t word = sh.cnt[cidx((int)(d & 7u), tid)];
+                    const uint32_t pos = ((word >> ((d >> 3) * 16u)) & 0xffffu) + (rl[j] & 0xffu);
+                    sh.keys[pos] = key[j];
+                    sh.labs[pos] = (uint8_t)(rl[j] >> 8);
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     const long long clk1 = clock64();
@@ -782,7 +778,7 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
     // ---- 3 distinct thresholds (blocked arrangement: thread t owns rows [t * per, (t + 1) * per))
     int m = 0;
     {
-        const int per = (nv + kSmallThreads - 1) / kSmallThreads;
+        const int per = ((nv + kSmallThreads - 1) / kSmallThreads) | 1;     // odd: the strided walks below are bank-conflict free
         const int lo = min(nv, tid * per), hi = min(nv, lo + per);
         uint32_t fc = 0, lc = 0;
         for (int i = lo; i < hi; ++i) {
@@ -808,7 +804,7 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
     // ---- 4 corners (roc_curve drop_intermediate=True), origin prepended; kept points -> sh.keys as (tps << 16 | fps)
     int kept = 0;
     {
-        const int per = (m + kSmallThreads - 1) / kSmallThreads;
+        const int per = ((m + kSmallThreads - 1) / kSmallThreads) | 1;
         const int lo = min(m, tid * per), hi = min(m, lo + per);
         uint32_t kc = 0;
         for (int i = lo; i < hi; ++i) {

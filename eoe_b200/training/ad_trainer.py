@@ -110,11 +110,12 @@ class ADTrainer(ABC):
             self.center = self.prepare_metric(clsstr, loader, model, seed)
             return model.eval(), None, []
         use_graph = self.graph_step and self.device.type == "cuda" and not (self.data_parallel and ws > 1)
-        # a captured Adam step reads the learning rate from a device tensor, which MultiStepLR updates in place; SGD's
-        # foreach update needs a python float (it is baked into the graph: the step is re-captured when the schedule moves)
-        lr = torch.tensor(self.lr, dtype=torch.float32, device=self.device) if (use_graph and not self.sgd) else self.lr
+        # a captured step reads the learning rate from a device tensor, which MultiStepLR updates in place (Adam:
+        # capturable=True; SGD: the fused implementation takes a tensor lr -- the foreach one would call .item() on it)
+        lr = torch.tensor(self.lr, dtype=torch.float32, device=self.device) if use_graph else self.lr
         if self.sgd:
-            opt = torch.optim.SGD(params, lr=lr, weight_decay=self.wdk, momentum=0.9, nesterov=True)
+            opt = torch.optim.SGD(params, lr=lr, weight_decay=self.wdk, momentum=0.9, nesterov=True,
+                                  **({"fused": True} if use_graph else {}))
         else:
             opt = torch.optim.Adam(params, lr=lr, weight_decay=self.wdk, amsgrad=False, capturable=use_graph)
         sched = torch.optim.lr_scheduler.MultiStepLR(opt, self.milestones, 0.1)
@@ -130,8 +131,10 @@ class ADTrainer(ABC):
                 lbls = lbls.to(self.device, non_blocking=True)
                 if use_graph:
                     lr_now = opt.param_groups[0]["lr"]
-                    if graph is not None and not torch.is_tensor(lr_now) and graph[5] != lr_now:
-                        graph = None                                       # lr milestone passed: capture again
+                    if graph is not None and not (torch.is_tensor(lr_now) and lr_now is graph[5]):
+                        # the schedule replaced the lr object the graph reads (or it is a python float baked into it)
+                        if not (isinstance(lr_now, float) and isinstance(graph[5], float) and lr_now == graph[5]):
+                            graph = None                                   # capture again with the current lr
                     if graph is None:
                         graph = self._capture_step(model, opt, center, imgs, lbls, nominal_label)
                     if graph[1].shape == imgs.shape and graph[2].shape == lbls.shape:
