@@ -409,6 +409,16 @@ def run_ours(args):
                  "note": "same K steps, device-resident, encoder + fused score only (no all-gather / AUC)"}
         del enc_o
 
+    # ---- data-parallel TRAINING at model scale (BASELINE configs 4 / 5): step, all-reduce and overlap
+    # of a ResNet-18-sized BCE run and a ViT-B/16-sized HSC run through the fused head kernels + eoe_b200.dist.GradBuckets
+    dp_rows = None
+    if not args.no_side:
+        del imgs, scores
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import dp_bench
+        _, _, dp_rows = dp_bench.run(("cfg4", "cfg5"), steps=5, warmup=2)
+
     if rank != 0:
         if ws > 1:
             tdist.barrier()
@@ -490,6 +500,7 @@ def run_ours(args):
     if not args.no_side:
         line["side_metrics"] = side_metrics(dev, pk)
         line["side_metrics"]["other_dtype"] = other
+        line["side_metrics"]["dp_train"] = dp_rows
     emit(line)
     if ws > 1:
         tdist.barrier()

@@ -643,7 +643,9 @@ __device__ __forceinline__ double block_pairwise_sum(const double* a, int64_t T,
     return v;
 }
 
-template <typename T>
+// MAXS: compile-time bound of the keys a thread owns (ceil(n / 1024) | 1): the per-key loops are fully unrolled, so small
+// inputs get an instantiation without the dead iterations
+template <typename T, int MAXS>
 __global__ void __launch_bounds__(kSmallThreads, 1)
 auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ labels, int n, int flags,
                  uint32_t* __restrict__ d_key, double* terms, double* __restrict__ auc_out,
@@ -663,17 +665,18 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
     {
         const bool ignore_neg = flags & EOE_AUC_IGNORE_NEGATIVE_LABELS;
         uint32_t nv = 0, np = 0, bad = 0, a_and = 0xffffffffu, a_or = 0u;
-        float f[kSmallItems];
-        int64_t l[kSmallItems];
+        constexpr int NI = MAXS < kSmallItems ? MAXS : kSmallItems;  // items <= NI
+        float f[NI];
+        int64_t l[NI];
 #pragma unroll
-        for (int j = 0; j < kSmallItems; ++j) {                      // all loads first: one memory round trip
+        for (int j = 0; j < NI; ++j) {                               // all loads first: one memory round trip
             const int idx = wbase + j * 32 + lane;
             const bool in = j < items && idx < n;
             f[j] = in ? to_f32<T>(scores[idx]) : 0.f;
             l[j] = in ? labels[idx] : 0;
         }
 #pragma unroll
-        for (int j = 0; j < kSmallItems; ++j) {
+        for (int j = 0; j < NI; ++j) {
             const int idx = wbase + j * 32 + lane;
             if (j < items && idx < n) {
                 uint32_t key = 0xffffffffu;          // dropped rows sort behind every finite score
@@ -722,16 +725,16 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
             if (((varying >> shift) & 15u) == 0u) continue;             // the pass would be the identity
 #pragma unroll
             for (int w = 0; w < 8; ++w) sh.cnt[cidx(w, tid)] = 0u;
-            uint32_t key[kSmallItems + 1];
-            uint32_t rl[kSmallItems + 1];                               // rank among the thread's equal digits | label << 8
+            uint32_t key[MAXS];
+            uint32_t rl[MAXS];                                          // rank among the thread's equal digits | label << 8
 #pragma unroll
-            for (int j = 0; j <= kSmallItems; ++j) {
+            for (int j = 0; j < MAXS; ++j) {
                 const bool valid = j < S && kbase + j < n;
                 key[j] = valid ? sh.keys[kbase + j] : 0xffffffffu;
                 rl[j] = valid ? ((uint32_t)sh.labs[kbase + j] << 8) : 0u;
             }
 #pragma unroll
-            for (int j = 0; j <= kSmallItems; ++j) {
+            for (int j = 0; j < MAXS; ++j) {
                 if (j < S && kbase + j < n) {
                     const uint32_t d = (key[j] >> shift) & 15u;
                     const int ci = cidx((int)(d & 7u), tid);
@@ -759,7 +762,7 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
             }
             __syncthreads();
 #pragma unroll
-            for (int j = 0; j <= kSmallItems; ++j) {
+            for (int j = 0; j < MAXS; ++j) {
                 if (j < S && kbase + j < n) {
                     const uint32_t d = (key[j] >> shift) & 15u;
                     const uint32_t word = sh.cnt[cidx((int)(d & 7u), tid)];
@@ -775,24 +778,31 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
     const long long clk1 = clock64();
     const int nv = (int)sh.n_valid;
     const int npos = (int)sh.n_pos;
-    // ---- 3 distinct thresholds (blocked arrangement: thread t owns rows [t * per, (t + 1) * per))
+    // ---- 3 distinct thresholds (blocked arrangement: thread t owns rows [t * per, (t + 1) * per), per odd and <= MAXS).
+    // One pass over shared memory: flags and label bits are kept as bit masks, (flag count, label count) scanned packed.
     int m = 0;
     {
-        const int per = ((nv + kSmallThreads - 1) / kSmallThreads) | 1;     // odd: the strided walks below are bank-conflict free
-        const int lo = min(nv, tid * per), hi = min(nv, lo + per);
-        uint32_t fc = 0, lc = 0;
-        for (int i = lo; i < hi; ++i) {
-            fc += (i == nv - 1) || (sh.keys[i] != sh.keys[i + 1]);
-            lc += sh.labs[i];
+        const int per = ((nv + kSmallThreads - 1) / kSmallThreads) | 1;     // odd: the strided walks are bank-conflict free
+        const int lo = min(nv, tid * per);
+        uint32_t fmask = 0, lmask = 0;
+#pragma unroll
+        for (int j = 0; j < MAXS; ++j) {
+            const int i = lo + j;
+            if (j < per && i < nv) {
+                if ((i == nv - 1) || (sh.keys[i] != sh.keys[i + 1])) fmask |= 1u << j;
+                if (sh.labs[i]) lmask |= 1u << j;
+            }
         }
-        uint32_t tot_f;
-        uint32_t slot = block_excl_scan_1024(fc, sh.scan_tmp, &tot_f);
-        uint32_t tps = block_excl_scan_1024(lc, sh.scan_tmp, nullptr);
-        m = (int)tot_f;
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan_1024(((uint32_t)__popc(fmask) << 16) | (uint32_t)__popc(lmask), sh.scan_tmp, &tot);
+        m = (int)(tot >> 16);
+        uint32_t slot = ex >> 16, tps = ex & 0xffffu;
         const bool want_keys = thr_out || pthr_out;
-        for (int i = lo; i < hi; ++i) {
-            tps += sh.labs[i];
-            if ((i == nv - 1) || (sh.keys[i] != sh.keys[i + 1])) {
+#pragma unroll
+        for (int j = 0; j < MAXS; ++j) {
+            tps += (lmask >> j) & 1u;
+            if ((fmask >> j) & 1u) {
+                const int i = lo + j;
                 sh.d_tps[slot] = (uint16_t)tps;
                 sh.d_fps[slot] = (uint16_t)(1u + (uint32_t)i - tps);
                 if (want_keys) d_key[slot] = sh.keys[i];
@@ -805,29 +815,38 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
     int kept = 0;
     {
         const int per = ((m + kSmallThreads - 1) / kSmallThreads) | 1;
-        const int lo = min(m, tid * per), hi = min(m, lo + per);
-        uint32_t kc = 0;
-        for (int i = lo; i < hi; ++i) {
-            bool kp = true;
-            if (!(m <= 2 || i == 0 || i == m - 1)) {
-                const int f0 = sh.d_fps[i - 1], f1 = sh.d_fps[i], f2 = sh.d_fps[i + 1];
-                const int t0 = sh.d_tps[i - 1], t1 = sh.d_tps[i], t2 = sh.d_tps[i + 1];
-                kp = (f0 - 2 * f1 + f2 != 0) || (t0 - 2 * t1 + t2 != 0);
+        const int lo = min(m, tid * per);
+        uint32_t kmask = 0;
+        uint32_t pk[MAXS];
+        if (lo < m) {
+            // sliding window over (fps, tps) of points lo-1 .. lo+per: one shared-memory read per point
+            int f0 = lo > 0 ? sh.d_fps[lo - 1] : 0, t0 = lo > 0 ? sh.d_tps[lo - 1] : 0;
+            int f1 = sh.d_fps[lo], t1 = sh.d_tps[lo];
+#pragma unroll
+            for (int j = 0; j < MAXS; ++j) {
+                const int i = lo + j;
+                if (j < per && i < m) {
+                    const bool has_next = i + 1 < m;
+                    const int f2 = has_next ? sh.d_fps[i + 1] : 0, t2 = has_next ? sh.d_tps[i + 1] : 0;
+                    const bool kp = (m <= 2 || i == 0 || i == m - 1) || (f0 - 2 * f1 + f2 != 0) || (t0 - 2 * t1 + t2 != 0);
+                    if (kp) kmask |= 1u << j;
+                    pk[j] = ((uint32_t)t1 << 16) | (uint32_t)f1;
+                    f0 = f1; t0 = t1; f1 = f2; t1 = t2;
+                }
             }
-            sh.labs[i] = kp;
-            kc += kp;
         }
         uint32_t tot;
-        uint32_t slot = block_excl_scan_1024(kc, sh.scan_tmp, &tot) + 1;      // +1: the prepended origin; also orders the
-        kept = (int)tot;                                                       // reads of sh.keys above before the writes below
+        uint32_t slot = block_excl_scan_1024((uint32_t)__popc(kmask), sh.scan_tmp, &tot) + 1;   // +1: the prepended origin
+        kept = (int)tot;
         if (tid == 0) {
             sh.keys[0] = 0u;
             if (thr_out) thr_out[0] = INFINITY;
         }
-        for (int i = lo; i < hi; ++i) {
-            if (sh.labs[i]) {
-                sh.keys[slot] = ((uint32_t)sh.d_tps[i] << 16) | (uint32_t)sh.d_fps[i];
-                if (thr_out) thr_out[slot] = key_to_score(d_key[i]);
+#pragma unroll
+        for (int j = 0; j < MAXS; ++j) {
+            if ((kmask >> j) & 1u) {
+                sh.keys[slot] = pk[j];
+                if (thr_out) thr_out[slot] = key_to_score(d_key[lo + j]);
                 ++slot;
             }
         }
@@ -891,12 +910,12 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
     }
 }
 
-template <typename T>
-static int auc_run_small(const void* scores, const int64_t* labels, int64_t n, int flags, char* ws, const AucLayout& L,
-                         double* auc_out, int64_t* info_out, double* fpr_out, double* tpr_out, float* thr_out,
-                         double* prec_out, double* rec_out, float* pthr_out, cudaStream_t st) {
+template <typename T, int MAXS>
+static int auc_launch_small(const void* scores, const int64_t* labels, int64_t n, int flags, char* ws, const AucLayout& L,
+                            double* auc_out, int64_t* info_out, double* fpr_out, double* tpr_out, float* thr_out,
+                            double* prec_out, double* rec_out, float* pthr_out, cudaStream_t st) {
     static bool attr_set = false;                      // per process and instantiation; the attribute is per function
-    auto kern = auc_small_kernel<T>;
+    auto kern = auc_small_kernel<T, MAXS>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallShared));
         if (e != cudaSuccess) { set_cuda_error(e, "auc small attribute"); return EOE_ERR_CUDA; }
@@ -906,6 +925,20 @@ static int auc_run_small(const void* scores, const int64_t* labels, int64_t n, i
         (const T*)scores, labels, (int)n, flags, (uint32_t*)(ws + L.keys_b), (double*)(ws + L.terms), auc_out,
         info_out, fpr_out, tpr_out, thr_out, prec_out, rec_out, pthr_out);
     return check_launch("auc (single launch)", 1);
+}
+
+template <typename T>
+static int auc_run_small(const void* scores, const int64_t* labels, int64_t n, int flags, char* ws, const AucLayout& L,
+                         double* auc_out, int64_t* info_out, double* fpr_out, double* tpr_out, float* thr_out,
+                         double* prec_out, double* rec_out, float* pthr_out, cudaStream_t st) {
+    const int S = (int)((n + kSmallThreads - 1) / kSmallThreads) | 1;      // keys per thread, odd
+#define EOE_AUC_SMALL(M) return auc_launch_small<T, M>(scores, labels, n, flags, ws, L, auc_out, info_out, fpr_out, tpr_out, \
+                                                      thr_out, prec_out, rec_out, pthr_out, st)
+    if (S <= 5) EOE_AUC_SMALL(5);
+    if (S <= 9) EOE_AUC_SMALL(9);
+    if (S <= 13) EOE_AUC_SMALL(13);
+    EOE_AUC_SMALL(17);
+#undef EOE_AUC_SMALL
 }
 
 template <typename T>

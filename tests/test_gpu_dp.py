@@ -1,7 +1,8 @@
 """GPU, >= 2 devices (skipped otherwise): data-parallel training through the re-hosted trainer over NCCL equals the
 single-process run on the global batch, including the BatchNorm caveat SURVEY section 7 raised:
 
-  * a model without batch statistics: DP == global batch to 1e-5 (gradient buckets average equal shards exactly)
+  * a model without batch statistics: DP == global batch to ~1e-5 (gradient buckets average equal shards; only the
+    summation order differs)
   * BatchNorm under plain DP normalises each rank's 128 || 128 shard with its OWN statistics: the run DIFFERS from the
     global-batch run (delta reported, asserted to be visible) -- this is the reference's semantics only at world size 1
   * the same model converted with torch.nn.SyncBatchNorm: statistics are all-reduced, DP == global batch again (1e-4)
@@ -97,7 +98,9 @@ def test_dp_training_equals_global_batch_nccl_world2(kind):
     dl = max(abs((l0 + l1) / 2 - w) / abs(w) for l0, l1, w in zip(res[0][1], res[1][1], want_l))
     print("DP_VS_GLOBAL", dict(kind=kind, max_abs_weight_diff=dw, max_rel_loss_diff=dl, auc_dp=res[0][2], auc_global=want_auc))
     if kind == "plain":
-        assert dw < 1e-5 and dl < 1e-5
+        # measured on 2 x B200: 1.1e-5 on the weights after 6 SGD steps (lr 1e-2, momentum 0.9), 3.6e-5 on the epoch losses:
+        # the all-reduce adds the two shard gradients in another order than one kernel sums the global batch
+        assert dw < 5e-5 and dl < 1e-4
         assert abs(res[0][2] - want_auc) < 1e-6
     elif kind == "syncbn":
         assert dw < 1e-4 and dl < 1e-4
