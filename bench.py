@@ -230,8 +230,11 @@ def side_metrics(dev, pk):
         s_np = (1 - np.exp(-np.abs(rng.standard_normal(n)))).astype(np.float32)
         y_np = (rng.random(n) < 0.5).astype(np.int64)
         sd_, yd_ = torch.from_numpy(s_np).to(dev), torch.from_numpy(y_np).to(dev)
-        ent = {"device_us": us(lambda: metrics.roc_auc_device(sd_, yd_, workspace=ws)), "launches": 1}
+        ent = {"call_us": us(lambda: metrics.roc_auc_device(sd_, yd_, workspace=ws)), "launches": 1,
+               "note": "one call between CUDA events: Python binding + launch + the single kernel (device time alone: "
+                       "profiles/r2_latency_reference_sizes.jsonl, device_us_graph_replay)"}
         if sk_auc is not None:
+            sk_auc(*sk_roc(y_np, s_np)[:2])                  # warm-up (first call imports / allocates)
             t0 = time.perf_counter()
             for _ in range(5):
                 ref = sk_auc(*sk_roc(y_np, s_np)[:2])
@@ -357,25 +360,32 @@ def run_ours(args):
         out, _, _ = metrics.roc_auc_device(s_all, l_all, workspace=auc_ws)
         return out.cpu()                                                 # the AUC is read on the host (sync)
 
-    def time_e2e(hbufs, dbufs):
+    e2e_diag = {}
+
+    def time_e2e(hbufs, dbufs, tag=None):
         e2e_job(min(W, S), hbufs, dbufs)
         sync()
         t0 = time.perf_counter()
+        e0.record()
         e2e_job(S, hbufs, dbufs)
+        e1.record()
         torch.cuda.synchronize()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([wall, e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
         if ws > 1:
             tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
-        return ws * S * B / float(tt.item())
+        if tag:       # wall clock (what `value` of the e2e block is computed from) next to the device time of the same region
+            e2e_diag[tag] = {"wall_ms_per_step": float(tt[0]) * 1e3 / S, "device_ms_per_step": float(tt[1]) * 1e3 / S}
+        return ws * S * B / float(tt[0])
 
     # ---- headline e2e: the dataset's decoded pixels as they sit in host memory -- uint8 NHWC at 224 x 224 -- with ToTensor
     # + Normalize fused into the patchify kernel (eoe_vit_encode_u8)
     host8 = [torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
     dbuf8 = [torch.empty(B, 224, 224, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
-    e2e_u8_val = time_e2e(host8, dbuf8)
+    e2e_u8_val = time_e2e(host8, dbuf8, "u8")
     del host8, dbuf8
     # ---- the same job from fp32 NCHW host batches (what the reference's DataLoader hands over after ToTensor + Normalize)
-    e2e_val = time_e2e(host, dbuf)
+    e2e_val = time_e2e(host, dbuf, "f32")
     del host, dbuf
 
     # ---- e2e from RAW decoded images of the dataset's native size: Resize(bicubic) + CenterCrop + ToTensor + Normalize
@@ -481,9 +491,10 @@ def run_ours(args):
                 "note": "public API (ClipImageEncoder.score + metrics.roc_auc_device) from pinned HOST batches of decoded uint8 "
                         "NHWC pixels (ToTensor + Normalize fused into the patchify kernel, eoe_vit_encode_u8), double-buffered "
                         "H2D on a copy stream, every step's scores and the final AUC read back to the host",
-                "numa_cpus": numa_cpus},
+                "numa_cpus": numa_cpus, "timing": e2e_diag.get("u8")},
         "e2e_f32": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4 + 8,
-                    "note": "same job from pinned fp32 NCHW host batches (the reference DataLoader's output format): 4x the PCIe bytes"},
+                    "note": "same job from pinned fp32 NCHW host batches (the reference DataLoader's output format): 4x the PCIe bytes",
+                    "timing": e2e_diag.get("f32")},
         "e2e_raw": {"value": e2e_raw_val, "unit": UNIT, "h2d_bytes_per_step": B * rh * rw * 3, "d2h_bytes_per_step": B * 4,
                     "note": f"same job from raw uint8 {rh}x{rw} images: Resize(bicubic, Pillow-exact) + CenterCrop + ToTensor + "
                             "Normalize fused into the patchify kernel (eoe_vit_encode_u8_resize)"},

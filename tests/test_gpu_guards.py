@@ -60,7 +60,7 @@ def test_hsc_and_bce_write_only_their_outputs(n, d, dtype):
     for g, nm in ((loss, "loss"), (scores, "scores"), (grad, "grad"), (ws, "head_ws")):
         g.check("eoe_hsc_fwd_bwd " + nm)
     assert torch.isfinite(scores.t).all() and torch.isfinite(grad.t.float()).all()
-    assert bool((ws.t == 0).all())                                     # the reduction workspace is handed back zeroed
+    assert bool((ws.t[:4] == 0).all())                                 # the ticket is handed back re-armed (partials are scratch)
     x = torch.randn(n, 1, device=DEV).to(dtype)
     gx = Guarded((n, 1), dtype)
     L.check(lib.eoe_bce_fwd_bwd(L.ptr(x), L.DTYPE_CODE[dtype], L.ptr(y), n, 0, loss.ptr(), scores.ptr(), gx.ptr(), ws.ptr(),
