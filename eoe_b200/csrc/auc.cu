@@ -718,15 +718,18 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
     {
         const int S = items | 1;
         const int kbase = tid * S;
-        auto cidx = [](int w, int t) { const int lin = w * kSmallThreads + t; return lin + (lin >> 5); };   // padded
+        // counter of digit d for thread t: 16-bit element 2 * (w * 1056 + t + t / 32) + (d >> 3), w = d & 7  (word w * 1024
+        // + t of the (digit word, thread) order, one padding word per 32)
+        uint16_t* c16 = reinterpret_cast<uint16_t*>(sh.cnt);
+        const uint32_t tb2 = 2u * (uint32_t)(tid + (tid >> 5));
 #pragma unroll 1
         for (int pass = 0; pass < 8; ++pass) {
             const int shift = pass * 4;
             if (((varying >> shift) & 15u) == 0u) continue;             // the pass would be the identity
 #pragma unroll
-            for (int w = 0; w < 8; ++w) sh.cnt[cidx(w, tid)] = 0u;
+            for (int w = 0; w < 8; ++w) sh.cnt[w * 1056 + (tb2 >> 1)] = 0u;
             uint32_t key[MAXS];
-            uint32_t rl[MAXS];                                          // rank among the thread's equal digits | label << 8
+            uint32_t rl[MAXS];                 // rank among the thread's equal digits | label << 8 | counter index << 16
 #pragma unroll
             for (int j = 0; j < MAXS; ++j) {
                 const bool valid = j < S && kbase + j < n;
@@ -737,11 +740,10 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
             for (int j = 0; j < MAXS; ++j) {
                 if (j < S && kbase + j < n) {
                     const uint32_t d = (key[j] >> shift) & 15u;
-                    const int ci = cidx((int)(d & 7u), tid);
-                    const uint32_t hs = (d >> 3) * 16u;
-                    const uint32_t word = sh.cnt[ci];
-                    rl[j] |= (word >> hs) & 0xffu;
-                    sh.cnt[ci] = word + (1u << hs);
+                    const uint32_t ci = (d & 7u) * 2112u + (d >> 3) + tb2;
+                    const uint32_t old = c16[ci];
+                    c16[ci] = (uint16_t)(old + 1u);
+                    rl[j] |= old | (ci << 16);
                 }
             }
             __syncthreads();                                            // every key is in registers, every count is final
@@ -764,11 +766,9 @@ auc_small_kernel(const T* __restrict__ scores, const int64_t* __restrict__ label
 #pragma unroll
             for (int j = 0; j < MAXS; ++j) {
                 if (j < S && kbase + j < n) {
-                    const uint32_t d = (key[j] >> shift) & 15u;
-                    const uint32_t word = sh.cnt[cidx((int)(d & 7u), tid)];
-                    const uint32_t pos = ((word >> ((d >> 3) * 16u)) & 0xffffu) + (rl[j] & 0xffu);
+                    const uint32_t pos = (uint32_t)c16[rl[j] >> 16] + (rl[j] & 0xffu);
                     sh.keys[pos] = key[j];
-                    sh.labs[pos] = (uint8_t)(rl[j] >> 8);
+                    sh.labs[pos] = (uint8_t)((rl[j] >> 8) & 1u);
                 }
             }
             __syncthreads();
