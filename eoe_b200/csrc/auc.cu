@@ -1011,6 +1011,7 @@ extern "C" int eoe_auc(const void* scores, int score_dtype, const int64_t* label
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
     const bool small = n <= kSmallMax && !(flags & EOE_AUC_FORCE_TILED);
+    NvtxRange nvtx(small ? "eoe:auc (single launch)" : "eoe:auc (tiled pipeline)");
 #define EOE_AUC_DISPATCH(T)                                                                                              \
     return small ? auc_run_small<T>(scores, labels, n, flags, ws, L, auc_out, info_out, fpr_out, tpr_out, thr_out,       \
                                     prec_out, rec_out, prc_thr_out, st)                                                  \

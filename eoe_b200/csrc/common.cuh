@@ -1,5 +1,6 @@
 // Shared device/host helpers for the eoe_b200 kernels (sm_100a only).
 #pragma once
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost a branch unless a profiler is attached
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -140,6 +141,15 @@ __device__ __forceinline__ float warp_max(float v) {
 // Deterministic mean over the grid: every block deposits one partial, the last block to arrive
 // (threadfence + ticket) adds the partials in index order in fp64 and writes sum/n.  The ticket is
 // reset so the (zero-initialised) workspace can be reused by the next call.
+// RAII NVTX range around a host-side launch sequence (visible as named spans in Nsight Systems / Compute timelines:
+// "eoe:vit_encode" > "eoe:block 3", "eoe:auc", ...).  SURVEY section 5 ("tracing").
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 struct HeadWorkspace {
     unsigned int ticket;
     unsigned int pad[31];

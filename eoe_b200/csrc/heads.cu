@@ -1169,6 +1169,7 @@ extern "C" int eoe_hsc_fwd_bwd(const void* z, int z_dtype, const int64_t* labels
                                int64_t nominal_label, float* loss_out, float* scores_out, void* grad_z_out,
                                void* head_ws, void* stream) {
     if (!z || !labels || !loss_out || !head_ws || n <= 0 || d <= 0) return EOE_ERR_ARG;
+    NvtxRange nvtx("eoe:hsc fwd+bwd+score");
     cudaStream_t st = (cudaStream_t)stream;
     EOE_DISPATCH_DTYPE(z_dtype, (hsc_launch<T>(z, labels, n, d, nominal_label, loss_out, scores_out, grad_z_out, head_ws, st)))
 }
@@ -1182,6 +1183,7 @@ extern "C" int eoe_hsc_score(const void* z, int z_dtype, int64_t n, int64_t d, f
 extern "C" int eoe_bce_fwd_bwd(const void* x, int x_dtype, const int64_t* labels, int64_t n, int64_t nominal_label,
                                float* loss_out, float* scores_out, void* grad_x_out, void* head_ws, void* stream) {
     if (!x || !labels || !loss_out || !head_ws || n <= 0) return EOE_ERR_ARG;
+    NvtxRange nvtx("eoe:bce fwd+bwd+score");
     cudaStream_t st = (cudaStream_t)stream;
     EOE_DISPATCH_DTYPE(x_dtype, (bce_launch<T>(x, labels, n, nominal_label, loss_out, scores_out, grad_x_out, head_ws, st)))
 }
@@ -1232,6 +1234,7 @@ extern "C" int eoe_clip_score(const void* z, int z_dtype, const float* text, int
     int rc = clip_check(z, text, n, d, K);
     if (rc) return rc;
     if (!scores_out) return EOE_ERR_ARG;
+    NvtxRange nvtx("eoe:clip score");
     cudaStream_t st = (cudaStream_t)stream;
     EOE_DISPATCH_DTYPE(z_dtype, (clip_score_launch<T>(z, text, n, d, K, scale, scores_out, st)))
 }
@@ -1244,6 +1247,7 @@ extern "C" int eoe_clip_oe_loss_fwd_bwd(const void* z, int z_dtype, const float*
     if (rc) return rc;
     if (!labels || !loss_out || !head_ws) return EOE_ERR_ARG;
     if (grad_z_out && (uintptr_t)grad_z_out % 16 != 0) return EOE_ERR_ALIGN;
+    NvtxRange nvtx("eoe:clip oe loss fwd+bwd");
     cudaStream_t st = (cudaStream_t)stream;
     EOE_DISPATCH_DTYPE(z_dtype, (clip_loss_launch<T>(z, text, labels, n, d, K, scale, nominal_label, leave_one_out, loss_out, grad_z_out, head_ws, st)))
 }

@@ -1303,6 +1303,7 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
     const int64_t M = B * L, Mp = B * p->g2;
     int rc;
     if (text && !clip_prompts_ok(K)) return EOE_ERR_SHAPE;      // before any work: not after the whole forward pass
+    NvtxRange nvtx_all("eoe:vit_encode");
     // 1. patchify
     if (imgs_f32) {
         const int64_t total = B * 3 * (int64_t)w.resolution * w.resolution / 8;
@@ -1357,6 +1358,9 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
     float2* st_cur = p->stats;           // chunk sums of the residual stream as it is now (written by ln_pre)
     float2* st_nxt = p->stats2;
     for (int i = 0; i < w.n_layers; ++i) {
+        char nvtx_name[32];
+        snprintf(nvtx_name, sizeof(nvtx_name), "eoe:block %d", i);
+        NvtxRange nvtx_block(nvtx_name);
         const eoe_vit_layer& l = p->layers[i];
         const bool last = (i == w.n_layers - 1);
         if (!p->fused_ln) {
@@ -1405,6 +1409,7 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
         }
     }
     // 5. ln_post + proj (+ zero-shot score head)
+    NvtxRange nvtx_tail("eoe:tail + score head");
     float* feats = feats_out ? feats_out : p->feats;
     {
         const dim3 grid((unsigned)((B + kTailImgs - 1) / kTailImgs), (unsigned)((w.embed_dim + kTailCols - 1) / kTailCols));
