@@ -363,14 +363,23 @@ def run_ours(args):
     e2e_diag = {}
 
     def time_e2e(hbufs, dbufs, tag=None):
+        sampler = None
+        if tag == "u8" and rank == 0:          # SM clock / power during the headline e2e region (it runs seconds after `value`)
+            sampler = ClockSampler(local)
+            sampler.start()
         e2e_job(min(W, S), hbufs, dbufs)
-        sync()
+        sync()                                 # (barrier: every rank enters the timed region together)
+        if sampler is not None:
+            sampler.begin()
         t0 = time.perf_counter()
         e0.record()
         e2e_job(S, hbufs, dbufs)
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
+        if sampler is not None:
+            sampler.end()
+            e2e_diag["u8_clocks"] = sampler.stop()
         tt = torch.tensor([wall, e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
         if ws > 1:
             tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
@@ -491,7 +500,7 @@ def run_ours(args):
                 "note": "public API (ClipImageEncoder.score + metrics.roc_auc_device) from pinned HOST batches of decoded uint8 "
                         "NHWC pixels (ToTensor + Normalize fused into the patchify kernel, eoe_vit_encode_u8), double-buffered "
                         "H2D on a copy stream, every step's scores and the final AUC read back to the host",
-                "numa_cpus": numa_cpus, "timing": e2e_diag.get("u8")},
+                "numa_cpus": numa_cpus, "timing": e2e_diag.get("u8"), "clocks": e2e_diag.get("u8_clocks")},
         "e2e_f32": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": B * 4 + 8,
                     "note": "same job from pinned fp32 NCHW host batches (the reference DataLoader's output format): 4x the PCIe bytes",
                     "timing": e2e_diag.get("f32")},
