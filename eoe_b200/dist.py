@@ -110,6 +110,10 @@ class GradBuckets:
         self.group = group
         self.enabled = True          # False: gradients stay local (no collective is launched; A/B timing of the overlap)
         self.rank, self.ws = world()
+        # NCCL averages inside the collective (ReduceOp.AVG): no extra pass over the buckets after the wait; gloo (CPU
+        # tests) only sums, so the division stays a separate step there
+        self._avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self._op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         self.params = [p for p in params if p.requires_grad]
         self.buckets: List[torch.Tensor] = []
         self._bucket_of = {}
@@ -146,18 +150,19 @@ class GradBuckets:
         bi = self._bucket_of[p]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
-            self._works.append(dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._works.append(dist.all_reduce(self.buckets[bi], op=self._op, group=self.group, async_op=True))
 
     def finish(self):
         """Call after loss.backward(): wait for the in-flight all-reduces, average, re-arm."""
         if self.ws > 1 and self.enabled:
             for bi, left in enumerate(self._pending):          # parameters that received no gradient this step
                 if left != 0:
-                    self._works.append(dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                    self._works.append(dist.all_reduce(self.buckets[bi], op=self._op, group=self.group, async_op=True))
             for w in self._works:
                 w.wait()
-            for b in self.buckets:
-                b.div_(self.ws)
+            if not self._avg:
+                for b in self.buckets:
+                    b.div_(self.ws)
         self._works = []
         self._pending = list(self._counts)
 
