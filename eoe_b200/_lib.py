@@ -18,7 +18,9 @@ EOE_HEAD_WS_BYTES = 32768
 EOE_AUC_IGNORE_NEGATIVE_LABELS = 1
 EOE_AUC_WITH_PRC = 2
 EOE_AUC_FORCE_TILED = 4
-EOE_AUC_SINGLE_LAUNCH_MAX = 16384
+EOE_AUC_FORCE_SINGLE_CTA = 8
+EOE_AUC_FORCE_CLUSTER = 16
+EOE_AUC_SINGLE_LAUNCH_MAX = 49152
 EOE_AUC_STATUS_NONFINITE = 1
 EOE_AUC_STATUS_SINGLE_CLASS = 2
 EOE_EPI_BIAS, EOE_EPI_BIAS_QUICKGELU, EOE_EPI_BIAS_RESIDUAL_F32, EOE_EPI_PATCH_EMBED = 0, 1, 2, 3

@@ -11,7 +11,11 @@
 //   6 leaves    numpy pairwise-sum leaves (<=128 terms: 8 strided accumulators)              [np.trapezoid -> sum]
 //   7 tree      numpy pairwise-sum internal nodes (split at n/2 rounded down to a multiple of 8)
 // The float64 summation ORDER is what makes the result bit-identical to sklearn; see oracle/auc.py.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace eoe {
 
@@ -941,6 +945,401 @@ static int auc_run_small(const void* scores, const int64_t* labels, int64_t n, i
 #undef EOE_AUC_SMALL
 }
 
+// ------------------------------------------------------------------------------------------ cluster path
+// The one-CTA kernel above is bound by ONE SM's shared-memory port (7 radix passes x 7 accesses per key).  Here a thread
+// block CLUSTER of 8 CTAs (8 SMs, one launch) shares the work: CTA c owns slots [c P, (c + 1) P) of the global order in
+// its shared memory, ranks its keys exactly as the one-CTA kernel does, and the passes are stitched together through
+// distributed shared memory -- per pass every CTA publishes its 16 digit totals, reads the other seven's, and scatters
+// its keys straight into the owning CTA's shared memory (st.shared::cluster).  Two cluster barriers per pass (~380
+// clocks each).  The scans, terms and pairwise leaves are split the same way through the global workspace; CTA 0 finishes
+// the tree.  Same arithmetic, same order: bit-identical to both other paths.  Up to 8 x 16 384 scores.
+constexpr int kClusterCtas = 8;
+constexpr int kClusterMax = kClusterCtas * kSmallMax;
+// measured cross-overs (tools/microbench_latency.py, profiles/r2_latency_reference_sizes.jsonl; device time per call):
+// one CTA wins up to ~12 k scores (20 us at 3 000, 42 us at 10 000 -- the cluster's DSMEM scatter and its ~20 cluster
+// barriers cost what its 8 SMs save), the cluster between 12 k and 48 k (50 vs 61 us at 16 384; 73 us at 32 768 against
+// 78 us device / 115 us per call for the 11 launches of the tiled pipeline), the tiled pipeline above
+constexpr int kSingleCtaBelow = 12288;
+constexpr int kClusterUseMax = 49152;
+
+struct ClusterShared {
+    uint32_t keys[kSmallMax + 8];
+    uint32_t cnt[8 * kSmallThreads + 8 * kSmallThreads / 32];
+    uint8_t labs[kSmallMax];
+    uint32_t scan_tmp[32];
+    uint32_t dtot[16];                 // this CTA's digit totals of the running pass (read by the other CTAs)
+    int32_t adj[16];                   // global position = local exclusive prefix + rank + adj[digit]
+    uint32_t pub[4];                   // per-phase totals published to the other CTAs
+    uint32_t and_all, or_all, n_valid, n_pos, status;      // CTA 0's copies accumulate the whole cluster's
+    uint32_t g_varying, g_nv, g_npos, g_status;            // every CTA's copy of the cluster-wide values
+};
+
+template <typename T, int MAXS>
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kSmallThreads, 1)
+auc_cluster_kernel(const T* __restrict__ scores, const int64_t* __restrict__ labels, int n, int flags,
+                   uint32_t* d_tps, uint32_t* d_fps, uint32_t* d_key, uint32_t* k_tps, uint32_t* k_fps, double* terms,
+                   double* nodes, double* nodes2, double* __restrict__ auc_out, int64_t* __restrict__ info_out,
+                   double* __restrict__ fpr_out, double* __restrict__ tpr_out, float* __restrict__ thr_out,
+                   double* __restrict__ prec_out, double* __restrict__ rec_out, float* __restrict__ pthr_out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    ClusterShared& sh = *reinterpret_cast<ClusterShared*>(smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = (n + kClusterCtas - 1) / kClusterCtas;           // slots per CTA
+    const unsigned long long invP = (((unsigned long long)1 << 32) + (unsigned)P - 1) / (unsigned)P;    // pos / P = (pos * invP) >> 32
+    const int lo_g = c * P;
+    const int nloc = max(0, min(n - lo_g, P));
+    const int items = (P + kSmallThreads - 1) / kSmallThreads;     // uniform over the cluster
+    const int S = items | 1;
+    const int kbase = tid * S;
+    ClusterShared* sh0 = cluster.map_shared_rank(&sh, 0);
+    if (tid == 0) { sh.and_all = 0xffffffffu; sh.or_all = 0u; sh.n_valid = 0; sh.n_pos = 0; sh.status = 0; }
+    cluster.sync();
+    const long long clk0 = clock64();
+
+    // ---- 1 keys
+    {
+        const bool ignore_neg = flags & EOE_AUC_IGNORE_NEGATIVE_LABELS;
+        const int wbase = warp * items * 32;
+        uint32_t nv = 0, np = 0, bad = 0, a_and = 0xffffffffu, a_or = 0u;
+        constexpr int NI = MAXS < kSmallItems ? MAXS : kSmallItems;
+        float f[NI];
+        int64_t l[NI];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const int idx = wbase + j * 32 + lane;
+            const bool in = j < items && idx < nloc;
+            f[j] = in ? to_f32<T>(scores[lo_g + idx]) : 0.f;
+            l[j] = in ? labels[lo_g + idx] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const int idx = wbase + j * 32 + lane;
+            if (j < items && idx < nloc) {
+                uint32_t key = 0xffffffffu;
+                uint8_t lb = 0;
+                if (!(ignore_neg && l[j] < 0)) {
+                    if (!isfinite(f[j])) bad = 1;
+                    key = desc_key(f[j]);
+                    lb = (l[j] == 1);
+                    nv++;
+                    np += lb;
+                }
+                sh.keys[idx] = key;
+                sh.labs[idx] = lb;
+                a_and &= key;
+                a_or |= key;
+            }
+        }
+        nv = __reduce_add_sync(kFullMask, nv);
+        np = __reduce_add_sync(kFullMask, np);
+        bad = __reduce_or_sync(kFullMask, bad);
+        a_and = __reduce_and_sync(kFullMask, a_and);
+        a_or = __reduce_or_sync(kFullMask, a_or);
+        if (lane == 0) {                                   // straight into CTA 0's accumulators
+            atomicAdd(&sh0->n_valid, nv);
+            atomicAdd(&sh0->n_pos, np);
+            if (bad) atomicOr(&sh0->status, (uint32_t)EOE_AUC_STATUS_NONFINITE);
+            atomicAnd(&sh0->and_all, a_and);
+            atomicOr(&sh0->or_all, a_or);
+        }
+    }
+    cluster.sync();
+    if (tid == 0) {
+        sh.g_varying = sh0->and_all ^ sh0->or_all;
+        sh.g_nv = sh0->n_valid; sh.g_npos = sh0->n_pos; sh.g_status = sh0->status;
+    }
+    __syncthreads();
+    const uint32_t varying = sh.g_varying;
+    const int nv = (int)sh.g_nv, npos = (int)sh.g_npos;
+
+    // ---- 2 sort (see auc_small_kernel; the digit totals of the 8 CTAs are combined through distributed shared memory)
+    {
+        uint16_t* c16 = reinterpret_cast<uint16_t*>(sh.cnt);
+        const uint32_t tb2 = 2u * (uint32_t)(tid + (tid >> 5));
+#pragma unroll 1
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = pass * 4;
+            if (((varying >> shift) & 15u) == 0u) continue;             // cluster-uniform
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sh.cnt[w * 1056 + (tb2 >> 1)] = 0u;
+            uint32_t key[MAXS];
+            uint32_t rl[MAXS];
+#pragma unroll
+            for (int j = 0; j < MAXS; ++j) {
+                const bool valid = j < S && kbase + j < nloc;
+                key[j] = valid ? sh.keys[kbase + j] : 0xffffffffu;
+                rl[j] = valid ? ((uint32_t)sh.labs[kbase + j] << 8) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < MAXS; ++j) {
+                if (j < S && kbase + j < nloc) {
+                    const uint32_t d = (key[j] >> shift) & 15u;
+                    const uint32_t ci = (d & 7u) * 2112u + (d >> 3) + tb2;
+                    const uint32_t old = c16[ci];
+                    c16[ci] = (uint16_t)(old + 1u);
+                    rl[j] |= old | (ci << 16);
+                }
+            }
+            __syncthreads();
+            uint32_t c8[8], tot = 0, block_tot;
+            {
+                const int lin0 = tid * 8, p0 = lin0 + (lin0 >> 5);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { c8[i] = sh.cnt[p0 + i]; tot += c8[i]; }
+                uint32_t run = block_excl_scan_1024(tot, sh.scan_tmp, &block_tot);
+                const uint32_t low_total = block_tot & 0xffffu;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    sh.cnt[p0 + i] = run + (low_total << 16);
+                    run += c8[i];
+                }
+                block_tot += low_total << 16;              // "row 8" of the high halves, with the same offset
+            }
+            __syncthreads();
+            // digit d's total and first local position in this CTA, from the prefixes of thread 0 in rows w and w + 1
+            uint32_t lstart = 0;
+            if (tid < 16) {
+                const int w = tid & 7, hs = (tid >> 3) * 16;
+                const uint32_t e0 = (sh.cnt[w * 1056] >> hs) & 0xffffu;
+                const uint32_t e1 = ((w == 7 ? block_tot : sh.cnt[(w + 1) * 1056]) >> hs) & 0xffffu;
+                sh.dtot[tid] = e1 - e0;
+                lstart = e0;
+            }
+            cluster.sync();                                // every CTA's keys are in registers, every dtot is published
+            if (tid < 32) {
+                uint32_t before = 0, rowsum = 0;           // keys with my digit in CTAs < c / in all CTAs
+                if (tid < 16) {
+#pragma unroll
+                    for (int cc = 0; cc < kClusterCtas; ++cc) {
+                        const uint32_t v = cluster.map_shared_rank(&sh, cc)->dtot[tid];
+                        rowsum += v;
+                        if (cc < c) before += v;
+                    }
+                }
+                uint32_t inc = rowsum;                     // exclusive prefix over digits: keys with a smaller digit
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFullMask, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (tid < 16) sh.adj[tid] = (int32_t)(inc - rowsum + before) - (int32_t)lstart;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < MAXS; ++j) {
+                if (j < S && kbase + j < nloc) {
+                    const uint32_t d = (key[j] >> shift) & 15u;
+                    const uint32_t pos = (uint32_t)((int32_t)((uint32_t)c16[rl[j] >> 16] + (rl[j] & 0xffu)) + sh.adj[d]);
+                    const uint32_t dest = (uint32_t)(((unsigned long long)pos * invP) >> 32);     // exact for pos * P < 2^32
+                    const uint32_t slot = pos - dest * (uint32_t)P;
+                    ClusterShared* r = cluster.map_shared_rank(&sh, dest);
+                    r->keys[slot] = key[j];
+                    r->labs[slot] = (uint8_t)((rl[j] >> 8) & 1u);
+                }
+            }
+            cluster.sync();                                // every slice holds the keys of this pass's order
+        }
+    }
+    const long long clk1 = clock64();
+
+    // ---- 3 distinct thresholds -> global d_tps / d_fps / d_key
+    const int nvl = max(0, min(nv - lo_g, nloc));                  // kept rows of this slice
+    int m = 0;
+    {
+        uint32_t fmask = 0, lmask = 0;
+        const uint32_t next_first = (c + 1 < kClusterCtas) ? cluster.map_shared_rank(&sh, c + 1)->keys[0] : 0u;
+#pragma unroll
+        for (int j = 0; j < MAXS; ++j) {
+            const int i = kbase + j;
+            if (j < S && i < nvl) {
+                const int gi = lo_g + i;
+                const uint32_t nxt = (i + 1 < P) ? sh.keys[i + 1] : next_first;
+                if (gi == nv - 1 || sh.keys[i] != nxt) fmask |= 1u << j;
+                if (sh.labs[i]) lmask |= 1u << j;
+            }
+        }
+        uint32_t tf, tl;
+        uint32_t slot = block_excl_scan_1024((uint32_t)__popc(fmask), sh.scan_tmp, &tf);
+        uint32_t tps = block_excl_scan_1024((uint32_t)__popc(lmask), sh.scan_tmp, &tl);
+        if (tid == 0) { sh.pub[0] = tf; sh.pub[1] = tl; }
+        cluster.sync();
+        for (int cc = 0; cc < kClusterCtas; ++cc) {
+            const ClusterShared* r = cluster.map_shared_rank(&sh, cc);
+            const uint32_t vf = r->pub[0], vl = r->pub[1];
+            m += (int)vf;
+            if (cc < c) { slot += vf; tps += vl; }
+        }
+        const bool want_keys = thr_out || pthr_out;
+#pragma unroll
+        for (int j = 0; j < MAXS; ++j) {
+            tps += (lmask >> j) & 1u;
+            if ((fmask >> j) & 1u) {
+                const int gi = lo_g + kbase + j;
+                d_tps[slot] = tps;
+                d_fps[slot] = 1u + (uint32_t)gi - tps;
+                if (want_keys) d_key[slot] = sh.keys[kbase + j];
+                ++slot;
+            }
+        }
+    }
+    cluster.sync();
+    // ---- 4 corners -> global k_tps / k_fps (+ thresholds); CTA c takes points [c Q, (c + 1) Q)
+    int kept = 0;
+    {
+        const int Q = (m + kClusterCtas - 1) / kClusterCtas;
+        const int q_lo = min(m, c * Q), q_hi = min(m, q_lo + Q);
+        const int per = ((Q + kSmallThreads - 1) / kSmallThreads) | 1;      // <= S
+        const int lo = min(q_hi, q_lo + tid * per);
+        uint32_t kmask = 0;
+        uint32_t pt[MAXS], pf[MAXS];
+        if (lo < q_hi) {
+            int f0 = lo > 0 ? (int)__ldcg(d_fps + lo - 1) : 0, t0 = lo > 0 ? (int)__ldcg(d_tps + lo - 1) : 0;
+            int f1 = (int)__ldcg(d_fps + lo), t1 = (int)__ldcg(d_tps + lo);
+#pragma unroll
+            for (int j = 0; j < MAXS; ++j) {
+                const int i = lo + j;
+                if (j < per && i < q_hi) {
+                    const bool has_next = i + 1 < m;
+                    const int f2 = has_next ? (int)__ldcg(d_fps + i + 1) : 0, t2 = has_next ? (int)__ldcg(d_tps + i + 1) : 0;
+                    const bool kp = (m <= 2 || i == 0 || i == m - 1) || (f0 - 2 * f1 + f2 != 0) || (t0 - 2 * t1 + t2 != 0);
+                    if (kp) kmask |= 1u << j;
+                    pt[j] = (uint32_t)t1; pf[j] = (uint32_t)f1;
+                    f0 = f1; t0 = t1; f1 = f2; t1 = t2;
+                }
+            }
+        }
+        uint32_t tk;
+        uint32_t slot = block_excl_scan_1024((uint32_t)__popc(kmask), sh.scan_tmp, &tk) + 1;     // +1: the prepended origin
+        if (tid == 0) sh.pub[2] = tk;
+        cluster.sync();
+        for (int cc = 0; cc < kClusterCtas; ++cc) {
+            const uint32_t v = cluster.map_shared_rank(&sh, cc)->pub[2];
+            kept += (int)v;
+            if (cc < c) slot += v;
+        }
+        if (c == 0 && tid == 0) {
+            k_tps[0] = 0; k_fps[0] = 0;
+            if (thr_out) thr_out[0] = INFINITY;
+        }
+#pragma unroll
+        for (int j = 0; j < MAXS; ++j) {
+            if ((kmask >> j) & 1u) {
+                k_tps[slot] = pt[j];
+                k_fps[slot] = pf[j];
+                if (thr_out) thr_out[slot] = key_to_score(__ldcg(d_key + lo + j));
+                ++slot;
+            }
+        }
+    }
+    cluster.sync();
+    const long long clk2 = clock64();
+    // ---- 5 terms: warp chunks of 31 terms, dealt round-robin over the cluster's 256 warps
+    {
+        const int Ppts = kept + 1;
+        const double ftot = (double)(nv - npos), ttot = (double)npos;
+        for (int base = (c * 32 + warp) * 31; base < Ppts; base += kClusterCtas * 32 * 31) {
+            const int i = base + lane;
+            double f0 = 0.0, t0 = 0.0;
+            if (i < Ppts) {
+                f0 = __ddiv_rn((double)__ldcg(k_fps + i), ftot);
+                t0 = __ddiv_rn((double)__ldcg(k_tps + i), ttot);
+                if (fpr_out && lane < 31) { fpr_out[i] = f0; tpr_out[i] = t0; }
+            }
+            const double f1 = __shfl_down_sync(kFullMask, f0, 1), t1 = __shfl_down_sync(kFullMask, t0, 1);
+            if (lane < 31 && i + 1 < Ppts)
+                terms[i] = __dmul_rn(__dmul_rn(__dsub_rn(f1, f0), __dadd_rn(t1, t0)), 0.5);
+        }
+    }
+    cluster.sync();
+    // ---- 6 leaves of numpy's pairwise tree over the cluster, 7 the tree itself by CTA 0
+    const bool single = (npos == 0) || (npos == nv);
+    const uint32_t status = sh.g_status | (single ? (uint32_t)EOE_AUC_STATUS_SINGLE_CLASS : 0u);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const bool undefined = single || (status & ~(uint32_t)EOE_AUC_STATUS_SINGLE_CLASS);
+    auto leaves = [&](const double* a, int64_t Tn, double* nd) {
+        if (Tn <= 0) return;
+        const int D = dev_pairwise_depth(Tn);
+        for (int64_t g0 = (int64_t)c * (kSmallThreads / 8); g0 < ((int64_t)1 << D); g0 += (int64_t)kClusterCtas * (kSmallThreads / 8))
+            pairwise_leaf_slot(a, Tn, D, g0 + (tid >> 3), tid & 7, 0xffu << (tid & 24), nd);
+    };
+    auto tree = [&](int64_t Tn, double* nd) {              // CTA 0 only (block-uniform call)
+        if (Tn <= 0) return 0.0;
+        pairwise_tree_levels<kSmallThreads>(Tn, dev_pairwise_depth(Tn), nd);
+        return __ldcg(nd + 1);
+    };
+    leaves(terms, kept, nodes);
+    cluster.sync();
+    if (c == 0) {
+        const double v = tree(kept, nodes);
+        if (tid == 0) auc_out[0] = undefined ? qnan : v;
+    }
+    if (flags & EOE_AUC_WITH_PRC) {
+        const double ttot = (double)npos;
+        auto prec = [&](int j) {
+            const double tp = (double)__ldcg(d_tps + j), ps = __dadd_rn(tp, (double)__ldcg(d_fps + j));
+            return ps != 0.0 ? __ddiv_rn(tp, ps) : 0.0;
+        };
+        auto rec = [&](int j) { return ttot == 0.0 ? 1.0 : __ddiv_rn((double)__ldcg(d_tps + j), ttot); };
+        for (int i = c * kSmallThreads + tid; i < m; i += kClusterCtas * kSmallThreads) {
+            const int j = m - 1 - i;
+            const double p = prec(j), r = rec(j);
+            const double r_next = (i + 1 < m) ? rec(j - 1) : 0.0;
+            terms[i] = __dmul_rn(__dsub_rn(r_next, r), p);
+            if (prec_out) { prec_out[i] = p; rec_out[i] = r; }
+            if (pthr_out) pthr_out[i] = key_to_score(__ldcg(d_key + j));
+        }
+        if (prec_out && c == 0 && tid == 0) { prec_out[m] = 1.0; rec_out[m] = 0.0; }
+        cluster.sync();
+        leaves(terms, m, nodes2);
+        cluster.sync();
+        if (c == 0) {
+            const double v = tree(m, nodes2);
+            if (tid == 0) auc_out[1] = undefined ? qnan : fmax(0.0, -v);
+        }
+    }
+    if (info_out && c == 0 && tid == 0) {
+        info_out[0] = nv; info_out[1] = npos; info_out[2] = m; info_out[3] = kept + 1; info_out[4] = (int64_t)status;
+        info_out[5] = clk1 - clk0; info_out[6] = clk2 - clk1; info_out[7] = clock64() - clk2;
+    }
+    cluster.sync();                                        // no CTA exits while a peer may still read its shared memory
+}
+
+template <typename T, int MAXS>
+static int auc_launch_cluster(const void* scores, const int64_t* labels, int64_t n, int flags, char* ws, const AucLayout& L,
+                              double* auc_out, int64_t* info_out, double* fpr_out, double* tpr_out, float* thr_out,
+                              double* prec_out, double* rec_out, float* pthr_out, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = auc_cluster_kernel<T, MAXS>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ClusterShared));
+        if (e != cudaSuccess) { set_cuda_error(e, "auc cluster attribute"); return EOE_ERR_CUDA; }
+        attr_set = true;
+    }
+    // PRC tree nodes live in the k_tps / k_fps region (dead once the ROC terms exist): (n + 2) * 8 bytes >= (2 << depth) * 8
+    kern<<<kClusterCtas, kSmallThreads, sizeof(ClusterShared), st>>>(
+        (const T*)scores, labels, (int)n, flags, (uint32_t*)(ws + L.d_tps), (uint32_t*)(ws + L.d_fps), (uint32_t*)(ws + L.keys_b),
+        (uint32_t*)(ws + L.k_tps), (uint32_t*)(ws + L.k_fps), (double*)(ws + L.terms), (double*)(ws + L.nodes),
+        (double*)(ws + L.k_tps), auc_out, info_out, fpr_out, tpr_out, thr_out, prec_out, rec_out, pthr_out);
+    return check_launch("auc (one cluster launch)", 1);
+}
+
+template <typename T>
+static int auc_run_cluster(const void* scores, const int64_t* labels, int64_t n, int flags, char* ws, const AucLayout& L,
+                           double* auc_out, int64_t* info_out, double* fpr_out, double* tpr_out, float* thr_out,
+                           double* prec_out, double* rec_out, float* pthr_out, cudaStream_t st) {
+    const int P = (int)((n + kClusterCtas - 1) / kClusterCtas);
+    const int S = ((P + kSmallThreads - 1) / kSmallThreads) | 1;
+#define EOE_AUC_CLUSTER(M) return auc_launch_cluster<T, M>(scores, labels, n, flags, ws, L, auc_out, info_out, fpr_out, tpr_out, \
+                                                          thr_out, prec_out, rec_out, pthr_out, st)
+    if (S <= 3) EOE_AUC_CLUSTER(3);
+    if (S <= 5) EOE_AUC_CLUSTER(5);
+    if (S <= 9) EOE_AUC_CLUSTER(9);
+    EOE_AUC_CLUSTER(17);
+#undef EOE_AUC_CLUSTER
+}
+
 template <typename T>
 static int auc_run(const void* scores, const int64_t* labels, int64_t n, int flags, char* ws, const AucLayout& L,
                    double* auc_out, int64_t* info_out, double* fpr_out, double* tpr_out, float* thr_out,
@@ -1010,13 +1409,19 @@ extern "C" int eoe_auc(const void* scores, int score_dtype, const int64_t* label
     if ((uintptr_t)workspace % 256 != 0) return EOE_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
-    const bool small = n <= kSmallMax && !(flags & EOE_AUC_FORCE_TILED);
-    NvtxRange nvtx(small ? "eoe:auc (single launch)" : "eoe:auc (tiled pipeline)");
+    // one launch up to 49 152 scores: one CTA for the reference's sizes (<= 12 288), a cluster of 8 CTAs above that; the
+    // tiled pipeline beyond (the cluster kernel itself handles up to 131 072: EOE_AUC_FORCE_CLUSTER, used by the tests)
+    const bool force_cluster = (flags & EOE_AUC_FORCE_CLUSTER) && n <= kClusterMax;
+    const bool tiled = !force_cluster && (n > kClusterUseMax || (flags & EOE_AUC_FORCE_TILED));
+    const bool one_cta = !tiled && !force_cluster && n <= kSmallMax && ((flags & EOE_AUC_FORCE_SINGLE_CTA) || n <= kSingleCtaBelow);
+    NvtxRange nvtx(tiled ? "eoe:auc (tiled pipeline)" : (one_cta ? "eoe:auc (one CTA)" : "eoe:auc (one cluster)"));
 #define EOE_AUC_DISPATCH(T)                                                                                              \
-    return small ? auc_run_small<T>(scores, labels, n, flags, ws, L, auc_out, info_out, fpr_out, tpr_out, thr_out,       \
-                                    prec_out, rec_out, prc_thr_out, st)                                                  \
-                 : auc_run<T>(scores, labels, n, flags, ws, L, auc_out, info_out, fpr_out, tpr_out, thr_out, prec_out,   \
-                              rec_out, prc_thr_out, st)
+    return tiled ? auc_run<T>(scores, labels, n, flags, ws, L, auc_out, info_out, fpr_out, tpr_out, thr_out, prec_out,    \
+                              rec_out, prc_thr_out, st)                                                                   \
+                 : (one_cta ? auc_run_small<T>(scores, labels, n, flags, ws, L, auc_out, info_out, fpr_out, tpr_out,      \
+                                               thr_out, prec_out, rec_out, prc_thr_out, st)                               \
+                            : auc_run_cluster<T>(scores, labels, n, flags, ws, L, auc_out, info_out, fpr_out, tpr_out,    \
+                                                 thr_out, prec_out, rec_out, prc_thr_out, st))
     switch (score_dtype) {
         case EOE_F32: EOE_AUC_DISPATCH(float);
         case EOE_F16: EOE_AUC_DISPATCH(__half);

@@ -66,13 +66,14 @@ _default_ws = AucWorkspace()
 
 def roc_auc_device(scores: torch.Tensor, labels: torch.Tensor, *, ignore_negative_labels: bool = False,
                    with_prc: bool = False, curves: bool = False, workspace: Optional[AucWorkspace] = None,
-                   force_tiled: bool = False):
+                   force_tiled: bool = False, force_single_cta: bool = False, force_cluster: bool = False):
     """Launch the AUC pipeline asynchronously on the current stream.
 
     Returns (out, info, arrays): `out` float64[2] device = (auc, average precision), `info` int64[8] device
     (n kept, n pos, n distinct, n ROC points, status bits), `arrays` dict of device curve buffers or None.
-    No host synchronisation happens here.  Up to EOE_AUC_SINGLE_LAUNCH_MAX scores this is ONE kernel launch
-    (`force_tiled` selects the multi-kernel radix-sort pipeline anyway: tests compare the two bit for bit)."""
+    No host synchronisation happens here.  Up to EOE_AUC_SINGLE_LAUNCH_MAX scores this is ONE kernel launch (one CTA up
+    to 12 288 scores, a cluster of 8 CTAs above; `force_single_cta` / `force_cluster` / `force_tiled` select a path
+    explicitly: tests compare the three bit for bit)."""
     L.require_cuda(scores, labels)
     scores = scores.detach().reshape(-1).contiguous()
     if scores.dtype not in L.DTYPE_CODE:
@@ -98,7 +99,8 @@ def roc_auc_device(scores: torch.Tensor, labels: torch.Tensor, *, ignore_negativ
             pthr = torch.empty(n, dtype=torch.float32, device=scores.device)
             arrays.update(prec=prec, rec=rec, pthr=pthr)
     flags = ((L.EOE_AUC_IGNORE_NEGATIVE_LABELS if ignore_negative_labels else 0) | (L.EOE_AUC_WITH_PRC if with_prc else 0)
-             | (L.EOE_AUC_FORCE_TILED if force_tiled else 0))
+             | (L.EOE_AUC_FORCE_TILED if force_tiled else 0) | (L.EOE_AUC_FORCE_SINGLE_CTA if force_single_cta else 0)
+             | (L.EOE_AUC_FORCE_CLUSTER if force_cluster else 0))
     L.check(L.lib().eoe_auc(L.ptr(scores), L.dtype_code(scores), L.ptr(labels), n, flags, L.ptr(w.ws),
                             w.ws.numel(), L.ptr(w.out), L.ptr(w.info), L.ptr(fpr), L.ptr(tpr), L.ptr(thr),
                             L.ptr(prec), L.ptr(rec), L.ptr(pthr), L.stream_ptr(scores.device)), "eoe_auc")
@@ -120,11 +122,12 @@ def roc_auc(scores, labels, **kw) -> float:
     return float(host[:2].view(torch.float64)[0])
 
 
-def roc_curve_auc(scores, labels, with_prc: bool = False, ignore_negative_labels: bool = False, force_tiled: bool = False
-                  ) -> Tuple[Optional[ROC], Optional[PRC]]:
+def roc_curve_auc(scores, labels, with_prc: bool = False, ignore_negative_labels: bool = False, force_tiled: bool = False,
+                  force_single_cta: bool = False, force_cluster: bool = False) -> Tuple[Optional[ROC], Optional[PRC]]:
     """What eval_cls keeps (ad_trainer.py:516-527): (ROC, PRC) or (None, None) if a class is missing."""
     out, info, arr = roc_auc_device(scores, labels, with_prc=with_prc, curves=True,
-                                    ignore_negative_labels=ignore_negative_labels, force_tiled=force_tiled)
+                                    ignore_negative_labels=ignore_negative_labels, force_tiled=force_tiled,
+                                    force_single_cta=force_single_cta, force_cluster=force_cluster)
     info_h = info.cpu()
     _raise_on_status(int(info_h[4]))
     if int(info_h[4]) & L.EOE_AUC_STATUS_SINGLE_CLASS:

@@ -136,11 +136,14 @@ int eoe_clip_oe_loss_fwd_bwd(const void* z, int z_dtype, const float* text, cons
 enum {
     EOE_AUC_IGNORE_NEGATIVE_LABELS = 1,   /* drop rows with label < 0 (ad_trainer.py:517 filter)   */
     EOE_AUC_WITH_PRC = 2,                 /* also compute average precision (+ PRC arrays if given) */
-    EOE_AUC_FORCE_TILED = 4               /* n <= EOE_AUC_SINGLE_LAUNCH_MAX: use the multi-kernel pipeline anyway (tests) */
+    EOE_AUC_FORCE_TILED = 4,              /* n <= EOE_AUC_SINGLE_LAUNCH_MAX: use the multi-kernel pipeline anyway (tests) */
+    EOE_AUC_FORCE_SINGLE_CTA = 8,         /* n <= 16 384: the one-CTA kernel (tests, A/B timing)                          */
+    EOE_AUC_FORCE_CLUSTER = 16            /* n <= 131 072: the 8-CTA cluster kernel (tests, A/B timing)                   */
 };
-#define EOE_AUC_SINGLE_LAUNCH_MAX 16384   /* up to here eoe_auc is ONE kernel launch of one CTA (the reference's sizes:
-                                             3 000 - 10 000 scores per class and epoch, ad_trainer.py:452-455,516-522);
-                                             larger inputs run the tiled radix-sort pipeline (15 launches) */
+#define EOE_AUC_SINGLE_LAUNCH_MAX 49152   /* up to here eoe_auc is ONE kernel launch: one CTA up to 12 288 scores (the
+                                             reference's sizes: 3 000 - 10 000 per class and epoch, ad_trainer.py:452-455,
+                                             516-522), a thread-block cluster of 8 CTAs sorting through distributed shared
+                                             memory above that; larger inputs run the tiled radix-sort pipeline (11+ launches) */
 enum {                                    /* bits of info_out[4]                                    */
     EOE_AUC_STATUS_NONFINITE = 1,         /* a kept score is NaN/Inf (sklearn raises ValueError)     */
     EOE_AUC_STATUS_SINGLE_CLASS = 2       /* only one class present: AUC undefined (NaN)             */

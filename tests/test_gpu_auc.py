@@ -102,13 +102,15 @@ def test_auc_ignore_negative_labels_and_errors():
     assert roc is None and prc is None                   # ad_trainer.py:516,523-527: single class -> None
 
 
-@pytest.mark.parametrize("n", [2, 5, 100, 1023, 1024, 1025, 3000, 10000, 16383, 16384])
+@pytest.mark.parametrize("n", [2, 5, 9, 100, 1023, 1024, 1025, 3000, 8191, 10000, 16383, 16384, 16385, 24577, 65536, 100003,
+                               131071, 131072])
 @pytest.mark.parametrize("kind", ["f32", "f16", "coarse", "signed", "unlabeled"])
 def test_auc_single_launch_equals_tiled_pipeline(n, kind):
-    """n <= EOE_AUC_SINGLE_LAUNCH_MAX runs as ONE kernel launch (the sizes the reference evaluates, ad_trainer.py:452-455,
-    516-522); the multi-kernel radix-sort pipeline (EOE_AUC_FORCE_TILED) must give the same bits for every output."""
+    """n <= EOE_AUC_SINGLE_LAUNCH_MAX runs as ONE kernel launch: one CTA up to 12 288 scores (the sizes the reference
+    evaluates, ad_trainer.py:452-455,516-522), a cluster of 8 CTAs sorting through distributed shared memory above.  All
+    three paths (one CTA, cluster -- forced up to its 131 072 limit --, tiled multi-kernel pipeline) must give the same
+    bits for every output."""
     from eoe_b200 import _lib, metrics
-    assert n <= _lib.EOE_AUC_SINGLE_LAUNCH_MAX
     rng = np.random.default_rng(n * 17 + len(kind))
     s = (1 - np.exp(-np.abs(rng.standard_normal(n)))).astype(np.float32)
     y = (rng.random(n) < 0.35).astype(np.int64)
@@ -124,17 +126,27 @@ def test_auc_single_launch_equals_tiled_pipeline(n, kind):
     st, yt = torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV)
     ign = kind == "unlabeled"
     launches0 = _lib.lib().eoe_launch_count()
-    a = metrics.roc_curve_auc(st, yt, with_prc=True, ignore_negative_labels=ign)
-    assert _lib.lib().eoe_launch_count() - launches0 == 1
-    b = metrics.roc_curve_auc(st, yt, with_prc=True, ignore_negative_labels=ign, force_tiled=True)
+    a = metrics.roc_curve_auc(st, yt, with_prc=True, ignore_negative_labels=ign)            # the default path for this n
+    if n <= _lib.EOE_AUC_SINGLE_LAUNCH_MAX:
+        assert _lib.lib().eoe_launch_count() - launches0 == 1
+    launches0 = _lib.lib().eoe_launch_count()
+    arms = [metrics.roc_curve_auc(st, yt, with_prc=True, ignore_negative_labels=ign, force_tiled=True)]
     assert _lib.lib().eoe_launch_count() - launches0 > 10
-    for x, w in zip(a, b):
-        for f in ("auc", "avg_prec"):
-            if hasattr(x, f):
-                assert getattr(x, f) == getattr(w, f)
-        for f in ("tpr", "fpr", "prec", "rec", "ths"):
-            if hasattr(x, f):
-                assert np.array_equal(getattr(x, f), getattr(w, f)), f
+    launches0 = _lib.lib().eoe_launch_count()
+    arms.append(metrics.roc_curve_auc(st, yt, with_prc=True, ignore_negative_labels=ign, force_cluster=True))
+    assert _lib.lib().eoe_launch_count() - launches0 == 1
+    if n <= 16384:
+        launches0 = _lib.lib().eoe_launch_count()
+        arms.append(metrics.roc_curve_auc(st, yt, with_prc=True, ignore_negative_labels=ign, force_single_cta=True))
+        assert _lib.lib().eoe_launch_count() - launches0 == 1
+    for b in arms:
+        for x, w in zip(a, b):
+            for f in ("auc", "avg_prec"):
+                if hasattr(x, f):
+                    assert getattr(x, f) == getattr(w, f)
+            for f in ("tpr", "fpr", "prec", "rec", "ths"):
+                if hasattr(x, f):
+                    assert np.array_equal(getattr(x, f), getattr(w, f)), f
     keep = y >= 0
     assert a[0].auc == oauc.roc_auc(y[keep], s[keep])
 

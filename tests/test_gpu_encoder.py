@@ -301,6 +301,28 @@ def test_end_to_end_scores(golden_dir, patch, K, dtype, record_property):
     np.testing.assert_allclose(s, oh.clip_score(feats, text), rtol=1e-3, atol=1e-30)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 3e-4), (torch.bfloat16, 2.4e-3)])
+def test_encoder_with_massive_activation_channels(dtype, tol):
+    """Pretrained CLIP towers carry a few residual channels two orders of magnitude above the rest ("massive activations");
+    random-init weights do not.  Here ln_pre's bias plants four such channels (+60, -45, +80, -30) into every token row,
+    so the folded LayerNorms, the centred 16-bit copy of the residual stream and the fp16 operands all see them: features
+    stay as close to the fp32 oracle as without outliers, and the fold equals the stand-alone LayerNorm kernels."""
+    from eoe_b200.encoder import ClipImageEncoder
+    sd = ovit.synth_state_dict(32, seed=9, layers=3)
+    b = sd["visual.ln_pre.bias"].clone()
+    b[[5, 100, 400, 700]] = torch.tensor([60.0, -45.0, 80.0, -30.0])
+    sd["visual.ln_pre.bias"] = b
+    imgs = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(2))
+    want = ovit.encode_image(sd, imgs)
+    got = {}
+    for fold in (True, False):
+        enc = ClipImageEncoder(sd, device=DEV, operand_dtype=dtype, max_batch=4, fold_layernorm=fold)
+        got[fold] = enc(imgs.to(DEV)).cpu()
+        assert torch.isfinite(got[fold]).all()
+        assert _rel(got[fold], want) < tol, (fold, _rel(got[fold], want))
+    assert _rel(got[True], got[False]) < tol
+
+
 def test_encoder_batching_and_fused_score(tower):
     """max_batch chunking is invisible; the fused score equals clip_score(features); B not a multiple of anything."""
     from eoe_b200 import ops

@@ -94,7 +94,7 @@ def main():
     lib = _lib.lib()
     # ---- AUC at the reference's sizes
     from sklearn.metrics import auc, roc_curve
-    for n in (3000, 10000, 16384, 32768, 65536):
+    for n in (1000, 3000, 10000, 16384, 32768, 65536, 131072):
         rng = np.random.default_rng(n)
         s_np = (1 - np.exp(-np.abs(rng.standard_normal(n)))).astype(np.float32)
         y_np = (rng.random(n) < 0.5).astype(np.int64)
@@ -111,7 +111,12 @@ def main():
             info = metrics.roc_auc_device(s, y, workspace=ws)[1].cpu()
             row["phase_clocks_keys_sort__scans__terms_sum"] = [int(v) for v in info[5:8]]
             med_t, best_t = gpu_us(lambda: metrics.roc_auc_device(s, y, workspace=ws, force_tiled=True))
-            row.update(tiled_us=med_t, tiled_best_us=best_t)
+            row.update(tiled_us=med_t, tiled_best_us=best_t,
+                       tiled_device_us_graph_replay=graph_us(lambda: metrics.roc_auc_device(s, y, workspace=ws, force_tiled=True)))
+        if n <= 131072:
+            row["cluster_device_us_graph_replay"] = graph_us(lambda: metrics.roc_auc_device(s, y, workspace=ws, force_cluster=True))
+        if n <= 16384:
+            row["one_cta_device_us_graph_replay"] = graph_us(lambda: metrics.roc_auc_device(s, y, workspace=ws, force_single_cta=True))
         med_prc, _ = gpu_us(lambda: metrics.roc_auc_device(s, y, workspace=ws, with_prc=True))
         row["with_ap_us"] = med_prc
         med_h, best_h = host_us(lambda: auc(*roc_curve(y_np, s_np)[:2]))
