@@ -106,7 +106,7 @@ class GradBuckets:
     post-accumulate-grad hook as soon as its last gradient has been written, so communication overlaps the rest of
     backward.  `finish()` waits and scales by 1/world.  Use `zero_grad()` of this object (keeps the views)."""
 
-    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None):
+    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None, tail_bytes: int = 4 << 20):
         self.group = group
         self.enabled = True          # False: gradients stay local (no collective is launched; A/B timing of the overlap)
         self.rank, self.ws = world()
@@ -131,6 +131,15 @@ class GradBuckets:
             cur_bytes += nb
         if cur:
             groups.append(cur)
+        # The LAST bucket holds the first layers' gradients and can only be launched when backward ends: nothing is left
+        # to overlap it with, so it is kept small (its all-reduce is then latency, not bandwidth: tools/dp_bench.py).
+        if groups and len(groups[-1]) > 1 and tail_bytes > 0:
+            last, tail, nb = groups[-1], [], 0
+            while len(last) > 1 and nb + last[-1].numel() * last[-1].element_size() <= tail_bytes:
+                nb += last[-1].numel() * last[-1].element_size()
+                tail.insert(0, last.pop())
+            if tail:
+                groups.append(tail)
         for bi, ps in enumerate(groups):
             flat = torch.zeros(sum(p.numel() for p in ps), dtype=ps[0].dtype, device=ps[0].device)
             off = 0
