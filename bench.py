@@ -297,6 +297,29 @@ def run_ours(args):
         clocks.start()
     job(W, scores, labels)
     sync()
+    # Settle: the power-capped clock keeps falling for about a second after load starts (1.6 -> 1.3 GHz), so a timed region
+    # that begins right after three warm-up steps runs partly on burst clocks while everything measured after it (the
+    # instrumented pass, the e2e passes) does not.  An untimed second of the same job first puts `value`, the roofline
+    # pass and `e2e` into the same sustained state -- the state MEASURED_PEAKS.json's sustained figure describes.
+    def settle(run):
+        """`run(n)` repeated for about args.settle_s seconds; the repeat count is agreed over the ranks (the job contains
+        collectives, so every rank must run it the same number of times)."""
+        if args.settle_s <= 0:
+            return
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        run(min(S, 10))
+        b_.record()
+        sync()
+        tt_ = torch.tensor([a_.elapsed_time(b_)], dtype=torch.float64, device=dev)
+        if ws > 1:
+            tdist.all_reduce(tt_, op=tdist.ReduceOp.MAX)
+        reps = int(args.settle_s * 1e3 / max(float(tt_.item()), 1e-3))
+        for _ in range(min(reps, 200)):
+            run(min(S, 10))
+        sync()
+
+    settle(lambda n_: job(n_, scores, labels))
 
     # ---- timed region (device-resident inputs).  Pass 1 is clean and gives `value`; pass 2 repeats the identical K
     # steps with every GEMM launch bracketed by a CUDA event pair (98 events per step) and gives the roofline.
@@ -368,6 +391,8 @@ def run_ours(args):
             sampler = ClockSampler(local)
             sampler.start()
         e2e_job(min(W, S), hbufs, dbufs)
+        settle(lambda n_: e2e_job(n_, hbufs, dbufs))    # same settle as before `value`: the host buffers above were built
+                                                        # while the GPU idled, so the clocks are back at burst
         sync()                                 # (barrier: every rank enters the timed region together)
         if sampler is not None:
             sampler.begin()
@@ -417,6 +442,7 @@ def run_ours(args):
                 enc_o.score(imgs[k & 1], text, out=scores[k * B:(k + 1) * B])
         job_o(W)
         sync()
+        settle(job_o)
         e0.record()
         job_o(S)
         e1.record()
@@ -494,7 +520,8 @@ def run_ours(args):
                    "images_scored": ws * S * B, "weights": "random-init ViT-B/%d visual tower (reference state_dict layout)" % P,
                    "l2": "inputs exceed L2 (2 alternating %.0f MB image batches per GPU)" % (B * 3 * 224 * 224 * 4 / 1e6),
                    "parallelism": f"dp{ws}: images sharded by rank, all_gather(scores, labels) -> global device AUC",
-                   "timed_region": "K x (patchify + ViT encoder + fused score head) + all-gather + ROC-AUC"},
+                   "timed_region": "K x (patchify + ViT encoder + fused score head) + all-gather + ROC-AUC",
+                   "settle": f"{args.settle_s} s of the same job, untimed, after the W warm-up steps (sustained power-capped clocks)"},
         "roofline": roofline,
         "e2e": {"value": e2e_u8_val, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224, "d2h_bytes_per_step": B * 4 + 8,
                 "note": "public API (ClipImageEncoder.score + metrics.roc_auc_device) from pinned HOST batches of decoded uint8 "
@@ -544,6 +571,8 @@ def main():
     ap.add_argument("--ref-images", type=int, default=64, help="images per step of the CPU port (bounded sample)")
     ap.add_argument("--cpu-baseline-images", type=int, default=384,
                     help="bounded sample of the cpu_baseline leg inside our arm (about 10 s of CPU work on 16 cores)")
+    ap.add_argument("--settle-s", type=float, default=1.0,
+                    help="untimed seconds of the same job between the warm-up steps and the timed region (power-capped steady state)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side", action="store_true")
     ap.add_argument("--no-fold", action="store_true", help="stand-alone ln_1 / ln_2 kernels instead of the LayerNorm fold (A/B)")
