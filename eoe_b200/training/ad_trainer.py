@@ -176,10 +176,10 @@ class ADTrainer(ABC):
         return model.eval(), cls_roc, losses
 
     def _capture_step(self, model, opt, center, imgs, lbls, nominal_label):
-        """Capture `zero_grad -> model -> loss (fused kernel) -> backward -> optimiser step -> scores` once, on static input
-        buffers.  Three eager steps on a side stream first (PyTorch's whole-network capture recipe: lazy initialisations
-        and the optimiser state must exist before capture); they are REAL steps on this batch's data only if the caller
-        accepts that -- so they run on a deep copy of model + optimiser state and are discarded."""
+        """Capture `model -> loss (fused kernel) -> backward -> optimiser step -> scores` once, on static input buffers.
+        Three eager steps run on a side stream first (PyTorch's whole-network capture recipe: lazy initialisations and the
+        optimiser's state tensors must exist before capture).  They must not count as training: weights, BatchNorm
+        statistics and optimiser state are snapshotted before and restored in place afterwards."""
         import copy
         s_imgs, s_lbls = imgs.clone(), lbls.clone()
         saved_model = copy.deepcopy(model.state_dict())
