@@ -280,9 +280,11 @@ def run_ours(args):
     scores = torch.empty(SW * B, dtype=torch.float32, device=dev)
     auc_ws = metrics.AucWorkspace().ensure(SW * B * ws, dev)
 
-    def job(n_steps, sc, lb):
+    def job(n_steps, sc, lb, mid=None):
         for k in range(n_steps):
             enc.score(imgs[k & 1], text, out=sc[k * B:(k + 1) * B])
+        if mid is not None:
+            mid.record()                       # this rank's own scoring is done; what follows waits for the slowest rank
         sc, lb = sc[:n_steps * B], lb[:n_steps * B]
         s_all, l_all = (edist.all_gather_rows(sc, total=ws * n_steps * B), edist.all_gather_rows(lb, total=ws * n_steps * B)) if ws > 1 else (sc, lb)
         return metrics.roc_auc_device(s_all, l_all, workspace=auc_ws)
@@ -327,8 +329,9 @@ def run_ours(args):
     sync()
     clocks.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_mid = torch.cuda.Event(enable_timing=True)
     e0.record()
-    auc_out, auc_info, _ = job(S, scores, labels)
+    auc_out, auc_info, _ = job(S, scores, labels, mid=e_mid)
     e1.record()
     sync()
     clocks.end()
@@ -346,7 +349,13 @@ def run_ours(args):
     prof = enc.profile_read()
     enc.profile(False)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank_ms = [e0.elapsed_time(e_mid) / S]
     if ws > 1:
+        # every rank's own device time for its K scoring steps (before the all-gather, which waits for the slowest rank):
+        # `value` is bounded by the MAX of these -- the list shows how far the power-capped GPUs of one box are apart
+        allt = torch.zeros(ws, dtype=torch.float64, device=dev)
+        tdist.all_gather_into_tensor(allt, torch.tensor([e0.elapsed_time(e_mid)], dtype=torch.float64, device=dev))
+        per_rank_ms = [float(v) / S for v in allt.cpu().tolist()]
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = ws * S * B / (ms_max / 1e3)
@@ -514,8 +523,8 @@ def run_ours(args):
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": S, "warmup": W,
-        "ms_per_step": ms_max / S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic",
+        "ms_per_step": ms_max / S, "per_rank_scoring_ms_per_step": per_rank_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": f"clip_vitb{P}_zero_shot_ad_224px_{K}prompts", "batch_per_gpu": B, "global_batch": B * ws,
                    "images_scored": ws * S * B, "weights": "random-init ViT-B/%d visual tower (reference state_dict layout)" % P,
                    "l2": "inputs exceed L2 (2 alternating %.0f MB image batches per GPU)" % (B * 3 * 224 * 224 * 4 / 1e6),
