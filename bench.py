@@ -336,6 +336,7 @@ def run_ours(args):
     sync()
     clocks.end()
     ms = e0.elapsed_time(e1)
+    ms_mid = e0.elapsed_time(e_mid)            # this rank's K scoring steps alone (e0 is re-recorded below)
     clk = clocks.stop() if rank == 0 else None
     launches = _lib.lib().eoe_launch_count() - launches0
     auc_val = float(auc_out[0].item())
@@ -349,12 +350,12 @@ def run_ours(args):
     prof = enc.profile_read()
     enc.profile(False)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    per_rank_ms = [e0.elapsed_time(e_mid) / S]
+    per_rank_ms = [ms_mid / S]
     if ws > 1:
         # every rank's own device time for its K scoring steps (before the all-gather, which waits for the slowest rank):
         # `value` is bounded by the MAX of these -- the list shows how far the power-capped GPUs of one box are apart
         allt = torch.zeros(ws, dtype=torch.float64, device=dev)
-        tdist.all_gather_into_tensor(allt, torch.tensor([e0.elapsed_time(e_mid)], dtype=torch.float64, device=dev))
+        tdist.all_gather_into_tensor(allt, torch.tensor([ms_mid], dtype=torch.float64, device=dev))
         per_rank_ms = [float(v) / S for v in allt.cpu().tolist()]
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
     ms_max = float(t.item())
