@@ -102,8 +102,8 @@ def test_auc_ignore_negative_labels_and_errors():
     assert roc is None and prc is None                   # ad_trainer.py:516,523-527: single class -> None
 
 
-@pytest.mark.parametrize("n", [2, 5, 9, 100, 1023, 1024, 1025, 3000, 8191, 10000, 16383, 16384, 16385, 24577, 65536, 100003,
-                               131071, 131072])
+@pytest.mark.parametrize("n", [2, 5, 9, 100, 1023, 1024, 1025, 3000, 8191, 10000, 12288, 12289, 16383, 16384, 16385, 24577,
+                               49152, 49153, 65536, 100003, 131071, 131072])
 @pytest.mark.parametrize("kind", ["f32", "f16", "coarse", "signed", "unlabeled"])
 def test_auc_single_launch_equals_tiled_pipeline(n, kind):
     """n <= EOE_AUC_SINGLE_LAUNCH_MAX runs as ONE kernel launch: one CTA up to 12 288 scores (the sizes the reference
