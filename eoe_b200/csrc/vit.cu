@@ -55,6 +55,24 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t K, 
     return EOE_OK;
 }
 
+// the same for a [rows, cols] window of a wider row-major matrix (row stride `ld` elements): K and V columns of qkv
+static int make_tmap_ld(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int dtype) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return EOE_ERR_CUDA;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, dtype == EOE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(ld)");
+        return EOE_ERR_CUDA;
+    }
+    return EOE_OK;
+}
+
 // out [B, L, width] 16-bit as a 3-D map (width, token, image): a box of `box_rows` tokens x 64 columns that runs past the
 // image's last token is clipped by the TMA unit (stores) / zero-filled (loads)
 static int make_tmap_tokens(CUtensorMap* m, const void* base, int64_t B, int64_t L, int64_t width, int box_rows, int dtype) {
@@ -892,10 +910,27 @@ static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, 
 // output, out-proj, ln_2 and the MLP are evaluated for the class-token rows alone (the reference computes and discards
 // the other 196 rows).  K and V still come from all tokens.  One warp per (image, head): lanes own keys l, l+32, ...;
 // also gathers the class-token rows of the fp32 residual stream into the compact buffer x_cls [B, width].
+// Last block, LayerNorm-folded path: the class-token rows' 16-bit residual copy, chunk sums and shifts, compacted to
+// [B, ...] so that the folded QKV GEMM can produce Q for those B rows only (K and V are still needed for every token).
+__global__ void __launch_bounds__(256)
+gather_cls_rows_kernel(const uint16_t* __restrict__ xb, const float2* __restrict__ stats, const float* __restrict__ shift,
+                       uint16_t* __restrict__ xb_cls, float2* __restrict__ stats_cls, float* __restrict__ shift_cls,
+                       int64_t B, int L, int width) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int64_t row = b * L;
+    const int nvec = width / 8, nch = width / 128;
+    for (int i = lane; i < nvec; i += 32)
+        reinterpret_cast<uint4*>(xb_cls + b * width)[i] = __ldg(reinterpret_cast<const uint4*>(xb + row * width) + i);
+    if (lane < nch) stats_cls[b * nch + lane] = stats[row * nch + lane];
+    if (lane == 0) shift_cls[b] = shift[row];
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(128)
-attention_cls_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ x, uint16_t* __restrict__ h_cls,
-                     float* __restrict__ x_cls, int64_t B, int L, int heads) {
+attention_cls_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ q_cls, const float* __restrict__ x,
+                     uint16_t* __restrict__ h_cls, float* __restrict__ x_cls, int64_t B, int L, int heads) {
     __shared__ float s_red[4][32][33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t item = (int64_t)blockIdx.x * 4 + wib;
@@ -914,7 +949,8 @@ attention_cls_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__
     float q[64];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + h * 64) + i);
+        // the class token's query: from its own [B, width] buffer when the last block computed Q for those rows only
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(q_cls ? q_cls + b * width + h * 64 : base + h * 64) + i);
         cvt2(v.x, q[i * 8], q[i * 8 + 1]); cvt2(v.y, q[i * 8 + 2], q[i * 8 + 3]);
         cvt2(v.z, q[i * 8 + 4], q[i * 8 + 5]); cvt2(v.w, q[i * 8 + 6], q[i * 8 + 7]);
     }
@@ -1109,9 +1145,15 @@ struct eoe_vit_plan {
                          // a residual GEMM reads the previous producer's sums (row means) while it writes its own
     float2* stats2;
     float* shift;        // [B*L] what was subtracted from the row of xb (the row's mean before the last update)
+    uint16_t* xb_cls;    // [B, width]   last block: class-token rows of xb / stats / shift, and their queries
+    float2* stats_cls;   // [B, width/128]
+    float* shift_cls;    // [B]
+    uint16_t* q_cls;     // [B, width]
     bool fused_ln;       // every layer carries folded in_proj / c_fc weights: no stand-alone ln_1 / ln_2 launches
     CUtensorMap tm_patches, tm_h, tm_u, tm_conv, tm_qkv, tm_hc, tm_uc, tm_xb, tm_ho128, tm_ho72;
     CUtensorMap tm_qkv_st, tm_u_st, tm_uc_st;          // 32-row store boxes over the 16-bit GEMM outputs
+    CUtensorMap tm_kv_w, tm_kv_st, tm_xbc, tm_qc_st;   // last block: K;V rows of the folded in_proj weights, K;V columns of
+                                                       // qkv (stores), class-token rows of xb (A), their queries (stores)
     CUtensorMap *tm_in, *tm_out, *tm_fc, *tm_proj;     // per layer
     CUtensorMap *tm_inf, *tm_fcf;                      // per layer, LayerNorm-folded weights
     CUtensorMap* tm_projs;                             // per layer, c_proj weights / 1.702 (optional)
@@ -1171,7 +1213,8 @@ static int vit_check(const eoe_vit_weights* w) {
 }
 static bool vit_fused_ln(const eoe_vit_weights* w) { return w->layers_host[0].in_proj_wf != nullptr; }
 
-struct VitLayout { size_t patches, x, h, qkv, u, feats, x_cls, h_cls, u_cls, xb, stats, stats2, shift, total; };
+struct VitLayout { size_t patches, x, h, qkv, u, feats, x_cls, h_cls, u_cls, xb, stats, stats2, shift, xb_cls, stats_cls,
+                   shift_cls, q_cls, total; };
 static VitLayout vit_layout(const eoe_vit_weights* w, int64_t B) {
     const int g = w->resolution / w->patch;
     const int64_t g2 = g * g, L = g2 + 1, W = w->width;
@@ -1193,6 +1236,13 @@ static VitLayout vit_layout(const eoe_vit_weights* w, int64_t B) {
         l.stats = o; o += rup((size_t)(B * L) * (W / 128) * sizeof(float2));
         l.stats2 = o; o += rup((size_t)(B * L) * (W / 128) * sizeof(float2));
         l.shift = o; o += rup((size_t)(B * L + 256) * sizeof(float));
+    }
+    l.xb_cls = o; l.stats_cls = o; l.shift_cls = o; l.q_cls = o;
+    if (vit_fused_ln(w)) {
+        l.xb_cls = o; o += rup((size_t)(B + 256) * W * 2);
+        l.stats_cls = o; o += rup((size_t)(B + 256) * (W / 128) * sizeof(float2));
+        l.shift_cls = o; o += rup((size_t)(B + 256) * sizeof(float));
+        l.q_cls = o; o += rup((size_t)(B + 256) * W * 2);
     }
     l.total = o;
     return l;
@@ -1240,6 +1290,10 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     p->stats = (float2*)(p->ws + lay.stats);
     p->stats2 = (float2*)(p->ws + lay.stats2);
     p->shift = (float*)(p->ws + lay.shift);
+    p->xb_cls = (uint16_t*)(p->ws + lay.xb_cls);
+    p->stats_cls = (float2*)(p->ws + lay.stats_cls);
+    p->shift_cls = (float*)(p->ws + lay.shift_cls);
+    p->q_cls = (uint16_t*)(p->ws + lay.q_cls);
     const int W = w->width, dt = w->operand_dtype;
     const int64_t rows = max_batch * p->L;
     p->tm_in = new CUtensorMap[w->n_layers];
@@ -1274,6 +1328,13 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
         if (!rc && p->fused_ln && l.c_proj_w_div1702) rc = make_tmap(&p->tm_projs[i], l.c_proj_w_div1702, W, 4 * W, gemm::CTA_NB, dt);
     }
     if (!rc && p->fused_ln) rc = make_tmap(&p->tm_xb, p->xb, rows, W, gemm::CTA_M, dt);
+    if (!rc && p->fused_ln) {
+        const eoe_vit_layer& ll = p->layers[w->n_layers - 1];
+        rc = make_tmap(&p->tm_kv_w, (const uint16_t*)ll.in_proj_wf + (size_t)W * W, 2 * W, W, gemm::CTA_NB, dt);
+        if (!rc) rc = make_tmap_ld(&p->tm_kv_st, p->qkv + W, rows, 2 * W, 3 * W, 32, dt);
+        if (!rc) rc = make_tmap(&p->tm_xbc, p->xb_cls, max_batch, W, gemm::CTA_M, dt);
+        if (!rc) rc = make_tmap(&p->tm_qc_st, p->q_cls, max_batch, W, 32, dt);
+    }
     if (rc) { eoe_vit_plan_destroy(p); return rc; }
     *plan_out = p;
     return EOE_OK;
@@ -1367,6 +1428,19 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
             if ((rc = layernorm_dispatch(p->x, l.ln_1_w, l.ln_1_b, p->h, dt, M, W, nullptr, nullptr, L, st))) return rc;
             gemm::Params g1{M, 3 * W, W, l.in_proj_b, p->qkv, nullptr, 0, nullptr, nullptr, nullptr};
             if ((rc = timed_gemm(p, KIND_QKV, p->tm_h, p->tm_in[i], g1, dt, EOE_EPI_BIAS, st, &p->tm_qkv_st))) return rc;
+        } else if (last && !(g_gemm_debug & 8)) {
+            // Last block: downstream only the class-token rows matter (model.py:231), so K and V are needed for every
+            // token but Q for B rows only.  K;V: the same folded GEMM over weight rows [W, 3W) into columns [W, 3W) of
+            // qkv (N = 2W instead of 3W); Q: the same folded GEMM over the B compacted class-token rows.  Same operands,
+            // same accumulation order as the full GEMM: the features do not change by a bit (diagnostics bit 3 = off).
+            gemm::Params gkv{M, 2 * W, W, (const float*)l.in_proj_c2 + W, p->qkv + W, (const float*)l.in_proj_c1 + W, 0, st_cur,
+                             nullptr, nullptr, p->shift, nullptr};
+            if ((rc = timed_gemm(p, KIND_QKV, p->tm_xb, p->tm_kv_w, gkv, dt, EOE_EPI_LNFOLD_BIAS, st, &p->tm_kv_st))) return rc;
+            gather_cls_rows_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(p->xb, st_cur, p->shift, p->xb_cls, p->stats_cls,
+                                                                            p->shift_cls, B, L, W);
+            if ((rc = check_launch("gather_cls_rows_kernel"))) return rc;
+            gemm::Params gq{B, W, W, l.in_proj_c2, p->q_cls, l.in_proj_c1, 0, p->stats_cls, nullptr, nullptr, p->shift_cls, nullptr};
+            if ((rc = timed_gemm(p, KIND_QKV, p->tm_xbc, p->tm_inf[i], gq, dt, EOE_EPI_LNFOLD_BIAS, st, &p->tm_qc_st))) return rc;
         } else {
             // ln_1 folded into the QKV GEMM: A = 16-bit residual stream, epilogue rstd*(acc - mean*c1) + c2
             gemm::Params g1{M, 3 * W, W, l.in_proj_c2, p->qkv, l.in_proj_c1, 0, st_cur, nullptr, nullptr, p->shift, nullptr};
@@ -1394,8 +1468,9 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
         } else {
             // last block: only the class-token rows are needed downstream (model.py:231)
             const unsigned grid = (unsigned)((B * w.heads + 3) / 4);
-            if (dt == EOE_BF16) attention_cls_kernel<true><<<grid, 128, 0, st>>>(p->qkv, p->x, p->h_cls, p->x_cls, B, L, w.heads);
-            else attention_cls_kernel<false><<<grid, 128, 0, st>>>(p->qkv, p->x, p->h_cls, p->x_cls, B, L, w.heads);
+            const uint16_t* qc = (p->fused_ln && !(g_gemm_debug & 8)) ? p->q_cls : nullptr;
+            if (dt == EOE_BF16) attention_cls_kernel<true><<<grid, 128, 0, st>>>(p->qkv, qc, p->x, p->h_cls, p->x_cls, B, L, w.heads);
+            else attention_cls_kernel<false><<<grid, 128, 0, st>>>(p->qkv, qc, p->x, p->h_cls, p->x_cls, B, L, w.heads);
             if ((rc = check_launch("attention_cls_kernel"))) return rc;
             gemm::Params g2{B, W, W, l.out_proj_b, p->x_cls, nullptr, 0, nullptr, nullptr, nullptr};
             if ((rc = timed_gemm(p, KIND_OUT, p->tm_hc, p->tm_out[i], g2, dt, EOE_EPI_BIAS_RESIDUAL_F32, st))) return rc;

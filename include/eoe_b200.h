@@ -261,7 +261,8 @@ int eoe_vit_fold_layernorm(const float* w_f32, const float* ln_w, const float* l
                            float* c2_out, void* stream);
 
 /* Diagnostics for tools/gemm_probe.py (NOT part of the stable ABI; 0 in production): bit 0 GEMM epilogues only release
- * their accumulators, bit 1 no global stores, bit 4 clusters of two CTA pairs with W multicast, bits 8.. grid size in CTA pairs. */
+ * their accumulators, bit 1 no global stores, bit 3 the last block computes Q for every token again (A/B of the class-token-only
+ * Q GEMM), bit 4 clusters of two CTA pairs with W multicast, bits 8.. grid size in CTA pairs. */
 void eoe_debug_set(int flags);
 
 /* Building blocks of the encoder, exported so that each kernel is parity-tested through the ABI. */

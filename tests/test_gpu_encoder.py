@@ -342,6 +342,25 @@ def test_encoder_batching_and_fused_score(tower):
     np.testing.assert_allclose(s_fused.cpu().numpy(), want, rtol=1e-3, atol=1e-30)   # head: 1e-3 given identical features
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_last_block_class_token_query_is_bit_identical(tower, dtype):
+    """The last block computes K;V for every token but Q for the class-token rows only (model.py:231 keeps x[:, 0]):
+    same folded GEMM, same operands, same accumulation order -- features equal the all-token QKV GEMM (diagnostics
+    bit 3) bit for bit, for a batch that is not a multiple of the 256-row tile."""
+    from eoe_b200 import _lib
+    from eoe_b200.encoder import ClipImageEncoder
+    patch, sd = tower
+    imgs = torch.randn(37, 3, 224, 224, generator=torch.Generator().manual_seed(8)).to(DEV)
+    enc = ClipImageEncoder(sd, device=DEV, operand_dtype=dtype, max_batch=37)
+    try:
+        _lib.lib().eoe_debug_set(8)
+        f_all = enc(imgs).clone()
+    finally:
+        _lib.lib().eoe_debug_set(0)
+    f_cls = enc(imgs)
+    assert torch.isfinite(f_cls).all() and torch.equal(f_cls, f_all)
+
+
 def test_encoder_full_batch_properties():
     """BASELINE-size step (512 images, ViT-B/16, 100 864 token rows, 16 waves of GEMM tiles): size-independent properties
     instead of a CPU oracle pass -- images are independent, so a permuted batch gives permuted features BIT FOR BIT, a
