@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # still no fallback: the named file must exist and export the full ABI.
 LIB_PATH = os.environ.get("EOE_B200_LIB") or os.path.join(_HERE, "libeoe_b200.so")
 
-EOE_F32, EOE_F16, EOE_BF16 = 0, 1, 2
+EOE_F32, EOE_F16, EOE_BF16, EOE_F16X2 = 0, 1, 2, 3
+F16X2 = "f16x2"      # operand_dtype of the precise mode (split fp16 pairs, include/eoe_b200.h EOE_F16X2)
 EOE_HEAD_WS_BYTES = 32768
 EOE_AUC_IGNORE_NEGATIVE_LABELS = 1
 EOE_AUC_WITH_PRC = 2
@@ -27,7 +28,7 @@ EOE_EPI_BIAS, EOE_EPI_BIAS_QUICKGELU, EOE_EPI_BIAS_RESIDUAL_F32, EOE_EPI_PATCH_E
 EOE_EPI_LNFOLD_BIAS, EOE_EPI_LNFOLD_QUICKGELU, EOE_EPI_RESIDUAL_STATS = 4, 5, 6
 EOE_EPI_LNFOLD_QUICKGELU_X1702 = 8
 GELU_SLOPE = 1.702
-EOE_ABI_VERSION = 5
+EOE_ABI_VERSION = 6
 EOE_LAYOUT_NCHW, EOE_LAYOUT_NHWC = 0, 1
 LAYOUT_RESIZE = 2            # host-side tag only: raw [B,H,W,3] pixels of another size -> eoe_vit_encode_u8_resize
 

@@ -25,6 +25,15 @@ namespace attn {
 constexpr int THREADS = 128;
 constexpr uint32_t TILE_BYTES = 128 * 128;                    // 128 rows x 64 x 16 bit
 constexpr uint32_t SMEM_BYTES = 6 * TILE_BYTES + 64 + 1024;   // Q0, Q1, K (2 boxes), V (2 boxes), barriers, alignment
+// SPLIT (operand dtype EOE_F16X2): qkv rows are [q k v | q_lo k_lo v_lo] fp16 pairs and the output rows [hi | lo].  A second
+// set of six tiles holds the lo halves; S = Qhi Khi^T + Qlo Khi^T + Qhi Klo^T and O = P Vhi + P Vlo accumulate in the same
+// TMEM columns (P stays a single fp16: it is the one 16-bit tensor whose rounding does not matter).
+// One CTA per SM (193 KB of shared memory).
+constexpr uint32_t SMEM_BYTES_SPLIT = 12 * TILE_BYTES + 64 + 1024;
+// hi / lo fp16 halves of two values scaled by `s` -> one word each
+__device__ __forceinline__ void split_scaled(uint32_t a, uint32_t b, float s, uint32_t& hi, uint32_t& lo) {
+    gemm::split2(__uint_as_float(a) * s, __uint_as_float(b) * s, hi, lo);
+}
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t O_COL = 128;
 
@@ -209,8 +218,8 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
     return 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
 }
 
-template <bool BF16, int L>
-__global__ void __launch_bounds__(THREADS, 2)
+template <bool BF16, int L, bool SPLIT = false>
+__global__ void __launch_bounds__(THREADS, SPLIT ? 1 : 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out128,
                     const __grid_constant__ CUtensorMap tm_out72, int num_items, int heads) {
     constexpr int LP = (L + 15) / 16 * 16;          // keys padded to the UMMA N granularity (208)
@@ -224,7 +233,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     // One load barrier per buffer, so that every buffer of the NEXT item is refilled as soon as this item is done with it
     // (K after the last S product, Q0 once its staged output has left, V after the last P.V product, Q1 at the item
     // boundary): the first S product of an item never waits for HBM.  Only the MMA-issuing thread waits on them.
-    uint64_t* bar_q0 = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES);
+    constexpr uint32_t LO = 6 * TILE_BYTES;     // SPLIT: the lo half of every tile sits one 6-tile set further on
+    constexpr uint32_t NH = SPLIT ? 2 : 1;
+    uint64_t* bar_q0 = reinterpret_cast<uint64_t*>(smem + NH * 6 * TILE_BYTES);
     uint64_t* bar_q1 = bar_q0 + 1;
     uint64_t* bar_k = bar_q0 + 2;
     uint64_t* bar_v = bar_q0 + 3;
@@ -264,15 +275,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     // L..255 cost no traffic and meet P == 0 with finite values
     auto load_q = [&](int tile, int bb, int hh, int row0) {
         const uint32_t lb = ptx::smem_u32(tile ? bar_q1 : bar_q0);
-        ptx::mbar_arrive_expect_tx(lb, TILE_BYTES);
+        ptx::mbar_arrive_expect_tx(lb, NH * TILE_BYTES);
         ptx::tma_load_3d(ptx::smem_u32(sQ + tile * TILE_BYTES), &tm_qkv, lb, hh * 64, row0, bb);
+        if (SPLIT) ptx::tma_load_3d(ptx::smem_u32(sQ + LO + tile * TILE_BYTES), &tm_qkv, lb, 3 * width + hh * 64, row0, bb);
     };
     auto load_kv = [&](int which, int bb, int hh) {         // which: 0 = K, 1 = V
         const uint32_t lb = ptx::smem_u32(which ? bar_v : bar_k);
         uint8_t* dst = which ? sV : sK;
-        ptx::mbar_arrive_expect_tx(lb, 2 * TILE_BYTES);
+        ptx::mbar_arrive_expect_tx(lb, NH * 2 * TILE_BYTES);
         ptx::tma_load_3d(ptx::smem_u32(dst), &tm_qkv, lb, (1 + which) * width + hh * 64, 0, bb);
         ptx::tma_load_3d(ptx::smem_u32(dst + TILE_BYTES), &tm_qkv, lb, (1 + which) * width + hh * 64, 128, bb);
+        if (SPLIT) {
+            ptx::tma_load_3d(ptx::smem_u32(dst + LO), &tm_qkv, lb, (4 + which) * width + hh * 64, 0, bb);
+            ptx::tma_load_3d(ptx::smem_u32(dst + LO + TILE_BYTES), &tm_qkv, lb, (4 + which) * width + hh * 64, 128, bb);
+        }
     };
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
@@ -300,6 +316,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 const uint64_t b_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sK));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                if (SPLIT) {
+                    const uint64_t a_lo = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ + LO + tile * TILE_BYTES));
+                    const uint64_t b_lo = ptx::make_smem_desc_sw128(ptx::smem_u32(sK + LO));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(tmem, a_lo + 2 * k, b_desc + 2 * k, idesc_s, 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(tmem, a_desc + 2 * k, b_lo + 2 * k, idesc_s, 1u);
+                }
                 ptx::umma_commit(ptx::smem_u32(bar_mma));
             }
             // query row owned by this thread, and whether its warp has any row to compute
@@ -327,6 +351,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 #pragma unroll
                 for (int kk = 0; kk < KSTEPS; ++kk)    // 16 keys per step: 8 packed columns of P, 16 rows (2 KB) of V
                     ptx::umma_f16_ts(tmem + O_COL, tmem + kk * 8, v_desc + (uint64_t)(kk * 2048 >> 4), idesc_o, kk != 0 ? 1u : 0u);
+                if (SPLIT) {
+                    const uint64_t v_lo = ptx::make_smem_desc_sw128(ptx::smem_u32(sV + LO));
+#pragma unroll
+                    for (int kk = 0; kk < KSTEPS; ++kk)
+                        ptx::umma_f16_ts(tmem + O_COL, tmem + kk * 8, v_lo + (uint64_t)(kk * 2048 >> 4), idesc_o, 1u);
+                }
                 ptx::umma_commit(ptx::smem_u32(bar_mma));
             }
             ptx::mbar_wait(ptx::smem_u32(bar_mma), mma_phase);
@@ -344,32 +374,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 ptx::tmem_ld_wait();
                 const uint32_t srow = ptx::smem_u32(stg + tid * 128);
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    const uint32_t q0 = gemm::pack2<BF16>(__uint_as_float(o0[j]) * inv_sum, __uint_as_float(o0[j + 1]) * inv_sum);
-                    const uint32_t q1 = gemm::pack2<BF16>(__uint_as_float(o0[j + 2]) * inv_sum, __uint_as_float(o0[j + 3]) * inv_sum);
-                    const uint32_t q2 = gemm::pack2<BF16>(__uint_as_float(o0[j + 4]) * inv_sum, __uint_as_float(o0[j + 5]) * inv_sum);
-                    const uint32_t q3 = gemm::pack2<BF16>(__uint_as_float(o0[j + 6]) * inv_sum, __uint_as_float(o0[j + 7]) * inv_sum);
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((((j >> 3)) ^ (tid & 7)) << 4)), "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
-                }
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint32_t (&oo)[32] = hh ? o1 : o0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    const uint32_t q0 = gemm::pack2<BF16>(__uint_as_float(o1[j]) * inv_sum, __uint_as_float(o1[j + 1]) * inv_sum);
-                    const uint32_t q1 = gemm::pack2<BF16>(__uint_as_float(o1[j + 2]) * inv_sum, __uint_as_float(o1[j + 3]) * inv_sum);
-                    const uint32_t q2 = gemm::pack2<BF16>(__uint_as_float(o1[j + 4]) * inv_sum, __uint_as_float(o1[j + 5]) * inv_sum);
-                    const uint32_t q3 = gemm::pack2<BF16>(__uint_as_float(o1[j + 6]) * inv_sum, __uint_as_float(o1[j + 7]) * inv_sum);
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + (((4 + (j >> 3)) ^ (tid & 7)) << 4)), "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
+                    for (int j = 0; j < 32; j += 8) {
+                        const uint32_t off = ((hh * 4 + (j >> 3)) ^ (tid & 7)) << 4;
+                        if (SPLIT) {
+                            uint32_t qh[4], ql[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) split_scaled(oo[j + 2 * e], oo[j + 2 * e + 1], inv_sum, qh[e], ql[e]);
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + off), "r"(qh[0]), "r"(qh[1]), "r"(qh[2]), "r"(qh[3]) : "memory");
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + LO + off), "r"(ql[0]), "r"(ql[1]), "r"(ql[2]), "r"(ql[3]) : "memory");
+                        } else {
+                            const uint32_t q0 = gemm::pack2<BF16>(__uint_as_float(oo[j]) * inv_sum, __uint_as_float(oo[j + 1]) * inv_sum);
+                            const uint32_t q1 = gemm::pack2<BF16>(__uint_as_float(oo[j + 2]) * inv_sum, __uint_as_float(oo[j + 3]) * inv_sum);
+                            const uint32_t q2 = gemm::pack2<BF16>(__uint_as_float(oo[j + 4]) * inv_sum, __uint_as_float(oo[j + 5]) * inv_sum);
+                            const uint32_t q3 = gemm::pack2<BF16>(__uint_as_float(oo[j + 6]) * inv_sum, __uint_as_float(oo[j + 7]) * inv_sum);
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + off), "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
+                        }
+                    }
                 }
             }
             ptx::fence_proxy_async_smem();
             ptx::tc_fence_before();
             __syncthreads();                       // O has been read and staged: TMEM is free
             if (tid == 0) {
-                if (tile == 0) {
-                    ptx::tma_store_3d(&tm_out128, ptx::smem_u32(stg), h * 64, 0, b);
-                } else if (t1_start == 128) {      // rows [128, 200): rows >= L are clipped
-                    ptx::tma_store_3d(&tm_out72, ptx::smem_u32(stg), h * 64, 128, b);
-                } else {                           // tile rows [L-128, L): store from staging row 56 = token L-72 (8-row aligned),
-                    ptx::tma_store_3d(&tm_out72, ptx::smem_u32(stg + 56 * 128), h * 64, L - 72, b);   // tokens < 128 repeat tile 0's values
+#pragma unroll
+                for (uint32_t part = 0; part < NH; ++part) {     // SPLIT: the lo tile goes to columns [width, 2 width) of the output rows
+                    const uint32_t src = ptx::smem_u32(stg + part * LO);
+                    const int col = (int)part * width + h * 64;
+                    if (tile == 0) {
+                        ptx::tma_store_3d(&tm_out128, src, col, 0, b);
+                    } else if (t1_start == 128) {      // rows [128, 200): rows >= L are clipped
+                        ptx::tma_store_3d(&tm_out72, src, col, 128, b);
+                    } else {                           // tile rows [L-128, L): store from staging row 56 = token L-72 (8-row aligned),
+                        ptx::tma_store_3d(&tm_out72, src + 56 * 128, col, L - 72, b);   // tokens < 128 repeat tile 0's values
+                    }
                 }
                 ptx::bulk_commit_group();
             }
@@ -399,12 +439,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 namespace tc64 {
 constexpr int THREADS = 128;
 constexpr uint32_t SMEM_BYTES = 3 * TILE_BYTES + 64 + 1024;     // Q, K, V tiles of 128 rows x 128 B, barriers, alignment
+constexpr uint32_t SMEM_BYTES_SPLIT = 6 * TILE_BYTES + 64 + 1024;   // + the lo halves (attn::SMEM_BYTES_SPLIT); two CTAs per SM
 constexpr uint32_t TMEM_COLS = 128;
 constexpr uint32_t O_COL = 64;
 }  // namespace tc64
 
-template <bool BF16>
-__global__ void __launch_bounds__(tc64::THREADS, 4)
+template <bool BF16, bool SPLIT = false>
+__global__ void __launch_bounds__(tc64::THREADS, SPLIT ? 2 : 4)
 attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, int num_pairs,
                       int heads, int L) {
     extern __shared__ uint8_t smem_raw[];
@@ -412,7 +453,8 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     uint8_t* sQ = smem;                         // [128][128 B]: rows 0..63 head h, rows 64..127 head h + 1
     uint8_t* sK = smem + TILE_BYTES;
     uint8_t* sV = smem + 2 * TILE_BYTES;
-    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 3 * TILE_BYTES);
+    constexpr uint32_t LO = 3 * TILE_BYTES, NH = SPLIT ? 2 : 1;
+    uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + NH * 3 * TILE_BYTES);
     uint64_t* bar_mma = bar_load + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_load + 2);
 
@@ -449,12 +491,17 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         if (tid == 0) {
             ptx::bulk_wait_group_read0();        // the previous pair's output (staged in the Q tile) has left
             const uint32_t lb = ptx::smem_u32(bar_load);
-            ptx::mbar_arrive_expect_tx(lb, 3 * TILE_BYTES);
+            ptx::mbar_arrive_expect_tx(lb, NH * 3 * TILE_BYTES);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {        // 64-token boxes: tokens >= L arrive as zeros
                 ptx::tma_load_3d(ptx::smem_u32(sQ + i * (TILE_BYTES / 2)), &tm_qkv, lb, (h + i) * 64, 0, b);
                 ptx::tma_load_3d(ptx::smem_u32(sK + i * (TILE_BYTES / 2)), &tm_qkv, lb, width + (h + i) * 64, 0, b);
                 ptx::tma_load_3d(ptx::smem_u32(sV + i * (TILE_BYTES / 2)), &tm_qkv, lb, 2 * width + (h + i) * 64, 0, b);
+                if (SPLIT) {
+                    ptx::tma_load_3d(ptx::smem_u32(sQ + LO + i * (TILE_BYTES / 2)), &tm_qkv, lb, 3 * width + (h + i) * 64, 0, b);
+                    ptx::tma_load_3d(ptx::smem_u32(sK + LO + i * (TILE_BYTES / 2)), &tm_qkv, lb, 4 * width + (h + i) * 64, 0, b);
+                    ptx::tma_load_3d(ptx::smem_u32(sV + LO + i * (TILE_BYTES / 2)), &tm_qkv, lb, 5 * width + (h + i) * 64, 0, b);
+                }
             }
         }
         ptx::mbar_wait(ptx::smem_u32(bar_load), load_phase);
@@ -465,6 +512,14 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             const uint64_t b_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sK));
 #pragma unroll
             for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+            if (SPLIT) {
+                const uint64_t a_lo = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ + LO));
+                const uint64_t b_lo = ptx::make_smem_desc_sw128(ptx::smem_u32(sK + LO));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(tmem, a_lo + 2 * k, b_desc + 2 * k, idesc_s, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ptx::umma_f16<1>(tmem, a_desc + 2 * k, b_lo + 2 * k, idesc_s, 1u);
+            }
             ptx::umma_commit(ptx::smem_u32(bar_mma));
         }
         ptx::mbar_wait(ptx::smem_u32(bar_mma), mma_phase);
@@ -516,6 +571,12 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)         // 16 keys per step: 8 packed columns of P, 16 rows (2 KB) of V
                 ptx::umma_f16_ts(tmem + tc64::O_COL, tmem + kk * 8, v_desc + (uint64_t)(kk * 2048 >> 4), idesc_o, kk != 0 ? 1u : 0u);
+            if (SPLIT) {
+                const uint64_t v_lo = ptx::make_smem_desc_sw128(ptx::smem_u32(sV + LO));
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    ptx::umma_f16_ts(tmem + tc64::O_COL, tmem + kk * 8, v_lo + (uint64_t)(kk * 2048 >> 4), idesc_o, 1u);
+            }
             ptx::umma_commit(ptx::smem_u32(bar_mma));
         }
         ptx::mbar_wait(ptx::smem_u32(bar_mma), mma_phase);
@@ -529,20 +590,25 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             ptx::tmem_ld_wait();
             const uint32_t srow = ptx::smem_u32(sQ + tid * 128);
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                const uint32_t q0 = gemm::pack2<BF16>(__uint_as_float(o0[j]) * inv_sum, __uint_as_float(o0[j + 1]) * inv_sum);
-                const uint32_t q1 = gemm::pack2<BF16>(__uint_as_float(o0[j + 2]) * inv_sum, __uint_as_float(o0[j + 3]) * inv_sum);
-                const uint32_t q2 = gemm::pack2<BF16>(__uint_as_float(o0[j + 4]) * inv_sum, __uint_as_float(o0[j + 5]) * inv_sum);
-                const uint32_t q3 = gemm::pack2<BF16>(__uint_as_float(o0[j + 6]) * inv_sum, __uint_as_float(o0[j + 7]) * inv_sum);
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((((j >> 3)) ^ (tid & 7)) << 4)), "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
-            }
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t (&oo)[32] = hh ? o1 : o0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                const uint32_t q0 = gemm::pack2<BF16>(__uint_as_float(o1[j]) * inv_sum, __uint_as_float(o1[j + 1]) * inv_sum);
-                const uint32_t q1 = gemm::pack2<BF16>(__uint_as_float(o1[j + 2]) * inv_sum, __uint_as_float(o1[j + 3]) * inv_sum);
-                const uint32_t q2 = gemm::pack2<BF16>(__uint_as_float(o1[j + 4]) * inv_sum, __uint_as_float(o1[j + 5]) * inv_sum);
-                const uint32_t q3 = gemm::pack2<BF16>(__uint_as_float(o1[j + 6]) * inv_sum, __uint_as_float(o1[j + 7]) * inv_sum);
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + (((4 + (j >> 3)) ^ (tid & 7)) << 4)), "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
+                for (int j = 0; j < 32; j += 8) {
+                    const uint32_t off = ((hh * 4 + (j >> 3)) ^ (tid & 7)) << 4;
+                    if (SPLIT) {
+                        uint32_t qh[4], ql[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) split_scaled(oo[j + 2 * e], oo[j + 2 * e + 1], inv_sum, qh[e], ql[e]);
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + off), "r"(qh[0]), "r"(qh[1]), "r"(qh[2]), "r"(qh[3]) : "memory");
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + LO + off), "r"(ql[0]), "r"(ql[1]), "r"(ql[2]), "r"(ql[3]) : "memory");
+                    } else {
+                        const uint32_t q0 = gemm::pack2<BF16>(__uint_as_float(oo[j]) * inv_sum, __uint_as_float(oo[j + 1]) * inv_sum);
+                        const uint32_t q1 = gemm::pack2<BF16>(__uint_as_float(oo[j + 2]) * inv_sum, __uint_as_float(oo[j + 3]) * inv_sum);
+                        const uint32_t q2 = gemm::pack2<BF16>(__uint_as_float(oo[j + 4]) * inv_sum, __uint_as_float(oo[j + 5]) * inv_sum);
+                        const uint32_t q3 = gemm::pack2<BF16>(__uint_as_float(oo[j + 6]) * inv_sum, __uint_as_float(oo[j + 7]) * inv_sum);
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + off), "r"(q0), "r"(q1), "r"(q2), "r"(q3) : "memory");
+                    }
+                }
             }
         }
         ptx::fence_proxy_async_smem();
@@ -551,6 +617,10 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         if (tid == 0) {
             ptx::tma_store_3d(&tm_out, ptx::smem_u32(sQ), h * 64, 0, b);
             ptx::tma_store_3d(&tm_out, ptx::smem_u32(sQ + TILE_BYTES / 2), (h + 1) * 64, 0, b);
+            if (SPLIT) {
+                ptx::tma_store_3d(&tm_out, ptx::smem_u32(sQ + LO), width + h * 64, 0, b);
+                ptx::tma_store_3d(&tm_out, ptx::smem_u32(sQ + LO + TILE_BYTES / 2), width + (h + 1) * 64, 0, b);
+            }
             ptx::bulk_commit_group();
         }
     }

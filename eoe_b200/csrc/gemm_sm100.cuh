@@ -50,9 +50,9 @@ constexpr float kGeluHalfSlope = 0.851f, kGeluSlope = 1.702f;
 #ifndef EOE_F16_GELU_EXACT
 #define EOE_F16_GELU_EXACT 0       // 1: fp16 outputs use exp + divide (2 MUFU per element) instead of the single tanh.approx
 #endif
-template <bool BF16>
+template <bool BF16, bool EXACT = false>
 __device__ __forceinline__ float quick_gelu_x(float ap) {
-    if (BF16 || !EOE_F16_GELU_EXACT) {
+    if (!EXACT && (BF16 || !EOE_F16_GELU_EXACT)) {
         float t;
         asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(ap));
         return fmaf(ap, t, ap);
@@ -61,7 +61,11 @@ __device__ __forceinline__ float quick_gelu_x(float ap) {
     return __fdividef(x2, 1.0f + __expf(-x2));
 }
 
-template <int EPI>
+// SPLIT (operand dtype EOE_F16X2, "split fp16"): every 16-bit matrix [rows, C] is stored as [rows, 2C] = [hi | lo] with
+// hi = rn16(x), lo = rn16(x - hi) (both fp16), and a product is evaluated as hi*hi + lo*hi + hi*lo in the same fp32
+// accumulator: the GEMM runs 3 K/64 blocks per logical k block (same tiles, same descriptors, TMA column offsets 0 / K).
+// 16-bit outputs leave as two tiles (hi at column n, lo at column lo_off + n).
+template <int EPI, bool SPLIT = false>
 struct Cfg {
     static constexpr bool kGeluX = (EPI == EOE_EPI_LNFOLD_QUICKGELU_X1702);
     static constexpr bool kLnFold = (EPI == EOE_EPI_LNFOLD_BIAS || EPI == EOE_EPI_LNFOLD_QUICKGELU || kGeluX);
@@ -73,8 +77,8 @@ struct Cfg {
     static constexpr bool kStatsAsync = (EPI == EPI_RESIDUAL_STATS_ASYNC);
     static constexpr bool kStatsReg = (EPI == EOE_EPI_RESIDUAL_STATS);
     static constexpr bool kStats = kStatsAsync || kStatsReg;
-    static constexpr int kStages = kStatsAsync ? 4 : 5;
-    static constexpr int kStageBufs = kStatsAsync ? 2 : 1;
+    static constexpr int kStages = (kStatsAsync || (SPLIT && kOut16)) ? 4 : 5;
+    static constexpr int kStageBufs = (kStatsAsync || (SPLIT && kOut16)) ? 2 : 1;   // SPLIT 16-bit outputs: a hi and a lo block
     // one warp's parameters: double-buffered {bias|c2 [128], c1 [128]} + single-buffered stats [32][MAX_NCH] float2
     static constexpr int kColBytes = kLnFold ? 1024 : 512;
     // + single-buffered per-row data: chunk sums of the tile's 32 rows and 32 row shifts
@@ -98,9 +102,11 @@ struct Params {
     const float2* stats_in; // LNFOLD_*: [M, K/128] per-row (sum, sum of squares) of the fp32 residual stream per chunk
     float2* stats_out;      // RESIDUAL_STATS: [M, N/128]
     uint16_t* xb_out;       // RESIDUAL_STATS: [M, N] operand-dtype copy of the updated residual stream, CENTRED on shift_out
+                            // (SPLIT: [M, 2N] = [hi | lo])
     const float* shift_in;  // LNFOLD_*: [M] value that was subtracted from every element of the row of A (null: 0)
     float* shift_out;       // RESIDUAL_STATS: [M] = the row's mean BEFORE this update (from stats_in; null stats_in: 0)
     int dbg;                // diagnostics (eoe_debug_set): 1 epilogue only releases accumulators, 2 no global stores
+    int64_t lo_off;         // SPLIT, 16-bit outputs: column of the lo tile of output column 0 in the store map (0: N)
 };
 
 template <bool BF16>
@@ -114,11 +120,20 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     }
 }
 
+// split fp16 pair: hi = rn(a), lo = rn(a - hi), two values per word
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // x * sigmoid(1.702 x).  bf16 output (2^-9 rounding): sigmoid(y) = 0.5 + 0.5 tanh(y/2) with the single-MUFU
 // tanh.approx (abs error ~5e-4 on the sigmoid, below the output rounding); fp16 output keeps exp + divide.
-template <bool BF16>
+template <bool BF16, bool EXACT = false>
 __device__ __forceinline__ float quick_gelu(float x) {
-    if (BF16 || !EOE_F16_GELU_EXACT) {
+    if (!EXACT && (BF16 || !EOE_F16_GELU_EXACT)) {
         float t;
         asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
         const float hx = 0.5f * x;
@@ -147,11 +162,12 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // vertically adjacent tiles (same n block, m blocks 2i and 2i+1) and share the W tile: each half of it is fetched from L2
 // ONCE and multicast into both pairs' shared memory, which cuts the operand traffic per flop by a quarter -- the main
 // loop is bound by L2 -> SM bandwidth (12.6 TB/s at 1.6 PFLOP/s with 256 x 256 tiles).
-template <int EPI, bool BF16, int CLP>
+template <int EPI, bool BF16, int CLP, bool SPLIT = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_c, const Params p) {
-    using C = Cfg<EPI>;
+    using C = Cfg<EPI, SPLIT>;
+    static_assert(!SPLIT || !BF16, "split operands are fp16 pairs");
     constexpr int STAGES = C::kStages;
     constexpr bool kLnFold = C::kLnFold, kGelu = C::kGelu, kOut16 = C::kOut16, kGeluX = C::kGeluX;
     constexpr bool kStatsAsync = C::kStatsAsync, kStatsReg = C::kStatsReg;
@@ -185,7 +201,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int num_n = (int)(p.N / BN);
     const int num_m = (int)((p.M + BM - 1) / BM);
     const int num_tiles = ((num_m + CLP - 1) / CLP) * num_n;
-    const int num_k = (int)(p.K / BK);
+    const int num_k = (int)(p.K / BK) * (SPLIT ? 3 : 1);    // SPLIT: (hi, hi), (lo, hi), (hi, lo) per logical k block
     auto m_block = [&](int unit) { return (unit / num_n) * CLP + cpair; };
 
     if (warp == 0 && lane == 0) {
@@ -229,14 +245,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     ptx::mbar_wait(ptx::smem_u32(&empty[stage]), phase ^ 1);   // released by EVERY pair of the cluster
                     const uint32_t fb_leader = ptx::mapa(ptx::smem_u32(&full[stage]), leader_rank);
                     if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full[stage]), 2 * STAGE_BYTES);
-                    ptx::tma_load_2d_cg2(ptx::smem_u32(smem_a + stage * A_BYTES), &tma_a, fb_leader, kb * BK, a_row);
+                    const int seg = SPLIT ? kb % 3 : 0, kcol = (SPLIT ? kb / 3 : kb) * BK;
+                    const int a_col = kcol + (seg == 1 ? (int)p.K : 0), b_col = kcol + (seg == 2 ? (int)p.K : 0);
+                    ptx::tma_load_2d_cg2(ptx::smem_u32(smem_a + stage * A_BYTES), &tma_a, fb_leader, a_col, a_row);
                     if (CLP == 1) {
-                        ptx::tma_load_2d_cg2(ptx::smem_u32(smem_b + stage * B_BYTES), &tma_b, fb_leader, kb * BK, b_row);
+                        ptx::tma_load_2d_cg2(ptx::smem_u32(smem_b + stage * B_BYTES), &tma_b, fb_leader, b_col, b_row);
                     } else if (cpair == 0) {
                         // W half `cta_rank` goes to the CTAs of that rank in both pairs; each copy signals the `full`
                         // barrier of ITS pair's leader (cta_group::2: the barrier operand names the even CTA of the pair)
                         const uint32_t fb_even = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
-                        ptx::tma_load_2d_cg2_mc(ptx::smem_u32(smem_b + stage * B_BYTES), &tma_b, fb_even, kb * BK, b_row,
+                        ptx::tma_load_2d_cg2_mc(ptx::smem_u32(smem_b + stage * B_BYTES), &tma_b, fb_even, b_col, b_row,
                                                 (uint16_t)(0x5u << cta_rank));
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -490,16 +508,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                 b[e] = __uint_as_float(r1[j + e]) + sbias[c * 64 + 32 + j + e];
                             }
                             if (kGelu) {                              // QuickGELU (model.py:162-164): x * sigmoid(1.702 x)
-                                a[e] = quick_gelu<BF16>(a[e]);
-                                b[e] = quick_gelu<BF16>(b[e]);
+                                a[e] = quick_gelu<BF16, SPLIT>(a[e]);        // (SPLIT: exp + divide, not tanh.approx)
+                                b[e] = quick_gelu<BF16, SPLIT>(b[e]);
                             }
                             if (kGeluX) {                             // 1.702 * QuickGELU from the pre-scaled argument
-                                a[e] = quick_gelu_x<BF16>(a[e]);
-                                b[e] = quick_gelu_x<BF16>(b[e]);
+                                a[e] = quick_gelu_x<BF16, SPLIT>(a[e]);
+                                b[e] = quick_gelu_x<BF16, SPLIT>(b[e]);
                             }
                         }
                         const uint32_t ka = (uint32_t)(((j >> 3)) ^ (lane & 7)) << 4, kb = (uint32_t)((4 + (j >> 3)) ^ (lane & 7)) << 4;
-                        if (do_store) {
+                        if (do_store && SPLIT) {
+                            uint32_t ah[4], al[4], bh[4], bl[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                split2(a[2 * e], a[2 * e + 1], ah[e], al[e]);
+                                split2(b[2 * e], b[2 * e + 1], bh[e], bl[e]);
+                            }
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ka), "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]) : "memory");
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + kb), "r"(bh[0]), "r"(bh[1]), "r"(bh[2]), "r"(bh[3]) : "memory");
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + 4096 + ka), "r"(al[0]), "r"(al[1]), "r"(al[2]), "r"(al[3]) : "memory");
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + 4096 + kb), "r"(bl[0]), "r"(bl[1]), "r"(bl[2]), "r"(bl[3]) : "memory");
+                        } else if (do_store) {
                             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ka), "r"(pack2<BF16>(a[0], a[1])),
                                          "r"(pack2<BF16>(a[2], a[3])), "r"(pack2<BF16>(a[4], a[5])), "r"(pack2<BF16>(a[6], a[7])) : "memory");
                             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(srow + kb), "r"(pack2<BF16>(b[0], b[1])),
@@ -510,6 +539,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     __syncwarp();
                     if (lane == 0 && do_store) {
                         ptx::tma_store_2d(&tma_c, ptx::smem_u32(st), (int)(nb + c * 64), (int)row0);
+                        if (SPLIT)
+                            ptx::tma_store_2d(&tma_c, ptx::smem_u32(st) + 4096, (int)((p.lo_off ? p.lo_off : p.N) + nb + c * 64), (int)row0);
                         ptx::bulk_commit_group();
                     }
                 }
@@ -560,8 +591,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         ssq[it] += (xn.x * xn.x + xn.y * xn.y) + (xn.z * xn.z + xn.w * xn.w);
                         if (row0 + r < p.M && do_store) {
                             *reinterpret_cast<float4*>(xout + (row0 + r) * p.N + col) = xn;
-                            *reinterpret_cast<uint2*>(p.xb_out + (row0 + r) * p.N + col) =
-                                make_uint2(pack2<BF16>(xn.x - mu8[it], xn.y - mu8[it]), pack2<BF16>(xn.z - mu8[it], xn.w - mu8[it]));
+                            if (SPLIT) {
+                                uint32_t h0, l0, h1, l1;
+                                split2(xn.x - mu8[it], xn.y - mu8[it], h0, l0);
+                                split2(xn.z - mu8[it], xn.w - mu8[it], h1, l1);
+                                uint16_t* xbr = p.xb_out + (row0 + r) * 2 * p.N + col;
+                                *reinterpret_cast<uint2*>(xbr) = make_uint2(h0, h1);
+                                *reinterpret_cast<uint2*>(xbr + p.N) = make_uint2(l0, l1);
+                            } else {
+                                *reinterpret_cast<uint2*>(p.xb_out + (row0 + r) * p.N + col) =
+                                    make_uint2(pack2<BF16>(xn.x - mu8[it], xn.y - mu8[it]), pack2<BF16>(xn.z - mu8[it], xn.w - mu8[it]));
+                            }
                         }
                     }
                 }
@@ -637,8 +677,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         const float4 xn = *reinterpret_cast<const float4*>(xb + r * STAGE_LD + grp * 4);
                         if (row0 + r < p.M && do_store) {
                             *reinterpret_cast<float4*>(xout + (row0 + r) * p.N + col) = xn;
-                            *reinterpret_cast<uint2*>(p.xb_out + (row0 + r) * p.N + col) =
-                                make_uint2(pack2<BF16>(xn.x - mu8[it], xn.y - mu8[it]), pack2<BF16>(xn.z - mu8[it], xn.w - mu8[it]));
+                            if (SPLIT) {
+                                uint32_t h0, l0, h1, l1;
+                                split2(xn.x - mu8[it], xn.y - mu8[it], h0, l0);
+                                split2(xn.z - mu8[it], xn.w - mu8[it], h1, l1);
+                                uint16_t* xbr = p.xb_out + (row0 + r) * 2 * p.N + col;
+                                *reinterpret_cast<uint2*>(xbr) = make_uint2(h0, h1);
+                                *reinterpret_cast<uint2*>(xbr + p.N) = make_uint2(l0, l1);
+                            } else {
+                                *reinterpret_cast<uint2*>(p.xb_out + (row0 + r) * p.N + col) =
+                                    make_uint2(pack2<BF16>(xn.x - mu8[it], xn.y - mu8[it]), pack2<BF16>(xn.z - mu8[it], xn.w - mu8[it]));
+                            }
                         }
                     }
                     __syncwarp();                      // every lane is done with this buffer: refill it two rounds ahead

@@ -106,12 +106,12 @@ static int num_sms() {
 static int g_gemm_debug = 0;            // eoe_debug_set(): diagnostics only, 0 in production
 static int g_last_max_clusters[2] = {0, 0};
 
-template <int EPI, bool BF16, int CLP>
+template <int EPI, bool BF16, int CLP, bool SPLIT = false>
 static int gemm_launch_c(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const gemm::Params& p, cudaStream_t st) {
-    auto kern = gemm::gemm_kernel<EPI, BF16, CLP>;
+    auto kern = gemm::gemm_kernel<EPI, BF16, CLP, SPLIT>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::Cfg<EPI>::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm::Cfg<EPI, SPLIT>::kSmemBytes);
         if (e != cudaSuccess) { set_cuda_error(e, "gemm smem attr"); return EOE_ERR_CUDA; }
         attr_done = true;
     }
@@ -123,7 +123,7 @@ static int gemm_launch_c(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
         cudaLaunchConfig_t q = {};
         q.gridDim = dim3((unsigned)(num_sms() / (2 * CLP) * 2 * CLP), 1, 1);
         q.blockDim = dim3(gemm::THREADS, 1, 1);
-        q.dynamicSmemBytes = gemm::Cfg<EPI>::kSmemBytes;
+        q.dynamicSmemBytes = gemm::Cfg<EPI, SPLIT>::kSmemBytes;
         cudaLaunchAttribute qa[1];
         qa[0].id = cudaLaunchAttributeClusterDimension;
         qa[0].val.clusterDim.x = 2 * CLP; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
@@ -139,7 +139,7 @@ static int gemm_launch_c(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * 2 * CLP), 1, 1);
     cfg.blockDim = dim3(gemm::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = gemm::Cfg<EPI>::kSmemBytes;
+    cfg.dynamicSmemBytes = gemm::Cfg<EPI, SPLIT>::kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -158,25 +158,46 @@ static int gemm_launch_c(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
 // Default: one CTA pair per cluster (all 148 SMs).  Diagnostics bit 4 (16) selects two pairs per cluster sharing the W
 // tile by TMA multicast: -25 % operand traffic and +8 % per SM, but only 33 clusters of 4 fit the GPCs (132 SMs), so it
 // does not pay on B200 (profiles/r1_gemm_probe_multicast.json).
-template <int EPI, bool BF16>
+template <int EPI, bool BF16, bool SPLIT = false>
 static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p_in, cudaStream_t st,
                          const CUtensorMap* tc) {
     gemm::Params p = p_in;
     p.dbg = g_gemm_debug & 7;
-    // 16-bit outputs leave through TMA tile stores: box 32 rows x 64 columns over out [M, N] (rows >= M are clipped)
+    // 16-bit outputs leave through TMA tile stores: box 32 rows x 64 columns over out [M, N] (rows >= M are clipped);
+    // SPLIT: out is [M, 2N] = [hi | lo]
     CUtensorMap local;
     if (gemm::Cfg<EPI>::kOut16 && !tc) {
-        int rc = make_tmap(&local, p.out, p.M, p.N, 32, BF16 ? EOE_BF16 : EOE_F16);
+        int rc = make_tmap(&local, p.out, p.M, SPLIT ? 2 * p.N : p.N, 32, BF16 ? EOE_BF16 : EOE_F16);
         if (rc) return rc;
         tc = &local;
     }
     if (!tc) tc = &ta;                                       // unused by the fp32-output epilogues
+    if (SPLIT) return gemm_launch_c<EPI, false, 1, SPLIT>(ta, tb, *tc, p, st);
     if (g_gemm_debug & 16) return gemm_launch_c<EPI, BF16, 2>(ta, tb, *tc, p, st);
     return gemm_launch_c<EPI, BF16, 1>(ta, tb, *tc, p, st);
 }
 
+// operand dtype EOE_F16X2: the same epilogues over split fp16 operands (gemm::Cfg)
+static int gemm_launch_split(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int epi, cudaStream_t st,
+                             const CUtensorMap* tc) {
+    switch (epi) {
+        case EOE_EPI_BIAS: return gemm_launch_t<EOE_EPI_BIAS, false, true>(ta, tb, p, st, tc);
+        case EOE_EPI_BIAS_QUICKGELU: return gemm_launch_t<EOE_EPI_BIAS_QUICKGELU, false, true>(ta, tb, p, st, tc);
+        case EOE_EPI_BIAS_RESIDUAL_F32: return gemm_launch_t<EOE_EPI_BIAS_RESIDUAL_F32, false, true>(ta, tb, p, st, tc);
+        case EOE_EPI_PATCH_EMBED: return gemm_launch_t<EOE_EPI_PATCH_EMBED, false, true>(ta, tb, p, st, tc);
+        case EOE_EPI_LNFOLD_BIAS: return gemm_launch_t<EOE_EPI_LNFOLD_BIAS, false, true>(ta, tb, p, st, tc);
+        case EOE_EPI_LNFOLD_QUICKGELU: return gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU, false, true>(ta, tb, p, st, tc);
+        case EOE_EPI_LNFOLD_QUICKGELU_X1702: return gemm_launch_t<EOE_EPI_LNFOLD_QUICKGELU_X1702, false, true>(ta, tb, p, st, tc);
+        case EOE_EPI_RESIDUAL_STATS:
+            if (p.K <= 1024) return gemm_launch_t<gemm::EPI_RESIDUAL_STATS_ASYNC, false, true>(ta, tb, p, st, tc);
+            return gemm_launch_t<EOE_EPI_RESIDUAL_STATS, false, true>(ta, tb, p, st, tc);
+        default: return EOE_ERR_ARG;
+    }
+}
+
 static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const gemm::Params& p, int dtype, int epi,
                        cudaStream_t st, const CUtensorMap* tc = nullptr) {
+    if (dtype == EOE_F16X2) return gemm_launch_split(ta, tb, p, epi, st, tc);
     const bool bf = dtype == EOE_BF16;
     switch (epi) {
         case EOE_EPI_BIAS: return bf ? gemm_launch_t<EOE_EPI_BIAS, true>(ta, tb, p, st, tc) : gemm_launch_t<EOE_EPI_BIAS, false>(ta, tb, p, st, tc);
@@ -196,14 +217,15 @@ static int gemm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const gemm:
 
 static int gemm_check(int64_t M, int64_t N, int64_t K, int dtype) {
     if (M <= 0 || N <= 0 || K <= 0) return EOE_ERR_ARG;
-    if (dtype != EOE_BF16 && dtype != EOE_F16) return EOE_ERR_DTYPE;
+    if (dtype != EOE_BF16 && dtype != EOE_F16 && dtype != EOE_F16X2) return EOE_ERR_DTYPE;
     if (N % gemm::BN != 0 || K % gemm::BK != 0) return EOE_ERR_SHAPE;
     return EOE_OK;
 }
 
 // ------------------------------------------------------------------------------------------ im2col
 // imgs [B,3,R,R] fp32 NCHW -> patches [B*g*g, 3*P*P] 16-bit with k = c*P*P + py*P + px (= conv1.weight.view(width,-1))
-template <bool BF16>
+// SPLIT (operand dtype EOE_F16X2): patches [B*g*g, 2 * 3*P*P] = [hi | lo] fp16 pairs (gemm::split2)
+template <bool BF16, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ imgs, uint16_t* __restrict__ patches, int64_t B, int R, int P) {
     // one thread: 8 consecutive pixels of a patch row (two 16-byte loads, one 16-byte store); 8 | P
@@ -223,6 +245,17 @@ im2col_kernel(const float* __restrict__ imgs, uint16_t* __restrict__ patches, in
         float v0[4], v1[4];
         load4_stream<float>(reinterpret_cast<const float*>(src), v0);
         load4_stream<float>(reinterpret_cast<const float*>(src + 1), v1);
+        if (SPLIT) {
+            uint4 hi, lo;
+            gemm::split2(v0[0], v0[1], hi.x, lo.x);
+            gemm::split2(v0[2], v0[3], hi.y, lo.y);
+            gemm::split2(v1[0], v1[1], hi.z, lo.z);
+            gemm::split2(v1[2], v1[3], hi.w, lo.w);
+            const int64_t kp = 3 * (int64_t)P * P, row = idx * 8 / kp, k = idx * 8 % kp;
+            *reinterpret_cast<uint4*>(patches + row * 2 * kp + k) = hi;
+            *reinterpret_cast<uint4*>(patches + row * 2 * kp + kp + k) = lo;
+            continue;
+        }
         uint4 o;
         o.x = gemm::pack2<BF16>(v0[0], v0[1]);
         o.y = gemm::pack2<BF16>(v0[2], v0[3]);
@@ -240,16 +273,25 @@ im2col_kernel(const float* __restrict__ imgs, uint16_t* __restrict__ patches, in
 // NHWC == false: imgs [B,3,R,R] (ToTensor's layout);  NHWC == true: imgs [B,R,R,3] (decoded image files).
 // One thread converts 16 consecutive pixels of one patch row (16 | P).
 struct NormParams { float mean[3], stdv[3]; };
-template <bool BF16, bool NHWC>
+template <bool BF16, bool NHWC, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 im2col_u8_kernel(const uint8_t* __restrict__ imgs, uint16_t* __restrict__ patches, int64_t B, int R, int P, NormParams np) {
     __shared__ uint16_t lut[3][256];
+    __shared__ uint16_t lut_lo[SPLIT ? 3 : 1][256];     // SPLIT: the lo halves, written P*P*3 elements behind the hi halves
     for (int i = threadIdx.x; i < 768; i += 256) {
         const int c = i >> 8, v = i & 255;
         const float x = __fdiv_rn(__fdiv_rn((float)v, 255.0f) - np.mean[c], np.stdv[c]);
-        lut[c][v] = (uint16_t)(gemm::pack2<BF16>(x, 0.f) & 0xffffu);
+        if (SPLIT) {
+            uint32_t hi, lo;
+            gemm::split2(x, 0.f, hi, lo);
+            lut[c][v] = (uint16_t)(hi & 0xffffu);
+            lut_lo[c][v] = (uint16_t)(lo & 0xffffu);
+        } else {
+            lut[c][v] = (uint16_t)(gemm::pack2<BF16>(x, 0.f) & 0xffffu);
+        }
     }
     __syncthreads();
+    const int64_t rstride = (SPLIT ? 2 : 1) * 3 * (int64_t)(P * P);      // elements per patch row
     const int g = R / P, segs = P / 16;
     const int64_t total = NHWC ? B * (int64_t)R * (R / 16) : B * 3 * (int64_t)R * (R / 16);
     for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
@@ -262,37 +304,44 @@ im2col_u8_kernel(const uint8_t* __restrict__ imgs, uint16_t* __restrict__ patche
             const uint4* src = reinterpret_cast<const uint4*>(imgs + ((b * R + y) * (int64_t)R + xs * 16) * 3);
             const uint4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
             const uint32_t wds[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-            uint16_t o[3][16];
 #pragma unroll
-            for (int i = 0; i < 48; ++i) {
-                const uint32_t byte = (wds[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-                o[i % 3][i / 3] = lut[i % 3][byte];
-            }
+            for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+                uint16_t o[3][16];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                uint16_t* dst = patches + (((b * g + gy) * g + gx) * 3 + c) * (int64_t)(P * P) + py * P + sx * 16;
-                uint4 w0, w1;
-                w0.x = o[c][0] | ((uint32_t)o[c][1] << 16); w0.y = o[c][2] | ((uint32_t)o[c][3] << 16);
-                w0.z = o[c][4] | ((uint32_t)o[c][5] << 16); w0.w = o[c][6] | ((uint32_t)o[c][7] << 16);
-                w1.x = o[c][8] | ((uint32_t)o[c][9] << 16); w1.y = o[c][10] | ((uint32_t)o[c][11] << 16);
-                w1.z = o[c][12] | ((uint32_t)o[c][13] << 16); w1.w = o[c][14] | ((uint32_t)o[c][15] << 16);
-                reinterpret_cast<uint4*>(dst)[0] = w0;
-                reinterpret_cast<uint4*>(dst)[1] = w1;
+                for (int i = 0; i < 48; ++i) {
+                    const uint32_t byte = (wds[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+                    o[i % 3][i / 3] = part ? lut_lo[SPLIT ? i % 3 : 0][byte] : lut[i % 3][byte];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    uint16_t* dst = patches + ((b * g + gy) * g + gx) * rstride + (part * 3 + c) * (int64_t)(P * P) + py * P + sx * 16;
+                    uint4 w0, w1;
+                    w0.x = o[c][0] | ((uint32_t)o[c][1] << 16); w0.y = o[c][2] | ((uint32_t)o[c][3] << 16);
+                    w0.z = o[c][4] | ((uint32_t)o[c][5] << 16); w0.w = o[c][6] | ((uint32_t)o[c][7] << 16);
+                    w1.x = o[c][8] | ((uint32_t)o[c][9] << 16); w1.y = o[c][10] | ((uint32_t)o[c][11] << 16);
+                    w1.z = o[c][12] | ((uint32_t)o[c][13] << 16); w1.w = o[c][14] | ((uint32_t)o[c][15] << 16);
+                    reinterpret_cast<uint4*>(dst)[0] = w0;
+                    reinterpret_cast<uint4*>(dst)[1] = w1;
+                }
             }
         } else {
             const int c = (int)(t % 3); t /= 3;
             const int64_t b = t;
             const uint4 q = __ldg(reinterpret_cast<const uint4*>(imgs + ((b * 3 + c) * R + y) * (int64_t)R + xs * 16));
             const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
-            uint32_t o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t b0 = (wds[i >> 1] >> ((i & 1) * 16)) & 0xffu, b1 = (wds[i >> 1] >> ((i & 1) * 16 + 8)) & 0xffu;
-                o[i] = lut[c][b0] | ((uint32_t)lut[c][b1] << 16);
+            for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+                const uint16_t* lt = part ? lut_lo[SPLIT ? c : 0] : lut[c];
+                uint32_t o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t b0 = (wds[i >> 1] >> ((i & 1) * 16)) & 0xffu, b1 = (wds[i >> 1] >> ((i & 1) * 16 + 8)) & 0xffu;
+                    o[i] = lt[b0] | ((uint32_t)lt[b1] << 16);
+                }
+                uint16_t* dst = patches + ((b * g + gy) * g + gx) * rstride + (part * 3 + c) * (int64_t)(P * P) + py * P + sx * 16;
+                reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
             }
-            uint16_t* dst = patches + (((b * g + gy) * g + gx) * 3 + c) * (int64_t)(P * P) + py * P + sx * 16;
-            reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
     }
 }
@@ -346,12 +395,13 @@ __device__ __forceinline__ int pil_clip8(int acc) {
     return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-template <bool BF16>
+template <bool BF16, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 resize_patchify_kernel(const uint8_t* __restrict__ imgs, uint16_t* __restrict__ patches, int R, int P, ResizeGeom gm,
                        NormParams np, int max_rows) {
     extern __shared__ uint8_t rs_smem[];
     __shared__ uint16_t lut[3][256];
+    __shared__ uint16_t lut_lo[SPLIT ? 3 : 1][256];
     __shared__ int s_vfirst[32], s_vcount[32];
     __shared__ int s_rlo, s_rhi;
     const int g = R / P, gy = blockIdx.x;
@@ -364,7 +414,14 @@ resize_patchify_kernel(const uint8_t* __restrict__ imgs, uint16_t* __restrict__ 
     for (int i = threadIdx.x; i < 768; i += 256) {
         const int c = i >> 8, v = i & 255;
         const float x = __fdiv_rn(__fdiv_rn((float)v, 255.0f) - np.mean[c], np.stdv[c]);
-        lut[c][v] = (uint16_t)(gemm::pack2<BF16>(x, 0.f) & 0xffffu);
+        if (SPLIT) {
+            uint32_t hi, lo;
+            gemm::split2(x, 0.f, hi, lo);
+            lut[c][v] = (uint16_t)(hi & 0xffffu);
+            lut_lo[c][v] = (uint16_t)(lo & 0xffffu);
+        } else {
+            lut[c][v] = (uint16_t)(gemm::pack2<BF16>(x, 0.f) & 0xffffu);
+        }
     }
     // coefficient tables: R cropped output columns, P output rows of this patch row
     for (int i = threadIdx.x; i < R + P; i += 256) {
@@ -412,13 +469,17 @@ resize_patchify_kernel(const uint8_t* __restrict__ imgs, uint16_t* __restrict__ 
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[e] += (int)srow[3 * e] * w;
         }
-        uint32_t o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            o[e] = lut[c][pil_clip8(acc[2 * e])] | ((uint32_t)lut[c][pil_clip8(acc[2 * e + 1])] << 16);
         const int xx = seg * 8, gx = xx / P, px = xx % P;
-        uint16_t* dst = patches + (((b * g + gy) * g + gx) * 3 + c) * (int64_t)(P * P) + py * P + px;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+            const uint16_t* lt = part ? lut_lo[SPLIT ? c : 0] : lut[c];
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                o[e] = lt[pil_clip8(acc[2 * e])] | ((uint32_t)lt[pil_clip8(acc[2 * e + 1])] << 16);
+            uint16_t* dst = patches + ((b * g + gy) * g + gx) * (int64_t)((SPLIT ? 6 : 3) * P * P) + (part * 3 + c) * (int64_t)(P * P) + py * P + px;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
@@ -451,7 +512,8 @@ static int resize_geometry(int64_t H, int64_t W, int n_px, ResizeGeom* gm) {
 // fp32 statistics over `width` (model.py:153-159, eps 1e-5); one warp per row, row kept in registers.
 // cls_emb != null: rows with row % L == 0 are synthesised as class_embedding + positional_embedding[0]
 // (model.py:223-224) -- used by ln_pre, whose other rows already hold patch_embed + pos_emb from the GEMM epilogue.
-template <typename OutT, int ITERS>
+// SPLIT (out_dtype EOE_F16X2): y [M, 2 * width] = [hi | lo] fp16 pairs.
+template <typename OutT, int ITERS, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                  OutT* __restrict__ y, int64_t M, int width, const float* __restrict__ cls_emb,
@@ -499,8 +561,14 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
             const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + vi);
             float o[4] = {(v[it][0] - mean) * rstd * ww.x + bb.x, (v[it][1] - mean) * rstd * ww.y + bb.y,
                           (v[it][2] - mean) * rstd * ww.z + bb.z, (v[it][3] - mean) * rstd * ww.w + bb.w};
-            OutT* dst = y + row * width + vi * 4;
-            if (sizeof(OutT) == 4) {
+            OutT* dst = y + row * (SPLIT ? 2 : 1) * width + vi * 4;
+            if (SPLIT) {
+                uint2 hi, lo;
+                gemm::split2(o[0], o[1], hi.x, lo.x);
+                gemm::split2(o[2], o[3], hi.y, lo.y);
+                *reinterpret_cast<uint2*>(dst) = hi;
+                *reinterpret_cast<uint2*>(dst + width) = lo;
+            } else if (sizeof(OutT) == 4) {
                 *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
                 uint2 pk;
@@ -513,14 +581,14 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     }
 }
 
-template <typename OutT>
+template <typename OutT, bool SPLIT = false>
 static int layernorm_launch(const float* x, const float* w, const float* b, void* y, int64_t M, int64_t width,
                             const float* cls_emb, const float* pos0, int L, cudaStream_t st) {
     const int grid = (int)((M + 7) / 8);
     if (width <= 768)
-        layernorm_kernel<OutT, 6><<<grid, 256, 0, st>>>(x, w, b, (OutT*)y, M, (int)width, cls_emb, pos0, L);
+        layernorm_kernel<OutT, 6, SPLIT><<<grid, 256, 0, st>>>(x, w, b, (OutT*)y, M, (int)width, cls_emb, pos0, L);
     else
-        layernorm_kernel<OutT, 8><<<grid, 256, 0, st>>>(x, w, b, (OutT*)y, M, (int)width, cls_emb, pos0, L);
+        layernorm_kernel<OutT, 8, SPLIT><<<grid, 256, 0, st>>>(x, w, b, (OutT*)y, M, (int)width, cls_emb, pos0, L);
     return check_launch("layernorm_kernel");
 }
 
@@ -531,13 +599,14 @@ static int layernorm_dispatch(const float* x, const float* w, const float* b, vo
         case EOE_F32: return layernorm_launch<float>(x, w, b, y, M, width, cls_emb, pos0, L, st);
         case EOE_F16: return layernorm_launch<__half>(x, w, b, y, M, width, cls_emb, pos0, L, st);
         case EOE_BF16: return layernorm_launch<__nv_bfloat16>(x, w, b, y, M, width, cls_emb, pos0, L, st);
+        case EOE_F16X2: return layernorm_launch<__half, true>(x, w, b, y, M, width, cls_emb, pos0, L, st);
         default: return EOE_ERR_DTYPE;
     }
 }
 
 // ln_pre for the LayerNorm-folded encoder: y = LN(x) in place (fp32, class-token rows synthesised as above) plus what the
 // first folded GEMM needs: xb = round16(y) and stats[row][0] = (sum y, sum y^2), stats[row][1..nch) = 0.
-template <bool BF16, int ITERS>
+template <bool BF16, int ITERS, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 ln_pre_stats_kernel(float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                     uint16_t* __restrict__ xb, float2* __restrict__ stats, float* __restrict__ shift, int64_t M, int width,
@@ -598,9 +667,16 @@ ln_pre_stats_kernel(float* __restrict__ x, const float* __restrict__ w, const fl
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
         const int vi = it * 32 + lane;
-        if (vi < nvec)
+        if (vi < nvec && SPLIT) {
+            uint2 hi, lo;
+            gemm::split2(v[it][0] - ymean, v[it][1] - ymean, hi.x, lo.x);
+            gemm::split2(v[it][2] - ymean, v[it][3] - ymean, hi.y, lo.y);
+            *reinterpret_cast<uint2*>(xb + row * 2 * width + vi * 4) = hi;
+            *reinterpret_cast<uint2*>(xb + row * 2 * width + width + vi * 4) = lo;
+        } else if (vi < nvec) {
             *reinterpret_cast<uint2*>(xb + row * width + vi * 4) =
                 make_uint2(gemm::pack2<BF16>(v[it][0] - ymean, v[it][1] - ymean), gemm::pack2<BF16>(v[it][2] - ymean, v[it][3] - ymean));
+        }
     }
     const int nch = width >> 7;
     if (lane < nch) stats[row * nch + lane] = lane == 0 ? make_float2(ys, yq) : make_float2(0.f, 0.f);
@@ -608,7 +684,8 @@ ln_pre_stats_kernel(float* __restrict__ x, const float* __restrict__ w, const fl
 }
 
 // LayerNorm fold of one Linear (eoe_vit_fold_layernorm): one warp per output row n.
-template <bool BF16>
+// SPLIT (EOE_F16X2): wf [N, 2K] = [hi | lo] fp16 pairs of W * ln_w, c1 = rowsum(hi + lo).
+template <bool BF16, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                const float* __restrict__ bias, int64_t N, int64_t K, uint16_t* __restrict__ wf,
@@ -621,8 +698,17 @@ fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ ln_w, cons
         const float4 a = *reinterpret_cast<const float4*>(w + n * K + k);
         const float4 g = __ldg(reinterpret_cast<const float4*>(ln_w + k));
         const float4 be = __ldg(reinterpret_cast<const float4*>(ln_b + k));
-        const uint32_t p0 = gemm::pack2<BF16>(a.x * g.x, a.y * g.y), p1 = gemm::pack2<BF16>(a.z * g.z, a.w * g.w);
-        *reinterpret_cast<uint2*>(wf + n * K + k) = make_uint2(p0, p1);
+        uint32_t p0, p1, q0 = 0, q1 = 0;
+        if (SPLIT) {
+            gemm::split2(a.x * g.x, a.y * g.y, p0, q0);
+            gemm::split2(a.z * g.z, a.w * g.w, p1, q1);
+            *reinterpret_cast<uint2*>(wf + n * 2 * K + k) = make_uint2(p0, p1);
+            *reinterpret_cast<uint2*>(wf + n * 2 * K + K + k) = make_uint2(q0, q1);
+        } else {
+            p0 = gemm::pack2<BF16>(a.x * g.x, a.y * g.y);
+            p1 = gemm::pack2<BF16>(a.z * g.z, a.w * g.w);
+            *reinterpret_cast<uint2*>(wf + n * K + k) = make_uint2(p0, p1);
+        }
         float r[4];
         if (BF16) {
             r[0] = __uint_as_float(p0 << 16); r[1] = __uint_as_float(p0 & 0xffff0000u);
@@ -631,6 +717,11 @@ fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ ln_w, cons
             const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&p0));
             const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&p1));
             r[0] = f0.x; r[1] = f0.y; r[2] = f1.x; r[3] = f1.y;
+            if (SPLIT) {
+                const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&q0));
+                const float2 l1 = __half22float2(*reinterpret_cast<const __half2*>(&q1));
+                r[0] += l0.x; r[1] += l0.y; r[2] += l1.x; r[3] += l1.y;
+            }
         }
         s1 += (r[0] + r[1]) + (r[2] + r[3]);
         s2 += (a.x * be.x + a.y * be.y) + (a.z * be.z + a.w * be.w);
@@ -803,30 +894,32 @@ static int attention_launch_t(const void* qkv, void* out, int64_t B, int L, int 
 }
 
 // tcgen05 path (L == 197): qkv is read through a TMA descriptor with 128-row x 64-column boxes
-template <bool BF16>
+template <bool BF16, bool SPLIT = false>
 static int attention_tc_launch(const CUtensorMap& tm_qkv, void* out, int64_t B, int heads, int dtype, cudaStream_t st,
                                const CUtensorMap* tm_o128 = nullptr, const CUtensorMap* tm_o72 = nullptr) {
     CUtensorMap l128, l72;
     if (!tm_o128) {
-        int rc = make_tmap_tokens(&l128, out, B, 197, heads * 64, 128, dtype);
-        if (!rc) rc = make_tmap_tokens(&l72, out, B, 197, heads * 64, 72, dtype);
+        int rc = make_tmap_tokens(&l128, out, B, 197, (SPLIT ? 2 : 1) * heads * 64, 128, dtype);
+        if (!rc) rc = make_tmap_tokens(&l72, out, B, 197, (SPLIT ? 2 : 1) * heads * 64, 72, dtype);
         if (rc) return rc;
         tm_o128 = &l128;
         tm_o72 = &l72;
     }
-    auto kern = attn::attention_tc_kernel<BF16, 197>;
+    auto kern = attn::attention_tc_kernel<BF16, 197, SPLIT>;
+    constexpr uint32_t smem_bytes = SPLIT ? attn::SMEM_BYTES_SPLIT : attn::SMEM_BYTES;
+    constexpr int per_sm = SPLIT ? 1 : 2;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) { set_cuda_error(e, "attention_tc smem attr"); return EOE_ERR_CUDA; }
         attr_done = true;
     }
     const int64_t items = B * heads;
-    const int grid = (int)(items < 2 * (int64_t)num_sms() ? items : 2 * (int64_t)num_sms());
+    const int grid = (int)(items < per_sm * (int64_t)num_sms() ? items : per_sm * (int64_t)num_sms());
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.blockDim = dim3(attn::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = attn::SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -839,30 +932,32 @@ static int attention_tc_launch(const CUtensorMap& tm_qkv, void* out, int64_t B, 
 }
 
 // tcgen05 path for L <= 64 (ViT-B/32: 50 tokens): two heads of an image per 128-row tile, 64-token TMA boxes
-template <bool BF16>
+template <bool BF16, bool SPLIT = false>
 static int attention_tc64_launch(const void* qkv, void* out, int64_t B, int L, int heads, int dtype, cudaStream_t st,
                                  const CUtensorMap* tm_qkv64 = nullptr, const CUtensorMap* tm_o64 = nullptr) {
     CUtensorMap lq, lo;
     if (!tm_qkv64) {
-        int rc = make_tmap_tokens(&lq, qkv, B, L, 3 * heads * 64, 64, dtype);
-        if (!rc) rc = make_tmap_tokens(&lo, out, B, L, heads * 64, 64, dtype);
+        int rc = make_tmap_tokens(&lq, qkv, B, L, (SPLIT ? 6 : 3) * heads * 64, 64, dtype);
+        if (!rc) rc = make_tmap_tokens(&lo, out, B, L, (SPLIT ? 2 : 1) * heads * 64, 64, dtype);
         if (rc) return rc;
         tm_qkv64 = &lq;
         tm_o64 = &lo;
     }
-    auto kern = attn::attention_tc64_kernel<BF16>;
+    auto kern = attn::attention_tc64_kernel<BF16, SPLIT>;
+    constexpr uint32_t smem_bytes = SPLIT ? attn::tc64::SMEM_BYTES_SPLIT : attn::tc64::SMEM_BYTES;
+    constexpr int per_sm = SPLIT ? 2 : 4;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::tc64::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) { set_cuda_error(e, "attention_tc64 smem attr"); return EOE_ERR_CUDA; }
         attr_done = true;
     }
     const int64_t pairs = B * (heads / 2);
-    const int grid = (int)(pairs < 4 * (int64_t)num_sms() ? pairs : 4 * (int64_t)num_sms());
+    const int grid = (int)(pairs < per_sm * (int64_t)num_sms() ? pairs : per_sm * (int64_t)num_sms());
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.blockDim = dim3(attn::tc64::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = attn::tc64::SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -877,8 +972,24 @@ static int attention_tc64_launch(const void* qkv, void* out, int64_t B, int L, i
 static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, int64_t heads, int dtype, cudaStream_t st,
                               const CUtensorMap* tm_qkv = nullptr, const CUtensorMap* tm_o128 = nullptr,
                               const CUtensorMap* tm_o72 = nullptr, bool causal = false) {
-    if (dtype != EOE_BF16 && dtype != EOE_F16) return EOE_ERR_DTYPE;
+    if (dtype != EOE_BF16 && dtype != EOE_F16 && dtype != EOE_F16X2) return EOE_ERR_DTYPE;
     if (B <= 0 || L <= 0 || heads <= 0 || B * heads > 0x7fffffff) return EOE_ERR_ARG;
+    if (dtype == EOE_F16X2) {
+        // split fp16 operands: qkv [B*L, 6*width] = [q k v | lo halves], out [B*L, 2*width]; the two tcgen05 kernels only
+        if (causal || (uintptr_t)qkv % 16 != 0 || (uintptr_t)out % 16 != 0) return EOE_ERR_SHAPE;
+        if (L == 197) {
+            CUtensorMap local;
+            if (!tm_qkv) {
+                int rc = make_tmap_tokens(&local, qkv, B, L, 6 * heads * 64, 128, EOE_F16);
+                if (rc) return rc;
+                tm_qkv = &local;
+            }
+            return attention_tc_launch<false, true>(*tm_qkv, out, B, (int)heads, EOE_F16, st, tm_o128, tm_o72);
+        }
+        if (L <= 64 && heads % 2 == 0)
+            return attention_tc64_launch<false, true>(qkv, out, B, (int)L, (int)heads, EOE_F16, st, tm_qkv, tm_o128);
+        return EOE_ERR_SHAPE;
+    }
     const bool bf = dtype == EOE_BF16;
     if (causal) {                                    // text tower (context 77): warp-level kernel, keys in shared memory
         if (L <= 80) return bf ? attention_launch_t<true, 80, true>(qkv, out, B, (int)L, (int)heads, st) : attention_launch_t<false, 80, true>(qkv, out, B, (int)L, (int)heads, st);
@@ -915,19 +1026,20 @@ static int attention_dispatch(const void* qkv, void* out, int64_t B, int64_t L, 
 __global__ void __launch_bounds__(256)
 gather_cls_rows_kernel(const uint16_t* __restrict__ xb, const float2* __restrict__ stats, const float* __restrict__ shift,
                        uint16_t* __restrict__ xb_cls, float2* __restrict__ stats_cls, float* __restrict__ shift_cls,
-                       int64_t B, int L, int width) {
+                       int64_t B, int L, int width, int xw) {      // xw: elements per row of xb (2 * width for split operands)
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= B) return;
     const int64_t row = b * L;
-    const int nvec = width / 8, nch = width / 128;
+    const int nvec = xw / 8, nch = width / 128;
     for (int i = lane; i < nvec; i += 32)
-        reinterpret_cast<uint4*>(xb_cls + b * width)[i] = __ldg(reinterpret_cast<const uint4*>(xb + row * width) + i);
+        reinterpret_cast<uint4*>(xb_cls + b * xw)[i] = __ldg(reinterpret_cast<const uint4*>(xb + row * xw) + i);
     if (lane < nch) stats_cls[b * nch + lane] = stats[row * nch + lane];
     if (lane == 0) shift_cls[b] = shift[row];
 }
 
-template <bool BF16>
+// SPLIT (EOE_F16X2): qkv rows are [q k v | q_lo k_lo v_lo], q_cls and h_cls rows [hi | lo]; values are hi + lo in fp32.
+template <bool BF16, bool SPLIT = false>
 __global__ void __launch_bounds__(128)
 attention_cls_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ q_cls, const float* __restrict__ x,
                      uint16_t* __restrict__ h_cls, float* __restrict__ x_cls, int64_t B, int L, int heads) {
@@ -945,14 +1057,27 @@ attention_cls_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
     if (h == 0)                                     // gather the residual-stream row of the class token
         for (int i = lane; i < width / 4; i += 32)
             reinterpret_cast<float4*>(x_cls + b * width)[i] = reinterpret_cast<const float4*>(x + b * L * (int64_t)width)[i];
-    const uint16_t* base = qkv + b * L * (int64_t)(3 * width);
+    constexpr int S = SPLIT ? 2 : 1;
+    const int64_t rs = (int64_t)S * 3 * width;       // elements per qkv row
+    const uint16_t* base = qkv + b * L * rs;
+    // 8 consecutive 16-bit values (+ their lo halves `lo_off` elements further on) -> fp32
+    auto load8 = [&](const uint16_t* src, int lo_off, float* f) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+        cvt2(v.x, f[0], f[1]); cvt2(v.y, f[2], f[3]); cvt2(v.z, f[4], f[5]); cvt2(v.w, f[6], f[7]);
+        if (SPLIT) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + lo_off));
+            float g[8];
+            cvt2(u.x, g[0], g[1]); cvt2(u.y, g[2], g[3]); cvt2(u.z, g[4], g[5]); cvt2(u.w, g[6], g[7]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += g[e];
+        }
+    };
     float q[64];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         // the class token's query: from its own [B, width] buffer when the last block computed Q for those rows only
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(q_cls ? q_cls + b * width + h * 64 : base + h * 64) + i);
-        cvt2(v.x, q[i * 8], q[i * 8 + 1]); cvt2(v.y, q[i * 8 + 2], q[i * 8 + 3]);
-        cvt2(v.z, q[i * 8 + 4], q[i * 8 + 5]); cvt2(v.w, q[i * 8 + 6], q[i * 8 + 7]);
+        if (q_cls) load8(q_cls + b * S * width + h * 64 + i * 8, width, q + i * 8);
+        else load8(base + h * 64 + i * 8, 3 * width, q + i * 8);
     }
     constexpr int MAXK = 7;                         // keys per lane: L <= 224
     float sc[MAXK];
@@ -962,16 +1087,16 @@ attention_cls_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
         const int j = t * 32 + lane;
         float d = -INFINITY;
         if (j < L) {
-            const uint4* kr = reinterpret_cast<const uint4*>(base + (int64_t)j * 3 * width + width + h * 64);
+            const uint16_t* kr = base + (int64_t)j * rs + width + h * 64;
             d = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const uint4 v = __ldg(kr + i);
-                float a0, a1;
-                cvt2(v.x, a0, a1); d += q[i * 8] * a0 + q[i * 8 + 1] * a1;
-                cvt2(v.y, a0, a1); d += q[i * 8 + 2] * a0 + q[i * 8 + 3] * a1;
-                cvt2(v.z, a0, a1); d += q[i * 8 + 4] * a0 + q[i * 8 + 5] * a1;
-                cvt2(v.w, a0, a1); d += q[i * 8 + 6] * a0 + q[i * 8 + 7] * a1;
+                float a[8];
+                load8(kr + i * 8, 3 * width, a);
+                d += q[i * 8] * a[0] + q[i * 8 + 1] * a[1];
+                d += q[i * 8 + 2] * a[2] + q[i * 8 + 3] * a[3];
+                d += q[i * 8 + 4] * a[4] + q[i * 8 + 5] * a[5];
+                d += q[i * 8 + 6] * a[6] + q[i * 8 + 7] * a[7];
             }
             d *= 0.125f;
         }
@@ -989,15 +1114,15 @@ attention_cls_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
         if (j < L) {
             const float pj = __expf(sc[t] - m);
             sum += pj;
-            const uint4* vr = reinterpret_cast<const uint4*>(base + (int64_t)j * 3 * width + 2 * width + h * 64);
+            const uint16_t* vr = base + (int64_t)j * rs + 2 * width + h * 64;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const uint4 v = __ldg(vr + i);
-                float a0, a1;
-                cvt2(v.x, a0, a1); o[i * 8] += pj * a0; o[i * 8 + 1] += pj * a1;
-                cvt2(v.y, a0, a1); o[i * 8 + 2] += pj * a0; o[i * 8 + 3] += pj * a1;
-                cvt2(v.z, a0, a1); o[i * 8 + 4] += pj * a0; o[i * 8 + 5] += pj * a1;
-                cvt2(v.w, a0, a1); o[i * 8 + 6] += pj * a0; o[i * 8 + 7] += pj * a1;
+                float a[8];
+                load8(vr + i * 8, 3 * width, a);
+                o[i * 8] += pj * a[0]; o[i * 8 + 1] += pj * a[1];
+                o[i * 8 + 2] += pj * a[2]; o[i * 8 + 3] += pj * a[3];
+                o[i * 8 + 4] += pj * a[4]; o[i * 8 + 5] += pj * a[5];
+                o[i * 8 + 6] += pj * a[6]; o[i * 8 + 7] += pj * a[7];
             }
         }
     }
@@ -1015,8 +1140,14 @@ attention_cls_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
         res[half] = acc / sum;
         __syncwarp();
     }
-    uint16_t* dst = h_cls + b * width + h * 64;
-    if (BF16) {
+    uint16_t* dst = h_cls + b * S * width + h * 64;
+    if (SPLIT) {
+        const __half h0 = __float2half_rn(res[0]), h1 = __float2half_rn(res[1]);
+        dst[lane] = __half_as_ushort(h0);
+        dst[32 + lane] = __half_as_ushort(h1);
+        dst[width + lane] = __half_as_ushort(__float2half_rn(res[0] - __half2float(h0)));
+        dst[width + 32 + lane] = __half_as_ushort(__float2half_rn(res[1] - __half2float(h1)));
+    } else if (BF16) {
         dst[lane] = __bfloat16_as_ushort(__float2bfloat16_rn(res[0]));
         dst[32 + lane] = __bfloat16_as_ushort(__float2bfloat16_rn(res[1]));
     } else {
@@ -1187,7 +1318,7 @@ static size_t rup(size_t x) { return (x + 1023) / 1024 * 1024; }
 
 static int vit_check(const eoe_vit_weights* w) {
     if (!w || !w->layers_host) return EOE_ERR_ARG;
-    if (w->operand_dtype != EOE_BF16 && w->operand_dtype != EOE_F16) return EOE_ERR_DTYPE;
+    if (w->operand_dtype != EOE_BF16 && w->operand_dtype != EOE_F16 && w->operand_dtype != EOE_F16X2) return EOE_ERR_DTYPE;
     if (w->patch <= 0 || w->resolution % w->patch != 0 || w->patch % 8 != 0) return EOE_ERR_SHAPE;
     if (w->width != w->heads * 64 || w->width % 256 != 0 || w->width > 1024) return EOE_ERR_SHAPE;
     if ((3 * w->patch * w->patch) % 64 != 0 || w->embed_dim > 1024 || w->embed_dim % 4 != 0 || w->width % 2 != 0) return EOE_ERR_SHAPE;
@@ -1203,6 +1334,11 @@ static int vit_check(const eoe_vit_weights* w) {
         folded += have == 6;
     }
     if (folded != 0 && folded != w->n_layers) return EOE_ERR_ARG;   // every layer or none
+    if (w->operand_dtype == EOE_F16X2) {
+        // split fp16 operands: LayerNorm-folded path only (width <= 768), and the two tcgen05 attention shapes
+        if (folded != w->n_layers || w->width > 128 * gemm::MAX_NCH) return EOE_ERR_ARG;
+        if (g * g + 1 != 197 && !(g * g + 1 <= 64 && w->heads % 2 == 0)) return EOE_ERR_SHAPE;
+    }
     for (int i = 0; i < w->n_layers; ++i) {                         // epilogue parameter vectors travel by 16-byte cp.async
         const eoe_vit_layer& l = w->layers_host[i];
         const void* v[] = {l.in_proj_b, l.out_proj_b, l.c_fc_b, l.c_proj_b, l.in_proj_c1, l.in_proj_c2, l.c_fc_c1, l.c_fc_c2};
@@ -1221,28 +1357,29 @@ static VitLayout vit_layout(const eoe_vit_weights* w, int64_t B) {
     // +256 rows of slack: TMA boxes of the last M tile may start below M but never beyond the allocation
     VitLayout l;
     size_t o = 0;
-    l.patches = o; o += rup((size_t)(B * g2 + 256) * 3 * w->patch * w->patch * 2);
+    const size_t eb = w->operand_dtype == EOE_F16X2 ? 4 : 2;   // bytes per stored operand element (split: hi + lo)
+    l.patches = o; o += rup((size_t)(B * g2 + 256) * 3 * w->patch * w->patch * eb);
     l.x = o; o += rup((size_t)(B * L + 256) * W * 4);
-    l.h = o; o += rup((size_t)(B * L + 256) * W * 2);
-    l.qkv = o; o += rup((size_t)(B * L + 256) * 3 * W * 2);
-    l.u = o; o += rup((size_t)(B * L + 256) * 4 * W * 2);
+    l.h = o; o += rup((size_t)(B * L + 256) * W * eb);
+    l.qkv = o; o += rup((size_t)(B * L + 256) * 3 * W * eb);
+    l.u = o; o += rup((size_t)(B * L + 256) * 4 * W * eb);
     l.feats = o; o += rup((size_t)B * w->embed_dim * 4);
     l.x_cls = o; o += rup((size_t)B * W * 4);                  // last block, class-token rows only
-    l.h_cls = o; o += rup((size_t)(B + 256) * W * 2);
-    l.u_cls = o; o += rup((size_t)(B + 256) * 4 * W * 2);
+    l.h_cls = o; o += rup((size_t)(B + 256) * W * eb);
+    l.u_cls = o; o += rup((size_t)(B + 256) * 4 * W * eb);
     l.xb = o; l.stats = o; l.stats2 = o; l.shift = o;
     if (vit_fused_ln(w)) {
-        o += rup((size_t)(B * L + 256) * W * 2);
+        o += rup((size_t)(B * L + 256) * W * eb);
         l.stats = o; o += rup((size_t)(B * L) * (W / 128) * sizeof(float2));
         l.stats2 = o; o += rup((size_t)(B * L) * (W / 128) * sizeof(float2));
         l.shift = o; o += rup((size_t)(B * L + 256) * sizeof(float));
     }
     l.xb_cls = o; l.stats_cls = o; l.shift_cls = o; l.q_cls = o;
     if (vit_fused_ln(w)) {
-        l.xb_cls = o; o += rup((size_t)(B + 256) * W * 2);
+        l.xb_cls = o; o += rup((size_t)(B + 256) * W * eb);
         l.stats_cls = o; o += rup((size_t)(B + 256) * (W / 128) * sizeof(float2));
         l.shift_cls = o; o += rup((size_t)(B + 256) * sizeof(float));
-        l.q_cls = o; o += rup((size_t)(B + 256) * W * 2);
+        l.q_cls = o; o += rup((size_t)(B + 256) * W * eb);
     }
     l.total = o;
     return l;
@@ -1303,37 +1440,40 @@ extern "C" int eoe_vit_plan_create(const eoe_vit_weights* w, int64_t max_batch, 
     p->tm_inf = new CUtensorMap[w->n_layers];
     p->tm_fcf = new CUtensorMap[w->n_layers];
     p->tm_projs = new CUtensorMap[w->n_layers];
-    rc = make_tmap(&p->tm_patches, p->patches, max_batch * p->g2, p->kpatch, gemm::CTA_M, dt);
-    if (!rc) rc = make_tmap(&p->tm_h, p->h, rows, W, gemm::CTA_M, dt);
-    if (!rc) rc = make_tmap(&p->tm_u, p->u, rows, 4 * W, gemm::CTA_M, dt);
-    if (!rc) rc = make_tmap(&p->tm_conv, w->conv1_w, W, p->kpatch, gemm::CTA_NB, dt);
+    // split fp16 operands (EOE_F16X2): every 16-bit matrix [rows, C] is [rows, S * C] = [hi | lo]
+    const int S = dt == EOE_F16X2 ? 2 : 1;
+    rc = make_tmap(&p->tm_patches, p->patches, max_batch * p->g2, S * p->kpatch, gemm::CTA_M, dt);
+    if (!rc) rc = make_tmap(&p->tm_h, p->h, rows, S * W, gemm::CTA_M, dt);
+    if (!rc) rc = make_tmap(&p->tm_u, p->u, rows, S * 4 * W, gemm::CTA_M, dt);
+    if (!rc) rc = make_tmap(&p->tm_conv, w->conv1_w, W, S * p->kpatch, gemm::CTA_NB, dt);
     // attention maps: 128-token boxes for the L = 197 kernel, 64-token boxes (loads and stores) for the L <= 64 kernel
-    if (!rc) rc = make_tmap_tokens(&p->tm_qkv, p->qkv, max_batch, p->L, 3 * W, p->L <= 64 ? 64 : 128, dt);
-    if (!rc && p->L <= 64) rc = make_tmap_tokens(&p->tm_ho128, p->h, max_batch, p->L, W, 64, dt);
-    if (!rc && p->L == 197) rc = make_tmap_tokens(&p->tm_ho128, p->h, max_batch, p->L, W, 128, dt);
-    if (!rc && p->L == 197) rc = make_tmap_tokens(&p->tm_ho72, p->h, max_batch, p->L, W, 72, dt);
-    if (!rc) rc = make_tmap(&p->tm_hc, p->h_cls, max_batch, W, gemm::CTA_M, dt);
-    if (!rc) rc = make_tmap(&p->tm_qkv_st, p->qkv, rows, 3 * W, 32, dt);
-    if (!rc) rc = make_tmap(&p->tm_u_st, p->u, rows, 4 * W, 32, dt);
-    if (!rc) rc = make_tmap(&p->tm_uc_st, p->u_cls, max_batch, 4 * W, 32, dt);
-    if (!rc) rc = make_tmap(&p->tm_uc, p->u_cls, max_batch, 4 * W, gemm::CTA_M, dt);
+    if (!rc) rc = make_tmap_tokens(&p->tm_qkv, p->qkv, max_batch, p->L, S * 3 * W, p->L <= 64 ? 64 : 128, dt);
+    if (!rc && p->L <= 64) rc = make_tmap_tokens(&p->tm_ho128, p->h, max_batch, p->L, S * W, 64, dt);
+    if (!rc && p->L == 197) rc = make_tmap_tokens(&p->tm_ho128, p->h, max_batch, p->L, S * W, 128, dt);
+    if (!rc && p->L == 197) rc = make_tmap_tokens(&p->tm_ho72, p->h, max_batch, p->L, S * W, 72, dt);
+    if (!rc) rc = make_tmap(&p->tm_hc, p->h_cls, max_batch, S * W, gemm::CTA_M, dt);
+    if (!rc) rc = make_tmap(&p->tm_qkv_st, p->qkv, rows, S * 3 * W, 32, dt);
+    if (!rc) rc = make_tmap(&p->tm_u_st, p->u, rows, S * 4 * W, 32, dt);
+    if (!rc) rc = make_tmap(&p->tm_uc_st, p->u_cls, max_batch, S * 4 * W, 32, dt);
+    if (!rc) rc = make_tmap(&p->tm_uc, p->u_cls, max_batch, S * 4 * W, gemm::CTA_M, dt);
     for (int i = 0; i < w->n_layers && !rc; ++i) {
         const eoe_vit_layer& l = p->layers[i];
-        rc = make_tmap(&p->tm_in[i], l.in_proj_w, 3 * W, W, gemm::CTA_NB, dt);
-        if (!rc) rc = make_tmap(&p->tm_out[i], l.out_proj_w, W, W, gemm::CTA_NB, dt);
-        if (!rc) rc = make_tmap(&p->tm_fc[i], l.c_fc_w, 4 * W, W, gemm::CTA_NB, dt);
-        if (!rc) rc = make_tmap(&p->tm_proj[i], l.c_proj_w, W, 4 * W, gemm::CTA_NB, dt);
-        if (!rc && p->fused_ln) rc = make_tmap(&p->tm_inf[i], l.in_proj_wf, 3 * W, W, gemm::CTA_NB, dt);
-        if (!rc && p->fused_ln) rc = make_tmap(&p->tm_fcf[i], l.c_fc_wf, 4 * W, W, gemm::CTA_NB, dt);
-        if (!rc && p->fused_ln && l.c_proj_w_div1702) rc = make_tmap(&p->tm_projs[i], l.c_proj_w_div1702, W, 4 * W, gemm::CTA_NB, dt);
+        rc = make_tmap(&p->tm_in[i], l.in_proj_w, 3 * W, S * W, gemm::CTA_NB, dt);
+        if (!rc) rc = make_tmap(&p->tm_out[i], l.out_proj_w, W, S * W, gemm::CTA_NB, dt);
+        if (!rc) rc = make_tmap(&p->tm_fc[i], l.c_fc_w, 4 * W, S * W, gemm::CTA_NB, dt);
+        if (!rc) rc = make_tmap(&p->tm_proj[i], l.c_proj_w, W, S * 4 * W, gemm::CTA_NB, dt);
+        if (!rc && p->fused_ln) rc = make_tmap(&p->tm_inf[i], l.in_proj_wf, 3 * W, S * W, gemm::CTA_NB, dt);
+        if (!rc && p->fused_ln) rc = make_tmap(&p->tm_fcf[i], l.c_fc_wf, 4 * W, S * W, gemm::CTA_NB, dt);
+        if (!rc && p->fused_ln && l.c_proj_w_div1702) rc = make_tmap(&p->tm_projs[i], l.c_proj_w_div1702, W, S * 4 * W, gemm::CTA_NB, dt);
     }
-    if (!rc && p->fused_ln) rc = make_tmap(&p->tm_xb, p->xb, rows, W, gemm::CTA_M, dt);
+    if (!rc && p->fused_ln) rc = make_tmap(&p->tm_xb, p->xb, rows, S * W, gemm::CTA_M, dt);
     if (!rc && p->fused_ln) {
         const eoe_vit_layer& ll = p->layers[w->n_layers - 1];
-        rc = make_tmap(&p->tm_kv_w, (const uint16_t*)ll.in_proj_wf + (size_t)W * W, 2 * W, W, gemm::CTA_NB, dt);
-        if (!rc) rc = make_tmap_ld(&p->tm_kv_st, p->qkv + W, rows, 2 * W, 3 * W, 32, dt);
-        if (!rc) rc = make_tmap(&p->tm_xbc, p->xb_cls, max_batch, W, gemm::CTA_M, dt);
-        if (!rc) rc = make_tmap(&p->tm_qc_st, p->q_cls, max_batch, W, 32, dt);
+        rc = make_tmap(&p->tm_kv_w, (const uint16_t*)ll.in_proj_wf + (size_t)W * S * W, 2 * W, S * W, gemm::CTA_NB, dt);
+        // K;V columns of qkv: [W, 3W) and, split, their lo halves 3W further on -- one window from column W to the row's end
+        if (!rc) rc = make_tmap_ld(&p->tm_kv_st, p->qkv + W, rows, S == 2 ? 5 * W : 2 * W, S * 3 * W, 32, dt);
+        if (!rc) rc = make_tmap(&p->tm_xbc, p->xb_cls, max_batch, S * W, gemm::CTA_M, dt);
+        if (!rc) rc = make_tmap(&p->tm_qc_st, p->q_cls, max_batch, S * W, 32, dt);
     }
     if (rc) { eoe_vit_plan_destroy(p); return rc; }
     *plan_out = p;
@@ -1361,6 +1501,7 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
     cudaStream_t st = (cudaStream_t)stream;
     const eoe_vit_weights& w = p->w;
     const int W = w.width, dt = w.operand_dtype, L = p->L;
+    const bool split = dt == EOE_F16X2;              // split fp16 operands: SPLIT kernel variants, fp16 everywhere else
     const int64_t M = B * L, Mp = B * p->g2;
     int rc;
     if (text && !clip_prompts_ok(K)) return EOE_ERR_SHAPE;      // before any work: not after the whole forward pass
@@ -1370,6 +1511,7 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
         const int64_t total = B * 3 * (int64_t)w.resolution * w.resolution / 8;
         int grid = (int)((total + 255) / 256 < (int64_t)num_sms() * 16 ? (total + 255) / 256 : (int64_t)num_sms() * 16);
         if (dt == EOE_BF16) im2col_kernel<true><<<grid, 256, 0, st>>>(imgs_f32, p->patches, B, w.resolution, w.patch);
+        else if (split) im2col_kernel<false, true><<<grid, 256, 0, st>>>(imgs_f32, p->patches, B, w.resolution, w.patch);
         else im2col_kernel<false><<<grid, 256, 0, st>>>(imgs_f32, p->patches, B, w.resolution, w.patch);
         if ((rc = check_launch("im2col_kernel"))) return rc;
     } else if (geom) {
@@ -1379,7 +1521,7 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
         const int max_rows = (int)(P * geom->scv + 4.0 * fv) + 4;               // source rows one row of patches can touch
         const size_t smem = (size_t)(2 * R + R * geom->ksh + P * geom->ksv) * sizeof(int) + (size_t)max_rows * R * 3;
         if (P > 32 || smem > 200 * 1024) return EOE_ERR_SHAPE;                   // down-scaling beyond ~12x per patch row
-        auto kern = dt == EOE_BF16 ? resize_patchify_kernel<true> : resize_patchify_kernel<false>;
+        auto kern = dt == EOE_BF16 ? resize_patchify_kernel<true> : (split ? resize_patchify_kernel<false, true> : resize_patchify_kernel<false>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_cuda_error(e, "resize_patchify smem attr"); return EOE_ERR_CUDA; }
         kern<<<dim3((unsigned)(R / P), (unsigned)B), 256, smem, st>>>(imgs_u8, p->patches, R, P, *geom, norm, max_rows);
@@ -1390,6 +1532,10 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
         int grid = (int)((total + 255) / 256 < (int64_t)num_sms() * 8 ? (total + 255) / 256 : (int64_t)num_sms() * 8);
 #define EOE_U8(BF, HWC) im2col_u8_kernel<BF, HWC><<<grid, 256, 0, st>>>(imgs_u8, p->patches, B, R, w.patch, norm)
         if (dt == EOE_BF16) { if (layout) EOE_U8(true, true); else EOE_U8(true, false); }
+        else if (split) {
+            if (layout) im2col_u8_kernel<false, true, true><<<grid, 256, 0, st>>>(imgs_u8, p->patches, B, R, w.patch, norm);
+            else im2col_u8_kernel<false, false, true><<<grid, 256, 0, st>>>(imgs_u8, p->patches, B, R, w.patch, norm);
+        }
         else { if (layout) EOE_U8(false, true); else EOE_U8(false, false); }
 #undef EOE_U8
         if ((rc = check_launch("im2col_u8_kernel"))) return rc;
@@ -1408,6 +1554,9 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
 #define EOE_LN_PRE(BF, IT) ln_pre_stats_kernel<BF, IT><<<grid, 256, 0, st>>>( \
         p->x, w.ln_pre_w, w.ln_pre_b, p->xb, p->stats, p->shift, M, W, w.class_embedding, w.positional_embedding, L)
         if (dt == EOE_BF16) { if (W <= 768) EOE_LN_PRE(true, 6); else EOE_LN_PRE(true, 8); }
+        else if (split)
+            ln_pre_stats_kernel<false, 6, true><<<grid, 256, 0, st>>>(p->x, w.ln_pre_w, w.ln_pre_b, p->xb, p->stats, p->shift, M, W,
+                                                                      w.class_embedding, w.positional_embedding, L);
         else { if (W <= 768) EOE_LN_PRE(false, 6); else EOE_LN_PRE(false, 8); }
 #undef EOE_LN_PRE
         if ((rc = check_launch("ln_pre_stats_kernel"))) return rc;
@@ -1435,9 +1584,10 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
             // same accumulation order as the full GEMM: the features do not change by a bit (diagnostics bit 3 = off).
             gemm::Params gkv{M, 2 * W, W, (const float*)l.in_proj_c2 + W, p->qkv + W, (const float*)l.in_proj_c1 + W, 0, st_cur,
                              nullptr, nullptr, p->shift, nullptr};
+            gkv.lo_off = 3 * W;                      // split operands: lo halves of K;V sit 3W columns behind the hi halves
             if ((rc = timed_gemm(p, KIND_QKV, p->tm_xb, p->tm_kv_w, gkv, dt, EOE_EPI_LNFOLD_BIAS, st, &p->tm_kv_st))) return rc;
             gather_cls_rows_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(p->xb, st_cur, p->shift, p->xb_cls, p->stats_cls,
-                                                                            p->shift_cls, B, L, W);
+                                                                            p->shift_cls, B, L, W, split ? 2 * W : W);
             if ((rc = check_launch("gather_cls_rows_kernel"))) return rc;
             gemm::Params gq{B, W, W, l.in_proj_c2, p->q_cls, l.in_proj_c1, 0, p->stats_cls, nullptr, nullptr, p->shift_cls, nullptr};
             if ((rc = timed_gemm(p, KIND_QKV, p->tm_xbc, p->tm_inf[i], gq, dt, EOE_EPI_LNFOLD_BIAS, st, &p->tm_qc_st))) return rc;
@@ -1470,6 +1620,7 @@ static int vit_encode_impl(eoe_vit_plan* p, const float* imgs_f32, const uint8_t
             const unsigned grid = (unsigned)((B * w.heads + 3) / 4);
             const uint16_t* qc = (p->fused_ln && !(g_gemm_debug & 8)) ? p->q_cls : nullptr;
             if (dt == EOE_BF16) attention_cls_kernel<true><<<grid, 128, 0, st>>>(p->qkv, qc, p->x, p->h_cls, p->x_cls, B, L, w.heads);
+            else if (split) attention_cls_kernel<false, true><<<grid, 128, 0, st>>>(p->qkv, qc, p->x, p->h_cls, p->x_cls, B, L, w.heads);
             else attention_cls_kernel<false><<<grid, 128, 0, st>>>(p->qkv, qc, p->x, p->h_cls, p->x_cls, B, L, w.heads);
             if ((rc = check_launch("attention_cls_kernel"))) return rc;
             gemm::Params g2{B, W, W, l.out_proj_b, p->x_cls, nullptr, 0, nullptr, nullptr, nullptr};
@@ -1585,8 +1736,9 @@ extern "C" int eoe_gemm(const void* A, const void* Wt, const float* bias, void* 
     if ((uintptr_t)A % 16 != 0 || (uintptr_t)Wt % 16 != 0 || (uintptr_t)out % 16 != 0 || (uintptr_t)bias % 16 != 0)
         return EOE_ERR_ALIGN;
     CUtensorMap ta, tb;
-    if ((rc = make_tmap(&ta, A, M, K, gemm::CTA_M, operand_dtype))) return rc;
-    if ((rc = make_tmap(&tb, Wt, N, K, gemm::CTA_NB, operand_dtype))) return rc;
+    const int S = operand_dtype == EOE_F16X2 ? 2 : 1;       // split fp16: A [M, 2K], W [N, 2K], 16-bit out [M, 2N]
+    if ((rc = make_tmap(&ta, A, M, S * K, gemm::CTA_M, operand_dtype))) return rc;
+    if ((rc = make_tmap(&tb, Wt, N, S * K, gemm::CTA_NB, operand_dtype))) return rc;
     gemm::Params p{M, N, K, bias, out, aux, aux_i, nullptr, nullptr, nullptr};
     return gemm_launch(ta, tb, p, operand_dtype, epilogue, (cudaStream_t)stream);
 }
@@ -1608,8 +1760,9 @@ extern "C" int eoe_gemm_lnfold(const void* A, const void* Wf, const float* c1, c
     if ((uintptr_t)A % 16 != 0 || (uintptr_t)Wf % 16 != 0 || (uintptr_t)out % 16 != 0 || (uintptr_t)stats % 16 != 0 ||
         (uintptr_t)c1 % 16 != 0 || (uintptr_t)c2 % 16 != 0 || (uintptr_t)shift % 16 != 0) return EOE_ERR_ALIGN;
     CUtensorMap ta, tb;
-    if ((rc = make_tmap(&ta, A, M, K, gemm::CTA_M, operand_dtype))) return rc;
-    if ((rc = make_tmap(&tb, Wf, N, K, gemm::CTA_NB, operand_dtype))) return rc;
+    const int S = operand_dtype == EOE_F16X2 ? 2 : 1;
+    if ((rc = make_tmap(&ta, A, M, S * K, gemm::CTA_M, operand_dtype))) return rc;
+    if ((rc = make_tmap(&tb, Wf, N, S * K, gemm::CTA_NB, operand_dtype))) return rc;
     gemm::Params p{M, N, K, c2, out, c1, 0, reinterpret_cast<const float2*>(stats), nullptr, nullptr, shift, nullptr};
     return gemm_launch(ta, tb, p, operand_dtype,
                        quick_gelu == 2 ? EOE_EPI_LNFOLD_QUICKGELU_X1702 : (quick_gelu ? EOE_EPI_LNFOLD_QUICKGELU : EOE_EPI_LNFOLD_BIAS),
@@ -1628,8 +1781,9 @@ extern "C" int eoe_gemm_residual_stats(const void* A, const void* Wt, const floa
     if ((uintptr_t)A % 16 != 0 || (uintptr_t)Wt % 16 != 0 || (uintptr_t)x % 16 != 0 || (uintptr_t)xb_out % 8 != 0 || (uintptr_t)bias % 16 != 0 ||
         (uintptr_t)stats_out % 8 != 0) return EOE_ERR_ALIGN;
     CUtensorMap ta, tb;
-    if ((rc = make_tmap(&ta, A, M, K, gemm::CTA_M, operand_dtype))) return rc;
-    if ((rc = make_tmap(&tb, Wt, N, K, gemm::CTA_NB, operand_dtype))) return rc;
+    const int S = operand_dtype == EOE_F16X2 ? 2 : 1;
+    if ((rc = make_tmap(&ta, A, M, S * K, gemm::CTA_M, operand_dtype))) return rc;
+    if ((rc = make_tmap(&tb, Wt, N, S * K, gemm::CTA_NB, operand_dtype))) return rc;
     gemm::Params p{M, N, K, bias, x, nullptr, 0, reinterpret_cast<const float2*>(stats_in), reinterpret_cast<float2*>(stats_out),
                    reinterpret_cast<uint16_t*>(xb_out), nullptr, shift_out};
     return gemm_launch(ta, tb, p, operand_dtype, EOE_EPI_RESIDUAL_STATS, (cudaStream_t)stream);
@@ -1639,7 +1793,7 @@ extern "C" int eoe_vit_fold_layernorm(const float* w_f32, const float* ln_w, con
                                       int64_t N, int64_t K, int operand_dtype, void* w_folded_out, float* c1_out,
                                       float* c2_out, void* stream) {
     if (!w_f32 || !ln_w || !ln_b || !w_folded_out || !c1_out || !c2_out || N <= 0 || K <= 0) return EOE_ERR_ARG;
-    if (operand_dtype != EOE_BF16 && operand_dtype != EOE_F16) return EOE_ERR_DTYPE;
+    if (operand_dtype != EOE_BF16 && operand_dtype != EOE_F16 && operand_dtype != EOE_F16X2) return EOE_ERR_DTYPE;
     if (K % 4 != 0) return EOE_ERR_SHAPE;
     if ((uintptr_t)w_f32 % 16 != 0 || (uintptr_t)ln_w % 16 != 0 || (uintptr_t)ln_b % 16 != 0 || (uintptr_t)w_folded_out % 8 != 0)
         return EOE_ERR_ALIGN;
@@ -1647,6 +1801,8 @@ extern "C" int eoe_vit_fold_layernorm(const float* w_f32, const float* ln_w, con
     cudaStream_t st = (cudaStream_t)stream;
     if (operand_dtype == EOE_BF16)
         fold_ln_kernel<true><<<grid, 256, 0, st>>>(w_f32, ln_w, ln_b, bias, N, K, (uint16_t*)w_folded_out, c1_out, c2_out);
+    else if (operand_dtype == EOE_F16X2)
+        fold_ln_kernel<false, true><<<grid, 256, 0, st>>>(w_f32, ln_w, ln_b, bias, N, K, (uint16_t*)w_folded_out, c1_out, c2_out);
     else
         fold_ln_kernel<false><<<grid, 256, 0, st>>>(w_f32, ln_w, ln_b, bias, N, K, (uint16_t*)w_folded_out, c1_out, c2_out);
     return check_launch("fold_ln_kernel");

@@ -29,10 +29,18 @@ class ClipImageEncoder(nn.Module):
                  input_std=(0.26862954, 0.26130258, 0.27577711)):
         """fold_layernorm: fold ln_1 / ln_2 into the QKV / c_fc GEMMs (eoe_vit_fold_layernorm; DESIGN.md "LayerNorm
         fold") instead of launching stand-alone LayerNorm kernels.  Same math (fp32 statistics of the fp32 residual
-        stream); the 16-bit rounding point moves from LN(x) to x and to W*ln_w."""
+        stream); the 16-bit rounding point moves from LN(x) to x and to W*ln_w.
+
+        operand_dtype: torch.float16 (default; the reference's own GPU dtype), torch.bfloat16, or "f16x2" -- the PRECISE
+        mode (EOE_F16X2): every stored 16-bit tensor is an fp16 (hi, lo) pair and products are hi*hi + lo*hi + hi*lo in
+        fp32 accumulators: 3x the tensor work, and end-to-end scores within 1e-3 relative of the reference's fp32 scores
+        on every image (tests/test_gpu_encoder.py::test_end_to_end_scores)."""
         super().__init__()
+        self.split = operand_dtype in (L.F16X2, "split")
+        if self.split:
+            operand_dtype = torch.float16
         if operand_dtype not in (torch.bfloat16, torch.float16):
-            raise L.EoeError("operand_dtype must be torch.bfloat16 or torch.float16")
+            raise L.EoeError('operand_dtype must be torch.bfloat16, torch.float16 or "f16x2"')
         sd = _strip(state_dict)
         dev = torch.device(device)
         if dev.type != "cuda":
@@ -49,6 +57,9 @@ class ClipImageEncoder(nn.Module):
         self.max_batch = int(max_batch)
         self.device_ = dev
         self.fold_layernorm = bool(fold_layernorm) and self.width <= 768      # eoe_gemm_lnfold: K <= 768
+        if self.split and not self.fold_layernorm:
+            raise L.EoeError('operand_dtype "f16x2" needs the LayerNorm-folded path (fold_layernorm=True, width <= 768)')
+        self._code = L.EOE_F16X2 if self.split else L.DTYPE_CODE[operand_dtype]
         # uint8 inputs get ToTensor + Normalize fused into the patchify kernel; defaults are CLIP's constants
         # (clip_official/clip/clip.py:64)
         self._mean = (C.c_float * 3)(*[float(v) for v in input_mean])
@@ -58,13 +69,17 @@ class ClipImageEncoder(nn.Module):
             return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
         def op(t):
-            return t.detach().to(device=dev, dtype=torch.float32).to(operand_dtype).contiguous()
+            t32 = t.detach().to(device=dev, dtype=torch.float32)
+            if self.split:                        # [N, 2K] = [hi | lo], lo = rn(x - hi)
+                hi = t32.to(torch.float16)
+                return torch.cat([hi, (t32 - hi.float()).to(torch.float16)], dim=1).contiguous()
+            return t32.to(operand_dtype).contiguous()
 
         # device-resident parameters in kernel layout (buffers so .to()/state_dict do not disturb pointers)
         self._keep = []
         w = L.VitWeights()
         w.patch, w.resolution, w.width, w.heads = self.patch, self.resolution, self.width, self.heads
-        w.n_layers, w.embed_dim, w.operand_dtype = self.n_layers, self.embed_dim, L.DTYPE_CODE[operand_dtype]
+        w.n_layers, w.embed_dim, w.operand_dtype = self.n_layers, self.embed_dim, self._code
 
         def put(t):
             self._keep.append(t)
@@ -111,11 +126,11 @@ class ClipImageEncoder(nn.Module):
     def _fold(self, w32, ln_w_ptr, ln_b_ptr, bias_ptr, put):
         """eoe_vit_fold_layernorm on the fp32 master weights -> device pointers (folded W, c1, c2)."""
         N, K = w32.shape
-        wf = torch.empty(N, K, dtype=self.operand_dtype, device=w32.device)
+        wf = torch.empty(N, (2 if self.split else 1) * K, dtype=self.operand_dtype, device=w32.device)
         c1 = torch.empty(N, dtype=torch.float32, device=w32.device)
         c2 = torch.empty(N, dtype=torch.float32, device=w32.device)
         L.check(L.lib().eoe_vit_fold_layernorm(L.ptr(w32), C.c_void_p(ln_w_ptr), C.c_void_p(ln_b_ptr), C.c_void_p(bias_ptr),
-                                               N, K, L.DTYPE_CODE[self.operand_dtype], L.ptr(wf), L.ptr(c1), L.ptr(c2),
+                                               N, K, self._code, L.ptr(wf), L.ptr(c1), L.ptr(c2),
                                                L.stream_ptr(w32.device)), "eoe_vit_fold_layernorm")
         torch.cuda.current_stream(w32.device).synchronize()      # w32 is a temporary
         return put(wf), put(c1), put(c2)
@@ -209,54 +224,76 @@ class ClipImageEncoder(nn.Module):
 
 
 # thin functional wrappers over the exported building blocks (parity-tested one by one)
-def gemm(A, W, bias=None, epilogue=L.EOE_EPI_BIAS, out=None, aux=None, aux_i=0):
+def split_f16(t):
+    """[rows, C] fp32 -> [rows, 2C] fp16 = [hi | lo], the EOE_F16X2 storage of a matrix; join_f16 is its inverse (fp32)."""
+    t32 = t.to(torch.float32)
+    hi = t32.to(torch.float16)
+    return torch.cat([hi, (t32 - hi.float()).to(torch.float16)], dim=1).contiguous()
+
+
+def join_f16(t):
+    C2 = t.shape[1] // 2
+    return t[:, :C2].float() + t[:, C2:].float()
+
+
+def gemm(A, W, bias=None, epilogue=L.EOE_EPI_BIAS, out=None, aux=None, aux_i=0, split=False):
+    """split=True: A [M, 2K], W [N, 2K] and 16-bit outputs [M, 2N] are fp16 (hi | lo) pairs (EOE_F16X2)."""
     L.require_cuda(A, W)
     M, K = A.shape
     N = W.shape[0]
+    if split:
+        K //= 2
     if out is None:
-        out = torch.empty(M, N, dtype=A.dtype, device=A.device)
-    L.check(L.lib().eoe_gemm(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(out), M, N, K, L.DTYPE_CODE[A.dtype], epilogue,
+        out = torch.empty(M, (2 if split else 1) * N, dtype=A.dtype, device=A.device)
+    L.check(L.lib().eoe_gemm(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(out), M, N, K, L.EOE_F16X2 if split else L.DTYPE_CODE[A.dtype], epilogue,
                              L.ptr(aux), int(aux_i), L.stream_ptr(A.device)), "eoe_gemm")
     return out
 
 
 def fold_layernorm(w32, ln_w, ln_b, bias, operand_dtype=torch.bfloat16):
-    """(W*ln_w rounded to operand dtype, c1, c2) of eoe_vit_fold_layernorm."""
+    """(W*ln_w rounded to operand dtype, c1, c2) of eoe_vit_fold_layernorm; operand_dtype "f16x2": W*ln_w as [N, 2K] pairs."""
     L.require_cuda(w32, ln_w, ln_b)
     N, K = w32.shape
-    wf = torch.empty(N, K, dtype=operand_dtype, device=w32.device)
+    split = operand_dtype == L.F16X2
+    wf = torch.empty(N, (2 if split else 1) * K, dtype=torch.float16 if split else operand_dtype, device=w32.device)
     c1 = torch.empty(N, dtype=torch.float32, device=w32.device)
     c2 = torch.empty(N, dtype=torch.float32, device=w32.device)
     L.check(L.lib().eoe_vit_fold_layernorm(L.ptr(w32), L.ptr(ln_w), L.ptr(ln_b), L.ptr(bias), N, K,
-                                           L.DTYPE_CODE[operand_dtype], L.ptr(wf), L.ptr(c1), L.ptr(c2),
+                                           L.EOE_F16X2 if split else L.DTYPE_CODE[operand_dtype], L.ptr(wf), L.ptr(c1), L.ptr(c2),
                                            L.stream_ptr(w32.device)), "eoe_vit_fold_layernorm")
     return wf, c1, c2
 
 
-def gemm_lnfold(A, Wf, c1, c2, stats, quick_gelu=False, shift=None):
+def gemm_lnfold(A, Wf, c1, c2, stats, quick_gelu=False, shift=None, split=False):
     """rstd*(A @ Wf^T - (mean - shift)*c1) + c2 with (mean, rstd) from the per-row chunk sums `stats` [M, K/128, 2];
     `shift` [M] is what was subtracted from the rows of A (None: nothing)."""
     L.require_cuda(A, Wf, stats)
     M, K = A.shape
     N = Wf.shape[0]
-    out = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    if split:
+        K //= 2
+    out = torch.empty(M, (2 if split else 1) * N, dtype=A.dtype, device=A.device)
     # quick_gelu: False / True, or 2 for 1.702 * QuickGELU (EOE_EPI_LNFOLD_QUICKGELU_X1702)
     L.check(L.lib().eoe_gemm_lnfold(L.ptr(A), L.ptr(Wf), L.ptr(c1), L.ptr(c2), L.ptr(stats), L.ptr(shift), L.ptr(out), M, N, K,
-                                    L.DTYPE_CODE[A.dtype], int(quick_gelu), L.stream_ptr(A.device)), "eoe_gemm_lnfold")
+                                    L.EOE_F16X2 if split else L.DTYPE_CODE[A.dtype], int(quick_gelu), L.stream_ptr(A.device)),
+            "eoe_gemm_lnfold")
     return out
 
 
-def gemm_residual_stats(A, W, bias, x, stats_in=None):
+def gemm_residual_stats(A, W, bias, x, stats_in=None, split=False):
     """x += A @ W^T + bias in place; returns (xb, stats, shift): stats [M, N/128, 2] chunk sums of the updated x, shift [M] =
     row means of x BEFORE the update (from `stats_in`, the previous sums; None: zeros), xb = (x - shift) rounded to A.dtype."""
     L.require_cuda(A, W, x)
     M, K = A.shape
     N = W.shape[0]
-    xb = torch.empty(M, N, dtype=A.dtype, device=A.device)
+    if split:
+        K //= 2
+    xb = torch.empty(M, (2 if split else 1) * N, dtype=A.dtype, device=A.device)
     stats = torch.empty(M, N // 128, 2, dtype=torch.float32, device=A.device)
     shift = torch.empty(M, dtype=torch.float32, device=A.device)
     L.check(L.lib().eoe_gemm_residual_stats(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(stats_in), L.ptr(x), L.ptr(xb), L.ptr(stats),
-                                            L.ptr(shift), M, N, K, L.DTYPE_CODE[A.dtype], L.stream_ptr(A.device)),
+                                            L.ptr(shift), M, N, K, L.EOE_F16X2 if split else L.DTYPE_CODE[A.dtype],
+                                            L.stream_ptr(A.device)),
             "eoe_gemm_residual_stats")
     return xb, stats, shift
 
@@ -264,16 +301,18 @@ def gemm_residual_stats(A, W, bias, x, stats_in=None):
 def layernorm(x, w, b, out_dtype=torch.bfloat16):
     L.require_cuda(x)
     M, width = x.shape
-    y = torch.empty(M, width, dtype=out_dtype, device=x.device)
-    L.check(L.lib().eoe_layernorm(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.DTYPE_CODE[out_dtype], M, width,
+    split = out_dtype == L.F16X2
+    y = torch.empty(M, (2 if split else 1) * width, dtype=torch.float16 if split else out_dtype, device=x.device)
+    L.check(L.lib().eoe_layernorm(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.EOE_F16X2 if split else L.DTYPE_CODE[out_dtype], M, width,
                                   L.stream_ptr(x.device)), "eoe_layernorm")
     return y
 
 
-def attention(qkv, B, Lseq, heads):
+def attention(qkv, B, Lseq, heads, split=False):
+    """split=True: qkv [B*L, 6*width] = [q k v | lo halves] and the output [B*L, 2*width] are fp16 (hi | lo) pairs."""
     L.require_cuda(qkv)
-    width = qkv.shape[1] // 3
-    out = torch.empty(B * Lseq, width, dtype=qkv.dtype, device=qkv.device)
-    L.check(L.lib().eoe_attention(L.ptr(qkv), L.ptr(out), B, Lseq, heads, L.DTYPE_CODE[qkv.dtype],
+    width = qkv.shape[1] // (6 if split else 3)
+    out = torch.empty(B * Lseq, (2 if split else 1) * width, dtype=qkv.dtype, device=qkv.device)
+    L.check(L.lib().eoe_attention(L.ptr(qkv), L.ptr(out), B, Lseq, heads, L.EOE_F16X2 if split else L.DTYPE_CODE[qkv.dtype],
                                   L.stream_ptr(qkv.device)), "eoe_attention")
     return out

@@ -28,9 +28,17 @@
 extern "C" {
 #endif
 
-#define EOE_ABI_VERSION 5
+#define EOE_ABI_VERSION 6
 
-enum { EOE_F32 = 0, EOE_F16 = 1, EOE_BF16 = 2 };
+enum { EOE_F32 = 0, EOE_F16 = 1, EOE_BF16 = 2,
+       /* Encoder operand dtype only ("split fp16", the precise mode): every 16-bit matrix [rows, C] is stored as
+        * [rows, 2C] = [hi | lo] with hi = rn_fp16(x), lo = rn_fp16(x - hi), and every product of two stored tensors is
+        * evaluated as hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (3x the tensor work, ~2^-21 relative operand
+        * error instead of 2^-12).  This is the mode whose end-to-end SCORES are within 1e-3 relative of the fp32
+        * reference on every image (clip.py:66-79 on top of model.py:219-236); softmax probabilities stay single fp16.
+        * Accepted by eoe_vit_* (LayerNorm-folded weights required), eoe_gemm*, eoe_vit_fold_layernorm, eoe_layernorm
+        * (out_dtype) and eoe_attention (L == 197, or L <= 64 with an even head count). */
+       EOE_F16X2 = 3 };
 
 enum {
     EOE_OK = 0,
@@ -196,7 +204,7 @@ typedef struct eoe_vit_weights {
     int32_t heads;            /* 12 (head dim must be 64)                                           */
     int32_t n_layers;         /* 12                                                                 */
     int32_t embed_dim;        /* 512                                                                */
-    int32_t operand_dtype;    /* EOE_BF16 or EOE_F16: dtype of all *_w matrices below               */
+    int32_t operand_dtype;    /* EOE_BF16, EOE_F16 or EOE_F16X2 (every *_w matrix [N, K] is then [N, 2K] = [hi | lo]) */
     int32_t reserved;
     const void*  conv1_w;     /* [width, 3*patch*patch]  (visual.conv1.weight flattened)            */
     const float* class_embedding;       /* [width]                                                  */
