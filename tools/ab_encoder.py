@@ -42,7 +42,10 @@ def main():
         encs = {n: base for n in names}
     else:
         names = a.variants.split(",")
-        encs = {n: ClipImageEncoder(sd, device=dev, max_batch=a.batch, fold_layernorm=(n == "fold")) for n in names}
+        # variant names: fold / nofold (LayerNorm fold on / off, fp16) or an operand dtype: f16 / bf16 / f16x2 (precise mode)
+        ops = {"f16": torch.float16, "bf16": torch.bfloat16, "f16x2": "f16x2"}
+        encs = {n: ClipImageEncoder(sd, device=dev, max_batch=a.batch, fold_layernorm=(n != "nofold"),
+                                    operand_dtype=ops.get(n, torch.float16)) for n in names}
     imgs = [torch.randn(a.batch, 3, 224, 224, device=dev) for _ in range(2)]
     text = torch.nn.functional.normalize(torch.randn(a.prompts, 512, device=dev), dim=-1)
     out = torch.empty(a.batch, device=dev)
