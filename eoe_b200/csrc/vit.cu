@@ -1156,6 +1156,101 @@ attention_cls_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restric
     }
 }
 
+// Causal attention over split fp16 operands (EOE_F16X2), text tower only (model.py:324-331: key j is visible to query i
+// iff j <= i): 2 310 rows once per class, so plain fp32 CUDA-core arithmetic on hi + lo values, one warp per
+// (prompt, head, query row), lanes own keys l, l + 32, ... -- no 16-bit rounding anywhere inside (P stays fp32).
+// qkv [B*L, 6*width] = [q k v | lo halves], out [B*L, 2*width] = [hi | lo].
+__global__ void __launch_bounds__(128)
+attention_causal_split_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int64_t B, int L, int heads) {
+    __shared__ float s_red[4][32][33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t item = (int64_t)blockIdx.x * 4 + wib;
+    if (item >= B * heads * L) return;
+    const int width = heads * 64;
+    const int i = (int)(item % L);
+    const int h = (int)((item / L) % heads);
+    const int64_t b = item / ((int64_t)L * heads);
+    const int64_t rs = 6 * (int64_t)width;
+    const uint16_t* base = qkv + b * L * rs;
+    auto load8 = [&](const uint16_t* src, float* f) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + 3 * width));
+        const uint32_t vw[4] = {v.x, v.y, v.z, v.w}, uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&vw[e]));
+            const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&uw[e]));
+            f[2 * e] = a.x + c.x;
+            f[2 * e + 1] = a.y + c.y;
+        }
+    };
+    float q[64];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) load8(base + (int64_t)i * rs + h * 64 + c * 8, q + c * 8);
+    constexpr int MAXK = 7;                         // keys per lane: L <= 224
+    float sc[MAXK];
+    float m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < MAXK; ++t) {
+        const int j = t * 32 + lane;
+        float d = -INFINITY;
+        if (j <= i) {
+            const uint16_t* kr = base + (int64_t)j * rs + width + h * 64;
+            d = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float a[8];
+                load8(kr + c * 8, a);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d = fmaf(q[c * 8 + e], a[e], d);
+            }
+            d *= 0.125f;
+        }
+        sc[t] = d;
+        m = fmaxf(m, d);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    float o[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int t = 0; t < MAXK; ++t) {
+        const int j = t * 32 + lane;
+        if (j <= i) {
+            const float pj = expf(sc[t] - m);
+            sum += pj;
+            const uint16_t* vr = base + (int64_t)j * rs + 2 * width + h * 64;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float a[8];
+                load8(vr + c * 8, a);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[c * 8 + e] = fmaf(pj, a[e], o[c * 8 + e]);
+            }
+        }
+    }
+    sum = warp_sum(sum);
+    float res[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) s_red[wib][lane][c] = o[half * 32 + c];
+        __syncwarp();
+        float acc = 0.f;
+#pragma unroll
+        for (int l2 = 0; l2 < 32; ++l2) acc += s_red[wib][l2][lane];
+        res[half] = acc / sum;
+        __syncwarp();
+    }
+    uint16_t* dst = out + (b * L + i) * 2 * (int64_t)width + h * 64;
+    const __half h0 = __float2half_rn(res[0]), h1 = __float2half_rn(res[1]);
+    dst[lane] = __half_as_ushort(h0);
+    dst[32 + lane] = __half_as_ushort(h1);
+    dst[width + lane] = __half_as_ushort(__float2half_rn(res[0] - __half2float(h0)));
+    dst[width + 32 + lane] = __half_as_ushort(__float2half_rn(res[1] - __half2float(h1)));
+}
+
 // ------------------------------------------------------------------------------------------ tail
 // feats[b] = ln_post(x[b, 0, :]) @ proj   (model.py:231-234), fp32 throughout (it feeds a 100x cosine logit).
 // Block = 4 images x 128 output columns; proj (1.5 MB, L2 resident) is streamed once per 4 images.  Thread
@@ -1824,6 +1919,13 @@ extern "C" int eoe_attention_causal(const void* qkv, void* out, int64_t B, int64
                                     void* stream) {
     if (!qkv || !out) return EOE_ERR_ARG;
     if ((uintptr_t)qkv % 16 != 0) return EOE_ERR_ALIGN;
+    if (operand_dtype == EOE_F16X2) {                // split fp16 pairs: fp32 CUDA-core kernel (the text tower is 2 310 rows)
+        if (B <= 0 || L <= 0 || heads <= 0) return EOE_ERR_ARG;
+        if (L > 224 || B * heads * L > 0x7fffffff) return EOE_ERR_SHAPE;
+        attention_causal_split_kernel<<<(unsigned)((B * heads * L + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+            (const uint16_t*)qkv, (uint16_t*)out, B, (int)L, (int)heads);
+        return check_launch("attention_causal_split_kernel");
+    }
     return attention_dispatch(qkv, out, B, L, heads, operand_dtype, (cudaStream_t)stream, nullptr, nullptr, nullptr, true);
 }
 

@@ -82,8 +82,15 @@ def n_layers_of(sd):
     return len({k.split(".")[2] for k in sd if k.startswith("transformer.resblocks.")})
 
 
-def _r(t, dt):
-    return t if dt is None else t.to(dt).to(torch.float32)
+def _r(t, dt, is_prob=False):
+    if dt is None:
+        return t
+    if dt == "f16x2":          # precise mode (oracle.vit.F16X2): fp16 (hi, lo) pairs; the text tower's attention keeps P in fp32
+        if is_prob:
+            return t
+        hi = t.to(torch.float16).to(torch.float32)
+        return hi + (t - hi).to(torch.float16).to(torch.float32)
+    return t.to(dt).to(torch.float32)
 
 
 @torch.no_grad()
@@ -112,7 +119,7 @@ def encode_text(sd, tokens, operand_dtype=None, heads: int = TEXT_HEADS):
             o = torch.softmax(s, dim=-1) @ v
         else:
             e = torch.exp(s - s.amax(dim=-1, keepdim=True))
-            o = (_r(e, dt) @ v) / e.sum(dim=-1, keepdim=True)
+            o = (_r(e, dt, is_prob=True) @ v) / e.sum(dim=-1, keepdim=True)
         o = _r(o.transpose(1, 2).reshape(n, ctx, width), dt)
         x = x + F.linear(o, _r(w[p + "attn.out_proj.weight"], dt), w[p + "attn.out_proj.bias"])
         h = _r(F.layer_norm(x, (width,), w[p + "ln_2.weight"], w[p + "ln_2.bias"], 1e-5), dt)

@@ -148,3 +148,57 @@ def test_clip_model_has_the_reference_surface():
     assert torch.equal(m.score(imgs, center), ops.clip_score(f, center))
     with pytest.raises(L.EoeError):
         ClipModel(ovit.synth_state_dict(32, seed=3, layers=1), device=DEV, max_batch=2).encode_text(tok)
+
+
+# ---------------------------------------------------------------------------------------------- precise mode (EOE_F16X2)
+@pytest.mark.parametrize("B,L,heads", [(3, 77, 8), (1, 16, 8), (2, 100, 8), (1, 1, 8)])
+def test_attention_causal_split_vs_torch(B, L, heads):
+    """split fp16 pairs in and out, fp32 arithmetic inside (no 16-bit rounding of P): fp32-level agreement with torch fp64"""
+    from eoe_b200 import encoder as E, text_encoder as T
+    W = heads * 64
+    g = torch.Generator(device=DEV).manual_seed(B * L + heads)
+    qkv = E.split_f16(torch.randn(B * L, 3 * W, device=DEV, generator=g))
+    got = T.attention_causal(qkv, B, L, heads, split=True)
+    assert got.shape == (B * L, 2 * W)
+    q, k, v = (t.reshape(B, L, heads, 64).transpose(1, 2) for t in E.join_f16(qkv).double().split(W, dim=-1))
+    mask = torch.full((L, L), float("-inf"), device=DEV, dtype=torch.float64).triu_(1)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8.0 + mask, dim=-1) @ v).transpose(1, 2).reshape(B * L, W)
+    assert ((E.join_f16(got).double() - ref).norm() / ref.norm()).item() < 2e-6
+
+
+def test_text_encoder_split_vs_golden(golden_dir):
+    """precise mode: text features within 2e-5 of the live reference's fp32 features (7.4e-4 with single fp16 operands)
+    and of the precision-matched oracle."""
+    from eoe_b200.text_encoder import ClipTextEncoder
+    from oracle import vit as ovit
+    sd = otext.synth_text_state_dict(seed=gi.TEXT_WEIGHT_SEED)
+    tokens = gi.text_tokens()
+    enc = ClipTextEncoder(sd, device=DEV, operand_dtype="f16x2")
+    feats = enc(tokens.to(DEV)).cpu()
+    gold = torch.from_numpy(np.load(os.path.join(golden_dir, "text.npz"))["features"])
+    assert feats.shape == gold.shape and torch.isfinite(feats).all()
+    emu = otext.encode_text(sd, tokens, operand_dtype=ovit.F16X2)
+    print("SPLIT_TEXT", _rel(feats, gold), _rel(feats, emu), _rel(emu, gold))
+    assert _rel(feats, gold) < 2e-5
+    assert _rel(feats, emu) < 2e-5
+    assert torch.equal(enc(tokens[3:4].to(DEV)).cpu(), feats[3:4])
+
+
+def test_clip_model_precise_mode_scores_from_prompts_to_scores():
+    """Both towers in precise mode, prompts' token ids -> text features -> normalised centre -> fused image scores: every
+    score within 1e-3 relative of the fp32 oracle run end to end (oracle.text + oracle.vit + oracle.heads)."""
+    from eoe_b200.clip_model import ClipModel
+    from oracle import heads as oh, vit as ovit
+    sd = {**ovit.synth_state_dict(32, seed=gi.VIT_WEIGHT_SEED), **otext.synth_text_state_dict(seed=gi.TEXT_WEIGHT_SEED)}
+    m = ClipModel(sd, device=DEV, operand_dtype="f16x2", max_batch=16)
+    imgs = torch.randn(16, 3, 224, 224, generator=torch.Generator().manual_seed(12))
+    tok = gi.text_tokens()
+    t = m.encode_text(tok.to(DEV))
+    center = torch.nn.functional.normalize(t, dim=-1)
+    s = m.score(imgs.to(DEV), center).cpu().numpy().astype(np.float64)
+    t32 = otext.encode_text(sd, tok)
+    c32 = (t32 / t32.norm(dim=-1, keepdim=True)).numpy()
+    want = oh.clip_score(ovit.encode_image(sd, imgs).numpy(), c32).astype(np.float64)
+    rel = np.abs(s - want) / np.abs(want)
+    print("SPLIT_CLIP_MODEL", float(np.median(rel)), float(rel.max()))
+    assert rel.max() <= 1e-3
