@@ -27,8 +27,8 @@ constexpr uint32_t TILE_BYTES = 128 * 128;                    // 128 rows x 64 x
 constexpr uint32_t SMEM_BYTES = 6 * TILE_BYTES + 64 + 1024;   // Q0, Q1, K (2 boxes), V (2 boxes), barriers, alignment
 // SPLIT (operand dtype EOE_F16X2): qkv rows are [q k v | q_lo k_lo v_lo] fp16 pairs and the output rows [hi | lo].  A second
 // set of six tiles holds the lo halves; S = Qhi Khi^T + Qlo Khi^T + Qhi Klo^T and O = P Vhi + P Vlo accumulate in the same
-// TMEM columns (P stays a single fp16: it is the one 16-bit tensor whose rounding does not matter).
-// One CTA per SM (193 KB of shared memory).
+// TMEM columns; the probabilities are an fp16 pair as well (P_lo in its own TMEM columns, O = P_hi V_hi + P_hi V_lo +
+// P_lo V_hi).  One CTA per SM (193 KB of shared memory, all 512 TMEM columns).
 constexpr uint32_t SMEM_BYTES_SPLIT = 12 * TILE_BYTES + 64 + 1024;
 // hi / lo fp16 halves of two values scaled by `s` -> one word each
 __device__ __forceinline__ void split_scaled(uint32_t a, uint32_t b, float s, uint32_t& hi, uint32_t& lo) {
@@ -36,6 +36,8 @@ __device__ __forceinline__ void split_scaled(uint32_t a, uint32_t b, float s, ui
 }
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t O_COL = 128;
+// SPLIT: the whole TMEM of the SM (one CTA per SM): S / P_hi [0, 208), P_lo [256, 360), O [384, 448)
+constexpr uint32_t TMEM_COLS_SPLIT = 512, PLO_COL_SPLIT = 256, O_COL_SPLIT = 384;
 
 __device__ __forceinline__ float fast_exp2(float x) {      // x <= 0 here; MUFU.EX2, flushes denormal results to 0
     float y;
@@ -65,24 +67,30 @@ __device__ __forceinline__ float fast_exp2(float x) {      // x <= 0 here; MUFU.
 #endif
 
 // rare path of the fp16 single-pass softmax: P of chunks < c (columns [16 cc, 16 cc + 16)) times f (warp-collective)
-__device__ __noinline__ void softmax_rescale_stored_p(uint32_t t_lane, int c, float f) {
+// (plo_col != 0: the lo halves of split probabilities, stored plo_col columns further on, are rescaled too; after a rescale
+// the stored pairs are accurate to one fp16 rounding only, like the single-fp16 path)
+__device__ __noinline__ void softmax_rescale_stored_p(uint32_t t_lane, int c, float f, uint32_t plo_col = 0) {
     const __half2 f2 = __float2half2_rn(f);
 #pragma unroll 1
-    for (int cc = 0; cc < c; ++cc) {
-        uint32_t pk[16];
-        ptx::tmem_ld_32x32b_x16(t_lane + cc * 16, pk);
-        ptx::tmem_ld_wait();
+    for (int part = 0; part < (plo_col ? 2 : 1); ++part) {
+#pragma unroll 1
+        for (int cc = 0; cc < c; ++cc) {
+            uint32_t pk[16];
+            ptx::tmem_ld_32x32b_x16(t_lane + part * plo_col + cc * 16, pk);
+            ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            __half2 h = __hmul2(*reinterpret_cast<__half2*>(&pk[j]), f2);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            for (int j = 0; j < 16; ++j) {
+                __half2 h = __hmul2(*reinterpret_cast<__half2*>(&pk[j]), f2);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            ptx::tmem_st_32x32b_x16(t_lane + part * plo_col + cc * 16, pk);
         }
-        ptx::tmem_st_32x32b_x16(t_lane + cc * 16, pk);
     }
     ptx::tmem_st_wait();
 }
 
-template <bool BF16, int L>
+// PLO != 0 (split operands): P is stored as an fp16 (hi, lo) pair, the lo halves PLO columns behind the hi halves.
+template <bool BF16, int L, uint32_t PLO = 0>
 __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
     constexpr int LP = (L + 15) / 16 * 16;
     constexpr int NC = LP / 32;                 // full 32-column chunks; LP % 32 == 16 leaves one half chunk
@@ -131,7 +139,7 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
     constexpr bool RESCALE = !BF16 && ONEPASS;          // fp16, single pass: the reference may have to rise
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        uint32_t pk[16];
+        uint32_t pk[16], pl[PLO ? 16 : 1];
         if (!(ONEPASS && c == 0)) {                     // single pass: chunk 0 is already in registers, chunk 1 in flight
             ptx::tmem_ld_wait();
             if (c + 1 < NC) ptx::tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, r[(c + 1) & 1]);
@@ -143,7 +151,8 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
             const float p0 = (c * 32 + j < L) ? prob(r[c & 1][j]) : 0.f;
             const float p1 = (c * 32 + j + 1 < L) ? prob(r[c & 1][j + 1]) : 0.f;
             c4[(j >> 1) & 3] += p0 + p1;
-            pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
+            if (PLO) gemm::split2(p0, p1, pk[j >> 1], pl[j >> 1]);
+            else pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
         }
         if (RESCALE && c > 0) {
             const bool ovf = (c4[0] + c4[1]) + (c4[2] + c4[3]) >= 32768.0f;
@@ -157,7 +166,7 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
                 ms = new_ms;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) s4[i] *= f;
-                softmax_rescale_stored_p(t_lane, c, f);
+                softmax_rescale_stored_p(t_lane, c, f, PLO);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) c4[i] = 0.f;
 #pragma unroll
@@ -165,7 +174,8 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
                     const float p0 = (c * 32 + j < L) ? prob(r[c & 1][j]) : 0.f;
                     const float p1 = (c * 32 + j + 1 < L) ? prob(r[c & 1][j + 1]) : 0.f;
                     c4[(j >> 1) & 3] += p0 + p1;
-                    pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
+                    if (PLO) gemm::split2(p0, p1, pk[j >> 1], pl[j >> 1]);
+                    else pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
                 }
             }
         }
@@ -174,9 +184,10 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
         // columns [16c, 16c+16) hold scores consumed in rounds <= c; the in-flight load of round c+1 reads
         // columns >= 32(c+1) > 16c+16, so the store cannot clobber unread scores
         ptx::tmem_st_32x32b_x16(t_lane + c * 16, pk);
+        if (PLO) ptx::tmem_st_32x32b_x16(t_lane + PLO + c * 16, reinterpret_cast<const uint32_t(&)[16]>(pl));
     }
     if (LP % 32) {
-        uint32_t pk[8];
+        uint32_t pk[8], pl[PLO ? 8 : 1];
         ptx::tmem_ld_wait();
         float c4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -184,7 +195,8 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
             const float p0 = (NC * 32 + j < L) ? prob(r[NC & 1][j]) : 0.f;
             const float p1 = (NC * 32 + j + 1 < L) ? prob(r[NC & 1][j + 1]) : 0.f;
             c4[(j >> 1) & 3] += p0 + p1;
-            pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
+            if (PLO) gemm::split2(p0, p1, pk[j >> 1], pl[j >> 1]);
+            else pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
         }
         if (RESCALE) {
             const bool ovf = (c4[0] + c4[1]) + (c4[2] + c4[3]) >= 32768.0f;
@@ -198,7 +210,7 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
                 ms = new_ms;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) s4[i] *= f;
-                softmax_rescale_stored_p(t_lane, NC, f);
+                softmax_rescale_stored_p(t_lane, NC, f, PLO);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) c4[i] = 0.f;
 #pragma unroll
@@ -206,13 +218,15 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t t_lane, float sl2) {
                     const float p0 = (NC * 32 + j < L) ? prob(r[NC & 1][j]) : 0.f;
                     const float p1 = (NC * 32 + j + 1 < L) ? prob(r[NC & 1][j + 1]) : 0.f;
                     c4[(j >> 1) & 3] += p0 + p1;
-                    pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
+                    if (PLO) gemm::split2(p0, p1, pk[j >> 1], pl[j >> 1]);
+                    else pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
                 }
             }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) s4[i] += c4[i];
         ptx::tmem_st_32x32b_x8(t_lane + NC * 16, pk);
+        if (PLO) ptx::tmem_st_32x32b_x8(t_lane + PLO + NC * 16, reinterpret_cast<const uint32_t(&)[8]>(pl));
     }
     ptx::tmem_st_wait();
     return 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
@@ -241,7 +255,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     uint64_t* bar_v = bar_q0 + 3;
     uint64_t* bar_mma = bar_q0 + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q0 + 5);
-    constexpr uint32_t o_col = O_COL;
+    constexpr uint32_t o_col = SPLIT ? O_COL_SPLIT : O_COL;
+    constexpr uint32_t tmem_cols = SPLIT ? TMEM_COLS_SPLIT : TMEM_COLS;
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int width = heads * 64;
@@ -255,7 +270,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         ptx::fence_barrier_init();
     }
     if (warp == 0) {
-        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_slot), TMEM_COLS);
+        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_slot), tmem_cols);
         ptx::tmem_relinquish<1>();
     }
     ptx::tc_fence_before();
@@ -340,7 +355,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             }
             float inv_sum = 0.f;
             if (warp_active) {
-                inv_sum = softmax_row_tmem<BF16, L>(t_lane, sl2);
+                inv_sum = softmax_row_tmem<BF16, L, SPLIT ? PLO_COL_SPLIT : 0>(t_lane, sl2);
             }
             ptx::tc_fence_before();
             __syncthreads();                       // P of all rows is in TMEM (and the V tail is zeroed)
@@ -350,12 +365,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 const uint64_t v_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sV));
 #pragma unroll
                 for (int kk = 0; kk < KSTEPS; ++kk)    // 16 keys per step: 8 packed columns of P, 16 rows (2 KB) of V
-                    ptx::umma_f16_ts(tmem + O_COL, tmem + kk * 8, v_desc + (uint64_t)(kk * 2048 >> 4), idesc_o, kk != 0 ? 1u : 0u);
-                if (SPLIT) {
+                    ptx::umma_f16_ts(tmem + o_col, tmem + kk * 8, v_desc + (uint64_t)(kk * 2048 >> 4), idesc_o, kk != 0 ? 1u : 0u);
+                if (SPLIT) {                           // + P_hi V_lo + P_lo V_hi
                     const uint64_t v_lo = ptx::make_smem_desc_sw128(ptx::smem_u32(sV + LO));
 #pragma unroll
                     for (int kk = 0; kk < KSTEPS; ++kk)
-                        ptx::umma_f16_ts(tmem + O_COL, tmem + kk * 8, v_lo + (uint64_t)(kk * 2048 >> 4), idesc_o, 1u);
+                        ptx::umma_f16_ts(tmem + o_col, tmem + kk * 8, v_lo + (uint64_t)(kk * 2048 >> 4), idesc_o, 1u);
+#pragma unroll
+                    for (int kk = 0; kk < KSTEPS; ++kk)
+                        ptx::umma_f16_ts(tmem + o_col, tmem + PLO_COL_SPLIT + kk * 8, v_desc + (uint64_t)(kk * 2048 >> 4), idesc_o, 1u);
                 }
                 ptx::umma_commit(ptx::smem_u32(bar_mma));
             }
@@ -419,7 +437,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     if (tid == 0) ptx::bulk_wait_group_read0();
     if (warp == 0) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<1>(tmem, TMEM_COLS);
+        ptx::tmem_dealloc<1>(tmem, tmem_cols);
     }
 }
 
@@ -440,6 +458,7 @@ namespace tc64 {
 constexpr int THREADS = 128;
 constexpr uint32_t SMEM_BYTES = 3 * TILE_BYTES + 64 + 1024;     // Q, K, V tiles of 128 rows x 128 B, barriers, alignment
 constexpr uint32_t SMEM_BYTES_SPLIT = 6 * TILE_BYTES + 64 + 1024;   // + the lo halves (attn::SMEM_BYTES_SPLIT); two CTAs per SM
+constexpr uint32_t TMEM_COLS_SPLIT = 256, PLO_COL_SPLIT = 128;       // SPLIT: P_lo packed over [128, 192), same block structure
 constexpr uint32_t TMEM_COLS = 128;
 constexpr uint32_t O_COL = 64;
 }  // namespace tc64
@@ -469,7 +488,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         ptx::fence_barrier_init();
     }
     if (warp == 0) {
-        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_slot), tc64::TMEM_COLS);
+        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_slot), SPLIT ? tc64::TMEM_COLS_SPLIT : tc64::TMEM_COLS);
         ptx::tmem_relinquish<1>();
     }
     ptx::tc_fence_before();
@@ -540,7 +559,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             }
             const float ms = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sl2;
             float s4[4] = {0.f, 0.f, 0.f, 0.f};
-            uint32_t pk[32];
+            uint32_t pk[32], pl[SPLIT ? 32 : 1];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 const float p0 = (j < L) ? fast_exp2(fmaf(__uint_as_float(r0[j]), sl2, -ms)) : 0.f;
@@ -548,8 +567,13 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 const float p2 = (32 + j < L) ? fast_exp2(fmaf(__uint_as_float(r1[j]), sl2, -ms)) : 0.f;
                 const float p3 = (33 + j < L) ? fast_exp2(fmaf(__uint_as_float(r1[j + 1]), sl2, -ms)) : 0.f;
                 s4[(j >> 1) & 3] += (p0 + p1) + (p2 + p3);
-                pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
-                pk[16 + (j >> 1)] = gemm::pack2<BF16>(p2, p3);
+                if (SPLIT) {
+                    gemm::split2(p0, p1, pk[j >> 1], pl[j >> 1]);
+                    gemm::split2(p2, p3, pk[16 + (j >> 1)], pl[(SPLIT ? 16 : 0) + (j >> 1)]);
+                } else {
+                    pk[j >> 1] = gemm::pack2<BF16>(p0, p1);
+                    pk[16 + (j >> 1)] = gemm::pack2<BF16>(p2, p3);
+                }
             }
             inv_sum = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
             // P over columns [0, 64): keys 2c, 2c+1 in column c; this row's block at [own / 2, +32), zeros in the other block
@@ -561,6 +585,13 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             ptx::tmem_st_32x32b_x16(t_lane + pcol + 16, reinterpret_cast<const uint32_t(&)[16]>(pk[16]));
             ptx::tmem_st_32x32b_x16(t_lane + zcol, zero);
             ptx::tmem_st_32x32b_x16(t_lane + zcol + 16, zero);
+            if (SPLIT) {                           // the lo halves of P: same block structure, PLO_COL_SPLIT columns further on
+                constexpr uint32_t PL = tc64::PLO_COL_SPLIT;
+                ptx::tmem_st_32x32b_x16(t_lane + PL + pcol, reinterpret_cast<const uint32_t(&)[16]>(pl[0]));
+                ptx::tmem_st_32x32b_x16(t_lane + PL + pcol + 16, reinterpret_cast<const uint32_t(&)[16]>(pl[SPLIT ? 16 : 0]));
+                ptx::tmem_st_32x32b_x16(t_lane + PL + zcol, zero);
+                ptx::tmem_st_32x32b_x16(t_lane + PL + zcol + 16, zero);
+            }
             ptx::tmem_st_wait();
         }
         ptx::tc_fence_before();
@@ -576,6 +607,9 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)
                     ptx::umma_f16_ts(tmem + tc64::O_COL, tmem + kk * 8, v_lo + (uint64_t)(kk * 2048 >> 4), idesc_o, 1u);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)     // + P_lo V_hi
+                    ptx::umma_f16_ts(tmem + tc64::O_COL, tmem + tc64::PLO_COL_SPLIT + kk * 8, v_desc + (uint64_t)(kk * 2048 >> 4), idesc_o, 1u);
             }
             ptx::umma_commit(ptx::smem_u32(bar_mma));
         }
@@ -627,7 +661,7 @@ attention_tc64_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     if (tid == 0) ptx::bulk_wait_group_read0();
     if (warp == 0) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<1>(tmem, tc64::TMEM_COLS);
+        ptx::tmem_dealloc<1>(tmem, SPLIT ? tc64::TMEM_COLS_SPLIT : tc64::TMEM_COLS);
     }
 }
 

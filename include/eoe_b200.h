@@ -35,7 +35,7 @@ enum { EOE_F32 = 0, EOE_F16 = 1, EOE_BF16 = 2,
         * [rows, 2C] = [hi | lo] with hi = rn_fp16(x), lo = rn_fp16(x - hi), and every product of two stored tensors is
         * evaluated as hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (3x the tensor work, ~2^-21 relative operand
         * error instead of 2^-12).  This is the mode whose end-to-end SCORES are within 1e-3 relative of the fp32
-        * reference on every image (clip.py:66-79 on top of model.py:219-236); softmax probabilities stay single fp16.
+        * reference on every image (clip.py:66-79 on top of model.py:219-236); the softmax probabilities are pairs too.
         * Accepted by eoe_vit_* (LayerNorm-folded weights required), eoe_gemm*, eoe_vit_fold_layernorm, eoe_layernorm
         * (out_dtype) and eoe_attention (L == 197, or L <= 64 with an even head count). */
        EOE_F16X2 = 3 };

@@ -91,7 +91,7 @@ _active_points = None          # None = every point; else the subset that is rou
 
 # operand_dtype of the CUDA path's precise mode (include/eoe_b200.h EOE_F16X2): every stored 16-bit tensor is an fp16 pair
 # hi = rn(x), lo = rn(x - hi) -- the value the kernels multiply with is hi + lo (the lo * lo term they drop is 2^-24
-# relative) -- except the softmax probabilities, which stay a single fp16.
+# relative) -- the softmax probabilities included.
 F16X2 = "f16x2"
 
 
@@ -104,7 +104,7 @@ def _r(t, dt, point=None):
     if dt is None or (_active_points is not None and point is not None and point not in _active_points):
         return t
     if dt == F16X2:
-        return t.to(torch.float16).to(torch.float32) if point == "p" else split_round(t)
+        return split_round(t)
     return t.to(dt).to(torch.float32)
 
 

@@ -167,8 +167,8 @@ def test_attention_causal_split_vs_torch(B, L, heads):
 
 
 def test_text_encoder_split_vs_golden(golden_dir):
-    """precise mode: text features within 2e-5 of the live reference's fp32 features (7.4e-4 with single fp16 operands)
-    and of the precision-matched oracle."""
+    """precise mode: text features within 2e-5 of the live reference's fp32 features (measured 8.7e-6; 7.4e-4 with single
+    fp16 operands) and of the precision-matched oracle."""
     from eoe_b200.text_encoder import ClipTextEncoder
     from oracle import vit as ovit
     sd = otext.synth_text_state_dict(seed=gi.TEXT_WEIGHT_SEED)
@@ -201,4 +201,4 @@ def test_clip_model_precise_mode_scores_from_prompts_to_scores():
     want = oh.clip_score(ovit.encode_image(sd, imgs).numpy(), c32).astype(np.float64)
     rel = np.abs(s - want) / np.abs(want)
     print("SPLIT_CLIP_MODEL", float(np.median(rel)), float(rel.max()))
-    assert rel.max() <= 1e-3
+    assert rel.max() <= 2e-4                                  # north_star's bar is 1e-3; measured: median 6e-6, max 1.8e-5

@@ -161,10 +161,11 @@ def test_end_to_end_score_fixture(golden_dir, patch, K):
 
 
 def test_split_operand_emulation_meets_the_score_bar(golden_dir):
-    """The precise mode's emulation (oracle.vit F16X2: fp16 (hi, lo) pairs at every stored 16-bit tensor except the softmax
-    probabilities) against the live reference's fp32 scores, cfg2, 16-image slice: every score within 1e-3 (max ~3e-4),
-    where the single-fp16 emulation has half of them outside -- the CPU statement of what
-    tests/test_gpu_encoder_split.py::test_end_to_end_scores_split asserts for the kernels on all 64 images."""
+    """The precise mode's emulation (oracle.vit F16X2: fp16 (hi, lo) pairs at every stored 16-bit tensor, the softmax
+    probabilities included) against the live reference's fp32 scores, cfg2, 16-image slice: every score within 1e-4
+    (measured max 2.6e-5, features 2.4e-6 -- the fp32 reference's own rounding noise), where the single-fp16 emulation has
+    half of them outside 1e-3 -- the CPU statement of what tests/test_gpu_encoder_split.py::test_end_to_end_scores_split
+    asserts for the kernels on all 64 images."""
     patch, K = gi.SCORE_PARITY_CFGS[0]
     g = _load(golden_dir, f"score_parity_b{patch}.npz")
     imgs, text, _ = gi.score_parity_inputs(K)
@@ -174,10 +175,10 @@ def test_split_operand_emulation_meets_the_score_bar(golden_dir):
     f1 = ovit.encode_image(sd, imgs[:16], operand_dtype=torch.float16, fold_layernorm=True).numpy()
     med2, mx2, frac2 = score_errors(oh.clip_score(f2, text), g["scores"][:16])
     med1, mx1, frac1 = score_errors(oh.clip_score(f1, text), g["scores"][:16])
-    assert mx2 < 6e-4 and frac2 == 1.0, (med2, mx2)
-    assert med2 < 0.25 * med1, (med2, med1)
+    assert mx2 < 1e-4 and frac2 == 1.0, (med2, mx2)
+    assert med2 < 0.1 * med1, (med2, med1)
     want = g["features"][:16]
-    assert np.linalg.norm(f2 - want) / np.linalg.norm(want) < 5e-5
+    assert np.linalg.norm(f2 - want) / np.linalg.norm(want) < 1e-5
 
 
 def test_text_oracle_matches_reference_fixture(golden_dir):
