@@ -737,6 +737,84 @@ __device__ __forceinline__ void clip_forward_tile(const T* __restrict__ z, const
     }
 }
 
+// The same tile, software pipelined: the 16-byte loads of the NEXT 64 feature columns are issued before the MMAs of the
+// current 64 (two register buffers, each holding a 64-column slab of both rows), so a warp's loads and tensor work overlap
+// instead of alternating -- with 16 resident warps per SM the non-pipelined form leaves both the tensor pipe and HBM at
+// ~45 % (ncu, profiles/r1_v10_ncu_full_heads.md).  Same k order per accumulator: bit-identical results.
+template <typename T, int NT, bool KEEP = false>
+__device__ __forceinline__ void clip_forward_tile_pipe(const T* __restrict__ z, const int64_t (&row)[2], const bool (&ok)[2], int d,
+                                                       const uint4* s_frag, int lane, float (&acc)[NT][4], float (&ss)[2],
+                                                       uint64_t keep_policy = 0) {
+    constexpr bool BF = ClipMma<T>::kBF16;
+    constexpr bool SPLIT = ClipMma<T>::kSplitA;
+    constexpr int HL = sizeof(T) == 4 ? 4 : 2;                    // 16-byte loads per row per 64-column slab
+    const int t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    ss[0] = ss[1] = 0.f;
+    uint4 raw[2][2][HL];
+    auto issue = [&](uint4 (&buf)[2][HL], int c0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < HL; ++q) {
+                const int col = c0 + (sizeof(T) == 4 ? 16 * q + 4 * t : 32 * q + 8 * t);
+                if (!ok[r]) buf[r][q] = make_uint4(0u, 0u, 0u, 0u);
+                else if (KEEP)
+                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                                 : "=r"(buf[r][q].x), "=r"(buf[r][q].y), "=r"(buf[r][q].z), "=r"(buf[r][q].w)
+                                 : "l"(z + row[r] * d + col), "l"(keep_policy));
+                else
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(buf[r][q].x), "=r"(buf[r][q].y), "=r"(buf[r][q].z), "=r"(buf[r][q].w)
+                                 : "l"(z + row[r] * d + col));
+            }
+    };
+    auto compute = [&](const uint4 (&buf)[2][HL], int c0) {
+#pragma unroll
+        for (int js = 0; js < 4; ++js) {                          // 4 k-steps of 16 columns per slab
+            uint32_t a_hi[4], a_lo[4];
+            if (SPLIT) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const uint4 w = buf[r][js];
+                    const float e[4] = {__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w)};
+                    ss[r] += (e[0] * e[0] + e[1] * e[1]) + (e[2] * e[2] + e[3] * e[3]);
+                    a_hi[r] = clip_pack2<true>(e[0], e[1]);
+                    a_hi[2 + r] = clip_pack2<true>(e[2], e[3]);
+                    const float2 h0 = clip_unpack2<true>(a_hi[r]), h1 = clip_unpack2<true>(a_hi[2 + r]);
+                    a_lo[r] = clip_pack2<true>(e[0] - h0.x, e[1] - h0.y);
+                    a_lo[2 + r] = clip_pack2<true>(e[2] - h1.x, e[3] - h1.y);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const uint4 w = buf[r][js >> 1];
+                    a_hi[r] = (js & 1) ? w.z : w.x;
+                    a_hi[2 + r] = (js & 1) ? w.w : w.y;
+                    const float2 f0 = clip_unpack2<BF>(a_hi[r]), f1 = clip_unpack2<BF>(a_hi[2 + r]);
+                    ss[r] += (f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y);
+                }
+            }
+            const uint4* fr = s_frag + ((size_t)((c0 >> 4) + js) * NT) * 32 + lane;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const uint4 f = fr[nt * 32];
+                clip_mma<BF>(acc[nt], a_hi, f.z, f.w);          // small terms first
+                if (SPLIT) clip_mma<BF>(acc[nt], a_lo, f.x, f.y);
+                clip_mma<BF>(acc[nt], a_hi, f.x, f.y);
+            }
+        }
+    };
+    issue(raw[0], 0);
+    for (int c0 = 0; c0 < d; c0 += 128) {                         // d % 128 == 0
+        issue(raw[1], c0 + 64);
+        compute(raw[0], c0);
+        if (c0 + 128 < d) issue(raw[0], c0 + 128);
+        compute(raw[1], c0 + 64);
+    }
+}
+
 template <typename T, int NT>
 __global__ void __launch_bounds__(kHeadBlock, 2)
 clip_score_mma_kernel(const T* __restrict__ z, const float* __restrict__ text, int64_t n, int d, int K, float scale,
@@ -755,7 +833,7 @@ clip_score_mma_kernel(const T* __restrict__ z, const float* __restrict__ text, i
         const bool ok[2] = {row[0] < n, row[1] < n};
         float acc[NT][4];
         float ss[2];
-        clip_forward_tile<T, NT>(z, row, ok, d, s_frag, lane, acc, ss);
+        clip_forward_tile_pipe<T, NT>(z, row, ok, d, s_frag, lane, acc, ss);
         // rows g (accumulator slots 0, 1) and g + 8 (slots 2, 3): prompt nt*8 + 2t + e lives in this lane
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
