@@ -155,6 +155,43 @@ def test_clip_trainer_zero_shot_eval():
     assert roc.auc == oauc.roc_auc(labels.cpu().numpy(), scores.cpu().numpy())
 
 
+def test_clip_trainer_zero_shot_eval_precise_mode_matches_the_fp32_reference_path():
+    """cfg2 through the plug-in API, end to end, in the precise mode: ClipModel (both towers, operand_dtype "f16x2") behind
+    ADClipTrainer -- prompts' token ids -> prepare_metric -> eval_cls -> scores + AUC -- against the fp32 ORACLE of the whole
+    reference path (oracle.text -> normalise -> oracle.vit -> oracle.heads.clip_score -> oracle.auc): every score within
+    north_star's 1e-3 relative (measured ~2e-5) and the AUC identical."""
+    from eoe_b200.clip_model import ClipModel
+    from eoe_b200.training import ADClipTrainer
+    from oracle import golden_inputs as gi, text as otext, vit as ovit
+    sd = {**ovit.synth_state_dict(32, seed=gi.VIT_WEIGHT_SEED), **otext.synth_text_state_dict(seed=gi.TEXT_WEIGHT_SEED)}
+    m = ClipModel(sd, device=DEV, operand_dtype="f16x2", max_batch=16)
+    tok = gi.text_tokens()                                              # 10 prompts (9 classes + the anomaly prompt)
+    seen = []
+
+    def text_encoder(prompts):                                          # the caller's tokenizer: here the seeded ids, one row per prompt
+        seen.append(list(prompts))
+        assert len(prompts) == tok.shape[0]
+        return m.encode_text(tok.to(DEV))
+
+    tr = ADClipTrainer(m, device=DEV, epochs=0, ad_mode="leave_one_out", text_encoder=text_encoder,
+                       class_names=[f"c{i}" for i in range(10)])       # leave_one_out: 9 nominal prompts + the anomaly prompt
+    tr.train_cls(m, [], clsstr="c3")
+    assert seen and seen[0][-1] == "a photo of something" and "a photo of a c3" not in seen[0]
+    g = torch.Generator().manual_seed(17)
+    batches = [(torch.randn(16, 3, 224, 224, generator=g), (torch.rand(16, generator=g) < 0.5).long(), torch.arange(16))
+               for _ in range(2)]
+    roc, _ = tr.eval_cls(m, batches, nominal_label=0)
+    labels, scores = tr.last_eval
+    t32 = otext.encode_text(sd, tok)
+    c32 = (t32 / t32.norm(dim=-1, keepdim=True)).numpy()
+    torch.testing.assert_close(tr.center.cpu(), torch.from_numpy(c32), rtol=0, atol=2e-6)
+    want = oh.clip_score(ovit.encode_image(sd, torch.cat([b[0] for b in batches])).numpy(), c32)
+    s = scores.cpu().numpy().astype(np.float64)
+    rel = np.abs(s - want) / np.abs(want)
+    assert rel.max() <= 1e-3 and rel.max() <= 2e-4, (float(np.median(rel)), float(rel.max()))
+    assert roc.auc == oauc.roc_auc(labels.cpu().numpy(), want.astype(np.float32))
+
+
 def test_cfg5_hsc_on_clip_vitb16_features_with_sgd():
     """BASELINE config 5, the part on the hot path: [n, 512] features of the B200 ViT-B/16 tower (frozen: the encoder is
     forward-only) -> HSC loss + backward + scores, optimiser = SGD(nesterov, momentum 0.9) as the reference picks for CLIP
