@@ -740,7 +740,9 @@ __device__ __forceinline__ void clip_forward_tile(const T* __restrict__ z, const
 // The same tile, software pipelined: the 16-byte loads of the NEXT 64 feature columns are issued before the MMAs of the
 // current 64 (two register buffers, each holding a 64-column slab of both rows), so a warp's loads and tensor work overlap
 // instead of alternating -- with 16 resident warps per SM the non-pipelined form leaves both the tensor pipe and HBM at
-// ~45 % (ncu, profiles/r1_v10_ncu_full_heads.md).  Same k order per accumulator: bit-identical results.
+// ~45 % (ncu, profiles/r1_v10_ncu_full_heads.md).  Same k order per accumulator: bit-identical results.  Used by the score
+// kernel (+2 ... +4 % of HBM bandwidth); in the loss kernel the second buffer spills (128 registers at 512 threads) and it
+// measured 1-2 % slower, so the loss keeps the form above.
 template <typename T, int NT, bool KEEP = false>
 __device__ __forceinline__ void clip_forward_tile_pipe(const T* __restrict__ z, const int64_t (&row)[2], const bool (&ok)[2], int d,
                                                        const uint4* s_frag, int lane, float (&acc)[NT][4], float (&ss)[2],

@@ -13,13 +13,18 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "eoe_b200", "libeoe_b200.so")
 WANT = [  # (mangled-name regex, label): fp16 instantiations (the default operand dtype), 1 CTA pair per cluster
-    (r"gemm_kernelILi4ELb0ELi1E", "gemm_kernel<EOE_EPI_LNFOLD_BIAS, fp16> (QKV with ln_1 folded in)"),
-    (r"gemm_kernelILi8ELb0ELi1E", "gemm_kernel<EOE_EPI_LNFOLD_QUICKGELU_X1702, fp16> (c_fc with ln_2 folded in)"),
-    (r"gemm_kernelILi7ELb0ELi1E", "gemm_kernel<EPI_RESIDUAL_STATS_ASYNC, fp16> (out-proj, residual + statistics)"),
-    (r"gemm_kernelILi6ELb0ELi1E", "gemm_kernel<EOE_EPI_RESIDUAL_STATS, fp16> (c_proj, residual + statistics)"),
-    (r"gemm_kernelILi3ELb0ELi1E", "gemm_kernel<EOE_EPI_PATCH_EMBED, fp16> (patch embedding)"),
-    (r"attention_tc_kernelILb0ELi197E", "attention_tc_kernel<fp16, L = 197> (ViT-B/16)"),
-    (r"attention_tc64_kernelILb0E", "attention_tc64_kernel<fp16> (L <= 64, ViT-B/32)"),
+    (r"gemm_kernelILi4ELb0ELi1ELb0E", "gemm_kernel<EOE_EPI_LNFOLD_BIAS, fp16> (QKV with ln_1 folded in)"),
+    (r"gemm_kernelILi8ELb0ELi1ELb0E", "gemm_kernel<EOE_EPI_LNFOLD_QUICKGELU_X1702, fp16> (c_fc with ln_2 folded in)"),
+    (r"gemm_kernelILi7ELb0ELi1ELb0E", "gemm_kernel<EPI_RESIDUAL_STATS_ASYNC, fp16> (out-proj, residual + statistics)"),
+    (r"gemm_kernelILi6ELb0ELi1ELb0E", "gemm_kernel<EOE_EPI_RESIDUAL_STATS, fp16> (c_proj, residual + statistics)"),
+    (r"gemm_kernelILi3ELb0ELi1ELb0E", "gemm_kernel<EOE_EPI_PATCH_EMBED, fp16> (patch embedding)"),
+    (r"attention_tc_kernelILb0ELi197ELb0E", "attention_tc_kernel<fp16, L = 197> (ViT-B/16)"),
+    (r"attention_tc64_kernelILb0ELb0E", "attention_tc64_kernel<fp16> (L <= 64, ViT-B/32)"),
+    # precise mode (operand dtype EOE_F16X2: split fp16 pairs, SPLIT = true)
+    (r"gemm_kernelILi8ELb0ELi1ELb1E", "gemm_kernel<EOE_EPI_LNFOLD_QUICKGELU_X1702, SPLIT> (c_fc, precise mode: hi / lo output tiles)"),
+    (r"gemm_kernelILi6ELb0ELi1ELb1E", "gemm_kernel<EOE_EPI_RESIDUAL_STATS, SPLIT> (c_proj, precise mode)"),
+    (r"attention_tc_kernelILb0ELi197ELb1E", "attention_tc_kernel<fp16, L = 197, SPLIT> (precise mode: 3 S products, P as a pair, 3 P.V products)"),
+    (r"attention_tc64_kernelILb0ELb1E", "attention_tc64_kernel<fp16, SPLIT> (precise mode, L <= 64)"),
 ]
 MNEMONICS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTMAPF", "SYNCS", "HMMA", "MUFU.EX2", "MUFU.TANH",
              "REDG", "LDGSTS"]
