@@ -53,7 +53,8 @@ class ClipImageEncoder(nn.Module):
         self.heads = heads or self.width // 64
         self.embed_dim = sd["proj"].shape[1]
         self.n_layers = len({k.split(".")[2] for k in sd if k.startswith("transformer.resblocks.")})
-        self.operand_dtype = operand_dtype
+        self.operand_dtype = operand_dtype           # storage dtype of the 16-bit tensors (fp16 in the precise mode)
+        self.operand_mode = L.F16X2 if self.split else {torch.float16: "f16", torch.bfloat16: "bf16"}[operand_dtype]
         self.max_batch = int(max_batch)
         self.device_ = dev
         self.fold_layernorm = bool(fold_layernorm) and self.width <= 768      # eoe_gemm_lnfold: K <= 768
