@@ -20,3 +20,7 @@ for dt in f16 bf16; do
 done
 python tools/make_gemm_traffic.py $BID f16=gpurun_out/prof_${tag}_f16.ncu-rep bf16=gpurun_out/prof_${tag}_bf16.ncu-rep > gpurun_out/gemm_traffic_$tag.json
 cat gpurun_out/gemm_traffic_$tag.json
+# gpurun copies back at most 64 MiB: the summaries above are the evidence, the raw reports stay on the box
+rm -f gpurun_out/prof_${tag}_bf16.ncu-rep
+[ $(stat -c %s gpurun_out/prof_${tag}_f16.ncu-rep 2>/dev/null || echo 0) -gt 30000000 ] && rm -f gpurun_out/prof_${tag}_f16.ncu-rep
+ls -la gpurun_out | head -30

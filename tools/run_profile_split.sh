@@ -12,3 +12,4 @@ python tools/summarize_launches.py gpurun_out/launches_${tag}.csv "Launch list, 
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_kernel|attention_tc" -s 50 -c 7 -o gpurun_out/prof_${tag} $CMD > gpurun_out/ncu2_${tag}.log 2>&1
 echo "full capture rc=$?"
 python tools/summarize_ncu_full.py gpurun_out/prof_${tag}.ncu-rep "ncu --set full, build $BID (f16x2): split GEMM instantiations + split attention of one step" "ncu --set full --clock-control none --import-source on -k regex:gemm_kernel|attention_tc -s 50 -c 7 $CMD" > gpurun_out/${tag}_ncu_full.md
+rm -f gpurun_out/prof_${tag}.ncu-rep      # gpurun copies back at most 64 MiB; the summary above is the evidence
