@@ -9,6 +9,7 @@ BASELINE configs 2 (ViT-B/32, K = 10) and 3 (ViT-B/16, K = 30) on the seeded ima
     against the fp32 oracle: feature rel-L2, score relative error (median / p90 / max / fraction within 1e-3), AUC delta;
   * the same with ONE rounding point active at a time (oracle.vit.ROUND_POINTS): which stored 16-bit tensor the error
     comes from;
+  * the precise mode's emulation (oracle.vit.F16X2: every stored 16-bit tensor an fp16 (hi, lo) pair) against the same;
   * the reference's OWN GPU precision (fp16 weights and fp16 residual stream, model.py:371-392), both as the emulation
     oracle.vit.encode_image_ref_fp16 and, where /root/reference is mounted, as the live reference run in half.
 
@@ -64,6 +65,10 @@ def run_cfg(patch, K, n_img, live):
             per[pt] = {"feat_rel_l2": st["feat_rel_l2"], "score_rel_median": st["score_rel_median"]}
         res[f"ours_{name}_one_point_at_a_time"] = per
         print(patch, name, res[f"ours_{name}"], flush=True)
+    # the precise mode (operand dtype EOE_F16X2: fp16 (hi, lo) pairs at every stored 16-bit tensor), all points and all but one
+    f = ovit.encode_image(sd, imgs, operand_dtype=ovit.F16X2, fold_layernorm=True).numpy()
+    res["ours_f16x2"] = stats(oh.clip_score(f, text), s32, f, f32, labels)
+    print(patch, "f16x2", res["ours_f16x2"], flush=True)
     f = ovit.encode_image_ref_fp16(sd, imgs).numpy()
     res["reference_fp16_path_emulated"] = stats(oh.clip_score(f, text), s32, f, f32, labels)
     print(patch, "ref fp16 emu", res["reference_fp16_path_emulated"], flush=True)
