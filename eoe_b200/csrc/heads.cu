@@ -1163,9 +1163,18 @@ static int clip_score_mma_launch(const void* z, const float* text, int64_t n, in
     return check_launch("clip_score_mma_kernel");
 }
 
+// vit.cu: the tcgen05 / TMEM / TMA score head for many 16-bit rows (clip_head_sm100.cuh)
+int clip_score_tc16(const void* z, int dtype, const float* text, int64_t n, int64_t d, int64_t K, float scale, float* scores,
+                    cudaStream_t st);
+static int g_clip_tc_min_rows = 16384;          // below: the warp-level kernel (fewer than one 128-row tile per SM otherwise)
+
 template <typename T>
 static int clip_score_launch(const void* z, const float* text, int64_t n, int64_t d, int64_t K, float scale,
                              float* scores, cudaStream_t st) {
+    // 16-bit rows, many of them: logits on tcgen05 with the rows used as UMMA operands where TMA puts them
+    if (sizeof(T) == 2 && n >= g_clip_tc_min_rows && d % 64 == 0 && d <= 512 && K >= 1 && K <= 32 &&
+        (uintptr_t)z % 16 == 0 && (uintptr_t)text % 16 == 0)
+        return clip_score_tc16(z, std::is_same<T, __half>::value ? EOE_F16 : EOE_BF16, text, n, d, K, scale, scores, st);
     if (clip_mma_ok<T>(z, text, n, d, K)) return clip_score_mma_launch<T>(z, text, n, d, K, scale, scores, st);
     const int iters = (int)((d / 4 + 31) / 32);
     const int it_pad = iters <= 2 ? 2 : (iters <= 4 ? 4 : 8);

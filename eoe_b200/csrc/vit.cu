@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "attention_sm100.cuh"
+#include "clip_head_sm100.cuh"
 #include "gemm_sm100.cuh"
 
 namespace eoe {
@@ -90,6 +91,33 @@ static int make_tmap_tokens(CUtensorMap* m, const void* base, int64_t B, int64_t
         return EOE_ERR_CUDA;
     }
     return EOE_OK;
+}
+
+static int num_sms();
+
+// CLIP score head for many 16-bit rows on tcgen05 (clip_head_sm100.cuh); called by heads.cu's dispatch.  z [n, d] fp16 / bf16
+// (d % 64 == 0, d <= 512, 16-byte aligned), text [K, d] fp32 (K <= 32), scores [n] fp32.
+int clip_score_tc16(const void* z, int dtype, const float* text, int64_t n, int64_t d, int64_t K, float scale, float* scores,
+                    cudaStream_t st) {
+    CUtensorMap tm;
+    int rc = make_tmap(&tm, z, n, d, 128, dtype);
+    if (rc) return rc;
+    const int64_t tiles = (n + 127) / 128;
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+#define EOE_CLIP_TC(BF)                                                                                                   \
+    {                                                                                                                     \
+        auto kern = cliptc::clip_score_tc_kernel<BF>;                                                                     \
+        static bool attr_done = false;                                                                                    \
+        if (!attr_done) {                                                                                                 \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cliptc::SMEM_BYTES); \
+            if (e != cudaSuccess) { set_cuda_error(e, "clip_score_tc smem attr"); return EOE_ERR_CUDA; }                  \
+            attr_done = true;                                                                                             \
+        }                                                                                                                 \
+        kern<<<grid, cliptc::THREADS, cliptc::SMEM_BYTES, st>>>(tm, text, n, (int)d, (int)K, scale, scores);             \
+    }
+    if (dtype == EOE_BF16) EOE_CLIP_TC(true) else EOE_CLIP_TC(false)
+#undef EOE_CLIP_TC
+    return check_launch("clip_score_tc_kernel");
 }
 
 static int num_sms() {

@@ -232,6 +232,49 @@ def test_clip_large_prompt_sets(n, d, K, dtype):
             _close(_np(zz.grad)[keep], oh.clip_oe_grad(zq, y, cu, nom, loo)[keep], rtol=gtol, atol=1e-5)
 
 
+@pytest.mark.parametrize("n,d,K", [(16384, 512, 30), (20001, 512, 10), (16500, 512, 32), (17000, 256, 2), (16385, 64, 1),
+                                   (40000, 384, 17)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_clip_score_tcgen05_path_vs_oracle(n, d, K, dtype):
+    """16-bit rows, n >= 16 384, d % 64 == 0, d <= 512, K <= 32: clip_score_tc_kernel (tcgen05 / TMEM, rows brought by TMA and
+    used as UMMA operands as they are, text hi ; lo as one N = 64 operand).  Same bars as the warp-level kernel: 1e-3 on the
+    scores including far-tail ones, ragged last tile, and agreement with the warp-level kernel on a slice below the
+    dispatch threshold."""
+    from eoe_b200 import ops
+    rng = np.random.default_rng(n + d + K)
+    z = rng.standard_normal((n, d)).astype(np.float32) * rng.uniform(0.01, 30.0, (n, 1)).astype(np.float32)
+    c = (rng.standard_normal((K, d)) * 1.7).astype(np.float32)
+    z[: n // 3] += 0.2 * np.sqrt(d) * c[rng.integers(0, K, n // 3)]
+    zt = _t(z, dtype)
+    zq = _np(zt)
+    got = _np(ops.clip_score(zt, _t(c)))
+    _close(got, oh.clip_score(zq, c), rtol=1e-3, atol=1e-30)
+    if d % 128 == 0:                                        # the mma.sync kernel on the first 4 000 rows
+        _close(_np(ops.clip_score(zt[:4000].contiguous(), _t(c))), got[:4000], rtol=1e-3, atol=1e-30)
+    else:
+        _close(_np(ops.clip_score(zt[:100].contiguous(), _t(c))), got[:100], rtol=1e-3, atol=1e-30)
+
+
+def test_clip_score_tcgen05_path_special_rows_and_determinism():
+    from eoe_b200 import ops
+    rng = np.random.default_rng(5)
+    n, d, K = 16384 + 77, 512, 30
+    z = rng.standard_normal((n, d)).astype(np.float32)
+    c = rng.standard_normal((K, d)).astype(np.float32)
+    z[7, 100] = np.nan
+    z[8, 5] = np.inf
+    z[24] = 0.0
+    z[n - 1, 511] = np.nan
+    zt = _t(z, torch.float16)
+    got = ops.clip_score(zt, _t(c))
+    assert torch.equal(got, ops.clip_score(zt, _t(c)).clone()) or torch.equal(torch.nan_to_num(got), torch.nan_to_num(ops.clip_score(zt, _t(c))))
+    got = _np(got)
+    bad = np.zeros(n, bool)
+    bad[[7, 8, 24, n - 1]] = True
+    assert np.isnan(got[bad]).all() and np.isfinite(got[~bad]).all()
+    _close(got[~bad], oh.clip_score(_np(zt)[~bad], c), rtol=1e-3, atol=1e-30)
+
+
 def test_clip_score_tensor_core_path_special_rows():
     """NaN / Inf / zero rows give NaN scores (z / ||z|| in the reference, clip.py:70), neighbours are untouched."""
     from eoe_b200 import ops
