@@ -1166,6 +1166,8 @@ static int clip_score_mma_launch(const void* z, const float* text, int64_t n, in
 // vit.cu: the tcgen05 / TMEM / TMA score head for many 16-bit rows (clip_head_sm100.cuh)
 int clip_score_tc16(const void* z, int dtype, const float* text, int64_t n, int64_t d, int64_t K, float scale, float* scores,
                     cudaStream_t st);
+int clip_loss_tc16(const void* z, int dtype, const float* text, const int64_t* labels, int64_t n, int64_t d, int64_t K,
+                   float scale, int64_t nominal, int loo, float* loss_out, void* grad, void* ws, cudaStream_t st);
 static int g_clip_tc_min_rows = 16384;          // below: the warp-level kernel (fewer than one 128-row tile per SM otherwise)
 
 template <typename T>
@@ -1204,6 +1206,10 @@ template <typename T>
 static int clip_loss_launch(const void* z, const float* text, const int64_t* labels, int64_t n, int64_t d,
                             int64_t K, float scale, int64_t nominal, int loo, float* loss_out, void* grad,
                             void* ws, cudaStream_t st) {
+    if (sizeof(T) == 2 && grad && n >= g_clip_tc_min_rows && d % 64 == 0 && d <= 512 && K >= 1 && K <= 32 &&
+        (uintptr_t)z % 16 == 0 && (uintptr_t)text % 16 == 0 && (uintptr_t)grad % 16 == 0)
+        return clip_loss_tc16(z, std::is_same<T, __half>::value ? EOE_F16 : EOE_BF16, text, labels, n, d, K, scale, nominal, loo,
+                              loss_out, grad, ws, st);
     if (clip_mma_ok<T>(z, text, n, d, K) && (uintptr_t)grad % 16 == 0 && d <= 512)
         return clip_loss_mma_launch<T>(z, text, labels, n, d, K, scale, nominal, loo, loss_out, grad, ws, st);
     const int iters = (int)((d / 4 + 31) / 32);

@@ -120,6 +120,34 @@ int clip_score_tc16(const void* z, int dtype, const float* text, int64_t n, int6
     return check_launch("clip_score_tc_kernel");
 }
 
+// CLIP OE loss + backward for many 16-bit rows on tcgen05 (clip_head_sm100.cuh); grad [n, d] in the dtype of z.
+int clip_loss_tc16(const void* z, int dtype, const float* text, const int64_t* labels, int64_t n, int64_t d, int64_t K,
+                   float scale, int64_t nominal, int loo, float* loss_out, void* grad, void* ws, cudaStream_t st) {
+    CUtensorMap tm_z, tm_g;
+    int rc = make_tmap(&tm_z, z, n, d, 128, dtype);
+    if (!rc) rc = make_tmap(&tm_g, grad, n, d, 32, dtype);
+    if (rc) return rc;
+    const int64_t tiles = (n + 127) / 128;
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    const float inv_n_f = 1.0f / (float)n;
+    const double inv_n = 1.0 / (double)n;
+#define EOE_CLIPL_TC(BF)                                                                                                  \
+    {                                                                                                                     \
+        auto kern = cliptc::clip_oe_loss_tc_kernel<BF>;                                                                   \
+        static bool attr_done = false;                                                                                    \
+        if (!attr_done) {                                                                                                 \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cliptc::LOSS_SMEM_BYTES); \
+            if (e != cudaSuccess) { set_cuda_error(e, "clip_oe_loss_tc smem attr"); return EOE_ERR_CUDA; }                \
+            attr_done = true;                                                                                             \
+        }                                                                                                                 \
+        kern<<<grid, cliptc::LOSS_THREADS, cliptc::LOSS_SMEM_BYTES, st>>>(tm_z, tm_g, text, labels, n, (int)d, (int)K, scale,   \
+                                                                     nominal, loo, (HeadWorkspace*)ws, loss_out, inv_n_f, inv_n); \
+    }
+    if (dtype == EOE_BF16) EOE_CLIPL_TC(true) else EOE_CLIPL_TC(false)
+#undef EOE_CLIPL_TC
+    return check_launch("clip_oe_loss_tc_kernel");
+}
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {

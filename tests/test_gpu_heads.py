@@ -255,6 +255,41 @@ def test_clip_score_tcgen05_path_vs_oracle(n, d, K, dtype):
         _close(_np(ops.clip_score(zt[:100].contiguous(), _t(c))), got[:100], rtol=1e-3, atol=1e-30)
 
 
+@pytest.mark.parametrize("n,d,K", [(16384, 512, 30), (20001, 512, 10), (16500, 512, 32), (17000, 256, 2), (16385, 64, 1),
+                                   (33000, 384, 17)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("loo", [False, True])
+def test_clip_oe_loss_tcgen05_path_vs_oracle(n, d, K, dtype, loo):
+    """16-bit rows, n >= 16 384: clip_oe_loss_tc_kernel (forward logits and G @ C on tcgen05, G handed over in TMEM, dz written
+    in place over the z chunks and TMA-stored).  Same bars as the warp-level kernel: loss 1e-4, gradients 2e-2 of the 16-bit
+    outputs (leave-one-out rows whose two best nominal logits nearly tie are excluded: their arg-max target legitimately
+    depends on the last bit), labels outside {0, 1} contribute nothing, ragged last tile."""
+    from eoe_b200 import ops
+    if loo and K == 1:
+        pytest.skip("leave-one-out needs at least one nominal prompt beside the anomaly prompt")
+    rng = np.random.default_rng(n + d + K + int(loo))
+    z = rng.standard_normal((n, d)).astype(np.float32) * rng.uniform(0.5, 4.0, (n, 1)).astype(np.float32)
+    c = rng.standard_normal((K, d)).astype(np.float32)
+    cu = c / np.linalg.norm(c, axis=1, keepdims=True)
+    y = rng.integers(0, 2, n).astype(np.int64)
+    y[::17] = -1                                            # unlabeled rows: no loss, zero gradient
+    for nom in (0, 1):
+        zt = _t(z, dtype).requires_grad_(True)
+        zq = _np(zt.detach())
+        loss = ops.clip_oe_loss(zt, _t(y), _t(cu), nom, leave_one_out=loo)
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), oh.clip_oe_loss(zq, y, cu, nom, loo), rtol=1e-4)
+        g = _np(zt.grad)
+        want = oh.clip_oe_grad(zq, y, cu, nom, loo)
+        keep = np.ones(n, bool)
+        if loo and K > 2:
+            lg = np.sort(oh.clip_logits(zq, cu, False, 100.0)[:, : K - 1], axis=1)
+            keep = (lg[:, -1] - lg[:, -2]) > 1e-3
+            assert keep.mean() > 0.99
+        assert np.all(g[y == -1] == 0)
+        _close(g[keep], want[keep], rtol=2e-2, atol=1e-5 / n * 128)
+
+
 def test_clip_score_tcgen05_path_special_rows_and_determinism():
     from eoe_b200 import ops
     rng = np.random.default_rng(5)
