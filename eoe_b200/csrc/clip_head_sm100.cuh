@@ -208,67 +208,80 @@ clip_score_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const float* __re
 // CLIP outlier-exposure loss + backward w.r.t. the features (ADClipTrainer.loss, clip.py:81-103) for many 16-bit rows.
 // Forward as above.  Backward: with G = softmax - onehot(target) (x scale) per row,
 //     dz = (G @ C - (sum_k G_k logit_k) z^) / (n ||z||),        C = the text rows as given (the loss does not renormalise)
-// G @ C is the second small GEMM: A = G (hi, lo as 16-bit pairs) written by the row owners into TMEM -- a thread owns a
-// row = a TMEM lane, so it goes from registers straight to where tcgen05.mma reads its A operand --, B = the forward's text
+// G @ C is the second small GEMM: A = G (hi, lo as 16-bit pairs) written by a row owner into TMEM -- a thread owns a row =
+// a TMEM lane, so it goes from registers straight to where tcgen05.mma reads its A operand --, B = the forward's text
 // tiles read as MN-major operands (features contiguous, prompts = k): six MMAs per 64-column chunk (G_hi T_hi, G_hi T_lo,
-// G_lo T_hi over two 16-prompt k-steps), D_bwd [128 x 64] fp32, double buffered.  The z chunks stay in the shared-memory
-// ring through the backward pass: the row owner reads its 64 values of chunk c again, overwrites them IN PLACE with dz and
-// each warp hands its 32-row block to the TMA unit (tile store, rows past n clipped); a stage goes back to the producer
-// when its store has been read out, so the loads of the next tile overlap this tile's backward pass chunk by chunk.
-// Row-owner work (~5 600 instructions per row and tile) is what bounds a 4-warp version (58 % of HBM), so TWO warps share
-// each TMEM lane quarter: set A (warps 0-3) and set B (warps 4-7) split the chunks of the norm pass, A alone does the
-// softmax / loss / G of its row (B waits on a named barrier and receives the two row scalars through shared memory), and
-// in the backward pass A takes the even chunks (accumulator 0) and B the odd ones (accumulator 1).
-// TMEM (512 columns, one CTA per SM): D_fwd 2 x 64 | G 32 | D_bwd 2 x 64.
-constexpr int LOSS_THREADS = 320;                    // warps 0-3 set A, 4-7 set B, 8 TMA producer, 9 TMEM allocator + MMA issuer
+// G_lo T_hi over two 16-prompt k-steps), D_bwd [128 x 64] fp32, double buffered.
+// The two halves of a tile's work are done by DIFFERENT warps, one tile apart, so that neither HBM nor the tensor pipe
+// waits for a softmax:
+//   warps 0-3  "F": norm pass over the forward chunks, logits from TMEM, softmax / loss / G of tile j+1 ...
+//   warps 4-11 "B": ... while they turn tile j's accumulator chunks into dz: z is streamed a second time (TMA, L2 hits:
+//              148 x 128 KB in flight is far below the 126 MB L2), dz goes through a per-warp staging block and out by TMA.
+//              A chunk costs a warp ~1 500 clocks of mostly fixed latencies (three mbarrier waits, TMEM load, proxy
+//              fence, the serial TMA-store tail), so two sets share the work: B0 = warps 4-7 takes the even chunks
+//              (accumulator 0), B1 = warps 8-11 the odd ones (accumulator 1)
+//   warp 12    TMA producer: forward(t0), then forward(t_{j+1}), backward(t_j), ... through one 7-stage ring
+//   warp 13    TMEM allocator + MMA issuer, in the same order
+// F hands a tile to B and to the MMA issuer through `gready` (G in TMEM, the two row scalars in shared memory, both double
+// buffered) and gets the buffers back through `gfree`.
+// TMEM (512 columns, one CTA per SM): D_fwd 2 x 64 | G 2 x 32 | D_bwd 2 x 64.
+constexpr int LOSS_THREADS = 448;                    // warps 0-3 F, 4-7 B0 (even chunks), 8-11 B1 (odd chunks), 12 TMA, 13 MMA
 constexpr uint32_t LOSS_TMEM_COLS = 512, G_COL = 128, DB_COL = 192;
-constexpr uint32_t LOSS_SMEM_BYTES = MAX_CH * TCH + NST * ZCH + 512 + 3 * 512 + 1024;
-
-__device__ __forceinline__ void owners_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+constexpr int LNST = 7;                              // ring stages (text 64 KB + 7 x 16 KB + 8 x 4 KB staging)
+constexpr uint32_t LOSS_SMEM_BYTES = MAX_CH * TCH + LNST * ZCH + 8 * 4096 + 512 + 4 * 512 + 1024;
 
 template <bool BF16>
 __global__ void __launch_bounds__(LOSS_THREADS, 1)
 clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_g,
                        const float* __restrict__ text, const int64_t* __restrict__ labels, int64_t n, int d, int K, float scale,
-                       int64_t nominal_label, int loo, HeadWorkspace* ws, float* loss_out, float inv_n_f, double inv_n) {
+                       int64_t nominal_label, int loo, HeadWorkspace* ws, float* loss_out, float inv_n_f, double inv_n, int dbg) {
+    constexpr int NST = LNST;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sT = smem;
     uint8_t* sZ = smem + MAX_CH * TCH;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sZ + NST * ZCH);   // [NST] TMA -> MMA and row owners
-    uint64_t* empty = full + NST;                                   // [NST] the 4 warps whose dz store of the chunk has left -> TMA
-    uint64_t* tfull = empty + NST;                                  // [2]   forward accumulator: MMA -> set A
-    uint64_t* tempty = tfull + 2;                                   // [2]   set A -> MMA
-    uint64_t* bfull = tempty + 2;                                   // [2]   backward accumulator b: MMA -> set b
-    uint64_t* bempty = bfull + 2;                                   // [2]   set b -> MMA
-    uint64_t* gready = bempty + 2;                                  // [1]   G of the tile is in TMEM: set A -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gready + 1);
-    float* s_ss = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 512);      // [128] set B's share of sum z^2
-    float* s_gdz = s_ss + 128;                                      // [128] (sum_k G_k l_k) / ||z||
-    float* s_osc = s_gdz + 128;                                     // [128] 1 / (n ||z||)
+    uint8_t* sOut = sZ + NST * ZCH;                                 // [8 B warps][32 rows][128 B] dz staging
+    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + 8 * 4096);  // [NST] TMA -> readers
+    uint64_t* empty = full + NST;                                   // [NST] 5 arrivals per use -> TMA: forward use = MMA commit + the 4
+                                                                    //       F warps; backward use = the 4 B warps, the first one twice
+    uint64_t* tfull = empty + NST;                                  // [2]   forward accumulator: MMA -> F
+    uint64_t* tempty = tfull + 2;                                   // [2]   F -> MMA
+    uint64_t* bfull = tempty + 2;                                   // [2]   backward accumulator: MMA -> B
+    uint64_t* bempty = bfull + 2;                                   // [2]   B -> MMA
+    uint64_t* gready = bempty + 2;                                  // [2]   G + row scalars of a tile are published: F -> MMA, B
+    uint64_t* gfree = gready + 2;                                   // [2]   ... and consumed: MMA commit + the 8 B warps -> F
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gfree + 2);
+    float* s_gdz = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 512);     // [2][128] (sum_k G_k l_k) / ||z||
+    float* s_osc = s_gdz + 256;                                     // [2][128] 1 / (n ||z||)
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(kFullMask, tid >> 5, 0);
     const int nch = d >> 6;
     const int64_t tiles = (n + 127) >> 7;
+    const int64_t m = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;      // tiles of this CTA
+    // Ring use indices (identical in every role): forward(t_0) takes uses [0, nch); then for j = 0 .. m-1 the producer issues
+    // forward(t_{j+1}) (if it exists) and backward(t_j).
+    auto fwd_use = [&](int64_t j) { return j == 0 ? (int64_t)0 : (2 * j - 1) * (int64_t)nch; };
+    auto bwd_use = [&](int64_t j) { return (j + 1 < m ? 2 * j + 2 : 2 * j + 1) * (int64_t)nch; };
 
     if (tid == 0) {
         ptx::prefetch_tensormap(&tm_z);
         ptx::prefetch_tensormap(&tm_g);
         for (int s = 0; s < NST; ++s) {
             ptx::mbar_init(ptx::smem_u32(&full[s]), 1);
-            ptx::mbar_init(ptx::smem_u32(&empty[s]), 4);
+            ptx::mbar_init(ptx::smem_u32(&empty[s]), 5);
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(ptx::smem_u32(&tfull[a]), 1);
             ptx::mbar_init(ptx::smem_u32(&tempty[a]), 4);
             ptx::mbar_init(ptx::smem_u32(&bfull[a]), 1);
             ptx::mbar_init(ptx::smem_u32(&bempty[a]), 4);
+            ptx::mbar_init(ptx::smem_u32(&gready[a]), 4);
+            ptx::mbar_init(ptx::smem_u32(&gfree[a]), 9);
         }
-        ptx::mbar_init(ptx::smem_u32(gready), 4);
         ptx::fence_barrier_init();
     }
-    if (warp == 9) {
+    if (warp == 13) {
         ptx::tmem_alloc<1>(ptx::smem_u32(tmem_slot), LOSS_TMEM_COLS);
         ptx::tmem_relinquish<1>();
     }
@@ -301,85 +314,89 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     float loss_acc = 0.f;
+    auto tile_of = [&](int64_t j) { return (int64_t)blockIdx.x + j * gridDim.x; };
 
-    if (warp == 8) {
+    if (warp == 12) {
         if (lane == 0) {
             // ------------------------------------------------------------------ TMA producer
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                for (int ch = 0; ch < nch; ++ch) {
-                    ptx::mbar_wait(ptx::smem_u32(&empty[stage]), phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full[stage]), ZCH);
-                    ptx::tma_load_2d(ptx::smem_u32(sZ + stage * ZCH), &tm_z, ptx::smem_u32(&full[stage]), ch * 64, (int)(tile * 128));
-                    if (++stage == NST) { stage = 0; phase ^= 1; }
+            int64_t u = 0;
+            auto load_tile = [&](int64_t tile) {
+                for (int ch = 0; ch < nch; ++ch, ++u) {
+                    const int s = (int)(u % NST);
+                    ptx::mbar_wait(ptx::smem_u32(&empty[s]), (uint32_t)(((u / NST) & 1) ^ 1));
+                    ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full[s]), ZCH);
+                    ptx::tma_load_2d(ptx::smem_u32(sZ + s * ZCH), &tm_z, ptx::smem_u32(&full[s]), ch * 64, (int)(tile * 128));
                 }
+            };
+            if (m > 0) load_tile(tile_of(0));
+            for (int64_t j = 0; j < m; ++j) {
+                if (j + 1 < m) load_tile(tile_of(j + 1));
+                load_tile(tile_of(j));                                  // the same chunks again for the backward pass
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 13) {
         if (lane == 0) {
             // ------------------------------------------------------------------ MMA issuer
             constexpr uint32_t idesc_f = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, 64);
             constexpr uint32_t idesc_b = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, 64, 0, 1);      // B = text chunk, MN-major
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0, g_phase = 0;
             uint32_t b_phase[2] = {0, 0};
-            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                ptx::mbar_wait(ptx::smem_u32(&tempty[acc]), acc_phase ^ 1);
+            auto forward = [&](int64_t j) {
+                const int acc = (int)(j & 1);
+                ptx::mbar_wait(ptx::smem_u32(&tempty[acc]), (uint32_t)(((j >> 1) & 1) ^ 1));
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem + (uint32_t)acc * 64;
-                for (int ch = 0; ch < nch; ++ch) {
-                    ptx::mbar_wait(ptx::smem_u32(&full[stage]), phase);
+                int64_t u = fwd_use(j);
+                for (int ch = 0; ch < nch; ++ch, ++u) {
+                    const int s = (int)(u % NST);
+                    ptx::mbar_wait(ptx::smem_u32(&full[s]), (uint32_t)((u / NST) & 1));
                     ptx::tc_fence_after();
-                    const uint64_t a_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sZ + stage * ZCH));
+                    const uint64_t a_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sZ + s * ZCH));
                     const uint64_t b_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sT + ch * TCH));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         ptx::umma_f16<1>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_f, (ch | k) != 0 ? 1u : 0u);
-                    if (++stage == NST) { stage = 0; phase ^= 1; }
+                    ptx::umma_commit(ptx::smem_u32(&empty[s]));
                 }
                 ptx::umma_commit(ptx::smem_u32(&tfull[acc]));
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                // backward of this tile: G is in TMEM once set A has seen the logits
-                ptx::mbar_wait(ptx::smem_u32(gready), g_phase);
-                g_phase ^= 1;
+            };
+            if (m > 0) forward(0);
+            for (int64_t j = 0; j < m; ++j) {
+                if (j + 1 < m) forward(j + 1);
+                const int g = (int)(j & 1);
+                ptx::mbar_wait(ptx::smem_u32(&gready[g]), (uint32_t)((j >> 1) & 1));
                 ptx::tc_fence_after();
+                const uint32_t gcol = tmem + G_COL + (uint32_t)g * 32;
                 for (int ch = 0; ch < nch; ++ch) {
-                    const int bb = ch & 1;                              // even chunks -> accumulator 0 (set A), odd -> 1 (set B)
+                    const int bb = ch & 1;
                     ptx::mbar_wait(ptx::smem_u32(&bempty[bb]), b_phase[bb] ^ 1);
                     ptx::tc_fence_after();
                     const uint32_t db = tmem + DB_COL + (uint32_t)bb * 64;
                     const uint64_t t_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(sT + ch * TCH));
                     // A: packed G columns (8 per 16 prompts): hi [0, 16), lo [16, 32); B: 16-prompt row blocks of 2 KB: hi 0, 1, lo 2, 3
-                    ptx::umma_f16_ts(db, tmem + G_COL + 0, t_desc + (uint64_t)(0 * 2048 >> 4), idesc_b, 0u);      // G_hi T_hi
-                    ptx::umma_f16_ts(db, tmem + G_COL + 8, t_desc + (uint64_t)(1 * 2048 >> 4), idesc_b, 1u);
-                    ptx::umma_f16_ts(db, tmem + G_COL + 0, t_desc + (uint64_t)(2 * 2048 >> 4), idesc_b, 1u);      // G_hi T_lo
-                    ptx::umma_f16_ts(db, tmem + G_COL + 8, t_desc + (uint64_t)(3 * 2048 >> 4), idesc_b, 1u);
-                    ptx::umma_f16_ts(db, tmem + G_COL + 16, t_desc + (uint64_t)(0 * 2048 >> 4), idesc_b, 1u);     // G_lo T_hi
-                    ptx::umma_f16_ts(db, tmem + G_COL + 24, t_desc + (uint64_t)(1 * 2048 >> 4), idesc_b, 1u);
+                    ptx::umma_f16_ts(db, gcol + 0, t_desc + (uint64_t)(0 * 2048 >> 4), idesc_b, 0u);      // G_hi T_hi
+                    ptx::umma_f16_ts(db, gcol + 8, t_desc + (uint64_t)(1 * 2048 >> 4), idesc_b, 1u);
+                    ptx::umma_f16_ts(db, gcol + 0, t_desc + (uint64_t)(2 * 2048 >> 4), idesc_b, 1u);      // G_hi T_lo
+                    ptx::umma_f16_ts(db, gcol + 8, t_desc + (uint64_t)(3 * 2048 >> 4), idesc_b, 1u);
+                    ptx::umma_f16_ts(db, gcol + 16, t_desc + (uint64_t)(0 * 2048 >> 4), idesc_b, 1u);     // G_lo T_hi
+                    ptx::umma_f16_ts(db, gcol + 24, t_desc + (uint64_t)(1 * 2048 >> 4), idesc_b, 1u);
                     ptx::umma_commit(ptx::smem_u32(&bfull[bb]));
                     b_phase[bb] ^= 1;
                 }
+                ptx::umma_commit(ptx::smem_u32(&gfree[g]));             // every MMA that reads this G buffer has completed
             }
         }
-    } else {
-        // ---------------------------------------------------------------------- row owners: set A (warps 0-3), set B (warps 4-7)
-        const int set = warp >> 2;                                       // 0 = A, 1 = B
-        const int rt = tid & 127;                                        // row of the tile = TMEM lane
-        const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        int stage = 0, acc = 0;
-        uint32_t phase = 0, acc_phase = 0, b_phase = 0;
+    } else if (warp < 4) {
+        // ---------------------------------------------------------------------- F: norm, logits, softmax, loss, G
+        const int rt = tid;                                              // row of the tile = TMEM lane
+        const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
         const int64_t anom_label = 1 - nominal_label;
-        const int nch_a = (nch + 1) >> 1;                                // norm pass: A reads chunks [0, nch_a), B the rest
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int st0 = stage;
-            const uint32_t ph0 = phase;
-            // ---- pass 1: row norm while the chunks arrive (the stages are NOT released: the backward pass reads them again)
+        for (int64_t j = 0; j < m; ++j) {
+            const int64_t tile = tile_of(j);
             float ss = 0.f;
-            for (int ch = set ? nch_a : 0; ch < (set ? nch : nch_a); ++ch) {
-                const int s = (st0 + ch) % NST;
-                const uint32_t ph = ph0 ^ (uint32_t)((st0 + ch) >= NST);
-                ptx::mbar_wait(ptx::smem_u32(&full[s]), ph);
+            int64_t u = fwd_use(j);
+            for (int ch = 0; ch < nch; ++ch, ++u) {
+                const int s = (int)(u % NST);
+                ptx::mbar_wait(ptx::smem_u32(&full[s]), (uint32_t)((u / NST) & 1));
                 const uint8_t* rowp = sZ + s * ZCH + rt * 128;
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
@@ -387,89 +404,101 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
                     const float2 a = unpack2<BF16>(v.x), b = unpack2<BF16>(v.y), c = unpack2<BF16>(v.z), e = unpack2<BF16>(v.w);
                     ss += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y) + (c.x * c.x + c.y * c.y) + (e.x * e.x + e.y * e.y);
                 }
-            }
-            if (set) s_ss[rt] = ss;
-            owners_barrier();                                            // B's share of the norm is in shared memory
-            float gdz, osc;
-            if (!set) {
-                ss += s_ss[rt];
-                // ---- logits -> softmax, loss, G (set A)
-                ptx::mbar_wait(ptx::smem_u32(&tfull[acc]), acc_phase);
-                ptx::tc_fence_after();
-                uint32_t r0[32], r1[32];
-                ptx::tmem_ld_32x32b_x32(t_lane + (uint32_t)acc * 64, r0);
-                ptx::tmem_ld_32x32b_x32(t_lane + (uint32_t)acc * 64 + 32, r1);
-                ptx::tmem_ld_wait();
-                ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty[acc]));
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                const int64_t row = tile * 128 + rt;
-                const bool ok = row < n;
-                const float inv_nrm = 1.0f / sqrtf(ss);
-                const float sc = scale * inv_nrm;
-                float l[32];
-                float mx = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    l[k] = k < K ? (__uint_as_float(r1[k]) + __uint_as_float(r0[k])) * sc : -INFINITY;
-                    mx = fmaxf(mx, l[k]);
-                }
-                float pr[32];
-                float sum = 0.f;
-#pragma unroll
-                for (int k = 0; k < 32; ++k) { pr[k] = expf(l[k] - mx); sum += pr[k]; }
-                const float lse = mx + logf(sum);
-                const int64_t lab = ok ? labels[row] : 0;
-                int loo_t = 0;                                        // argmax over k < K - 1, first maximal index (clip.py:95)
-                if (loo) {
-                    float best = -INFINITY;
-                    bool have = false;
-#pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        if (k < K - 1 && (!have || l[k] > best)) { best = l[k]; loo_t = k; have = true; }
-                }
-                int tg = -1;
-                if (ok && lab == anom_label) tg = K - 1;
-                else if (ok && lab == nominal_label) tg = loo_t;
-                float lt = 0.f;
-#pragma unroll
-                for (int k = 0; k < 32; ++k) if (k == tg) lt = l[k];
-                if (tg >= 0) loss_acc += lse - lt;
-                float gd = 0.f;
-                uint32_t gh[16], gl[16];
-                const float inv_sum = 1.0f / sum;
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    float g2[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int k = 2 * c + e;
-                        const float gk = (tg >= 0 && k < K) ? (pr[k] * inv_sum - (k == tg ? 1.f : 0.f)) : 0.f;
-                        if (tg >= 0 && k < K) gd += gk * l[k];
-                        g2[e] = gk * scale;
-                    }
-                    gh[c] = gemm::pack2<BF16>(g2[0], g2[1]);
-                    const float2 f = unpack2<BF16>(gh[c]);
-                    gl[c] = gemm::pack2<BF16>(g2[0] - f.x, g2[1] - f.y);
-                }
-                gdz = gd * inv_nrm;
-                osc = inv_nrm * inv_n_f;
-                s_gdz[rt] = gdz;
-                s_osc[rt] = osc;
-                ptx::tmem_st_32x32b_x16(t_lane + G_COL, gh);
-                ptx::tmem_st_32x32b_x16(t_lane + G_COL + 16, gl);
-                ptx::tmem_st_wait();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(gready));
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&empty[s]));
             }
-            owners_barrier();                                            // the row scalars are in shared memory
-            if (set) { gdz = s_gdz[rt]; osc = s_osc[rt]; }
-            // ---- pass 2: per 64-column chunk  dz = (G @ C - gdz * z) * osc, in place over z, out through TMA
-            int prev = -1;
+            const int acc = (int)(j & 1);
+            ptx::mbar_wait(ptx::smem_u32(&tfull[acc]), (uint32_t)((j >> 1) & 1));
+            ptx::tc_fence_after();
+            uint32_t r0[32], r1[32];
+            ptx::tmem_ld_32x32b_x32(t_lane + (uint32_t)acc * 64, r0);
+            ptx::tmem_ld_32x32b_x32(t_lane + (uint32_t)acc * 64 + 32, r1);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty[acc]));
+            const int64_t row = tile * 128 + rt;
+            const bool ok = row < n;
+            const float inv_nrm = 1.0f / sqrtf(ss);
+            const float sc = scale * inv_nrm;
+            float l[32];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                l[k] = k < K ? (__uint_as_float(r1[k]) + __uint_as_float(r0[k])) * sc : -INFINITY;
+                mx = fmaxf(mx, l[k]);
+            }
+            float pr[32];
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { pr[k] = expf(l[k] - mx); sum += pr[k]; }
+            const float lse = mx + logf(sum);
+            const int64_t lab = ok ? labels[row] : 0;
+            int loo_t = 0;                                            // argmax over k < K - 1, first maximal index (clip.py:95)
+            if (loo) {
+                float best = -INFINITY;
+                bool have = false;
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (k < K - 1 && (!have || l[k] > best)) { best = l[k]; loo_t = k; have = true; }
+            }
+            int tg = -1;
+            if (ok && lab == anom_label) tg = K - 1;
+            else if (ok && lab == nominal_label) tg = loo_t;
+            float lt = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) if (k == tg) lt = l[k];
+            if (tg >= 0) loss_acc += lse - lt;
+            float gd = 0.f;
+            uint32_t gh[16], gl[16];
+            const float inv_sum = 1.0f / sum;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                float g2[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = 2 * c + e;
+                    const float gk = (tg >= 0 && k < K) ? (pr[k] * inv_sum - (k == tg ? 1.f : 0.f)) : 0.f;
+                    if (tg >= 0 && k < K) gd += gk * l[k];
+                    g2[e] = gk * scale;
+                }
+                gh[c] = gemm::pack2<BF16>(g2[0], g2[1]);
+                const float2 f = unpack2<BF16>(gh[c]);
+                gl[c] = gemm::pack2<BF16>(g2[0] - f.x, g2[1] - f.y);
+            }
+            // publish: the G buffer and the scalar slots of tile j-2 must have been consumed
+            const int g = (int)(j & 1);
+            ptx::mbar_wait(ptx::smem_u32(&gfree[g]), (uint32_t)(((j >> 1) & 1) ^ 1));
+            ptx::tc_fence_after();
+            s_gdz[g * 128 + rt] = gd * inv_nrm;
+            s_osc[g * 128 + rt] = inv_nrm * inv_n_f;
+            ptx::tmem_st_32x32b_x16(t_lane + G_COL + (uint32_t)g * 32, gh);
+            ptx::tmem_st_32x32b_x16(t_lane + G_COL + (uint32_t)g * 32 + 16, gl);
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&gready[g]));
+        }
+    } else {
+        // ---------------------------------------------------------------------- B0 / B1: dz = (G @ C - gdz z) osc per chunk
+        const int set = (warp - 4) >> 2;                                 // 0: even chunks / accumulator 0, 1: odd / 1
+        const int bw = (warp - 4) & 3;                                   // TMEM lane quarter
+        const int rt = (tid - 128) & 127;
+        const uint32_t t_lane = tmem + ((uint32_t)(bw * 32) << 16);
+        uint8_t* blk = sOut + (warp - 4) * 4096;                         // this warp's staging block, 32 rows x 128 B
+        uint8_t* outp = blk + (rt & 31) * 128;
+        uint32_t b_phase = 0;
+        for (int64_t j = 0; j < m; ++j) {
+            const int64_t tile = tile_of(j);
+            const int g = (int)(j & 1);
+            ptx::mbar_wait(ptx::smem_u32(&gready[g]), (uint32_t)((j >> 1) & 1));
+            const float gdz = s_gdz[g * 128 + rt], osc = s_osc[g * 128 + rt];
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&gfree[g]));
             for (int ch = set; ch < nch; ch += 2) {
-                const int s = (st0 + ch) % NST;
+                const int64_t u = bwd_use(j) + ch;
+                const int s = (int)(u % NST);
                 ptx::mbar_wait(ptx::smem_u32(&bfull[set]), b_phase);
                 b_phase ^= 1;
                 ptx::tc_fence_after();
@@ -479,47 +508,46 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bempty[set]));
-                uint8_t* rowp = sZ + s * ZCH + rt * 128;
+                if (lane == 0) {
+                    ptx::mbar_arrive(ptx::smem_u32(&bempty[set]));
+                    ptx::bulk_wait_group_read0();                       // this warp's previous dz block has left its staging
+                }
+                ptx::mbar_wait(ptx::smem_u32(&full[s]), (uint32_t)((u / NST) & 1));
+                __syncwarp();
+                const uint8_t* rowp = sZ + s * ZCH + rt * 128;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {                          // logical 16-byte column q = features 8q .. 8q+7 of the chunk
-                    uint4* cell = reinterpret_cast<uint4*>(rowp + ((q ^ (rt & 7)) << 4));
-                    const uint4 v = *cell;
+                    const uint32_t off = (uint32_t)((q ^ (rt & 7)) << 4);
+                    const uint4 v = *reinterpret_cast<const uint4*>(rowp + off);
                     const uint32_t zw[4] = {v.x, v.y, v.z, v.w};
                     uint32_t ow[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 zv = unpack2<BF16>(zw[j]);
-                        const int c = 8 * q + 2 * j;
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const float2 zv = unpack2<BF16>(zw[jj]);
+                        const int c = 8 * q + 2 * jj;
                         const float ga = __uint_as_float(c < 32 ? g0[c & 31] : g1[c & 31]);
                         const float gb = __uint_as_float(c < 32 ? g0[(c + 1) & 31] : g1[(c + 1) & 31]);
-                        ow[j] = gemm::pack2<BF16>((ga - gdz * zv.x) * osc, (gb - gdz * zv.y) * osc);
+                        ow[jj] = gemm::pack2<BF16>((ga - gdz * zv.x) * osc, (gb - gdz * zv.y) * osc);
                     }
-                    *cell = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    *reinterpret_cast<uint4*>(outp + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    ptx::tma_store_2d(&tm_g, ptx::smem_u32(sZ + s * ZCH + (warp & 3) * 4096), ch * 64, (int)(tile * 128 + (warp & 3) * 32));
-                    ptx::bulk_commit_group();
-                    if (prev >= 0) {                                   // this warp's previous block has left shared memory
-                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        ptx::mbar_arrive(ptx::smem_u32(&empty[(st0 + prev) % NST]));
+                    ptx::mbar_arrive(ptx::smem_u32(&empty[s]));        // every lane of this warp has read its z values
+                    if (bw == 0) ptx::mbar_arrive(ptx::smem_u32(&empty[s]));            // (5th arrival: no MMA reads this use)
+                    if (!(dbg & 1)) {                                  // (diagnostics bit 0: no dz stores)
+                        ptx::tma_store_2d(&tm_g, ptx::smem_u32(blk), ch * 64, (int)(tile * 128 + bw * 32));
+                        ptx::bulk_commit_group();
                     }
                 }
-                prev = ch;
             }
-            if (lane == 0 && prev >= 0) {
-                ptx::bulk_wait_group_read0();
-                ptx::mbar_arrive(ptx::smem_u32(&empty[(st0 + prev) % NST]));
-            }
-            stage = st0 + nch;
-            if (stage >= NST) { stage -= NST; phase ^= 1; }
         }
+        if (lane == 0) ptx::bulk_wait_group_read0();
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 13) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<1>(tmem, LOSS_TMEM_COLS);
     }

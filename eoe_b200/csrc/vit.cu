@@ -94,6 +94,7 @@ static int make_tmap_tokens(CUtensorMap* m, const void* base, int64_t B, int64_t
 }
 
 static int num_sms();
+static int g_gemm_debug = 0;            // eoe_debug_set(): diagnostics only, 0 in production
 
 // CLIP score head for many 16-bit rows on tcgen05 (clip_head_sm100.cuh); called by heads.cu's dispatch.  z [n, d] fp16 / bf16
 // (d % 64 == 0, d <= 512, 16-byte aligned), text [K, d] fp32 (K <= 32), scores [n] fp32.
@@ -141,7 +142,7 @@ int clip_loss_tc16(const void* z, int dtype, const float* text, const int64_t* l
             attr_done = true;                                                                                             \
         }                                                                                                                 \
         kern<<<grid, cliptc::LOSS_THREADS, cliptc::LOSS_SMEM_BYTES, st>>>(tm_z, tm_g, text, labels, n, (int)d, (int)K, scale,   \
-                                                                     nominal, loo, (HeadWorkspace*)ws, loss_out, inv_n_f, inv_n); \
+                                                                     nominal, loo, (HeadWorkspace*)ws, loss_out, inv_n_f, inv_n, (g_gemm_debug >> 20) & 7); \
     }
     if (dtype == EOE_BF16) EOE_CLIPL_TC(true) else EOE_CLIPL_TC(false)
 #undef EOE_CLIPL_TC
@@ -159,7 +160,7 @@ static int num_sms() {
     return n;
 }
 
-static int g_gemm_debug = 0;            // eoe_debug_set(): diagnostics only, 0 in production
+
 static int g_last_max_clusters[2] = {0, 0};
 
 template <int EPI, bool BF16, int CLP, bool SPLIT = false>
