@@ -25,6 +25,9 @@ WANT = [  # (mangled-name regex, label): fp16 instantiations (the default operan
     (r"gemm_kernelILi6ELb0ELi1ELb1E", "gemm_kernel<EOE_EPI_RESIDUAL_STATS, SPLIT> (c_proj, precise mode)"),
     (r"attention_tc_kernelILb0ELi197ELb1E", "attention_tc_kernel<fp16, L = 197, SPLIT> (precise mode: 3 S products, P as a pair, 3 P.V products)"),
     (r"attention_tc64_kernelILb0ELb1E", "attention_tc64_kernel<fp16, SPLIT> (precise mode, L <= 64)"),
+    # CLIP heads for 16-bit rows (csrc/clip_head_sm100.cuh)
+    (r"clip_score_tc_kernelILb1E", "cliptc::clip_score_tc_kernel<bf16> (zero-shot score head, 16-bit rows)"),
+    (r"clip_oe_loss_tc_kernelILb1E", "cliptc::clip_oe_loss_tc_kernel<bf16> (OE loss + backward, 16-bit rows: G through TMEM, MN-major text tiles)"),
 ]
 MNEMONICS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTMAPF", "SYNCS", "HMMA", "MUFU.EX2", "MUFU.TANH",
              "REDG", "LDGSTS"]
