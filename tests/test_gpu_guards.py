@@ -177,3 +177,89 @@ def test_encoder_stays_inside_its_workspace(patch, B):
     finally:
         torch.cuda.synchronize()
         lib.eoe_vit_plan_destroy(plan)
+
+
+# ------------------------------------------------------------------------------------------ round 2: new paths
+@pytest.mark.parametrize("n,K", [(16384, 30), (16385, 10), (20001, 32), (16500, 2)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_clip_tcgen05_heads_write_only_their_outputs(n, K, dtype):
+    """16-bit rows at n >= 16 384 take the tcgen05 kernels (TMA tile stores of dz, rows past n clipped by the tensor map)."""
+    L, lib = _lib()
+    d = 512
+    z = torch.randn(n, d, device=DEV).to(dtype)
+    c = torch.nn.functional.normalize(torch.randn(K, d, device=DEV), dim=-1)
+    y = torch.randint(0, 2, (n,), device=DEV)
+    scores, loss, grad = Guarded((n,), torch.float32), Guarded((1,), torch.float32), Guarded((n, d), dtype)
+    ws = Guarded((L.EOE_HEAD_WS_BYTES,), torch.uint8, fill=0)
+    L.check(lib.eoe_clip_score(L.ptr(z), L.DTYPE_CODE[dtype], L.ptr(c), n, d, K, 100.0, scores.ptr(), _stream()), "clip_score")
+    scores.check("eoe_clip_score (tcgen05) scores")
+    assert torch.isfinite(scores.t).all()
+    for loo in (0, 1):
+        L.check(lib.eoe_clip_oe_loss_fwd_bwd(L.ptr(z), L.DTYPE_CODE[dtype], L.ptr(c), L.ptr(y), n, d, K, 100.0, 0, loo,
+                                             loss.ptr(), grad.ptr(), ws.ptr(), _stream()), "clip_oe")
+        for g, nm in ((loss, "loss"), (grad, "grad"), (ws, "head_ws")):
+            g.check("eoe_clip_oe_loss_fwd_bwd (tcgen05) " + nm)
+        assert torch.isfinite(grad.t.float()).all() and bool((ws.t[:4] == 0).all())
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 256, 64), (257, 768, 768), (100, 2304, 768), (515, 768, 3072)])
+def test_split_gemm_and_attention_write_only_their_outputs(M, N, K):
+    """operand dtype EOE_F16X2: operands [rows, 2K], 16-bit outputs [M, 2N] (hi | lo tiles, two TMA stores per 64 columns)."""
+    from eoe_b200 import encoder as E
+    L, lib = _lib()
+    A = E.split_f16(torch.randn(M, K, device=DEV) * 0.5)
+    W = E.split_f16(torch.randn(N, K, device=DEV) * 0.05)
+    bias = torch.randn(N, device=DEV)
+    out16 = Guarded((M, 2 * N), torch.float16)
+    for epi in (L.EOE_EPI_BIAS, L.EOE_EPI_BIAS_QUICKGELU):
+        L.check(lib.eoe_gemm(L.ptr(A), L.ptr(W), L.ptr(bias), out16.ptr(), M, N, K, L.EOE_F16X2, epi, None, 0, _stream()), "gemm")
+        out16.check(f"eoe_gemm split epi {epi}")
+        assert torch.isfinite(out16.t.float()).all()
+    if N % 128 == 0 and N <= 1024:
+        x = Guarded((M, N), torch.float32, fill=torch.randn(M, N, device=DEV))
+        xb, stats, shift = Guarded((M, 2 * N), torch.float16), Guarded((M, N // 128, 2), torch.float32), Guarded((M,), torch.float32)
+        L.check(lib.eoe_gemm_residual_stats(L.ptr(A), L.ptr(W), L.ptr(bias), None, x.ptr(), xb.ptr(), stats.ptr(), shift.ptr(),
+                                            M, N, K, L.EOE_F16X2, _stream()), "gemm_residual_stats")
+        for g, nm in ((x, "x"), (xb, "xb"), (stats, "stats"), (shift, "shift")):
+            g.check("eoe_gemm_residual_stats split " + nm)
+    for B, Lseq in ((2, 197), (3, 50), (1, 17)):
+        qkv = E.split_f16(torch.randn(B * Lseq, 3 * 768, device=DEV))
+        out = Guarded((B * Lseq, 2 * 768), torch.float16)
+        L.check(lib.eoe_attention(L.ptr(qkv), out.ptr(), B, Lseq, 12, L.EOE_F16X2, _stream()), "attention")
+        out.check("eoe_attention split out")
+        assert torch.isfinite(out.t.float()).all()
+        if Lseq <= 100:
+            outc = Guarded((B * Lseq, 2 * 768), torch.float16)
+            L.check(lib.eoe_attention_causal(L.ptr(qkv), outc.ptr(), B, Lseq, 12, L.EOE_F16X2, _stream()), "attention_causal")
+            outc.check("eoe_attention_causal split out")
+
+
+@pytest.mark.parametrize("patch,B", [(32, 3), (16, 2)])
+def test_encoder_precise_mode_stays_inside_its_workspace(patch, B):
+    """the precise mode doubles every 16-bit buffer: eoe_vit_workspace_bytes must account for all of them"""
+    from eoe_b200.encoder import ClipImageEncoder
+    from oracle import vit as ovit
+    L, lib = _lib()
+    sd = ovit.synth_state_dict(patch, seed=2, layers=2)
+    enc = ClipImageEncoder(sd, device=DEV, max_batch=B, operand_dtype="f16x2")
+    nbytes = lib.eoe_vit_workspace_bytes(C.byref(enc._w), B)
+    ws = Guarded((nbytes + 1024,), torch.uint8)
+    base = ws.t.data_ptr() + ((-ws.t.data_ptr()) % 1024)
+    plan = C.c_void_p()
+    L.check(lib.eoe_vit_plan_create(C.byref(enc._w), B, C.c_void_p(base), nbytes, C.byref(plan)), "plan")
+    try:
+        imgs = torch.randn(B, 3, 224, 224, device=DEV)
+        text = torch.nn.functional.normalize(torch.randn(10, 512, device=DEV), dim=-1)
+        feats, scores = Guarded((B, 512), torch.float32), Guarded((B,), torch.float32)
+        L.check(lib.eoe_vit_encode(plan, L.ptr(imgs), B, feats.ptr(), L.ptr(text), 10, 100.0, scores.ptr(), _stream()), "encode")
+        for g, nm in ((ws, "workspace"), (feats, "features"), (scores, "scores")):
+            g.check("eoe_vit_encode (f16x2) " + nm)
+        assert torch.equal(feats.t, enc(imgs))
+        u8 = torch.randint(0, 256, (B, 64, 100, 3), dtype=torch.uint8, device=DEV)
+        L.check(lib.eoe_vit_encode_u8_resize(plan, L.ptr(u8), 64, 100, enc._mean, enc._std, B, feats.ptr(), L.ptr(text), 10,
+                                             100.0, scores.ptr(), _stream()), "encode_u8_resize")
+        for g, nm in ((ws, "workspace"), (feats, "features"), (scores, "scores")):
+            g.check("eoe_vit_encode_u8_resize (f16x2) " + nm)
+    finally:
+        torch.cuda.synchronize()
+        lib.eoe_vit_plan_destroy(plan)
