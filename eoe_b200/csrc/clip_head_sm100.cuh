@@ -220,15 +220,21 @@ clip_score_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const float* __re
 //              A chunk costs a warp ~1 500 clocks of mostly fixed latencies (three mbarrier waits, TMEM load, proxy
 //              fence, the serial TMA-store tail), so two sets share the work: B0 = warps 4-7 takes the even chunks
 //              (accumulator 0), B1 = warps 8-11 the odd ones (accumulator 1)
-//   warp 12    TMA producer: forward(t0), then forward(t_{j+1}), backward(t_j), ... through one 7-stage ring
-//   warp 13    TMEM allocator + MMA issuer, in the same order
+//   warp 12    TMA producer of the forward ring (3 stages; consumers: F and the forward issuer, in lockstep on every use)
+//   warp 13    TMEM allocator + issuer of the forward MMAs;  warp 14  issuer of the backward MMAs.  One thread issuing
+//              all 80 MMAs + 24 commits of a tile was busy for 10 000 of the tile's 14 000 clocks and starved B (clock64
+//              probes, profiles/r2_clip_loss_tc_clocks.json): issuing a small tcgen05.mma costs its thread ~100 clocks,
+//              three times what an M 128 x N 64 x K 16 product occupies the tensor pipe.
+// Each consumer group has its OWN ring -- an mbarrier carries one phase bit, so a waiter may never skip a use of a stage:
+// the forward ring above, and a private 2-stage ring per backward set that the set feeds itself (when its four warps have
+// passed a named barrier behind a chunk, one thread issues the TMA load of the set's chunk after next into that stage).
 // F hands a tile to B and to the MMA issuer through `gready` (G in TMEM, the two row scalars in shared memory, both double
 // buffered) and gets the buffers back through `gfree`.
 // TMEM (512 columns, one CTA per SM): D_fwd 2 x 64 | G 2 x 32 | D_bwd 2 x 64.
-constexpr int LOSS_THREADS = 448;                    // warps 0-3 F, 4-7 B0 (even chunks), 8-11 B1 (odd chunks), 12 TMA, 13 MMA
+constexpr int LOSS_THREADS = 480;                    // warps 0-3 F, 4-7 B0 (even chunks), 8-11 B1 (odd chunks), 12 TMA, 13 / 14 MMA
 constexpr uint32_t LOSS_TMEM_COLS = 512, G_COL = 128, DB_COL = 192;
-constexpr int LNST = 7;                              // ring stages (text 64 KB + 7 x 16 KB + 8 x 4 KB staging)
-constexpr uint32_t LOSS_SMEM_BYTES = MAX_CH * TCH + LNST * ZCH + 8 * 4096 + 512 + 4 * 512 + 1024;
+constexpr int LNST = 3;                              // forward ring stages (text 64 KB + 3 x 16 KB + 2 x 2 x 16 KB + 8 x 4 KB staging)
+constexpr uint32_t LOSS_SMEM_BYTES = MAX_CH * TCH + (LNST + 4) * ZCH + 8 * 4096 + 512 + 4 * 512 + 1024;
 
 template <bool BF16>
 __global__ void __launch_bounds__(LOSS_THREADS, 1)
@@ -240,11 +246,12 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sT = smem;
     uint8_t* sZ = smem + MAX_CH * TCH;
-    uint8_t* sOut = sZ + NST * ZCH;                                 // [8 B warps][32 rows][128 B] dz staging
-    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + 8 * 4096);  // [NST] TMA -> readers
-    uint64_t* empty = full + NST;                                   // [NST] 5 arrivals per use -> TMA: forward use = MMA commit + the 4
-                                                                    //       F warps; backward use = the 4 B warps, the first one twice
-    uint64_t* tfull = empty + NST;                                  // [2]   forward accumulator: MMA -> F
+    uint8_t* sZb = sZ + NST * ZCH;                                  // [2 sets][2 stages][128 rows][128 B] the backward sets' own rings
+    uint8_t* sOut = sZb + 4 * ZCH;                                  // [8 B warps][32 rows][128 B] dz staging
+    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + 8 * 4096);  // [NST] forward ring: TMA -> F, forward issuer
+    uint64_t* empty = full + NST;                                   // [NST] forward issuer's commit + the 4 F warps -> TMA
+    uint64_t* fullb = empty + NST;                                  // [2][2] backward rings: TMA -> the set
+    uint64_t* tfull = fullb + 4;                                    // [2]   forward accumulator: MMA -> F
     uint64_t* tempty = tfull + 2;                                   // [2]   F -> MMA
     uint64_t* bfull = tempty + 2;                                   // [2]   backward accumulator: MMA -> B
     uint64_t* bempty = bfull + 2;                                   // [2]   B -> MMA
@@ -259,10 +266,7 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
     const int nch = d >> 6;
     const int64_t tiles = (n + 127) >> 7;
     const int64_t m = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;      // tiles of this CTA
-    // Ring use indices (identical in every role): forward(t_0) takes uses [0, nch); then for j = 0 .. m-1 the producer issues
-    // forward(t_{j+1}) (if it exists) and backward(t_j).
-    auto fwd_use = [&](int64_t j) { return j == 0 ? (int64_t)0 : (2 * j - 1) * (int64_t)nch; };
-    auto bwd_use = [&](int64_t j) { return (j + 1 < m ? 2 * j + 2 : 2 * j + 1) * (int64_t)nch; };
+    auto fwd_use = [&](int64_t j) { return j * (int64_t)nch; };      // forward ring: use index of chunk 0 of the CTA's j-th tile
 
     if (tid == 0) {
         ptx::prefetch_tensormap(&tm_z);
@@ -271,6 +275,7 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
             ptx::mbar_init(ptx::smem_u32(&full[s]), 1);
             ptx::mbar_init(ptx::smem_u32(&empty[s]), 5);
         }
+        for (int a = 0; a < 4; ++a) ptx::mbar_init(ptx::smem_u32(&fullb[a]), 1);
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(ptx::smem_u32(&tfull[a]), 1);
             ptx::mbar_init(ptx::smem_u32(&tempty[a]), 4);
@@ -320,27 +325,21 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
         if (lane == 0) {
             // ------------------------------------------------------------------ TMA producer
             int64_t u = 0;
-            auto load_tile = [&](int64_t tile) {
+            for (int64_t j = 0; j < m; ++j) {
+                const int64_t tile = tile_of(j);
                 for (int ch = 0; ch < nch; ++ch, ++u) {
                     const int s = (int)(u % NST);
                     ptx::mbar_wait(ptx::smem_u32(&empty[s]), (uint32_t)(((u / NST) & 1) ^ 1));
                     ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full[s]), ZCH);
                     ptx::tma_load_2d(ptx::smem_u32(sZ + s * ZCH), &tm_z, ptx::smem_u32(&full[s]), ch * 64, (int)(tile * 128));
                 }
-            };
-            if (m > 0) load_tile(tile_of(0));
-            for (int64_t j = 0; j < m; ++j) {
-                if (j + 1 < m) load_tile(tile_of(j + 1));
-                load_tile(tile_of(j));                                  // the same chunks again for the backward pass
             }
         }
     } else if (warp == 13) {
         if (lane == 0) {
-            // ------------------------------------------------------------------ MMA issuer
+            // ------------------------------------------------------------------ issuer of the forward MMAs
             constexpr uint32_t idesc_f = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, 64);
-            constexpr uint32_t idesc_b = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, 64, 0, 1);      // B = text chunk, MN-major
-            uint32_t b_phase[2] = {0, 0};
-            auto forward = [&](int64_t j) {
+            for (int64_t j = 0; j < m; ++j) {
                 const int acc = (int)(j & 1);
                 ptx::mbar_wait(ptx::smem_u32(&tempty[acc]), (uint32_t)(((j >> 1) & 1) ^ 1));
                 ptx::tc_fence_after();
@@ -358,10 +357,14 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
                     ptx::umma_commit(ptx::smem_u32(&empty[s]));
                 }
                 ptx::umma_commit(ptx::smem_u32(&tfull[acc]));
-            };
-            if (m > 0) forward(0);
+            }
+        }
+    } else if (warp == 14) {
+        if (lane == 0) {
+            // ------------------------------------------------------------------ issuer of the backward MMAs
+            constexpr uint32_t idesc_b = ptx::make_idesc_f16(BF16 ? 1u : 0u, 128, 64, 0, 1);      // B = text chunk, MN-major
+            uint32_t b_phase[2] = {0, 0};
             for (int64_t j = 0; j < m; ++j) {
-                if (j + 1 < m) forward(j + 1);
                 const int g = (int)(j & 1);
                 ptx::mbar_wait(ptx::smem_u32(&gready[g]), (uint32_t)((j >> 1) & 1));
                 ptx::tc_fence_after();
@@ -480,7 +483,7 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&gready[g]));
         }
-    } else {
+    } else if (warp < 12) {
         // ---------------------------------------------------------------------- B0 / B1: dz = (G @ C - gdz z) osc per chunk
         const int set = (warp - 4) >> 2;                                 // 0: even chunks / accumulator 0, 1: odd / 1
         const int bw = (warp - 4) & 3;                                   // TMEM lane quarter
@@ -488,7 +491,23 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
         const uint32_t t_lane = tmem + ((uint32_t)(bw * 32) << 16);
         uint8_t* blk = sOut + (warp - 4) * 4096;                         // this warp's staging block, 32 rows x 128 B
         uint8_t* outp = blk + (rt & 31) * 128;
+        uint8_t* ring = sZb + set * 2 * ZCH;                             // this set's own 2-stage ring
+        uint64_t* rfull = fullb + set * 2;
+        const bool loader = bw == 0 && lane == 0;
         uint32_t b_phase = 0;
+        // the set's chunk sequence: (tile j, chunk ch) for ch = set, set + 2, ...; `seq` numbers them over all tiles
+        int64_t seq = 0, lseq = 0, lj = 0;
+        int lch = set;
+        auto load_next = [&]() {                                         // loader thread: the next chunk of the sequence -> stage lseq & 1
+            while (lj < m && lch >= nch) { ++lj; lch = set; }
+            if (lj >= m) return;
+            const int st = (int)(lseq & 1);
+            ptx::mbar_arrive_expect_tx(ptx::smem_u32(&rfull[st]), ZCH);
+            ptx::tma_load_2d(ptx::smem_u32(ring + st * ZCH), &tm_z, ptx::smem_u32(&rfull[st]), lch * 64, (int)(tile_of(lj) * 128));
+            ++lseq;
+            lch += 2;
+        };
+        if (loader) { load_next(); load_next(); }
         for (int64_t j = 0; j < m; ++j) {
             const int64_t tile = tile_of(j);
             const int g = (int)(j & 1);
@@ -496,9 +515,8 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
             const float gdz = s_gdz[g * 128 + rt], osc = s_osc[g * 128 + rt];
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&gfree[g]));
-            for (int ch = set; ch < nch; ch += 2) {
-                const int64_t u = bwd_use(j) + ch;
-                const int s = (int)(u % NST);
+            for (int ch = set; ch < nch; ch += 2, ++seq) {
+                const int st = (int)(seq & 1);
                 ptx::mbar_wait(ptx::smem_u32(&bfull[set]), b_phase);
                 b_phase ^= 1;
                 ptx::tc_fence_after();
@@ -512,9 +530,9 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
                     ptx::mbar_arrive(ptx::smem_u32(&bempty[set]));
                     ptx::bulk_wait_group_read0();                       // this warp's previous dz block has left its staging
                 }
-                ptx::mbar_wait(ptx::smem_u32(&full[s]), (uint32_t)((u / NST) & 1));
+                ptx::mbar_wait(ptx::smem_u32(&rfull[st]), (uint32_t)((seq >> 1) & 1));
                 __syncwarp();
-                const uint8_t* rowp = sZ + s * ZCH + rt * 128;
+                const uint8_t* rowp = ring + st * ZCH + rt * 128;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {                          // logical 16-byte column q = features 8q .. 8q+7 of the chunk
                     const uint32_t off = (uint32_t)((q ^ (rt & 7)) << 4);
@@ -532,14 +550,12 @@ clip_oe_loss_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_co
                     *reinterpret_cast<uint4*>(outp + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
                 ptx::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    ptx::mbar_arrive(ptx::smem_u32(&empty[s]));        // every lane of this warp has read its z values
-                    if (bw == 0) ptx::mbar_arrive(ptx::smem_u32(&empty[s]));            // (5th arrival: no MMA reads this use)
-                    if (!(dbg & 1)) {                                  // (diagnostics bit 0: no dz stores)
-                        ptx::tma_store_2d(&tm_g, ptx::smem_u32(blk), ch * 64, (int)(tile * 128 + bw * 32));
-                        ptx::bulk_commit_group();
-                    }
+                // all four warps of the set are done with the ring stage: it takes the set's chunk after next
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + set) : "memory");
+                if (loader) load_next();
+                if (lane == 0 && !(dbg & 1)) {                          // (diagnostics bit 0: no dz stores)
+                    ptx::tma_store_2d(&tm_g, ptx::smem_u32(blk), ch * 64, (int)(tile * 128 + bw * 32));
+                    ptx::bulk_commit_group();
                 }
             }
         }
