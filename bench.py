@@ -519,14 +519,21 @@ def run_ours(args):
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         ent = (tj.get("by_dtype") or {}).get(args.dtype, tj)
-        if tj.get("build_id") != build_id:
+        from eoe_b200 import build as ebuild
+        # the capture is valid for this library if it IS the profiled build, or if this library was built from the tree's
+        # sources and the sources the GEMM kernels come from (gemm_sm100.cuh, sm100_ptx.cuh, common.cuh, vit.cu, flags) are
+        # byte-identical to the profiled build's (a later change to the heads / AUC translation units does not touch them)
+        same_gemm = (tj.get("gemm_source_id") is not None and ebuild.source_id() == build_id
+                     and tj.get("gemm_source_id") == ebuild.gemm_source_id())
+        if tj.get("build_id") != build_id and not same_gemm:
             # an ncu capture of ANOTHER build says nothing about this one: refuse it instead of quoting a stale figure
             traffic_note = {"refused": f"profiles/gemm_traffic.json was captured on build {tj.get('build_id')}, "
                                        f"this library is build {build_id}"}
         elif tj.get("batch") == B and P == 16 and ent.get("dram_bytes_per_launch"):
             traffic = ent.get("dram_bytes_per_launch")         # ncu --set full capture of the c_fc GEMM at this batch size
             traffic_note = {"kernel": ent.get("kernel"), "algorithmic_bytes_per_launch": ent.get("algorithmic_bytes_per_launch"),
-                            "source": ent.get("source"), "build_id": build_id, "note": ent.get("note")}
+                            "source": ent.get("source"), "build_id": build_id, "captured_on_build": tj.get("build_id"),
+                            "gemm_source_id": tj.get("gemm_source_id"), "note": ent.get("note")}
     fc = prof.get("c_fc", (0.0, 0, 0.0))
     Lt = (224 // P) ** 2 + 1
     exec_gflop = (g_fl / (S * B) + (enc.n_layers - 1) * 4.0 * Lt * Lt * enc.width + 4.0 * Lt * enc.width) / 1e9

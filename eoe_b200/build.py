@@ -46,6 +46,21 @@ def source_id() -> str:
     return h.hexdigest()[:16]
 
 
+GEMM_SOURCES = ("gemm_sm100.cuh", "sm100_ptx.cuh", "common.cuh", "attention_sm100.cuh", "vit.cu")
+
+
+def gemm_source_id() -> str:
+    """sha256 over the sources the encoder's GEMM / attention kernels and their launches are compiled from (and the nvcc
+    flags): an ncu capture of those kernels (profiles/gemm_traffic.json) stays valid across builds that only touch the
+    heads / AUC translation units, and only across those."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in GEMM_SOURCES + ("../../include/eoe_b200.h",):
+        h.update(os.path.basename(f).encode() + b"\0")
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def _compile(src):
     obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
     if os.path.basename(src) == "capi.cu":       # carries the build id: always rebuilt with the link (a 1 s compile)

@@ -181,6 +181,14 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
 }
 
 // ------------------------------------------------------------------------------------------ 2 sort pass
+// Scatter: with a random 8-bit digit the 32 keys of a warp belong to ~28 different digit runs, so writing them straight to
+// their global positions costs one 32-byte sector per 4-byte key and another per label byte (measured: 31 us per pass at
+// 1 M scores against 15 us for the top-digit pass, whose runs are long).  The tile is therefore reordered by digit in
+// shared memory first (local position = start of the digit's run within the tile + rank), and written out in local
+// order: the keys of a digit are consecutive there AND at their destination, so a warp's stores cover whole sectors.
+#ifndef EOE_AUC_DIRECT_SCATTER
+#define EOE_AUC_DIRECT_SCATTER 0                        // 1: the round-1 form (registers -> global), kept for A/B builds
+#endif
 __global__ void __launch_bounds__(kSortThreads)
 auc_sort_pass_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                      uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int64_t n, int pass,
@@ -189,6 +197,10 @@ auc_sort_pass_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __rest
     __shared__ uint32_t s_base[256];
     __shared__ uint32_t s_tmp[8];
     __shared__ unsigned int s_tile;
+#if !EOE_AUC_DIRECT_SCATTER
+    __shared__ uint32_t s_keys[kSortTile];
+    __shared__ uint8_t s_labs[kSortTile];
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(&c->tickets[pass], 1u);
     for (int i = tid; i < 8 * 256; i += kSortThreads) (&s_warp_hist[0][0])[i] = 0;
@@ -234,11 +246,27 @@ auc_sort_pass_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __rest
     }
     const uint32_t gstart = block_excl_scan_256(c->hist[pass * 256 + d], s_tmp, nullptr);
     uint32_t* my = status + (size_t)tile * 256 + d;
+    // published before the local reordering: successors can use the aggregate (tile 0: the inclusive value) from here on
+    st_volatile_u32(my, run | ((tile == 0 ? kFlagIncl : kFlagAgg) << 30));
+#if !EOE_AUC_DIRECT_SCATTER
+    // start of digit d's run within the tile, folded into the per-warp offsets; then every key goes to its local position
+    const uint32_t lstart = block_excl_scan_256(run, s_tmp, nullptr);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s_warp_hist[w][d] += lstart;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        if ((base + j * 32 + lane) < n) {
+            const uint32_t lp = s_warp_hist[warp][(key[j] >> shift) & 255u] + rank[j];
+            s_keys[lp] = key[j];
+            s_labs[lp] = lab[j];
+        }
+    }
+#else
+    const uint32_t lstart = 0;
+#endif
     uint32_t excl = 0;
-    if (tile == 0) {
-        st_volatile_u32(my, run | (kFlagIncl << 30));
-    } else {
-        st_volatile_u32(my, run | (kFlagAgg << 30));
+    if (tile != 0) {
         int64_t t = (int64_t)tile - 1;
         bool done = false;
         int spins = 0;
@@ -268,8 +296,22 @@ auc_sort_pass_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __rest
         }
         st_volatile_u32(my, (excl + run) | (kFlagIncl << 30));
     }
-    s_base[d] = gstart + excl;
+    s_base[d] = gstart + excl - lstart;                // global position of local position lp of digit d: s_base[d] + lp
     __syncthreads();
+#if !EOE_AUC_DIRECT_SCATTER
+    const int64_t left = n - (int64_t)tile * kSortTile;
+    const int cnt = left < kSortTile ? (int)left : kSortTile;          // valid keys of the tile = local positions in use
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        const int lp = j * kSortThreads + tid;
+        if (lp < cnt) {
+            const uint32_t k = s_keys[lp];
+            const uint32_t pos = s_base[(k >> shift) & 255u] + (uint32_t)lp;
+            keys_out[pos] = k;
+            labs_out[pos] = s_labs[lp];
+        }
+    }
+#else
 #pragma unroll
     for (int j = 0; j < kSortItems; ++j) {
         if ((base + j * 32 + lane) < n) {
@@ -279,6 +321,7 @@ auc_sort_pass_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __rest
             labs_out[pos] = lab[j];
         }
     }
+#endif
 }
 
 // Warp-parallel decoupled look-back over packed 64-bit tile states: [63:62] flag, [61:31] a, [30:0] b.
@@ -322,57 +365,87 @@ __device__ __forceinline__ void lookback_pair(unsigned long long* status, unsign
 // ------------------------------------------------------------------------------------------ 3 distinct
 // sklearn _binary_clf_curve: distinct_value_indices = where(diff(sorted_scores)); threshold_idxs = r_[., n-1];
 // tps = cumsum(y)[idxs]; fps = 1 + idxs - tps.
+// Layout of both scan kernels: a warp owns 32 * kScanItems consecutive elements, lane l the elements l, 32 + l, ... of
+// them (every load a full 128-byte line, neighbours by shuffle).  Flags and label bits are single bits, so the scan inside
+// a warp is ballot + popc, and the kept elements of a warp leave as dense runs (lane order = element order): coalesced
+// stores.  (The thread-contiguous form this replaces touched 32 sectors per load and per store instruction and took
+// 24 + 18 us at 1 M scores.)
+// exclusive prefix over the 8 warps of (a, b) given per warp by lane 0; totals in tot_a / tot_b
+__device__ __forceinline__ void warp_totals_excl(uint32_t a, uint32_t b, uint32_t (*s_w)[8], uint32_t& ex_a, uint32_t& ex_b,
+                                                 uint32_t& tot_a, uint32_t& tot_b) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_w[0][warp] = a; s_w[1][warp] = b; }
+    __syncthreads();
+    ex_a = ex_b = tot_a = tot_b = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t ta = s_w[0][w], tb = s_w[1][w];
+        if (w < warp) { ex_a += ta; ex_b += tb; }
+        tot_a += ta; tot_b += tb;
+    }
+}
+
 __global__ void __launch_bounds__(kScanThreads)
 auc_distinct_kernel(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ labs, AucControl* c,
                     unsigned long long* status, uint32_t* __restrict__ d_tps, uint32_t* __restrict__ d_fps,
                     uint32_t* __restrict__ d_key) {
-    __shared__ uint32_t s_tmp[8];
+    __shared__ uint32_t s_w[2][8];
     __shared__ uint32_t s_excl[2];
     __shared__ unsigned int s_tile;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(&c->tickets[4], 1u);
     __syncthreads();
     const unsigned int tile = s_tile;
     const int64_t nv = (int64_t)c->n_valid;
-    const int64_t base = (int64_t)tile * kScanTile + tid * kScanItems;
     if ((int64_t)tile * kScanTile >= nv) return;          // whole tile beyond the kept rows (uniform per block)
-    uint32_t k[kScanItems + 1];
-    uint32_t f[kScanItems], l[kScanItems];
+    const int64_t wbase = (int64_t)tile * kScanTile + warp * (32 * kScanItems);
+    uint32_t k[kScanItems], lb[kScanItems], fb[kScanItems];            // lb / fb: warp-uniform ballots (lb: the label first)
 #pragma unroll
-    for (int j = 0; j <= kScanItems; ++j) k[j] = (base + j < nv) ? keys[base + j] : 0u;
+    for (int j = 0; j < kScanItems; ++j) {
+        const int64_t i = wbase + j * 32 + lane;
+        k[j] = (i < nv) ? keys[i] : 0u;
+        lb[j] = (i < nv) ? (uint32_t)labs[i] : 0u;        // (all loads go out before the first vote below)
+    }
+    const int64_t after = wbase + 32 * kScanItems;                      // first element of the next warp's chunk
+    const uint32_t k_after = (after < nv) ? keys[after] : 0u;
     uint32_t fc = 0, lc = 0;
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
-        const int64_t i = base + j;
-        const bool in = i < nv;
-        l[j] = in ? (uint32_t)labs[i] : 0u;
-        f[j] = in && (i == nv - 1 || k[j] != k[j + 1]);
-        fc += f[j];
-        lc += l[j];
+        const int64_t i = wbase + j * 32 + lane;
+        const uint32_t dn = __shfl_down_sync(kFullMask, k[j], 1);
+        const uint32_t first_next = (j + 1 < kScanItems) ? __shfl_sync(kFullMask, k[(j + 1 < kScanItems) ? j + 1 : j], 0) : k_after;
+        const uint32_t kn = (lane == 31) ? first_next : dn;
+        const bool f = (i < nv) && (i == nv - 1 || k[j] != kn);
+        fb[j] = __ballot_sync(kFullMask, f);
+        lb[j] = __ballot_sync(kFullMask, lb[j] != 0u);
+        fc += __popc(fb[j]);
+        lc += __popc(lb[j]);
     }
-    uint32_t tot_f, tot_l;
-    uint32_t ex_f = block_excl_scan_256(fc, s_tmp, &tot_f);
-    uint32_t ex_l = block_excl_scan_256(lc, s_tmp, &tot_l);
+    uint32_t ex_f, ex_l, tot_f, tot_l;
+    warp_totals_excl(fc, lc, s_w, ex_f, ex_l, tot_f, tot_l);
     if (tid < 32) {
         uint32_t ea, eb;
         lookback_pair(status, tile, tot_f, tot_l, ea, eb, c);
         if (tid == 0) { s_excl[0] = ea; s_excl[1] = eb; }
     }
     __syncthreads();
-    uint32_t slot = s_excl[0] + ex_f;
-    uint32_t tps = s_excl[1] + ex_l;
+    uint32_t slot0 = s_excl[0] + ex_f;                   // slot of the warp's next kept element
+    uint32_t tps0 = s_excl[1] + ex_l;                    // positives before the warp's next row of 32
+    const uint32_t lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
-        tps += l[j];
-        if (f[j]) {
-            const uint32_t i = (uint32_t)(base + j);
+        if ((fb[j] >> lane) & 1u) {
+            const int64_t i = wbase + j * 32 + lane;
+            const uint32_t slot = slot0 + __popc(fb[j] & lt_mask);
+            const uint32_t tps = tps0 + __popc(lb[j] & le_mask);
             d_tps[slot] = tps;
-            d_fps[slot] = 1u + i - tps;
+            d_fps[slot] = 1u + (uint32_t)i - tps;
             d_key[slot] = k[j];
-            ++slot;
+            if (i == nv - 1) c->n_distinct = slot + 1;    // the last row always closes a run
         }
+        slot0 += __popc(fb[j]);
+        tps0 += __popc(lb[j]);
     }
-    if (base <= nv - 1 && nv - 1 < base + kScanItems) c->n_distinct = slot;   // the thread owning the last row
 }
 
 // ------------------------------------------------------------------------------------------ 4 corners
@@ -382,59 +455,72 @@ __global__ void __launch_bounds__(kScanThreads)
 auc_corner_kernel(const uint32_t* __restrict__ d_tps, const uint32_t* __restrict__ d_fps,
                   const uint32_t* __restrict__ d_key, AucControl* c, unsigned long long* status,
                   uint32_t* __restrict__ k_tps, uint32_t* __restrict__ k_fps, float* __restrict__ thr_out) {
-    __shared__ uint32_t s_tmp[8];
+    __shared__ uint32_t s_w[2][8];
     __shared__ uint32_t s_excl;
     __shared__ unsigned int s_tile;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(&c->tickets[5], 1u);
     __syncthreads();
     const unsigned int tile = s_tile;
     const int64_t m = (int64_t)c->n_distinct;
     if ((int64_t)tile * kScanTile >= m) return;
-    const int64_t base = (int64_t)tile * kScanTile + tid * kScanItems;
     if (tile == 0 && tid == 0) {
         k_tps[0] = 0; k_fps[0] = 0;
         if (thr_out) thr_out[0] = INFINITY;
     }
-    int64_t tp[kScanItems + 2], fp[kScanItems + 2];
-#pragma unroll
-    for (int j = 0; j < kScanItems + 2; ++j) {
-        const int64_t i = base + j - 1;
-        const bool in = (i >= 0 && i < m);
-        tp[j] = in ? (int64_t)d_tps[i] : 0;
-        fp[j] = in ? (int64_t)d_fps[i] : 0;
-    }
-    uint32_t keep[kScanItems], kc = 0;
+    const int64_t wbase = (int64_t)tile * kScanTile + warp * (32 * kScanItems);
+    uint32_t tp[kScanItems], fp[kScanItems], kb[kScanItems];           // kb: warp-uniform ballot of the kept points
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
-        const int64_t i = base + j;
-        bool kp = false;
-        if (i < m) {
-            kp = (m <= 2) || i == 0 || i == m - 1 || (fp[j] - 2 * fp[j + 1] + fp[j + 2] != 0) ||
-                 (tp[j] - 2 * tp[j + 1] + tp[j + 2] != 0);
-        }
-        keep[j] = kp;
-        kc += kp;
+        const int64_t i = wbase + j * 32 + lane;
+        tp[j] = (i < m) ? d_tps[i] : 0u;
+        fp[j] = (i < m) ? d_fps[i] : 0u;
     }
-    uint32_t tot;
-    uint32_t ex = block_excl_scan_256(kc, s_tmp, &tot);
+    // the points just before and just after the warp's chunk (values outside [0, m) are never used: the first and the
+    // last point are kept unconditionally)
+    const int64_t before = wbase - 1, after = wbase + 32 * kScanItems;
+    const uint32_t tp_before = (before >= 0 && before < m) ? d_tps[before] : 0u, fp_before = (before >= 0 && before < m) ? d_fps[before] : 0u;
+    const uint32_t tp_after = (after < m) ? d_tps[after] : 0u, fp_after = (after < m) ? d_fps[after] : 0u;
+    uint32_t kc = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        const int64_t i = wbase + j * 32 + lane;
+        const uint32_t tu = __shfl_up_sync(kFullMask, tp[j], 1), fu = __shfl_up_sync(kFullMask, fp[j], 1);
+        const uint32_t td = __shfl_down_sync(kFullMask, tp[j], 1), fd = __shfl_down_sync(kFullMask, fp[j], 1);
+        const uint32_t tl = (j > 0) ? __shfl_sync(kFullMask, tp[(j > 0) ? j - 1 : 0], 31) : tp_before;
+        const uint32_t fl = (j > 0) ? __shfl_sync(kFullMask, fp[(j > 0) ? j - 1 : 0], 31) : fp_before;
+        const uint32_t tn = (j + 1 < kScanItems) ? __shfl_sync(kFullMask, tp[(j + 1 < kScanItems) ? j + 1 : j], 0) : tp_after;
+        const uint32_t fn = (j + 1 < kScanItems) ? __shfl_sync(kFullMask, fp[(j + 1 < kScanItems) ? j + 1 : j], 0) : fp_after;
+        const int64_t t0 = (lane == 0) ? tl : tu, f0 = (lane == 0) ? fl : fu;       // point i - 1
+        const int64_t t2 = (lane == 31) ? tn : td, f2 = (lane == 31) ? fn : fd;     // point i + 1
+        const int64_t t1 = tp[j], f1 = fp[j];
+        bool kp = false;
+        if (i < m) kp = (m <= 2) || i == 0 || i == m - 1 || (f0 - 2 * f1 + f2 != 0) || (t0 - 2 * t1 + t2 != 0);
+        kb[j] = __ballot_sync(kFullMask, kp);
+        kc += __popc(kb[j]);
+    }
+    uint32_t ex, ex_unused, tot, tot_unused;
+    warp_totals_excl(kc, 0u, s_w, ex, ex_unused, tot, tot_unused);
     if (tid < 32) {
         uint32_t ea, eb;
         lookback_pair(status, tile, tot, 0u, ea, eb, c);
         if (tid == 0) s_excl = ea;
     }
     __syncthreads();
-    uint32_t slot = s_excl + ex + 1;           // +1: the prepended origin
+    uint32_t slot0 = s_excl + ex + 1;           // +1: the prepended origin
+    const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
-        if (keep[j]) {
-            k_tps[slot] = (uint32_t)tp[j + 1];
-            k_fps[slot] = (uint32_t)fp[j + 1];
-            if (thr_out) thr_out[slot] = key_to_score(d_key[base + j]);
-            ++slot;
+        if ((kb[j] >> lane) & 1u) {
+            const int64_t i = wbase + j * 32 + lane;
+            const uint32_t slot = slot0 + __popc(kb[j] & lt_mask);
+            k_tps[slot] = tp[j];
+            k_fps[slot] = fp[j];
+            if (thr_out) thr_out[slot] = key_to_score(d_key[i]);
+            if (i == m - 1) c->n_kept = slot;     // the last point is always kept; the count excludes the origin
         }
+        slot0 += __popc(kb[j]);
     }
-    if (base <= m - 1 && m - 1 < base + kScanItems) c->n_kept = slot - 1;
 }
 
 // ------------------------------------------------------------------------------------------ 5 terms

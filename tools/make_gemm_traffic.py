@@ -20,7 +20,13 @@ def rows_of(rep):
 
 def main():
     build_id = sys.argv[1]
-    out = {"build_id": build_id, "batch": 512, "by_dtype": {},
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from eoe_b200 import build as b
+    # gemm_source_id: identity of the sources the GEMM kernels are compiled from -- only meaningful if the profiled library
+    # was built from the sources in the tree (build_id == source_id())
+    out = {"build_id": build_id, "gemm_source_id": b.gemm_source_id() if b.source_id() == build_id else None,
+           "batch": 512, "by_dtype": {},
            "how": "ncu --set full --clock-control none of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-side "
                   "--dtype <dtype>` after the same command exited 0 without ncu (tools/run_profile_r2.sh); per launch"}
     to_b = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
