@@ -20,8 +20,19 @@ namespace cg = cooperative_groups;
 namespace eoe {
 
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;
+#ifndef EOE_AUC_SORT_ITEMS
+#define EOE_AUC_SORT_ITEMS 16
+#endif
+constexpr int kSortItems = EOE_AUC_SORT_ITEMS;
 constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 keys per tile
+#ifndef EOE_AUC_BALLOT_RANK
+#define EOE_AUC_BALLOT_RANK 0                          // 1: rank with eight ballots per key instead of match.any (A/B builds)
+#endif
+#ifndef EOE_AUC_KEYS_V2
+#define EOE_AUC_KEYS_V2 1                              // 0: the round-1 keys kernel (A/B builds)
+#endif
+constexpr int kKeysThreads = EOE_AUC_KEYS_V2 ? 1024 : 256;
+constexpr int kKeysBatch = 4;                          // rows per thread and trip (loads issued together)
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;   // 2048
@@ -109,35 +120,58 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
 
 // ------------------------------------------------------------------------------------------ 1 keys
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kKeysThreads)
 auc_keys_kernel(const T* __restrict__ scores, const int64_t* __restrict__ labels, int64_t n, int flags,
                 uint32_t* __restrict__ keys, uint8_t* __restrict__ labs, AucControl* c) {
     __shared__ uint32_t s_hist[4 * 256];
     __shared__ unsigned int s_cnt[3];
-    for (int i = threadIdx.x; i < 1024; i += 256) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < 1024; i += kKeysThreads) s_hist[i] = 0;
     if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     unsigned int nv = 0, np = 0, bad = 0;
     const bool ignore_neg = flags & EOE_AUC_IGNORE_NEGATIVE_LABELS;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const float f = to_f32<T>(scores[i]);
-        const int64_t l = labels[i];
-        const bool valid = !(ignore_neg && l < 0);
-        uint32_t key = 0xffffffffu;      // dropped rows sort behind every finite score
-        uint8_t lb = 0;
-        if (valid) {
-            if (!isfinite(f)) bad = 1;
-            key = desc_key(f);
-            lb = (l == 1);
-            nv++;
-            np += lb;
+#if EOE_AUC_KEYS_V2
+    // One block of 1024 threads per SM at most: every block ends with up to 1024 atomics onto the same 4 KB of global
+    // counters, so fewer, larger blocks (148 x 1024 adds instead of 489 x 1024 at 1 M scores); kKeysBatch rows per thread
+    // are loaded before the first is used (48 KB in flight per SM)
+    for (int64_t i0 = (int64_t)blockIdx.x * (kKeysThreads * kKeysBatch); i0 < n; i0 += (int64_t)gridDim.x * (kKeysThreads * kKeysBatch)) {
+        float fv[kKeysBatch];
+        int64_t lv[kKeysBatch];
+#pragma unroll
+        for (int q = 0; q < kKeysBatch; ++q) {
+            const int64_t i = i0 + q * kKeysThreads + threadIdx.x;
+            fv[q] = (i < n) ? to_f32<T>(scores[i]) : 0.f;
+            lv[q] = (i < n) ? labels[i] : 0;
         }
-        keys[i] = key;
-        labs[i] = lb;
-        atomicAdd(&s_hist[key & 255], 1u);
-        atomicAdd(&s_hist[256 + ((key >> 8) & 255)], 1u);
-        atomicAdd(&s_hist[512 + ((key >> 16) & 255)], 1u);
-        atomicAdd(&s_hist[768 + (key >> 24)], 1u);
+#pragma unroll
+        for (int q = 0; q < kKeysBatch; ++q) {
+            const int64_t i = i0 + q * kKeysThreads + threadIdx.x;
+            if (i >= n) continue;
+            const float f = fv[q];
+            const int64_t l = lv[q];
+#else
+    {
+        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+            const float f = to_f32<T>(scores[i]);
+            const int64_t l = labels[i];
+#endif
+            const bool valid = !(ignore_neg && l < 0);
+            uint32_t key = 0xffffffffu;      // dropped rows sort behind every finite score
+            uint8_t lb = 0;
+            if (valid) {
+                if (!isfinite(f)) bad = 1;
+                key = desc_key(f);
+                lb = (l == 1);
+                nv++;
+                np += lb;
+            }
+            keys[i] = key;
+            labs[i] = lb;
+            atomicAdd(&s_hist[key & 255], 1u);
+            atomicAdd(&s_hist[256 + ((key >> 8) & 255)], 1u);
+            atomicAdd(&s_hist[512 + ((key >> 16) & 255)], 1u);
+            atomicAdd(&s_hist[768 + (key >> 24)], 1u);
+        }
     }
     nv = __reduce_add_sync(kFullMask, nv);
     np = __reduce_add_sync(kFullMask, np);
@@ -148,7 +182,7 @@ auc_keys_kernel(const T* __restrict__ scores, const int64_t* __restrict__ labels
         atomicOr(&s_cnt[2], bad);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 1024; i += 256)
+    for (int i = threadIdx.x; i < 1024; i += kKeysThreads)
         if (s_hist[i]) atomicAdd(&c->hist[i], s_hist[i]);
     if (threadIdx.x == 0) {
         atomicAdd(&c->n_valid, (unsigned long long)s_cnt[0]);
@@ -223,7 +257,18 @@ auc_sort_pass_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __rest
     for (int j = 0; j < kSortItems; ++j) {
         const bool valid = (base + j * 32 + lane) < n;
         const uint32_t d = (key[j] >> shift) & 255u;
+#if EOE_AUC_BALLOT_RANK
+        uint32_t mask = __ballot_sync(kFullMask, valid);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t bal = __ballot_sync(kFullMask, bit);
+            mask &= bit ? bal : ~bal;
+        }
+        if (!valid) mask = 1u << lane;
+#else
         const uint32_t mask = __match_any_sync(kFullMask, valid ? d : (256u + lane));
+#endif
         const int leader = __ffs(mask) - 1;
         uint32_t old = 0;
         if (lane == leader && valid) {
@@ -603,9 +648,10 @@ pairwise_leaves_kernel(const double* __restrict__ a, const unsigned long long* n
 }
 
 // internal nodes of the numpy pairwise tree, bottom-up, by one block of NT threads (barrier per level)
+// levels D - 1 ... stop (a node's existence and heap slot depend on T and its own level only)
 template <int NT>
-__device__ __forceinline__ void pairwise_tree_levels(int64_t T, int D, double* nodes) {
-    for (int lvl = D - 1; lvl >= 0; --lvl) {
+__device__ __forceinline__ void pairwise_tree_levels(int64_t T, int D, double* nodes, int stop = 0) {
+    for (int lvl = D - 1; lvl >= stop; --lvl) {
         for (int64_t p = threadIdx.x; p < ((int64_t)1 << lvl); p += NT) {
             int64_t len = T;
             bool exists = true;
@@ -624,12 +670,55 @@ __device__ __forceinline__ void pairwise_tree_levels(int64_t T, int D, double* n
 }
 
 // Internal nodes bottom-up (single block); finally writes the result (NaN if the curve is undefined).
+// The top kTreeSmemDepth levels run in shared memory: in global memory every level is a dependent load + store + barrier
+// (an L2 round trip per level, 13 of them at 1 M terms) and every node re-derives its length by walking down from the
+// root.  Here the heap [1, 2 << Dc) is fetched once (batched loads), the node lengths are produced top-down (a child's
+// length follows from its parent's), and the sums go bottom-up, all behind __syncthreads(): same additions, same order.
+// Levels >= kTreeSmemDepth (more than ~2 M terms) are reduced in global memory first.
+constexpr int kTreeSmemDepth = 13;              // 2 << 13 doubles (128 KB) + 1 << 13 lengths (32 KB)
 __global__ void __launch_bounds__(1024)
 pairwise_tree_kernel(const unsigned long long* n_ptr, int64_t n_minus, double* __restrict__ nodes, AucControl* c,
-                     double* __restrict__ out, int negate_clip) {
+                     double* __restrict__ out, int negate_clip, int64_t* info /* last launch of a call: counts + status */) {
+    extern __shared__ double s_nodes[];
     const int64_t T = (int64_t)(*n_ptr) - n_minus;
     const int D = (T > 0) ? dev_pairwise_depth(T) : 0;
-    pairwise_tree_levels<1024>(T, D, nodes);
+    const int Dc = D < kTreeSmemDepth ? D : kTreeSmemDepth;
+    uint32_t* s_len = reinterpret_cast<uint32_t*>(s_nodes + ((size_t)2 << Dc));   // [1 << Dc): lengths of levels < Dc
+    pairwise_tree_levels<1024>(T, D, nodes, Dc);                     // (no-op unless D > kTreeSmemDepth; ends with a barrier)
+    const int total = 2 << Dc;
+    for (int i0 = 0; i0 < total; i0 += 8 * 1024) {                    // up to 8 independent loads per thread in flight
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = i0 + q * 1024 + threadIdx.x;
+            v[q] = (i >= 1 && i < total) ? nodes[i] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = i0 + q * 1024 + threadIdx.x;
+            if (i >= 1 && i < total) s_nodes[i] = v[q];
+        }
+    }
+    if (threadIdx.x == 0 && Dc > 0) s_len[1] = (uint32_t)T;           // (Dc > 0 implies 128 < T; T < 2^31)
+    __syncthreads();
+    for (int lvl = 0; lvl + 1 < Dc; ++lvl) {                         // lengths of level lvl + 1 from level lvl
+        for (int p = threadIdx.x; p < (1 << lvl); p += 1024) {
+            const int heap = (1 << lvl) + p;
+            const uint32_t len = s_len[heap];
+            const uint32_t h = (len > 128u) ? ((len >> 1) & ~7u) : 0u;   // 0: no such node (or a leaf's absent children)
+            s_len[2 * heap] = h;
+            s_len[2 * heap + 1] = (len > 128u) ? (len - h) : 0u;
+        }
+        __syncthreads();
+    }
+    for (int lvl = Dc - 1; lvl >= 0; --lvl) {
+        for (int p = threadIdx.x; p < (1 << lvl); p += 1024) {
+            const int heap = (1 << lvl) + p;
+            if (s_len[heap] > 128u) s_nodes[heap] = __dadd_rn(s_nodes[2 * heap], s_nodes[2 * heap + 1]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) nodes[1] = s_nodes[1];
     if (threadIdx.x == 0) {
         double v = nodes[1];
         if (negate_clip) v = fmax(0.0, -v);
@@ -637,6 +726,10 @@ pairwise_tree_kernel(const unsigned long long* n_ptr, int64_t n_minus, double* _
         if (single) atomicOr(&c->status, (uint32_t)EOE_AUC_STATUS_SINGLE_CLASS);
         if (single || (c->status & ~(uint32_t)EOE_AUC_STATUS_SINGLE_CLASS)) v = __longlong_as_double(0x7ff8000000000000LL);
         *out = v;
+        if (info) {
+            info[0] = (int64_t)c->n_valid; info[1] = (int64_t)c->n_pos; info[2] = (int64_t)c->n_distinct;
+            info[3] = (int64_t)c->n_kept + 1; info[4] = (int64_t)c->status; info[5] = info[6] = info[7] = 0;
+        }
     }
 }
 
@@ -663,11 +756,6 @@ auc_prc_terms_kernel(const uint32_t* __restrict__ d_tps, const uint32_t* __restr
         if (pthr_out) pthr_out[i] = key_to_score(d_key[j]);     // thresholds[::-1]: the distinct scores, increasing
     }
     if (prec_out && blockIdx.x == 0 && threadIdx.x == 0) { prec_out[m] = 1.0; rec_out[m] = 0.0; }
-}
-
-__global__ void auc_info_kernel(const AucControl* c, int64_t* info) {
-    info[0] = (int64_t)c->n_valid; info[1] = (int64_t)c->n_pos; info[2] = (int64_t)c->n_distinct;
-    info[3] = (int64_t)c->n_kept + 1; info[4] = (int64_t)c->status; info[5] = info[6] = info[7] = 0;
 }
 
 
@@ -1438,9 +1526,14 @@ static int auc_run(const void* scores, const int64_t* labels, int64_t n, int fla
     uint32_t* sort_status = (uint32_t*)(ws + L.sort_status);
     cudaError_t e = cudaMemsetAsync(ws, 0, L.control_bytes, st);
     if (e != cudaSuccess) { set_cuda_error(e, "auc memset"); return EOE_ERR_CUDA; }
+#if EOE_AUC_KEYS_V2
+    int kgrid = (int)((n + kKeysThreads * kKeysBatch - 1) / (kKeysThreads * kKeysBatch));
+    if (kgrid > kNumSMs) kgrid = kNumSMs;
+#else
     int kgrid = (int)((n + 256 * 8 - 1) / (256 * 8));
     if (kgrid > kNumSMs * 8) kgrid = kNumSMs * 8;
-    auc_keys_kernel<T><<<kgrid, 256, 0, st>>>((const T*)scores, labels, n, flags, keys_a, labs_a, c);
+#endif
+    auc_keys_kernel<T><<<kgrid, kKeysThreads, 0, st>>>((const T*)scores, labels, n, flags, keys_a, labs_a, c);
     for (int pass = 0; pass < 4; ++pass) {
         const bool fwd = (pass & 1) == 0;
         auc_sort_pass_kernel<<<L.sort_tiles, kSortThreads, 0, st>>>(
@@ -1462,15 +1555,22 @@ static int auc_run(const void* scores, const int64_t* labels, int64_t n, int fla
     if (tgrid > kNumSMs * 4) tgrid = kNumSMs * 4;
     auc_terms_kernel<<<tgrid, 256, 0, st>>>(k_tps, k_fps, c, terms, fpr_out, tpr_out);
     const int lgrid = (int)((((int64_t)8 << L.max_depth) + 255) / 256);
+    const int tdepth = L.max_depth < kTreeSmemDepth ? L.max_depth : kTreeSmemDepth;
+    const size_t tree_smem = ((size_t)2 << tdepth) * sizeof(double) + ((size_t)1 << tdepth) * sizeof(uint32_t);
+    if (tree_smem > 48 * 1024) {                 // per device and idempotent; only past ~0.2 M scores
+        e = cudaFuncSetAttribute(pairwise_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(((size_t)2 << kTreeSmemDepth) * sizeof(double) + ((size_t)1 << kTreeSmemDepth) * sizeof(uint32_t)));
+        if (e != cudaSuccess) { set_cuda_error(e, "pairwise_tree smem attr"); return EOE_ERR_CUDA; }
+    }
     pairwise_leaves_kernel<<<lgrid, 256, 0, st>>>(terms, &c->n_kept, 0, nodes);
-    pairwise_tree_kernel<<<1, 1024, 0, st>>>(&c->n_kept, 0, nodes, c, auc_out, 0);
+    const bool prc = (flags & EOE_AUC_WITH_PRC) != 0;
+    pairwise_tree_kernel<<<1, 1024, tree_smem, st>>>(&c->n_kept, 0, nodes, c, auc_out, 0, prc ? nullptr : info_out);
     if (flags & EOE_AUC_WITH_PRC) {
         auc_prc_terms_kernel<<<tgrid, 256, 0, st>>>(d_tps, d_fps, keys_b, c, terms, prec_out, rec_out, pthr_out);
         pairwise_leaves_kernel<<<lgrid, 256, 0, st>>>(terms, &c->n_distinct, 0, nodes);
-        pairwise_tree_kernel<<<1, 1024, 0, st>>>(&c->n_distinct, 0, nodes, c, auc_out + 1, 1);
+        pairwise_tree_kernel<<<1, 1024, tree_smem, st>>>(&c->n_distinct, 0, nodes, c, auc_out + 1, 1, info_out);
     }
-    if (info_out) auc_info_kernel<<<1, 1, 0, st>>>(c, info_out);
-    return check_launch("auc pipeline", 10 + ((flags & EOE_AUC_WITH_PRC) ? 3 : 0) + (info_out ? 1 : 0));
+    return check_launch("auc pipeline", 10 + (prc ? 3 : 0));
 }
 
 }  // namespace eoe
