@@ -20,11 +20,17 @@ namespace cg = cooperative_groups;
 namespace eoe {
 
 constexpr int kSortThreads = 256;
+// Keys per thread of a sort tile: 16 (4096-key tiles) or, up to kSortSmallTileMax scores, 8 (2048-key tiles: below ~150
+// large tiles part of the SMs would idle; measured 8 - 17 % faster up to 512 k scores, a tie at 640 - 768 k, 7 % slower at
+// 1 M, within +-5 % beyond -- profiles/r2_auc_tile_size_sweep.jsonl)
 #ifndef EOE_AUC_SORT_ITEMS
-#define EOE_AUC_SORT_ITEMS 16
+#define EOE_AUC_SORT_ITEMS 0                           // 8 / 16: force one tile size (A/B builds)
 #endif
-constexpr int kSortItems = EOE_AUC_SORT_ITEMS;
-constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 keys per tile
+constexpr int64_t kSortSmallTileMax = 640 * 1024;
+static inline int sort_items_for(int64_t n) {
+    if (EOE_AUC_SORT_ITEMS) return EOE_AUC_SORT_ITEMS;
+    return n <= kSortSmallTileMax ? 8 : 16;
+}
 #ifndef EOE_AUC_BALLOT_RANK
 #define EOE_AUC_BALLOT_RANK 0                          // 1: rank with eight ballots per key instead of match.any (A/B builds)
 #endif
@@ -34,7 +40,10 @@ constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 keys per tile
 constexpr int kKeysThreads = EOE_AUC_KEYS_V2 ? 1024 : 256;
 constexpr int kKeysBatch = 4;                          // rows per thread and trip (loads issued together)
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
+#ifndef EOE_AUC_SCAN_ITEMS
+#define EOE_AUC_SCAN_ITEMS 8
+#endif
+constexpr int kScanItems = EOE_AUC_SCAN_ITEMS;
 constexpr int kScanTile = kScanThreads * kScanItems;   // 2048
 constexpr uint32_t kFlagAgg = 1u, kFlagIncl = 2u;
 constexpr int kSpinLimit = 1 << 20;                     // bounded spins: a protocol bug must not hang the GPU
@@ -67,12 +76,18 @@ static int pairwise_depth(int64_t n) {
 
 static AucLayout auc_layout(int64_t n) {
     AucLayout L;
-    L.sort_tiles = (int)((n + kSortTile - 1) / kSortTile);
+    const int64_t sort_tile = (int64_t)kSortThreads * sort_items_for(n);
+    L.sort_tiles = (int)((n + sort_tile - 1) / sort_tile);
     L.scan_tiles = (int)((n + kScanTile - 1) / kScanTile);
     L.max_depth = pairwise_depth(n);
     size_t o = 0;
     L.control = o; o = align_up(o + sizeof(AucControl), 256);
-    L.sort_status = o; o = align_up(o + (size_t)4 * L.sort_tiles * 256 * 4, 256);
+    // (reserved for the larger of the two tile counts a smaller n could need: eoe_auc_workspace_bytes stays monotone in n,
+    //  which grow-only callers rely on)
+    const int64_t small_n = n < kSortSmallTileMax ? n : kSortSmallTileMax;
+    const int64_t small_tiles = EOE_AUC_SORT_ITEMS ? 0 : (small_n + kSortThreads * 8 - 1) / (kSortThreads * 8);
+    const int64_t status_tiles = L.sort_tiles > small_tiles ? L.sort_tiles : small_tiles;
+    L.sort_status = o; o = align_up(o + (size_t)4 * status_tiles * 256 * 4, 256);
     L.scan1_status = o; o = align_up(o + (size_t)L.scan_tiles * 8, 256);
     L.scan2_status = o; o = align_up(o + (size_t)L.scan_tiles * 8, 256);
     L.control_bytes = o;
@@ -223,6 +238,7 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
 #ifndef EOE_AUC_DIRECT_SCATTER
 #define EOE_AUC_DIRECT_SCATTER 0                        // 1: the round-1 form (registers -> global), kept for A/B builds
 #endif
+template <int kSortItems>
 __global__ void __launch_bounds__(kSortThreads)
 auc_sort_pass_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                      uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int64_t n, int pass,
@@ -231,6 +247,7 @@ auc_sort_pass_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __rest
     __shared__ uint32_t s_base[256];
     __shared__ uint32_t s_tmp[8];
     __shared__ unsigned int s_tile;
+    constexpr int kSortTile = kSortThreads * kSortItems;
 #if !EOE_AUC_DIRECT_SCATTER
     __shared__ uint32_t s_keys[kSortTile];
     __shared__ uint8_t s_labs[kSortTile];
@@ -1536,7 +1553,8 @@ static int auc_run(const void* scores, const int64_t* labels, int64_t n, int fla
     auc_keys_kernel<T><<<kgrid, kKeysThreads, 0, st>>>((const T*)scores, labels, n, flags, keys_a, labs_a, c);
     for (int pass = 0; pass < 4; ++pass) {
         const bool fwd = (pass & 1) == 0;
-        auc_sort_pass_kernel<<<L.sort_tiles, kSortThreads, 0, st>>>(
+        auto sort_pass = sort_items_for(n) == 8 ? auc_sort_pass_kernel<8> : auc_sort_pass_kernel<16>;
+        sort_pass<<<L.sort_tiles, kSortThreads, 0, st>>>(
             fwd ? keys_a : keys_b, fwd ? labs_a : labs_b, fwd ? keys_b : keys_a, fwd ? labs_b : labs_a, n, pass, c,
             sort_status + (size_t)pass * L.sort_tiles * 256);
     }

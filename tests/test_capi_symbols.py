@@ -46,6 +46,17 @@ def test_python_binding_covers_header_and_loads():
     assert l.eoe_auc_workspace_bytes(0) == 0
 
 
+def test_auc_workspace_bytes_is_monotone():
+    """Grow-only callers (eoe_b200.metrics.AucWorkspace) reuse a workspace sized for a larger n: the size must never shrink
+    as n grows -- also across the sizes where the sort switches tile size (640 k) and the single-launch paths end."""
+    from eoe_b200 import _lib
+    l = _lib.lib()
+    ns = sorted(set(list(range(1, 70000, 997)) + [12288, 12289, 16384, 16385, 49152, 49153]
+                    + list(range(640 * 1024 - 5000, 640 * 1024 + 5000, 61)) + [1 << 20, 1 << 21, 3 << 20, 1 << 24]))
+    sizes = [l.eoe_auc_workspace_bytes(n) for n in ns]
+    assert all(b >= a for a, b in zip(sizes, sizes[1:])), [(n, a, b) for n, a, b in zip(ns[1:], sizes, sizes[1:]) if b < a][:3]
+
+
 def test_argument_validation_without_gpu(lib):
     """Entry points reject bad arguments before touching the device."""
     lib.eoe_hsc_score.restype = ctypes.c_int

@@ -85,6 +85,22 @@ def test_auc_permutation_invariance_and_reuse():
     assert abs(metrics.roc_auc(-s, y) - (1 - a)) < 1e-12
 
 
+def test_auc_sort_tile_switch_and_grown_workspace():
+    """The sort uses 2048-key tiles up to 655 360 scores and 4096-key tiles above: both sides of the switch against sklearn,
+    the smaller size through a workspace that was sized for the larger one (grow-only reuse)."""
+    from sklearn.metrics import roc_auc_score
+    from eoe_b200 import metrics
+    rng = np.random.default_rng(11)
+    ws = metrics.AucWorkspace()
+    for n in (700_001, 655_361, 655_360, 300_000):
+        s = (1 - np.exp(-np.abs(rng.standard_normal(n)))).astype(np.float32)
+        y = (rng.random(n) < 0.3).astype(np.int64)
+        out, info, _ = metrics.roc_auc_device(torch.from_numpy(s).to(DEV), torch.from_numpy(y).to(DEV), workspace=ws)
+        assert int(info[4].item()) == 0
+        assert out[0].item() == roc_auc_score(y, s), n
+    assert ws.n == 700_001
+
+
 def test_auc_ignore_negative_labels_and_errors():
     from eoe_b200 import metrics
     rng = np.random.default_rng(4)

@@ -90,7 +90,7 @@ def test_clip_heads_write_only_their_outputs(n, K, dtype):
         assert torch.isfinite(grad.t.float()).all()
 
 
-@pytest.mark.parametrize("n", [1, 2, 3001, 16384, 16385, 70001])
+@pytest.mark.parametrize("n", [1, 2, 3001, 16384, 16385, 70001, 655360, 655361])      # 655 360: last size with 2048-key sort tiles
 def test_auc_writes_only_its_outputs_and_workspace(n):
     L, lib = _lib()
     rng = np.random.default_rng(n)

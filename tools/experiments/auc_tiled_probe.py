@@ -9,7 +9,8 @@ from eoe_b200 import _lib, metrics  # noqa: E402
 dev = "cuda"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 tag = os.environ.get("EOE_B200_LIB", "default")
-for n in (65536, 262144, 1000000, 1 << 20, 1 << 22, 1 << 24):
+SIZES = [int(a) for a in sys.argv[1:]] or [65536, 262144, 1000000, 1 << 20, 1 << 22, 1 << 24]
+for n in SIZES:
     s = 1 - torch.exp(-torch.randn(n, device=dev).abs())
     y = (torch.rand(n, device=dev) < 0.5).long()
     ws = metrics.AucWorkspace()
