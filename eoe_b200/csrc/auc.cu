@@ -3,13 +3,16 @@
 //
 // Pipeline (all on the caller's stream, no host sync; every size after the sort is a DEVICE value):
 //   1 keys      score -> descending-sortable u32 key (-0.0 == +0.0), label bit, 4x256 digit histogram, counts
-//   2 sort      4 LSD radix passes (8 bit), one kernel each: per-warp match_any ranking + decoupled look-back
+//   2 sort      4 LSD radix passes (8 bit), one kernel each: per-warp match_any ranking + decoupled look-back, the tile
+//               reordered by digit in shared memory so that the scatter writes whole runs
 //   3 distinct  tie merge: flag last element of every run of equal keys, inclusive label count -> (tps, fps)
 //               at distinct thresholds, compacted with a single-pass (look-back) scan         [_binary_clf_curve]
+//               (warp-striped layout: ballot + popc scans, coalesced loads and stores; 4 likewise)
 //   4 corners   drop_intermediate: keep points whose 2nd difference of fps or tps is non-zero [roc_curve]
 //   5 terms     fpr = fps/fps[-1], tpr = tps/tps[-1]; term_i = (fpr[i+1]-fpr[i]) * (tpr[i+1]+tpr[i]) / 2.0
 //   6 leaves    numpy pairwise-sum leaves (<=128 terms: 8 strided accumulators)              [np.trapezoid -> sum]
-//   7 tree      numpy pairwise-sum internal nodes (split at n/2 rounded down to a multiple of 8)
+//   7 tree      numpy pairwise-sum internal nodes (split at n/2 rounded down to a multiple of 8), top levels in shared
+//               memory; the last launch also writes the counts / status words (info_out)
 // The float64 summation ORDER is what makes the result bit-identical to sklearn; see oracle/auc.py.
 #include <cooperative_groups.h>
 
@@ -778,7 +781,7 @@ auc_prc_terms_kernel(const uint32_t* __restrict__ d_tps, const uint32_t* __restr
 
 // ------------------------------------------------------------------------------------------ single-launch path
 // The reference evaluates the AUC on 3 000 - 10 000 scores per class and epoch (ad_trainer.py:452-455, 516-522): there the
-// multi-kernel pipeline above is pure launch latency (11+ launches, ~0.1 ms).  For n <= kSmallMax the whole computation
+// multi-kernel pipeline above is pure launch latency (10+ launches, ~0.1 ms).  For n <= kSmallMax the whole computation
 // runs in ONE launch of ONE CTA with everything but the fp64 terms in shared memory: keys and label bits, 4 (or fewer)
 // LSD radix passes, the tie / corner scans, then the fp64 terms and numpy's pairwise tree, phase after phase behind
 // __syncthreads().  Every arithmetic step is the one of the multi-kernel path (same __d*_rn sequence, same tree), so the
@@ -1149,7 +1152,7 @@ constexpr int kClusterMax = kClusterCtas * kSmallMax;
 // measured cross-overs (tools/microbench_latency.py, profiles/r2_latency_reference_sizes.jsonl; device time per call):
 // one CTA wins up to ~12 k scores (20 us at 3 000, 42 us at 10 000 -- the cluster's DSMEM scatter and its ~20 cluster
 // barriers cost what its 8 SMs save), the cluster between 12 k and 48 k (50 vs 61 us at 16 384; 73 us at 32 768 against
-// 78 us device / 115 us per call for the 11 launches of the tiled pipeline), the tiled pipeline above
+// 78 us device / 115 us per call for the then 11 launches of the tiled pipeline), the tiled pipeline above
 constexpr int kSingleCtaBelow = 12288;
 constexpr int kClusterUseMax = 49152;
 
