@@ -49,6 +49,37 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = EOE_AUC_SCAN_ITEMS;
 constexpr int kScanTile = kScanThreads * kScanItems;   // 2048
 constexpr uint32_t kFlagAgg = 1u, kFlagIncl = 2u;
+
+// Programmatic dependent launch between the kernels of the tiled pipeline: every kernel lets its successor be scheduled at
+// once (its blocks become resident as slots free up) and itself waits, before touching anything, until its predecessor
+// has completed and its writes are visible -- the ~2 us of launch latency and block scheduling per boundary overlap the
+// predecessor's tail.  Completion is transitive (a kernel cannot finish before its predecessor did), so data produced
+// several kernels back is covered as well.  Both instructions are no-ops in a launch without the attribute.
+#ifndef EOE_AUC_PDL
+#define EOE_AUC_PDL 1
+#endif
+__device__ __forceinline__ void pdl_enter() {
+#if EOE_AUC_PDL
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dependent(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = EOE_AUC_PDL ? 1 : 0;
+    const cudaError_t r = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    if (r != cudaSuccess) set_cuda_error(r, "auc pipeline (dependent launch)");
+    return r;
+}
 constexpr int kSpinLimit = 1 << 20;                     // bounded spins: a protocol bug must not hang the GPU
 
 struct AucControl {            // zeroed by one memset per call
@@ -141,6 +172,7 @@ template <typename T>
 __global__ void __launch_bounds__(kKeysThreads)
 auc_keys_kernel(const T* __restrict__ scores, const int64_t* __restrict__ labels, int64_t n, int flags,
                 uint32_t* __restrict__ keys, uint8_t* __restrict__ labs, AucControl* c) {
+    pdl_enter();
     __shared__ uint32_t s_hist[4 * 256];
     __shared__ unsigned int s_cnt[3];
     for (int i = threadIdx.x; i < 1024; i += kKeysThreads) s_hist[i] = 0;
@@ -246,6 +278,7 @@ __global__ void __launch_bounds__(kSortThreads)
 auc_sort_pass_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                      uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int64_t n, int pass,
                      AucControl* c, uint32_t* status /* [tiles][256] for this pass */) {
+    pdl_enter();
     __shared__ uint32_t s_warp_hist[8][256];
     __shared__ uint32_t s_base[256];
     __shared__ uint32_t s_tmp[8];
@@ -454,6 +487,7 @@ __global__ void __launch_bounds__(kScanThreads)
 auc_distinct_kernel(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ labs, AucControl* c,
                     unsigned long long* status, uint32_t* __restrict__ d_tps, uint32_t* __restrict__ d_fps,
                     uint32_t* __restrict__ d_key) {
+    pdl_enter();
     __shared__ uint32_t s_w[2][8];
     __shared__ uint32_t s_excl[2];
     __shared__ unsigned int s_tile;
@@ -520,6 +554,7 @@ __global__ void __launch_bounds__(kScanThreads)
 auc_corner_kernel(const uint32_t* __restrict__ d_tps, const uint32_t* __restrict__ d_fps,
                   const uint32_t* __restrict__ d_key, AucControl* c, unsigned long long* status,
                   uint32_t* __restrict__ k_tps, uint32_t* __restrict__ k_fps, float* __restrict__ thr_out) {
+    pdl_enter();
     __shared__ uint32_t s_w[2][8];
     __shared__ uint32_t s_excl;
     __shared__ unsigned int s_tile;
@@ -593,6 +628,7 @@ auc_corner_kernel(const uint32_t* __restrict__ d_tps, const uint32_t* __restrict
 __global__ void __launch_bounds__(256)
 auc_terms_kernel(const uint32_t* __restrict__ k_tps, const uint32_t* __restrict__ k_fps, AucControl* c,
                  double* __restrict__ terms, double* __restrict__ fpr_out, double* __restrict__ tpr_out) {
+    pdl_enter();
     const int64_t P = (int64_t)c->n_kept + 1;        // points incl. origin
     const double ftot = (double)(c->n_valid - c->n_pos);
     const double ttot = (double)c->n_pos;
@@ -660,6 +696,7 @@ __device__ __forceinline__ void pairwise_leaf_slot(const double* a, int64_t T, i
 __global__ void __launch_bounds__(256)
 pairwise_leaves_kernel(const double* __restrict__ a, const unsigned long long* n_ptr, int64_t n_minus,
                        double* __restrict__ nodes) {
+    pdl_enter();
     const int64_t T = (int64_t)(*n_ptr) - n_minus;   // number of terms
     if (T <= 0) { if (blockIdx.x == 0 && threadIdx.x == 0) nodes[1] = 0.0; return; }
     const int D = dev_pairwise_depth(T);
@@ -699,6 +736,7 @@ constexpr int kTreeSmemDepth = 13;              // 2 << 13 doubles (128 KB) + 1 
 __global__ void __launch_bounds__(1024)
 pairwise_tree_kernel(const unsigned long long* n_ptr, int64_t n_minus, double* __restrict__ nodes, AucControl* c,
                      double* __restrict__ out, int negate_clip, int64_t* info /* last launch of a call: counts + status */) {
+    pdl_enter();
     extern __shared__ double s_nodes[];
     const int64_t T = (int64_t)(*n_ptr) - n_minus;
     const int D = (T > 0) ? dev_pairwise_depth(T) : 0;
@@ -760,6 +798,7 @@ __global__ void __launch_bounds__(256)
 auc_prc_terms_kernel(const uint32_t* __restrict__ d_tps, const uint32_t* __restrict__ d_fps,
                      const uint32_t* __restrict__ d_key, AucControl* c, double* __restrict__ terms,
                      double* __restrict__ prec_out, double* __restrict__ rec_out, float* __restrict__ pthr_out) {
+    pdl_enter();
     const int64_t m = (int64_t)c->n_distinct;
     const double ttot = (double)c->n_pos;
     auto prec = [&](int64_t j) {
@@ -1554,12 +1593,13 @@ static int auc_run(const void* scores, const int64_t* labels, int64_t n, int fla
     if (kgrid > kNumSMs * 8) kgrid = kNumSMs * 8;
 #endif
     auc_keys_kernel<T><<<kgrid, kKeysThreads, 0, st>>>((const T*)scores, labels, n, flags, keys_a, labs_a, c);
+    cudaError_t launch_err = cudaSuccess;
+#define AUC_LAUNCH(...) do { if (launch_err == cudaSuccess) launch_err = launch_dependent(__VA_ARGS__); } while (0)
     for (int pass = 0; pass < 4; ++pass) {
         const bool fwd = (pass & 1) == 0;
         auto sort_pass = sort_items_for(n) == 8 ? auc_sort_pass_kernel<8> : auc_sort_pass_kernel<16>;
-        sort_pass<<<L.sort_tiles, kSortThreads, 0, st>>>(
-            fwd ? keys_a : keys_b, fwd ? labs_a : labs_b, fwd ? keys_b : keys_a, fwd ? labs_b : labs_a, n, pass, c,
-            sort_status + (size_t)pass * L.sort_tiles * 256);
+        AUC_LAUNCH(sort_pass, L.sort_tiles, kSortThreads, 0, st, fwd ? keys_a : keys_b, fwd ? labs_a : labs_b,
+                   fwd ? keys_b : keys_a, fwd ? labs_b : labs_a, n, pass, c, sort_status + (size_t)pass * L.sort_tiles * 256);
     }
     // sorted data is back in (keys_a, labs_a); keys_b is free and receives the distinct thresholds
     uint32_t* d_tps = (uint32_t*)(ws + L.d_tps);
@@ -1568,13 +1608,13 @@ static int auc_run(const void* scores, const int64_t* labels, int64_t n, int fla
     uint32_t* k_fps = (uint32_t*)(ws + L.k_fps);
     double* terms = (double*)(ws + L.terms);
     double* nodes = (double*)(ws + L.nodes);
-    auc_distinct_kernel<<<L.scan_tiles, kScanThreads, 0, st>>>(keys_a, labs_a, c, (unsigned long long*)(ws + L.scan1_status),
-                                                               d_tps, d_fps, keys_b);
-    auc_corner_kernel<<<L.scan_tiles, kScanThreads, 0, st>>>(d_tps, d_fps, keys_b, c,
-                                                             (unsigned long long*)(ws + L.scan2_status), k_tps, k_fps, thr_out);
+    AUC_LAUNCH(auc_distinct_kernel, L.scan_tiles, kScanThreads, 0, st, keys_a, labs_a, c,
+               (unsigned long long*)(ws + L.scan1_status), d_tps, d_fps, keys_b);
+    AUC_LAUNCH(auc_corner_kernel, L.scan_tiles, kScanThreads, 0, st, d_tps, d_fps, keys_b, c,
+               (unsigned long long*)(ws + L.scan2_status), k_tps, k_fps, thr_out);
     int tgrid = (int)((n + 1 + 255) / 256);
     if (tgrid > kNumSMs * 4) tgrid = kNumSMs * 4;
-    auc_terms_kernel<<<tgrid, 256, 0, st>>>(k_tps, k_fps, c, terms, fpr_out, tpr_out);
+    AUC_LAUNCH(auc_terms_kernel, tgrid, 256, 0, st, k_tps, k_fps, c, terms, fpr_out, tpr_out);
     const int lgrid = (int)((((int64_t)8 << L.max_depth) + 255) / 256);
     const int tdepth = L.max_depth < kTreeSmemDepth ? L.max_depth : kTreeSmemDepth;
     const size_t tree_smem = ((size_t)2 << tdepth) * sizeof(double) + ((size_t)1 << tdepth) * sizeof(uint32_t);
@@ -1583,14 +1623,19 @@ static int auc_run(const void* scores, const int64_t* labels, int64_t n, int fla
                                  (int)(((size_t)2 << kTreeSmemDepth) * sizeof(double) + ((size_t)1 << kTreeSmemDepth) * sizeof(uint32_t)));
         if (e != cudaSuccess) { set_cuda_error(e, "pairwise_tree smem attr"); return EOE_ERR_CUDA; }
     }
-    pairwise_leaves_kernel<<<lgrid, 256, 0, st>>>(terms, &c->n_kept, 0, nodes);
+    const unsigned long long* n_kept = &c->n_kept;
+    const unsigned long long* n_distinct = &c->n_distinct;
+    AUC_LAUNCH(pairwise_leaves_kernel, lgrid, 256, 0, st, terms, n_kept, (int64_t)0, nodes);
     const bool prc = (flags & EOE_AUC_WITH_PRC) != 0;
-    pairwise_tree_kernel<<<1, 1024, tree_smem, st>>>(&c->n_kept, 0, nodes, c, auc_out, 0, prc ? nullptr : info_out);
-    if (flags & EOE_AUC_WITH_PRC) {
-        auc_prc_terms_kernel<<<tgrid, 256, 0, st>>>(d_tps, d_fps, keys_b, c, terms, prec_out, rec_out, pthr_out);
-        pairwise_leaves_kernel<<<lgrid, 256, 0, st>>>(terms, &c->n_distinct, 0, nodes);
-        pairwise_tree_kernel<<<1, 1024, tree_smem, st>>>(&c->n_distinct, 0, nodes, c, auc_out + 1, 1, info_out);
+    AUC_LAUNCH(pairwise_tree_kernel, 1, 1024, tree_smem, st, n_kept, (int64_t)0, nodes, c, auc_out, 0,
+               prc ? (int64_t*)nullptr : info_out);
+    if (prc) {
+        AUC_LAUNCH(auc_prc_terms_kernel, tgrid, 256, 0, st, d_tps, d_fps, keys_b, c, terms, prec_out, rec_out, pthr_out);
+        AUC_LAUNCH(pairwise_leaves_kernel, lgrid, 256, 0, st, terms, n_distinct, (int64_t)0, nodes);
+        AUC_LAUNCH(pairwise_tree_kernel, 1, 1024, tree_smem, st, n_distinct, (int64_t)0, nodes, c, auc_out + 1, 1, info_out);
     }
+#undef AUC_LAUNCH
+    if (launch_err != cudaSuccess) return EOE_ERR_CUDA;
     return check_launch("auc pipeline", 10 + (prc ? 3 : 0));
 }
 
