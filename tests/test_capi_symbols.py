@@ -57,6 +57,25 @@ def test_auc_workspace_bytes_is_monotone():
     assert all(b >= a for a, b in zip(sizes, sizes[1:])), [(n, a, b) for n, a, b in zip(ns[1:], sizes, sizes[1:]) if b < a][:3]
 
 
+def test_committed_gemm_capture_names_its_sources():
+    """profiles/gemm_traffic.json (the ncu DRAM-traffic figure bench.py quotes in `roofline.traffic`) is keyed on the build
+    it was captured on and on `gemm_source_id`, the hash of the sources the GEMM / attention kernels are compiled from;
+    bench.py quotes it only if one of the two matches the loaded library.  A capture that no longer matches the tree is
+    reported here (skip, not failure: re-capture with tools/run_profile_r2.sh on a GPU box)."""
+    import json
+    import os
+    from eoe_b200 import build as b
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "gemm_traffic.json")
+    tj = json.load(open(path))
+    assert set(tj) >= {"build_id", "gemm_source_id", "batch", "by_dtype"}
+    for ent in tj["by_dtype"].values():
+        assert ent["dram_bytes_per_launch"] > 0 and ent["algorithmic_bytes_per_launch"] > 0
+    assert len(b.gemm_source_id()) == 16 and b.gemm_source_id() != b.source_id()
+    if tj["gemm_source_id"] != b.gemm_source_id() and tj["build_id"] != b.source_id():
+        pytest.skip(f"profiles/gemm_traffic.json was captured on other GEMM sources ({tj['gemm_source_id']}) than the tree's "
+                    f"({b.gemm_source_id()}): bench.py will print roofline.traffic = null until it is re-captured")
+
+
 def test_argument_validation_without_gpu(lib):
     """Entry points reject bad arguments before touching the device."""
     lib.eoe_hsc_score.restype = ctypes.c_int
