@@ -101,6 +101,42 @@ def test_auc_sort_tile_switch_and_grown_workspace():
     assert ws.n == 700_001
 
 
+@pytest.mark.parametrize("n", [10_000, 200_000, 1_000_000])
+def test_auc_replays_from_a_cuda_graph(n):
+    """The whole call -- one launch (n = 10 000), or the memset + ten kernels of the tiled pipeline chained by programmatic
+    dependent launch -- is captured once and replayed on new scores: bit-identical to sklearn every time (the dependent-launch
+    edges must survive capture, and the workspace must carry no state from one replay to the next)."""
+    from sklearn.metrics import roc_auc_score
+    from eoe_b200 import metrics
+    rng = np.random.default_rng(n)
+    s_static = torch.empty(n, dtype=torch.float32, device=DEV)
+    y_static = torch.empty(n, dtype=torch.int64, device=DEV)
+    ws = metrics.AucWorkspace()
+
+    def fresh():
+        s = (1 - np.exp(-np.abs(rng.standard_normal(n)))).astype(np.float32)
+        y = (rng.random(n) < 0.35).astype(np.int64)
+        s_static.copy_(torch.from_numpy(s))
+        y_static.copy_(torch.from_numpy(y))
+        return s, y
+
+    fresh()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        metrics.roc_auc_device(s_static, y_static, workspace=ws)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out, info, _ = metrics.roc_auc_device(s_static, y_static, workspace=ws)
+    for _ in range(3):
+        s, y = fresh()
+        g.replay()
+        torch.cuda.synchronize()
+        assert int(info[4].item()) == 0
+        assert out[0].item() == roc_auc_score(y, s)
+
+
 def test_auc_ignore_negative_labels_and_errors():
     from eoe_b200 import metrics
     rng = np.random.default_rng(4)
